@@ -1,0 +1,393 @@
+// oracle/ref_capi.cc — TEST INFRASTRUCTURE ONLY (never linked into or called by the product path).
+//
+// A C ABI over the UNMODIFIED reference library (google/s2geometry sources compiled in place from
+// /root/reference/src against oracle/absl_shim). It is the "reference" oracle the GPU path is checked
+// against and the multithreaded CPU baseline bench.py times (cpu_baseline.kind = "reference").
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
+//
+// Every function calls the reference's own public API for the path:
+//   S2CellId(S2Point)/S2CellId(S2LatLng)      s2cell_id.cc:309-317
+//   S2ContainsPointQuery                      s2contains_point_query.h:255-389
+//   MutableS2ShapeIndex                       mutable_s2shape_index.h
+//   s2pred::Sign / S2::CrossingSign / ...     s2predicates.h, s2edge_crossings.h
+//   S2CellUnion::Contains, S2RegionCoverer    s2cell_union.cc:564, s2region_coverer.h
+
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#include "s2/mutable_s2shape_index.h"
+#include "s2/s1angle.h"
+#include "s2/s2cap.h"
+#include "s2/s2cell_id.h"
+#include "s2/s2cell_union.h"
+#include "s2/s2contains_point_query.h"
+#include "s2/s2edge_crosser.h"
+#include "s2/s2edge_crossings.h"
+#include "s2/s2latlng.h"
+#include "s2/s2point.h"
+#include "s2/s2pointutil.h"
+#include "s2/s2predicates.h"
+#include "s2/s2predicates_internal.h"
+#include "s2/s2region_coverer.h"
+#include "s2/s2shape.h"
+#include "s2/s2shapeutil_contains_brute_force.h"
+#include "s2/s2shapeutil_get_reference_point.h"
+
+namespace {
+
+// Geometry enters through the reference's own plugin interface (S2Shape, s2shape.h:64-260): a shape is
+// a list of vertex chains; dimension 2 chains are closed loops (S2LaxPolygonShape semantics), dimension 1
+// chains are polylines (S2LaxPolylineShape), dimension 0 vertices are degenerate edges (S2PointVectorShape).
+class SoupShape : public S2Shape {
+ public:
+  SoupShape(int dim, std::vector<std::vector<S2Point>> chains) : dim_(dim), chains_(std::move(chains)) {
+    int start = 0;
+    for (const auto& c : chains_) {
+      int n = (int)c.size();
+      int ne = dim_ == 2 ? n : (dim_ == 1 ? std::max(0, n - 1) : n);
+      starts_.push_back(start);
+      start += ne;
+    }
+    starts_.push_back(start);
+  }
+  int num_edges() const override { return starts_.back(); }
+  Edge edge(int e) const override {
+    int c = (int)(std::upper_bound(starts_.begin(), starts_.end(), e) - starts_.begin()) - 1;
+    return chain_edge(c, e - starts_[c]);
+  }
+  int dimension() const override { return dim_; }
+  ReferencePoint GetReferencePoint() const override {
+    if (dim_ < 2) return ReferencePoint::Contained(false);
+    return s2shapeutil::GetReferencePoint(*this);
+  }
+  int num_chains() const override { return (int)chains_.size(); }
+  Chain chain(int i) const override { return Chain(starts_[i], starts_[i + 1] - starts_[i]); }
+  Edge chain_edge(int i, int j) const override {
+    const auto& c = chains_[i];
+    if (dim_ == 0) return Edge(c[j], c[j]);
+    int k = j + 1;
+    if (dim_ == 2 && k == (int)c.size()) k = 0;
+    return Edge(c[j], c[k]);
+  }
+  ChainPosition chain_position(int e) const override {
+    int c = (int)(std::upper_bound(starts_.begin(), starts_.end(), e) - starts_.begin()) - 1;
+    return ChainPosition(c, e - starts_[c]);
+  }
+
+ private:
+  int dim_;
+  std::vector<std::vector<S2Point>> chains_;
+  std::vector<int> starts_;
+};
+
+struct RefIndex {
+  MutableS2ShapeIndex index;
+  explicit RefIndex(const MutableS2ShapeIndex::Options& o) : index(o) {}
+};
+
+inline S2Point P(const double* p) { return S2Point(p[0], p[1], p[2]); }
+
+template <class F>
+void ParallelFor(size_t n, int threads, F f) {
+  if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+  if (threads < 1) threads = 1;
+  if (threads == 1 || n < 1024) { f(0, n, 0); return; }
+  std::vector<std::thread> pool;
+  size_t chunk = (n + threads - 1) / threads;
+  for (int t = 0; t < threads; ++t) {
+    size_t b = std::min(n, (size_t)t * chunk), e = std::min(n, b + chunk);
+    if (b < e) pool.emplace_back([=] { f(b, e, t); });
+  }
+  for (auto& th : pool) th.join();
+}
+
+S2VertexModel Model(int m) { return m == 0 ? S2VertexModel::OPEN : (m == 1 ? S2VertexModel::SEMI_OPEN : S2VertexModel::CLOSED); }
+
+}  // namespace
+
+extern "C" {
+
+int ref_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
+
+// ---------------------------------------------------------------- cell ids
+void ref_encode_points(const double* xyz, size_t n, int level, uint64_t* out, int threads) {
+  ParallelFor(n, threads, [=](size_t b, size_t e, int) {
+    for (size_t i = b; i < e; ++i) {
+      S2CellId id(P(xyz + 3 * i));
+      out[i] = (level >= 30 ? id : id.parent(level)).id();
+    }
+  });
+}
+
+void ref_encode_latlng(const double* latlng_rad, size_t n, int level, uint64_t* out, int threads) {
+  ParallelFor(n, threads, [=](size_t b, size_t e, int) {
+    for (size_t i = b; i < e; ++i) {
+      S2CellId id(S2LatLng::FromRadians(latlng_rad[2 * i], latlng_rad[2 * i + 1]));
+      out[i] = (level >= 30 ? id : id.parent(level)).id();
+    }
+  });
+}
+
+void ref_encode_latlng_deg(const double* latlng_deg, size_t n, int level, uint64_t* out, int threads) {
+  ParallelFor(n, threads, [=](size_t b, size_t e, int) {
+    for (size_t i = b; i < e; ++i) {
+      S2CellId id(S2LatLng::FromDegrees(latlng_deg[2 * i], latlng_deg[2 * i + 1]));
+      out[i] = (level >= 30 ? id : id.parent(level)).id();
+    }
+  });
+}
+
+void ref_encode_latlng_e7(const int32_t* latlng_e7, size_t n, int level, uint64_t* out, int threads) {
+  ParallelFor(n, threads, [=](size_t b, size_t e, int) {
+    for (size_t i = b; i < e; ++i) {
+      S2CellId id(S2LatLng::FromE7(latlng_e7[2 * i], latlng_e7[2 * i + 1]));
+      out[i] = (level >= 30 ? id : id.parent(level)).id();
+    }
+  });
+}
+
+// S2LatLng::ToPoint only (the libm-dependent front end), for diagnosing lat/lng parity.
+void ref_latlng_to_point(const double* latlng_rad, size_t n, double* xyz) {
+  for (size_t i = 0; i < n; ++i) {
+    S2Point p = S2LatLng::FromRadians(latlng_rad[2 * i], latlng_rad[2 * i + 1]).ToPoint();
+    xyz[3 * i] = p[0]; xyz[3 * i + 1] = p[1]; xyz[3 * i + 2] = p[2];
+  }
+}
+
+void ref_cellid_parent(const uint64_t* ids, size_t n, int level, uint64_t* out) {
+  for (size_t i = 0; i < n; ++i) out[i] = S2CellId(ids[i]).parent(level).id();
+}
+
+void ref_cellid_level(const uint64_t* ids, size_t n, int32_t* out) {
+  for (size_t i = 0; i < n; ++i) out[i] = S2CellId(ids[i]).level();
+}
+
+void ref_cellid_range(const uint64_t* ids, size_t n, uint64_t* rmin, uint64_t* rmax) {
+  for (size_t i = 0; i < n; ++i) { rmin[i] = S2CellId(ids[i]).range_min().id(); rmax[i] = S2CellId(ids[i]).range_max().id(); }
+}
+
+// tokens: 16 bytes per id, NUL padded; len_out = strlen.
+void ref_cellid_to_token(const uint64_t* ids, size_t n, char* tokens16, uint8_t* len_out, int threads) {
+  ParallelFor(n, threads, [=](size_t b, size_t e, int) {
+    for (size_t i = b; i < e; ++i) {
+      std::string t = S2CellId(ids[i]).ToToken();
+      std::memset(tokens16 + 16 * i, 0, 16);
+      std::memcpy(tokens16 + 16 * i, t.data(), std::min<size_t>(16, t.size()));
+      if (len_out) len_out[i] = (uint8_t)t.size();
+    }
+  });
+}
+
+void ref_cellid_from_token(const char* tokens16, const uint8_t* len, size_t n, uint64_t* out) {
+  for (size_t i = 0; i < n; ++i) out[i] = S2CellId::FromToken(absl::string_view(tokens16 + 16 * i, len[i])).id();
+}
+
+void ref_cellid_to_point(const uint64_t* ids, size_t n, double* xyz) {
+  for (size_t i = 0; i < n; ++i) {
+    S2Point p = S2CellId(ids[i]).ToPoint();
+    xyz[3 * i] = p[0]; xyz[3 * i + 1] = p[1]; xyz[3 * i + 2] = p[2];
+  }
+}
+
+uint64_t ref_cellid_from_face_pos_level(int face, uint64_t pos, int level) { return S2CellId::FromFacePosLevel(face, pos, level).id(); }
+
+// ---------------------------------------------------------------- predicates (unit-test hooks)
+// kind: 0 s2pred::Sign, 1 TriageSign, 2 StableSign, 3 ExactSign(perturb=true), 4 ExpensiveSign, 5 ExactSign(perturb=false)
+void ref_sign(const double* abc, size_t n, int kind, int8_t* out) {
+  for (size_t i = 0; i < n; ++i) {
+    S2Point a = P(abc + 9 * i), b = P(abc + 9 * i + 3), c = P(abc + 9 * i + 6);
+    int s;
+    switch (kind) {
+      case 1: s = s2pred::TriageSign(a, b, c, a.CrossProd(b)); break;
+      case 2: s = s2pred::StableSign(a, b, c); break;
+      case 3: s = s2pred::ExactSign(a, b, c, true); break;
+      case 4: s = s2pred::ExpensiveSign(a, b, c); break;
+      case 5: s = s2pred::ExactSign(a, b, c, false); break;
+      default: s = s2pred::Sign(a, b, c);
+    }
+    out[i] = (int8_t)s;
+  }
+}
+
+// kind: 0 S2::CrossingSign (fresh S2EdgeCrosser), 1 S2CopyingEdgeCrosser, 2 VertexCrossing, 3 EdgeOrVertexCrossing
+void ref_crossing(const double* abcd, size_t n, int kind, int8_t* out) {
+  for (size_t i = 0; i < n; ++i) {
+    S2Point a = P(abcd + 12 * i), b = P(abcd + 12 * i + 3), c = P(abcd + 12 * i + 6), d = P(abcd + 12 * i + 9);
+    int s;
+    switch (kind) {
+      case 1: { S2CopyingEdgeCrosser cr(a, b); s = cr.CrossingSign(c, d); break; }
+      case 2: s = S2::VertexCrossing(a, b, c, d); break;
+      case 3: s = S2::EdgeOrVertexCrossing(a, b, c, d); break;
+      default: s = S2::CrossingSign(a, b, c, d);
+    }
+    out[i] = (int8_t)s;
+  }
+}
+
+void ref_ortho(const double* a, size_t n, double* out) {
+  for (size_t i = 0; i < n; ++i) { S2Point o = S2::Ortho(P(a + 3 * i)); out[3 * i] = o[0]; out[3 * i + 1] = o[1]; out[3 * i + 2] = o[2]; }
+}
+
+// ---------------------------------------------------------------- index
+// Shape soup: shape s has dimension shape_dim[s] and chains [shape_chain_begin[s], shape_chain_begin[s+1]);
+// chain c has vertices [chain_vertex_begin[c], chain_vertex_begin[c+1]) of `vertices` (N×3 doubles).
+void* ref_index_create(int num_shapes, const int8_t* shape_dim, const uint32_t* shape_chain_begin,
+                       const uint32_t* chain_vertex_begin, const double* vertices, int max_edges_per_cell) {
+  MutableS2ShapeIndex::Options opt;
+  if (max_edges_per_cell > 0) opt.set_max_edges_per_cell(max_edges_per_cell);
+  auto* r = new RefIndex(opt);
+  for (int s = 0; s < num_shapes; ++s) {
+    std::vector<std::vector<S2Point>> chains;
+    for (uint32_t c = shape_chain_begin[s]; c < shape_chain_begin[s + 1]; ++c) {
+      std::vector<S2Point> v;
+      for (uint32_t k = chain_vertex_begin[c]; k < chain_vertex_begin[c + 1]; ++k) v.push_back(P(vertices + 3 * (size_t)k));
+      chains.push_back(std::move(v));
+    }
+    r->index.Add(std::make_unique<SoupShape>(shape_dim[s], std::move(chains)));
+  }
+  r->index.ForceBuild();
+  return r;
+}
+
+void ref_index_destroy(void* h) { delete (RefIndex*)h; }
+
+// Sizes of the flattened form: C cells, K clipped shapes, E clipped edges.
+void ref_index_flat_sizes(void* h, uint64_t* C, uint64_t* K, uint64_t* E) {
+  auto& index = ((RefIndex*)h)->index;
+  uint64_t c = 0, k = 0, e = 0;
+  for (MutableS2ShapeIndex::Iterator it(&index, S2ShapeIndex::BEGIN); !it.done(); it.Next()) {
+    ++c;
+    const S2ShapeIndexCell& cell = it.cell();
+    k += cell.num_clipped();
+    for (int i = 0; i < cell.num_clipped(); ++i) e += cell.clipped(i).num_edges();
+  }
+  *C = c; *K = k; *E = e;
+}
+
+// Walks the reference's public iteration API (s2shape_index.h:244-258) and writes the flat arrays.
+void ref_index_flatten(void* h, uint64_t* cell_ids, double* cell_center, uint32_t* cell_clip_begin,
+                       int32_t* clip_shape_id, uint8_t* clip_flags, uint32_t* clip_edge_begin,
+                       int32_t* edge_id, double* edge_v0, double* edge_v1) {
+  auto& index = ((RefIndex*)h)->index;
+  uint64_t c = 0, k = 0, e = 0;
+  for (MutableS2ShapeIndex::Iterator it(&index, S2ShapeIndex::BEGIN); !it.done(); it.Next()) {
+    cell_ids[c] = it.id().id();
+    S2Point ctr = it.id().ToPoint();
+    cell_center[3 * c] = ctr[0]; cell_center[3 * c + 1] = ctr[1]; cell_center[3 * c + 2] = ctr[2];
+    cell_clip_begin[c] = (uint32_t)k;
+    const S2ShapeIndexCell& cell = it.cell();
+    for (int i = 0; i < cell.num_clipped(); ++i) {
+      const S2ClippedShape& cl = cell.clipped(i);
+      const S2Shape* shape = index.shape(cl.shape_id());
+      clip_shape_id[k] = cl.shape_id();
+      clip_flags[k] = (uint8_t)((cl.contains_center() ? 1 : 0) | (shape->dimension() << 1));
+      clip_edge_begin[k] = (uint32_t)e;
+      for (int j = 0; j < cl.num_edges(); ++j) {
+        S2Shape::Edge ed = shape->edge(cl.edge(j));
+        if (edge_id) edge_id[e] = cl.edge(j);
+        for (int q = 0; q < 3; ++q) { edge_v0[3 * e + q] = ed.v0[q]; edge_v1[3 * e + q] = ed.v1[q]; }
+        ++e;
+      }
+      ++k;
+    }
+    ++c;
+  }
+  cell_clip_begin[c] = (uint32_t)k;
+  clip_edge_begin[k] = (uint32_t)e;
+}
+
+int ref_index_num_shape_ids(void* h) { return ((RefIndex*)h)->index.num_shape_ids(); }
+
+// S2ContainsPointQuery::Contains, one query object per thread (s2contains_point_query.h:86-91).
+void ref_contains(void* h, const double* xyz, size_t n, int vertex_model, uint8_t* out, int threads) {
+  auto* index = &((RefIndex*)h)->index;
+  ParallelFor(n, threads, [=](size_t b, size_t e, int) {
+    S2ContainsPointQuery<MutableS2ShapeIndex> q(index, Model(vertex_model));
+    for (size_t i = b; i < e; ++i) out[i] = q.Contains(P(xyz + 3 * i));
+  });
+}
+
+void ref_shape_contains(void* h, int shape_id, const double* xyz, size_t n, int vertex_model, uint8_t* out, int threads) {
+  auto* index = &((RefIndex*)h)->index;
+  ParallelFor(n, threads, [=](size_t b, size_t e, int) {
+    S2ContainsPointQuery<MutableS2ShapeIndex> q(index, Model(vertex_model));
+    for (size_t i = b; i < e; ++i) out[i] = q.ShapeContains(shape_id, P(xyz + 3 * i));
+  });
+}
+
+// Spatial join: counts[s] += 1 for every point contained by shape s (VisitContainingShapeIds).
+void ref_shape_histogram(void* h, const double* xyz, size_t n, int vertex_model, uint64_t* counts, int threads) {
+  auto* index = &((RefIndex*)h)->index;
+  int S = index->num_shape_ids();
+  if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+  std::vector<std::vector<uint64_t>> local(threads, std::vector<uint64_t>(S, 0));
+  ParallelFor(n, threads, [&](size_t b, size_t e, int t) {
+    S2ContainsPointQuery<MutableS2ShapeIndex> q(index, Model(vertex_model));
+    uint64_t* cnt = local[t].data();
+    for (size_t i = b; i < e; ++i) q.VisitContainingShapeIds(P(xyz + 3 * i), [cnt](int id) { ++cnt[id]; return true; });
+  });
+  for (int s = 0; s < S; ++s) { uint64_t v = 0; for (auto& l : local) v += l[s]; counts[s] = v; }
+}
+
+// GetContainingShapeIds: offsets[n+1] and ascending shape ids per point (capacity-limited). Returns total count.
+uint64_t ref_containing_shapes(void* h, const double* xyz, size_t n, int vertex_model, uint32_t* offsets, int32_t* ids, uint64_t capacity) {
+  auto* index = &((RefIndex*)h)->index;
+  S2ContainsPointQuery<MutableS2ShapeIndex> q(index, Model(vertex_model));
+  uint64_t total = 0;
+  for (size_t i = 0; i < n; ++i) {
+    offsets[i] = (uint32_t)total;
+    for (int id : q.GetContainingShapeIds(P(xyz + 3 * i))) { if (total < capacity) ids[total] = id; ++total; }
+  }
+  offsets[n] = (uint32_t)total;
+  return total;
+}
+
+// Ground truth of the reference's own tests: s2shapeutil::ContainsBruteForce (SEMI_OPEN).
+void ref_brute_force_contains(void* h, int shape_id, const double* xyz, size_t n, uint8_t* out, int threads) {
+  auto* index = &((RefIndex*)h)->index;
+  const S2Shape* shape = index->shape(shape_id);
+  ParallelFor(n, threads, [=](size_t b, size_t e, int) {
+    for (size_t i = b; i < e; ++i) out[i] = s2shapeutil::ContainsBruteForce(*shape, P(xyz + 3 * i));
+  });
+}
+
+// ---------------------------------------------------------------- cell unions
+void ref_cellunion_contains(const uint64_t* ids, size_t m, const double* xyz, size_t n, uint8_t* out, int threads) {
+  std::vector<S2CellId> v(m);
+  for (size_t i = 0; i < m; ++i) v[i] = S2CellId(ids[i]);
+  S2CellUnion u = S2CellUnion::FromVerbatim(std::move(v));
+  const S2CellUnion* up = &u;
+  ParallelFor(n, threads, [=](size_t b, size_t e, int) {
+    for (size_t i = b; i < e; ++i) out[i] = up->Contains(P(xyz + 3 * i));
+  });
+}
+
+// S2CellUnion normalisation (sort + merge) of arbitrary ids; returns count written.
+size_t ref_cellunion_normalize(const uint64_t* ids, size_t m, uint64_t* out) {
+  std::vector<S2CellId> v(m);
+  for (size_t i = 0; i < m; ++i) v[i] = S2CellId(ids[i]);
+  S2CellUnion u(std::move(v));
+  for (size_t i = 0; i < u.cell_ids().size(); ++i) out[i] = u.cell_ids()[i].id();
+  return u.cell_ids().size();
+}
+
+// S2RegionCoverer covering of a cap (centre, radius in radians); returns number of cells (≤ capacity written).
+size_t ref_cover_cap(const double* center, double radius_rad, int max_cells, int min_level, int max_level,
+                     uint64_t* out, size_t capacity) {
+  S2RegionCoverer::Options opt;
+  opt.set_max_cells(max_cells);
+  if (min_level >= 0) opt.set_min_level(min_level);
+  if (max_level >= 0) opt.set_max_level(max_level);
+  S2RegionCoverer coverer(opt);
+  S2Cap cap(P(center).Normalize(), S1Angle::Radians(radius_rad));
+  S2CellUnion u = coverer.GetCovering(cap);
+  size_t k = 0;
+  for (S2CellId id : u.cell_ids()) { if (k < capacity) out[k] = id.id(); ++k; }
+  return k;
+}
+
+}  // extern "C"
