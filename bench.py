@@ -1,0 +1,277 @@
+#!/usr/bin/env python3
+"""bench.py — points/sec of the S2 hot path on B200 (BASELINE.json metric), one JSON line on rank 0.
+
+Headline workload (BASELINE.json configs[1]): 100M (lat,lng) pairs per GPU -> S2CellId at levels 12/20/30 plus
+ToToken of the level-30 id — S2CellId(S2LatLng), parent(12), parent(20), ToToken() per point — ONE fused kernel launch
+per step (s2b_encode_latlng_levels_tokens_dev).
+
+  value   : whole-job points/s with inputs resident in HBM (CUDA events on the launching stream, max over ranks)
+  e2e     : same metric through the host-pointer C ABI call with pinned host buffers (H2D + kernel + D2H inside)
+  roofline: the encode kernel against the measured HBM peak (algorithmic bytes/pt: 16 in + 3x8 ids + 16 token + 1 len = 57);
+            "fp64" gives the second roofline the north star asks for (measured DFMA peak vs FP64 instructions/pt).
+  cpu_baseline / --impl reference: the UNMODIFIED reference (oracle/_ref/libs2ref.so) on the box's host cores.
+
+Multi-GPU (torchrun, one rank per GPU): points are independent, each rank encodes its own 100M (weak scaling), no
+data-path collective; NCCL is used only for the barrier and the max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+LEVELS = [12, 20, 30]
+TOKEN_LEVEL_INDEX = 2
+N_POINTS = 100_000_000
+BYTES_PER_POINT = 16 + 8 * len(LEVELS) + 16 + 1   # algorithmic HBM bytes per point of the fused kernel
+# FP64-pipe instructions per point on the common path, counted in the SASS of encode_kernel<1>;
+# used only for the informational fp64 roofline.
+FP64_INSTR_PER_POINT = 330
+METRIC = "points/sec (S2CellId encode, lat/lng -> levels 12/20/30 + ToToken)"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        # "under load" = upper half of samples
+        sm_sorted = sorted(sm)
+        return {"sm_mhz": float(np.median(sm_sorted[len(sm_sorted) // 2:])), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the step on this box's host cores, on a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import reflib  # the one place bench.py may execute oracle/ besides cpu_baseline
+    from s2geometry_b200 import synth
+    ref = reflib.load()
+    threads = ref.hardware_threads()
+    sample = 20_000_000
+    ll = synth.sphere_latlng(sample, 2)
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        ref.encode_latlng_levels_tokens(ll, LEVELS, TOKEN_LEVEL_INDEX, threads)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = sample / (ms * 1e-3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: lat/lng -> S2CellId levels 12/20/30 + ToToken(level 30)", "points_per_step": sample,
+                   "note": "bounded sample of the 100M-point workload; unmodified reference sources + abseil stand-in, -O2"},
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": threads, "kind": "reference",
+                         "sample": "%d of 100M lat/lng points per step, %d threads" % (sample, threads)},
+        "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def cpu_baseline():
+    from oracle import reflib  # cpu_baseline leg
+    from s2geometry_b200 import synth
+    ref = reflib.load()
+    threads = ref.hardware_threads()
+    probe = synth.sphere_latlng(2_000_000, 2)
+    t0 = time.perf_counter()
+    ref.encode_latlng_levels_tokens(probe, LEVELS, TOKEN_LEVEL_INDEX, threads)
+    rate = len(probe) / (time.perf_counter() - t0)
+    sample = int(min(N_POINTS, max(4_000_000, rate * 4)))   # ~4 s per pass, 3 passes
+    ll = synth.sphere_latlng(sample, 2)
+    best = 1e30
+    for _ in range(3):
+        t0 = time.perf_counter()
+        ref.encode_latlng_levels_tokens(ll, LEVELS, TOKEN_LEVEL_INDEX, threads)
+        best = min(best, time.perf_counter() - t0)
+    return {"value": sample / best, "unit": "points/s", "cores": threads, "kind": "reference",
+            "sample": "%d of 100M lat/lng points, best of 3, %d threads (reference sources + abseil stand-in)" % (sample, threads)}
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from s2geometry_b200 import _lib, cellid, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    n = args.points
+    ll = synth.sphere_latlng_cuda(n, 2 + rank, dev)
+    ids = torch.empty((len(LEVELS), n), dtype=torch.int64, device=dev)
+    tok = torch.empty((n, 16), dtype=torch.uint8, device=dev)
+    ln = torch.empty(n, dtype=torch.uint8, device=dev)
+
+    def step():
+        cellid.from_lat_lng_levels_tokens(ll, LEVELS, TOKEN_LEVEL_INDEX, out_ids=ids, out_tokens=tok, out_len=ln)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = _lib.launch_count()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    evs[0].record()
+    for k in range(args.steps):
+        step()
+        evs[k + 1].record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    total_ms = evs[0].elapsed_time(evs[-1])
+    per_launch_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * n / (ms_per_step * 1e-3)
+
+    # ---- end to end through the host-pointer C ABI call with pinned host buffers
+    h_ll = torch.empty((n, 2), dtype=torch.float64, pin_memory=True)
+    h_ll.copy_(ll)
+    h_ids = torch.empty((len(LEVELS), n), dtype=torch.int64, pin_memory=True)
+    h_tok = torch.empty((n, 16), dtype=torch.uint8, pin_memory=True)
+    h_len = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    a_ll, a_ids, a_tok, a_len = h_ll.numpy(), h_ids.numpy().view(np.uint64), h_tok.numpy(), h_len.numpy()
+    e2e_steps = max(1, min(args.steps, 3))
+    cellid.from_lat_lng_levels_tokens(a_ll, LEVELS, TOKEN_LEVEL_INDEX, out_ids=a_ids, out_tokens=a_tok, out_len=a_len)  # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        cellid.from_lat_lng_levels_tokens(a_ll, LEVELS, TOKEN_LEVEL_INDEX, out_ids=a_ids, out_tokens=a_tok, out_len=a_len)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n / float(t.item())
+    # the e2e result equals the device-resident result
+    same = bool((h_ids[2, :1_000_000].to(dev) == ids[2, :1_000_000]).all())
+
+    if rank == 0:
+        hbm_peak, peak_src = peaks()
+        kern_ms = float(np.mean(per_launch_ms))
+        achieved = BYTES_PER_POINT * n / (kern_ms * 1e-3) / 1e9
+        dfma = _lib.ctypes.c_double(0)
+        fp64 = None
+        if lib.s2b_diag_fp64_peak(_lib.ctypes.byref(dfma)) == 0 and dfma.value > 0:
+            fp64_ach = FP64_INSTR_PER_POINT * n / (kern_ms * 1e-3)
+            fp64 = {"peak_dfma_per_s": dfma.value, "peak_tflops": 2 * dfma.value / 1e12, "fp64_instr_per_point": FP64_INSTR_PER_POINT,
+                    "achieved_instr_per_s": fp64_ach, "frac": fp64_ach / dfma.value, "peak_source": "measured live (s2b_diag_fp64_peak)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "configs[1]: 100M lat/lng (radians, uniform on sphere) per GPU -> S2CellId at levels 12/20/30 + ToToken(level 30)",
+                       "points_per_gpu": n, "levels": LEVELS, "l2_policy": "inputs (1.6 GB) and outputs (4.1 GB) per step exceed the 126 MB L2",
+                       "kernel": "encode_kernel<latlng> (1 launch per step)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": None, "peak_source": peak_src, "bytes_per_point": BYTES_PER_POINT, "kernel_ms": kern_ms, "fp64": fp64},
+            "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": (8 * len(LEVELS) + 17) * n,
+                    "ms_per_step": 1e3 * float(t.item()), "matches_device_result": same},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline()
+            except Exception as e:  # the oracle library is test infrastructure; its absence must not hide the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": "points/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--points", type=int, default=N_POINTS, help="points per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

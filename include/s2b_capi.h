@@ -1,0 +1,104 @@
+/* s2b_capi.h — C ABI of the B200-native S2 hot path (libs2b.so).
+ *
+ * The reference (google/s2geometry) has no FFI for this path; its seams are C++ value types and
+ * templates. Each entry point below is the BATCH form of one reference call and cites
+ * the reference interface it replaces (paths relative to the reference's src/s2/). INTEGRATION.md shows
+ * the C++ sugar a maintainer adds on the reference side (S2CellId::FromPoints, ...ContainsBatch).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; caller owns every buffer; opaque handles own device memory.
+ *  - functions return 0 on success or a negative S2B_E* code and never throw; s2b_last_error() returns a
+ *    thread-local message for the last failure on the calling thread.
+ *  - un-suffixed functions take HOST pointers (copies are made inside the call, pipelined over PCIe);
+ *    `_dev` functions take DEVICE pointers on the current CUDA device plus a cudaStream_t passed as
+ *    void* (NULL = legacy default stream) and only enqueue work — no synchronisation.
+ *  - results are bit-exact with the reference for cell ids, containment booleans and counts. There is
+ *    NO CPU fallback: if no CUDA device / kernel image is usable the call fails with S2B_ECUDA.
+ *  - points are S2Point = 3 doubles AoS, 24 bytes (s2point.h:35); lat/lng are 2 doubles AoS in radians
+ *    (lat, lng) like S2LatLng's internal R2Point (s2latlng.h:47-60); cell ids are uint64 (S2CellId::id()).
+ */
+#ifndef S2B_CAPI_H_
+#define S2B_CAPI_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S2B_OK 0
+#define S2B_EINVAL (-1)  /* bad argument (null pointer, level out of range, ...) */
+#define S2B_ECUDA (-2)   /* CUDA runtime / launch failure, or no usable device */
+#define S2B_ENOMEM (-3)  /* host or device allocation failed */
+#define S2B_ECAPACITY (-4) /* caller-provided output capacity too small; required size is reported */
+
+/* S2VertexModel (s2contains_point_query.h:54) */
+#define S2B_VERTEX_MODEL_OPEN 0
+#define S2B_VERTEX_MODEL_SEMI_OPEN 1
+#define S2B_VERTEX_MODEL_CLOSED 2
+
+const char* s2b_last_error(void);
+const char* s2b_version(void);
+/* Number of visible CUDA devices (0 if none / driver missing). Never fails. */
+int s2b_device_count(void);
+/* Kernel launches issued by this library in this process so far (all threads). */
+uint64_t s2b_launch_count(void);
+
+/* Diagnostic: measured FP64 FMA issue rate of the current device (DFMA/s; x2 for FLOP/s), from a
+ * register-resident DFMA chain. It is the FP64 roofline denominator bench.py reports next to the HBM one. */
+int s2b_diag_fp64_peak(double* dfma_per_second_out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Cell-id encoding.  Replaces the per-point constructors
+ *   S2CellId::S2CellId(const S2Point&)   s2cell_id.cc:309-315  (XYZtoFaceUV s2coords.h:389-419,
+ *                                         UVtoST :329-332, STtoIJ :345-356, FromFaceIJ s2cell_id.cc:267-307)
+ *   S2CellId::S2CellId(const S2LatLng&)  s2cell_id.cc:317      (S2LatLng::ToPoint s2latlng.cc:68-77)
+ * followed by S2CellId::parent(level)    s2cell_id.h:662-668 when level < 30.
+ * level must be in [0,30].
+ * ---------------------------------------------------------------------------------------------- */
+int s2b_encode_points(const double* xyz, size_t n, int level, uint64_t* ids_out);
+int s2b_encode_points_dev(const double* xyz_dev, size_t n, int level, uint64_t* ids_out_dev, void* stream);
+
+/* lat/lng in radians. sin/cos are evaluated on the device, correctly rounded (DESIGN.md "lat/lng").
+ * boundary_flag_out (nullable): 1 where a ±1-ulp change of sin/cos results could move the leaf cell, i.e.
+ * where a host libm that is not correctly rounded (glibc: ~0.13% of arguments) may legitimately differ. */
+int s2b_encode_latlng(const double* latlng_rad, size_t n, int level, uint64_t* ids_out, uint8_t* boundary_flag_out);
+int s2b_encode_latlng_dev(const double* latlng_rad_dev, size_t n, int level, uint64_t* ids_out_dev,
+                          uint8_t* boundary_flag_out_dev, void* stream);
+/* E7 fixed point: S2LatLng::FromE7 = S1Angle::E7 = Degrees(1e-7 * v) (s1angle.h:367-377). */
+int s2b_encode_latlng_e7(const int32_t* latlng_e7, size_t n, int level, uint64_t* ids_out, uint8_t* boundary_flag_out);
+int s2b_encode_latlng_e7_dev(const int32_t* latlng_e7_dev, size_t n, int level, uint64_t* ids_out_dev,
+                             uint8_t* boundary_flag_out_dev, void* stream);
+
+/* Fused multi-level encode (BASELINE config 2: ids at levels 12/20/30 in one pass): ids_out is
+ * num_levels arrays of n ids, array k at ids_out + k*n, for levels[k]. num_levels in [1,4]. */
+int s2b_encode_latlng_levels(const double* latlng_rad, size_t n, const int* levels, int num_levels, uint64_t* ids_out);
+int s2b_encode_latlng_levels_dev(const double* latlng_rad_dev, size_t n, const int* levels, int num_levels,
+                                 uint64_t* ids_out_dev, void* stream);
+int s2b_encode_points_levels_dev(const double* xyz_dev, size_t n, const int* levels, int num_levels,
+                                 uint64_t* ids_out_dev, void* stream);
+
+/* As s2b_encode_latlng_levels, and additionally S2CellId::ToToken (s2cell_id.cc:217-233) of the id at
+ * levels[token_level_index], in the same pass (no second read of the ids): tokens16_out is n 16-byte slots,
+ * NUL padded; len_out (nullable) receives strlen. */
+int s2b_encode_latlng_levels_tokens(const double* latlng_rad, size_t n, const int* levels, int num_levels, uint64_t* ids_out,
+                                    int token_level_index, char* tokens16_out, uint8_t* len_out);
+int s2b_encode_latlng_levels_tokens_dev(const double* latlng_rad_dev, size_t n, const int* levels, int num_levels,
+                                        uint64_t* ids_out_dev, int token_level_index, char* tokens16_out_dev,
+                                        uint8_t* len_out_dev, void* stream);
+
+/* S2CellId::parent(level) (s2cell_id.h:662-668). Ids whose level is < `level` are the caller's error
+ * (reference: DCHECK only); they are transformed by the same bit formula. */
+int s2b_cellid_parent(const uint64_t* ids, size_t n, int level, uint64_t* out);
+int s2b_cellid_parent_dev(const uint64_t* ids_dev, size_t n, int level, uint64_t* out_dev, void* stream);
+
+/* S2CellId::ToToken (s2cell_id.cc:209-233): tokens16_out is n fixed 16-byte slots, NUL padded;
+ * len_out (nullable) receives strlen. id 0 -> "X". */
+int s2b_cellid_to_token(const uint64_t* ids, size_t n, char* tokens16_out, uint8_t* len_out);
+int s2b_cellid_to_token_dev(const uint64_t* ids_dev, size_t n, char* tokens16_out_dev, uint8_t* len_out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S2B_CAPI_H_ */

@@ -150,6 +150,27 @@ void ref_encode_latlng_e7(const int32_t* latlng_e7, size_t n, int level, uint64_
   });
 }
 
+// BASELINE config 2 as the reference would run it: one S2CellId(S2LatLng) per point, parent() at each requested
+// level, ToToken() of the id at levels[token_level_index]. ids_out: num_levels arrays of n; tokens: 16-byte slots.
+void ref_encode_latlng_levels_tokens(const double* latlng_rad, size_t n, const int* levels, int num_levels, uint64_t* ids_out,
+                                     int token_level_index, char* tokens16, uint8_t* len_out, int threads) {
+  ParallelFor(n, threads, [=](size_t b, size_t e, int) {
+    for (size_t i = b; i < e; ++i) {
+      S2CellId leaf(S2LatLng::FromRadians(latlng_rad[2 * i], latlng_rad[2 * i + 1]));
+      for (int k = 0; k < num_levels; ++k) {
+        S2CellId id = levels[k] >= 30 ? leaf : leaf.parent(levels[k]);
+        ids_out[(size_t)k * n + i] = id.id();
+        if (k == token_level_index) {
+          std::string t = id.ToToken();
+          std::memset(tokens16 + 16 * i, 0, 16);
+          std::memcpy(tokens16 + 16 * i, t.data(), std::min<size_t>(16, t.size()));
+          if (len_out) len_out[i] = (uint8_t)t.size();
+        }
+      }
+    }
+  });
+}
+
 // S2LatLng::ToPoint only (the libm-dependent front end), for diagnosing lat/lng parity.
 void ref_latlng_to_point(const double* latlng_rad, size_t n, double* xyz) {
   for (size_t i = 0; i < n; ++i) {

@@ -1,0 +1,241 @@
+"""ctypes wrapper over oracle/_ref/libs2ref.so — the UNMODIFIED reference (google/s2geometry) compiled from
+/root/reference/src against oracle/absl_shim by oracle/build_ref.sh, behind the C ABI in oracle/ref_capi.cc.
+
+TEST INFRASTRUCTURE ONLY: the checker for parity tests and the timed CPU baseline. Never on the product path.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_ref", "libs2ref.so")
+
+_vp = ctypes.c_void_p
+_sz = ctypes.c_size_t
+
+
+def _p(a):
+    return _vp(a.ctypes.data) if a is not None else None
+
+
+def build():
+    """(Re)builds libs2ref.so when the reference sources are present (development container only)."""
+    subprocess.check_call(["bash", os.path.join(HERE, "build_ref.sh")])
+
+
+class Ref:
+    def __init__(self, lib):
+        self.lib = lib
+        lib.ref_index_create.restype = _vp
+        lib.ref_cover_cap.restype = _sz
+        lib.ref_cellunion_normalize.restype = _sz
+        lib.ref_containing_shapes.restype = ctypes.c_uint64
+        lib.ref_cellid_from_face_pos_level.restype = ctypes.c_uint64
+        lib.ref_cellid_from_face_pos_level.argtypes = [ctypes.c_int, ctypes.c_uint64, ctypes.c_int]
+
+    def hardware_threads(self):
+        return int(self.lib.ref_hardware_threads())
+
+    # ---- cell ids
+    def encode_points(self, xyz, level=30, threads=0):
+        xyz = np.ascontiguousarray(xyz, np.float64)
+        out = np.empty(len(xyz), np.uint64)
+        self.lib.ref_encode_points(_p(xyz), _sz(len(xyz)), level, _p(out), threads)
+        return out
+
+    def encode_latlng(self, ll, level=30, threads=0):
+        ll = np.ascontiguousarray(ll, np.float64)
+        out = np.empty(len(ll), np.uint64)
+        self.lib.ref_encode_latlng(_p(ll), _sz(len(ll)), level, _p(out), threads)
+        return out
+
+    def encode_latlng_deg(self, ll, level=30, threads=0):
+        ll = np.ascontiguousarray(ll, np.float64)
+        out = np.empty(len(ll), np.uint64)
+        self.lib.ref_encode_latlng_deg(_p(ll), _sz(len(ll)), level, _p(out), threads)
+        return out
+
+    def encode_latlng_e7(self, e7, level=30, threads=0):
+        e7 = np.ascontiguousarray(e7, np.int32)
+        out = np.empty(len(e7), np.uint64)
+        self.lib.ref_encode_latlng_e7(_p(e7), _sz(len(e7)), level, _p(out), threads)
+        return out
+
+    def encode_latlng_levels_tokens(self, ll, levels, token_level_index, threads=0):
+        ll = np.ascontiguousarray(ll, np.float64)
+        n = len(ll)
+        lv = (ctypes.c_int * len(levels))(*levels)
+        ids = np.empty((len(levels), n), np.uint64); tok = np.empty((n, 16), np.uint8); ln = np.empty(n, np.uint8)
+        self.lib.ref_encode_latlng_levels_tokens(_p(ll), _sz(n), lv, len(levels), _p(ids), token_level_index, _p(tok), _p(ln), threads)
+        return ids, tok, ln
+
+    def latlng_to_point(self, ll):
+        ll = np.ascontiguousarray(ll, np.float64)
+        out = np.empty((len(ll), 3), np.float64)
+        self.lib.ref_latlng_to_point(_p(ll), _sz(len(ll)), _p(out))
+        return out
+
+    def parent(self, ids, level):
+        ids = np.ascontiguousarray(ids, np.uint64)
+        out = np.empty_like(ids)
+        self.lib.ref_cellid_parent(_p(ids), _sz(ids.size), level, _p(out))
+        return out
+
+    def level(self, ids):
+        ids = np.ascontiguousarray(ids, np.uint64)
+        out = np.empty(ids.size, np.int32)
+        self.lib.ref_cellid_level(_p(ids), _sz(ids.size), _p(out))
+        return out
+
+    def id_range(self, ids):
+        ids = np.ascontiguousarray(ids, np.uint64)
+        lo = np.empty_like(ids); hi = np.empty_like(ids)
+        self.lib.ref_cellid_range(_p(ids), _sz(ids.size), _p(lo), _p(hi))
+        return lo, hi
+
+    def to_token(self, ids, threads=1):
+        ids = np.ascontiguousarray(ids, np.uint64)
+        tok = np.empty((ids.size, 16), np.uint8); ln = np.empty(ids.size, np.uint8)
+        self.lib.ref_cellid_to_token(_p(ids), _sz(ids.size), _p(tok), _p(ln), threads)
+        return tok, ln
+
+    def from_token(self, tok, ln):
+        tok = np.ascontiguousarray(tok, np.uint8); ln = np.ascontiguousarray(ln, np.uint8)
+        out = np.empty(len(ln), np.uint64)
+        self.lib.ref_cellid_from_token(_p(tok), _p(ln), _sz(len(ln)), _p(out))
+        return out
+
+    def to_point(self, ids):
+        ids = np.ascontiguousarray(ids, np.uint64)
+        out = np.empty((ids.size, 3), np.float64)
+        self.lib.ref_cellid_to_point(_p(ids), _sz(ids.size), _p(out))
+        return out
+
+    def from_face_pos_level(self, face, pos, level):
+        return int(self.lib.ref_cellid_from_face_pos_level(face, pos, level))
+
+    # ---- predicates
+    def sign(self, abc, kind=0):
+        abc = np.ascontiguousarray(abc, np.float64).reshape(-1, 9)
+        out = np.empty(len(abc), np.int8)
+        self.lib.ref_sign(_p(abc), _sz(len(abc)), kind, _p(out))
+        return out
+
+    def crossing(self, abcd, kind=0):
+        abcd = np.ascontiguousarray(abcd, np.float64).reshape(-1, 12)
+        out = np.empty(len(abcd), np.int8)
+        self.lib.ref_crossing(_p(abcd), _sz(len(abcd)), kind, _p(out))
+        return out
+
+    def ortho(self, a):
+        a = np.ascontiguousarray(a, np.float64).reshape(-1, 3)
+        out = np.empty_like(a)
+        self.lib.ref_ortho(_p(a), _sz(len(a)), _p(out))
+        return out
+
+    # ---- index
+    def index_create(self, soup, max_edges_per_cell=0):
+        return RefIndex(self, soup, max_edges_per_cell)
+
+    # ---- cell unions
+    def cellunion_contains(self, ids, xyz, threads=0):
+        ids = np.ascontiguousarray(ids, np.uint64); xyz = np.ascontiguousarray(xyz, np.float64)
+        out = np.empty(len(xyz), np.uint8)
+        self.lib.ref_cellunion_contains(_p(ids), _sz(ids.size), _p(xyz), _sz(len(xyz)), _p(out), threads)
+        return out
+
+    def cellunion_normalize(self, ids):
+        ids = np.ascontiguousarray(ids, np.uint64)
+        out = np.empty_like(ids)
+        k = self.lib.ref_cellunion_normalize(_p(ids), _sz(ids.size), _p(out))
+        return out[:k].copy()
+
+    def cover_cap(self, center, radius_rad, max_cells=8, min_level=-1, max_level=-1):
+        center = np.ascontiguousarray(center, np.float64)
+        out = np.empty(max(4 * max_cells, 64), np.uint64)
+        k = self.lib.ref_cover_cap(_p(center), ctypes.c_double(radius_rad), max_cells, min_level, max_level, _p(out), _sz(out.size))
+        assert k <= out.size
+        return out[:k].copy()
+
+
+class RefIndex:
+    """A MutableS2ShapeIndex built by the reference from a shape soup (see s2geometry_b200.shapes.ShapeSoup)."""
+
+    def __init__(self, ref, soup, max_edges_per_cell=0):
+        self.ref = ref
+        self.lib = ref.lib
+        self._keep = soup
+        self.h = self.lib.ref_index_create(int(soup.num_shapes), _p(soup.shape_dim), _p(soup.shape_chain_begin),
+                                           _p(soup.chain_vertex_begin), _p(soup.vertices), int(max_edges_per_cell))
+        self.num_shape_ids = int(self.lib.ref_index_num_shape_ids(_vp(self.h)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.ref_index_destroy(_vp(self.h))
+            self.h = None
+
+    def flatten(self):
+        C = ctypes.c_uint64(); K = ctypes.c_uint64(); E = ctypes.c_uint64()
+        self.lib.ref_index_flat_sizes(_vp(self.h), ctypes.byref(C), ctypes.byref(K), ctypes.byref(E))
+        C, K, E = C.value, K.value, E.value
+        f = dict(
+            cell_ids=np.empty(C, np.uint64), cell_center=np.empty((C, 3), np.float64),
+            cell_clip_begin=np.empty(C + 1, np.uint32), clip_shape_id=np.empty(K, np.int32),
+            clip_flags=np.empty(K, np.uint8), clip_edge_begin=np.empty(K + 1, np.uint32),
+            edge_id=np.empty(E, np.int32), edge_v0=np.empty((E, 3), np.float64), edge_v1=np.empty((E, 3), np.float64),
+            num_shape_ids=self.num_shape_ids)
+        self.lib.ref_index_flatten(_vp(self.h), _p(f["cell_ids"]), _p(f["cell_center"]), _p(f["cell_clip_begin"]),
+                                   _p(f["clip_shape_id"]), _p(f["clip_flags"]), _p(f["clip_edge_begin"]),
+                                   _p(f["edge_id"]), _p(f["edge_v0"]), _p(f["edge_v1"]))
+        return f
+
+    def contains(self, xyz, model=1, threads=0):
+        xyz = np.ascontiguousarray(xyz, np.float64)
+        out = np.empty(len(xyz), np.uint8)
+        self.lib.ref_contains(_vp(self.h), _p(xyz), _sz(len(xyz)), model, _p(out), threads)
+        return out
+
+    def shape_contains(self, shape_id, xyz, model=1, threads=0):
+        xyz = np.ascontiguousarray(xyz, np.float64)
+        out = np.empty(len(xyz), np.uint8)
+        self.lib.ref_shape_contains(_vp(self.h), shape_id, _p(xyz), _sz(len(xyz)), model, _p(out), threads)
+        return out
+
+    def shape_histogram(self, xyz, model=1, threads=0):
+        xyz = np.ascontiguousarray(xyz, np.float64)
+        out = np.zeros(self.num_shape_ids, np.uint64)
+        self.lib.ref_shape_histogram(_vp(self.h), _p(xyz), _sz(len(xyz)), model, _p(out), threads)
+        return out
+
+    def containing_shapes(self, xyz, model=1):
+        xyz = np.ascontiguousarray(xyz, np.float64)
+        off = np.empty(len(xyz) + 1, np.uint32)
+        cap = max(1024, 4 * len(xyz))
+        while True:
+            ids = np.empty(cap, np.int32)
+            total = self.lib.ref_containing_shapes(_vp(self.h), _p(xyz), _sz(len(xyz)), model, _p(off), _p(ids), ctypes.c_uint64(cap))
+            if total <= cap:
+                return off, ids[:total].copy()
+            cap = int(total)
+
+    def brute_force_contains(self, shape_id, xyz, threads=0):
+        xyz = np.ascontiguousarray(xyz, np.float64)
+        out = np.empty(len(xyz), np.uint8)
+        self.lib.ref_brute_force_contains(_vp(self.h), shape_id, _p(xyz), _sz(len(xyz)), _p(out), threads)
+        return out
+
+
+_ref = None
+
+
+def load():
+    global _ref
+    if _ref is None:
+        if not os.path.exists(LIB):
+            build()
+        if not os.path.exists(LIB):
+            raise RuntimeError("oracle/_ref/libs2ref.so is missing and the reference sources are not available to build it")
+        _ref = Ref(ctypes.CDLL(LIB))
+    return _ref

@@ -1,0 +1,73 @@
+"""ctypes binding of libs2b.so (the C ABI declared in include/s2b_capi.h).
+
+The library is the ONLY implementation of the batch entry points: if it cannot be loaded, or a call fails,
+an exception is raised — nothing falls back to Python/NumPy/the oracle.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libs2b.so")
+
+_c = ctypes
+_vp, _sz, _i, _u64 = _c.c_void_p, _c.c_size_t, _c.c_int, _c.c_uint64
+
+# name -> (restype, argtypes); mirrors include/s2b_capi.h one to one (tests/test_capi_symbols.py checks it).
+SIGNATURES = {
+    "s2b_last_error": (_c.c_char_p, []),
+    "s2b_version": (_c.c_char_p, []),
+    "s2b_device_count": (_i, []),
+    "s2b_launch_count": (_u64, []),
+    "s2b_diag_fp64_peak": (_i, [_vp]),
+    "s2b_encode_points": (_i, [_vp, _sz, _i, _vp]),
+    "s2b_encode_points_dev": (_i, [_vp, _sz, _i, _vp, _vp]),
+    "s2b_encode_latlng": (_i, [_vp, _sz, _i, _vp, _vp]),
+    "s2b_encode_latlng_dev": (_i, [_vp, _sz, _i, _vp, _vp, _vp]),
+    "s2b_encode_latlng_e7": (_i, [_vp, _sz, _i, _vp, _vp]),
+    "s2b_encode_latlng_e7_dev": (_i, [_vp, _sz, _i, _vp, _vp, _vp]),
+    "s2b_encode_latlng_levels": (_i, [_vp, _sz, _vp, _i, _vp]),
+    "s2b_encode_latlng_levels_dev": (_i, [_vp, _sz, _vp, _i, _vp, _vp]),
+    "s2b_encode_points_levels_dev": (_i, [_vp, _sz, _vp, _i, _vp, _vp]),
+    "s2b_encode_latlng_levels_tokens": (_i, [_vp, _sz, _vp, _i, _vp, _i, _vp, _vp]),
+    "s2b_encode_latlng_levels_tokens_dev": (_i, [_vp, _sz, _vp, _i, _vp, _i, _vp, _vp, _vp]),
+    "s2b_cellid_parent": (_i, [_vp, _sz, _i, _vp]),
+    "s2b_cellid_parent_dev": (_i, [_vp, _sz, _i, _vp, _vp]),
+    "s2b_cellid_to_token": (_i, [_vp, _sz, _vp, _vp]),
+    "s2b_cellid_to_token_dev": (_i, [_vp, _sz, _vp, _vp, _vp]),
+}
+
+
+class S2BError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("libs2b error %d: %s" % (code, message))
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Loads libs2b.so (built by s2geometry_b200/build.py). Raises if it is missing — there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "%s not found: build it with `python -m s2geometry_b200.build` (needs nvcc). "
+            "s2geometry_b200 has no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise S2BError(rc, load().s2b_last_error().decode("utf-8", "replace"))
+
+
+def launch_count():
+    return int(load().s2b_launch_count())

@@ -1,0 +1,201 @@
+"""Batched S2CellId operations — the host-side mirror of the reference's S2CellId interface for the hot path.
+
+Reference calls replaced (src/s2/): S2CellId(const S2Point&) s2cell_id.cc:309-315, S2CellId(const S2LatLng&)
+:317, parent(level) s2cell_id.h:662-668, ToToken s2cell_id.cc:217-233. Names follow the pybind11 binding
+(src/python/s2cell_id_bindings.cc): from_point(s) / from_lat_lng / parent / to_token.
+
+Inputs may be NumPy arrays (host path: the C ABI stages them through the GPU in chunks) or CUDA torch tensors
+(device path: kernels are enqueued on torch's current stream, results stay on the device).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+try:  # torch is plumbing only (device memory, streams); numpy inputs work without it
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+def _is_tensor(x):
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+def _np_in(a, dtype, cols):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    if cols and (a.ndim != 2 or a.shape[1] != cols):
+        raise ValueError("expected an (N, %d) array" % cols)
+    return a
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data) if isinstance(a, np.ndarray) else ctypes.c_void_p(a.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _tensor_in(t, dtype, cols):
+    if not t.is_cuda:
+        raise ValueError("torch inputs must be CUDA tensors (use NumPy arrays for host data)")
+    if t.dtype != dtype:
+        raise ValueError("expected dtype %s, got %s" % (dtype, t.dtype))
+    t = t.contiguous()
+    if cols and (t.dim() != 2 or t.shape[1] != cols):
+        raise ValueError("expected an (N, %d) tensor" % cols)
+    return t
+
+
+def _levels_arg(levels):
+    lv = [int(l) for l in levels]
+    if not 1 <= len(lv) <= 4:
+        raise ValueError("between 1 and 4 levels")
+    return (ctypes.c_int * len(lv))(*lv), len(lv)
+
+
+def from_points(xyz, level=30):
+    """S2CellId(S2Point) for every row of xyz (N,3) float64 -> uint64 ids at `level` (int64 tensor on the device path)."""
+    lib = _lib.load()
+    if _is_tensor(xyz):
+        xyz = _tensor_in(xyz, torch.float64, 3)
+        out = torch.empty(xyz.shape[0], dtype=torch.int64, device=xyz.device)
+        with torch.cuda.device(xyz.device):
+            _lib.check(lib.s2b_encode_points_dev(_ptr(xyz), xyz.shape[0], int(level), _ptr(out), _stream()))
+        return out
+    xyz = _np_in(xyz, np.float64, 3)
+    out = np.empty(xyz.shape[0], dtype=np.uint64)
+    _lib.check(lib.s2b_encode_points(_ptr(xyz), xyz.shape[0], int(level), _ptr(out)))
+    return out
+
+
+def from_lat_lng(latlng_rad, level=30, return_boundary_flags=False):
+    """S2CellId(S2LatLng::FromRadians(lat, lng)) for every row of latlng_rad (N,2) float64."""
+    lib = _lib.load()
+    if _is_tensor(latlng_rad):
+        ll = _tensor_in(latlng_rad, torch.float64, 2)
+        n = ll.shape[0]
+        out = torch.empty(n, dtype=torch.int64, device=ll.device)
+        flags = torch.empty(n, dtype=torch.uint8, device=ll.device) if return_boundary_flags else None
+        with torch.cuda.device(ll.device):
+            _lib.check(lib.s2b_encode_latlng_dev(_ptr(ll), n, int(level), _ptr(out),
+                                                 _ptr(flags) if flags is not None else None, _stream()))
+        return (out, flags) if return_boundary_flags else out
+    ll = _np_in(latlng_rad, np.float64, 2)
+    n = ll.shape[0]
+    out = np.empty(n, dtype=np.uint64)
+    flags = np.empty(n, dtype=np.uint8) if return_boundary_flags else None
+    _lib.check(lib.s2b_encode_latlng(_ptr(ll), n, int(level), _ptr(out), _ptr(flags) if flags is not None else None))
+    return (out, flags) if return_boundary_flags else out
+
+
+def from_lat_lng_e7(latlng_e7, level=30):
+    """S2CellId(S2LatLng::FromE7(lat_e7, lng_e7)) for every row of latlng_e7 (N,2) int32."""
+    lib = _lib.load()
+    if _is_tensor(latlng_e7):
+        ll = _tensor_in(latlng_e7, torch.int32, 2)
+        out = torch.empty(ll.shape[0], dtype=torch.int64, device=ll.device)
+        with torch.cuda.device(ll.device):
+            _lib.check(lib.s2b_encode_latlng_e7_dev(_ptr(ll), ll.shape[0], int(level), _ptr(out), None, _stream()))
+        return out
+    ll = _np_in(latlng_e7, np.int32, 2)
+    out = np.empty(ll.shape[0], dtype=np.uint64)
+    _lib.check(lib.s2b_encode_latlng_e7(_ptr(ll), ll.shape[0], int(level), _ptr(out), None))
+    return out
+
+
+def from_lat_lng_levels(latlng_rad, levels, out=None):
+    """Fused encode at several levels: returns (len(levels), N) ids, row k = S2CellId(ll).parent(levels[k])."""
+    lib = _lib.load()
+    lv, nl = _levels_arg(levels)
+    if _is_tensor(latlng_rad):
+        ll = _tensor_in(latlng_rad, torch.float64, 2)
+        n = ll.shape[0]
+        if out is None:
+            out = torch.empty((nl, n), dtype=torch.int64, device=ll.device)
+        with torch.cuda.device(ll.device):
+            _lib.check(lib.s2b_encode_latlng_levels_dev(_ptr(ll), n, lv, nl, _ptr(out), _stream()))
+        return out
+    ll = _np_in(latlng_rad, np.float64, 2)
+    n = ll.shape[0]
+    if out is None:
+        out = np.empty((nl, n), dtype=np.uint64)
+    _lib.check(lib.s2b_encode_latlng_levels(_ptr(ll), n, lv, nl, _ptr(out)))
+    return out
+
+
+def from_lat_lng_levels_tokens(latlng_rad, levels, token_level_index, out_ids=None, out_tokens=None, out_len=None):
+    """Fused: ids at several levels plus ToToken of the id at levels[token_level_index], one pass.
+    Returns (ids (L,N), tokens (N,16) uint8, lengths (N,) uint8)."""
+    lib = _lib.load()
+    lv, nl = _levels_arg(levels)
+    if _is_tensor(latlng_rad):
+        ll = _tensor_in(latlng_rad, torch.float64, 2)
+        n = ll.shape[0]
+        ids = out_ids if out_ids is not None else torch.empty((nl, n), dtype=torch.int64, device=ll.device)
+        tok = out_tokens if out_tokens is not None else torch.empty((n, 16), dtype=torch.uint8, device=ll.device)
+        ln = out_len if out_len is not None else torch.empty(n, dtype=torch.uint8, device=ll.device)
+        with torch.cuda.device(ll.device):
+            _lib.check(lib.s2b_encode_latlng_levels_tokens_dev(_ptr(ll), n, lv, nl, _ptr(ids), int(token_level_index),
+                                                               _ptr(tok), _ptr(ln), _stream()))
+        return ids, tok, ln
+    ll = _np_in(latlng_rad, np.float64, 2)
+    n = ll.shape[0]
+    ids = out_ids if out_ids is not None else np.empty((nl, n), dtype=np.uint64)
+    tok = out_tokens if out_tokens is not None else np.empty((n, 16), dtype=np.uint8)
+    ln = out_len if out_len is not None else np.empty(n, dtype=np.uint8)
+    _lib.check(lib.s2b_encode_latlng_levels_tokens(_ptr(ll), n, lv, nl, _ptr(ids), int(token_level_index), _ptr(tok), _ptr(ln)))
+    return ids, tok, ln
+
+
+def from_points_levels(xyz, levels):
+    """Device path only: fused S2CellId(S2Point).parent(level) at several levels -> (len(levels), N) int64 tensor."""
+    lib = _lib.load()
+    lv, nl = _levels_arg(levels)
+    xyz = _tensor_in(xyz, torch.float64, 3)
+    out = torch.empty((nl, xyz.shape[0]), dtype=torch.int64, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        _lib.check(lib.s2b_encode_points_levels_dev(_ptr(xyz), xyz.shape[0], lv, nl, _ptr(out), _stream()))
+    return out
+
+
+def parent(ids, level):
+    """S2CellId::parent(level) element-wise."""
+    lib = _lib.load()
+    if _is_tensor(ids):
+        ids = _tensor_in(ids, torch.int64, 0)
+        out = torch.empty_like(ids)
+        with torch.cuda.device(ids.device):
+            _lib.check(lib.s2b_cellid_parent_dev(_ptr(ids), ids.numel(), int(level), _ptr(out), _stream()))
+        return out
+    ids = _np_in(ids, np.uint64, 0)
+    out = np.empty_like(ids)
+    _lib.check(lib.s2b_cellid_parent(_ptr(ids), ids.size, int(level), _ptr(out)))
+    return out
+
+
+def to_token(ids, out=None, out_len=None):
+    """S2CellId::ToToken element-wise. Returns (tokens, lengths): tokens is (N,16) uint8, NUL padded."""
+    lib = _lib.load()
+    if _is_tensor(ids):
+        ids = _tensor_in(ids, torch.int64, 0)
+        n = ids.numel()
+        tok = out if out is not None else torch.empty((n, 16), dtype=torch.uint8, device=ids.device)
+        ln = out_len if out_len is not None else torch.empty(n, dtype=torch.uint8, device=ids.device)
+        with torch.cuda.device(ids.device):
+            _lib.check(lib.s2b_cellid_to_token_dev(_ptr(ids), n, _ptr(tok), _ptr(ln), _stream()))
+        return tok, ln
+    ids = _np_in(ids, np.uint64, 0)
+    tok = np.empty((ids.size, 16), dtype=np.uint8)
+    ln = np.empty(ids.size, dtype=np.uint8)
+    _lib.check(lib.s2b_cellid_to_token(_ptr(ids), ids.size, _ptr(tok), _ptr(ln)))
+    return tok, ln
+
+
+def tokens_to_str(tokens, lengths):
+    """Convenience: decode (N,16) uint8 token slots into Python strings."""
+    tokens = tokens.cpu().numpy() if _is_tensor(tokens) else np.asarray(tokens)
+    lengths = lengths.cpu().numpy() if _is_tensor(lengths) else np.asarray(lengths)
+    return [bytes(tokens[i, : lengths[i]]).decode("ascii") for i in range(len(lengths))]

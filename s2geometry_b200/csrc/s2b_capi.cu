@@ -1,0 +1,289 @@
+// s2b_capi.cu — the C ABI of libs2b.so (include/s2b_capi.h): argument checking, error reporting, and the
+// host-pointer entry points, which stream the batch through the device in chunks on three CUDA streams so that
+// the H2D copy of chunk k+1, the kernel of chunk k and the D2H copy of chunk k-1 overlap (PCIe is full duplex).
+// There is no CPU implementation behind these calls: without a usable CUDA device they return S2B_ECUDA.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/s2b_capi.h"
+#include "s2b_internal.h"
+
+namespace s2b {
+
+static thread_local char t_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_err, sizeof t_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  return set_error(e == cudaErrorMemoryAllocation ? S2B_ENOMEM : S2B_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define S2B_CUDA(call)                                   \
+  do {                                                   \
+    cudaError_t e__ = (call);                            \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+int sm_count() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    cached = v;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Chunked host<->device pipeline. One workspace per (thread, device): three slots of device buffers + streams.
+struct Slot {
+  cudaStream_t stream = nullptr;
+  void* in = nullptr;
+  void* out = nullptr;
+  size_t in_cap = 0, out_cap = 0;
+};
+
+struct Workspace {
+  int device = -1;
+  Slot slot[3];
+  int ensure(int dev, size_t in_bytes, size_t out_bytes) {
+    if (device != dev) {
+      release();
+      device = dev;
+    }
+    for (Slot& s : slot) {
+      if (!s.stream) S2B_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+      if (s.in_cap < in_bytes) {
+        if (s.in) cudaFree(s.in);
+        s.in = nullptr; s.in_cap = 0;
+        S2B_CUDA(cudaMalloc(&s.in, in_bytes));
+        s.in_cap = in_bytes;
+      }
+      if (s.out_cap < out_bytes) {
+        if (s.out) cudaFree(s.out);
+        s.out = nullptr; s.out_cap = 0;
+        S2B_CUDA(cudaMalloc(&s.out, out_bytes));
+        s.out_cap = out_bytes;
+      }
+    }
+    return S2B_OK;
+  }
+  void release() {
+    for (Slot& s : slot) {
+      if (s.in) cudaFree(s.in);
+      if (s.out) cudaFree(s.out);
+      if (s.stream) cudaStreamDestroy(s.stream);
+      s = Slot();
+    }
+  }
+};
+
+static thread_local Workspace t_ws;
+
+constexpr size_t kChunk = size_t(1) << 22;  // points per chunk (4 Mi): 64-100 MB per slot, >> launch overheads
+
+// One output stream of a pipelined call: host base pointer, bytes per point, and (for multi-array outputs) the
+// number of arrays laid out n apart on the host but chunk-size apart in the device slot.
+struct OutSpec { void* host; size_t bytes_per_point; int arrays; };
+
+// launch(in_dev, count, out_dev[], stream): out_dev[j] points at the slot region for OutSpec j.
+template <class Launch>
+int run_pipelined(const void* in_host, size_t in_bpp, size_t n, const OutSpec* outs, int n_outs, Launch launch) {
+  int dev = 0;
+  S2B_CUDA(cudaGetDevice(&dev));
+  size_t chunk = n < kChunk ? n : kChunk;
+  size_t out_bytes = 0;
+  auto region = [&](int j) { return outs[j].host ? ((outs[j].bytes_per_point * outs[j].arrays * chunk + 255) / 256) * 256 : size_t(0); };
+  for (int j = 0; j < n_outs; ++j) out_bytes += region(j);
+  int rc = t_ws.ensure(dev, in_bpp * chunk, out_bytes ? out_bytes : 256);
+  if (rc) return rc;
+  size_t k = 0;
+  for (size_t off = 0; off < n; off += chunk, ++k) {
+    Slot& s = t_ws.slot[k % 3];
+    size_t cnt = n - off < chunk ? n - off : chunk;
+    // the slot's previous D2H must have drained before its buffers are reused
+    if (k >= 3) S2B_CUDA(cudaStreamSynchronize(s.stream));
+    S2B_CUDA(cudaMemcpyAsync(s.in, (const char*)in_host + off * in_bpp, cnt * in_bpp, cudaMemcpyHostToDevice, s.stream));
+    void* out_dev[4] = {nullptr, nullptr, nullptr, nullptr};
+    char* cur = (char*)s.out;
+    for (int j = 0; j < n_outs; ++j) {
+      out_dev[j] = cur;
+      cur += region(j);
+    }
+    cudaError_t e = launch(s.in, cnt, out_dev, s.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    for (int j = 0; j < n_outs; ++j) {
+      if (!outs[j].host) continue;
+      for (int a = 0; a < outs[j].arrays; ++a) {
+        // device arrays are cnt apart (the kernels index array a at base + a*cnt), host arrays n apart
+        S2B_CUDA(cudaMemcpyAsync((char*)outs[j].host + ((size_t)a * n + off) * outs[j].bytes_per_point,
+                                 (char*)out_dev[j] + (size_t)a * cnt * outs[j].bytes_per_point,
+                                 cnt * outs[j].bytes_per_point, cudaMemcpyDeviceToHost, s.stream));
+      }
+    }
+  }
+  for (Slot& s : t_ws.slot) S2B_CUDA(cudaStreamSynchronize(s.stream));
+  return S2B_OK;
+}
+
+static int check_levels(const int* levels, int num_levels, LevelSpec* out) {
+  if (!levels || num_levels < 1 || num_levels > 4) return set_error(S2B_EINVAL, "num_levels must be in [1,4]");
+  out->n = num_levels;
+  for (int k = 0; k < 4; ++k) out->level[k] = 30;
+  for (int k = 0; k < num_levels; ++k) {
+    if (levels[k] < 0 || levels[k] > 30) return set_error(S2B_EINVAL, "level %d out of range [0,30]", levels[k]);
+    out->level[k] = levels[k];
+  }
+  return S2B_OK;
+}
+
+// tok_level_index < 0: no tokens.
+static int encode_host(InputKind kind, const void* in, size_t in_bpp, size_t n, const int* levels, int num_levels,
+                       uint64_t* ids_out, uint8_t* flags_out, int tok_level_index = -1, char* tok_out = nullptr,
+                       uint8_t* tok_len_out = nullptr) {
+  LevelSpec lv;
+  int rc = check_levels(levels, num_levels, &lv);
+  if (rc) return rc;
+  if (tok_level_index >= num_levels) return set_error(S2B_EINVAL, "token_level_index out of range");
+  if (n == 0) return S2B_OK;
+  if (!in || !ids_out || (tok_level_index >= 0 && !tok_out)) return set_error(S2B_EINVAL, "null input or output pointer");
+  OutSpec outs[4] = {{ids_out, 8, num_levels}, {flags_out, 1, 1}, {tok_out, 16, 1}, {tok_len_out, 1, 1}};
+  return run_pipelined(in, in_bpp, n, outs, 4, [&](const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
+    EncodeOut o;
+    o.levels = lv;
+    o.ids = (uint64_t*)out_dev[0];
+    o.flags = flags_out ? (uint8_t*)out_dev[1] : nullptr;
+    o.token_level_index = tok_level_index;
+    o.tokens16 = tok_level_index >= 0 ? (char*)out_dev[2] : nullptr;
+    o.token_len = tok_level_index >= 0 && tok_len_out ? (uint8_t*)out_dev[3] : nullptr;
+    return launch_encode(kind, in_dev, cnt, o, st);
+  });
+}
+
+static int encode_dev(InputKind kind, const void* in, size_t n, const int* levels, int num_levels, uint64_t* ids_out,
+                      uint8_t* flags_out, void* stream, int tok_level_index = -1, char* tok_out = nullptr,
+                      uint8_t* tok_len_out = nullptr) {
+  LevelSpec lv;
+  int rc = check_levels(levels, num_levels, &lv);
+  if (rc) return rc;
+  if (tok_level_index >= num_levels) return set_error(S2B_EINVAL, "token_level_index out of range");
+  if (n == 0) return S2B_OK;
+  if (!in || !ids_out || (tok_level_index >= 0 && !tok_out)) return set_error(S2B_EINVAL, "null input or output pointer");
+  size_t align = kind == kInLatLngRad ? 16 : 8;
+  if (((uintptr_t)in % align) || ((uintptr_t)ids_out % 8) || ((uintptr_t)tok_out % 16))
+    return set_error(S2B_EINVAL, "device pointers must be %zu-byte (input), 8-byte (ids) and 16-byte (tokens) aligned", align);
+  EncodeOut o;
+  o.levels = lv;
+  o.ids = ids_out;
+  o.flags = flags_out;
+  o.token_level_index = tok_level_index;
+  o.tokens16 = tok_out;
+  o.token_len = tok_len_out;
+  cudaError_t e = launch_encode(kind, in, n, o, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "encode launch");
+  return S2B_OK;
+}
+
+}  // namespace s2b
+
+using namespace s2b;
+
+extern "C" {
+
+const char* s2b_last_error(void) { return t_err; }
+const char* s2b_version(void) { return "s2b 0.1 (sm_100a)"; }
+int s2b_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+uint64_t s2b_launch_count(void) { return g_launches.load(); }
+
+int s2b_encode_points(const double* xyz, size_t n, int level, uint64_t* ids_out) {
+  return encode_host(kInXYZ, xyz, 24, n, &level, 1, ids_out, nullptr);
+}
+int s2b_encode_points_dev(const double* xyz_dev, size_t n, int level, uint64_t* ids_out_dev, void* stream) {
+  return encode_dev(kInXYZ, xyz_dev, n, &level, 1, ids_out_dev, nullptr, stream);
+}
+int s2b_encode_latlng(const double* ll, size_t n, int level, uint64_t* ids_out, uint8_t* flag_out) {
+  return encode_host(kInLatLngRad, ll, 16, n, &level, 1, ids_out, flag_out);
+}
+int s2b_encode_latlng_dev(const double* ll_dev, size_t n, int level, uint64_t* ids_out_dev, uint8_t* flag_out_dev, void* stream) {
+  return encode_dev(kInLatLngRad, ll_dev, n, &level, 1, ids_out_dev, flag_out_dev, stream);
+}
+int s2b_encode_latlng_e7(const int32_t* e7, size_t n, int level, uint64_t* ids_out, uint8_t* flag_out) {
+  return encode_host(kInLatLngE7, e7, 8, n, &level, 1, ids_out, flag_out);
+}
+int s2b_encode_latlng_e7_dev(const int32_t* e7_dev, size_t n, int level, uint64_t* ids_out_dev, uint8_t* flag_out_dev, void* stream) {
+  return encode_dev(kInLatLngE7, e7_dev, n, &level, 1, ids_out_dev, flag_out_dev, stream);
+}
+int s2b_encode_latlng_levels(const double* ll, size_t n, const int* levels, int num_levels, uint64_t* ids_out) {
+  return encode_host(kInLatLngRad, ll, 16, n, levels, num_levels, ids_out, nullptr);
+}
+int s2b_encode_latlng_levels_dev(const double* ll_dev, size_t n, const int* levels, int num_levels, uint64_t* ids_out_dev, void* stream) {
+  return encode_dev(kInLatLngRad, ll_dev, n, levels, num_levels, ids_out_dev, nullptr, stream);
+}
+int s2b_encode_points_levels_dev(const double* xyz_dev, size_t n, const int* levels, int num_levels, uint64_t* ids_out_dev, void* stream) {
+  return encode_dev(kInXYZ, xyz_dev, n, levels, num_levels, ids_out_dev, nullptr, stream);
+}
+int s2b_encode_latlng_levels_tokens(const double* ll, size_t n, const int* levels, int num_levels, uint64_t* ids_out,
+                                    int token_level_index, char* tokens16_out, uint8_t* len_out) {
+  if (token_level_index < 0) return set_error(S2B_EINVAL, "token_level_index must be >= 0");
+  return encode_host(kInLatLngRad, ll, 16, n, levels, num_levels, ids_out, nullptr, token_level_index, tokens16_out, len_out);
+}
+int s2b_encode_latlng_levels_tokens_dev(const double* ll_dev, size_t n, const int* levels, int num_levels, uint64_t* ids_out_dev,
+                                        int token_level_index, char* tokens16_out_dev, uint8_t* len_out_dev, void* stream) {
+  if (token_level_index < 0) return set_error(S2B_EINVAL, "token_level_index must be >= 0");
+  return encode_dev(kInLatLngRad, ll_dev, n, levels, num_levels, ids_out_dev, nullptr, stream, token_level_index,
+                    tokens16_out_dev, len_out_dev);
+}
+
+int s2b_cellid_parent(const uint64_t* ids, size_t n, int level, uint64_t* out) {
+  if (level < 0 || level > 30) return set_error(S2B_EINVAL, "level %d out of range [0,30]", level);
+  if (n == 0) return S2B_OK;
+  if (!ids || !out) return set_error(S2B_EINVAL, "null pointer");
+  OutSpec outs[1] = {{out, 8, 1}};
+  return run_pipelined(ids, 8, n, outs, 1, [&](const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
+    return launch_parent((const uint64_t*)in_dev, cnt, level, (uint64_t*)out_dev[0], st);
+  });
+}
+int s2b_cellid_parent_dev(const uint64_t* ids_dev, size_t n, int level, uint64_t* out_dev, void* stream) {
+  if (level < 0 || level > 30) return set_error(S2B_EINVAL, "level %d out of range [0,30]", level);
+  if (n == 0) return S2B_OK;
+  if (!ids_dev || !out_dev) return set_error(S2B_EINVAL, "null pointer");
+  cudaError_t e = launch_parent(ids_dev, n, level, out_dev, (cudaStream_t)stream);
+  return e == cudaSuccess ? S2B_OK : cuda_fail(e, "parent launch");
+}
+
+int s2b_cellid_to_token(const uint64_t* ids, size_t n, char* tokens16_out, uint8_t* len_out) {
+  if (n == 0) return S2B_OK;
+  if (!ids || !tokens16_out) return set_error(S2B_EINVAL, "null pointer");
+  OutSpec outs[2] = {{tokens16_out, 16, 1}, {len_out, 1, 1}};
+  return run_pipelined(ids, 8, n, outs, 2, [&](const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
+    return launch_to_token((const uint64_t*)in_dev, cnt, (char*)out_dev[0], len_out ? (uint8_t*)out_dev[1] : nullptr, st);
+  });
+}
+int s2b_cellid_to_token_dev(const uint64_t* ids_dev, size_t n, char* tok_dev, uint8_t* len_dev, void* stream) {
+  if (n == 0) return S2B_OK;
+  if (!ids_dev || !tok_dev) return set_error(S2B_EINVAL, "null pointer");
+  if ((uintptr_t)tok_dev % 16) return set_error(S2B_EINVAL, "tokens16_out_dev must be 16-byte aligned");
+  cudaError_t e = launch_to_token(ids_dev, n, tok_dev, len_dev, (cudaStream_t)stream);
+  return e == cudaSuccess ? S2B_OK : cuda_fail(e, "token launch");
+}
+
+}  // extern "C"

@@ -1,0 +1,151 @@
+// s2b_core.cuh — scalar building blocks of the S2 hot path, written once for device code (nvcc, sm_100a,
+// -fmad=false) and also compilable as plain C++ (g++ -ffp-contract=off) so tests/hostsim can check the
+// LOGIC against the oracle on a machine without a GPU. The product only ever runs the CUDA build.
+//
+// Arithmetic must reproduce the reference bit for bit: no FMA contraction except where
+// fma() is spelled out (exact two-products), IEEE division and square root, and the reference's evaluation order.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define S2B_HD __host__ __device__ __forceinline__
+#define S2B_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define S2B_HD inline
+#define S2B_HD_NOINLINE inline
+#endif
+
+namespace s2b {
+
+struct P3 { double x, y, z; };
+
+S2B_HD bool eq(const P3& a, const P3& b) { return a.x == b.x && a.y == b.y && a.z == b.z; }  // -0 == +0 (vector.h operator==)
+// Vector3::DotProd accumulates ((0 + a0*b0) + a1*b1) + a2*b2 (util/math/vector.h:315-318).
+S2B_HD double dot(const P3& a, const P3& b) { return ((0.0 + a.x * b.x) + a.y * b.y) + a.z * b.z; }
+// Vector3::CrossProd (util/math/vector.h:474-478).
+S2B_HD P3 cross(const P3& a, const P3& b) { return P3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+S2B_HD P3 sub(const P3& a, const P3& b) { return P3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+S2B_HD P3 neg(const P3& a) { return P3{-a.x, -a.y, -a.z}; }
+S2B_HD double norm2(const P3& a) { return dot(a, a); }
+// Vector3::Normalize: one reciprocal then three multiplies (util/math/vector.h:191-198).
+S2B_HD P3 normalize(const P3& a) {
+  double n = sqrt(norm2(a));
+  if (n != 0) n = 1.0 / n;
+  return P3{a.x * n, a.y * n, a.z * n};
+}
+// Vector3::LargestAbsComponent (util/math/vector.h:508-513): strict '>' decides ties.
+S2B_HD int largest_abs_component(const P3& p) {
+  double ax = fabs(p.x), ay = fabs(p.y), az = fabs(p.z);
+  return ax > ay ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
+}
+S2B_HD double comp(const P3& p, int k) { return k == 0 ? p.x : (k == 1 ? p.y : p.z); }
+// lexicographic operator< of Vector3 (used by ExactSign's sort).
+S2B_HD bool lex_less(const P3& a, const P3& b) {
+  if (a.x < b.x) return true; if (b.x < a.x) return false;
+  if (a.y < b.y) return true; if (b.y < a.y) return false;
+  return a.z < b.z;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Cube-face projection: S2::XYZtoFaceUV (s2coords.h:389-419), quadratic UVtoST (:329-332), STtoIJ (:345-356).
+S2B_HD int xyz_to_face_uv(const P3& p, double* u, double* v) {
+  int face = largest_abs_component(p);
+  double m = comp(p, face);
+  if (m < 0) face += 3;
+  switch (face) {
+    case 0: *u =  p.y / p.x; *v =  p.z / p.x; break;
+    case 1: *u = -p.x / p.y; *v =  p.z / p.y; break;
+    case 2: *u = -p.x / p.z; *v = -p.y / p.z; break;
+    case 3: *u =  p.z / p.x; *v =  p.y / p.x; break;
+    case 4: *u =  p.z / p.y; *v = -p.x / p.y; break;
+    default: *u = -p.y / p.z; *v = -p.x / p.z; break;
+  }
+  return face;
+}
+S2B_HD double uv_to_st(double u) {
+  if (u >= 0) return 0.5 * sqrt(1 + 3 * u);
+  return 1 - 0.5 * sqrt(1 - 3 * u);
+}
+S2B_HD double st_to_uv(double s) {  // s2coords.h:324-327
+  if (s >= 0.5) return (1 / 3.) * (4 * s * s - 1);
+  return (1 / 3.) * (1 - 4 * (1 - s) * (1 - s));
+}
+S2B_HD uint32_t st_to_ij(double s) {
+  if (!(s > 0)) return 0;  // also NaN
+  int v = (int)(1073741824.0 * s);  // truncation, s <= 1
+  return (uint32_t)(v < 1073741823 ? v : 1073741823);
+}
+
+// S2CellId::FromFaceIJ (s2cell_id.cc:267-307). `pos` is the 1024-entry iiiijjjjoo -> ppppppppoo table.
+template <class TableT>
+S2B_HD uint64_t from_face_ij(int face, uint32_t i, uint32_t j, const TableT* pos) {
+  uint64_t n = (uint64_t)face << 60;
+  uint32_t bits = (uint32_t)face & 1u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 7; k >= 0; --k) {
+    bits += ((i >> (4 * k)) & 15u) << 6;
+    bits += ((j >> (4 * k)) & 15u) << 2;
+    bits = pos[bits];
+    n |= (uint64_t)(bits >> 2) << (8 * k);
+    bits &= 3u;
+  }
+  return n * 2 + 1;
+}
+
+// S2CellId(const S2Point&) (s2cell_id.cc:309-315).
+template <class TableT>
+S2B_HD uint64_t cellid_from_point(const P3& p, const TableT* pos) {
+  double u, v;
+  int face = xyz_to_face_uv(p, &u, &v);
+  uint32_t i = st_to_ij(uv_to_st(u));
+  uint32_t j = st_to_ij(uv_to_st(v));
+  return from_face_ij(face, i, j, pos);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Cell id algebra (s2cell_id.h:583-668).
+S2B_HD uint64_t lsb_for_level(int level) { return 1ull << (2 * (30 - level)); }
+S2B_HD uint64_t cellid_lsb(uint64_t id) { return id & (~id + 1); }
+S2B_HD uint64_t cellid_parent(uint64_t id, int level) {
+  uint64_t lsb = lsb_for_level(level);
+  return (id & (~lsb + 1)) | lsb;
+}
+S2B_HD uint64_t cellid_range_min(uint64_t id) { return id - (cellid_lsb(id) - 1); }
+S2B_HD uint64_t cellid_range_max(uint64_t id) { return id + (cellid_lsb(id) - 1); }
+S2B_HD bool cellid_contains(uint64_t a, uint64_t b) { return b >= cellid_range_min(a) && b <= cellid_range_max(a); }
+
+// S2CellId::ToToken (s2cell_id.cc:217-233): the 16-digit lowercase hex of the id without its trailing '0'
+// digits ("X" for id 0), written as a fixed 16-byte slot (two little-endian words, NUL padded). Returns strlen.
+S2B_HD uint64_t hex8(uint32_t x) {  // 8 nibbles -> 8 ASCII bytes, most significant nibble in the lowest byte
+  uint64_t v = x;
+  v = (v | (v << 16)) & 0x0000FFFF0000FFFFull;
+  v = (v | (v << 8)) & 0x00FF00FF00FF00FFull;
+  v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0Full;   // byte b = nibble b
+  v = ((v & 0x00000000FFFFFFFFull) << 32) | (v >> 32);
+  v = ((v & 0x0000FFFF0000FFFFull) << 16) | ((v >> 16) & 0x0000FFFF0000FFFFull);
+  v = ((v & 0x00FF00FF00FF00FFull) << 8) | ((v >> 8) & 0x00FF00FF00FF00FFull);  // byte-reversed
+  uint64_t ge10 = ((v + 0x0606060606060606ull) >> 4) & 0x0101010101010101ull;
+  return v + 0x3030303030303030ull + ge10 * 39;  // '0'.. or 'a'.. ('a' - '0' - 10 = 39)
+}
+S2B_HD int ctz64(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+  return __ffsll((long long)v) - 1;
+#else
+  return __builtin_ctzll(v);
+#endif
+}
+S2B_HD int cellid_to_token(uint64_t id, uint64_t out[2]) {
+  if (id == 0) { out[0] = 0x58; out[1] = 0; return 1; }  // "X"
+  int len = 16 - (ctz64(id) >> 2);
+  uint64_t w0 = hex8((uint32_t)(id >> 32)), w1 = hex8((uint32_t)id);
+  if (len < 8) w0 &= (1ull << (8 * len)) - 1;
+  if (len <= 8) w1 = 0;
+  else if (len < 16) w1 &= (1ull << (8 * (len - 8))) - 1;
+  out[0] = w0; out[1] = w1;
+  return len;
+}
+
+}  // namespace s2b

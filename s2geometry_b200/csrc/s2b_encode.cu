@@ -1,0 +1,150 @@
+// s2b_encode.cu — K1: batched point -> S2CellId encoding for sm_100a.
+//
+// One thread per point, persistent grid (SM count x resident CTAs), grid-stride loop. The 2 KB Hilbert
+// lookup_pos table (s2cell_id.cc:75-115) and, for lat/lng input, the 3.3 KB sin/cos node table live in shared
+// memory. Input is streamed with cache-streaming loads (read once), ids are written coalesced with
+// streaming stores. All FP64 arithmetic is IEEE (div.rn/sqrt.rn, -fmad=false) so ids equal the reference's bit for bit.
+//
+// Algorithmic traffic per point: xyz 24 B in + 8 B per level out; lat/lng 16 B (E7: 8 B) in + 8 B per level out.
+#include "s2b_core.cuh"
+#include "s2b_hilbert.h"
+#include "s2b_internal.h"
+#include "s2b_sincos.cuh"
+
+namespace s2b {
+
+__device__ const HilbertTables g_hilbert = kHilbert;
+__device__ const double g_sincos_tab[sc_tab::kTableSize][4] = {
+#define S2B_ROW(i) {sc_tab::kSinCosTable[i][0], sc_tab::kSinCosTable[i][1], sc_tab::kSinCosTable[i][2], sc_tab::kSinCosTable[i][3]}
+#define S2B_ROW5(i) S2B_ROW(i), S2B_ROW(i + 1), S2B_ROW(i + 2), S2B_ROW(i + 3), S2B_ROW(i + 4)
+#define S2B_ROW25(i) S2B_ROW5(i), S2B_ROW5(i + 5), S2B_ROW5(i + 10), S2B_ROW5(i + 15), S2B_ROW5(i + 20)
+    S2B_ROW25(0), S2B_ROW25(25), S2B_ROW25(50), S2B_ROW25(75), S2B_ROW5(100)};
+static_assert(sc_tab::kTableSize == 105, "table rows are spelled out above");
+
+constexpr int kThreads = 256;
+
+// Conservative "the leaf cell could change if sin/cos were off by one ulp" test (s2b_capi.h, boundary_flag_out).
+// Four trig results each off by <= 1 ulp perturb x,y,z by <= 3 ulp relative, u,v by <= 7 ulp, s,t by <= 2e-15
+// absolute, i.e. <= 2.2e-6 in units of leaf cells; the face choice changes only if two |components| are within 4 ulp.
+__device__ __forceinline__ bool boundary_sensitive(const P3& p) {
+  double ax = fabs(p.x), ay = fabs(p.y), az = fabs(p.z);
+  double hi = fmax(ax, fmax(ay, az));
+  double mid = fmax(fmin(ax, ay), fmin(fmax(ax, ay), az));
+  if (hi - mid <= hi * 0x1p-50) return true;
+  double u, v;
+  xyz_to_face_uv(p, &u, &v);
+  double fi = 1073741824.0 * uv_to_st(u), fj = 1073741824.0 * uv_to_st(v);
+  const double tol = 4e-6;
+  double di = fi - floor(fi), dj = fj - floor(fj);
+  return di < tol || di > 1 - tol || dj < tol || dj > 1 - tol;
+}
+
+// levels live in kernel parameter space; a switch keeps them out of local memory (dynamic indexing would copy them).
+__device__ __forceinline__ int level_at(const LevelSpec& l, int k) {
+  return k == 0 ? l.level[0] : (k == 1 ? l.level[1] : (k == 2 ? l.level[2] : l.level[3]));
+}
+
+template <int kKind>
+__global__ void __launch_bounds__(kThreads)
+encode_kernel(const void* __restrict__ in, size_t n, const EncodeOut o) {
+  __shared__ uint16_t s_pos[1024];
+  __shared__ double s_sc[kKind == kInXYZ ? 1 : sc_tab::kTableSize][4];
+  for (int k = threadIdx.x; k < 1024; k += kThreads) s_pos[k] = g_hilbert.pos[k];
+  if (kKind != kInXYZ) {
+    for (int k = threadIdx.x; k < sc_tab::kTableSize * 4; k += kThreads) (&s_sc[0][0])[k] = (&g_sincos_tab[0][0])[k];
+  }
+  __syncthreads();
+
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    P3 p;
+    if (kKind == kInXYZ) {
+      const double* q = (const double*)in + 3 * i;
+      p.x = __ldcs(q); p.y = __ldcs(q + 1); p.z = __ldcs(q + 2);
+    } else {
+      double lat, lng;
+      if (kKind == kInLatLngRad) {
+        double2 ll = __ldcs((const double2*)in + i);
+        lat = ll.x; lng = ll.y;
+      } else {
+        int2 e7 = __ldcs((const int2*)in + i);
+        // S1Angle::E7 = Degrees(1e-7 * e7) = (M_PI / 180) * (1e-7 * e7)   (s1angle.h:363-377)
+        lat = (M_PI / 180) * (1e-7 * (double)e7.x);
+        lng = (M_PI / 180) * (1e-7 * (double)e7.y);
+      }
+      p = latlng_to_point(lat, lng, s_sc);
+    }
+    const uint64_t id = cellid_from_point(p, s_pos);
+    for (int k = 0; k < o.levels.n; ++k) {  // uniform trip count
+      int L = level_at(o.levels, k);
+      __stcs(o.ids + (size_t)k * n + i, L < 30 ? cellid_parent(id, L) : id);
+    }
+    if (o.token_level_index >= 0) {
+      int L = level_at(o.levels, o.token_level_index);
+      uint64_t w[2];
+      int len = cellid_to_token(L < 30 ? cellid_parent(id, L) : id, w);
+      __stcs((ulonglong2*)o.tokens16 + i, make_ulonglong2(w[0], w[1]));
+      if (o.token_len) o.token_len[i] = (uint8_t)len;
+    }
+    if (o.flags) o.flags[i] = boundary_sensitive(p) ? 1 : 0;
+  }
+}
+
+static int grid_for(size_t n, const void* kernel) {
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
+  if (per_sm < 1) per_sm = 1;
+  size_t want = (n + kThreads - 1) / kThreads;
+  size_t cap = (size_t)sm_count() * per_sm;
+  return (int)(want < cap ? (want ? want : 1) : cap);
+}
+
+template <int kKind>
+static cudaError_t launch_encode_k(const void* in, size_t n, const EncodeOut& o, cudaStream_t st) {
+  auto kern = encode_kernel<kKind>;
+  kern<<<grid_for(n, (const void*)kern), kThreads, 0, st>>>(in, n, o);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_encode(InputKind kind, const void* in, size_t n, const EncodeOut& o, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  switch (kind) {
+    case kInXYZ: return launch_encode_k<kInXYZ>(in, n, o, st);
+    case kInLatLngRad: return launch_encode_k<kInLatLngRad>(in, n, o, st);
+    default: return launch_encode_k<kInLatLngE7>(in, n, o, st);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// S2CellId::parent (s2cell_id.h:662-668) and ToToken (s2cell_id.cc:217-233): pure integer, HBM-bound.
+__global__ void __launch_bounds__(kThreads) parent_kernel(const uint64_t* __restrict__ ids, size_t n, int level, uint64_t* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) __stcs(out + i, cellid_parent(__ldcs(ids + i), level));
+}
+
+__global__ void __launch_bounds__(kThreads) token_kernel(const uint64_t* __restrict__ ids, size_t n, ulonglong2* __restrict__ tok, uint8_t* __restrict__ len) {
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    uint64_t w[2];
+    int l = cellid_to_token(__ldcs(ids + i), w);
+    __stcs(tok + i, make_ulonglong2(w[0], w[1]));
+    if (len) len[i] = (uint8_t)l;
+  }
+}
+
+cudaError_t launch_parent(const uint64_t* ids, size_t n, int level, uint64_t* out, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  parent_kernel<<<grid_for(n, (const void*)parent_kernel), kThreads, 0, st>>>(ids, n, level, out);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_to_token(const uint64_t* ids, size_t n, char* tok, uint8_t* len, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  token_kernel<<<grid_for(n, (const void*)token_kernel), kThreads, 0, st>>>(ids, n, (ulonglong2*)tok, len);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace s2b

@@ -1,0 +1,32 @@
+// s2b_internal.h — declarations shared by the .cu translation units of libs2b.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace s2b {
+
+struct LevelSpec { int n; int level[4]; };
+
+// Everything the encode kernel can emit for a point. ids: `levels.n` arrays of n ids (array k at ids + k*n).
+// tokens (optional): ToToken of the id at levels.level[token_level_index], 16-byte slots + strlen bytes.
+struct EncodeOut {
+  LevelSpec levels;
+  uint64_t* ids;
+  uint8_t* flags;       // nullable: boundary-sensitivity flags (lat/lng input)
+  int token_level_index;  // -1: no tokens
+  char* tokens16;       // nullable unless token_level_index >= 0
+  uint8_t* token_len;   // nullable
+};
+
+enum InputKind { kInXYZ = 0, kInLatLngRad = 1, kInLatLngE7 = 2 };
+
+// Kernel launchers (device pointers, enqueue only). Return cudaGetLastError() of the launch.
+cudaError_t launch_encode(InputKind kind, const void* in_dev, size_t n, const EncodeOut& out, cudaStream_t stream);
+cudaError_t launch_parent(const uint64_t* ids_dev, size_t n, int level, uint64_t* out_dev, cudaStream_t stream);
+cudaError_t launch_to_token(const uint64_t* ids_dev, size_t n, char* tokens16_dev, uint8_t* len_dev, cudaStream_t stream);
+
+void count_launch();
+int sm_count();  // SMs of the current device (cached)
+
+}  // namespace s2b

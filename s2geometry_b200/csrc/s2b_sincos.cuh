@@ -1,0 +1,192 @@
+// s2b_sincos.cuh — correctly rounded sin/cos for the lat/lng front end of the encoder
+// (S2LatLng::ToPoint, s2latlng.cc:68-77, calls libm sin and cos separately: s1angle.h:343-357).
+//
+// Why not the CUDA math library: its sin/cos are 1-2 ulp, and a 1-ulp slip in x/y/z moves a level-30 cell
+// with p ≈ 2.4e-7 per coordinate. The reference's own results depend on the platform libm (glibc is < 1 ulp but
+// NOT correctly rounded for ~0.13% of arguments), so the only platform-independent definition is the correctly
+// rounded one; that is what this file computes. Ziv's two-step strategy:
+//   1. Cody-Waite reduction by pi/2 in four parts -> r as a double-double, |r| <= pi/4 (+ slack);
+//   2. fast path: table of sin/cos(i/128) as double-double + short Taylor polynomials in delta = |r| - i/128,
+//      assembled as hi + lo with relative error <= kFastErr; accept RN(hi+lo) when the rounding cannot be affected;
+//   3. otherwise (≈1e-5 of arguments) redo the evaluation entirely in double-double (error ~2^-100).
+// |x| >= 2^20 (outside S2LatLng::is_valid's domain by a factor 3e5) and non-finite x use the CUDA / libm function.
+#pragma once
+#include "s2b_core.cuh"
+#include "s2b_sincos_tables.h"
+
+namespace s2b {
+
+struct SinCos { double s, c; };
+
+S2B_HD void two_sum(double a, double b, double& s, double& e) {
+  s = a + b;
+  double bb = s - a;
+  e = (a - (s - bb)) + (b - bb);
+}
+S2B_HD void fast_two_sum(double a, double b, double& s, double& e) {  // requires |a| >= |b| or a == 0
+  s = a + b;
+  e = b - (s - a);
+}
+S2B_HD void two_prod(double a, double b, double& p, double& e) {
+  p = a * b;
+  e = fma(a, b, -p);
+}
+
+// double-double helpers for the slow path
+struct DD { double h, l; };
+S2B_HD DD dd_norm(double h, double l) { DD r; two_sum(h, l, r.h, r.l); return r; }
+S2B_HD DD dd_add(DD a, DD b) {
+  double s, e, t, f;
+  two_sum(a.h, b.h, s, e);
+  two_sum(a.l, b.l, t, f);
+  e += t;
+  double s2, e2;
+  fast_two_sum(s, e, s2, e2);
+  e2 += f;
+  DD r;
+  fast_two_sum(s2, e2, r.h, r.l);
+  return r;
+}
+S2B_HD DD dd_mul(DD a, DD b) {
+  double p, e;
+  two_prod(a.h, b.h, p, e);
+  e += a.h * b.l + a.l * b.h;
+  DD r;
+  fast_two_sum(p, e, r.h, r.l);
+  return r;
+}
+S2B_HD DD dd_neg(DD a) { return DD{-a.h, -a.l}; }
+
+// Relative error bound of the fast path's hi+lo (measured max 2^-69.3 against mpmath over 4e6 arguments incl.
+// the neighbourhoods of multiples of pi/2 and of the table nodes; see tests/test_sincos.py). 2^-67 leaves ~7x margin.
+static constexpr double kFastErr = 0x1p-67;
+
+// Reduction: x = k*(pi/2) + (rh + rl), |x| < 2^20. Returns k.
+S2B_HD int reduce_pio2(double x, double& rh, double& rl) {
+  using namespace sc_tab;
+  double kd = rint(x * kTwoOverPi);
+  double t1 = x - kd * kPio2_1;  // product exact (33+20 bits), difference exact (Sterbenz)
+  double w2 = kd * kPio2_2;      // exact
+  double a, e1;
+  two_sum(t1, -w2, a, e1);
+  double wh, wl;
+  two_prod(kd, kPio2_3, wh, wl);
+  double b, e2;
+  two_sum(a, -wh, b, e2);
+  double low = ((e1 + e2) - wl) - kd * kPio2_4;
+  two_sum(b, low, rh, rl);
+  return (int)kd;
+}
+
+// sin and cos of a = ah + al, 0 <= a <= ~0.81, as hi+lo pairs. tab = sc_tab::kSinCosTable (shared memory on device).
+template <bool kSlow>
+S2B_HD void sincos_core(double ah, double al, const double (*tab)[4], double& sh, double& sl, double& ch, double& cl) {
+  int i = (int)(ah * 128.0 + 0.5);
+  double d0 = ah - (double)i * 0.0078125;  // exact
+  double dh, dl;
+  two_sum(d0, al, dh, dl);
+  const double Sh = tab[i][0], Sl = tab[i][1], Ch = tab[i][2], Cl = tab[i][3];
+  if (!kSlow) {
+    double qh, ql;
+    two_prod(dh, dh, qh, ql);
+    double z = qh;
+    double sp = dh * (z * (-1.0 / 6 + z * (1.0 / 120 + z * (-1.0 / 5040))));         // sin(d) - d
+    double cp = (z * z) * (1.0 / 24 + z * (-1.0 / 720 + z * (1.0 / 40320)));         // cos(d) - 1 + d^2/2
+    double cm1h = -0.5 * qh;                                                          // cos(d) - 1 = cm1h + cm1l
+    double cm1l = (-0.5 * ql - dh * dl) + cp;
+    double sdl = dl + sp;                                                             // sin(d) = dh + sdl
+    double p1, e1, p2, e2, s1, t1, s2, t2;
+    // sin(a) = S*cos(d) + C*sin(d)
+    two_prod(Ch, dh, p1, e1);
+    two_prod(Sh, cm1h, p2, e2);
+    two_sum(Sh, p1, s1, t1);
+    two_sum(s1, p2, s2, t2);
+    double low = (((Sl * cm1h + Cl * dh) + (Sh * cm1l + Ch * sdl)) + (e1 + e2)) + ((t1 + t2) + Sl);
+    fast_two_sum(s2, low, sh, sl);
+    // cos(a) = C*cos(d) - S*sin(d)
+    two_prod(-Sh, dh, p1, e1);
+    two_prod(Ch, cm1h, p2, e2);
+    two_sum(Ch, p1, s1, t1);
+    two_sum(s1, p2, s2, t2);
+    low = (((Cl * cm1h - Sl * dh) + (Ch * cm1l - Sh * sdl)) + (e1 + e2)) + ((t1 + t2) + Cl);
+    fast_two_sum(s2, low, ch, cl);
+  } else {
+    using sc_tab::kInvFact;
+    DD d{dh, dl};
+    DD z = dd_mul(d, d);
+    // sin(d)/d - 1 = z*(-1/3! + z*(1/5! + z*(-1/7! + z*(1/9! + z*(-1/11! + z/13!)))))
+    DD ps{kInvFact[13][0], kInvFact[13][1]};
+    ps = dd_add(dd_mul(ps, z), DD{-kInvFact[11][0], -kInvFact[11][1]});
+    ps = dd_add(dd_mul(ps, z), DD{kInvFact[9][0], kInvFact[9][1]});
+    ps = dd_add(dd_mul(ps, z), DD{-kInvFact[7][0], -kInvFact[7][1]});
+    ps = dd_add(dd_mul(ps, z), DD{kInvFact[5][0], kInvFact[5][1]});
+    ps = dd_add(dd_mul(ps, z), DD{-kInvFact[3][0], -kInvFact[3][1]});
+    ps = dd_mul(ps, z);
+    DD sind = dd_add(d, dd_mul(d, ps));
+    // cos(d) - 1 = z*(-1/2! + z*(1/4! + z*(-1/6! + z*(1/8! + z*(-1/10! + z/12!)))))
+    DD pc{kInvFact[12][0], kInvFact[12][1]};
+    pc = dd_add(dd_mul(pc, z), DD{-kInvFact[10][0], -kInvFact[10][1]});
+    pc = dd_add(dd_mul(pc, z), DD{kInvFact[8][0], kInvFact[8][1]});
+    pc = dd_add(dd_mul(pc, z), DD{-kInvFact[6][0], -kInvFact[6][1]});
+    pc = dd_add(dd_mul(pc, z), DD{kInvFact[4][0], kInvFact[4][1]});
+    pc = dd_add(dd_mul(pc, z), DD{-0.5, 0.0});
+    DD cm1 = dd_mul(pc, z);
+    DD S{Sh, Sl}, C{Ch, Cl};
+    // sin(a) = S + (S*cm1 + C*sind), cos(a) = C + (C*cm1 - S*sind)
+    DD rs = dd_add(S, dd_add(dd_mul(S, cm1), dd_mul(C, sind)));
+    DD rc = dd_add(C, dd_add(dd_mul(C, cm1), dd_neg(dd_mul(S, sind))));
+    sh = rs.h; sl = rs.l; ch = rc.h; cl = rc.l;
+  }
+}
+
+// true when RN(hi + lo + e) is the same double for every |e| <= kFastErr*|hi|.
+S2B_HD bool ziv_ok(double hi, double lo) {
+  double E = fabs(hi) * kFastErr;
+  return hi + (lo + E) == hi + (lo - E);
+}
+
+// Correctly rounded sin(x), cos(x). n_slow (nullable) counts arguments that needed the double-double stage.
+template <bool kForceSlow = false>
+S2B_HD SinCos sincos_cr(double x, const double (*tab)[4], int* n_slow = nullptr) {
+  double ax = fabs(x);
+  SinCos out;
+  if (!(ax < 1048576.0)) {  // huge, inf or NaN: outside the supported domain, defer to the platform function
+    out.s = sin(x);
+    out.c = cos(x);
+    return out;
+  }
+  if (ax < 0x1p-27) { out.s = x; out.c = 1.0; return out; }  // |x^2/6| < 2^-56: RN(sin x) = x, RN(cos x) = 1
+  double rh = x, rl = 0.0;
+  int k = 0;
+  if (ax > sc_tab::kPio4Hi) k = reduce_pio2(x, rh, rl);
+  bool negr = rh < 0;
+  double ah = negr ? -rh : rh, al = negr ? -rl : rl;
+  double sh, sl, ch, cl;
+  bool ok = false;
+  if (!kForceSlow) {
+    sincos_core<false>(ah, al, tab, sh, sl, ch, cl);
+    ok = ziv_ok(sh, sl) && ziv_ok(ch, cl);
+  }
+  if (!ok) {
+    sincos_core<true>(ah, al, tab, sh, sl, ch, cl);
+    if (n_slow) ++*n_slow;
+  }
+  double sr = negr ? -sh : sh;  // sin(r), cos(r); sh = RN(sh + sl) by construction
+  double cr = ch;
+  switch (k & 3) {
+    case 0: out.s = sr; out.c = cr; break;
+    case 1: out.s = cr; out.c = -sr; break;
+    case 2: out.s = -sr; out.c = -cr; break;
+    default: out.s = -cr; out.c = sr; break;
+  }
+  return out;
+}
+
+// S2LatLng::ToPoint (s2latlng.cc:68-77): (cos(lng)*cos(lat), sin(lng)*cos(lat), sin(lat)).
+S2B_HD P3 latlng_to_point(double lat, double lng, const double (*tab)[4], int* n_slow = nullptr) {
+  SinCos phi = sincos_cr(lat, tab, n_slow);
+  SinCos theta = sincos_cr(lng, tab, n_slow);
+  return P3{theta.c * phi.c, theta.s * phi.c, phi.s};
+}
+
+}  // namespace s2b

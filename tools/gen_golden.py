@@ -1,0 +1,58 @@
+#!/usr/bin/env python3
+"""Generates the reference-derived golden fixtures under tests/golden/ by running the UNMODIFIED reference
+(oracle/_ref/libs2ref.so, built from /root/reference/src). /root/reference does not exist on the GPU box, so the
+outputs are committed and this script documents how they were made.  Run from the repo root:
+    python tools/gen_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import reflib  # noqa: E402
+from s2geometry_b200 import synth  # noqa: E402
+
+G = os.path.join(ROOT, "tests", "golden")
+
+
+def encode_fixture(ref):
+    n = 20000
+    pts = synth.sphere_points(n, 101)
+    # add adversarial rows: axis points, face ties, zeros, negative zero, NaN, tiny and huge magnitudes
+    extra = np.array([
+        [1, 0, 0], [0, 1, 0], [0, 0, 1], [-1, 0, 0], [0, -1, 0], [0, 0, -1],
+        [1, 1, 0], [1, 0, 1], [0, 1, 1], [1, 1, 1], [-1, -1, -1], [1, -1, 1], [-1, 1, 1],
+        [0, 0, 0], [-0.0, 0, 0], [0, -0.0, 1], [np.nan, 1, 1], [1, np.nan, 0], [1e-300, 1e-300, 1e-300],
+        [1e300, 1e-300, 1], [5e-324, 0, 0], [1, 1 - 2 ** -53, 0], [1 - 2 ** -53, 1, 1], [0.5, 0.5, 0.5 + 2 ** -54],
+        [1, 2, 3], [3, 2, 1], [-3, 2, -1], [np.inf, 1, 1], [1, 1 / 3.0, -1 / 3.0], [1, -1 / 3.0, 1 / 3.0],
+    ], dtype=np.float64)
+    pts = np.concatenate([pts, extra])
+    ll = synth.sphere_latlng(n, 102)
+    ll_extra = np.array([[0, 0], [0, np.pi / 2], [np.pi / 2, 0], [0, np.pi], [0, -np.pi / 2], [-np.pi / 2, 0], [0, -np.pi],
+                         [np.pi / 4, np.pi / 4], [-np.pi / 4, 3 * np.pi / 4], [1e-300, -1e-300], [0.6154797086703873, np.pi / 4],
+                         [np.radians(39.0), np.radians(-120.0)], [np.radians(63.431052), np.radians(10.395083)]])
+    ll = np.concatenate([ll, ll_extra])
+    e7 = np.random.default_rng(103).integers([-900000000, -1800000000], [900000001, 1800000001], size=(5000, 2)).astype(np.int32)
+    out = {"xyz": pts, "latlng": ll, "e7": e7}
+    for lvl in (30, 20, 12, 0):
+        out["xyz_ids_L%d" % lvl] = ref.encode_points(pts, lvl, 1)
+        out["latlng_ids_L%d" % lvl] = ref.encode_latlng(ll, lvl, 1)
+    out["e7_ids_L30"] = ref.encode_latlng_e7(e7, 30, 1)
+    # random ids at all levels + tokens
+    rng = np.random.default_rng(104)
+    leaf = ref.encode_points(synth.sphere_points(4000, 105), 30, 1)
+    ids = np.array([ref.parent(leaf[i:i + 1], int(l))[0] for i, l in enumerate(rng.integers(0, 31, len(leaf)))], dtype=np.uint64)
+    ids = np.concatenate([ids, np.array([0, 0xFFFFFFFFFFFFFFFF, 0xF000000000000000, 1, 0x1000000000000000], dtype=np.uint64)])
+    tok, ln = ref.to_token(ids)
+    out["tok_ids"] = ids; out["tok"] = tok; out["tok_len"] = ln
+    np.savez_compressed(os.path.join(G, "encode_fixture.npz"), **out)
+    print("encode_fixture.npz", {k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    ref = reflib.load()
+    encode_fixture(ref)
+    if len(sys.argv) > 1 and sys.argv[1] == "all":
+        pass
