@@ -98,6 +98,83 @@ int s2b_cellid_parent_dev(const uint64_t* ids_dev, size_t n, int level, uint64_t
 int s2b_cellid_to_token(const uint64_t* ids, size_t n, char* tokens16_out, uint8_t* len_out);
 int s2b_cellid_to_token_dev(const uint64_t* ids_dev, size_t n, char* tokens16_out_dev, uint8_t* len_out_dev, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Shape index: a flattened, device-resident MutableS2ShapeIndex.
+ *
+ * S2bFlatIndex is the index walked once through the reference's public iteration API
+ * (S2ShapeIndex::Iterator BEGIN..done(), cell().clipped(i), shape(id)->edge(e), dimension();
+ * s2shape_index.h:244-258,286-530) — INTEGRATION.md has the 30-line flattener. All pointers are HOST pointers; the
+ * arrays are copied.
+ *   cell_ids[C]            ascending, disjoint S2CellIds (index cells)
+ *   cell_center[C*3]       S2CellId::ToPoint() of each cell (s2cell_id.h:184) — may be NULL: computed here
+ *   cell_clip_begin[C+1]   clipped shapes of cell c are [cell_clip_begin[c], cell_clip_begin[c+1])
+ *   clip_shape_id[K]       ascending within a cell (S2ShapeIndexCell order, s2shape_index.h:133-191)
+ *   clip_flags[K]          bit0 = contains_center, bits1-2 = shape dimension (0,1,2)
+ *   clip_edge_begin[K+1]   clipped edges of clip k are [clip_edge_begin[k], clip_edge_begin[k+1]), ascending edge id
+ *   edge_v0/edge_v1[E*3]   endpoints of each clipped edge (S2Shape::edge(e), s2shape.h:185)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct S2bFlatIndex {
+  uint64_t num_cells, num_clips, num_edges;
+  int32_t num_shape_ids;
+  const uint64_t* cell_ids;
+  const double* cell_center;
+  const uint32_t* cell_clip_begin;
+  const int32_t* clip_shape_id;
+  const uint8_t* clip_flags;
+  const uint32_t* clip_edge_begin;
+  const double* edge_v0;
+  const double* edge_v1;
+} S2bFlatIndex;
+
+typedef struct S2bIndex S2bIndex;
+
+/* Uploads the index to the CURRENT CUDA device (one replica per GPU: call once per process/device). */
+int s2b_index_create(const S2bFlatIndex* flat, S2bIndex** index_out);
+void s2b_index_destroy(S2bIndex* index);
+/* Any output may be NULL. device_bytes = HBM held by the replica (ids + cells + clips + edges + lookup table). */
+int s2b_index_info(const S2bIndex* index, uint64_t* num_cells, uint64_t* num_clips, uint64_t* num_edges,
+                   int32_t* num_shape_ids, uint64_t* device_bytes);
+
+/* S2ContainsPointQuery<S2ShapeIndex>(index, vertex_model).Contains(p)  (s2contains_point_query.h:255-265):
+ * out[i] = 1 if any shape contains point i. Locate = s2cell_iterator.h:137-155. */
+int s2b_contains(const S2bIndex* index, const double* xyz, size_t n, int vertex_model, uint8_t* out);
+int s2b_contains_dev(const S2bIndex* index, const double* xyz_dev, size_t n, int vertex_model, uint8_t* out_dev, void* stream);
+
+/* ...ShapeContains(shape_id, p)  (s2contains_point_query.h:267-280). */
+int s2b_shape_contains(const S2bIndex* index, int shape_id, const double* xyz, size_t n, int vertex_model, uint8_t* out);
+int s2b_shape_contains_dev(const S2bIndex* index, int shape_id, const double* xyz_dev, size_t n, int vertex_model,
+                           uint8_t* out_dev, void* stream);
+
+/* Spatial join: counts[s] = number of points contained by shape s, s in [0, num_shape_ids)
+ * (VisitContainingShapeIds, s2contains_point_query.h:282-295, accumulated per shape).
+ * Host form overwrites counts; the _dev form ADDS into counts_dev (zero it first) so batches and, across GPUs,
+ * an NCCL all-reduce of the uint64 array compose. */
+int s2b_shape_histogram(const S2bIndex* index, const double* xyz, size_t n, int vertex_model, uint64_t* counts);
+int s2b_shape_histogram_dev(const S2bIndex* index, const double* xyz_dev, size_t n, int vertex_model,
+                            uint64_t* counts_dev, void* stream);
+
+/* GetContainingShapeIds (s2contains_point_query.h:342-350) for a batch, CSR form: shape ids of point i are
+ * shape_ids_out[offsets_out[i] .. offsets_out[i+1]) in ascending order. total_out receives the number of
+ * (point, shape) pairs; if it exceeds capacity the call returns S2B_ECAPACITY after filling offsets_out only. */
+int s2b_containing_shapes(const S2bIndex* index, const double* xyz, size_t n, int vertex_model, uint32_t* offsets_out,
+                          int32_t* shape_ids_out, size_t capacity, size_t* total_out);
+/* Device building blocks of the same: per-point counts, then (after the caller's exclusive scan) the fill. */
+int s2b_containing_shapes_count_dev(const S2bIndex* index, const double* xyz_dev, size_t n, int vertex_model,
+                                    uint32_t* counts_out_dev, void* stream);
+int s2b_containing_shapes_fill_dev(const S2bIndex* index, const double* xyz_dev, size_t n, int vertex_model,
+                                   const uint32_t* offsets_dev, int32_t* shape_ids_out_dev, void* stream);
+
+/* Number of predicate evaluations that needed the exact (arbitrary-precision) stage on the device since the
+ * last reset, summed over all launches of this process on the current device. Resets the counter when reset != 0.
+ * There is no CPU stage behind it: this is purely a statistic. */
+int s2b_exact_stage_count(uint64_t* count_out, int reset);
+
+/* S2CellUnion::Contains(const S2Point&) (s2cell_union.cc:285-300,564-566): sorted_ids are the union's cell ids
+ * (S2CellUnion::cell_ids(): sorted, non-overlapping), out[i] = 1 if the union contains point i. */
+int s2b_cellunion_contains(const uint64_t* sorted_ids, size_t m, const double* xyz, size_t n, uint8_t* out);
+int s2b_cellunion_contains_dev(const uint64_t* sorted_ids_dev, size_t m, const double* xyz_dev, size_t n, uint8_t* out_dev,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -249,6 +249,10 @@ void ref_crossing(const double* abcd, size_t n, int kind, int8_t* out) {
   }
 }
 
+void ref_normalize(const double* a, size_t n, double* out) {
+  for (size_t i = 0; i < n; ++i) { S2Point o = P(a + 3 * i).Normalize(); out[3 * i] = o[0]; out[3 * i + 1] = o[1]; out[3 * i + 2] = o[2]; }
+}
+
 void ref_ortho(const double* a, size_t n, double* out) {
   for (size_t i = 0; i < n; ++i) { S2Point o = S2::Ortho(P(a + 3 * i)); out[3 * i] = o[0]; out[3 * i + 1] = o[1]; out[3 * i + 2] = o[2]; }
 }

@@ -129,6 +129,12 @@ class Ref:
         self.lib.ref_crossing(_p(abcd), _sz(len(abcd)), kind, _p(out))
         return out
 
+    def normalize(self, a):
+        a = np.ascontiguousarray(a, np.float64).reshape(-1, 3)
+        out = np.empty_like(a)
+        self.lib.ref_normalize(_p(a), _sz(len(a)), _p(out))
+        return out
+
     def ortho(self, a):
         a = np.ascontiguousarray(a, np.float64).reshape(-1, 3)
         out = np.empty_like(a)

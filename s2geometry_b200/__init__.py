@@ -5,6 +5,8 @@ include/s2b_capi.h). Importing the package does not require a GPU; calling a bat
 """
 from . import _lib  # noqa: F401
 from . import cellid  # noqa: F401
+from . import index  # noqa: F401
+from . import shapes  # noqa: F401
 from ._lib import S2BError, launch_count  # noqa: F401
 
-__all__ = ["cellid", "S2BError", "launch_count"]
+__all__ = ["cellid", "index", "shapes", "S2BError", "launch_count"]

@@ -34,6 +34,21 @@ SIGNATURES = {
     "s2b_cellid_parent_dev": (_i, [_vp, _sz, _i, _vp, _vp]),
     "s2b_cellid_to_token": (_i, [_vp, _sz, _vp, _vp]),
     "s2b_cellid_to_token_dev": (_i, [_vp, _sz, _vp, _vp, _vp]),
+    "s2b_index_create": (_i, [_vp, _vp]),
+    "s2b_index_destroy": (None, [_vp]),
+    "s2b_index_info": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "s2b_contains": (_i, [_vp, _vp, _sz, _i, _vp]),
+    "s2b_contains_dev": (_i, [_vp, _vp, _sz, _i, _vp, _vp]),
+    "s2b_shape_contains": (_i, [_vp, _i, _vp, _sz, _i, _vp]),
+    "s2b_shape_contains_dev": (_i, [_vp, _i, _vp, _sz, _i, _vp, _vp]),
+    "s2b_shape_histogram": (_i, [_vp, _vp, _sz, _i, _vp]),
+    "s2b_shape_histogram_dev": (_i, [_vp, _vp, _sz, _i, _vp, _vp]),
+    "s2b_containing_shapes": (_i, [_vp, _vp, _sz, _i, _vp, _vp, _sz, _vp]),
+    "s2b_containing_shapes_count_dev": (_i, [_vp, _vp, _sz, _i, _vp, _vp]),
+    "s2b_containing_shapes_fill_dev": (_i, [_vp, _vp, _sz, _i, _vp, _vp, _vp]),
+    "s2b_exact_stage_count": (_i, [_vp, _i]),
+    "s2b_cellunion_contains": (_i, [_vp, _sz, _vp, _sz, _vp]),
+    "s2b_cellunion_contains_dev": (_i, [_vp, _sz, _vp, _sz, _vp, _vp]),
 }
 
 

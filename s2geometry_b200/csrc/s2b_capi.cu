@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "../../include/s2b_capi.h"
 #include "s2b_internal.h"
@@ -125,8 +126,8 @@ int run_pipelined(const void* in_host, size_t in_bpp, size_t n, const OutSpec* o
       out_dev[j] = cur;
       cur += region(j);
     }
-    cudaError_t e = launch(s.in, cnt, out_dev, s.stream);
-    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    int lrc = launch(s.in, cnt, out_dev, s.stream);
+    if (lrc != S2B_OK) return lrc;
     for (int j = 0; j < n_outs; ++j) {
       if (!outs[j].host) continue;
       for (int a = 0; a < outs[j].arrays; ++a) {
@@ -171,7 +172,8 @@ static int encode_host(InputKind kind, const void* in, size_t in_bpp, size_t n, 
     o.token_level_index = tok_level_index;
     o.tokens16 = tok_level_index >= 0 ? (char*)out_dev[2] : nullptr;
     o.token_len = tok_level_index >= 0 && tok_len_out ? (uint8_t*)out_dev[3] : nullptr;
-    return launch_encode(kind, in_dev, cnt, o, st);
+    cudaError_t e = launch_encode(kind, in_dev, cnt, o, st);
+    return e == cudaSuccess ? S2B_OK : cuda_fail(e, "encode launch");
   });
 }
 
@@ -259,7 +261,8 @@ int s2b_cellid_parent(const uint64_t* ids, size_t n, int level, uint64_t* out) {
   if (!ids || !out) return set_error(S2B_EINVAL, "null pointer");
   OutSpec outs[1] = {{out, 8, 1}};
   return run_pipelined(ids, 8, n, outs, 1, [&](const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
-    return launch_parent((const uint64_t*)in_dev, cnt, level, (uint64_t*)out_dev[0], st);
+    cudaError_t e = launch_parent((const uint64_t*)in_dev, cnt, level, (uint64_t*)out_dev[0], st);
+    return e == cudaSuccess ? S2B_OK : cuda_fail(e, "parent launch");
   });
 }
 int s2b_cellid_parent_dev(const uint64_t* ids_dev, size_t n, int level, uint64_t* out_dev, void* stream) {
@@ -275,7 +278,8 @@ int s2b_cellid_to_token(const uint64_t* ids, size_t n, char* tokens16_out, uint8
   if (!ids || !tokens16_out) return set_error(S2B_EINVAL, "null pointer");
   OutSpec outs[2] = {{tokens16_out, 16, 1}, {len_out, 1, 1}};
   return run_pipelined(ids, 8, n, outs, 2, [&](const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
-    return launch_to_token((const uint64_t*)in_dev, cnt, (char*)out_dev[0], len_out ? (uint8_t*)out_dev[1] : nullptr, st);
+    cudaError_t e = launch_to_token((const uint64_t*)in_dev, cnt, (char*)out_dev[0], len_out ? (uint8_t*)out_dev[1] : nullptr, st);
+    return e == cudaSuccess ? S2B_OK : cuda_fail(e, "token launch");
   });
 }
 int s2b_cellid_to_token_dev(const uint64_t* ids_dev, size_t n, char* tok_dev, uint8_t* len_dev, void* stream) {
@@ -284,6 +288,128 @@ int s2b_cellid_to_token_dev(const uint64_t* ids_dev, size_t n, char* tok_dev, ui
   if ((uintptr_t)tok_dev % 16) return set_error(S2B_EINVAL, "tokens16_out_dev must be 16-byte aligned");
   cudaError_t e = launch_to_token(ids_dev, n, tok_dev, len_dev, (cudaStream_t)stream);
   return e == cudaSuccess ? S2B_OK : cuda_fail(e, "token launch");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Host-pointer forms of the index queries: the points stream through the same three-slot pipeline.
+
+int s2b_contains(const S2bIndex* ix, const double* xyz, size_t n, int model, uint8_t* out) {
+  if (n && (!xyz || !out)) return set_error(S2B_EINVAL, "null pointer");
+  if (n == 0) return s2b_contains_dev(ix, nullptr, 0, model, nullptr, nullptr);
+  OutSpec outs[1] = {{out, 1, 1}};
+  return run_pipelined(xyz, 24, n, outs, 1, [&](const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
+    return s2b_contains_dev(ix, (const double*)in_dev, cnt, model, (uint8_t*)out_dev[0], st);
+  });
+}
+
+int s2b_shape_contains(const S2bIndex* ix, int shape_id, const double* xyz, size_t n, int model, uint8_t* out) {
+  if (n && (!xyz || !out)) return set_error(S2B_EINVAL, "null pointer");
+  if (n == 0) return s2b_shape_contains_dev(ix, shape_id, nullptr, 0, model, nullptr, nullptr);
+  OutSpec outs[1] = {{out, 1, 1}};
+  return run_pipelined(xyz, 24, n, outs, 1, [&](const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
+    return s2b_shape_contains_dev(ix, shape_id, (const double*)in_dev, cnt, model, (uint8_t*)out_dev[0], st);
+  });
+}
+
+int s2b_shape_histogram(const S2bIndex* ix, const double* xyz, size_t n, int model, uint64_t* counts) {
+  if (!ix || !counts) return set_error(S2B_EINVAL, "null argument");
+  int32_t S = 0;
+  s2b_index_info(ix, nullptr, nullptr, nullptr, &S, nullptr);
+  if (n && !xyz) return set_error(S2B_EINVAL, "null pointer");
+  uint64_t* d_counts = nullptr;
+  size_t bytes = sizeof(uint64_t) * (size_t)(S > 0 ? S : 1);
+  S2B_CUDA(cudaMalloc(&d_counts, bytes));
+  cudaError_t e = cudaMemset(d_counts, 0, bytes);  // default stream: ordered before the non-blocking slot streams by the sync below
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  int rc = e == cudaSuccess ? S2B_OK : cuda_fail(e, "cudaMemset");
+  if (rc == S2B_OK && n)
+    rc = run_pipelined(xyz, 24, n, nullptr, 0, [&](const void* in_dev, size_t cnt, void**, cudaStream_t st) {
+      return s2b_shape_histogram_dev(ix, (const double*)in_dev, cnt, model, d_counts, st);
+    });
+  if (rc == S2B_OK && S > 0) {
+    e = cudaMemcpy(counts, d_counts, sizeof(uint64_t) * (size_t)S, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy(counts)");
+  }
+  cudaFree(d_counts);
+  return rc;
+}
+
+int s2b_containing_shapes(const S2bIndex* ix, const double* xyz, size_t n, int model, uint32_t* offsets_out,
+                          int32_t* shape_ids_out, size_t capacity, size_t* total_out) {
+  if (!ix || !offsets_out) return set_error(S2B_EINVAL, "null argument");
+  if (n && !xyz) return set_error(S2B_EINVAL, "null pointer");
+  if (total_out) *total_out = 0;
+  offsets_out[0] = 0;
+  if (n == 0) return S2B_OK;
+  // pass 1: per-point counts land in offsets_out[1..n], then an exclusive scan on the host
+  OutSpec outs[1] = {{offsets_out + 1, 4, 1}};
+  int rc = run_pipelined(xyz, 24, n, outs, 1, [&](const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
+    return s2b_containing_shapes_count_dev(ix, (const double*)in_dev, cnt, model, (uint32_t*)out_dev[0], st);
+  });
+  if (rc) return rc;
+  uint64_t total = 0;
+  for (size_t i = 1; i <= n; ++i) {
+    total += offsets_out[i];
+    if (total > 0xFFFFFFFFull) return set_error(S2B_ECAPACITY, "more than 2^32 (point, shape) pairs: split the batch");
+    offsets_out[i] = (uint32_t)total;
+  }
+  if (total_out) *total_out = (size_t)total;
+  if (total > capacity) return set_error(S2B_ECAPACITY, "shape_ids_out capacity %zu < %llu pairs", capacity, (unsigned long long)total);
+  if (total == 0) return S2B_OK;
+  if (!shape_ids_out) return set_error(S2B_EINVAL, "null shape_ids_out");
+  // pass 2: chunk by chunk, offsets rebased to the chunk, ids written to a device buffer and copied to their place
+  size_t chunk = n < kChunk ? n : kChunk;
+  uint32_t* d_off = nullptr;
+  int32_t* d_ids = nullptr;
+  size_t ids_cap = 0;
+  S2B_CUDA(cudaMalloc(&d_off, sizeof(uint32_t) * chunk));
+  std::vector<uint32_t> rebased(chunk);
+  rc = t_ws.ensure(/*dev*/ t_ws.device, 24 * chunk, 256);
+  cudaStream_t st = t_ws.slot[0].stream;
+  for (size_t off = 0; off < n && rc == S2B_OK; off += chunk) {
+    size_t cnt = n - off < chunk ? n - off : chunk;
+    uint32_t base = offsets_out[off];
+    size_t pairs = offsets_out[off + cnt] - base;
+    if (pairs == 0) continue;
+    for (size_t i = 0; i < cnt; ++i) rebased[i] = offsets_out[off + i] - base;
+    if (pairs > ids_cap) {
+      if (d_ids) cudaFree(d_ids);
+      d_ids = nullptr;
+      cudaError_t e = cudaMalloc(&d_ids, sizeof(int32_t) * pairs);
+      if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc(ids)"); break; }
+      ids_cap = pairs;
+    }
+    cudaError_t e = cudaMemcpyAsync(t_ws.slot[0].in, xyz + 3 * off, 24 * cnt, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_off, rebased.data(), sizeof(uint32_t) * cnt, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemcpyAsync"); break; }
+    rc = s2b_containing_shapes_fill_dev(ix, (const double*)t_ws.slot[0].in, cnt, model, d_off, d_ids, st);
+    if (rc) break;
+    e = cudaMemcpyAsync(shape_ids_out + base, d_ids, sizeof(int32_t) * pairs, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { rc = cuda_fail(e, "fill copy"); break; }
+  }
+  cudaFree(d_off);
+  if (d_ids) cudaFree(d_ids);
+  return rc;
+}
+
+int s2b_cellunion_contains(const uint64_t* sorted_ids, size_t m, const double* xyz, size_t n, uint8_t* out) {
+  if (n == 0) return S2B_OK;
+  if ((m && !sorted_ids) || !xyz || !out) return set_error(S2B_EINVAL, "null pointer");
+  for (size_t i = 1; i < m; ++i)
+    if (sorted_ids[i - 1] >= sorted_ids[i]) return set_error(S2B_EINVAL, "sorted_ids must be strictly ascending (S2CellUnion::cell_ids())");
+  uint64_t* d_ids = nullptr;
+  S2B_CUDA(cudaMalloc(&d_ids, sizeof(uint64_t) * (m ? m : 1)));
+  cudaError_t e = m ? cudaMemcpy(d_ids, sorted_ids, sizeof(uint64_t) * m, cudaMemcpyHostToDevice) : cudaSuccess;
+  int rc = e == cudaSuccess ? S2B_OK : cuda_fail(e, "cudaMemcpy(ids)");
+  if (rc == S2B_OK) {
+    OutSpec outs[1] = {{out, 1, 1}};
+    rc = run_pipelined(xyz, 24, n, outs, 1, [&](const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
+      return s2b_cellunion_contains_dev(d_ids, m, (const double*)in_dev, cnt, (uint8_t*)out_dev[0], st);
+    });
+  }
+  cudaFree(d_ids);
+  return rc;
 }
 
 }  // extern "C"

@@ -1,0 +1,117 @@
+// s2b_contains.cuh — Locate + containment over the flattened, device-resident shape index (host-compilable for
+// tests/hostsim). Restates, per point:
+//   S2CellIterator::LocateImpl          s2cell_iterator.h:137-155  (+ Iterator::Seek, mutable_s2shape_index.h:737-739)
+//   S2ContainsPointQuery::ShapeContains s2contains_point_query.h:352-389
+//   Contains / VisitContainingShapeIds  s2contains_point_query.h:255-295
+//
+// Flat layout (built on the host from the index's public iteration API, see s2b_capi.h S2bFlatIndex):
+//   cell_ids[C]  sorted S2CellIds of the index cells (disjoint)         — the search array
+//   cells[C]     cell centre (= S2CellId::ToPoint(), precomputed) + range of clipped shapes   32 B
+//   clips[K]     shape id, first clipped edge, edge count, flags (bit0 contains_center, bits1-2 dimension)   16 B
+//   edges[E]     both endpoints of every clipped edge, materialised so no shape is dereferenced          48 B
+//   lut[B+1]     bucket = leaf id >> lut_shift (face + 2*lut_level position bits) -> first candidate cell index,
+//                which turns Seek's O(log C) binary search into one table read plus 0-3 probes.
+#pragma once
+#include "s2b_core.cuh"
+#include "s2b_predicates.cuh"
+
+namespace s2b {
+
+struct FlatCell { double cx, cy, cz; uint32_t clip_begin, clip_count; };
+struct FlatClip { int32_t shape_id; uint32_t edge_begin; uint32_t num_edges; uint32_t flags; };
+struct FlatEdge { double v0x, v0y, v0z, v1x, v1y, v1z; };
+
+struct FlatIndexView {
+  const uint64_t* cell_ids;
+  const FlatCell* cells;
+  const FlatClip* clips;
+  const FlatEdge* edges;
+  const uint32_t* lut;
+  uint32_t num_cells;
+  int lut_shift;
+  int num_shape_ids;
+};
+
+enum VertexModel { kOpen = 0, kSemiOpen = 1, kClosed = 2 };
+
+// Index of the cell containing the leaf id, or -1. Equivalent to LocateImpl: the index cells are disjoint, so the
+// only candidate is the last cell whose range_min <= leaf.
+S2B_HD int locate_cell(const FlatIndexView& ix, uint64_t leaf) {
+  if (ix.num_cells == 0) return -1;
+  uint64_t bucket = leaf >> ix.lut_shift;
+  uint32_t lo = ix.lut[bucket], hi = ix.lut[bucket + 1];
+  if (lo >= ix.num_cells) return -1;
+  if (hi >= ix.num_cells) hi = ix.num_cells - 1;
+  while (lo < hi) {
+    uint32_t mid = (lo + hi + 1) >> 1;
+    if (cellid_range_min(ix.cell_ids[mid]) <= leaf) lo = mid; else hi = mid - 1;
+  }
+  uint64_t id = ix.cell_ids[lo];
+  return (cellid_range_min(id) <= leaf && leaf <= cellid_range_max(id)) ? (int)lo : -1;
+}
+
+S2B_HD P3 edge_v0(const FlatEdge& e) { return P3{e.v0x, e.v0y, e.v0z}; }
+S2B_HD P3 edge_v1(const FlatEdge& e) { return P3{e.v1x, e.v1y, e.v1z}; }
+
+// Everything past the S2EdgeCrosser fast path for one edge, out of line and with by-value arguments so that the hot
+// loop keeps its state in registers. Returns 0: no crossing, 1: crossing (toggle), 2: p is a vertex and the model is
+// OPEN (result false), 3: p is a vertex and the model is CLOSED (result true)  (s2contains_point_query.h:375-385).
+S2B_HD_NOINLINE int edge_slow_path(P3 a, P3 b, P3 c, P3 d, int acb, int bda, int model) {
+  int sign = crossing_sign_slow(a, b, c, d, acb, bda);
+  if (sign < 0) return 0;
+  if (sign == 0) {
+    if (model != kSemiOpen && (eq(c, b) || eq(d, b))) return model == kClosed ? 3 : 2;
+    sign = vertex_crossing(a, b, c, d) ? 1 : 0;
+  }
+  return sign;
+}
+
+// ShapeContains(cell_id, clipped, p): a = cell centre, b = p, a_cross_b = a x b (hoisted: one per located cell).
+S2B_HD bool clip_contains(const FlatIndexView& ix, const FlatClip& clip, const P3& a, const P3& b, const P3& a_cross_b, int model) {
+  bool inside = (clip.flags & 1u) != 0;
+  const uint32_t num_edges = clip.num_edges;
+  if (num_edges == 0) return inside;
+  const FlatEdge* edges = ix.edges + clip.edge_begin;
+  const int dim = (int)((clip.flags >> 1) & 3u);
+  if (dim < 2) {
+    if (model != kClosed) return false;
+    for (uint32_t i = 0; i < num_edges; ++i) {
+      FlatEdge e = edges[i];
+      if (eq(edge_v0(e), b) || eq(edge_v1(e), b)) return true;
+    }
+    return false;
+  }
+  for (uint32_t i = 0; i < num_edges; ++i) {
+    FlatEdge e = edges[i];
+    P3 c = edge_v0(e), d = edge_v1(e);
+    // S2EdgeCrosser fast path (s2edge_crosser.h:365-388): C and D strictly on the same side of AB.
+    int acb = -triage_sign(a_cross_b, c);
+    int bda = triage_sign(a_cross_b, d);
+    if (acb == -bda && bda != 0) continue;
+    int r = edge_slow_path(a, b, c, d, acb, bda, model);
+    if (r >= 2) return r == 3;
+    inside ^= (r != 0);
+  }
+  return inside;
+}
+
+// Calls visit(shape_id) for every shape that contains p, in ascending shape id order, until visit returns false.
+// Returns the located cell index (or -1).
+template <class HilbertT, class Visit>
+S2B_HD int visit_containing_shapes(const FlatIndexView& ix, const P3& p, const HilbertT* hilbert_pos, int model, Visit visit) {
+  uint64_t leaf = cellid_from_point(p, hilbert_pos);
+  int cell = locate_cell(ix, leaf);
+  if (cell < 0) return cell;
+  FlatCell fc = ix.cells[cell];
+  P3 a{fc.cx, fc.cy, fc.cz};
+  P3 a_cross_b = cross(a, p);
+  for (uint32_t k = 0; k < fc.clip_count; ++k) {
+    FlatClip clip = ix.clips[fc.clip_begin + k];
+    if (clip_contains(ix, clip, a, p, a_cross_b, model)) {
+      if (!visit(clip.shape_id)) break;
+    }
+  }
+  return cell;
+}
+
+}  // namespace s2b

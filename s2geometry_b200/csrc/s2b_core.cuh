@@ -53,19 +53,27 @@ S2B_HD int xyz_to_face_uv(const P3& p, double* u, double* v) {
   int face = largest_abs_component(p);
   double m = comp(p, face);
   if (m < 0) face += 3;
+  // ValidFaceXYZtoUV (s2coords.h:389-403) is, for every face, (+-numerator) / major axis: pick the operands, then
+  // issue exactly two IEEE divisions (the unary minus is applied to the numerator, as in the reference).
+  double nu, nv;
   switch (face) {
-    case 0: *u =  p.y / p.x; *v =  p.z / p.x; break;
-    case 1: *u = -p.x / p.y; *v =  p.z / p.y; break;
-    case 2: *u = -p.x / p.z; *v = -p.y / p.z; break;
-    case 3: *u =  p.z / p.x; *v =  p.y / p.x; break;
-    case 4: *u =  p.z / p.y; *v = -p.x / p.y; break;
-    default: *u = -p.y / p.z; *v = -p.x / p.z; break;
+    case 0: nu =  p.y; nv =  p.z; break;
+    case 1: nu = -p.x; nv =  p.z; break;
+    case 2: nu = -p.x; nv = -p.y; break;
+    case 3: nu =  p.z; nv =  p.y; break;
+    case 4: nu =  p.z; nv = -p.x; break;
+    default: nu = -p.y; nv = -p.x; break;
   }
+  *u = nu / m;
+  *v = nv / m;
   return face;
 }
 S2B_HD double uv_to_st(double u) {
-  if (u >= 0) return 0.5 * sqrt(1 + 3 * u);
-  return 1 - 0.5 * sqrt(1 - 3 * u);
+  // u >= 0 ? 0.5 * sqrt(1 + 3u) : 1 - 0.5 * sqrt(1 - 3u), with a single square root site.
+  bool pos = u >= 0;
+  double t = 3 * u;
+  double r = 0.5 * sqrt(pos ? 1 + t : 1 - t);
+  return pos ? r : 1 - r;
 }
 S2B_HD double st_to_uv(double s) {  // s2coords.h:324-327
   if (s >= 0.5) return (1 / 3.) * (4 * s * s - 1);
@@ -103,6 +111,49 @@ S2B_HD uint64_t cellid_from_point(const P3& p, const TableT* pos) {
   uint32_t i = st_to_ij(uv_to_st(u));
   uint32_t j = st_to_ij(uv_to_st(v));
   return from_face_ij(face, i, j, pos);
+}
+
+// S2CellId::ToFaceIJOrientation without the orientation (s2cell_id.cc:319-355). `ij` is the inverse table.
+template <class TableT>
+S2B_HD int cellid_to_face_ij(uint64_t id, const TableT* ij, int* pi, int* pj) {
+  int i = 0, j = 0;
+  int face = (int)(id >> 61);
+  int bits = face & 1;
+  for (int k = 7; k >= 0; --k) {
+    const int nbits = (k == 7) ? 2 : 4;
+    bits += ((int)(id >> (k * 8 + 1)) & ((1 << (2 * nbits)) - 1)) << 2;
+    bits = ij[bits];
+    i += (bits >> 6) << (k * 4);
+    j += ((bits >> 2) & 15) << (k * 4);
+    bits &= 3;
+  }
+  *pi = i; *pj = j;
+  return face;
+}
+
+// S2::FaceUVtoXYZ (s2coords.h:368-382).
+S2B_HD P3 face_uv_to_xyz(int face, double u, double v) {
+  switch (face) {
+    case 0: return P3{1, u, v};
+    case 1: return P3{-u, 1, v};
+    case 2: return P3{-u, -v, 1};
+    case 3: return P3{-1, -v, -u};
+    case 4: return P3{v, -1, -u};
+    default: return P3{v, u, -1};
+  }
+}
+
+// S2CellId::ToPoint: GetCenterSiTi (s2cell_id.h:555-581) -> FaceSiTitoXYZ (s2coords.cc:68-72) -> Normalize.
+template <class TableT>
+S2B_HD P3 cellid_to_point(uint64_t id, const TableT* ij) {
+  int i, j;
+  int face = cellid_to_face_ij(id, ij, &i, &j);
+  bool is_leaf = (id & 1) != 0;
+  int delta = is_leaf ? 1 : (((i ^ ((int)(uint32_t)id >> 2)) & 1) ? 2 : 0);
+  unsigned si = (unsigned)(2 * i + delta), ti = (unsigned)(2 * j + delta);
+  double u = st_to_uv((1.0 / 2147483648.0) * si);
+  double v = st_to_uv((1.0 / 2147483648.0) * ti);
+  return normalize(face_uv_to_xyz(face, u, v));
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -1,0 +1,82 @@
+// s2b_flat_host.h — host-side validation and packing of an S2bFlatIndex (include/s2b_capi.h) into the array-of-
+// struct form the kernels read (s2b_contains.cuh), including the bucket lookup table that replaces
+// MutableS2ShapeIndex::Iterator::Seek's ordered-map search (mutable_s2shape_index.h:737-739).
+#pragma once
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/s2b_capi.h"
+#include "s2b_contains.cuh"
+#include "s2b_hilbert.h"
+
+namespace s2b {
+
+struct HostFlat {
+  std::vector<FlatCell> cells;
+  std::vector<FlatClip> clips;
+  std::vector<FlatEdge> edges;
+  std::vector<uint32_t> lut;   // num_buckets + 2 entries
+  uint64_t num_buckets = 0;
+  int lut_shift = 0;
+  FlatIndexView view(const uint64_t* cell_ids, int num_shape_ids) const {
+    FlatIndexView v;
+    v.cell_ids = cell_ids; v.cells = cells.data(); v.clips = clips.data(); v.edges = edges.data(); v.lut = lut.data();
+    v.num_cells = (uint32_t)cells.size(); v.lut_shift = lut_shift; v.num_shape_ids = num_shape_ids;
+    return v;
+  }
+};
+
+inline int pack_flat_index(const S2bFlatIndex& f, HostFlat* out, std::string* err) {
+  const uint64_t C = f.num_cells, K = f.num_clips, E = f.num_edges;
+  auto fail = [&](int code, const std::string& m) { *err = m; return code; };
+  if (C > 0xFFFFFFF0ull || K > 0xFFFFFFF0ull || E > 0xFFFFFFF0ull) return fail(S2B_EINVAL, "index too large for 32-bit offsets");
+  if (C && (!f.cell_ids || !f.cell_clip_begin)) return fail(S2B_EINVAL, "null cell arrays");
+  if (K && (!f.clip_shape_id || !f.clip_flags || !f.clip_edge_begin)) return fail(S2B_EINVAL, "null clip arrays");
+  if (E && (!f.edge_v0 || !f.edge_v1)) return fail(S2B_EINVAL, "null edge arrays");
+  for (uint64_t c = 0; c < C; ++c) {
+    uint64_t id = f.cell_ids[c];
+    if (id == 0 || (id >> 61) > 5 || !(cellid_lsb(id) & 0x1555555555555555ull))
+      return fail(S2B_EINVAL, "cell_ids[" + std::to_string(c) + "] is not a valid S2CellId");
+    if (c && cellid_range_max(f.cell_ids[c - 1]) >= cellid_range_min(id))
+      return fail(S2B_EINVAL, "cell_ids must be ascending and disjoint (at " + std::to_string(c) + ")");
+    if (f.cell_clip_begin[c] > f.cell_clip_begin[c + 1] || f.cell_clip_begin[c + 1] > K) return fail(S2B_EINVAL, "cell_clip_begin is not monotone");
+  }
+  for (uint64_t k = 0; k < K; ++k) {
+    if (f.clip_edge_begin[k] > f.clip_edge_begin[k + 1] || f.clip_edge_begin[k + 1] > E) return fail(S2B_EINVAL, "clip_edge_begin is not monotone");
+    if (f.clip_shape_id[k] < 0 || f.clip_shape_id[k] >= f.num_shape_ids) return fail(S2B_EINVAL, "clip_shape_id out of range");
+  }
+  // lookup table level: ~4 buckets per cell, between level 2 (96 buckets) and level 10 (6.3M buckets, 25 MB)
+  int lut_level = 2;
+  while (lut_level < 10 && (6ull << (2 * lut_level)) < 4 * C) ++lut_level;
+  const uint64_t nb = 6ull << (2 * lut_level);
+  out->num_buckets = nb;
+  out->lut_shift = 61 - 2 * lut_level;
+  try {
+    out->cells.resize(C); out->clips.resize(K); out->edges.resize(E); out->lut.resize(nb + 2);
+  } catch (const std::bad_alloc&) {
+    return fail(S2B_ENOMEM, "host allocation failed");
+  }
+  for (uint64_t c = 0; c < C; ++c) {
+    P3 ctr;
+    if (f.cell_center) ctr = P3{f.cell_center[3 * c], f.cell_center[3 * c + 1], f.cell_center[3 * c + 2]};
+    else ctr = cellid_to_point(f.cell_ids[c], kHilbert.ij);
+    out->cells[c] = FlatCell{ctr.x, ctr.y, ctr.z, f.cell_clip_begin[c], f.cell_clip_begin[c + 1] - f.cell_clip_begin[c]};
+  }
+  for (uint64_t k = 0; k < K; ++k)
+    out->clips[k] = FlatClip{f.clip_shape_id[k], f.clip_edge_begin[k], f.clip_edge_begin[k + 1] - f.clip_edge_begin[k], f.clip_flags[k]};
+  for (uint64_t e = 0; e < E; ++e)
+    out->edges[e] = FlatEdge{f.edge_v0[3 * e], f.edge_v0[3 * e + 1], f.edge_v0[3 * e + 2], f.edge_v1[3 * e], f.edge_v1[3 * e + 1], f.edge_v1[3 * e + 2]};
+  // lut[b] = number of cells whose range_max < first leaf id of bucket b: the first cell a leaf of bucket b can be in
+  uint64_t c = 0;
+  for (uint64_t b = 0; b <= nb; ++b) {
+    uint64_t first = b << out->lut_shift;
+    while (c < C && cellid_range_max(f.cell_ids[c]) < first) ++c;
+    if (b == nb) c = C;
+    out->lut[b] = (uint32_t)c;
+  }
+  out->lut[nb + 1] = (uint32_t)C;
+  return S2B_OK;
+}
+
+}  // namespace s2b

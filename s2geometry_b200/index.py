@@ -1,0 +1,241 @@
+"""Batched point-in-shape queries against a device-resident shape index.
+
+Host-side mirror of the reference interface for this path (src/s2/):
+  S2ShapeIndex / MutableS2ShapeIndex   s2shape_index.h, mutable_s2shape_index.h   -> ShapeIndex (flattened, on the GPU)
+  S2ContainsPointQuery<Index>          s2contains_point_query.h:92-186            -> ContainsPointQuery
+  S2VertexModel                        s2contains_point_query.h:54                -> VertexModel
+  S2CellUnion::Contains(S2Point)       s2cell_union.cc:564-566                    -> cell_union_contains
+
+The flat form (FlatIndex) is what crosses the C ABI (S2bFlatIndex in include/s2b_capi.h): it is obtained either by
+walking a reference-built index through its public iterator or from this package's own builder.
+"""
+import ctypes
+import enum
+
+import numpy as np
+
+from . import _lib
+
+try:
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+class VertexModel(enum.IntEnum):
+    OPEN = 0
+    SEMI_OPEN = 1
+    CLOSED = 2
+
+
+class S2bFlatIndexStruct(ctypes.Structure):
+    _fields_ = [
+        ("num_cells", ctypes.c_uint64), ("num_clips", ctypes.c_uint64), ("num_edges", ctypes.c_uint64),
+        ("num_shape_ids", ctypes.c_int32),
+        ("cell_ids", ctypes.c_void_p), ("cell_center", ctypes.c_void_p), ("cell_clip_begin", ctypes.c_void_p),
+        ("clip_shape_id", ctypes.c_void_p), ("clip_flags", ctypes.c_void_p), ("clip_edge_begin", ctypes.c_void_p),
+        ("edge_v0", ctypes.c_void_p), ("edge_v1", ctypes.c_void_p),
+    ]
+
+
+class FlatIndex:
+    """Host arrays of a flattened shape index (see S2bFlatIndex)."""
+
+    FIELDS = ("cell_ids", "cell_center", "cell_clip_begin", "clip_shape_id", "clip_flags", "clip_edge_begin", "edge_v0", "edge_v1")
+    DTYPES = (np.uint64, np.float64, np.uint32, np.int32, np.uint8, np.uint32, np.float64, np.float64)
+
+    def __init__(self, num_shape_ids, cell_ids, cell_clip_begin, clip_shape_id, clip_flags, clip_edge_begin, edge_v0, edge_v1,
+                 cell_center=None, **_ignored):
+        self.num_shape_ids = int(num_shape_ids)
+        self.cell_ids = np.ascontiguousarray(cell_ids, np.uint64)
+        self.cell_center = None if cell_center is None else np.ascontiguousarray(cell_center, np.float64).reshape(-1, 3)
+        self.cell_clip_begin = np.ascontiguousarray(cell_clip_begin, np.uint32)
+        self.clip_shape_id = np.ascontiguousarray(clip_shape_id, np.int32)
+        self.clip_flags = np.ascontiguousarray(clip_flags, np.uint8)
+        self.clip_edge_begin = np.ascontiguousarray(clip_edge_begin, np.uint32)
+        self.edge_v0 = np.ascontiguousarray(edge_v0, np.float64).reshape(-1, 3)
+        self.edge_v1 = np.ascontiguousarray(edge_v1, np.float64).reshape(-1, 3)
+        if len(self.cell_clip_begin) != len(self.cell_ids) + 1 or len(self.clip_edge_begin) != len(self.clip_shape_id) + 1:
+            raise ValueError("offset arrays must have one more entry than the arrays they index")
+
+    @property
+    def num_cells(self):
+        return len(self.cell_ids)
+
+    @property
+    def num_clips(self):
+        return len(self.clip_shape_id)
+
+    @property
+    def num_edges(self):
+        return len(self.edge_v0)
+
+    def as_struct(self):
+        def p(a):
+            return None if a is None or a.size == 0 else a.ctypes.data
+        return S2bFlatIndexStruct(self.num_cells, self.num_clips, self.num_edges, self.num_shape_ids,
+                                  p(self.cell_ids), p(self.cell_center), self.cell_clip_begin.ctypes.data,
+                                  p(self.clip_shape_id), p(self.clip_flags), self.clip_edge_begin.ctypes.data,
+                                  p(self.edge_v0), p(self.edge_v1))
+
+    def save(self, path):
+        d = {k: getattr(self, k) for k in self.FIELDS if getattr(self, k) is not None}
+        np.savez_compressed(path, num_shape_ids=self.num_shape_ids, **d)
+
+    @classmethod
+    def load(cls, path):
+        z = np.load(path)
+        return cls(**{k: z[k] for k in z.files})
+
+
+def _is_tensor(x):
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+def _points(xyz):
+    if _is_tensor(xyz):
+        if not xyz.is_cuda or xyz.dtype != torch.float64 or xyz.dim() != 2 or xyz.shape[1] != 3:
+            raise ValueError("expected a CUDA float64 (N,3) tensor")
+        return xyz.contiguous()
+    a = np.ascontiguousarray(xyz, np.float64)
+    if a.ndim != 2 or a.shape[1] != 3:
+        raise ValueError("expected an (N,3) float64 array")
+    return a
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    return ctypes.c_void_p(a.ctypes.data) if isinstance(a, np.ndarray) else ctypes.c_void_p(a.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class ShapeIndex:
+    """A flattened MutableS2ShapeIndex resident on the current CUDA device (one replica per process/GPU)."""
+
+    def __init__(self, flat):
+        self._lib = _lib.load()
+        self.flat = flat
+        h = ctypes.c_void_p()
+        st = flat.as_struct()
+        _lib.check(self._lib.s2b_index_create(ctypes.byref(st), ctypes.byref(h)))
+        self._h = h
+        self.num_shape_ids = flat.num_shape_ids
+        self.device = torch.cuda.current_device() if torch is not None and torch.cuda.is_available() else 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.s2b_index_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        c = ctypes.c_uint64(); k = ctypes.c_uint64(); e = ctypes.c_uint64(); s = ctypes.c_int32(); b = ctypes.c_uint64()
+        _lib.check(self._lib.s2b_index_info(self._h, ctypes.byref(c), ctypes.byref(k), ctypes.byref(e), ctypes.byref(s), ctypes.byref(b)))
+        return dict(num_cells=c.value, num_clips=k.value, num_edges=e.value, num_shape_ids=s.value, device_bytes=b.value)
+
+
+class ContainsPointQuery:
+    """Batch form of S2ContainsPointQuery: every method takes (N,3) points (NumPy = host path, CUDA tensor = device path)."""
+
+    def __init__(self, index, vertex_model=VertexModel.SEMI_OPEN):
+        self.index = index
+        self.model = int(vertex_model)
+        self._lib = _lib.load()
+
+    def contains(self, xyz):
+        """S2ContainsPointQuery::Contains per point -> uint8 flags."""
+        p = _points(xyz)
+        n = p.shape[0]
+        if _is_tensor(p):
+            out = torch.empty(n, dtype=torch.uint8, device=p.device)
+            _lib.check(self._lib.s2b_contains_dev(self.index._h, _ptr(p), n, self.model, _ptr(out), _stream()))
+            return out
+        out = np.empty(n, np.uint8)
+        _lib.check(self._lib.s2b_contains(self.index._h, _ptr(p), n, self.model, _ptr(out)))
+        return out
+
+    def shape_contains(self, shape_id, xyz):
+        """S2ContainsPointQuery::ShapeContains(shape_id, p) per point -> uint8 flags."""
+        p = _points(xyz)
+        n = p.shape[0]
+        if _is_tensor(p):
+            out = torch.empty(n, dtype=torch.uint8, device=p.device)
+            _lib.check(self._lib.s2b_shape_contains_dev(self.index._h, int(shape_id), _ptr(p), n, self.model, _ptr(out), _stream()))
+            return out
+        out = np.empty(n, np.uint8)
+        _lib.check(self._lib.s2b_shape_contains(self.index._h, int(shape_id), _ptr(p), n, self.model, _ptr(out)))
+        return out
+
+    def shape_histogram(self, xyz, counts=None):
+        """Spatial join: number of points contained by each shape (VisitContainingShapeIds accumulated).
+        Device path: `counts` (int64 CUDA tensor of num_shape_ids, accumulated into) may be passed to chain batches."""
+        p = _points(xyz)
+        n = p.shape[0]
+        S = self.index.num_shape_ids
+        if _is_tensor(p):
+            if counts is None:
+                counts = torch.zeros(S, dtype=torch.int64, device=p.device)
+            _lib.check(self._lib.s2b_shape_histogram_dev(self.index._h, _ptr(p), n, self.model, _ptr(counts), _stream()))
+            return counts
+        out = np.zeros(S, np.uint64)
+        _lib.check(self._lib.s2b_shape_histogram(self.index._h, _ptr(p), n, self.model, _ptr(out)))
+        return out
+
+    def containing_shape_ids(self, xyz):
+        """GetContainingShapeIds for a batch in CSR form: (offsets (N+1,), shape_ids)."""
+        p = _points(xyz)
+        n = p.shape[0]
+        if _is_tensor(p):
+            cnt = torch.empty(n, dtype=torch.int32, device=p.device)
+            _lib.check(self._lib.s2b_containing_shapes_count_dev(self.index._h, _ptr(p), n, self.model, _ptr(cnt), _stream()))
+            off = torch.zeros(n + 1, dtype=torch.int64, device=p.device)
+            torch.cumsum(cnt, 0, out=off[1:])
+            total = int(off[-1].item())
+            off32 = off.to(torch.int32)
+            ids = torch.empty(max(total, 1), dtype=torch.int32, device=p.device)
+            if total:
+                _lib.check(self._lib.s2b_containing_shapes_fill_dev(self.index._h, _ptr(p), n, self.model, _ptr(off32), _ptr(ids), _stream()))
+            return off32, ids[:total]
+        off = np.empty(n + 1, np.uint32)
+        total = ctypes.c_size_t(0)
+        cap = max(1024, n // 8)
+        while True:
+            ids = np.empty(cap, np.int32)
+            rc = self._lib.s2b_containing_shapes(self.index._h, _ptr(p), n, self.model, _ptr(off), _ptr(ids), cap, ctypes.byref(total))
+            if rc == -4 and total.value > cap:
+                cap = total.value
+                continue
+            _lib.check(rc)
+            return off, ids[: total.value].copy()
+
+
+def cell_union_contains(sorted_ids, xyz):
+    """S2CellUnion::Contains(S2Point) per point; sorted_ids = S2CellUnion::cell_ids() (sorted, non-overlapping)."""
+    lib = _lib.load()
+    p = _points(xyz)
+    n = p.shape[0]
+    if _is_tensor(p):
+        ids = sorted_ids if _is_tensor(sorted_ids) else torch.from_numpy(np.ascontiguousarray(sorted_ids, np.uint64).view(np.int64)).to(p.device)
+        out = torch.empty(n, dtype=torch.uint8, device=p.device)
+        _lib.check(lib.s2b_cellunion_contains_dev(_ptr(ids), ids.numel(), _ptr(p), n, _ptr(out), _stream()))
+        return out
+    ids = np.ascontiguousarray(sorted_ids, np.uint64)
+    out = np.empty(n, np.uint8)
+    _lib.check(lib.s2b_cellunion_contains(_ptr(ids), ids.size, _ptr(p), n, _ptr(out)))
+    return out
+
+
+def exact_stage_count(reset=False):
+    """How many predicate evaluations ran the exact (superaccumulator) stage on the device so far."""
+    v = ctypes.c_uint64(0)
+    _lib.check(_lib.load().s2b_exact_stage_count(ctypes.byref(v), 1 if reset else 0))
+    return int(v.value)

@@ -1,0 +1,178 @@
+"""GPU parity tests for K2/K3/K4 (Locate, containment, histogram, cell union) through the C ABI."""
+import numpy as np
+import pytest
+
+from tests import scenes, util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+def make_index(ref_index):
+    from s2geometry_b200.index import FlatIndex, ShapeIndex
+    return ShapeIndex(FlatIndex(**ref_index.flatten()))
+
+
+def test_vertex_model_truth_tables(torch_cuda, ref):
+    from s2geometry_b200.index import ContainsPointQuery
+    ka = scenes.known_answers()
+    ri = ref.index_create(scenes.text_index(ka["index"]))
+    ix = make_index(ri)
+    q = scenes.latlng_deg_to_point(ka["queries"])
+    for name, m in scenes.MODELS.items():
+        query = ContainsPointQuery(ix, m)
+        want = np.array(ka["contains"][name], np.uint8)
+        assert (query.contains(q) == want).all(), name
+        assert (query.contains(torch_cuda.from_numpy(q).cuda()).cpu().numpy() == want).all(), name
+    for row in ka["shape_contains"]:
+        query = ContainsPointQuery(ix, scenes.MODELS[row["model"]])
+        assert query.shape_contains(row["shape"], scenes.latlng_deg_to_point([row["q"]]))[0] == row["expected"]
+    t = ka["closed_three_shapes"]
+    ix2 = make_index(ref.index_create(scenes.text_index(t["index"])))
+    off, ids = ContainsPointQuery(ix2, 2).containing_shape_ids(scenes.latlng_deg_to_point([t["q"]]))
+    assert list(off) == [0, 3] and list(ids) == t["containing_shape_ids_closed"]
+
+
+def test_golden_index_fixture(torch_cuda):
+    """Committed fixture: the reference-built index of the 10k-vertex loop and the reference's answers."""
+    from s2geometry_b200.index import ContainsPointQuery, FlatIndex, ShapeIndex
+    fx = util.fixture("index_loop10k.npz")
+    flat = FlatIndex(**{k: fx[k] for k in FlatIndex.FIELDS}, num_shape_ids=int(fx["num_shape_ids"]))
+    ix = ShapeIndex(flat)
+    info = ix.info()
+    assert info["num_cells"] == flat.num_cells and info["num_edges"] == flat.num_edges
+    q = fx["queries"]
+    for name, m in scenes.MODELS.items():
+        assert (ContainsPointQuery(ix, m).contains(q) == fx["contains_" + name]).all(), name
+    assert (ContainsPointQuery(ix, 1).contains(q) == fx["brute_force"]).all()
+    # cell centres recomputed by the library (cell_center = NULL) give the same answers
+    flat2 = FlatIndex(**{k: fx[k] for k in FlatIndex.FIELDS if k != "cell_center"}, num_shape_ids=int(fx["num_shape_ids"]))
+    assert (ContainsPointQuery(ShapeIndex(flat2), 1).contains(q) == fx["contains_SEMI_OPEN"]).all()
+
+
+def test_config3_loop_10k_vs_reference(torch_cuda, ref):
+    """BASELINE config 3 at 2M points per set: U (uniform), B (near the loop), D (on vertices / edges)."""
+    from s2geometry_b200.index import ContainsPointQuery, exact_stage_count
+    soup, v = scenes.loop_scene(10000)
+    ri = ref.index_create(soup)
+    ix = make_index(ri)
+    u, b, d = scenes.loop_points(v, 2_000_000, 2_000_000, 3)
+    for pts in (u, b, d):
+        for m in (0, 1, 2):
+            got = ContainsPointQuery(ix, m).contains(pts)
+            assert (got == ri.contains(pts, m)).all(), m
+    dev = torch_cuda.from_numpy(b).cuda()
+    assert (ContainsPointQuery(ix, 1).contains(dev).cpu().numpy() == ri.contains(b, 1)).all()
+    assert (ContainsPointQuery(ix, 1).contains(d) == ri.brute_force_contains(0, d)).all()
+    assert (ContainsPointQuery(ix, 1).shape_contains(0, b) == ri.shape_contains(0, b, 1)).all()
+
+
+def test_axis_aligned_exact_stage_on_device(torch_cuda, ref):
+    from s2geometry_b200.index import ContainsPointQuery, exact_stage_count
+    ri = ref.index_create(scenes.axis_aligned_scene())
+    ix = make_index(ri)
+    q = scenes.axis_aligned_queries()
+    exact_stage_count(reset=True)
+    for m in (0, 1, 2):
+        query = ContainsPointQuery(ix, m)
+        assert (query.contains(q) == ri.contains(q, m, 1)).all(), m
+        for s in range(ix.num_shape_ids):
+            assert (query.shape_contains(s, q) == ri.shape_contains(s, q, m, 1)).all(), (m, s)
+        assert (query.shape_histogram(q) == ri.shape_histogram(q, m, 1)).all()
+    assert exact_stage_count() > 100   # the exact (superaccumulator) stage ran on the GPU — there is no CPU stage
+
+
+def test_polygons_histogram_and_csr(torch_cuda, ref):
+    from s2geometry_b200 import synth
+    from s2geometry_b200.index import ContainsPointQuery
+    soup = scenes.polygons_scene(2000, 41, min_radius_km=100, max_radius_km=1500)
+    ri = ref.index_create(soup)
+    ix = make_index(ri)
+    pts = synth.sphere_points(3_000_000, 42)
+    query = ContainsPointQuery(ix, 1)
+    want = ri.shape_histogram(pts, 1)
+    assert want.sum() > 100000
+    assert (query.shape_histogram(pts) == want).all()
+    dev = torch_cuda.from_numpy(pts).cuda()
+    got_dev = query.shape_histogram(dev).cpu().numpy().view(np.uint64)
+    assert (got_dev == want).all()
+    sub = pts[:300000]
+    off, ids = query.containing_shape_ids(sub)
+    roff, rids = ri.containing_shapes(sub, 1)
+    assert (off == roff).all() and (ids == rids).all()
+    doff, dids = query.containing_shape_ids(dev[:300000])
+    assert (doff.cpu().numpy().astype(np.uint32) == roff).all() and (dids.cpu().numpy() == rids).all()
+    assert (query.contains(sub) == (np.diff(roff.astype(np.int64)) > 0)).all()
+
+
+def test_cell_union_contains(torch_cuda, ref):
+    from s2geometry_b200 import synth
+    from s2geometry_b200.index import cell_union_contains
+    center = np.array([0.4, 0.5, 0.76])
+    ids = ref.cover_cap(center, 0.05, max_cells=1000)
+    assert 100 < len(ids) <= 1000
+    pts = np.concatenate([synth.cap_points(center, 0.08, 1_000_000, 9), synth.sphere_points(1_000_000, 10), ref.to_point(ids)])
+    want = ref.cellunion_contains(ids, pts)
+    assert 0.2 < want.mean() < 0.8
+    assert (cell_union_contains(ids, pts) == want).all()
+    assert (cell_union_contains(ids, torch_cuda.from_numpy(pts).cuda()).cpu().numpy() == want).all()
+    # Trondheim known answer (python/s2geometry_test.py:254-259)
+    ka = util.known_answers()["latlng_deg_in_cells"][0]
+    cells = np.sort(np.array([int(c, 16) for c in ka["cells"]], np.uint64))
+    p = ref.latlng_to_point(np.radians(np.array([[ka["lat"], ka["lng"]]])))
+    assert cell_union_contains(cells, p)[0] == 1
+    big = ref.cover_cap(center, 0.3, max_cells=20000, min_level=12, max_level=12)   # > 4096 ids: global-memory path
+    assert len(big) > 4096
+    pts2 = synth.cap_points(center, 0.4, 500_000, 11)
+    assert (cell_union_contains(big, pts2) == ref.cellunion_contains(big, pts2)).all()
+
+
+def test_empty_inputs(torch_cuda, ref):
+    from s2geometry_b200.index import ContainsPointQuery, FlatIndex, ShapeIndex, cell_union_contains
+    from s2geometry_b200.shapes import ShapeSoup
+    empty = FlatIndex(0, np.zeros(0, np.uint64), np.zeros(1, np.uint32), np.zeros(0, np.int32), np.zeros(0, np.uint8),
+                      np.zeros(1, np.uint32), np.zeros((0, 3)), np.zeros((0, 3)))
+    ix = ShapeIndex(empty)
+    q = scenes.latlng_deg_to_point([[0, 0], [10, 10]])
+    assert (ContainsPointQuery(ix).contains(q) == 0).all()
+    assert ContainsPointQuery(ix).contains(np.zeros((0, 3))).shape == (0,)
+    assert (cell_union_contains(np.zeros(0, np.uint64), q) == 0).all()
+    # invalid index data is rejected, not crashed on
+    from s2geometry_b200 import S2BError
+    with pytest.raises(S2BError):
+        ShapeIndex(FlatIndex(1, np.array([5, 3], np.uint64), np.array([0, 0, 0], np.uint32), np.zeros(0, np.int32), np.zeros(0, np.uint8),
+                             np.zeros(1, np.uint32), np.zeros((0, 3)), np.zeros((0, 3))))
+
+
+def test_full_size_properties_config3(torch_cuda, ref):
+    """100M uniform points against the 10k-vertex loop, on the device (BASELINE config 3 size): size-independent
+    properties + an id-by-id check of a 4M sample against the reference."""
+    torch = torch_cuda
+    from s2geometry_b200 import synth
+    from s2geometry_b200.index import ContainsPointQuery
+    soup, v = scenes.loop_scene(10000)
+    ri = ref.index_create(soup)
+    ix = make_index(ri)
+    n = 100_000_000
+    pts = synth.sphere_points_cuda(n, 3, "cuda")
+    query = ContainsPointQuery(ix, 1)
+    inside = query.contains(pts)
+    again = query.contains(pts)
+    assert bool((inside == again).all())                                  # deterministic
+    hist = query.shape_histogram(pts)
+    assert int(hist[0].item()) == int(inside.sum().item())                # histogram == number of contained points
+    assert bool((query.shape_contains(0, pts) == inside).all())           # one shape: Contains == ShapeContains(0)
+    frac = float(inside.double().mean().item())
+    area = 2 * np.pi * (1 - np.cos(scenes.LOOP_RADIUS)) / (4 * np.pi)     # cap of the mean radius, within a few %
+    assert 0.9 * area < frac < 1.15 * area
+    # open <= semi-open <= closed pointwise
+    o = ContainsPointQuery(ix, 0).contains(pts); c = ContainsPointQuery(ix, 2).contains(pts)
+    assert bool((o <= inside).all()) and bool((inside <= c).all())
+    sample = pts[:4_000_000].cpu().numpy()
+    assert (inside[:4_000_000].cpu().numpy() == ri.contains(sample, 1)).all()

@@ -51,8 +51,30 @@ def encode_fixture(ref):
     print("encode_fixture.npz", {k: v.shape for k, v in out.items()})
 
 
+def index_fixture(ref):
+    """Flat index of the 10k-vertex loop as built and iterated by the reference + reference answers for a fixed query set."""
+    sys.path.insert(0, os.path.join(ROOT))
+    from tests import scenes
+    soup, v = scenes.loop_scene(10000)
+    ri = ref.index_create(soup)
+    f = ri.flatten()
+    u, b, d = scenes.loop_points(v, 20000, 40000, 77)
+    q = np.concatenate([u, b, d])
+    out = {k: f[k] for k in ("cell_ids", "cell_center", "cell_clip_begin", "clip_shape_id", "clip_flags", "clip_edge_begin", "edge_v0", "edge_v1")}
+    out["num_shape_ids"] = np.int32(f["num_shape_ids"])
+    out["loop_vertices"] = v
+    out["queries"] = q
+    for name, m in scenes.MODELS.items():
+        out["contains_" + name] = ri.contains(q, m, 1)
+    out["brute_force"] = ri.brute_force_contains(0, q, 0)
+    np.savez_compressed(os.path.join(G, "index_loop10k.npz"), **out)
+    print("index_loop10k.npz cells=%d clips=%d edges=%d queries=%d inside=%d" % (
+        len(f["cell_ids"]), len(f["clip_shape_id"]), len(f["edge_v0"]), len(q), out["contains_SEMI_OPEN"].sum()))
+
+
 if __name__ == "__main__":
     ref = reflib.load()
     encode_fixture(ref)
+    index_fixture(ref)
     if len(sys.argv) > 1 and sys.argv[1] == "all":
         pass
