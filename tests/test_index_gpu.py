@@ -119,7 +119,7 @@ def test_cell_union_contains(torch_cuda, ref):
     assert 100 < len(ids) <= 1000
     pts = np.concatenate([synth.cap_points(center, 0.08, 1_000_000, 9), synth.sphere_points(1_000_000, 10), ref.to_point(ids)])
     want = ref.cellunion_contains(ids, pts)
-    assert 0.2 < want.mean() < 0.8
+    assert 0.1 < want.mean() < 0.8
     assert (cell_union_contains(ids, pts) == want).all()
     assert (cell_union_contains(ids, torch_cuda.from_numpy(pts).cuda()).cpu().numpy() == want).all()
     # Trondheim known answer (python/s2geometry_test.py:254-259)
@@ -127,9 +127,9 @@ def test_cell_union_contains(torch_cuda, ref):
     cells = np.sort(np.array([int(c, 16) for c in ka["cells"]], np.uint64))
     p = ref.latlng_to_point(np.radians(np.array([[ka["lat"], ka["lng"]]])))
     assert cell_union_contains(cells, p)[0] == 1
-    big = ref.cover_cap(center, 0.3, max_cells=20000, min_level=12, max_level=12)   # > 4096 ids: global-memory path
+    big = ref.cover_cap(center, 0.15, max_cells=20000, min_level=9, max_level=9)   # 8868 ids (> 4096): global-memory path
     assert len(big) > 4096
-    pts2 = synth.cap_points(center, 0.4, 500_000, 11)
+    pts2 = synth.cap_points(center, 0.2, 500_000, 11)
     assert (cell_union_contains(big, pts2) == ref.cellunion_contains(big, pts2)).all()
 
 
