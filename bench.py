@@ -147,6 +147,86 @@ def cpu_baseline():
             "sample": "%d of 100M lat/lng points, best of 3, %d threads (reference sources + abseil stand-in)" % (sample, threads)}
 
 
+def pip_section(args, torch, dev, rank, world):
+    """BASELINE configs[2]: 100M points vs ONE 10k-vertex loop in a shape index (S2ContainsPointQuery::Contains).
+    The flat index is the committed fixture tests/golden/index_loop10k.npz (built and iterated by the reference, see
+    tools/gen_golden.py). Two point sets: U uniform on the sphere (1% locate a cell) and B uniform in the loop's
+    bounding cap (the reference's own benchmark design, s2loop_test.cc:1635-1666)."""
+    from s2geometry_b200 import _lib, synth
+    from s2geometry_b200.index import ContainsPointQuery, FlatIndex, ShapeIndex
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "index_loop10k.npz"))
+    flat = FlatIndex(**{k: fx[k] for k in FlatIndex.FIELDS}, num_shape_ids=int(fx["num_shape_ids"]))
+    ix = ShapeIndex(flat)
+    query = ContainsPointQuery(ix, 1)
+    n = args.points
+    hbm_peak, _ = peaks()
+    center = np.array([0.3, -0.5, 0.8]); radius = 0.17 * 1.25
+    out = {"workload": "configs[2]: %d points vs one 10k-vertex loop (index: %d cells, %d clipped edges), SEMI_OPEN" % (n, flat.num_cells, flat.num_edges),
+           "bytes_per_point": 25}
+    sets = {}
+    pts_u = synth.sphere_points_cuda(n, 3 + rank, dev)
+    sets["uniform"] = pts_u
+    # B: uniform in the bounding cap, generated on the device
+    g = torch.Generator(device=dev); g.manual_seed(7 + rank)
+    x, y, z = [torch.from_numpy(v).to(dev) for v in synth.frame(center)]
+    h = torch.rand(n, dtype=torch.float64, device=dev, generator=g) * (1 - np.cos(radius))
+    t = torch.rand(n, dtype=torch.float64, device=dev, generator=g) * (2 * np.pi)
+    cz = 1 - h; sz = torch.sqrt(torch.clamp(1 - cz * cz, min=0))
+    pts_b = cz[:, None] * z + sz[:, None] * (torch.cos(t)[:, None] * x + torch.sin(t)[:, None] * y)
+    pts_b /= pts_b.norm(dim=1, keepdim=True)
+    del h, t, cz, sz
+    sets["near"] = pts_b
+    res = torch.empty(n, dtype=torch.uint8, device=dev)
+    lib = _lib.load()
+    import ctypes
+    for name, pts in sets.items():
+        def step():
+            _lib.check(lib.s2b_contains_dev(ix._h, ctypes.c_void_p(pts.data_ptr()), n, 1, ctypes.c_void_p(res.data_ptr()),
+                                            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        ach = 25 * n / (ms * 1e-3) / 1e9
+        out[name] = {"points_per_s": n / (ms * 1e-3), "ms_per_step": ms, "inside_fraction": float(res.float().mean().item()),
+                     "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak}}
+    # end to end through the host-pointer call (pinned input, pinned output), U set
+    h_pts = torch.empty((n, 3), dtype=torch.float64, pin_memory=True); h_pts.copy_(pts_u)
+    h_out = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    a_pts, a_out = h_pts.numpy(), h_out.numpy()
+    _lib.check(lib.s2b_contains(ix._h, ctypes.c_void_p(a_pts.ctypes.data), n, 1, ctypes.c_void_p(a_out.ctypes.data)))
+    t0 = time.perf_counter()
+    _lib.check(lib.s2b_contains(ix._h, ctypes.c_void_p(a_pts.ctypes.data), n, 1, ctypes.c_void_p(a_out.ctypes.data)))
+    dt = time.perf_counter() - t0
+    out["e2e_uniform"] = {"points_per_s": n / dt, "ms_per_step": dt * 1e3, "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": n}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import reflib  # cpu_baseline leg
+            from s2geometry_b200.shapes import ShapeSoup
+            ref = reflib.load()
+            soup = ShapeSoup(); soup.add_polygon([fx["loop_vertices"]])
+            ri = ref.index_create(soup.freeze())
+            threads = ref.hardware_threads()
+            cb = {}
+            for name, pts in sets.items():
+                sample = pts[:20_000_000].cpu().numpy()
+                best = 1e30
+                for _ in range(2):
+                    t0 = time.perf_counter(); r = ri.contains(sample, 1, threads); best = min(best, time.perf_counter() - t0)
+                cb[name] = {"value": len(sample) / best, "unit": "points/s", "cores": threads, "kind": "reference",
+                            "sample": "first 20M points of the set, best of 2",
+                            "parity_on_sample": bool((r == query.contains(pts[:20_000_000]).cpu().numpy()).all())}
+            out["cpu_baseline"] = cb
+        except Exception as e:
+            out["cpu_baseline"] = {"unavailable": str(e)}
+    return out
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -224,6 +304,14 @@ def run_gpu(args):
     # the e2e result equals the device-resident result
     same = bool((h_ids[2, :1_000_000].to(dev) == ids[2, :1_000_000]).all())
 
+    del h_ll, h_ids, h_tok, h_len, ids, tok, ln, ll
+    torch.cuda.empty_cache()
+    pip = None
+    if not args.no_pip:
+        try:
+            pip = pip_section(args, torch, dev, rank, world)
+        except Exception as e:
+            pip = {"error": repr(e)}
     if rank == 0:
         hbm_peak, peak_src = peaks()
         kern_ms = float(np.mean(per_launch_ms))
@@ -248,6 +336,8 @@ def run_gpu(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if pip is not None:
+            line["pip"] = pip
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline()
@@ -267,6 +357,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--points", type=int, default=N_POINTS, help="points per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pip", action="store_true", help="skip the secondary point-in-polygon (configs[2]) measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
