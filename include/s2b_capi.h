@@ -126,6 +126,23 @@ typedef struct S2bFlatIndex {
   const double* edge_v1;
 } S2bFlatIndex;
 
+/* Builds the flat index on the host directly from shapes — the library's own counterpart of
+ * MutableS2ShapeIndex::Add + ForceBuild (mutable_s2shape_index.h:372,423; build: mutable_s2shape_index.cc:643-1925)
+ * for callers that do not have a reference-built index to flatten. Shapes are a "soup" of vertex chains
+ * (S2LaxPolygonShape / S2LaxPolylineShape / S2PointVectorShape semantics):
+ *   shape s has dimension shape_dim[s] (2 = closed loops, interior on the left; 1 = polylines; 0 = points) and
+ *   chains [shape_chain_begin[s], shape_chain_begin[s+1]); chain c has vertices
+ *   [chain_vertex_begin[c], chain_vertex_begin[c+1]) of `vertices` (x,y,z triples of unit vectors).
+ * max_edges_per_cell <= 0 selects the reference default (10). The result owns host arrays; s2b_built_index_flat
+ * exposes them as an S2bFlatIndex (valid until s2b_built_index_destroy) and, optionally, the shape-local edge id
+ * of every clipped edge. The cells are not required to coincide with MutableS2ShapeIndex's; query results do. */
+typedef struct S2bBuiltIndex S2bBuiltIndex;
+int s2b_index_build(int num_shapes, const int8_t* shape_dim, const uint32_t* shape_chain_begin,
+                    const uint32_t* chain_vertex_begin, const double* vertices, int max_edges_per_cell,
+                    S2bBuiltIndex** built_out);
+int s2b_built_index_flat(const S2bBuiltIndex* built, S2bFlatIndex* flat_out, const int32_t** edge_id_out);
+void s2b_built_index_destroy(S2bBuiltIndex* built);
+
 typedef struct S2bIndex S2bIndex;
 
 /* Uploads the index to the CURRENT CUDA device (one replica per GPU: call once per process/device). */

@@ -10,7 +10,7 @@
 
 #if defined(__CUDACC__)
 #define S2B_HD __host__ __device__ __forceinline__
-#define S2B_HD_NOINLINE __host__ __device__ __noinline__
+#define S2B_HD_NOINLINE inline __host__ __device__ __noinline__
 #else
 #define S2B_HD inline
 #define S2B_HD_NOINLINE inline

@@ -88,6 +88,34 @@ class FlatIndex:
         return cls(**{k: z[k] for k in z.files})
 
 
+def build_flat_index(soup, max_edges_per_cell=0):
+    """Builds a FlatIndex from a ShapeSoup with the library's own host builder (s2b_index_build): the counterpart of
+    MutableS2ShapeIndex::Add + ForceBuild for callers without a reference-built index."""
+    lib = _lib.load()
+    soup = soup.freeze()
+    h = ctypes.c_void_p()
+    keep = (soup.shape_dim, soup.shape_chain_begin, soup.chain_vertex_begin, soup.vertices)
+    _lib.check(lib.s2b_index_build(int(soup.num_shapes), keep[0].ctypes.data, keep[1].ctypes.data, keep[2].ctypes.data,
+                                   keep[3].ctypes.data if keep[3].size else None, int(max_edges_per_cell), ctypes.byref(h)))
+    try:
+        st = S2bFlatIndexStruct()
+        eid = ctypes.c_void_p()
+        _lib.check(lib.s2b_built_index_flat(h, ctypes.byref(st), ctypes.byref(eid)))
+
+        def arr(ptr, count, dtype):
+            if not ptr or count == 0:
+                return np.zeros(count, dtype)
+            return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(np.ctypeslib.as_ctypes_type(dtype))), shape=(count,)).copy()
+        C, K, E = st.num_cells, st.num_clips, st.num_edges
+        flat = FlatIndex(st.num_shape_ids, arr(st.cell_ids, C, np.uint64), arr(st.cell_clip_begin, C + 1, np.uint32),
+                         arr(st.clip_shape_id, K, np.int32), arr(st.clip_flags, K, np.uint8), arr(st.clip_edge_begin, K + 1, np.uint32),
+                         arr(st.edge_v0, 3 * E, np.float64), arr(st.edge_v1, 3 * E, np.float64), cell_center=arr(st.cell_center, 3 * C, np.float64))
+        flat.edge_id = arr(eid.value, E, np.int32)
+        return flat
+    finally:
+        lib.s2b_built_index_destroy(h)
+
+
 def _is_tensor(x):
     return torch is not None and isinstance(x, torch.Tensor)
 

@@ -112,3 +112,101 @@ def test_many_polygons_histogram(hostsim, ref):
     assert (got == want).all()
     off, ids = ri.containing_shapes(pts[:50000], 1)
     assert (hs_query(hostsim, flat, pts[:50000], 1, 4)[0] == np.diff(off.astype(np.int64))).all()
+
+
+# ---------------------------------------------------------------------------------------------------
+# The library's own host builder (s2b_index_build): query results over ITS index must equal the reference's.
+
+def own_flat(soup, max_edges=0):
+    from s2geometry_b200.index import build_flat_index
+    return build_flat_index(soup, max_edges)
+
+
+def check_index_invariants(flat, soup, ref):
+    """Structure checks in the spirit of the reference's QuadraticValidate/ValidateInterior
+    (mutable_s2shape_index_test.cc:127-229): sorted disjoint cells, sorted clips, and contains_center equal to the
+    reference's brute-force containment of the cell centre."""
+    lo, hi = ref.id_range(flat.cell_ids)
+    assert (lo[1:] > hi[:-1]).all()
+    assert (ref.to_point(flat.cell_ids) == flat.cell_center).all()
+    ri = ref.index_create(soup)
+    cell_of_clip = np.repeat(np.arange(flat.num_cells), np.diff(flat.cell_clip_begin.astype(np.int64)))
+    for c in range(flat.num_cells):
+        ids = flat.clip_shape_id[flat.cell_clip_begin[c]:flat.cell_clip_begin[c + 1]]
+        assert (np.diff(ids) > 0).all()
+    dims = soup.shape_dim
+    for s in range(flat.num_shape_ids):
+        if dims[s] != 2:
+            continue
+        want = ri.brute_force_contains(s, flat.cell_center, 1)
+        got = np.zeros(flat.num_cells, np.uint8)
+        sel = flat.clip_shape_id == s
+        got[cell_of_clip[sel]] = flat.clip_flags[sel] & 1
+        assert (got == want).all(), s
+
+
+def test_own_builder_truth_tables(hostsim, ref):
+    ka = scenes.known_answers()
+    soup = scenes.text_index(ka["index"])
+    flat = own_flat(soup)
+    q = scenes.latlng_deg_to_point(ka["queries"])
+    for name, m in scenes.MODELS.items():
+        assert (hs_query(hostsim, flat, q, m, 0)[0] == np.array(ka["contains"][name], np.uint8)).all(), name
+    for row in ka["shape_contains"]:
+        p = scenes.latlng_deg_to_point([row["q"]])
+        assert hs_query(hostsim, flat, p, scenes.MODELS[row["model"]], 1, row["shape"])[0][0] == row["expected"]
+    check_index_invariants(flat, soup, ref)
+
+
+def test_own_builder_loop_10k(hostsim, ref):
+    soup, v = scenes.loop_scene(10000)
+    flat = own_flat(soup)
+    ri = ref.index_create(soup)
+    rflat = flat_of(ri)
+    # comparable size to the reference's index (same subdivision rule, conservative edge lists)
+    assert 0.8 * rflat.num_cells <= flat.num_cells <= 1.3 * rflat.num_cells
+    assert flat.num_edges <= 1.3 * rflat.num_edges
+    check_index_invariants(flat, soup, ref)
+    u, b, d = scenes.loop_points(v, 200000, 200000, 33)
+    centers = flat.cell_center
+    for pts in (u, b, d, centers):
+        for m in (0, 1, 2):
+            assert (hs_query(hostsim, flat, pts, m, 0)[0] == ri.contains(pts, m)).all()
+
+
+def test_own_builder_axis_aligned_and_polygons(hostsim, ref):
+    soup = scenes.axis_aligned_scene()
+    flat = own_flat(soup)
+    check_index_invariants(flat, soup, ref)
+    ri = ref.index_create(soup)
+    q = scenes.axis_aligned_queries()
+    for m in (0, 1, 2):
+        assert (hs_query(hostsim, flat, q, m, 0)[0] == ri.contains(q, m, 1)).all()
+        assert (hs_query(hostsim, flat, q, m, 2)[0] == ri.shape_histogram(q, m, 1)).all()
+    # many polygons, some with holes, some overlapping, tiny max_edges_per_cell to force deep subdivision
+    from s2geometry_b200 import synth
+    soup2 = scenes.polygons_scene(300, 41, min_radius_km=200, max_radius_km=2000)
+    ri2 = ref.index_create(soup2)
+    pts = synth.sphere_points(300000, 43)
+    for max_edges in (0, 3):
+        flat2 = own_flat(soup2, max_edges)
+        assert (hs_query(hostsim, flat2, pts, 1, 2)[0] == ri2.shape_histogram(pts, 1)).all()
+    check_index_invariants(own_flat(soup2), soup2, ref)
+
+
+def test_own_builder_whole_face_and_full_polygon(hostsim, ref):
+    """A polygon larger than a hemisphere (contains whole cube faces) and its complement."""
+    from s2geometry_b200 import synth
+    from s2geometry_b200.shapes import ShapeSoup
+    small = synth.wobbly_loop([0.1, 0.2, 1.0], 0.3, 40)
+    soup = ShapeSoup()
+    soup.add_polygon([small[::-1].copy()])   # clockwise: everything EXCEPT the small cap
+    soup.add_polygon([small])
+    soup = soup.freeze()
+    flat = own_flat(soup)
+    check_index_invariants(flat, soup, ref)
+    ri = ref.index_create(soup)
+    pts = np.concatenate([synth.sphere_points(200000, 44), synth.cap_points([0.1, 0.2, 1.0], 0.4, 100000, 45), small])
+    assert (hs_query(hostsim, flat, pts, 1, 2)[0] == ri.shape_histogram(pts, 1)).all()
+    got, _ = hs_query(hostsim, flat, pts, 1, 4)
+    assert (got[: 300000] == 1).all()   # away from the boundary every point is in exactly one of the two

@@ -176,3 +176,30 @@ def test_full_size_properties_config3(torch_cuda, ref):
     assert bool((o <= inside).all()) and bool((inside <= c).all())
     sample = pts[:4_000_000].cpu().numpy()
     assert (inside[:4_000_000].cpu().numpy() == ri.contains(sample, 1)).all()
+
+
+def test_own_builder_index_on_gpu(torch_cuda, ref):
+    """Index built by the library's own host builder (no reference involved in the product path) -> same answers
+    as the reference's S2ContainsPointQuery over the reference-built index."""
+    from s2geometry_b200 import synth
+    from s2geometry_b200.index import ContainsPointQuery, ShapeIndex, build_flat_index
+    soup, v = scenes.loop_scene(10000)
+    ix = ShapeIndex(build_flat_index(soup))
+    ri = ref.index_create(soup)
+    u, b, d = scenes.loop_points(v, 1_000_000, 1_000_000, 13)
+    for pts in (u, b, d):
+        for m in (0, 1, 2):
+            assert (ContainsPointQuery(ix, m).contains(pts) == ri.contains(pts, m)).all()
+    soup2 = scenes.polygons_scene(3000, 51, min_radius_km=100, max_radius_km=1500)
+    ix2 = ShapeIndex(build_flat_index(soup2))
+    ri2 = ref.index_create(soup2)
+    pts = synth.sphere_points(3_000_000, 52)
+    want = ri2.shape_histogram(pts, 1)
+    assert want.sum() > 100000
+    assert (ContainsPointQuery(ix2, 1).shape_histogram(pts) == want).all()
+    soup3 = scenes.axis_aligned_scene()
+    ix3 = ShapeIndex(build_flat_index(soup3))
+    ri3 = ref.index_create(soup3)
+    q = scenes.axis_aligned_queries()
+    for m in (0, 1, 2):
+        assert (ContainsPointQuery(ix3, m).shape_histogram(q) == ri3.shape_histogram(q, m, 1)).all()
