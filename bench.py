@@ -227,6 +227,110 @@ def pip_section(args, torch, dev, rank, world):
     return out
 
 
+def join_section(args, torch, dev, rank, world):
+    """BASELINE configs[3]: spatial join, `join_points` uniform points (default 1B, sharded over the ranks: strong
+    scaling) vs 10k synthetic polygons -> per-polygon hit counts; the only collective is the NCCL all-reduce of the
+    uint64[10000] histogram. Index built by the library's own host builder and replicated on every GPU."""
+    from s2geometry_b200 import dist as sdist, synth
+    from s2geometry_b200.index import ContainsPointQuery, ShapeIndex, build_flat_index
+    from s2geometry_b200.shapes import ShapeSoup
+    soup = ShapeSoup()
+    for loops in synth.many_polygons(10000, 4):
+        soup.add_polygon(loops)
+    soup = soup.freeze()
+    t0 = time.perf_counter()
+    flat = build_flat_index(soup)
+    build_s = time.perf_counter() - t0
+    ix = ShapeIndex(flat)
+    query = ContainsPointQuery(ix, 1)
+    n_total = args.join_points
+    lo, hi = sdist.shard_range(n_total, rank, world)
+    n = hi - lo
+    pts = synth.sphere_points_cuda(n, 1000 + rank, dev)
+    counts = torch.zeros(flat.num_shape_ids, dtype=torch.int64, device=dev)
+
+    def step():
+        counts.zero_()
+        query.shape_histogram(pts, counts=counts)
+        sdist.all_reduce_sum_(counts)
+
+    for _ in range(3):
+        step()
+    sdist.barrier(); torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record(); sdist.barrier(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
+    sdist.all_reduce_max_(t)
+    ms = float(t.item())
+    hbm_peak, _ = peaks()
+    ach = 24 * n_total / world / (ms * 1e-3) / 1e9   # per-GPU algorithmic bytes over the step time
+    out = {"workload": "configs[3]: %d uniform points (sharded over %d GPU(s)) vs 10k polygons (%d vertices; index %d cells, %d clipped edges, %.1f MB on device), per-polygon counts + all-reduce"
+                       % (n_total, world, len(soup.vertices), flat.num_cells, flat.num_edges, ix.info()["device_bytes"] / 1e6),
+           "scaling": "strong", "points_per_s": n_total / (ms * 1e-3), "ms_per_step": ms, "index_build_s": build_s,
+           "total_hits": int(counts.sum().item()), "bytes_per_point": 24,
+           "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "note": "per GPU"}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import reflib  # cpu_baseline leg
+            ref = reflib.load()
+            t0 = time.perf_counter(); ri = ref.index_create(soup); ref_build_s = time.perf_counter() - t0
+            threads = ref.hardware_threads()
+            sample = pts[:20_000_000].cpu().numpy()
+            best = 1e30
+            for _ in range(2):
+                t0 = time.perf_counter(); want = ri.shape_histogram(sample, 1, threads); best = min(best, time.perf_counter() - t0)
+            got = query.shape_histogram(pts[:20_000_000]).cpu().numpy().view(np.uint64)
+            out["cpu_baseline"] = {"value": len(sample) / best, "unit": "points/s", "cores": threads, "kind": "reference",
+                                   "sample": "first 20M points, VisitContainingShapeIds histogram, best of 2", "index_build_s": ref_build_s,
+                                   "parity_on_sample": bool((got == want).all())}
+        except Exception as e:
+            out["cpu_baseline"] = {"unavailable": str(e)}
+    del pts
+    # ---- configs[4]: S2CellUnion containment (<= 1000 cells) of the same number of points, global hit count
+    from s2geometry_b200.index import cell_union_contains
+    loop = synth.wobbly_loop(np.array([0.3, -0.5, 0.8]), 0.17, 10000)
+    lsoup = ShapeSoup(); lsoup.add_polygon([loop])
+    union_ids = build_flat_index(lsoup.freeze(), 32).cell_ids      # covering of the loop: interior + boundary cells
+    d_ids = torch.from_numpy(union_ids.view(np.int64)).to(dev)
+    pts = synth.sphere_points_cuda(n, 2000 + rank, dev)
+    res = None
+
+    def ustep():
+        nonlocal res
+        res = cell_union_contains(d_ids, pts)
+        return sdist.sharded_count(0, dev)   # scalar all-reduce inside the step (the hit count is reduced after timing)
+
+    for _ in range(3):
+        ustep()
+    sdist.barrier(); torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        ustep()
+    e1.record(); sdist.barrier(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
+    sdist.all_reduce_max_(t)
+    ums = float(t.item())
+    hits = sdist.sharded_count(int(res.sum().item()), dev)
+    uach = 25 * n_total / world / (ums * 1e-3) / 1e9
+    cu = {"workload": "configs[4]: S2CellUnion (%d cells) containment of %d uniform points over %d GPU(s)" % (len(union_ids), n_total, world),
+          "scaling": "strong", "points_per_s": n_total / (ums * 1e-3), "ms_per_step": ums, "hits": hits, "bytes_per_point": 25,
+          "roofline": {"bound": "hbm", "achieved": uach, "peak": hbm_peak, "unit": "GB/s", "frac": uach / hbm_peak, "note": "per GPU"}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import reflib  # cpu_baseline leg
+            ref = reflib.load()
+            sample = pts[:20_000_000].cpu().numpy()
+            t0 = time.perf_counter(); want = ref.cellunion_contains(union_ids, sample, ref.hardware_threads()); dt = time.perf_counter() - t0
+            cu["cpu_baseline"] = {"value": len(sample) / dt, "unit": "points/s", "cores": ref.hardware_threads(), "kind": "reference",
+                                  "sample": "first 20M points", "parity_on_sample": bool((res[:20_000_000].cpu().numpy() == want).all())}
+        except Exception as e:
+            cu["cpu_baseline"] = {"unavailable": str(e)}
+    return out, cu
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -312,6 +416,13 @@ def run_gpu(args):
             pip = pip_section(args, torch, dev, rank, world)
         except Exception as e:
             pip = {"error": repr(e)}
+    join = cellunion = None
+    if not args.no_join:
+        try:
+            torch.cuda.empty_cache()
+            join, cellunion = join_section(args, torch, dev, rank, world)
+        except Exception as e:
+            join = {"error": repr(e)}
     if rank == 0:
         hbm_peak, peak_src = peaks()
         kern_ms = float(np.mean(per_launch_ms))
@@ -338,6 +449,10 @@ def run_gpu(args):
         }
         if pip is not None:
             line["pip"] = pip
+        if join is not None:
+            line["join"] = join
+        if cellunion is not None:
+            line["cellunion"] = cellunion
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline()
@@ -358,6 +473,8 @@ def main():
     ap.add_argument("--points", type=int, default=N_POINTS, help="points per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pip", action="store_true", help="skip the secondary point-in-polygon (configs[2]) measurements")
+    ap.add_argument("--no-join", action="store_true", help="skip the spatial-join (configs[3]) and cell-union (configs[4]) measurements")
+    ap.add_argument("--join-points", type=int, default=1_000_000_000, help="TOTAL points of the join / cell-union sections (sharded over ranks)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

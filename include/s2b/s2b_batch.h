@@ -1,0 +1,145 @@
+// s2b_batch.h — header-only C++ sugar over the C ABI (s2b_capi.h) that keeps the reference's names for the hot path.
+//
+// The reference (google/s2geometry) exposes this path as per-point C++ calls:
+//   S2CellId(const S2Point&), S2CellId(const S2LatLng&)        src/s2/s2cell_id.h:106-128
+//   S2CellId::parent(level), S2CellId::ToToken()               src/s2/s2cell_id.h:662-668, s2cell_id.cc:217-233
+//   S2ContainsPointQuery<Index>::Contains / ShapeContains / VisitContainingShapeIds / GetContainingShapeIds
+//                                                              src/s2/s2contains_point_query.h:92-186
+//   S2CellUnion::Contains(const S2Point&)                      src/s2/s2cell_union.cc:564-566
+// The batch forms below take spans of the same value types (layout compatible: S2Point = 3 doubles, S2CellId = one
+// uint64, S2LatLng = 2 doubles in radians) and run on the GPU. Errors: the reference's path has no error returns
+// (DCHECK only); here every call returns false on failure and s2b::LastError() explains (no exceptions).
+// INTEGRATION.md shows how these map onto static members added to the reference's own classes.
+#ifndef S2B_BATCH_H_
+#define S2B_BATCH_H_
+
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../s2b_capi.h"
+
+namespace s2b {
+
+struct Point { double x, y, z; };          // == S2Point (Vector3<double>, s2point.h:35)
+struct LatLng { double lat_rad, lng_rad; }; // == S2LatLng's R2Point of radians (s2latlng.h:47-60)
+static_assert(sizeof(Point) == 24 && sizeof(LatLng) == 16, "layout must match the reference value types");
+
+enum class S2VertexModel { OPEN = S2B_VERTEX_MODEL_OPEN, SEMI_OPEN = S2B_VERTEX_MODEL_SEMI_OPEN, CLOSED = S2B_VERTEX_MODEL_CLOSED };
+
+inline const char* LastError() { return s2b_last_error(); }
+
+// ---- S2CellId batch constructors and accessors -------------------------------------------------------------
+struct S2CellIdBatch {
+  // ids[i] = S2CellId(points[i]).parent(level).id()   (level 30 = leaf)
+  static bool FromPoints(const Point* points, size_t n, uint64_t* ids, int level = 30) {
+    return s2b_encode_points(&points->x, n, level, ids) == S2B_OK;
+  }
+  static bool FromPoints(const std::vector<Point>& points, std::vector<uint64_t>* ids, int level = 30) {
+    ids->resize(points.size());
+    return FromPoints(points.data(), points.size(), ids->data(), level);
+  }
+  // ids[i] = S2CellId(S2LatLng::FromRadians(lat, lng)).parent(level).id()
+  static bool FromLatLngs(const LatLng* ll, size_t n, uint64_t* ids, int level = 30, uint8_t* boundary_flags = nullptr) {
+    return s2b_encode_latlng(&ll->lat_rad, n, level, ids, boundary_flags) == S2B_OK;
+  }
+  // S2LatLng::FromE7 pairs
+  static bool FromE7(const int32_t* lat_lng_e7, size_t n, uint64_t* ids, int level = 30) {
+    return s2b_encode_latlng_e7(lat_lng_e7, n, level, ids, nullptr) == S2B_OK;
+  }
+  static bool Parent(const uint64_t* ids, size_t n, int level, uint64_t* out) { return s2b_cellid_parent(ids, n, level, out) == S2B_OK; }
+  // tokens: n fixed 16-byte slots, NUL padded (S2CellId::ToToken)
+  static bool ToTokens(const uint64_t* ids, size_t n, char* tokens16, uint8_t* lengths = nullptr) {
+    return s2b_cellid_to_token(ids, n, tokens16, lengths) == S2B_OK;
+  }
+  static std::vector<std::string> ToTokens(const std::vector<uint64_t>& ids) {
+    std::vector<char> buf(16 * ids.size());
+    std::vector<uint8_t> len(ids.size());
+    std::vector<std::string> out;
+    if (!ToTokens(ids.data(), ids.size(), buf.data(), len.data())) return out;
+    out.reserve(ids.size());
+    for (size_t i = 0; i < ids.size(); ++i) out.emplace_back(buf.data() + 16 * i, len[i]);
+    return out;
+  }
+};
+
+// ---- A shape index resident on the current CUDA device ------------------------------------------------------
+// Owns the device replica. Construct from an S2bFlatIndex (a reference-built MutableS2ShapeIndex walked through its
+// iterator — see INTEGRATION.md — or the result of s2b_index_build).
+class DeviceShapeIndex {
+ public:
+  DeviceShapeIndex() = default;
+  explicit DeviceShapeIndex(const S2bFlatIndex& flat) { Init(flat); }
+  DeviceShapeIndex(const DeviceShapeIndex&) = delete;
+  DeviceShapeIndex& operator=(const DeviceShapeIndex&) = delete;
+  DeviceShapeIndex(DeviceShapeIndex&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+  ~DeviceShapeIndex() { s2b_index_destroy(h_); }
+  bool Init(const S2bFlatIndex& flat) {
+    s2b_index_destroy(h_);
+    h_ = nullptr;
+    return s2b_index_create(&flat, &h_) == S2B_OK;
+  }
+  // Builds the index from shapes with the library's own host builder (no reference library involved).
+  bool InitFromShapes(int num_shapes, const int8_t* shape_dim, const uint32_t* shape_chain_begin,
+                      const uint32_t* chain_vertex_begin, const double* vertices, int max_edges_per_cell = 0) {
+    S2bBuiltIndex* built = nullptr;
+    if (s2b_index_build(num_shapes, shape_dim, shape_chain_begin, chain_vertex_begin, vertices, max_edges_per_cell, &built) != S2B_OK) return false;
+    S2bFlatIndex flat;
+    bool ok = s2b_built_index_flat(built, &flat, nullptr) == S2B_OK && Init(flat);
+    s2b_built_index_destroy(built);
+    return ok;
+  }
+  bool ok() const { return h_ != nullptr; }
+  int num_shape_ids() const { int32_t s = 0; if (h_) s2b_index_info(h_, nullptr, nullptr, nullptr, &s, nullptr); return s; }
+  const S2bIndex* handle() const { return h_; }
+
+ private:
+  S2bIndex* h_ = nullptr;
+};
+
+// ---- S2ContainsPointQuery, batch form -------------------------------------------------------------------------
+class S2ContainsPointQueryBatch {
+ public:
+  explicit S2ContainsPointQueryBatch(const DeviceShapeIndex* index, S2VertexModel model = S2VertexModel::SEMI_OPEN)
+      : index_(index), model_((int)model) {}
+  // out[i] = Contains(points[i])
+  bool Contains(const Point* points, size_t n, uint8_t* out) const { return s2b_contains(index_->handle(), &points->x, n, model_, out) == S2B_OK; }
+  // out[i] = ShapeContains(shape_id, points[i])
+  bool ShapeContains(int shape_id, const Point* points, size_t n, uint8_t* out) const {
+    return s2b_shape_contains(index_->handle(), shape_id, &points->x, n, model_, out) == S2B_OK;
+  }
+  // counts[s] = |{ i : shape s contains points[i] }|  — VisitContainingShapeIds accumulated per shape (spatial join)
+  bool CountContainingShapes(const Point* points, size_t n, std::vector<uint64_t>* counts) const {
+    counts->assign((size_t)index_->num_shape_ids(), 0);
+    return s2b_shape_histogram(index_->handle(), &points->x, n, model_, counts->data()) == S2B_OK;
+  }
+  // GetContainingShapeIds for every point, CSR: ids of point i are shape_ids[offsets[i] .. offsets[i+1])
+  bool GetContainingShapeIds(const Point* points, size_t n, std::vector<uint32_t>* offsets, std::vector<int32_t>* shape_ids) const {
+    offsets->resize(n + 1);
+    shape_ids->resize(n / 8 + 1024);
+    size_t total = 0;
+    int rc = s2b_containing_shapes(index_->handle(), &points->x, n, model_, offsets->data(), shape_ids->data(), shape_ids->size(), &total);
+    if (rc == S2B_ECAPACITY && total > shape_ids->size()) {
+      shape_ids->resize(total);
+      rc = s2b_containing_shapes(index_->handle(), &points->x, n, model_, offsets->data(), shape_ids->data(), shape_ids->size(), &total);
+    }
+    if (rc != S2B_OK) return false;
+    shape_ids->resize(total);
+    return true;
+  }
+
+ private:
+  const DeviceShapeIndex* index_;
+  int model_;
+};
+
+// ---- S2CellUnion::Contains(S2Point), batch form ------------------------------------------------------------------
+// cell_ids = S2CellUnion::cell_ids() (sorted, non-overlapping).
+inline bool S2CellUnionContainsBatch(const uint64_t* cell_ids, size_t num_cells, const Point* points, size_t n, uint8_t* out) {
+  return s2b_cellunion_contains(cell_ids, num_cells, &points->x, n, out) == S2B_OK;
+}
+
+}  // namespace s2b
+
+#endif  // S2B_BATCH_H_

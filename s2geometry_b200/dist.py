@@ -1,0 +1,77 @@
+"""Multi-GPU driver for the point workloads: one process per GPU (torch.distributed), points sharded by contiguous
+range, the index / cell union replicated on every GPU, and NCCL used ONLY where the path has a real exchange step:
+the all-reduce of the per-shape hit histogram (uint64[num_shape_ids], 80 KB for 10k polygons) and of scalar hit
+counts. The reference has no multi-device path; every point is independent, so there is no halo,
+shuffle or index sharding.
+"""
+import os
+
+import numpy as np
+
+try:
+    import torch
+    import torch.distributed as dist
+except Exception:  # pragma: no cover
+    torch = None
+    dist = None
+
+
+def env_rank_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def init(backend=None):
+    """Initialises torch.distributed from the torchrun environment (no-op for a single process).
+    Returns (rank, world, device). backend defaults to nccl when CUDA is available, else gloo (CPU tests)."""
+    rank, world, local_rank = env_rank_world()
+    cuda = torch is not None and torch.cuda.is_available()
+    device = torch.device("cuda", local_rank) if cuda else torch.device("cpu")
+    if cuda:
+        torch.cuda.set_device(local_rank)
+    if world > 1 and not dist.is_initialized():
+        backend = backend or ("nccl" if cuda else "gloo")
+        if backend == "nccl":
+            dist.init_process_group(backend, device_id=device)
+        else:
+            dist.init_process_group(backend)
+    return rank, world, device
+
+
+def shard_range(n, rank, world):
+    """Contiguous range [lo, hi) of n units owned by `rank`; ranges partition [0, n) and differ in size by at most 1."""
+    base, rem = divmod(int(n), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def all_reduce_sum_(t):
+    """In-place SUM all-reduce (no-op for a single process). int64 holds the uint64 counts (sums stay < 2^63)."""
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def all_reduce_max_(t):
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t
+
+
+def barrier():
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()
+
+
+def sharded_shape_histogram(local_histogram_fn, num_shape_ids, device):
+    """Spatial join across ranks: local_histogram_fn(counts) accumulates this rank's shard into the int64 tensor
+    `counts` (on the GPU: ContainsPointQuery.shape_histogram(points_shard, counts=counts)); the per-shape counts are
+    then summed over ranks. Every rank returns the global histogram."""
+    counts = torch.zeros(int(num_shape_ids), dtype=torch.int64, device=device)
+    local_histogram_fn(counts)
+    return all_reduce_sum_(counts)
+
+
+def sharded_count(local_count, device):
+    """Global number of hits given this rank's local count (e.g. S2CellUnion containment over a shard)."""
+    t = torch.tensor([int(local_count)], dtype=torch.int64, device=device)
+    return int(all_reduce_sum_(t).item())
