@@ -45,7 +45,7 @@ __device__ __forceinline__ int level_at(const LevelSpec& l, int k) {
 }
 
 template <int kKind>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 6)
 encode_kernel(const void* __restrict__ in, size_t n, const EncodeOut o) {
   __shared__ uint16_t s_pos[1024];
   __shared__ double s_sc[kKind == kInXYZ ? 1 : sc_tab::kTableSize][4];
@@ -55,8 +55,13 @@ encode_kernel(const void* __restrict__ in, size_t n, const EncodeOut o) {
   }
   __syncthreads();
 
+  // Warp-uniform trip count + __syncwarp() at the end of every iteration: lanes that took a rare path (double-double
+  // sin/cos, division/sqrt slow paths) rejoin their warp instead of running the rest of the loop on their own.
   const size_t stride = (size_t)gridDim.x * kThreads;
-  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+  const unsigned lane = threadIdx.x & 31u;
+  for (size_t base = (size_t)blockIdx.x * kThreads + (threadIdx.x & ~31u); base < n; base += stride, __syncwarp()) {
+    const size_t i = base + lane;
+    if (i >= n) continue;
     P3 p;
     if (kKind == kInXYZ) {
       const double* q = (const double*)in + 3 * i;

@@ -37,8 +37,13 @@ query_kernel(const FlatIndexView ix, const double* __restrict__ xyz, size_t n, i
   __shared__ uint16_t s_pos[1024];
   for (int k = threadIdx.x; k < 1024; k += kThreads) s_pos[k] = g_hilbert_ix.pos[k];
   __syncthreads();
+  // Warp-uniform trip count + __syncwarp() per iteration: the few lanes that land in an index cell (and the rarer
+  // ones in the exact stage) rejoin their warp before the next batch of 32 points instead of drifting apart for good.
   const size_t stride = (size_t)gridDim.x * kThreads;
-  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+  const unsigned lane = threadIdx.x & 31u;
+  for (size_t base = (size_t)blockIdx.x * kThreads + (threadIdx.x & ~31u); base < n; base += stride, __syncwarp()) {
+    const size_t i = base + lane;
+    if (i >= n) continue;
     const double* q = xyz + 3 * i;
     P3 p{__ldcs(q), __ldcs(q + 1), __ldcs(q + 2)};
     if (kMode == kModeAny) {
@@ -88,7 +93,10 @@ cellunion_kernel(const uint64_t* __restrict__ ids, uint32_t m, const double* __r
   __syncthreads();
   const uint64_t* tab = in_smem ? s_ids : ids;
   const size_t stride = (size_t)gridDim.x * kThreads;
-  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+  const unsigned lane = threadIdx.x & 31u;
+  for (size_t base = (size_t)blockIdx.x * kThreads + (threadIdx.x & ~31u); base < n; base += stride, __syncwarp()) {
+    const size_t i = base + lane;
+    if (i >= n) continue;
     const double* q = xyz + 3 * i;
     P3 p{__ldcs(q), __ldcs(q + 1), __ldcs(q + 2)};
     uint64_t leaf = cellid_from_point(p, s_pos);

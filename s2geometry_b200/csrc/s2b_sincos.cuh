@@ -156,9 +156,10 @@ S2B_HD SinCos sincos_cr(double x, const double (*tab)[4], int* n_slow = nullptr)
     return out;
   }
   if (ax < 0x1p-27) { out.s = x; out.c = 1.0; return out; }  // |x^2/6| < 2^-56: RN(sin x) = x, RN(cos x) = 1
-  double rh = x, rl = 0.0;
-  int k = 0;
-  if (ax > sc_tab::kPio4Hi) k = reduce_pio2(x, rh, rl);
+  // Always reduce: for |x| <= pi/4 the multiple is 0 and every step below is exact (rh = x, rl = 0), so the common
+  // path has no data-dependent branch (lat is mostly below pi/4, lng mostly above: a branch here splits every warp).
+  double rh, rl;
+  int k = reduce_pio2(x, rh, rl);
   bool negr = rh < 0;
   double ah = negr ? -rh : rh, al = negr ? -rl : rl;
   double sh, sl, ch, cl;
