@@ -49,6 +49,11 @@ uint64_t s2b_launch_count(void);
  * register-resident DFMA chain. It is the FP64 roofline denominator bench.py reports next to the HBM one. */
 int s2b_diag_fp64_peak(double* dfma_per_second_out);
 
+/* Diagnostic: the lat/lng encoders evaluate sin/cos with a fast bounded-error routine and re-evaluate with the
+ * correctly rounded one only where the leaf cell could depend on the difference. on != 0 makes every
+ * point take the correctly rounded routine, which must give identical ids (tests check it). Returns the old setting. */
+int s2b_diag_force_correctly_rounded(int on);
+
 /* ------------------------------------------------------------------------------------------------
  * Cell-id encoding.  Replaces the per-point constructors
  *   S2CellId::S2CellId(const S2Point&)   s2cell_id.cc:309-315  (XYZtoFaceUV s2coords.h:389-419,

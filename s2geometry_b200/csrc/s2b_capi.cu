@@ -16,6 +16,7 @@ namespace s2b {
 
 static thread_local char t_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_force_cr{0};
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
@@ -172,6 +173,7 @@ static int encode_host(InputKind kind, const void* in, size_t in_bpp, size_t n, 
     o.token_level_index = tok_level_index;
     o.tokens16 = tok_level_index >= 0 ? (char*)out_dev[2] : nullptr;
     o.token_len = tok_level_index >= 0 && tok_len_out ? (uint8_t*)out_dev[3] : nullptr;
+    o.force_cr = g_force_cr.load();
     cudaError_t e = launch_encode(kind, in_dev, cnt, o, st);
     return e == cudaSuccess ? S2B_OK : cuda_fail(e, "encode launch");
   });
@@ -196,6 +198,7 @@ static int encode_dev(InputKind kind, const void* in, size_t n, const int* level
   o.token_level_index = tok_level_index;
   o.tokens16 = tok_out;
   o.token_len = tok_len_out;
+  o.force_cr = g_force_cr.load();
   cudaError_t e = launch_encode(kind, in, n, o, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "encode launch");
   return S2B_OK;
@@ -215,6 +218,7 @@ int s2b_device_count(void) {
   return n;
 }
 uint64_t s2b_launch_count(void) { return g_launches.load(); }
+int s2b_diag_force_correctly_rounded(int on) { return g_force_cr.exchange(on ? 1 : 0); }
 
 int s2b_encode_points(const double* xyz, size_t n, int level, uint64_t* ids_out) {
   return encode_host(kInXYZ, xyz, 24, n, &level, 1, ids_out, nullptr);

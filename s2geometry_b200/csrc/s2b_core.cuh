@@ -103,6 +103,21 @@ S2B_HD uint64_t from_face_ij(int face, uint32_t i, uint32_t j, const TableT* pos
   return n * 2 + 1;
 }
 
+// The projection half of S2CellId(S2Point): face and the UNTRUNCATED leaf coordinates fi = 2^30 * s, fj = 2^30 * t.
+S2B_HD int point_to_face_fij(const P3& p, double* fi, double* fj) {
+  double u, v;
+  int face = xyz_to_face_uv(p, &u, &v);
+  *fi = 1073741824.0 * uv_to_st(u);
+  *fj = 1073741824.0 * uv_to_st(v);
+  return face;
+}
+// STtoIJ applied to fi = 2^30 * s (s2coords.h:345-356): s > 0 <=> fi > 0; NaN -> 0.
+S2B_HD uint32_t fij_to_ij(double f) {
+  if (!(f > 0)) return 0;
+  int v = (int)f;
+  return (uint32_t)(v < 1073741823 ? v : 1073741823);
+}
+
 // S2CellId(const S2Point&) (s2cell_id.cc:309-315).
 template <class TableT>
 S2B_HD uint64_t cellid_from_point(const P3& p, const TableT* pos) {

@@ -23,22 +23,6 @@ static_assert(sc_tab::kTableSize == 105, "table rows are spelled out above");
 
 constexpr int kThreads = 256;
 
-// Conservative "the leaf cell could change if sin/cos were off by one ulp" test (s2b_capi.h, boundary_flag_out).
-// Four trig results each off by <= 1 ulp perturb x,y,z by <= 3 ulp relative, u,v by <= 7 ulp, s,t by <= 2e-15
-// absolute, i.e. <= 2.2e-6 in units of leaf cells; the face choice changes only if two |components| are within 4 ulp.
-__device__ __forceinline__ bool boundary_sensitive(const P3& p) {
-  double ax = fabs(p.x), ay = fabs(p.y), az = fabs(p.z);
-  double hi = fmax(ax, fmax(ay, az));
-  double mid = fmax(fmin(ax, ay), fmin(fmax(ax, ay), az));
-  if (hi - mid <= hi * 0x1p-50) return true;
-  double u, v;
-  xyz_to_face_uv(p, &u, &v);
-  double fi = 1073741824.0 * uv_to_st(u), fj = 1073741824.0 * uv_to_st(v);
-  const double tol = 4e-6;
-  double di = fi - floor(fi), dj = fj - floor(fj);
-  return di < tol || di > 1 - tol || dj < tol || dj > 1 - tol;
-}
-
 // levels live in kernel parameter space; a switch keeps them out of local memory (dynamic indexing would copy them).
 __device__ __forceinline__ int level_at(const LevelSpec& l, int k) {
   return k == 0 ? l.level[0] : (k == 1 ? l.level[1] : (k == 2 ? l.level[2] : l.level[3]));
@@ -63,6 +47,9 @@ encode_kernel(const void* __restrict__ in, size_t n, const EncodeOut o) {
     const size_t i = base + lane;
     if (i >= n) continue;
     P3 p;
+    double fi, fj;
+    int face;
+    bool sensitive = false;
     if (kKind == kInXYZ) {
       const double* q = (const double*)in + 3 * i;
       p.x = __ldcs(q); p.y = __ldcs(q + 1); p.z = __ldcs(q + 2);
@@ -77,9 +64,10 @@ encode_kernel(const void* __restrict__ in, size_t n, const EncodeOut o) {
         lat = (M_PI / 180) * (1e-7 * (double)e7.x);
         lng = (M_PI / 180) * (1e-7 * (double)e7.y);
       }
-      p = latlng_to_point(lat, lng, s_sc);
+      face = latlng_to_face_fij(lat, lng, s_sc, o.force_cr != 0, &p, &fi, &fj, &sensitive);
     }
-    const uint64_t id = cellid_from_point(p, s_pos);
+    if (kKind == kInXYZ) face = point_to_face_fij(p, &fi, &fj);
+    const uint64_t id = from_face_ij(face, fij_to_ij(fi), fij_to_ij(fj), s_pos);
     for (int k = 0; k < o.levels.n; ++k) {  // uniform trip count
       int L = level_at(o.levels, k);
       __stcs(o.ids + (size_t)k * n + i, L < 30 ? cellid_parent(id, L) : id);
@@ -91,7 +79,7 @@ encode_kernel(const void* __restrict__ in, size_t n, const EncodeOut o) {
       __stcs((ulonglong2*)o.tokens16 + i, make_ulonglong2(w[0], w[1]));
       if (o.token_len) o.token_len[i] = (uint8_t)len;
     }
-    if (o.flags) o.flags[i] = boundary_sensitive(p) ? 1 : 0;
+    if (o.flags) o.flags[i] = (kKind == kInXYZ || sensitive) && near_cell_boundary(p, fi, fj, kFlagTolIj, kFlagTolFace) ? 1 : 0;
   }
 }
 

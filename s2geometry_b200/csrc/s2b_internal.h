@@ -17,6 +17,7 @@ struct EncodeOut {
   int token_level_index;  // -1: no tokens
   char* tokens16;       // nullable unless token_level_index >= 0
   uint8_t* token_len;   // nullable
+  int force_cr = 0;     // diagnostics: 1 = always use the correctly rounded sin/cos (skip the fast filter)
 };
 
 enum InputKind { kInXYZ = 0, kInLatLngRad = 1, kInLatLngE7 = 2 };

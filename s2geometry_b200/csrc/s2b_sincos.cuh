@@ -183,11 +183,94 @@ S2B_HD SinCos sincos_cr(double x, const double (*tab)[4], int* n_slow = nullptr)
   return out;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fast sin/cos with a PROVEN-SMALL absolute error, used by the encoder as a filter in front of sincos_cr: the cell id
+// computed from these values is identical to the one computed from correctly rounded values unless the point is
+// within kIjTolerance of a leaf-cell boundary (or two |components| nearly tie for the face), and exactly those points
+// are re-evaluated with sincos_cr (s2b_encode.cu). So the ids are those of the correctly rounded definition, at a
+// third of the FP64 work.
+//   reduction: x - k*pi/2 with three Cody-Waite parts in plain double (error <= 0.5 ulp(r) + k*2^-120)
+//   sin(r), cos(r): Taylor through r^15 / r^16 on |r| <= pi/4 (truncation < 5e-17), Horner in r^2
+// Absolute error bound assumed by the encoder: kFastSinCosAbsErr = 4.5e-16 (about twice the measured maximum,
+// tests/test_encode_cpu.py::test_fast_sincos_error_bound).
+static constexpr double kFastSinCosAbsErr = 4.5e-16;
+
+S2B_HD SinCos sincos_fast(double x) {  // requires |x| < 2^20
+  using namespace sc_tab;
+  double kd = rint(x * kTwoOverPi);
+  double r = ((x - kd * kPio2_1) - kd * kPio2_2) - kd * kPio2_3;
+  double z = r * r;
+  double ps = -1.0 / 1307674368000.0;                       // -1/15!
+  ps = ps * z + 1.0 / 6227020800.0;                         // 1/13!
+  ps = ps * z - 1.0 / 39916800.0;                           // -1/11!
+  ps = ps * z + 1.0 / 362880.0;                             // 1/9!
+  ps = ps * z - 1.0 / 5040.0;
+  ps = ps * z + 1.0 / 120.0;
+  ps = ps * z - 1.0 / 6.0;
+  double sr = r + r * (z * ps);
+  double pc = 1.0 / 20922789888000.0;                       // 1/16!
+  pc = pc * z - 1.0 / 87178291200.0;                        // -1/14!
+  pc = pc * z + 1.0 / 479001600.0;                          // 1/12!
+  pc = pc * z - 1.0 / 3628800.0;
+  pc = pc * z + 1.0 / 40320.0;
+  pc = pc * z - 1.0 / 720.0;
+  pc = pc * z + 1.0 / 24.0;
+  double cr = 1.0 + (z * (z * pc) - 0.5 * z);
+  SinCos out;
+  switch ((int)kd & 3) {
+    case 0: out.s = sr; out.c = cr; break;
+    case 1: out.s = cr; out.c = -sr; break;
+    case 2: out.s = -sr; out.c = -cr; break;
+    default: out.s = -cr; out.c = sr; break;
+  }
+  return out;
+}
+
+S2B_HD P3 latlng_to_point_fast(double lat, double lng) {
+  SinCos phi = sincos_fast(lat);
+  SinCos theta = sincos_fast(lng);
+  return P3{theta.c * phi.c, theta.s * phi.c, phi.s};
+}
+
 // S2LatLng::ToPoint (s2latlng.cc:68-77): (cos(lng)*cos(lat), sin(lng)*cos(lat), sin(lat)).
 S2B_HD P3 latlng_to_point(double lat, double lng, const double (*tab)[4], int* n_slow = nullptr) {
   SinCos phi = sincos_cr(lat, tab, n_slow);
   SinCos theta = sincos_cr(lng, tab, n_slow);
   return P3{theta.c * phi.c, theta.s * phi.c, phi.s};
+}
+
+// Sensitivity of the leaf cell to small errors in p (s2b_capi.h boundary_flag_out, and the filter in front of the
+// correctly rounded sin/cos). With |error| <= e in each of the four sin/cos values: x,y are off by <= 2e + 1.2e-16,
+// z by <= e; u,v by <= (3e + 2.4e-16)/0.577 + 1.2e-16 (the major axis is >= 1/sqrt(3)); s,t by <= 0.75 of that + 2e-16;
+// i.e. in units of leaf cells (x 2^30):  e = 4.5e-16 (fast sin/cos) -> 3.1e-6 ;  e = 1.1e-16 (1 ulp) -> 1.1e-6.
+// The face can flip only if the two largest |components| are within ~4e of each other.
+S2B_HD bool near_cell_boundary(const P3& p, double fi, double fj, double tol_ij, double tol_face) {
+  double ax = fabs(p.x), ay = fabs(p.y), az = fabs(p.z);
+  double hi = fmax(ax, fmax(ay, az));
+  double mid = fmax(fmin(ax, ay), fmin(fmax(ax, ay), az));
+  double di = fi - floor(fi), dj = fj - floor(fj);
+  // written so that NaN inputs come out "true"
+  return !(hi - mid > tol_face) || !(di > tol_ij && di < 1 - tol_ij && dj > tol_ij && dj < 1 - tol_ij);
+}
+static constexpr double kFilterTolIj = 1.6e-5, kFilterTolFace = 1e-14;   // fast-path filter: 5x the 3.1e-6 bound
+static constexpr double kFlagTolIj = 4e-6, kFlagTolFace = 2e-15;         // user-visible flag: 1-ulp sin/cos changes, 3.5x margin
+
+// lat/lng -> (face, fi, fj) with the filter described above. *sensitive reports whether the correctly rounded path ran.
+S2B_HD int latlng_to_face_fij(double lat, double lng, const double (*tab)[4], bool force_cr, P3* p, double* fi, double* fj, bool* sensitive) {
+  int face = 0;
+  // out-of-domain angles (|x| >= 2^20, inf, NaN) always take the correctly-rounded path, which handles them
+  bool sens = !(fabs(lat) < 1048576.0 && fabs(lng) < 1048576.0) || force_cr;
+  if (!sens) {
+    *p = latlng_to_point_fast(lat, lng);
+    face = point_to_face_fij(*p, fi, fj);
+    sens = near_cell_boundary(*p, *fi, *fj, kFilterTolIj, kFilterTolFace);
+  }
+  if (sens) {
+    *p = latlng_to_point(lat, lng, tab);
+    face = point_to_face_fij(*p, fi, fj);
+  }
+  *sensitive = sens;
+  return face;
 }
 
 }  // namespace s2b

@@ -18,6 +18,24 @@ void hs_encode_points(const double* xyz, size_t n, int level, uint64_t* out) {
   }
 }
 
+// The kernel's lat/lng path: fast bounded-error sin/cos as a filter, correctly rounded sin/cos where it matters.
+// force_cr = 1: every point takes the correctly rounded path. n_sensitive counts points that took it.
+void hs_encode_latlng_filtered(const double* ll, size_t n, int level, int force_cr, uint64_t* out, uint64_t* n_sensitive) {
+  uint64_t ns = 0;
+  for (size_t i = 0; i < n; ++i) {
+    P3 p; double fi, fj; bool sens;
+    int face = latlng_to_face_fij(ll[2 * i], ll[2 * i + 1], sc_tab::kSinCosTable, force_cr != 0, &p, &fi, &fj, &sens);
+    ns += sens;
+    uint64_t id = from_face_ij(face, fij_to_ij(fi), fij_to_ij(fj), kHilbert.pos);
+    out[i] = level < 30 ? cellid_parent(id, level) : id;
+  }
+  if (n_sensitive) *n_sensitive = ns;
+}
+
+void hs_sincos_fast(const double* x, size_t n, double* s, double* c) {
+  for (size_t i = 0; i < n; ++i) { SinCos r = sincos_fast(x[i]); s[i] = r.s; c[i] = r.c; }
+}
+
 void hs_encode_latlng(const double* ll, size_t n, int level, uint64_t* out, uint64_t* n_slow) {
   int slow = 0;
   for (size_t i = 0; i < n; ++i) {

@@ -90,3 +90,82 @@ def test_sincos_correctly_rounded(hostsim):
         hostsim.hs_sincos(vp(x), ctypes.c_size_t(len(x)), mode, vp(s), vp(c), None)
         for i in range(len(x)):
             assert float(mp.sin(mp.mpf(x[i]))) == s[i] and float(mp.cos(mp.mpf(x[i]))) == c[i], (mode, x[i].hex())
+
+
+def test_fast_sincos_error_bound(hostsim):
+    """The filter in front of the correctly rounded sin/cos assumes |error| <= 4.5e-16 (kFastSinCosAbsErr)."""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.prec = 200
+    rng = np.random.default_rng(12)
+    x = np.concatenate([rng.uniform(-np.pi, np.pi, 40000), rng.uniform(-2000, 2000, 5000), rng.uniform(-1e6, 1e6, 3000),
+                        np.pi / 2 * np.arange(-8, 9), np.pi / 4 * np.arange(-9, 10) * (1 + 1e-16), [0.0, 1e-300, -1e-10]])
+    s = np.empty_like(x); c = np.empty_like(x)
+    hostsim.hs_sincos_fast(vp(x), ctypes.c_size_t(len(x)), vp(s), vp(c))
+    worst = 0.0
+    for i in range(len(x)):
+        worst = max(worst, abs(float(mp.sin(mp.mpf(x[i])) - mp.mpf(s[i]))), abs(float(mp.cos(mp.mpf(x[i])) - mp.mpf(c[i]))))
+    assert worst < 2.3e-16, worst     # half of the bound the encoder budgets for
+
+
+def boundary_latlngs(ref, n, seed):
+    """lat/lng pairs whose points sit on or within a few ulps of leaf-cell boundaries, face boundaries and cube corners."""
+    rng = np.random.default_rng(seed)
+    # vertices / edge points of cells at several levels: one or both of (i, j) integral at that level
+    out = []
+    for lvl in (30, 30, 24, 12, 3):
+        step = 1 << (30 - lvl)
+        i = rng.integers(0, (1 << lvl) + 1, n) * step
+        j = rng.integers(0, (1 << lvl) + 1, n) * step
+        frac = rng.uniform(0, step, n)
+        which = rng.integers(0, 3, n)                 # 0: vertex, 1: i on a boundary, 2: j on a boundary
+        fi = np.where(which == 2, np.minimum(i + frac, 2.0 ** 30), i).astype(np.float64)
+        fj = np.where(which == 1, np.minimum(j + frac, 2.0 ** 30), j).astype(np.float64)
+        s_, t_ = fi / 2.0 ** 30, fj / 2.0 ** 30
+        st2uv = lambda s: np.where(s >= 0.5, (1 / 3.) * (4 * s * s - 1), (1 / 3.) * (1 - 4 * (1 - s) * (1 - s)))
+        u, v = st2uv(s_), st2uv(t_)
+        face = rng.integers(0, 6, n)
+        one = np.ones(n)
+        xyz = np.select([(face == k)[:, None] for k in range(6)],
+                        [np.stack(c, 1) for c in ((one, u, v), (-u, one, v), (-u, -v, one), (-one, -v, -u), (v, -one, -u), (v, u, -one))])
+        xyz /= np.sqrt((xyz * xyz).sum(1))[:, None]
+        out.append(np.stack([np.arcsin(np.clip(xyz[:, 2], -1, 1)), np.arctan2(xyz[:, 1], xyz[:, 0])], axis=1))
+    ll = np.vstack(out)
+    # nudge by a few ulps in both coordinates
+    k = rng.integers(-3, 4, ll.shape)
+    ll2 = ll.copy()
+    for _ in range(3):
+        ll2 = np.where(k > 0, np.nextafter(ll2, np.inf), np.where(k < 0, np.nextafter(ll2, -np.inf), ll2))
+        k = k - np.sign(k)
+    # face boundaries: |x| = |y| (lng = +-45, +-135 deg) and cube-corner latitudes
+    t = rng.uniform(-1.2, 1.2, 4000)
+    fb = np.stack([t, rng.choice([np.pi / 4, -np.pi / 4, 3 * np.pi / 4, -3 * np.pi / 4], 4000)], axis=1)
+    c35 = np.arctan(1 / np.sqrt(2))
+    fc = np.stack([rng.choice([c35, -c35], 2000), rng.choice([np.pi / 4, -np.pi / 4, 3 * np.pi / 4], 2000)], axis=1)
+    axis = np.array([[0, 0], [0, np.pi / 2], [np.pi / 2, 0], [0, np.pi], [0, -np.pi / 2], [-np.pi / 2, 0], [0, -np.pi], [np.pi / 4, 0], [0, 1e-300]])
+    return np.ascontiguousarray(np.vstack([ll, ll2, fb, fc, axis]))
+
+
+def hs_filtered(hs, ll, force_cr, level=30):
+    out = np.empty(len(ll), np.uint64)
+    ns = ctypes.c_uint64(0)
+    hs.hs_encode_latlng_filtered(vp(ll), ctypes.c_size_t(len(ll)), level, force_cr, vp(out), ctypes.byref(ns))
+    return out, ns.value
+
+
+def test_filtered_ids_equal_correctly_rounded_ids(hostsim, ref):
+    from s2geometry_b200 import synth
+    ll = synth.sphere_latlng(2_000_000, 9)
+    fast, n_sens = hs_filtered(hostsim, ll, 0)
+    exact, n_all = hs_filtered(hostsim, ll, 1)
+    assert n_all == len(ll) and n_sens < 1e-3 * len(ll)       # ~6e-5 of points pay for the correctly rounded path
+    assert (fast == exact).all()
+    old, _ = util.hs_encode_latlng(hostsim, ll)               # the unfiltered implementation
+    assert (exact == old).all()
+    bl = boundary_latlngs(ref, 20000, 10)
+    fast, n_sens = hs_filtered(hostsim, bl, 0)
+    exact, _ = hs_filtered(hostsim, bl, 1)
+    assert n_sens > 0.2 * len(bl)                              # these inputs really are boundary cases
+    assert (fast == exact).all()
+    # and against the reference (glibc): any difference must be a boundary-sensitive point
+    want = ref.encode_latlng(bl, 30, 1)
+    assert (fast != want).mean() < 0.01

@@ -129,3 +129,30 @@ def test_full_size_properties(torch_cuda):
     # a sample compared id by id with the host path (different launch geometry, same kernel)
     sample = ll[:1_000_000].cpu().numpy()
     assert (cellid.from_lat_lng(sample).view(np.int64) == cellid.from_lat_lng(ll[:1_000_000]).cpu().numpy()).all()
+
+
+def test_fast_filter_equals_correctly_rounded_on_device(torch_cuda, ref):
+    """The production lat/lng path (fast sin/cos + correctly rounded re-evaluation of boundary-sensitive points) gives
+    exactly the ids of the all-correctly-rounded path: 100M uniform points + 400k points sitting on cell boundaries."""
+    torch = torch_cuda
+    from s2geometry_b200 import _lib, cellid, synth
+    from tests.test_encode_cpu import boundary_latlngs
+    lib = _lib.load()
+    ll = synth.sphere_latlng_cuda(100_000_000, 5, "cuda")
+    bl = torch.from_numpy(boundary_latlngs(ref, 20000, 10)).cuda()
+    try:
+        fast = cellid.from_lat_lng(ll, 30)
+        fast_b, flags_b = cellid.from_lat_lng(bl, 30, return_boundary_flags=True)
+        assert lib.s2b_diag_force_correctly_rounded(1) == 0
+        exact = cellid.from_lat_lng(ll, 30)
+        exact_b, flags_b2 = cellid.from_lat_lng(bl, 30, return_boundary_flags=True)
+    finally:
+        lib.s2b_diag_force_correctly_rounded(0)
+    assert bool((fast == exact).all())
+    assert bool((fast_b == exact_b).all()) and bool((flags_b == flags_b2).all())
+    assert float(flags_b.float().mean()) > 0.1
+    # host reference (glibc libm): differences only where the flag is set
+    want = ref.encode_latlng(bl.cpu().numpy(), 30)
+    got = fast_b.cpu().numpy().view(np.uint64)
+    bad = got != want
+    assert (flags_b.cpu().numpy()[bad] == 1).all()
