@@ -50,23 +50,21 @@ S2B_HD bool lex_less(const P3& a, const P3& b) {
 // ---------------------------------------------------------------------------------------------------
 // Cube-face projection: S2::XYZtoFaceUV (s2coords.h:389-419), quadratic UVtoST (:329-332), STtoIJ (:345-356).
 S2B_HD int xyz_to_face_uv(const P3& p, double* u, double* v) {
-  int face = largest_abs_component(p);
-  double m = comp(p, face);
-  if (m < 0) face += 3;
-  // ValidFaceXYZtoUV (s2coords.h:389-403) is, for every face, (+-numerator) / major axis: pick the operands, then
-  // issue exactly two IEEE divisions (the unary minus is applied to the numerator, as in the reference).
-  double nu, nv;
-  switch (face) {
-    case 0: nu =  p.y; nv =  p.z; break;
-    case 1: nu = -p.x; nv =  p.z; break;
-    case 2: nu = -p.x; nv = -p.y; break;
-    case 3: nu =  p.z; nv =  p.y; break;
-    case 4: nu =  p.z; nv = -p.x; break;
-    default: nu = -p.y; nv = -p.x; break;
-  }
-  *u = nu / m;
-  *v = nv / m;
-  return face;
+  // GetFace (s2coords.h:409-413) + ValidFaceXYZtoUV (:389-403), written with selects instead of a six-way switch:
+  //   face:  0: ( y/x,  z/x)  1: (-x/y,  z/y)  2: (-x/z, -y/z)  3: ( z/x,  y/x)  4: ( z/y, -x/y)  5: (-y/z, -x/z)
+  // i.e. the major axis m, and numerators chosen per axis, swapped and sign-adjusted for the negative faces.
+  // The unary minus is applied to the numerator, as in the reference; exactly two IEEE divisions are issued.
+  const double ax = fabs(p.x), ay = fabs(p.y), az = fabs(p.z);
+  const int axis = ax > ay ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
+  const double m = axis == 0 ? p.x : (axis == 1 ? p.y : p.z);
+  const bool neg = m < 0;
+  // positive faces: (a, b) = axis 0: (y, z), 1: (-x, z), 2: (-x, -y)
+  const double a = axis == 0 ? p.y : -p.x;
+  const double b = axis == 2 ? -p.y : p.z;
+  // negative faces: axis 0: (z, y) = (b, a); axis 1: (z, -x) = (b, a); axis 2: (-y, -x) = (b, a)
+  *u = (neg ? b : a) / m;
+  *v = (neg ? a : b) / m;
+  return axis + (neg ? 3 : 0);
 }
 S2B_HD double uv_to_st(double u) {
   // u >= 0 ? 0.5 * sqrt(1 + 3u) : 1 - 0.5 * sqrt(1 - 3u), with a single square root site.
@@ -184,17 +182,18 @@ S2B_HD uint64_t cellid_range_max(uint64_t id) { return id + (cellid_lsb(id) - 1)
 S2B_HD bool cellid_contains(uint64_t a, uint64_t b) { return b >= cellid_range_min(a) && b <= cellid_range_max(a); }
 
 // S2CellId::ToToken (s2cell_id.cc:217-233): the 16-digit lowercase hex of the id without its trailing '0'
-// digits ("X" for id 0), written as a fixed 16-byte slot (two little-endian words, NUL padded). Returns strlen.
-S2B_HD uint64_t hex8(uint32_t x) {  // 8 nibbles -> 8 ASCII bytes, most significant nibble in the lowest byte
-  uint64_t v = x;
-  v = (v | (v << 16)) & 0x0000FFFF0000FFFFull;
-  v = (v | (v << 8)) & 0x00FF00FF00FF00FFull;
-  v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0Full;   // byte b = nibble b
-  v = ((v & 0x00000000FFFFFFFFull) << 32) | (v >> 32);
-  v = ((v & 0x0000FFFF0000FFFFull) << 16) | ((v >> 16) & 0x0000FFFF0000FFFFull);
-  v = ((v & 0x00FF00FF00FF00FFull) << 8) | ((v >> 8) & 0x00FF00FF00FF00FFull);  // byte-reversed
-  uint64_t ge10 = ((v + 0x0606060606060606ull) >> 4) & 0x0101010101010101ull;
-  return v + 0x3030303030303030ull + ge10 * 39;  // '0'.. or 'a'.. ('a' - '0' - 10 = 39)
+// digits ("X" for id 0), written as a fixed 16-byte slot (four little-endian 32-bit words, NUL padded). Returns strlen.
+// Works on 16-bit chunks in 32-bit registers (64-bit SWAR costs twice the instructions on the GPU).
+S2B_HD uint32_t hex4(uint32_t x) {  // 4 nibbles (16 bits) -> 4 ASCII bytes, most significant nibble in the lowest byte
+  uint32_t v = (x | (x << 8)) & 0x00FF00FFu;
+  v = (v | (v << 4)) & 0x0F0F0F0Fu;                    // byte b = nibble b
+#if defined(__CUDA_ARCH__)
+  v = __byte_perm(v, 0, 0x0123);                       // reverse the bytes
+#else
+  v = (v >> 24) | ((v >> 8) & 0xFF00u) | ((v << 8) & 0xFF0000u) | (v << 24);
+#endif
+  uint32_t ge10 = ((v + 0x06060606u) >> 4) & 0x01010101u;
+  return v + 0x30303030u + ge10 * 39u;                 // '0'.. or 'a'.. ('a' - '0' - 10 = 39)
 }
 S2B_HD int ctz64(uint64_t v) {
 #if defined(__CUDA_ARCH__)
@@ -203,14 +202,18 @@ S2B_HD int ctz64(uint64_t v) {
   return __builtin_ctzll(v);
 #endif
 }
-S2B_HD int cellid_to_token(uint64_t id, uint64_t out[2]) {
-  if (id == 0) { out[0] = 0x58; out[1] = 0; return 1; }  // "X"
-  int len = 16 - (ctz64(id) >> 2);
-  uint64_t w0 = hex8((uint32_t)(id >> 32)), w1 = hex8((uint32_t)id);
-  if (len < 8) w0 &= (1ull << (8 * len)) - 1;
-  if (len <= 8) w1 = 0;
-  else if (len < 16) w1 &= (1ull << (8 * (len - 8))) - 1;
-  out[0] = w0; out[1] = w1;
+S2B_HD int cellid_to_token(uint64_t id, uint32_t out[4]) {
+  if (id == 0) { out[0] = 0x58; out[1] = out[2] = out[3] = 0; return 1; }  // "X"
+  const int len = 16 - (ctz64(id) >> 2);
+  const uint32_t hi = (uint32_t)(id >> 32), lo = (uint32_t)id;
+  uint32_t w[4] = {hex4(hi >> 16), hex4(hi & 0xFFFFu), hex4(lo >> 16), hex4(lo & 0xFFFFu)};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 4; ++k) {
+    int keep = len - 4 * k;                            // characters of word k that belong to the token
+    out[k] = keep >= 4 ? w[k] : (keep <= 0 ? 0u : (w[k] & ((1u << (8 * keep)) - 1u)));
+  }
   return len;
 }
 

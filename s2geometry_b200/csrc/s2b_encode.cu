@@ -68,18 +68,22 @@ encode_kernel(const void* __restrict__ in, size_t n, const EncodeOut o) {
     }
     if (kKind == kInXYZ) face = point_to_face_fij(p, &fi, &fj);
     const uint64_t id = from_face_ij(face, fij_to_ij(fi), fij_to_ij(fj), s_pos);
-    for (int k = 0; k < o.levels.n; ++k) {  // uniform trip count
-      int L = level_at(o.levels, k);
-      __stcs(o.ids + (size_t)k * n + i, L < 30 ? cellid_parent(id, L) : id);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < o.levels.n) {
+        // parent(level): (id & -lsb) | lsb; for level 30 lsb = 1 and the id (odd) is unchanged (s2cell_id.h:662-668)
+        const uint64_t lsb = lsb_for_level(level_at(o.levels, k));
+        __stcs(o.ids + (size_t)k * n + i, (id & (~lsb + 1)) | lsb);
+      }
     }
     if (o.token_level_index >= 0) {
       int L = level_at(o.levels, o.token_level_index);
-      uint64_t w[2];
+      uint32_t w[4];
       int len = cellid_to_token(L < 30 ? cellid_parent(id, L) : id, w);
-      __stcs((ulonglong2*)o.tokens16 + i, make_ulonglong2(w[0], w[1]));
+      __stcs((uint4*)o.tokens16 + i, make_uint4(w[0], w[1], w[2], w[3]));
       if (o.token_len) o.token_len[i] = (uint8_t)len;
     }
-    if (o.flags) o.flags[i] = (kKind == kInXYZ || sensitive) && near_cell_boundary(p, fi, fj, kFlagTolIj, kFlagTolFace) ? 1 : 0;
+    if (o.flags) o.flags[i] = (kKind == kInXYZ || sensitive) && near_cell_boundary(fi, fj, kFlagTolIj) ? 1 : 0;
   }
 }
 
@@ -116,12 +120,12 @@ __global__ void __launch_bounds__(kThreads) parent_kernel(const uint64_t* __rest
   for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) __stcs(out + i, cellid_parent(__ldcs(ids + i), level));
 }
 
-__global__ void __launch_bounds__(kThreads) token_kernel(const uint64_t* __restrict__ ids, size_t n, ulonglong2* __restrict__ tok, uint8_t* __restrict__ len) {
+__global__ void __launch_bounds__(kThreads) token_kernel(const uint64_t* __restrict__ ids, size_t n, uint4* __restrict__ tok, uint8_t* __restrict__ len) {
   const size_t stride = (size_t)gridDim.x * kThreads;
   for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
-    uint64_t w[2];
+    uint32_t w[4];
     int l = cellid_to_token(__ldcs(ids + i), w);
-    __stcs(tok + i, make_ulonglong2(w[0], w[1]));
+    __stcs(tok + i, make_uint4(w[0], w[1], w[2], w[3]));
     if (len) len[i] = (uint8_t)l;
   }
 }
@@ -135,7 +139,7 @@ cudaError_t launch_parent(const uint64_t* ids, size_t n, int level, uint64_t* ou
 
 cudaError_t launch_to_token(const uint64_t* ids, size_t n, char* tok, uint8_t* len, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
-  token_kernel<<<grid_for(n, (const void*)token_kernel), kThreads, 0, st>>>(ids, n, (ulonglong2*)tok, len);
+  token_kernel<<<grid_for(n, (const void*)token_kernel), kThreads, 0, st>>>(ids, n, (uint4*)tok, len);
   count_launch();
   return cudaGetLastError();
 }

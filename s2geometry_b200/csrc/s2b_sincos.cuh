@@ -195,34 +195,49 @@ S2B_HD SinCos sincos_cr(double x, const double (*tab)[4], int* n_slow = nullptr)
 // tests/test_encode_cpu.py::test_fast_sincos_error_bound).
 static constexpr double kFastSinCosAbsErr = 4.5e-16;
 
+// Coefficients live in constant memory on the device so that DFMA reads them as c[bank][offset] operands; as
+// immediates each would cost two IMAD.MOV per use (measured: 175 IMAD/point before, see profiles/).
+#define S2B_FAST_COEFS { \
+  -1.0 / 6.0, 1.0 / 120.0, -1.0 / 5040.0, 1.0 / 362880.0, -1.0 / 39916800.0, 1.0 / 6227020800.0, -1.0 / 1307674368000.0, \
+  1.0 / 24.0, -1.0 / 720.0, 1.0 / 40320.0, -1.0 / 3628800.0, 1.0 / 479001600.0, -1.0 / 87178291200.0, 1.0 / 20922789888000.0, \
+  sc_tab::kTwoOverPi, -sc_tab::kPio2_1, -sc_tab::kPio2_2, -sc_tab::kPio2_3 }
+#if defined(__CUDACC__)
+__constant__ double c_fast_coef[18] = S2B_FAST_COEFS;
+#endif
+static constexpr double kFastCoefHost[18] = S2B_FAST_COEFS;
+#if defined(__CUDA_ARCH__)
+#define S2B_FC(i) c_fast_coef[i]
+#else
+#define S2B_FC(i) kFastCoefHost[i]
+#endif
+
+// This routine is a filter, not part of the bit-exact path, so fused multiply-adds are used freely.
 S2B_HD SinCos sincos_fast(double x) {  // requires |x| < 2^20
-  using namespace sc_tab;
-  double kd = rint(x * kTwoOverPi);
-  double r = ((x - kd * kPio2_1) - kd * kPio2_2) - kd * kPio2_3;
+  double kd = rint(x * S2B_FC(14));
+  double r = fma(kd, S2B_FC(17), fma(kd, S2B_FC(16), fma(kd, S2B_FC(15), x)));
   double z = r * r;
-  double ps = -1.0 / 1307674368000.0;                       // -1/15!
-  ps = ps * z + 1.0 / 6227020800.0;                         // 1/13!
-  ps = ps * z - 1.0 / 39916800.0;                           // -1/11!
-  ps = ps * z + 1.0 / 362880.0;                             // 1/9!
-  ps = ps * z - 1.0 / 5040.0;
-  ps = ps * z + 1.0 / 120.0;
-  ps = ps * z - 1.0 / 6.0;
-  double sr = r + r * (z * ps);
-  double pc = 1.0 / 20922789888000.0;                       // 1/16!
-  pc = pc * z - 1.0 / 87178291200.0;                        // -1/14!
-  pc = pc * z + 1.0 / 479001600.0;                          // 1/12!
-  pc = pc * z - 1.0 / 3628800.0;
-  pc = pc * z + 1.0 / 40320.0;
-  pc = pc * z - 1.0 / 720.0;
-  pc = pc * z + 1.0 / 24.0;
-  double cr = 1.0 + (z * (z * pc) - 0.5 * z);
+  double ps = S2B_FC(6);
+  ps = fma(ps, z, S2B_FC(5));
+  ps = fma(ps, z, S2B_FC(4));
+  ps = fma(ps, z, S2B_FC(3));
+  ps = fma(ps, z, S2B_FC(2));
+  ps = fma(ps, z, S2B_FC(1));
+  ps = fma(ps, z, S2B_FC(0));
+  double sr = fma(r * z, ps, r);
+  double pc = S2B_FC(13);
+  pc = fma(pc, z, S2B_FC(12));
+  pc = fma(pc, z, S2B_FC(11));
+  pc = fma(pc, z, S2B_FC(10));
+  pc = fma(pc, z, S2B_FC(9));
+  pc = fma(pc, z, S2B_FC(8));
+  pc = fma(pc, z, S2B_FC(7));
+  double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
+  int q = (int)kd;
+  // quadrant: swap for odd k, negate sin for k = 2,3 (mod 4), cos for k = 1,2
+  double s0 = (q & 1) ? cr : sr, c0 = (q & 1) ? sr : cr;
   SinCos out;
-  switch ((int)kd & 3) {
-    case 0: out.s = sr; out.c = cr; break;
-    case 1: out.s = cr; out.c = -sr; break;
-    case 2: out.s = -sr; out.c = -cr; break;
-    default: out.s = -cr; out.c = sr; break;
-  }
+  out.s = (q & 2) ? -s0 : s0;
+  out.c = ((q + 1) & 2) ? -c0 : c0;
   return out;
 }
 
@@ -243,17 +258,14 @@ S2B_HD P3 latlng_to_point(double lat, double lng, const double (*tab)[4], int* n
 // correctly rounded sin/cos). With |error| <= e in each of the four sin/cos values: x,y are off by <= 2e + 1.2e-16,
 // z by <= e; u,v by <= (3e + 2.4e-16)/0.577 + 1.2e-16 (the major axis is >= 1/sqrt(3)); s,t by <= 0.75 of that + 2e-16;
 // i.e. in units of leaf cells (x 2^30):  e = 4.5e-16 (fast sin/cos) -> 3.1e-6 ;  e = 1.1e-16 (1 ulp) -> 1.1e-6.
-// The face can flip only if the two largest |components| are within ~4e of each other.
-S2B_HD bool near_cell_boundary(const P3& p, double fi, double fj, double tol_ij, double tol_face) {
-  double ax = fabs(p.x), ay = fabs(p.y), az = fabs(p.z);
-  double hi = fmax(ax, fmax(ay, az));
-  double mid = fmax(fmin(ax, ay), fmin(fmax(ax, ay), az));
+S2B_HD bool near_cell_boundary(double fi, double fj, double tol_ij) {
+  // A face flip needs two |components| to (nearly) tie, i.e. |u| or |v| within ~1e-14 of 1 on the chosen face, i.e.
+  // fi or fj within ~4e-6 of 0 or 2^30: already covered by the distance-to-integer test below (tolerances >= 4e-6).
   double di = fi - floor(fi), dj = fj - floor(fj);
-  // written so that NaN inputs come out "true"
-  return !(hi - mid > tol_face) || !(di > tol_ij && di < 1 - tol_ij && dj > tol_ij && dj < 1 - tol_ij);
+  return !(di > tol_ij && di < 1 - tol_ij && dj > tol_ij && dj < 1 - tol_ij);   // NaN -> true
 }
-static constexpr double kFilterTolIj = 1.6e-5, kFilterTolFace = 1e-14;   // fast-path filter: 5x the 3.1e-6 bound
-static constexpr double kFlagTolIj = 4e-6, kFlagTolFace = 2e-15;         // user-visible flag: 1-ulp sin/cos changes, 3.5x margin
+static constexpr double kFilterTolIj = 1.6e-5;   // fast-path filter: 5x the 3.1e-6 bound
+static constexpr double kFlagTolIj = 4e-6;      // user-visible flag: 1-ulp sin/cos changes, 3.5x margin
 
 // lat/lng -> (face, fi, fj) with the filter described above. *sensitive reports whether the correctly rounded path ran.
 S2B_HD int latlng_to_face_fij(double lat, double lng, const double (*tab)[4], bool force_cr, P3* p, double* fi, double* fj, bool* sensitive) {
@@ -263,7 +275,7 @@ S2B_HD int latlng_to_face_fij(double lat, double lng, const double (*tab)[4], bo
   if (!sens) {
     *p = latlng_to_point_fast(lat, lng);
     face = point_to_face_fij(*p, fi, fj);
-    sens = near_cell_boundary(*p, *fi, *fj, kFilterTolIj, kFilterTolFace);
+    sens = near_cell_boundary(*fi, *fj, kFilterTolIj);
   }
   if (sens) {
     *p = latlng_to_point(lat, lng, tab);

@@ -73,7 +73,7 @@ void hs_sincos_hilo(const double* x, size_t n, int slow, double* out, double* re
 }
 
 void hs_cellid_to_token(const uint64_t* ids, size_t n, char* tok16, uint8_t* len) {
-  for (size_t i = 0; i < n; ++i) { uint64_t w[2]; len[i] = (uint8_t)cellid_to_token(ids[i], w); __builtin_memcpy(tok16 + 16 * i, w, 16); }
+  for (size_t i = 0; i < n; ++i) { uint32_t w[4]; len[i] = (uint8_t)cellid_to_token(ids[i], w); __builtin_memcpy(tok16 + 16 * i, w, 16); }
 }
 
 }  // extern "C"
