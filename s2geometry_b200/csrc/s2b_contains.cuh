@@ -34,12 +34,25 @@ struct FlatIndexView {
 
 enum VertexModel { kOpen = 0, kSemiOpen = 1, kClosed = 2 };
 
-// Index of the cell containing the leaf id, or -1. Equivalent to LocateImpl: the index cells are disjoint, so the
-// only candidate is the last cell whose range_min <= leaf.
+// Lookup-table entry: bits 29..0 = index of the first candidate cell of the bucket; bits 31..30 = what the bucket
+// (a cell of level lut_level, i.e. a contiguous range of leaf ids) looks like:
+//   kLutMixed  several index cells and/or gaps start inside the bucket: probe cell_ids[lo .. next bucket's lo]
+//   kLutEmpty  no index cell intersects the bucket: every leaf of it is a miss          (decided with ONE load)
+//   kLutInside the whole bucket lies inside index cell `lo`: every leaf of it is a hit   (decided with ONE load)
+constexpr uint32_t kLutIndexMask = 0x3FFFFFFFu;
+constexpr uint32_t kLutMixed = 0u, kLutEmpty = 1u << 30, kLutInside = 2u << 30;
+
+// Index of the cell containing the leaf id, or -1. Equivalent to LocateImpl (s2cell_iterator.h:137-155): the index
+// cells are disjoint, so the only candidate is the last cell whose range_min <= leaf.
 S2B_HD int locate_cell(const FlatIndexView& ix, uint64_t leaf) {
   if (ix.num_cells == 0) return -1;
-  uint64_t bucket = leaf >> ix.lut_shift;
-  uint32_t lo = ix.lut[bucket], hi = ix.lut[bucket + 1];
+  const uint64_t bucket = leaf >> ix.lut_shift;
+  const uint32_t e0 = ix.lut[bucket];
+  uint32_t lo = e0 & kLutIndexMask;
+  const uint32_t kind = e0 & ~kLutIndexMask;
+  if (kind == kLutEmpty) return -1;
+  if (kind == kLutInside) return (int)lo;
+  uint32_t hi = ix.lut[bucket + 1] & kLutIndexMask;
   if (lo >= ix.num_cells) return -1;
   if (hi >= ix.num_cells) hi = ix.num_cells - 1;
   while (lo < hi) {
@@ -81,16 +94,31 @@ S2B_HD bool clip_contains(const FlatIndexView& ix, const FlatClip& clip, const P
     }
     return false;
   }
-  for (uint32_t i = 0; i < num_edges; ++i) {
-    FlatEdge e = edges[i];
-    P3 c = edge_v0(e), d = edge_v1(e);
-    // S2EdgeCrosser fast path (s2edge_crosser.h:365-388): C and D strictly on the same side of AB.
-    int acb = -triage_sign(a_cross_b, c);
-    int bda = triage_sign(a_cross_b, d);
-    if (acb == -bda && bda != 0) continue;
-    int r = edge_slow_path(a, b, c, d, acb, bda, model);
-    if (r >= 2) return r == 3;
-    inside ^= (r != 0);
+  // Pass 1: the S2EdgeCrosser fast path (s2edge_crosser.h:365-388) for every edge — C and D strictly on the same side
+  // of AB means no crossing. Edges it cannot dismiss (~9 %) are only REMEMBERED here (bitmask per 64 edges) and
+  // resolved in pass 2, so a warp's lanes go through the expensive path together instead of one at a time at
+  // arbitrary iterations. The order of evaluation does not matter: the parity is a XOR, and the vertex-model early
+  // return yields the same value whichever qualifying edge triggers it (s2contains_point_query.h:377-382).
+  for (uint32_t base = 0; base < num_edges; base += 64) {
+    const uint32_t cnt = num_edges - base < 64 ? num_edges - base : 64;
+    uint64_t pending = 0;
+    for (uint32_t i = 0; i < cnt; ++i) {
+      const FlatEdge e = edges[base + i];
+      const int acb = -triage_sign(a_cross_b, edge_v0(e));
+      const int bda = triage_sign(a_cross_b, edge_v1(e));
+      if (!(acb == -bda && bda != 0)) pending |= 1ull << i;
+    }
+    while (pending) {
+      const int i = ctz64(pending);
+      pending &= pending - 1;
+      const FlatEdge e = edges[base + i];
+      const P3 c = edge_v0(e), d = edge_v1(e);
+      const int acb = -triage_sign(a_cross_b, c);
+      const int bda = triage_sign(a_cross_b, d);
+      const int r = edge_slow_path(a, b, c, d, acb, bda, model);
+      if (r >= 2) return r == 3;
+      inside ^= (r != 0);
+    }
   }
   return inside;
 }

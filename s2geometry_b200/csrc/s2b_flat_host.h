@@ -67,13 +67,21 @@ inline int pack_flat_index(const S2bFlatIndex& f, HostFlat* out, std::string* er
     out->clips[k] = FlatClip{f.clip_shape_id[k], f.clip_edge_begin[k], f.clip_edge_begin[k + 1] - f.clip_edge_begin[k], f.clip_flags[k]};
   for (uint64_t e = 0; e < E; ++e)
     out->edges[e] = FlatEdge{f.edge_v0[3 * e], f.edge_v0[3 * e + 1], f.edge_v0[3 * e + 2], f.edge_v1[3 * e], f.edge_v1[3 * e + 1], f.edge_v1[3 * e + 2]};
-  // lut[b] = number of cells whose range_max < first leaf id of bucket b: the first cell a leaf of bucket b can be in
+  // lut[b] = number of cells whose range_max < first leaf id of bucket b (the first cell a leaf of bucket b can be
+  // in), tagged with the bucket kind (s2b_contains.cuh): empty / entirely inside that cell / mixed.
+  if (C > kLutIndexMask) return fail(S2B_EINVAL, "index too large for the 30-bit lookup-table entries");
   uint64_t c = 0;
   for (uint64_t b = 0; b <= nb; ++b) {
-    uint64_t first = b << out->lut_shift;
+    const uint64_t first = b << out->lut_shift;
     while (c < C && cellid_range_max(f.cell_ids[c]) < first) ++c;
     if (b == nb) c = C;
-    out->lut[b] = (uint32_t)c;
+    uint32_t kind = kLutMixed;
+    if (b < nb) {
+      const uint64_t last = ((b + 1) << out->lut_shift) - 1;
+      if (c == C || cellid_range_min(f.cell_ids[c]) > last) kind = kLutEmpty;
+      else if (cellid_range_min(f.cell_ids[c]) <= first && cellid_range_max(f.cell_ids[c]) >= last) kind = kLutInside;
+    }
+    out->lut[b] = (uint32_t)c | kind;
   }
   out->lut[nb + 1] = (uint32_t)C;
   return S2B_OK;

@@ -31,52 +31,77 @@ struct QueryOut {
   int32_t* shape_ids;             // fill
 };
 
-template <int kMode>
-__global__ void __launch_bounds__(kThreads, 4)
-query_kernel(const FlatIndexView ix, const double* __restrict__ xyz, size_t n, int model, const QueryOut out) {
+// Two phases per batch, both on the caller's stream:
+//  A  locate_kernel   every point: K1 + Locate. Lean (no predicates inlined, ~40 registers, 6 CTAs/SM). Points that
+//                     land in an index cell are appended to a work list (point, cell) with one warp-aggregated
+//                     atomicAdd per warp; every point's output slot gets its "miss" value.
+//  B  process_kernel  one thread per work-list entry: crossing parity over the cell's clipped edges (s2b_contains.cuh),
+//                     so the divergent, register-hungry part runs on fully populated warps instead of on the 1-10 %
+//                     of lanes that hit, and does not cap the occupancy of phase A.
+struct HitWork { uint32_t point; int32_t cell; };
+
+__global__ void __launch_bounds__(kThreads, 6)
+locate_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint32_t n, HitWork* __restrict__ work,
+              unsigned int* __restrict__ work_count, uint8_t* __restrict__ miss_flags, uint32_t* __restrict__ miss_counts) {
   __shared__ uint16_t s_pos[1024];
   for (int k = threadIdx.x; k < 1024; k += kThreads) s_pos[k] = g_hilbert_ix.pos[k];
   __syncthreads();
-  // Warp-uniform trip count + __syncwarp() per iteration: the few lanes that land in an index cell (and the rarer
-  // ones in the exact stage) rejoin their warp before the next batch of 32 points instead of drifting apart for good.
-  const size_t stride = (size_t)gridDim.x * kThreads;
+  const uint32_t stride = gridDim.x * kThreads;
   const unsigned lane = threadIdx.x & 31u;
-  for (size_t base = (size_t)blockIdx.x * kThreads + (threadIdx.x & ~31u); base < n; base += stride, __syncwarp()) {
-    const size_t i = base + lane;
-    if (i >= n) continue;
-    const double* q = xyz + 3 * i;
-    P3 p{__ldcs(q), __ldcs(q + 1), __ldcs(q + 2)};
-    if (kMode == kModeAny) {
-      bool any = false;
-      visit_containing_shapes(ix, p, s_pos, model, [&](int) { any = true; return false; });
-      out.flags[i] = any ? 1 : 0;
-    } else if (kMode == kModeShape) {
-      // ShapeContains(shape_id, p): only the clip of that shape is evaluated (find_clipped).
-      bool hit = false;
-      uint64_t leaf = cellid_from_point(p, s_pos);
-      int cell = locate_cell(ix, leaf);
-      if (cell >= 0) {
-        FlatCell fc = ix.cells[cell];
-        for (uint32_t k = 0; k < fc.clip_count; ++k) {
-          FlatClip clip = ix.clips[fc.clip_begin + k];
-          if (clip.shape_id == out.shape_id) {
-            P3 a{fc.cx, fc.cy, fc.cz};
-            hit = clip_contains(ix, clip, a, p, cross(a, p), model);
-            break;
-          }
-        }
-      }
-      out.flags[i] = hit ? 1 : 0;
-    } else if (kMode == kModeHistogram) {
-      visit_containing_shapes(ix, p, s_pos, model, [&](int id) { atomicAdd(out.counts + id, 1ull); return true; });
-    } else if (kMode == kModeCount) {
-      uint32_t c = 0;
-      visit_containing_shapes(ix, p, s_pos, model, [&](int) { ++c; return true; });
-      out.per_point[i] = c;
-    } else {
-      uint32_t w = out.offsets[i];
-      visit_containing_shapes(ix, p, s_pos, model, [&](int id) { out.shape_ids[w++] = id; return true; });
+  // n is padded to a multiple of 32 for the loop bound so that whole warps iterate together (ballot needs all lanes)
+  for (uint32_t base = blockIdx.x * kThreads + (threadIdx.x & ~31u); base < n; base += stride) {
+    const uint32_t i = base + lane;
+    int cell = -1;
+    if (i < n) {
+      const double* q = xyz + 3 * (size_t)i;
+      const P3 p{__ldcs(q), __ldcs(q + 1), __ldcs(q + 2)};
+      cell = locate_cell(ix, cellid_from_point(p, s_pos));
+      if (miss_flags) miss_flags[i] = 0;
+      if (miss_counts) miss_counts[i] = 0;
     }
+    const unsigned hits = __ballot_sync(0xffffffffu, cell >= 0);
+    if (hits) {
+      unsigned int first = 0;
+      if (lane == (unsigned)(__ffs(hits) - 1)) first = atomicAdd(work_count, (unsigned int)__popc(hits));
+      first = __shfl_sync(0xffffffffu, first, __ffs(hits) - 1);
+      if (cell >= 0) work[first + __popc(hits & ((1u << lane) - 1u))] = HitWork{i, cell};
+    }
+  }
+}
+
+template <int kMode>
+__global__ void __launch_bounds__(kThreads, 2)
+process_kernel(const FlatIndexView ix, const double* __restrict__ xyz, const HitWork* __restrict__ work,
+               const unsigned int* __restrict__ work_count, int model, const QueryOut out) {
+  const unsigned int count = *work_count;
+  const unsigned int stride = gridDim.x * kThreads;
+  const unsigned lane = threadIdx.x & 31u;
+  // warp-uniform trip count + __syncwarp(): lanes with long edge lists or exact-stage work rejoin every iteration
+  for (unsigned int wbase = blockIdx.x * kThreads + (threadIdx.x & ~31u); wbase < count; wbase += stride, __syncwarp()) {
+    const unsigned int w = wbase + lane;
+    if (w >= count) continue;
+    const HitWork hw = work[w];
+    const double* q = xyz + 3 * (size_t)hw.point;
+    const P3 p{q[0], q[1], q[2]};
+    const FlatCell fc = ix.cells[hw.cell];
+    const P3 a{fc.cx, fc.cy, fc.cz};
+    const P3 a_cross_b = cross(a, p);
+    uint32_t result = 0;
+    uint32_t fill_at = kMode == kModeFill ? out.offsets[hw.point] : 0u;
+    for (uint32_t k = 0; k < fc.clip_count; ++k) {
+      const FlatClip clip = ix.clips[fc.clip_begin + k];
+      if (kMode == kModeShape && clip.shape_id != out.shape_id) continue;
+      if (clip_contains(ix, clip, a, p, a_cross_b, model)) {
+        if (kMode == kModeAny || kMode == kModeShape) { result = 1; break; }
+        if (kMode == kModeHistogram) atomicAdd(out.counts + clip.shape_id, 1ull);
+        if (kMode == kModeCount) ++result;
+        if (kMode == kModeFill) out.shape_ids[fill_at++] = clip.shape_id;
+      } else if (kMode == kModeShape) {
+        break;
+      }
+    }
+    if (kMode == kModeAny || kMode == kModeShape) { if (result) out.flags[hw.point] = 1; }
+    if (kMode == kModeCount) { if (result) out.per_point[hw.point] = result; }
   }
 }
 
@@ -119,13 +144,52 @@ static int grid_for_ix(size_t n, const void* kernel) {
   return (int)(want < cap ? (want ? want : 1) : cap);
 }
 
+// Points per phase-A/phase-B round: bounds the work list (8 B per point in the worst case) at 512 MB.
+constexpr size_t kRoundPoints = size_t(1) << 26;
+
+// The work list comes from the stream-ordered allocator; keep freed blocks cached in the pool (the default release
+// threshold of 0 hands them back to the driver at every synchronisation, which costs milliseconds per call).
+static void keep_pool_memory_once() {
+  static thread_local int done_for_device = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for_device) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  done_for_device = dev;
+}
+
 template <int kMode>
 static cudaError_t launch_query_t(const FlatIndexView& ix, const double* xyz, size_t n, int model, const QueryOut& out, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
-  auto kern = query_kernel<kMode>;
-  kern<<<grid_for_ix(n, (const void*)kern), kThreads, 0, st>>>(ix, xyz, n, model, out);
-  count_launch();
-  return cudaGetLastError();
+  keep_pool_memory_once();
+  const size_t round = n < kRoundPoints ? n : kRoundPoints;
+  HitWork* work = nullptr;
+  unsigned int* counter = nullptr;
+  cudaError_t e = cudaMallocAsync((void**)&work, sizeof(HitWork) * round + 256, st);
+  if (e != cudaSuccess) return e;
+  counter = (unsigned int*)((char*)work + sizeof(HitWork) * round);   // 8-byte aligned tail
+  const int proc_grid = grid_for_ix(round, (const void*)process_kernel<kMode>);
+  for (size_t off = 0; off < n && e == cudaSuccess; off += round) {
+    const size_t cnt = n - off < round ? n - off : round;
+    e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), st);
+    if (e != cudaSuccess) break;
+    QueryOut o = out;   // rebase per-point arrays to this round
+    if (o.flags) o.flags += off;
+    if (o.per_point) o.per_point += off;
+    if (o.offsets) o.offsets += off;
+    locate_kernel<<<grid_for_ix(cnt, (const void*)locate_kernel), kThreads, 0, st>>>(
+        ix, xyz + 3 * off, (uint32_t)cnt, work, counter, (kMode == kModeAny || kMode == kModeShape) ? o.flags : nullptr,
+        kMode == kModeCount ? o.per_point : nullptr);
+    count_launch();
+    process_kernel<kMode><<<proc_grid, kThreads, 0, st>>>(ix, xyz + 3 * off, work, counter, model, o);
+    count_launch();
+    e = cudaGetLastError();
+  }
+  cudaError_t e2 = cudaFreeAsync(work, st);
+  return e != cudaSuccess ? e : e2;
 }
 
 }  // namespace s2b
@@ -136,6 +200,7 @@ using namespace s2b;
 struct S2bIndex {
   int device = 0;
   FlatIndexView view{};
+  const FlatIndexView* view_dev = nullptr;   // the same view, stored at the end of the device blob
   void* blob = nullptr;   // one allocation holding every array
   size_t blob_bytes = 0;
   uint64_t num_clips = 0, num_edges = 0;
@@ -174,7 +239,7 @@ int s2b_index_create(const S2bFlatIndex* f, S2bIndex** out) {
   auto align = [](size_t v) { return (v + 255) / 256 * 256; };
   size_t o_ids = 0, o_cells = o_ids + align(8 * (C + 1)), o_clips = o_cells + align(sizeof(FlatCell) * (C + 1)),
          o_edges = o_clips + align(sizeof(FlatClip) * (K + 1)), o_lut = o_edges + align(sizeof(FlatEdge) * (E + 1)),
-         total = o_lut + align(4 * (nb + 2));
+         o_view = o_lut + align(4 * (nb + 2)), total = o_view + align(sizeof(FlatIndexView));
   e = cudaMalloc(&ix->blob, total);
   if (e != cudaSuccess) { delete ix; return cuda_fail(e, "cudaMalloc(index)"); }
   ix->blob_bytes = total;
@@ -195,6 +260,10 @@ int s2b_index_create(const S2bFlatIndex* f, S2bIndex** out) {
   ix->view.lut_shift = lut_shift;
   ix->view.num_shape_ids = f->num_shape_ids;
   ix->num_clips = K; ix->num_edges = E;
+  if (cudaMemcpy(base + o_view, &ix->view, sizeof(FlatIndexView), cudaMemcpyHostToDevice) != cudaSuccess) {
+    e = cudaGetLastError(); cudaFree(ix->blob); delete ix; return cuda_fail(e, "cudaMemcpy(view)");
+  }
+  ix->view_dev = (const FlatIndexView*)(base + o_view);
   *out = ix;
   return S2B_OK;
 }
