@@ -27,6 +27,7 @@ struct FlatIndexView {
   const FlatClip* clips;
   const FlatEdge* edges;
   const uint32_t* lut;
+  const uint8_t* interior_clips;   // per cell: k > 0 = no edges at all, k clips that all contain the centre; 0 = has edges
   uint32_t num_cells;
   int lut_shift;
   int num_shape_ids;

@@ -5,6 +5,7 @@
 // an index cell, the crossing test of s2b_contains.cuh from the precomputed cell centre over that cell's clipped
 // edges, with the Sign chain (triage -> stable -> exact superaccumulator -> symbolic) entirely on the device.
 // Index arrays are read through the read-only path; points are streamed (24 B in, 1 B / a few atomics out).
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -40,40 +41,110 @@ struct QueryOut {
 //                     of lanes that hit, and does not cap the occupancy of phase A.
 struct HitWork { uint32_t point; int32_t cell; };
 
-__global__ void __launch_bounds__(kThreads, 6)
-locate_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint32_t n, HitWork* __restrict__ work,
-              unsigned int* __restrict__ work_count, uint8_t* __restrict__ miss_flags, uint32_t* __restrict__ miss_counts) {
+// interior_mode: what phase A may answer by itself for points in pure interior cells (no edges, every clip contains the
+// centre): 0 nothing (all hits go to the work lists), 1 "any" (flag = 1), 2 "count" (per-point count = number of clips).
+// Hits that need edge work are appended at the front of `work` (count in counters[0]); interior hits that still
+// need per-shape output (histogram / fill / one shape) are appended from the back (count in counters[1]), so phase B
+// runs over two homogeneous lists.
+// Work-list slots are reserved per warp in chunks of kSlotChunk with ONE global atomicAdd per chunk (a same-address
+// atomic per warp iteration serialises at the L2: ~600k of them per 20M points when most warps see a hit). Unused slots
+// of a chunk are filled with a sentinel (cell = -1) that phase B skips.
+constexpr uint32_t kSlotChunk = 128;
+
+struct WarpSlots {
+  uint32_t next = 0, end = 0;   // warp-uniform
+  // Appends one entry for every lane with `want` set. dir = +1: list grows forward from work[0]; dir = -1: backward from
+  // work[capacity-1]. All 32 lanes must call.
+  __device__ __forceinline__ void append(bool want, HitWork value, HitWork* work, uint32_t capacity, unsigned int* counter, int dir, unsigned lane) {
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (!m) return;
+    const uint32_t k = (uint32_t)__popc(m);
+    if (next + k > end) {
+      // retire the rest of the current chunk, then take a new one
+      for (uint32_t s = next + lane; s < end; s += 32) work[dir > 0 ? s : capacity - 1 - s] = HitWork{0u, -1};
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(counter, kSlotChunk);
+      next = __shfl_sync(0xffffffffu, base, 0);
+      end = next + kSlotChunk;
+    }
+    if (want) {
+      const uint32_t s = next + (uint32_t)__popc(m & ((1u << lane) - 1u));
+      work[dir > 0 ? s : capacity - 1 - s] = value;
+    }
+    next += k;
+  }
+  __device__ __forceinline__ void finish(HitWork* work, uint32_t capacity, int dir, unsigned lane) {
+    for (uint32_t s = next + lane; s < end; s += 32) work[dir > 0 ? s : capacity - 1 - s] = HitWork{0u, -1};
+  }
+};
+
+// interior_mode: what phase A may answer by itself for points in pure interior cells (no edges, every clip contains the
+// centre): 0 nothing (all hits go to the work lists), 1 "any" (flag = 1), 2 "count" (per-point count = number of clips).
+// Hits that need edge work are appended at the front of `work` (slots reserved in counters[0]); interior hits that
+// still need per-shape output (histogram / fill / one shape) are appended from the back (counters[1]), so phase B runs
+// over two homogeneous lists.
+template <int kCtasPerSm, int kPointsPerThread>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
+locate_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint32_t n, HitWork* __restrict__ work, uint32_t capacity,
+              unsigned int* __restrict__ counters, int interior_mode, uint8_t* __restrict__ flags, uint32_t* __restrict__ counts) {
   __shared__ uint16_t s_pos[1024];
   for (int k = threadIdx.x; k < 1024; k += kThreads) s_pos[k] = g_hilbert_ix.pos[k];
   __syncthreads();
-  const uint32_t stride = gridDim.x * kThreads;
+  constexpr uint32_t kSpan = kThreads * kPointsPerThread;
+  const uint32_t stride = gridDim.x * kSpan;
   const unsigned lane = threadIdx.x & 31u;
-  // n is padded to a multiple of 32 for the loop bound so that whole warps iterate together (ballot needs all lanes)
-  for (uint32_t base = blockIdx.x * kThreads + (threadIdx.x & ~31u); base < n; base += stride) {
-    const uint32_t i = base + lane;
-    int cell = -1;
-    if (i < n) {
-      const double* q = xyz + 3 * (size_t)i;
-      const P3 p{__ldcs(q), __ldcs(q + 1), __ldcs(q + 2)};
-      cell = locate_cell(ix, cellid_from_point(p, s_pos));
-      if (miss_flags) miss_flags[i] = 0;
-      if (miss_counts) miss_counts[i] = 0;
+  WarpSlots edge_slots, interior_slots;
+  // whole warps iterate together (the ballots need all lanes); kPointsPerThread independent chains per thread
+  for (uint32_t base = blockIdx.x * kSpan + (threadIdx.x & ~31u); base < n; base += stride) {
+    uint32_t idx[kPointsPerThread];
+    int cell[kPointsPerThread];
+    P3 p[kPointsPerThread];
+#pragma unroll
+    for (int t = 0; t < kPointsPerThread; ++t) {
+      idx[t] = base + t * kThreads + lane;
+      if (idx[t] < n) {
+        const double* q = xyz + 3 * (size_t)idx[t];
+        p[t] = P3{__ldcs(q), __ldcs(q + 1), __ldcs(q + 2)};
+      } else {
+        p[t] = P3{1.0, 0.0, 0.0};
+      }
     }
-    const unsigned hits = __ballot_sync(0xffffffffu, cell >= 0);
-    if (hits) {
-      unsigned int first = 0;
-      if (lane == (unsigned)(__ffs(hits) - 1)) first = atomicAdd(work_count, (unsigned int)__popc(hits));
-      first = __shfl_sync(0xffffffffu, first, __ffs(hits) - 1);
-      if (cell >= 0) work[first + __popc(hits & ((1u << lane) - 1u))] = HitWork{i, cell};
+#pragma unroll
+    for (int t = 0; t < kPointsPerThread; ++t) cell[t] = locate_cell(ix, cellid_from_point(p[t], s_pos));
+#pragma unroll
+    for (int t = 0; t < kPointsPerThread; ++t) {
+      const uint32_t i = idx[t];
+      const int c = i < n ? cell[t] : -1;
+      uint32_t interior = 0;
+      if (c >= 0) interior = ix.interior_clips[c];
+      uint8_t flag = 0;
+      uint32_t cnt = 0;
+      const bool to_edges = c >= 0 && interior == 0;
+      bool to_interior = false;
+      if (c >= 0 && interior != 0) {
+        if (interior_mode == 1) flag = 1;
+        else if (interior_mode == 2) cnt = interior;
+        else to_interior = true;
+      }
+      if (i < n) {
+        if (flags) flags[i] = flag;
+        if (counts) counts[i] = cnt;
+      }
+      edge_slots.append(to_edges, HitWork{i, c}, work, capacity, counters, +1, lane);
+      if (interior_mode == 0) interior_slots.append(to_interior, HitWork{i, c}, work, capacity, counters + 1, -1, lane);
     }
   }
+  edge_slots.finish(work, capacity, +1, lane);
+  interior_slots.finish(work, capacity, -1, lane);
 }
 
 template <int kMode>
 __global__ void __launch_bounds__(kThreads, 2)
-process_kernel(const FlatIndexView ix, const double* __restrict__ xyz, const HitWork* __restrict__ work,
-               const unsigned int* __restrict__ work_count, int model, const QueryOut out) {
-  const unsigned int count = *work_count;
+process_kernel(const FlatIndexView ix, const double* __restrict__ xyz, const HitWork* __restrict__ work_base, uint32_t capacity,
+               const unsigned int* __restrict__ counters, int which_list, int model, const QueryOut out) {
+  // list 0: hits with edge work, stored forward from work_base[0]; list 1: interior hits, stored backward from the end
+  const unsigned int count = counters[which_list];
+  const HitWork* work = which_list == 0 ? work_base : work_base + (capacity - count);
   const unsigned int stride = gridDim.x * kThreads;
   const unsigned lane = threadIdx.x & 31u;
   // warp-uniform trip count + __syncwarp(): lanes with long edge lists or exact-stage work rejoin every iteration
@@ -81,6 +152,7 @@ process_kernel(const FlatIndexView ix, const double* __restrict__ xyz, const Hit
     const unsigned int w = wbase + lane;
     if (w >= count) continue;
     const HitWork hw = work[w];
+    if (hw.cell < 0) continue;   // unused slot of a reservation chunk
     const double* q = xyz + 3 * (size_t)hw.point;
     const P3 p{q[0], q[1], q[2]};
     const FlatCell fc = ix.cells[hw.cell];
@@ -161,6 +233,16 @@ static void keep_pool_memory_once() {
   done_for_device = dev;
 }
 
+// Tuning knob (env S2B_LOCATE_VARIANT): CTAs per SM x points per thread of phase A. 0 = default.
+static int locate_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("S2B_LOCATE_VARIANT");
+    v = e ? atoi(e) : 2;   // measured best overall on B200: 4 CTAs/SM x 2 points per thread
+  }
+  return v;
+}
+
 template <int kMode>
 static cudaError_t launch_query_t(const FlatIndexView& ix, const double* xyz, size_t n, int model, const QueryOut& out, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
@@ -168,24 +250,43 @@ static cudaError_t launch_query_t(const FlatIndexView& ix, const double* xyz, si
   const size_t round = n < kRoundPoints ? n : kRoundPoints;
   HitWork* work = nullptr;
   unsigned int* counter = nullptr;
-  cudaError_t e = cudaMallocAsync((void**)&work, sizeof(HitWork) * round + 256, st);
+  // every warp of phase A can leave at most one partly used chunk per list
+  const size_t max_warps = (size_t)sm_count() * 8 * (kThreads / 32);
+  const size_t capacity = round + 2 * max_warps * kSlotChunk;
+  cudaError_t e = cudaMallocAsync((void**)&work, sizeof(HitWork) * capacity + 256, st);
   if (e != cudaSuccess) return e;
-  counter = (unsigned int*)((char*)work + sizeof(HitWork) * round);   // 8-byte aligned tail
+  counter = (unsigned int*)((char*)work + sizeof(HitWork) * capacity);   // 8-byte aligned tail: [0] edge slots, [1] interior slots
   const int proc_grid = grid_for_ix(round, (const void*)process_kernel<kMode>);
+  const int interior_mode = kMode == kModeAny ? 1 : (kMode == kModeCount ? 2 : 0);
+  const int variant = locate_variant();
   for (size_t off = 0; off < n && e == cudaSuccess; off += round) {
     const size_t cnt = n - off < round ? n - off : round;
-    e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), st);
+    e = cudaMemsetAsync(counter, 0, 2 * sizeof(unsigned int), st);
     if (e != cudaSuccess) break;
     QueryOut o = out;   // rebase per-point arrays to this round
     if (o.flags) o.flags += off;
     if (o.per_point) o.per_point += off;
     if (o.offsets) o.offsets += off;
-    locate_kernel<<<grid_for_ix(cnt, (const void*)locate_kernel), kThreads, 0, st>>>(
-        ix, xyz + 3 * off, (uint32_t)cnt, work, counter, (kMode == kModeAny || kMode == kModeShape) ? o.flags : nullptr,
-        kMode == kModeCount ? o.per_point : nullptr);
+    uint8_t* fl = (kMode == kModeAny || kMode == kModeShape) ? o.flags : nullptr;
+    uint32_t* pc = kMode == kModeCount ? o.per_point : nullptr;
+#define S2B_LOCATE(C, P)                                                                                             \
+  locate_kernel<C, P><<<grid_for_ix((cnt + P - 1) / P, (const void*)locate_kernel<C, P>), kThreads, 0, st>>>(            \
+      ix, xyz + 3 * off, (uint32_t)cnt, work, (uint32_t)capacity, counter, interior_mode, fl, pc)
+    switch (variant) {
+      case 0: S2B_LOCATE(6, 1); break;
+      case 1: S2B_LOCATE(8, 1); break;
+      case 3: S2B_LOCATE(6, 2); break;
+      case 4: S2B_LOCATE(3, 4); break;
+      default: S2B_LOCATE(4, 2); break;
+    }
+#undef S2B_LOCATE
     count_launch();
-    process_kernel<kMode><<<proc_grid, kThreads, 0, st>>>(ix, xyz + 3 * off, work, counter, model, o);
+    process_kernel<kMode><<<proc_grid, kThreads, 0, st>>>(ix, xyz + 3 * off, work, (uint32_t)capacity, counter, 0, model, o);
     count_launch();
+    if (interior_mode == 0) {
+      process_kernel<kMode><<<proc_grid, kThreads, 0, st>>>(ix, xyz + 3 * off, work, (uint32_t)capacity, counter, 1, model, o);
+      count_launch();
+    }
     e = cudaGetLastError();
   }
   cudaError_t e2 = cudaFreeAsync(work, st);
@@ -239,7 +340,7 @@ int s2b_index_create(const S2bFlatIndex* f, S2bIndex** out) {
   auto align = [](size_t v) { return (v + 255) / 256 * 256; };
   size_t o_ids = 0, o_cells = o_ids + align(8 * (C + 1)), o_clips = o_cells + align(sizeof(FlatCell) * (C + 1)),
          o_edges = o_clips + align(sizeof(FlatClip) * (K + 1)), o_lut = o_edges + align(sizeof(FlatEdge) * (E + 1)),
-         o_view = o_lut + align(4 * (nb + 2)), total = o_view + align(sizeof(FlatIndexView));
+         o_kind = o_lut + align(4 * (nb + 2)), o_view = o_kind + align(C + 1), total = o_view + align(sizeof(FlatIndexView));
   e = cudaMalloc(&ix->blob, total);
   if (e != cudaSuccess) { delete ix; return cuda_fail(e, "cudaMalloc(index)"); }
   ix->blob_bytes = total;
@@ -250,12 +351,14 @@ int s2b_index_create(const S2bFlatIndex* f, S2bIndex** out) {
   ok &= K == 0 || cudaMemcpy(base + o_clips, clips.data(), sizeof(FlatClip) * K, cudaMemcpyHostToDevice) == cudaSuccess;
   ok &= E == 0 || cudaMemcpy(base + o_edges, edges.data(), sizeof(FlatEdge) * E, cudaMemcpyHostToDevice) == cudaSuccess;
   ok &= cudaMemcpy(base + o_lut, lut.data(), 4 * (nb + 2), cudaMemcpyHostToDevice) == cudaSuccess;
+  ok &= cudaMemcpy(base + o_kind, hf.interior_clips.data(), C + 1, cudaMemcpyHostToDevice) == cudaSuccess;
   if (!ok) { e = cudaGetLastError(); cudaFree(ix->blob); delete ix; return cuda_fail(e, "cudaMemcpy(index)"); }
   ix->view.cell_ids = (const uint64_t*)(base + o_ids);
   ix->view.cells = (const FlatCell*)(base + o_cells);
   ix->view.clips = (const FlatClip*)(base + o_clips);
   ix->view.edges = (const FlatEdge*)(base + o_edges);
   ix->view.lut = (const uint32_t*)(base + o_lut);
+  ix->view.interior_clips = (const uint8_t*)(base + o_kind);
   ix->view.num_cells = (uint32_t)C;
   ix->view.lut_shift = lut_shift;
   ix->view.num_shape_ids = f->num_shape_ids;
