@@ -138,8 +138,8 @@ locate_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint32_t n
   interior_slots.finish(work, capacity, -1, lane);
 }
 
-template <int kMode>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int kMode, int kCtasPerSm>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
 process_kernel(const FlatIndexView ix, const double* __restrict__ xyz, const HitWork* __restrict__ work_base, uint32_t capacity,
                const unsigned int* __restrict__ counters, int which_list, int model, const QueryOut out) {
   // list 0: hits with edge work, stored forward from work_base[0]; list 1: interior hits, stored backward from the end
@@ -243,6 +243,15 @@ static int locate_variant() {
   return v;
 }
 
+static int process_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("S2B_PROCESS_VARIANT");
+    v = e ? atoi(e) : 2;
+  }
+  return v;
+}
+
 template <int kMode>
 static cudaError_t launch_query_t(const FlatIndexView& ix, const double* xyz, size_t n, int model, const QueryOut& out, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
@@ -256,7 +265,10 @@ static cudaError_t launch_query_t(const FlatIndexView& ix, const double* xyz, si
   cudaError_t e = cudaMallocAsync((void**)&work, sizeof(HitWork) * capacity + 256, st);
   if (e != cudaSuccess) return e;
   counter = (unsigned int*)((char*)work + sizeof(HitWork) * capacity);   // 8-byte aligned tail: [0] edge slots, [1] interior slots
-  const int proc_grid = grid_for_ix(round, (const void*)process_kernel<kMode>);
+  const int pv = process_variant();
+  void (*proc)(const FlatIndexView, const double*, const HitWork*, uint32_t, const unsigned int*, int, int, const QueryOut) =
+      pv == 3 ? process_kernel<kMode, 3> : (pv == 4 ? process_kernel<kMode, 4> : process_kernel<kMode, 2>);
+  const int proc_grid = grid_for_ix(round, (const void*)proc);
   const int interior_mode = kMode == kModeAny ? 1 : (kMode == kModeCount ? 2 : 0);
   const int variant = locate_variant();
   for (size_t off = 0; off < n && e == cudaSuccess; off += round) {
@@ -281,10 +293,10 @@ static cudaError_t launch_query_t(const FlatIndexView& ix, const double* xyz, si
     }
 #undef S2B_LOCATE
     count_launch();
-    process_kernel<kMode><<<proc_grid, kThreads, 0, st>>>(ix, xyz + 3 * off, work, (uint32_t)capacity, counter, 0, model, o);
+    proc<<<proc_grid, kThreads, 0, st>>>(ix, xyz + 3 * off, work, (uint32_t)capacity, counter, 0, model, o);
     count_launch();
     if (interior_mode == 0) {
-      process_kernel<kMode><<<proc_grid, kThreads, 0, st>>>(ix, xyz + 3 * off, work, (uint32_t)capacity, counter, 1, model, o);
+      proc<<<proc_grid, kThreads, 0, st>>>(ix, xyz + 3 * off, work, (uint32_t)capacity, counter, 1, model, o);
       count_launch();
     }
     e = cudaGetLastError();
