@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/s2b_capi.h"
+#include "s2b_hilbert.h"
 #include "s2b_internal.h"
 
 namespace s2b {
@@ -19,6 +20,11 @@ static std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_force_cr{0};
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+const uint16_t* wide_hilbert_host() {
+  static const std::vector<uint16_t> table = [] { std::vector<uint16_t> t(16384); MakeWideHilbert(t.data()); return t; }();
+  return table.data();
+}
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;

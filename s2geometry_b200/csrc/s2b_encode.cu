@@ -14,6 +14,17 @@
 namespace s2b {
 
 __device__ const HilbertTables g_hilbert = kHilbert;
+__device__ uint16_t g_hilbert_wide[16384];   // uploaded on first use per device (ensure_wide_table)
+
+static cudaError_t ensure_wide_table() {
+  static thread_local int done_for_device = -1;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess || dev == done_for_device) return e;
+  e = cudaMemcpyToSymbol(g_hilbert_wide, wide_hilbert_host(), 16384 * sizeof(uint16_t));
+  if (e == cudaSuccess) done_for_device = dev;
+  return e;
+}
 __device__ const double g_sincos_tab[sc_tab::kTableSize][4] = {
 #define S2B_ROW(i) {sc_tab::kSinCosTable[i][0], sc_tab::kSinCosTable[i][1], sc_tab::kSinCosTable[i][2], sc_tab::kSinCosTable[i][3]}
 #define S2B_ROW5(i) S2B_ROW(i), S2B_ROW(i + 1), S2B_ROW(i + 2), S2B_ROW(i + 3), S2B_ROW(i + 4)
@@ -31,9 +42,9 @@ __device__ __forceinline__ int level_at(const LevelSpec& l, int k) {
 template <int kKind>
 __global__ void __launch_bounds__(kThreads, 6)
 encode_kernel(const void* __restrict__ in, size_t n, const EncodeOut o) {
-  __shared__ uint16_t s_pos[1024];
+  __shared__ uint16_t s_pos[16384];   // 6-bit Hilbert table: 5 dependent lookups per point
   __shared__ double s_sc[kKind == kInXYZ ? 1 : sc_tab::kTableSize][4];
-  for (int k = threadIdx.x; k < 1024; k += kThreads) s_pos[k] = g_hilbert.pos[k];
+  for (int k = threadIdx.x; k < 16384 / 8; k += kThreads) ((uint4*)s_pos)[k] = ((const uint4*)g_hilbert_wide)[k];
   if (kKind != kInXYZ) {
     for (int k = threadIdx.x; k < sc_tab::kTableSize * 4; k += kThreads) (&s_sc[0][0])[k] = (&g_sincos_tab[0][0])[k];
   }
@@ -67,7 +78,7 @@ encode_kernel(const void* __restrict__ in, size_t n, const EncodeOut o) {
       face = latlng_to_face_fij(lat, lng, s_sc, o.force_cr != 0, &p, &fi, &fj, &sensitive);
     }
     if (kKind == kInXYZ) face = point_to_face_fij(p, &fi, &fj);
-    const uint64_t id = from_face_ij(face, fij_to_ij(fi), fij_to_ij(fj), s_pos);
+    const uint64_t id = from_face_ij_wide(face, fij_to_ij(fi), fij_to_ij(fj), s_pos);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (k < o.levels.n) {
@@ -106,6 +117,8 @@ static cudaError_t launch_encode_k(const void* in, size_t n, const EncodeOut& o,
 
 cudaError_t launch_encode(InputKind kind, const void* in, size_t n, const EncodeOut& o, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
+  cudaError_t te = ensure_wide_table();
+  if (te != cudaSuccess) return te;
   switch (kind) {
     case kInXYZ: return launch_encode_k<kInXYZ>(in, n, o, st);
     case kInLatLngRad: return launch_encode_k<kInLatLngRad>(in, n, o, st);

@@ -33,4 +33,22 @@ constexpr HilbertTables MakeHilbertTables() {
 
 inline constexpr HilbertTables kHilbert = MakeHilbertTables();
 
+// 6-bit position table (see from_face_ij_wide): out[(i6 << 8) | (j6 << 2) | orientation] = (pos12 << 2) | orientation'.
+inline void MakeWideHilbert(uint16_t* out /* 16384 entries */) {
+  const int ij_to_pos[4][4] = {{0, 1, 3, 2}, {0, 3, 1, 2}, {2, 3, 1, 0}, {2, 1, 3, 0}};
+  const int pos_to_orient[4] = {1, 0, 0, 3};
+  for (int o = 0; o < 4; ++o)
+    for (int i = 0; i < 64; ++i)
+      for (int j = 0; j < 64; ++j) {
+        int pos = 0, orient = o;
+        for (int b = 5; b >= 0; --b) {
+          int ij = (((i >> b) & 1) << 1) | ((j >> b) & 1);
+          int p = ij_to_pos[orient][ij];
+          pos = (pos << 2) | p;
+          orient ^= pos_to_orient[p];
+        }
+        out[(i << 8) | (j << 2) | o] = (uint16_t)((pos << 2) | orient);
+      }
+}
+
 }  // namespace s2b

@@ -18,6 +18,17 @@
 namespace s2b {
 
 __device__ const HilbertTables g_hilbert_ix = kHilbert;
+__device__ uint16_t g_hilbert_wide_ix[16384];   // uploaded on first use per device
+
+static cudaError_t ensure_wide_table_ix() {
+  static thread_local int done_for_device = -1;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess || dev == done_for_device) return e;
+  e = cudaMemcpyToSymbol(g_hilbert_wide_ix, wide_hilbert_host(), 16384 * sizeof(uint16_t));
+  if (e == cudaSuccess) done_for_device = dev;
+  return e;
+}
 
 constexpr int kThreads = 256;
 
@@ -87,8 +98,8 @@ template <int kCtasPerSm, int kPointsPerThread>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 locate_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint32_t n, HitWork* __restrict__ work, uint32_t capacity,
               unsigned int* __restrict__ counters, int interior_mode, uint8_t* __restrict__ flags, uint32_t* __restrict__ counts) {
-  __shared__ uint16_t s_pos[1024];
-  for (int k = threadIdx.x; k < 1024; k += kThreads) s_pos[k] = g_hilbert_ix.pos[k];
+  __shared__ uint16_t s_pos[16384];   // 6-bit Hilbert table
+  for (int k = threadIdx.x; k < 16384 / 8; k += kThreads) ((uint4*)s_pos)[k] = ((const uint4*)g_hilbert_wide_ix)[k];
   __syncthreads();
   constexpr uint32_t kSpan = kThreads * kPointsPerThread;
   const uint32_t stride = gridDim.x * kSpan;
@@ -110,7 +121,11 @@ locate_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint32_t n
       }
     }
 #pragma unroll
-    for (int t = 0; t < kPointsPerThread; ++t) cell[t] = locate_cell(ix, cellid_from_point(p[t], s_pos));
+    for (int t = 0; t < kPointsPerThread; ++t) {
+      double fi, fj;
+      const int face = point_to_face_fij(p[t], &fi, &fj);
+      cell[t] = locate_cell(ix, from_face_ij_wide(face, fij_to_ij(fi), fij_to_ij(fj), s_pos));
+    }
 #pragma unroll
     for (int t = 0; t < kPointsPerThread; ++t) {
       const uint32_t i = idx[t];
@@ -256,6 +271,10 @@ template <int kMode>
 static cudaError_t launch_query_t(const FlatIndexView& ix, const double* xyz, size_t n, int model, const QueryOut& out, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
   keep_pool_memory_once();
+  {
+    cudaError_t te = ensure_wide_table_ix();
+    if (te != cudaSuccess) return te;
+  }
   const size_t round = n < kRoundPoints ? n : kRoundPoints;
   HitWork* work = nullptr;
   unsigned int* counter = nullptr;

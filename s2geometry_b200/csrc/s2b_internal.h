@@ -28,6 +28,8 @@ cudaError_t launch_parent(const uint64_t* ids_dev, size_t n, int level, uint64_t
 cudaError_t launch_to_token(const uint64_t* ids_dev, size_t n, char* tokens16_dev, uint8_t* len_dev, cudaStream_t stream);
 
 void count_launch();
+// Host copy of the 16384-entry 6-bit Hilbert table (built once); each .cu uploads it to its own __device__ array.
+const uint16_t* wide_hilbert_host();
 int sm_count();  // SMs of the current device (cached)
 
 }  // namespace s2b

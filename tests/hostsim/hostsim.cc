@@ -77,3 +77,15 @@ void hs_cellid_to_token(const uint64_t* ids, size_t n, char* tok16, uint8_t* len
 }
 
 }  // extern "C"
+
+// from_face_ij (4-bit table, the reference's layout) vs from_face_ij_wide (6-bit table): returns the number of mismatches.
+extern "C" uint64_t hs_check_wide_hilbert(const uint32_t* ij, size_t n) {
+  static uint16_t wide[16384];
+  static bool init = false;
+  if (!init) { MakeWideHilbert(wide); init = true; }
+  uint64_t bad = 0;
+  for (size_t k = 0; k < n; ++k)
+    for (int face = 0; face < 6; ++face)
+      bad += from_face_ij(face, ij[2 * k], ij[2 * k + 1], kHilbert.pos) != from_face_ij_wide(face, ij[2 * k], ij[2 * k + 1], wide);
+  return bad;
+}

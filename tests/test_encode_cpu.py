@@ -169,3 +169,12 @@ def test_filtered_ids_equal_correctly_rounded_ids(hostsim, ref):
     # and against the reference (glibc): any difference must be a boundary-sensitive point
     want = ref.encode_latlng(bl, 30, 1)
     assert (fast != want).mean() < 0.01
+
+
+def test_wide_hilbert_table_equals_reference_layout(hostsim):
+    """The kernels use a 6-bit (16384-entry) Hilbert table, 5 lookups; it must agree with the reference's 4-bit layout."""
+    rng = np.random.default_rng(3)
+    ij = rng.integers(0, 1 << 30, (500000, 2), dtype=np.uint32)
+    ij[:8] = [[0, 0], [(1 << 30) - 1, (1 << 30) - 1], [0, (1 << 30) - 1], [(1 << 30) - 1, 0], [1, 2], [63, 64], [4095, 4096], [1 << 29, 1 << 29]]
+    hostsim.hs_check_wide_hilbert.restype = ctypes.c_uint64
+    assert hostsim.hs_check_wide_hilbert(vp(ij), ctypes.c_size_t(len(ij))) == 0
