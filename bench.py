@@ -32,9 +32,9 @@ LEVELS = [12, 20, 30]
 TOKEN_LEVEL_INDEX = 2
 N_POINTS = 100_000_000
 BYTES_PER_POINT = 16 + 8 * len(LEVELS) + 16 + 1   # algorithmic HBM bytes per point of the fused kernel
-# FP64-pipe instructions per point on the common path, counted in the SASS of encode_kernel<1>;
-# used only for the informational fp64 roofline.
-FP64_INSTR_PER_POINT = 330
+# FP64-pipe instructions (DADD/DMUL/DFMA/DSETP) executed per point by encode_kernel<latlng>, measured with ncu's
+# per-instruction counts (profiles/r1_encode_latlng_final_ncu.json); used only for the informational fp64 roofline.
+FP64_INSTR_PER_POINT = 113
 METRIC = "points/sec (S2CellId encode, lat/lng -> levels 12/20/30 + ToToken)"
 
 
@@ -227,6 +227,38 @@ def pip_section(args, torch, dev, rank, world):
     return out
 
 
+def encode_xyz_section(args, torch, dev, rank, world):
+    """BASELINE configs[0] on the GPU: S2Points -> level-30 S2CellId (32 algorithmic bytes per point)."""
+    from s2geometry_b200 import cellid, synth
+    n = args.points
+    pts = synth.sphere_points_cuda(n, 1 + rank, dev)
+    ids = None
+    for _ in range(3):
+        ids = cellid.from_points(pts, 30)
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        ids = cellid.from_points(pts, 30)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    hbm_peak, _ = peaks()
+    ach = 32 * n / (ms * 1e-3) / 1e9
+    out = {"workload": "configs[0]: %d uniform S2Points -> level-30 S2CellId (per GPU)" % n, "points_per_s": n / (ms * 1e-3), "ms_per_step": ms,
+           "bytes_per_point": 32, "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import reflib  # cpu_baseline leg
+            ref = reflib.load()
+            sample = pts[:20_000_000].cpu().numpy()
+            t0 = time.perf_counter(); want = ref.encode_points(sample, 30, ref.hardware_threads()); dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": len(sample) / dt, "unit": "points/s", "cores": ref.hardware_threads(), "kind": "reference",
+                                   "sample": "first 20M points", "parity_on_sample": bool((ids[:20_000_000].cpu().numpy().view(np.uint64) == want).all())}
+        except Exception as e:
+            out["cpu_baseline"] = {"unavailable": str(e)}
+    return out
+
+
 def join_section(args, torch, dev, rank, world):
     """BASELINE configs[3]: spatial join, `join_points` uniform points (default 1B, sharded over the ranks: strong
     scaling) vs 10k synthetic polygons -> per-polygon hit counts; the only collective is the NCCL all-reduce of the
@@ -243,7 +275,7 @@ def join_section(args, torch, dev, rank, world):
     build_s = time.perf_counter() - t0
     ix = ShapeIndex(flat)
     query = ContainsPointQuery(ix, 1)
-    n_total = args.join_points
+    n_total = args.join_points   # each rank draws its own shard (independent seeds): a statistically equivalent global set
     lo, hi = sdist.shard_range(n_total, rank, world)
     n = hi - lo
     pts = synth.sphere_points_cuda(n, 1000 + rank, dev)
@@ -411,8 +443,11 @@ def run_gpu(args):
     del h_ll, h_ids, h_tok, h_len, ids, tok, ln, ll
     torch.cuda.empty_cache()
     pip = None
+    enc_xyz = None
     if not args.no_pip:
         try:
+            enc_xyz = encode_xyz_section(args, torch, dev, rank, world)
+            torch.cuda.empty_cache()
             pip = pip_section(args, torch, dev, rank, world)
         except Exception as e:
             pip = {"error": repr(e)}
@@ -439,7 +474,7 @@ def run_gpu(args):
             "data": "synthetic",
             "config": {"workload": "configs[1]: 100M lat/lng (radians, uniform on sphere) per GPU -> S2CellId at levels 12/20/30 + ToToken(level 30)",
                        "points_per_gpu": n, "levels": LEVELS, "l2_policy": "inputs (1.6 GB) and outputs (4.1 GB) per step exceed the 126 MB L2",
-                       "kernel": "encode_kernel<latlng> (1 launch per step)"},
+                       "kernel": "encode_kernel<latlng> (1 launch per step: fast sin/cos filter + correctly rounded path for boundary-sensitive points, fused parent/ToToken epilogues)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": None, "peak_source": peak_src, "bytes_per_point": BYTES_PER_POINT, "kernel_ms": kern_ms, "fp64": fp64},
             "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": (8 * len(LEVELS) + 17) * n,
@@ -447,6 +482,8 @@ def run_gpu(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if enc_xyz is not None:
+            line["encode_xyz"] = enc_xyz
         if pip is not None:
             line["pip"] = pip
         if join is not None:
