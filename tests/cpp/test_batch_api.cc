@@ -1,0 +1,70 @@
+// tests/cpp/test_batch_api.cc — exercises include/s2b/s2b_batch.h (the C++ sugar over the C ABI) the way a C++ caller of
+// the reference would use the batch entry points. Needs a GPU to run; tests/test_cpp_api.py compiles it everywhere.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "s2b/s2b_batch.h"
+
+#define CHECK(c) do { if (!(c)) { std::fprintf(stderr, "CHECK failed %s:%d: %s (%s)\n", __FILE__, __LINE__, #c, s2b::LastError()); return 1; } } while (0)
+
+static s2b::Point FromDegrees(double lat, double lng) {
+  const double d = M_PI / 180;
+  return s2b::Point{std::cos(lng * d) * std::cos(lat * d), std::sin(lng * d) * std::cos(lat * d), std::sin(lat * d)};
+}
+
+int main() {
+  // S2CellId(S2Point(1,2,3)) and S2CellId(S2LatLng::FromDegrees(39,-120))  (s2region_test.cc:66-68)
+  std::vector<s2b::Point> pts = {{1, 2, 3}};
+  std::vector<uint64_t> ids;
+  CHECK(s2b::S2CellIdBatch::FromPoints(pts, &ids));
+  CHECK(ids[0] == 0x43CC5DF3E09213F5ull);
+  s2b::LatLng ll{39 * M_PI / 180, -120 * M_PI / 180};
+  uint64_t id2 = 0;
+  CHECK(s2b::S2CellIdBatch::FromLatLngs(&ll, 1, &id2));
+  CHECK(id2 == 0x809984952A960863ull);
+  uint64_t parent = 0;
+  CHECK(s2b::S2CellIdBatch::Parent(&id2, 1, 10, &parent));
+  CHECK((parent & 0x1FFFFFFFFFFull) == (1ull << 40));   // lsb of a level-10 cell is bit 2*(30-10)
+  auto tok = s2b::S2CellIdBatch::ToTokens({0x487604C489F841C3ull, 0x4870000000000000ull, 0});
+  CHECK(tok.size() == 3 && tok[0] == "487604c489f841c3" && tok[1] == "487" && tok[2] == "X");
+
+  // index "0:0 # -1:1, 1:1 # 0:5, 0:7, 2:6" (s2contains_point_query_test.cc:55-123) built by the library's own builder
+  std::vector<s2b::Point> verts = {FromDegrees(0, 0), FromDegrees(-1, 1), FromDegrees(1, 1), FromDegrees(0, 5), FromDegrees(0, 7), FromDegrees(2, 6)};
+  int8_t dims[3] = {0, 1, 2};
+  uint32_t shape_chain_begin[4] = {0, 1, 2, 3};
+  uint32_t chain_vertex_begin[4] = {0, 1, 3, 6};
+  s2b::DeviceShapeIndex index;
+  CHECK(index.InitFromShapes(3, dims, shape_chain_begin, chain_vertex_begin, &verts[0].x));
+  CHECK(index.num_shape_ids() == 3);
+  std::vector<s2b::Point> q = {FromDegrees(0, 0), FromDegrees(-1, 1), FromDegrees(1, 1), FromDegrees(0, 2), FromDegrees(0, 5),
+                               FromDegrees(0, 7), FromDegrees(2, 6), FromDegrees(1, 6), FromDegrees(10, 10)};
+  const uint8_t want_open[9] = {0, 0, 0, 0, 0, 0, 0, 1, 0}, want_semi[9] = {0, 0, 0, 0, 0, 1, 0, 1, 0}, want_closed[9] = {1, 1, 1, 0, 1, 1, 1, 1, 0};
+  std::vector<uint8_t> out(q.size());
+  CHECK(s2b::S2ContainsPointQueryBatch(&index, s2b::S2VertexModel::OPEN).Contains(q.data(), q.size(), out.data()));
+  CHECK(std::memcmp(out.data(), want_open, 9) == 0);
+  CHECK(s2b::S2ContainsPointQueryBatch(&index, s2b::S2VertexModel::SEMI_OPEN).Contains(q.data(), q.size(), out.data()));
+  CHECK(std::memcmp(out.data(), want_semi, 9) == 0);
+  s2b::S2ContainsPointQueryBatch closed(&index, s2b::S2VertexModel::CLOSED);
+  CHECK(closed.Contains(q.data(), q.size(), out.data()));
+  CHECK(std::memcmp(out.data(), want_closed, 9) == 0);
+  CHECK(closed.ShapeContains(2, q.data(), q.size(), out.data()));
+  CHECK(out[4] == 1 && out[7] == 1 && out[0] == 0);
+  std::vector<uint64_t> counts;
+  CHECK(closed.CountContainingShapes(q.data(), q.size(), &counts));
+  CHECK(counts.size() == 3 && counts[0] == 1 && counts[1] == 2 && counts[2] == 4);
+  std::vector<uint32_t> offsets;
+  std::vector<int32_t> shape_ids;
+  CHECK(closed.GetContainingShapeIds(q.data(), q.size(), &offsets, &shape_ids));
+  CHECK(offsets.size() == 10 && offsets[9] == 7 && shape_ids.size() == 7 && shape_ids[0] == 0);
+
+  // S2CellUnion::Contains: Trondheim (python/s2geometry_test.py:254-259)
+  uint64_t cells[2] = {0x466D319000000000ull, 0x466D31B000000000ull};
+  s2b::Point trondheim = FromDegrees(63.431052, 10.395083);
+  uint8_t hit = 0;
+  CHECK(s2b::S2CellUnionContainsBatch(cells, 2, &trondheim, 1, &hit));
+  CHECK(hit == 1);
+  std::printf("test_batch_api: all checks passed\n");
+  return 0;
+}
