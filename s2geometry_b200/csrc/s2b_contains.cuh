@@ -116,7 +116,23 @@ S2B_HD bool clip_contains(const FlatIndexView& ix, const FlatClip& clip, const P
       const P3 c = edge_v0(e), d = edge_v1(e);
       const int acb = -triage_sign(a_cross_b, c);
       const int bda = triage_sign(a_cross_b, d);
-      const int r = edge_slow_path(a, b, c, d, acb, bda, model);
+      // Common case of a pending edge: both signs certain and equal (C and D strictly on opposite sides of AB). Then
+      // s2edge_crosser.cc:76-96 reduces to: shared vertex -> 0, degenerate edge -> -1, else compare with the signs
+      // of B and A against CD. Done inline when those two are certain too; anything uncertain goes out of line.
+      int r = -1;
+      bool resolved = false;
+      if (acb != 0 && bda != 0) {
+        const bool shared = eq(a, c) || eq(a, d) || eq(b, c) || eq(b, d);
+        const bool degenerate = eq(a, b) || eq(c, d);
+        if (!shared && !degenerate) {
+          const P3 c_cross_d = cross(c, d);
+          const int cbd = -triage_sign(c_cross_d, b);
+          const int dac = triage_sign(c_cross_d, a);
+          if (cbd != 0 && cbd != acb) { r = 0; resolved = true; }
+          else if (cbd != 0 && dac != 0) { r = (dac == acb) ? 1 : 0; resolved = true; }
+        }
+      }
+      if (!resolved) r = edge_slow_path(a, b, c, d, acb, bda, model);
       if (r >= 2) return r == 3;
       inside ^= (r != 0);
     }
