@@ -103,6 +103,16 @@ int s2b_cellid_parent_dev(const uint64_t* ids_dev, size_t n, int level, uint64_t
 int s2b_cellid_to_token(const uint64_t* ids, size_t n, char* tokens16_out, uint8_t* len_out);
 int s2b_cellid_to_token_dev(const uint64_t* ids_dev, size_t n, char* tokens16_out_dev, uint8_t* len_out_dev, void* stream);
 
+/* The step after encode in most pipelines: batched inverses.
+ * S2CellId::ToPoint (s2cell_id.h:184; GetCenterSiTi :555-581, FaceSiTitoXYZ s2coords.cc:68-72, Normalize): the unit
+ * vector of each cell's centre, bit-exact with the reference. xyz_out = n x 3 doubles. */
+int s2b_cellid_to_point(const uint64_t* ids, size_t n, double* xyz_out);
+int s2b_cellid_to_point_dev(const uint64_t* ids_dev, size_t n, double* xyz_out_dev, void* stream);
+/* S2CellId::FromToken (s2cell_id.cc:235-254): tokens as produced by s2b_cellid_to_token (16-byte slots + lengths);
+ * malformed tokens decode to 0 (S2CellId::None()). */
+int s2b_cellid_from_token(const char* tokens16, const uint8_t* len, size_t n, uint64_t* ids_out);
+int s2b_cellid_from_token_dev(const char* tokens16_dev, const uint8_t* len_dev, size_t n, uint64_t* ids_out_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Shape index: a flattened, device-resident MutableS2ShapeIndex.
  *

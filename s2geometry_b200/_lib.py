@@ -35,6 +35,10 @@ SIGNATURES = {
     "s2b_cellid_parent_dev": (_i, [_vp, _sz, _i, _vp, _vp]),
     "s2b_cellid_to_token": (_i, [_vp, _sz, _vp, _vp]),
     "s2b_cellid_to_token_dev": (_i, [_vp, _sz, _vp, _vp, _vp]),
+    "s2b_cellid_to_point": (_i, [_vp, _sz, _vp]),
+    "s2b_cellid_to_point_dev": (_i, [_vp, _sz, _vp, _vp]),
+    "s2b_cellid_from_token": (_i, [_vp, _vp, _sz, _vp]),
+    "s2b_cellid_from_token_dev": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "s2b_index_build": (_i, [_i, _vp, _vp, _vp, _vp, _i, _vp]),
     "s2b_built_index_flat": (_i, [_vp, _vp, _vp]),
     "s2b_built_index_destroy": (None, [_vp]),

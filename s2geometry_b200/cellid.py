@@ -194,6 +194,38 @@ def to_token(ids, out=None, out_len=None):
     return tok, ln
 
 
+def to_point(ids):
+    """S2CellId::ToPoint element-wise -> (N,3) float64 unit vectors (cell centres)."""
+    lib = _lib.load()
+    if _is_tensor(ids):
+        ids = _tensor_in(ids, torch.int64, 0)
+        out = torch.empty((ids.numel(), 3), dtype=torch.float64, device=ids.device)
+        with torch.cuda.device(ids.device):
+            _lib.check(lib.s2b_cellid_to_point_dev(_ptr(ids), ids.numel(), _ptr(out), _stream()))
+        return out
+    ids = _np_in(ids, np.uint64, 0)
+    out = np.empty((ids.size, 3), dtype=np.float64)
+    _lib.check(lib.s2b_cellid_to_point(_ptr(ids), ids.size, _ptr(out)))
+    return out
+
+
+def from_token(tokens, lengths):
+    """S2CellId::FromToken element-wise: tokens (N,16) uint8 slots + lengths (N,) uint8 -> ids (0 for malformed tokens)."""
+    lib = _lib.load()
+    if _is_tensor(tokens):
+        tokens = _tensor_in(tokens, torch.uint8, 16)
+        lengths = _tensor_in(lengths, torch.uint8, 0)
+        out = torch.empty(tokens.shape[0], dtype=torch.int64, device=tokens.device)
+        with torch.cuda.device(tokens.device):
+            _lib.check(lib.s2b_cellid_from_token_dev(_ptr(tokens), _ptr(lengths), tokens.shape[0], _ptr(out), _stream()))
+        return out
+    tokens = _np_in(tokens, np.uint8, 16)
+    lengths = _np_in(lengths, np.uint8, 0)
+    out = np.empty(tokens.shape[0], dtype=np.uint64)
+    _lib.check(lib.s2b_cellid_from_token(_ptr(tokens), _ptr(lengths), tokens.shape[0], _ptr(out)))
+    return out
+
+
 def tokens_to_str(tokens, lengths):
     """Convenience: decode (N,16) uint8 token slots into Python strings."""
     tokens = tokens.cpu().numpy() if _is_tensor(tokens) else np.asarray(tokens)

@@ -300,6 +300,46 @@ int s2b_cellid_to_token_dev(const uint64_t* ids_dev, size_t n, char* tok_dev, ui
   return e == cudaSuccess ? S2B_OK : cuda_fail(e, "token launch");
 }
 
+int s2b_cellid_to_point(const uint64_t* ids, size_t n, double* xyz_out) {
+  if (n == 0) return S2B_OK;
+  if (!ids || !xyz_out) return set_error(S2B_EINVAL, "null pointer");
+  OutSpec outs[1] = {{xyz_out, 24, 1}};
+  return run_pipelined(ids, 8, n, outs, 1, [&](const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
+    cudaError_t e = launch_to_point((const uint64_t*)in_dev, cnt, (double*)out_dev[0], st);
+    return e == cudaSuccess ? S2B_OK : cuda_fail(e, "to_point launch");
+  });
+}
+int s2b_cellid_to_point_dev(const uint64_t* ids_dev, size_t n, double* xyz_out_dev, void* stream) {
+  if (n == 0) return S2B_OK;
+  if (!ids_dev || !xyz_out_dev) return set_error(S2B_EINVAL, "null pointer");
+  cudaError_t e = launch_to_point(ids_dev, n, xyz_out_dev, (cudaStream_t)stream);
+  return e == cudaSuccess ? S2B_OK : cuda_fail(e, "to_point launch");
+}
+int s2b_cellid_from_token_dev(const char* tokens16_dev, const uint8_t* len_dev, size_t n, uint64_t* ids_out_dev, void* stream) {
+  if (n == 0) return S2B_OK;
+  if (!tokens16_dev || !len_dev || !ids_out_dev) return set_error(S2B_EINVAL, "null pointer");
+  if ((uintptr_t)tokens16_dev % 16) return set_error(S2B_EINVAL, "tokens16_dev must be 16-byte aligned");
+  cudaError_t e = launch_from_token(tokens16_dev, len_dev, n, ids_out_dev, (cudaStream_t)stream);
+  return e == cudaSuccess ? S2B_OK : cuda_fail(e, "from_token launch");
+}
+int s2b_cellid_from_token(const char* tokens16, const uint8_t* len, size_t n, uint64_t* ids_out) {
+  if (n == 0) return S2B_OK;
+  if (!tokens16 || !len || !ids_out) return set_error(S2B_EINVAL, "null pointer");
+  // two input arrays: stage the lengths next to the tokens (17 bytes per token) through one pipelined pass each
+  char* d_tok = nullptr; uint8_t* d_len = nullptr; uint64_t* d_ids = nullptr;
+  int rc = S2B_OK;
+  cudaError_t e = cudaMalloc(&d_tok, 16 * n);
+  if (e == cudaSuccess) e = cudaMalloc(&d_len, n);
+  if (e == cudaSuccess) e = cudaMalloc(&d_ids, 8 * n);
+  if (e == cudaSuccess) e = cudaMemcpy(d_tok, tokens16, 16 * n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_len, len, n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = launch_from_token(d_tok, d_len, n, d_ids, nullptr);
+  if (e == cudaSuccess) e = cudaMemcpy(ids_out, d_ids, 8 * n, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) rc = cuda_fail(e, "from_token");
+  cudaFree(d_tok); cudaFree(d_len); cudaFree(d_ids);
+  return rc;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Host-pointer forms of the index queries: the points stream through the same three-slot pipeline.
 

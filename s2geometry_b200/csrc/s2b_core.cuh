@@ -241,4 +241,24 @@ S2B_HD int cellid_to_token(uint64_t id, uint32_t out[4]) {
   return len;
 }
 
+// S2CellId::FromToken (s2cell_id.cc:235-254) from a 16-byte slot + length: hex digits (either case) placed from the
+// top nibble down; any other character, or a length above 16, gives S2CellId::None() (0). "X" therefore decodes to 0.
+S2B_HD uint64_t cellid_from_token(const unsigned char* tok, int len) {
+  if (len > 16 || len < 0) return 0;
+  uint64_t id = 0;
+  for (int i = 0; i < len; ++i) {
+    const unsigned c = tok[i];
+    uint64_t d;
+    if (c - '0' <= 9u) d = c - '0';
+    else if (c - 'a' <= 5u) d = c - 'a' + 10;
+    else if (c - 'A' <= 5u) d = c - 'A' + 10;
+    else return 0;
+    id |= d << (60 - 4 * i);
+  }
+  return id;
+}
+
+// S2CellId::level() (s2cell_id.h:595-603): -1 is never returned here; invalid ids give whatever the formula gives.
+S2B_HD int cellid_level(uint64_t id) { return 30 - (ctz64(id | (1ull << 63) ) >> 1); }
+
 }  // namespace s2b

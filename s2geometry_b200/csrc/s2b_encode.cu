@@ -143,6 +143,44 @@ __global__ void __launch_bounds__(kThreads) token_kernel(const uint64_t* __restr
   }
 }
 
+// S2CellId::ToPoint (s2cell_id.h:184, :555-581; s2coords.cc:68-72): inverse Hilbert table (2 KB) in shared memory.
+__global__ void __launch_bounds__(kThreads) to_point_kernel(const uint64_t* __restrict__ ids, size_t n, double* __restrict__ xyz) {
+  __shared__ uint16_t s_ij[1024];
+  for (int k = threadIdx.x; k < 1024; k += kThreads) s_ij[k] = g_hilbert.ij[k];
+  __syncthreads();
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    const P3 p = cellid_to_point(__ldcs(ids + i), s_ij);
+    double* q = xyz + 3 * i;
+    __stcs(q, p.x); __stcs(q + 1, p.y); __stcs(q + 2, p.z);
+  }
+}
+
+// S2CellId::FromToken (s2cell_id.cc:235-254).
+__global__ void __launch_bounds__(kThreads) from_token_kernel(const uint4* __restrict__ tok, const uint8_t* __restrict__ len, size_t n, uint64_t* __restrict__ ids) {
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    const uint4 t = __ldcs(tok + i);
+    unsigned char b[16];
+    *(uint4*)b = t;
+    __stcs(ids + i, cellid_from_token(b, len[i]));
+  }
+}
+
+cudaError_t launch_to_point(const uint64_t* ids, size_t n, double* xyz, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  to_point_kernel<<<grid_for(n, (const void*)to_point_kernel), kThreads, 0, st>>>(ids, n, xyz);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_from_token(const char* tok, const uint8_t* len, size_t n, uint64_t* ids, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  from_token_kernel<<<grid_for(n, (const void*)from_token_kernel), kThreads, 0, st>>>((const uint4*)tok, len, n, ids);
+  count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_parent(const uint64_t* ids, size_t n, int level, uint64_t* out, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
   parent_kernel<<<grid_for(n, (const void*)parent_kernel), kThreads, 0, st>>>(ids, n, level, out);

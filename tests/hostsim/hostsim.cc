@@ -89,3 +89,7 @@ extern "C" uint64_t hs_check_wide_hilbert(const uint32_t* ij, size_t n) {
       bad += from_face_ij(face, ij[2 * k], ij[2 * k + 1], kHilbert.pos) != from_face_ij_wide(face, ij[2 * k], ij[2 * k + 1], wide);
   return bad;
 }
+
+extern "C" void hs_cellid_from_token(const char* tok16, const uint8_t* len, size_t n, uint64_t* out) {
+  for (size_t i = 0; i < n; ++i) out[i] = cellid_from_token((const unsigned char*)tok16 + 16 * i, len[i]);
+}

@@ -210,3 +210,15 @@ def test_own_builder_whole_face_and_full_polygon(hostsim, ref):
     assert (hs_query(hostsim, flat, pts, 1, 2)[0] == ri.shape_histogram(pts, 1)).all()
     got, _ = hs_query(hostsim, flat, pts, 1, 4)
     assert (got[: 300000] == 1).all()   # away from the boundary every point is in exactly one of the two
+
+
+def test_cells_with_hundreds_of_edges(hostsim, ref):
+    """max_edges_per_cell = 1000 puts hundreds of edges in one clip: exercises the 64-edge chunks of the pending mask."""
+    soup, v = scenes.loop_scene(3000)
+    flat = own_flat(soup, 1000)
+    assert np.diff(flat.clip_edge_begin.astype(np.int64)).max() > 200
+    ri = ref.index_create(soup)
+    u, b, d = scenes.loop_points(v, 20000, 100000, 35)
+    for pts in (b, d):
+        for m in (0, 1, 2):
+            assert (hs_query(hostsim, flat, pts, m, 0)[0] == ri.contains(pts, m)).all()

@@ -203,3 +203,17 @@ def test_own_builder_index_on_gpu(torch_cuda, ref):
     q = scenes.axis_aligned_queries()
     for m in (0, 1, 2):
         assert (ContainsPointQuery(ix3, m).shape_histogram(q) == ri3.shape_histogram(q, m, 1)).all()
+
+
+def test_cells_with_hundreds_of_edges_on_gpu(torch_cuda, ref):
+    from s2geometry_b200.index import ContainsPointQuery, ShapeIndex, build_flat_index
+    soup, v = scenes.loop_scene(3000)
+    flat = build_flat_index(soup, 1000)
+    assert np.diff(flat.clip_edge_begin.astype(np.int64)).max() > 200
+    ix = ShapeIndex(flat)
+    ri = ref.index_create(soup)
+    u, b, d = scenes.loop_points(v, 20000, 300000, 35)
+    for pts in (b, d):
+        for m in (0, 1, 2):
+            assert (ContainsPointQuery(ix, m).contains(pts) == ri.contains(pts, m)).all()
+            assert (ContainsPointQuery(ix, m).shape_histogram(pts) == ri.shape_histogram(pts, m)).all()
