@@ -34,7 +34,7 @@ N_POINTS = 100_000_000
 BYTES_PER_POINT = 16 + 8 * len(LEVELS) + 16 + 1   # algorithmic HBM bytes per point of the fused kernel
 # FP64-pipe instructions (DADD/DMUL/DFMA/DSETP) executed per point by encode_kernel<latlng>, measured with ncu's
 # per-instruction counts (profiles/r1_encode_latlng_final_ncu.json); used only for the informational fp64 roofline.
-FP64_INSTR_PER_POINT = 113
+FP64_INSTR_PER_POINT = 109
 METRIC = "points/sec (S2CellId encode, lat/lng -> levels 12/20/30 + ToToken)"
 
 

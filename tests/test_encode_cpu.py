@@ -178,3 +178,22 @@ def test_wide_hilbert_table_equals_reference_layout(hostsim):
     ij[:8] = [[0, 0], [(1 << 30) - 1, (1 << 30) - 1], [0, (1 << 30) - 1], [(1 << 30) - 1, 0], [1, 2], [63, 64], [4095, 4096], [1 << 29, 1 << 29]]
     hostsim.hs_check_wide_hilbert.restype = ctypes.c_uint64
     assert hostsim.hs_check_wide_hilbert(vp(ij), ctypes.c_size_t(len(ij))) == 0
+
+
+def test_from_token_hostsim(hostsim, ref):
+    fx = util.fixture("encode_fixture.npz")
+    tok, ln, ids = fx["tok"], fx["tok_len"], fx["tok_ids"]
+    out = np.empty(len(ids), np.uint64)
+    hostsim.hs_cellid_from_token(vp(tok), vp(ln), ctypes.c_size_t(len(ids)), vp(out))
+    assert (out == ref.from_token(tok, ln)).all()
+    assert (out[ids != 0] == ids[ids != 0]).all()          # round trip (the token "X" of id 0 decodes to 0 too)
+    bad = np.zeros((4, 16), np.uint8); bl = np.array([8, 9, 8, 9], np.uint8)
+    for k, t in enumerate([b"876b e99", b"876bee99\n", b"876[ee99", b" 876bee99"]):   # s2cell_id_test.cc:362-368
+        bad[k, : len(t)] = np.frombuffer(t, np.uint8)
+    out = np.empty(4, np.uint64)
+    hostsim.hs_cellid_from_token(vp(bad), vp(bl), ctypes.c_size_t(4), vp(out))
+    assert (out == 0).all() and (ref.from_token(bad, bl) == 0).all()
+    up = np.zeros((1, 16), np.uint8); up[0, :3] = np.frombuffer(b"4AF", np.uint8)
+    o = np.empty(1, np.uint64)
+    hostsim.hs_cellid_from_token(vp(up), vp(np.array([3], np.uint8)), ctypes.c_size_t(1), vp(o))
+    assert o[0] == 0x4AF0000000000000 == ref.from_token(up, np.array([3], np.uint8))[0]

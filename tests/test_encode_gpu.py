@@ -156,3 +156,26 @@ def test_fast_filter_equals_correctly_rounded_on_device(torch_cuda, ref):
     got = fast_b.cpu().numpy().view(np.uint64)
     bad = got != want
     assert (flags_b.cpu().numpy()[bad] == 1).all()
+
+
+def test_to_point_and_from_token(torch_cuda, ref):
+    """Batched inverses (SURVEY.md §8f rank 2): S2CellId::ToPoint bit-exact, FromToken, token round trip."""
+    torch = torch_cuda
+    from s2geometry_b200 import cellid, synth
+    rng = np.random.default_rng(8)
+    leaf = cellid.from_points(synth.sphere_points(2_000_000, 21))
+    lv = rng.integers(0, 31, len(leaf))
+    lsb = np.uint64(1) << (2 * (30 - lv)).astype(np.uint64)
+    ids = (leaf & (~lsb + np.uint64(1))) | lsb                      # parent(level) with a per-id level
+    want = ref.to_point(ids)
+    assert (cellid.to_point(ids) == want).all()
+    d_ids = torch.from_numpy(ids.view(np.int64)).cuda()
+    assert (cellid.to_point(d_ids).cpu().numpy() == want).all()
+    # leaf cell of the centre of a cell is inside that cell (S2CellId.Inverses property, s2cell_id_test.cc:327-338)
+    back = cellid.from_points(want)
+    lo = ids - (lsb - np.uint64(1)); hi = ids + (lsb - np.uint64(1))
+    assert ((lo <= back) & (back <= hi)).all()
+    tok, ln = cellid.to_token(ids)
+    assert (cellid.from_token(tok, ln) == ids).all()
+    assert (cellid.from_token(torch.from_numpy(tok).cuda(), torch.from_numpy(ln).cuda()).cpu().numpy().view(np.uint64) == ids).all()
+    assert (ref.from_token(tok, ln) == ids).all()
