@@ -375,7 +375,10 @@ def run_gpu(args):
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = None
     if world > 1:
+        from s2geometry_b200 import dist as sdist_
+        numa_node = sdist_.bind_to_gpu_numa_node(local_rank)
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
@@ -488,7 +491,7 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": None, "peak_source": peak_src, "bytes_per_point": BYTES_PER_POINT, "kernel_ms": kern_ms, "fp64": fp64},
             "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": 16 * e2e_n, "d2h_bytes_per_step": (8 * len(LEVELS) + 17) * e2e_n, "points_per_gpu": e2e_n,
-                    "ms_per_step": 1e3 * float(t.item()), "matches_device_result": same},
+                    "ms_per_step": 1e3 * float(t.item()), "matches_device_result": same, "numa_node_rank0": numa_node},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

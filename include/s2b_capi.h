@@ -196,6 +196,11 @@ int s2b_containing_shapes_count_dev(const S2bIndex* index, const double* xyz_dev
 int s2b_containing_shapes_fill_dev(const S2bIndex* index, const double* xyz_dev, size_t n, int vertex_model,
                                    const uint32_t* offsets_dev, int32_t* shape_ids_out_dev, void* stream);
 
+/* Diagnostic: the index queries locate points with a single-precision pre-filter and fall back to the double-
+ * precision Locate for every point the filter cannot decide with certainty (DESIGN.md K3 phase A0). on != 0 sends all
+ * points through the double-precision path, which must give identical results (tests check it). Returns the old value. */
+int s2b_diag_force_exact_locate(int on);
+
 /* Number of predicate evaluations that needed the exact (arbitrary-precision) stage on the device since the
  * last reset, summed over all launches of this process on the current device. Resets the counter when reset != 0.
  * There is no CPU stage behind it: this is purely a statistic. */

@@ -55,6 +55,7 @@ SIGNATURES = {
     "s2b_containing_shapes_count_dev": (_i, [_vp, _vp, _sz, _i, _vp, _vp]),
     "s2b_containing_shapes_fill_dev": (_i, [_vp, _vp, _sz, _i, _vp, _vp, _vp]),
     "s2b_exact_stage_count": (_i, [_vp, _i]),
+    "s2b_diag_force_exact_locate": (_i, [_i]),
     "s2b_cellunion_contains": (_i, [_vp, _sz, _vp, _sz, _vp]),
     "s2b_cellunion_contains_dev": (_i, [_vp, _sz, _vp, _sz, _vp, _vp]),
 }

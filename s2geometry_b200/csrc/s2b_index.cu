@@ -96,8 +96,12 @@ struct WarpSlots {
 // over two homogeneous lists.
 template <int kCtasPerSm, int kPointsPerThread>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
-locate_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint32_t n, HitWork* __restrict__ work, uint32_t capacity,
-              unsigned int* __restrict__ counters, int interior_mode, uint8_t* __restrict__ flags, uint32_t* __restrict__ counts) {
+locate_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint32_t n_points, const uint32_t* __restrict__ list,
+              HitWork* __restrict__ work, uint32_t capacity, unsigned int* __restrict__ counters, int interior_mode,
+              uint8_t* __restrict__ flags, uint32_t* __restrict__ counts) {
+  // list == nullptr: points 0..n_points-1. Otherwise: the points whose indices are list[0..counters[2]) (entries equal
+  // to 0xFFFFFFFF are unused reservation slots) — the ones the FP32 pre-filter could not decide.
+  const uint32_t n = list ? counters[2] : n_points;
   __shared__ uint16_t s_pos[16384];   // 6-bit Hilbert table
   for (int k = threadIdx.x; k < 16384 / 8; k += kThreads) ((uint4*)s_pos)[k] = ((const uint4*)g_hilbert_wide_ix)[k];
   __syncthreads();
@@ -112,8 +116,10 @@ locate_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint32_t n
     P3 p[kPointsPerThread];
 #pragma unroll
     for (int t = 0; t < kPointsPerThread; ++t) {
-      idx[t] = base + t * kThreads + lane;
-      if (idx[t] < n) {
+      const uint32_t k = base + t * kThreads + lane;
+      idx[t] = 0xFFFFFFFFu;
+      if (k < n) idx[t] = list ? list[k] : k;
+      if (idx[t] != 0xFFFFFFFFu) {
         const double* q = xyz + 3 * (size_t)idx[t];
         p[t] = P3{__ldcs(q), __ldcs(q + 1), __ldcs(q + 2)};
       } else {
@@ -129,7 +135,8 @@ locate_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint32_t n
 #pragma unroll
     for (int t = 0; t < kPointsPerThread; ++t) {
       const uint32_t i = idx[t];
-      const int c = i < n ? cell[t] : -1;
+      const bool valid = i != 0xFFFFFFFFu;
+      const int c = valid ? cell[t] : -1;
       uint32_t interior = 0;
       if (c >= 0) interior = ix.interior_clips[c];
       uint8_t flag = 0;
@@ -141,7 +148,7 @@ locate_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint32_t n
         else if (interior_mode == 2) cnt = interior;
         else to_interior = true;
       }
-      if (i < n) {
+      if (valid) {
         if (flags) flags[i] = flag;
         if (counts) counts[i] = cnt;
       }
@@ -151,6 +158,128 @@ locate_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint32_t n
   }
   edge_slots.finish(work, capacity, +1, lane);
   interior_slots.finish(work, capacity, -1, lane);
+}
+
+// Phase A0: FP32 pre-filter for Locate. Most points are nowhere near a boundary that matters, so the face, (i,j) and
+// the lookup-table bucket are first computed in single precision (approximate reciprocal and square root: ~110
+// instructions instead of ~300), with a conservative error radius kFastRadius (in leaf cells) around the result:
+//   bucket kind EMPTY  and the point is > radius inside the bucket  -> certain miss
+//   bucket kind INSIDE (whole bucket inside index cell c), same margin -> certain hit of cell c
+//   anything else (mixed bucket, near a bucket/face boundary, NaN, ...) -> index appended to the "uncertain" list, which
+//   the exact FP64 kernel (locate_kernel) then processes. Results are therefore exactly those of the FP64 path.
+// Error budget: double->float inputs 2^-24 each, approximate division <= 2 ulp, sqrt 1 ulp, a few roundings: |u| error
+// < 5e-7, s error < 6e-7, i.e. < 650 leaf cells at 2^30; kFastRadius = 2048 leaves 3x margin. A wrong face choice needs
+// two |components| within 6e-8 of each other, which puts (i,j) within ~60 leaf cells of a face edge: inside the radius.
+constexpr int kFastRadius = 2048;
+
+struct U32Slots {   // like WarpSlots, for a list of point indices (sentinel 0xFFFFFFFF)
+  uint32_t next = 0, end = 0;
+  __device__ __forceinline__ void append(bool want, uint32_t value, uint32_t* list, unsigned int* counter, unsigned lane) {
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (!m) return;
+    const uint32_t k = (uint32_t)__popc(m);
+    if (next + k > end) {
+      for (uint32_t s = next + lane; s < end; s += 32) list[s] = 0xFFFFFFFFu;
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(counter, kSlotChunk);
+      next = __shfl_sync(0xffffffffu, base, 0);
+      end = next + kSlotChunk;
+    }
+    if (want) list[next + (uint32_t)__popc(m & ((1u << lane) - 1u))] = value;
+    next += k;
+  }
+  __device__ __forceinline__ void finish(uint32_t* list, unsigned lane) {
+    for (uint32_t s = next + lane; s < end; s += 32) list[s] = 0xFFFFFFFFu;
+  }
+};
+
+__device__ __forceinline__ int approx_leaf_coord(float w) {   // w = u or v  ->  approximate leaf index (may be off by < 650)
+  const float r = 0.5f * __fsqrt_rn(1.0f + fabsf(3.0f * w));
+  const float s = w >= 0.0f ? r : 1.0f - r;
+  return __float2int_rz(1073741824.0f * s);                     // saturating; NaN -> 0
+}
+
+template <int kPointsPerThread>
+__global__ void __launch_bounds__(kThreads, 6)
+locate_fast_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint32_t n, HitWork* __restrict__ work, uint32_t capacity,
+                   unsigned int* __restrict__ counters, uint32_t* __restrict__ uncertain, int interior_mode,
+                   uint8_t* __restrict__ flags, uint32_t* __restrict__ counts) {
+  __shared__ uint16_t s_pos[16384];   // 6-bit Hilbert table (only the top two steps are needed here)
+  for (int k = threadIdx.x; k < 16384 / 8; k += kThreads) ((uint4*)s_pos)[k] = ((const uint4*)g_hilbert_wide_ix)[k];
+  __syncthreads();
+  constexpr uint32_t kSpan = kThreads * kPointsPerThread;
+  const uint32_t stride = gridDim.x * kSpan;
+  const unsigned lane = threadIdx.x & 31u;
+  const int lut_level = (61 - ix.lut_shift) >> 1;               // 2..10
+  const int bucket_bits = 30 - lut_level;                       // log2 of the bucket size in leaf cells (>= 20)
+  const int bucket_mask = (1 << bucket_bits) - 1;
+  WarpSlots edge_slots, interior_slots;
+  U32Slots unc_slots;
+  for (uint32_t base = blockIdx.x * kSpan + (threadIdx.x & ~31u); base < n; base += stride) {
+#pragma unroll
+    for (int t = 0; t < kPointsPerThread; ++t) {
+      const uint32_t i = base + t * kThreads + lane;
+      const bool valid = i < n;
+      float x = 1.0f, y = 0.0f, z = 0.0f;
+      if (valid) {
+        const double* q = xyz + 3 * (size_t)i;
+        x = (float)__ldcs(q); y = (float)__ldcs(q + 1); z = (float)__ldcs(q + 2);
+      }
+      const float ax = fabsf(x), ay = fabsf(y), az = fabsf(z);
+      const int axis = ax > ay ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
+      const float m = axis == 0 ? x : (axis == 1 ? y : z);
+      const bool neg = m < 0.0f;
+      const float a = axis == 0 ? y : -x;
+      const float b = axis == 2 ? -y : z;
+      const float inv = __frcp_rn(m);
+      const int fi = approx_leaf_coord((neg ? b : a) * inv);
+      const int fj = approx_leaf_coord((neg ? a : b) * inv);
+      const int face = axis + (neg ? 3 : 0);
+      // certain only if both coordinates are well inside their lookup-table bucket (NaN/garbage gives fi = 0 or
+      // saturated values, which fail this test)
+      const int ri = fi & bucket_mask, rj = fj & bucket_mask;
+      bool certain = valid && fi >= 0 && fj >= 0 && fi < (1 << 30) && fj < (1 << 30) &&
+                     ri >= kFastRadius && ri <= bucket_mask - kFastRadius && rj >= kFastRadius && rj <= bucket_mask - kFastRadius;
+      // position bits of the top 12 levels (two table steps), then the bucket = top lut_level levels
+      uint32_t bits = (uint32_t)face & 1u;
+      bits += (((uint32_t)fi >> 24) & 63u) << 8; bits += (((uint32_t)fj >> 24) & 63u) << 2;
+      bits = s_pos[bits & 16383u];
+      uint32_t pos24 = (bits >> 2) << 12;
+      bits &= 3u;
+      bits += (((uint32_t)fi >> 18) & 63u) << 8; bits += (((uint32_t)fj >> 18) & 63u) << 2;
+      bits = s_pos[bits];
+      pos24 |= bits >> 2;
+      const uint32_t bucket = (((uint32_t)face << 24) | pos24) >> (24 - 2 * lut_level);
+      int c = -1;
+      if (certain) {
+        const uint32_t e0 = ix.lut[bucket];
+        const uint32_t kind = e0 & ~kLutIndexMask;
+        if (kind == kLutInside) c = (int)(e0 & kLutIndexMask);
+        else if (kind != kLutEmpty) certain = false;
+      }
+      uint32_t interior = 0;
+      if (certain && c >= 0) interior = ix.interior_clips[c];
+      uint8_t flag = 0;
+      uint32_t cnt = 0;
+      const bool to_edges = certain && c >= 0 && interior == 0;
+      bool to_interior = false;
+      if (certain && c >= 0 && interior != 0) {
+        if (interior_mode == 1) flag = 1;
+        else if (interior_mode == 2) cnt = interior;
+        else to_interior = true;
+      }
+      if (valid && certain) {          // uncertain points are written by the exact kernel
+        if (flags) flags[i] = flag;
+        if (counts) counts[i] = cnt;
+      }
+      edge_slots.append(to_edges, HitWork{i, c}, work, capacity, counters, +1, lane);
+      if (interior_mode == 0) interior_slots.append(to_interior, HitWork{i, c}, work, capacity, counters + 1, -1, lane);
+      unc_slots.append(valid && !certain, i, uncertain, counters + 2, lane);
+    }
+  }
+  edge_slots.finish(work, capacity, +1, lane);
+  interior_slots.finish(work, capacity, -1, lane);
+  unc_slots.finish(uncertain, lane);
 }
 
 template <int kMode, int kCtasPerSm>
@@ -248,6 +377,9 @@ static void keep_pool_memory_once() {
   done_for_device = dev;
 }
 
+// Diagnostics (s2b_diag_force_exact_locate): skip the FP32 pre-filter, every point goes through the FP64 Locate.
+static bool g_force_exact_locate = false;
+
 // Tuning knob (env S2B_LOCATE_VARIANT): CTAs per SM x points per thread of phase A. 0 = default.
 static int locate_variant() {
   static int v = -1;
@@ -278,12 +410,15 @@ static cudaError_t launch_query_t(const FlatIndexView& ix, const double* xyz, si
   const size_t round = n < kRoundPoints ? n : kRoundPoints;
   HitWork* work = nullptr;
   unsigned int* counter = nullptr;
-  // every warp of phase A can leave at most one partly used chunk per list
+  // every warp of phase A (two kernels) can leave at most one partly used chunk per list
   const size_t max_warps = (size_t)sm_count() * 8 * (kThreads / 32);
-  const size_t capacity = round + 2 * max_warps * kSlotChunk;
-  cudaError_t e = cudaMallocAsync((void**)&work, sizeof(HitWork) * capacity + 256, st);
+  const size_t capacity = round + 4 * max_warps * kSlotChunk;
+  const size_t unc_capacity = round + max_warps * kSlotChunk;
+  const bool use_fast = !g_force_exact_locate;
+  cudaError_t e = cudaMallocAsync((void**)&work, sizeof(HitWork) * capacity + 256 + (use_fast ? sizeof(uint32_t) * unc_capacity : 0), st);
   if (e != cudaSuccess) return e;
-  counter = (unsigned int*)((char*)work + sizeof(HitWork) * capacity);   // 8-byte aligned tail: [0] edge slots, [1] interior slots
+  counter = (unsigned int*)((char*)work + sizeof(HitWork) * capacity);   // 8-byte aligned tail: [0] edge slots, [1] interior slots, [2] uncertain
+  uint32_t* uncertain = (uint32_t*)((char*)counter + 256);
   const int pv = process_variant();
   void (*proc)(const FlatIndexView, const double*, const HitWork*, uint32_t, const unsigned int*, int, int, const QueryOut) =
       pv == 3 ? process_kernel<kMode, 3> : (pv == 4 ? process_kernel<kMode, 4> : process_kernel<kMode, 2>);
@@ -292,7 +427,7 @@ static cudaError_t launch_query_t(const FlatIndexView& ix, const double* xyz, si
   const int variant = locate_variant();
   for (size_t off = 0; off < n && e == cudaSuccess; off += round) {
     const size_t cnt = n - off < round ? n - off : round;
-    e = cudaMemsetAsync(counter, 0, 2 * sizeof(unsigned int), st);
+    e = cudaMemsetAsync(counter, 0, 4 * sizeof(unsigned int), st);
     if (e != cudaSuccess) break;
     QueryOut o = out;   // rebase per-point arrays to this round
     if (o.flags) o.flags += off;
@@ -300,9 +435,16 @@ static cudaError_t launch_query_t(const FlatIndexView& ix, const double* xyz, si
     if (o.offsets) o.offsets += off;
     uint8_t* fl = (kMode == kModeAny || kMode == kModeShape) ? o.flags : nullptr;
     uint32_t* pc = kMode == kModeCount ? o.per_point : nullptr;
+    const uint32_t* list = nullptr;
+    if (use_fast) {
+      locate_fast_kernel<2><<<grid_for_ix((cnt + 1) / 2, (const void*)locate_fast_kernel<2>), kThreads, 0, st>>>(
+          ix, xyz + 3 * off, (uint32_t)cnt, work, (uint32_t)capacity, counter, uncertain, interior_mode, fl, pc);
+      count_launch();
+      list = uncertain;
+    }
 #define S2B_LOCATE(C, P)                                                                                             \
   locate_kernel<C, P><<<grid_for_ix((cnt + P - 1) / P, (const void*)locate_kernel<C, P>), kThreads, 0, st>>>(            \
-      ix, xyz + 3 * off, (uint32_t)cnt, work, (uint32_t)capacity, counter, interior_mode, fl, pc)
+      ix, xyz + 3 * off, (uint32_t)cnt, list, work, (uint32_t)capacity, counter, interior_mode, fl, pc)
     switch (variant) {
       case 0: S2B_LOCATE(6, 1); break;
       case 1: S2B_LOCATE(8, 1); break;
@@ -466,6 +608,12 @@ int s2b_containing_shapes_fill_dev(const S2bIndex* ix, const double* xyz, size_t
   QueryOut o{}; o.offsets = offsets; o.shape_ids = shape_ids;
   cudaError_t e = launch_query_t<kModeFill>(ix->view, xyz, n, model, o, (cudaStream_t)stream);
   return e == cudaSuccess ? S2B_OK : cuda_fail(e, "fill launch");
+}
+
+int s2b_diag_force_exact_locate(int on) {
+  int old = g_force_exact_locate ? 1 : 0;
+  g_force_exact_locate = on != 0;
+  return old;
 }
 
 int s2b_exact_stage_count(uint64_t* count_out, int reset) {

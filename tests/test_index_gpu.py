@@ -217,3 +217,58 @@ def test_cells_with_hundreds_of_edges_on_gpu(torch_cuda, ref):
         for m in (0, 1, 2):
             assert (ContainsPointQuery(ix, m).contains(pts) == ri.contains(pts, m)).all()
             assert (ContainsPointQuery(ix, m).shape_histogram(pts) == ri.shape_histogram(pts, m)).all()
+
+
+def boundary_points(n, seed, levels=(2, 4, 6, 8, 9, 10, 12)):
+    """S2Points whose leaf coordinates sit within a few thousand leaf cells of level-L cell boundaries (the FP32
+    pre-filter's uncertainty radius is 2048 leaf cells), plus face edges and cube corners."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for lvl in levels:
+        step = 1 << (30 - lvl)
+        i = rng.integers(0, (1 << lvl) + 1, n) * step + rng.integers(-5000, 5001, n)
+        j = rng.integers(0, 1 << 30, n)
+        swap = rng.integers(0, 2, n).astype(bool)
+        fi = np.clip(np.where(swap, j, i), 0, 1 << 30).astype(np.float64) + rng.uniform(0, 1, n)
+        fj = np.clip(np.where(swap, i, j), 0, 1 << 30).astype(np.float64) + rng.uniform(0, 1, n)
+        s_, t_ = np.minimum(fi / 2.0 ** 30, 1.0), np.minimum(fj / 2.0 ** 30, 1.0)
+        st2uv = lambda s: np.where(s >= 0.5, (1 / 3.) * (4 * s * s - 1), (1 / 3.) * (1 - 4 * (1 - s) * (1 - s)))
+        u, v = st2uv(s_), st2uv(t_)
+        face = rng.integers(0, 6, n)
+        one = np.ones(n)
+        xyz = np.select([(face == k)[:, None] for k in range(6)],
+                        [np.stack(c, 1) for c in ((one, u, v), (-u, one, v), (-u, -v, one), (-one, -v, -u), (v, -one, -u), (v, u, -one))])
+        out.append(xyz / np.sqrt((xyz * xyz).sum(1))[:, None])
+    return np.ascontiguousarray(np.vstack(out))
+
+
+def test_fp32_prefilter_equals_exact_locate(torch_cuda, ref):
+    """Production Locate (FP32 pre-filter + FP64 pass over the undecided points) == all-FP64 Locate, on uniform points,
+    on points hugging cell/face boundaries at every level, and on garbage inputs; and both equal the reference."""
+    torch = torch_cuda
+    from s2geometry_b200 import _lib, synth
+    from s2geometry_b200.index import ContainsPointQuery, ShapeIndex, build_flat_index
+    lib = _lib.load()
+    scn = {"loop": scenes.loop_scene(10000)[0], "polys": scenes.polygons_scene(3000, 51, min_radius_km=100, max_radius_km=1500),
+           "axis": scenes.axis_aligned_scene()}
+    garbage = np.array([[0, 0, 0], [np.nan, 1, 0], [1, np.nan, np.nan], [np.inf, 1, 1], [1e-320, 0, 0], [1e300, 1e300, 1], [-0.0, 0, 1],
+                        [1, 1, 1], [1, 1, 0], [-1, -1, -1], [1e-30, 1e-30, 1e-30]], float)
+    pts = np.concatenate([synth.sphere_points(3_000_000, 61), boundary_points(200_000, 62), garbage,
+                          synth.cap_points(scenes.LOOP_CENTER, 0.25, 1_000_000, 63)])
+    dev = torch.from_numpy(pts).cuda()
+    for name, soup in scn.items():
+        ix = ShapeIndex(build_flat_index(soup))
+        ri = ref.index_create(soup)
+        q = ContainsPointQuery(ix, 1)
+        try:
+            fast = (q.contains(dev), q.shape_histogram(dev), q.containing_shape_ids(dev))
+            assert lib.s2b_diag_force_exact_locate(1) == 0
+            exact = (q.contains(dev), q.shape_histogram(dev), q.containing_shape_ids(dev))
+        finally:
+            lib.s2b_diag_force_exact_locate(0)
+        assert bool((fast[0] == exact[0]).all()), name
+        assert bool((fast[1] == exact[1]).all()), name
+        assert bool((fast[2][0] == exact[2][0]).all()) and bool((fast[2][1] == exact[2][1]).all()), name
+        finite = np.isfinite(pts).all(1)
+        want = ri.contains(pts[finite], 1)
+        assert (fast[0].cpu().numpy()[finite] == want).all(), name
