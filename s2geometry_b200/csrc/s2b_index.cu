@@ -5,6 +5,8 @@
 // an index cell, the crossing test of s2b_contains.cuh from the precomputed cell centre over that cell's clipped
 // edges, with the Sign chain (triage -> stable -> exact superaccumulator -> symbolic) entirely on the device.
 // Index arrays are read through the read-only path; points are streamed (24 B in, 1 B / a few atomics out).
+#include <cuda_pipeline.h>
+
 #include <cstdlib>
 #include <new>
 #include <vector>
@@ -199,32 +201,60 @@ __device__ __forceinline__ int approx_leaf_coord(float w) {   // w = u or v  -> 
   return __float2int_rz(1073741824.0f * s);                     // saturating; NaN -> 0
 }
 
+// The point stream is staged through shared memory with cp.async (LDGSTS), double buffered: the copy of tile k+1 is
+// in flight while tile k is processed, so the bytes in flight do not occupy registers (with ~150 instructions per point
+// a register-staged version of this kernel was DRAM-latency-bound at 2.0 TB/s: profiles/r1_query_prefilter_ncu.json).
+// Tile = kThreads * kPointsPerThread points = 12 KB for 2 points per thread; requires xyz to be 16-byte aligned.
 template <int kPointsPerThread>
 __global__ void __launch_bounds__(kThreads, 6)
 locate_fast_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint32_t n, HitWork* __restrict__ work, uint32_t capacity,
                    unsigned int* __restrict__ counters, uint32_t* __restrict__ uncertain, int interior_mode,
                    uint8_t* __restrict__ flags, uint32_t* __restrict__ counts) {
-  __shared__ uint16_t s_pos[16384];   // 6-bit Hilbert table (only the top two steps are needed here)
-  for (int k = threadIdx.x; k < 16384 / 8; k += kThreads) ((uint4*)s_pos)[k] = ((const uint4*)g_hilbert_wide_ix)[k];
-  __syncthreads();
-  constexpr uint32_t kSpan = kThreads * kPointsPerThread;
-  const uint32_t stride = gridDim.x * kSpan;
+  constexpr uint32_t kTilePoints = kThreads * kPointsPerThread;
+  constexpr uint32_t kTileBytes = kTilePoints * 24;
+  constexpr uint32_t kChunks = kTileBytes / 16;                 // 16-byte cp.async chunks per tile
+  __shared__ uint16_t s_pos[1024];                              // 4-bit Hilbert table: three steps give the top 12 levels
+  __shared__ __align__(16) double s_tile[2][kTilePoints * 3];
+  for (int k = threadIdx.x; k < 1024; k += kThreads) s_pos[k] = g_hilbert_ix.pos[k];
   const unsigned lane = threadIdx.x & 31u;
   const int lut_level = (61 - ix.lut_shift) >> 1;               // 2..10
   const int bucket_bits = 30 - lut_level;                       // log2 of the bucket size in leaf cells (>= 20)
   const int bucket_mask = (1 << bucket_bits) - 1;
+  const uint64_t total_bytes = (uint64_t)n * 24;
+  const uint32_t num_tiles = (n + kTilePoints - 1) / kTilePoints;
   WarpSlots edge_slots, interior_slots;
   U32Slots unc_slots;
-  for (uint32_t base = blockIdx.x * kSpan + (threadIdx.x & ~31u); base < n; base += stride) {
+
+  auto issue_tile = [&](uint32_t tile, int stage) {
+    const uint64_t tile_byte0 = (uint64_t)tile * kTileBytes;
+    const char* src = (const char*)xyz + tile_byte0;
+    char* dst = (char*)s_tile[stage];
+#pragma unroll
+    for (uint32_t c = threadIdx.x; c < kChunks; c += kThreads) {
+      const uint64_t off = (uint64_t)c * 16;
+      if (tile_byte0 + off + 16 <= total_bytes) __pipeline_memcpy_async(dst + off, src + off, 16);
+      else if (tile_byte0 + off + 8 <= total_bytes) __pipeline_memcpy_async(dst + off, src + off, 8);   // n odd: last 8 bytes
+    }
+    __pipeline_commit();
+  };
+
+  uint32_t tile = blockIdx.x;
+  int stage = 0;
+  if (tile < num_tiles) issue_tile(tile, 0);
+  for (; tile < num_tiles; tile += gridDim.x, stage ^= 1) {
+    const uint32_t next = tile + gridDim.x;
+    if (next < num_tiles) issue_tile(next, stage ^ 1); else __pipeline_commit();
+    __pipeline_wait_prior(1);                                   // this tile's copies have landed (the next may still fly)
+    __syncthreads();
+    const double* pts = s_tile[stage];
+    const uint32_t tile_point0 = tile * kTilePoints;
 #pragma unroll
     for (int t = 0; t < kPointsPerThread; ++t) {
-      const uint32_t i = base + t * kThreads + lane;
+      const uint32_t li = t * kThreads + threadIdx.x;
+      const uint32_t i = tile_point0 + li;
       const bool valid = i < n;
       float x = 1.0f, y = 0.0f, z = 0.0f;
-      if (valid) {
-        const double* q = xyz + 3 * (size_t)i;
-        x = (float)__ldcs(q); y = (float)__ldcs(q + 1); z = (float)__ldcs(q + 2);
-      }
+      if (valid) { x = (float)pts[3 * li]; y = (float)pts[3 * li + 1]; z = (float)pts[3 * li + 2]; }
       const float ax = fabsf(x), ay = fabsf(y), az = fabsf(z);
       const int axis = ax > ay ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
       const float m = axis == 0 ? x : (axis == 1 ? y : z);
@@ -240,16 +270,18 @@ locate_fast_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint3
       const int ri = fi & bucket_mask, rj = fj & bucket_mask;
       bool certain = valid && fi >= 0 && fj >= 0 && fi < (1 << 30) && fj < (1 << 30) &&
                      ri >= kFastRadius && ri <= bucket_mask - kFastRadius && rj >= kFastRadius && rj <= bucket_mask - kFastRadius;
-      // position bits of the top 12 levels (two table steps), then the bucket = top lut_level levels
-      uint32_t bits = (uint32_t)face & 1u;
-      bits += (((uint32_t)fi >> 24) & 63u) << 8; bits += (((uint32_t)fj >> 24) & 63u) << 2;
-      bits = s_pos[bits & 16383u];
-      uint32_t pos24 = (bits >> 2) << 12;
-      bits &= 3u;
-      bits += (((uint32_t)fi >> 18) & 63u) << 8; bits += (((uint32_t)fj >> 18) & 63u) << 2;
-      bits = s_pos[bits];
-      pos24 |= bits >> 2;
-      const uint32_t bucket = (((uint32_t)face << 24) | pos24) >> (24 - 2 * lut_level);
+      // position bits of the top 12 levels (three 4-bit table steps), then the bucket = top lut_level levels
+      uint32_t bits = (uint32_t)face & 1u, pos24 = 0;
+#pragma unroll
+      for (int k = 7; k >= 5; --k) {       // i,j bits 29..18 (the top step holds only 2 bits of each)
+        bits += (((uint32_t)fi >> (4 * k)) & 15u) << 6;
+        bits += (((uint32_t)fj >> (4 * k)) & 15u) << 2;
+        bits = s_pos[bits & 1023u];
+        pos24 = (pos24 << 8) | (bits >> 2);
+        bits &= 3u;
+      }
+      // the three steps produced 4 + 8 + 8 position bits = levels 1..10 exactly (top step = 2 levels): pos20
+      const uint32_t bucket = (((uint32_t)face << 20) | (pos24 & 0xFFFFFu)) >> (20 - 2 * lut_level);
       int c = -1;
       if (certain) {
         const uint32_t e0 = ix.lut[bucket];
@@ -268,7 +300,7 @@ locate_fast_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint3
         else if (interior_mode == 2) cnt = interior;
         else to_interior = true;
       }
-      if (valid && certain) {          // uncertain points are written by the exact kernel
+      if (valid && certain) {          // undecided points are written by the exact kernel
         if (flags) flags[i] = flag;
         if (counts) counts[i] = cnt;
       }
@@ -276,7 +308,9 @@ locate_fast_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint3
       if (interior_mode == 0) interior_slots.append(to_interior, HitWork{i, c}, work, capacity, counters + 1, -1, lane);
       unc_slots.append(valid && !certain, i, uncertain, counters + 2, lane);
     }
+    __syncthreads();                                            // everyone is done with this stage before it is refilled
   }
+  __pipeline_wait_prior(0);
   edge_slots.finish(work, capacity, +1, lane);
   interior_slots.finish(work, capacity, -1, lane);
   unc_slots.finish(uncertain, lane);
@@ -390,6 +424,15 @@ static int locate_variant() {
   return v;
 }
 
+static int fast_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("S2B_FAST_VARIANT");
+    v = e ? atoi(e) : 2;
+  }
+  return v;
+}
+
 static int process_variant() {
   static int v = -1;
   if (v < 0) {
@@ -414,7 +457,7 @@ static cudaError_t launch_query_t(const FlatIndexView& ix, const double* xyz, si
   const size_t max_warps = (size_t)sm_count() * 8 * (kThreads / 32);
   const size_t capacity = round + 4 * max_warps * kSlotChunk;
   const size_t unc_capacity = round + max_warps * kSlotChunk;
-  const bool use_fast = !g_force_exact_locate;
+  const bool use_fast = !g_force_exact_locate && ((uintptr_t)xyz % 16 == 0);   // cp.async staging needs 16-byte alignment
   cudaError_t e = cudaMallocAsync((void**)&work, sizeof(HitWork) * capacity + 256 + (use_fast ? sizeof(uint32_t) * unc_capacity : 0), st);
   if (e != cudaSuccess) return e;
   counter = (unsigned int*)((char*)work + sizeof(HitWork) * capacity);   // 8-byte aligned tail: [0] edge slots, [1] interior slots, [2] uncertain
@@ -437,8 +480,15 @@ static cudaError_t launch_query_t(const FlatIndexView& ix, const double* xyz, si
     uint32_t* pc = kMode == kModeCount ? o.per_point : nullptr;
     const uint32_t* list = nullptr;
     if (use_fast) {
-      locate_fast_kernel<2><<<grid_for_ix((cnt + 1) / 2, (const void*)locate_fast_kernel<2>), kThreads, 0, st>>>(
-          ix, xyz + 3 * off, (uint32_t)cnt, work, (uint32_t)capacity, counter, uncertain, interior_mode, fl, pc);
+#define S2B_FAST(P)                                                                                                   \
+  locate_fast_kernel<P><<<grid_for_ix((cnt + P - 1) / P, (const void*)locate_fast_kernel<P>), kThreads, 0, st>>>(        \
+      ix, xyz + 3 * off, (uint32_t)cnt, work, (uint32_t)capacity, counter, uncertain, interior_mode, fl, pc)
+      switch (fast_variant()) {
+        case 1: S2B_FAST(1); break;
+        case 3: S2B_FAST(3); break;
+        default: S2B_FAST(2); break;
+      }
+#undef S2B_FAST
       count_launch();
       list = uncertain;
     }
