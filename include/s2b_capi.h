@@ -162,6 +162,10 @@ typedef struct S2bIndex S2bIndex;
 
 /* Uploads the index to the CURRENT CUDA device (one replica per GPU: call once per process/device). */
 int s2b_index_create(const S2bFlatIndex* flat, S2bIndex** index_out);
+/* Wraps an S2CellUnion (S2CellUnion::cell_ids(): sorted, non-overlapping) as an index whose cells are all "interior"
+ * cells of shape 0: s2b_contains over it is S2CellUnion::Contains(S2Point) (s2cell_union.cc:564-566) on the fast
+ * Locate path. Preferable to s2b_cellunion_contains when the same union is queried with many batches. */
+int s2b_index_create_from_cellunion(const uint64_t* sorted_ids, size_t m, S2bIndex** index_out);
 void s2b_index_destroy(S2bIndex* index);
 /* Any output may be NULL. device_bytes = HBM held by the replica (ids + cells + clips + edges + lookup table). */
 int s2b_index_info(const S2bIndex* index, uint64_t* num_cells, uint64_t* num_clips, uint64_t* num_edges,

@@ -594,6 +594,23 @@ int s2b_index_create(const S2bFlatIndex* f, S2bIndex** out) {
   return S2B_OK;
 }
 
+// A cell union as an index: every cell becomes a pure interior cell of shape 0 (no edges, contains_center set), so
+// S2CellUnion::Contains(S2Point) (s2cell_union.cc:564-566) is s2b_contains over it and runs on the K3 Locate path
+// (lookup table + FP32 pre-filter) instead of a per-point binary search.
+int s2b_index_create_from_cellunion(const uint64_t* sorted_ids, size_t m, S2bIndex** out) {
+  if (!out || (m && !sorted_ids)) return set_error(S2B_EINVAL, "null argument");
+  std::vector<uint32_t> clip_begin(m + 1), edge_begin(m + 1, 0);
+  std::vector<int32_t> shape(m, 0);
+  std::vector<uint8_t> flags(m, (uint8_t)(1 | (2 << 1)));
+  for (size_t i = 0; i <= m; ++i) clip_begin[i] = (uint32_t)i;
+  S2bFlatIndex f{};
+  f.num_cells = m; f.num_clips = m; f.num_edges = 0; f.num_shape_ids = 1;
+  f.cell_ids = sorted_ids; f.cell_center = nullptr; f.cell_clip_begin = clip_begin.data();
+  f.clip_shape_id = shape.data(); f.clip_flags = flags.data(); f.clip_edge_begin = edge_begin.data();
+  f.edge_v0 = nullptr; f.edge_v1 = nullptr;
+  return s2b_index_create(&f, out);
+}
+
 void s2b_index_destroy(S2bIndex* ix) {
   if (!ix) return;
   int cur = 0;

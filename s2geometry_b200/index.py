@@ -171,6 +171,21 @@ class ShapeIndex:
         return dict(num_cells=c.value, num_clips=k.value, num_edges=e.value, num_shape_ids=s.value, device_bytes=b.value)
 
 
+class CellUnionIndex(ShapeIndex):
+    """An S2CellUnion resident on the device as an index of interior cells: ContainsPointQuery(CellUnionIndex(ids)).contains(p)
+    is S2CellUnion::Contains(S2Point) per point, on the fast Locate path."""
+
+    def __init__(self, sorted_ids):
+        self._lib = _lib.load()
+        ids = np.ascontiguousarray(sorted_ids, np.uint64)
+        h = ctypes.c_void_p()
+        _lib.check(self._lib.s2b_index_create_from_cellunion(ids.ctypes.data if ids.size else None, ids.size, ctypes.byref(h)))
+        self._h = h
+        self.flat = None
+        self.num_shape_ids = 1
+        self.device = torch.cuda.current_device() if torch is not None and torch.cuda.is_available() else 0
+
+
 class ContainsPointQuery:
     """Batch form of S2ContainsPointQuery: every method takes (N,3) points (NumPy = host path, CUDA tensor = device path)."""
 

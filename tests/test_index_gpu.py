@@ -127,6 +127,8 @@ def test_cell_union_contains(torch_cuda, ref):
     cells = np.sort(np.array([int(c, 16) for c in ka["cells"]], np.uint64))
     p = ref.latlng_to_point(np.radians(np.array([[ka["lat"], ka["lng"]]])))
     assert cell_union_contains(cells, p)[0] == 1
+    from s2geometry_b200.index import CellUnionIndex, ContainsPointQuery
+    assert (ContainsPointQuery(CellUnionIndex(ids), 1).contains(pts) == want).all()   # the union as an index of interior cells
     big = ref.cover_cap(center, 0.15, max_cells=20000, min_level=9, max_level=9)   # 8868 ids (> 4096): global-memory path
     assert len(big) > 4096
     pts2 = synth.cap_points(center, 0.2, 500_000, 11)
