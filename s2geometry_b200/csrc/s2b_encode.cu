@@ -5,6 +5,10 @@
 // memory. Input is streamed with cache-streaming loads (read once), ids are written coalesced with
 // streaming stores. All FP64 arithmetic is IEEE (div.rn/sqrt.rn, -fmad=false) so ids equal the reference's bit for bit.
 //
+// (A cp.async shared-memory staged variant of the xyz kernel was measured and rejected: 96 vs 112 Gpts/s — this kernel
+// is bound by instruction issue, not by DRAM latency; the staged design pays off only in the ~150-instruction Locate
+// pre-filter of s2b_index.cu.)
+//
 // Algorithmic traffic per point: xyz 24 B in + 8 B per level out; lat/lng 16 B (E7: 8 B) in + 8 B per level out.
 #include "s2b_core.cuh"
 #include "s2b_hilbert.h"
@@ -37,6 +41,26 @@ constexpr int kThreads = 256;
 // levels live in kernel parameter space; a switch keeps them out of local memory (dynamic indexing would copy them).
 __device__ __forceinline__ int level_at(const LevelSpec& l, int k) {
   return k == 0 ? l.level[0] : (k == 1 ? l.level[1] : (k == 2 ? l.level[2] : l.level[3]));
+}
+
+// Epilogue shared by the encode kernels: parent() at each requested level and, optionally, one token — in the same
+// pass, so ids are never re-read.
+__device__ __forceinline__ void emit_ids_and_token(uint64_t id, size_t i, size_t n, const EncodeOut& o) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k < o.levels.n) {
+      // parent(level): (id & -lsb) | lsb; for level 30 lsb = 1 and the id (odd) is unchanged (s2cell_id.h:662-668)
+      const uint64_t lsb = lsb_for_level(level_at(o.levels, k));
+      __stcs(o.ids + (size_t)k * n + i, (id & (~lsb + 1)) | lsb);
+    }
+  }
+  if (o.token_level_index >= 0) {
+    int L = level_at(o.levels, o.token_level_index);
+    uint32_t w[4];
+    int len = cellid_to_token(L < 30 ? cellid_parent(id, L) : id, w);
+    __stcs((uint4*)o.tokens16 + i, make_uint4(w[0], w[1], w[2], w[3]));
+    if (o.token_len) o.token_len[i] = (uint8_t)len;
+  }
 }
 
 template <int kKind>
@@ -79,21 +103,7 @@ encode_kernel(const void* __restrict__ in, size_t n, const EncodeOut o) {
     }
     if (kKind == kInXYZ) face = point_to_face_fij(p, &fi, &fj);
     const uint64_t id = from_face_ij_wide(face, fij_to_ij(fi), fij_to_ij(fj), s_pos);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (k < o.levels.n) {
-        // parent(level): (id & -lsb) | lsb; for level 30 lsb = 1 and the id (odd) is unchanged (s2cell_id.h:662-668)
-        const uint64_t lsb = lsb_for_level(level_at(o.levels, k));
-        __stcs(o.ids + (size_t)k * n + i, (id & (~lsb + 1)) | lsb);
-      }
-    }
-    if (o.token_level_index >= 0) {
-      int L = level_at(o.levels, o.token_level_index);
-      uint32_t w[4];
-      int len = cellid_to_token(L < 30 ? cellid_parent(id, L) : id, w);
-      __stcs((uint4*)o.tokens16 + i, make_uint4(w[0], w[1], w[2], w[3]));
-      if (o.token_len) o.token_len[i] = (uint8_t)len;
-    }
+    emit_ids_and_token(id, i, n, o);
     if (o.flags) o.flags[i] = (kKind == kInXYZ || sensitive) && near_cell_boundary(fi, fj, kFlagTolIj) ? 1 : 0;
   }
 }
