@@ -494,7 +494,9 @@ def run_gpu(args):
                        "points_per_gpu": n, "levels": LEVELS, "l2_policy": "inputs (1.6 GB) and outputs (4.1 GB) per step exceed the 126 MB L2",
                        "kernel": "encode_kernel<latlng> (1 launch per step: fast sin/cos filter + correctly rounded path for boundary-sensitive points, fused parent/ToToken epilogues)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_source": peak_src, "bytes_per_point": BYTES_PER_POINT, "kernel_ms": kern_ms, "fp64": fp64},
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from ncu --set full
+                         # (profiles/r1_encode_latlng_final_ncu.json: 54.1 B/point at 20M points), scaled to this launch
+                         "traffic": 54.14 * n, "traffic_unit": "bytes per launch (ncu dram read+write, 54.14 B/point)", "peak_source": peak_src, "bytes_per_point": BYTES_PER_POINT, "kernel_ms": kern_ms, "fp64": fp64},
             "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": 16 * e2e_n, "d2h_bytes_per_step": (8 * len(LEVELS) + 17) * e2e_n, "points_per_gpu": e2e_n,
                     "ms_per_step": 1e3 * float(t.item()), "matches_device_result": same, "numa_node_rank0": numa_node},
             "gpu_launches": int(launches),

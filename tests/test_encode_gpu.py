@@ -179,3 +179,25 @@ def test_to_point_and_from_token(torch_cuda, ref):
     assert (cellid.from_token(tok, ln) == ids).all()
     assert (cellid.from_token(torch.from_numpy(tok).cuda(), torch.from_numpy(ln).cuda()).cpu().numpy().view(np.uint64) == ids).all()
     assert (ref.from_token(tok, ln) == ids).all()
+
+
+def test_cuda_vs_independent_restatement(torch_cuda):
+    """Second, independent oracle (oracle/restatement.py: NumPy + exact rationals; no code shared with the kernels or with
+    the compiled reference): cell ids on 2M points, and containment with vertex models on a small polygon."""
+    from oracle import restatement as rs
+    from s2geometry_b200 import cellid, synth
+    from s2geometry_b200.index import ContainsPointQuery, ShapeIndex, build_flat_index
+    from s2geometry_b200.shapes import ShapeSoup
+    p = synth.sphere_points(2_000_000, 81)
+    assert (cellid.from_points(p) == rs.encode_points(p)).all()
+    assert (cellid.from_points(p, 7) == rs.encode_points(p, 7)).all()
+    ids = cellid.from_points(p[:20000], 11)
+    assert cellid.tokens_to_str(*cellid.to_token(ids)) == rs.to_token(ids)
+    assert (cellid.to_point(ids) == rs.to_point(ids)).all()
+    loop = synth.wobbly_loop(np.array([0.3, -0.5, 0.8]), 0.17, 40)
+    soup = ShapeSoup(); soup.add_polygon([loop])
+    ix = ShapeIndex(build_flat_index(soup.freeze()))
+    pts = np.concatenate([synth.cap_points(np.array([0.3, -0.5, 0.8]), 0.22, 120, 4), synth.degenerate_points(loop)])
+    for m in (0, 1, 2):
+        want = np.array([rs.polygon_contains([loop], q, m) for q in pts], np.uint8)
+        assert (ContainsPointQuery(ix, m).contains(pts) == want).all(), m
