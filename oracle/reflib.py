@@ -178,9 +178,12 @@ class RefIndex:
         self.num_shape_ids = int(self.lib.ref_index_num_shape_ids(_vp(self.h)))
 
     def __del__(self):
-        if getattr(self, "h", None):
-            self.lib.ref_index_destroy(_vp(self.h))
-            self.h = None
+        try:
+            if getattr(self, "h", None):
+                self.lib.ref_index_destroy(_vp(self.h))
+                self.h = None
+        except Exception:   # interpreter shutdown: module globals may already be gone
+            pass
 
     def flatten(self):
         C = ctypes.c_uint64(); K = ctypes.c_uint64(); E = ctypes.c_uint64()
