@@ -1,5 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests/test_encode_gpu.py tests/test_index_gpu.py -x -q -m gpu 2>&1 | tail -4
-python tools/time_encode_xyz.py | tail -1
-S2B_NO_STAGING=1 python tools/time_encode_xyz.py | tail -1
+python -m pytest tests/test_index_gpu.py tests/test_fuzz_gpu.py -x -q -m gpu 2>&1 | tail -4
+python tools/time_query.py 2>&1 | tail -1 | tee gpurun_out/sweep.txt
