@@ -20,7 +20,6 @@ namespace s2b {
 struct FlatCell { double cx, cy, cz; uint32_t clip_begin, clip_count; };
 struct FlatClip { int32_t shape_id; uint32_t edge_begin; uint32_t num_edges; uint32_t flags; };
 struct FlatEdge { double v0x, v0y, v0z, v1x, v1y, v1z; };
-struct FlatEdge32 { float v0x, v0y, v0z, v1x, v1y, v1z; };   // single-precision copy for the pass-1 filter
 
 struct FlatIndexView {
   const uint64_t* cell_ids;
@@ -28,7 +27,6 @@ struct FlatIndexView {
   const FlatClip* clips;
   const FlatEdge* edges;
   const uint32_t* lut;
-  const FlatEdge32* edges32;       // nullptr: no single-precision filter (some vertex is not of unit length)
   const uint8_t* interior_clips;   // per cell: k > 0 = no edges at all, k clips that all contain the centre; 0 = has edges
   uint32_t num_cells;
   int lut_shift;
@@ -36,9 +34,6 @@ struct FlatIndexView {
 };
 
 enum VertexModel { kOpen = 0, kSemiOpen = 1, kClosed = 2 };
-
-// Pass-1 filter margin (see clip_contains): 5x the single-precision error bound for vectors of length <= 1.1.
-constexpr float kDet32Margin = 4e-6f;
 
 // Lookup-table entry: bits 29..0 = index of the first candidate cell of the bucket; bits 31..30 = what the bucket
 // (a cell of level lut_level, i.e. a contiguous range of leaf ids) looks like:
@@ -100,34 +95,19 @@ S2B_HD bool clip_contains(const FlatIndexView& ix, const FlatClip& clip, const P
     }
     return false;
   }
-  // Pass 1 dismisses edges whose endpoints C and D are strictly on the same side of AB (the S2EdgeCrosser fast path,
-  // s2edge_crosser.h:365-388: no crossing). It runs in SINGLE precision on a float copy of the edges: with unit-length
-  // inputs |fl32((AxB).C) - (AxB).C| < 7e-7, so |det32| > kDet32Margin on both endpoints with equal signs implies the
-  // double-precision triage signs are certain and equal as well. Edges it cannot dismiss (a few per cent) are only
-  // REMEMBERED (bitmask per 64 edges) and resolved in pass 2 in double precision, so a warp's lanes go through the
-  // expensive path together. The order of evaluation does not matter: the parity is a XOR, and the vertex-model early
+  // Pass 1: the S2EdgeCrosser fast path (s2edge_crosser.h:365-388) for every edge — C and D strictly on the same side
+  // of AB means no crossing. Edges it cannot dismiss (~9 %) are only REMEMBERED here (bitmask per 64 edges) and
+  // resolved in pass 2, so a warp's lanes go through the expensive path together instead of one at a time at
+  // arbitrary iterations. The order of evaluation does not matter: the parity is a XOR, and the vertex-model early
   // return yields the same value whichever qualifying edge triggers it (s2contains_point_query.h:377-382).
-  const FlatEdge32* edges32 = ix.edges32 ? ix.edges32 + clip.edge_begin : nullptr;
-  const bool use32 = edges32 != nullptr && norm2(b) <= 1.21;     // the query point must be (about) unit length too
-  const float fx = (float)a_cross_b.x, fy = (float)a_cross_b.y, fz = (float)a_cross_b.z;
   for (uint32_t base = 0; base < num_edges; base += 64) {
     const uint32_t cnt = num_edges - base < 64 ? num_edges - base : 64;
     uint64_t pending = 0;
-    if (use32) {
-      for (uint32_t i = 0; i < cnt; ++i) {
-        const FlatEdge32 e = edges32[base + i];
-        const float dc = (fx * e.v0x + fy * e.v0y) + fz * e.v0z;
-        const float dd = (fx * e.v1x + fy * e.v1y) + fz * e.v1z;
-        const bool same_side = (dc > kDet32Margin && dd > kDet32Margin) || (dc < -kDet32Margin && dd < -kDet32Margin);
-        if (!same_side) pending |= 1ull << i;
-      }
-    } else {
-      for (uint32_t i = 0; i < cnt; ++i) {
-        const FlatEdge e = edges[base + i];
-        const int acb = -triage_sign(a_cross_b, edge_v0(e));
-        const int bda = triage_sign(a_cross_b, edge_v1(e));
-        if (!(acb == -bda && bda != 0)) pending |= 1ull << i;
-      }
+    for (uint32_t i = 0; i < cnt; ++i) {
+      const FlatEdge e = edges[base + i];
+      const int acb = -triage_sign(a_cross_b, edge_v0(e));
+      const int bda = triage_sign(a_cross_b, edge_v1(e));
+      if (!(acb == -bda && bda != 0)) pending |= 1ull << i;
     }
     while (pending) {
       const int i = ctz64(pending);
@@ -136,7 +116,6 @@ S2B_HD bool clip_contains(const FlatIndexView& ix, const FlatClip& clip, const P
       const P3 c = edge_v0(e), d = edge_v1(e);
       const int acb = -triage_sign(a_cross_b, c);
       const int bda = triage_sign(a_cross_b, d);
-      if (acb == -bda && bda != 0) continue;        // the double-precision fast path: same side, no crossing
       // Common case of a pending edge: both signs certain and equal (C and D strictly on opposite sides of AB). Then
       // s2edge_crosser.cc:76-96 reduces to: shared vertex -> 0, degenerate edge -> -1, else compare with the signs
       // of B and A against CD. Done inline when those two are certain too; anything uncertain goes out of line.

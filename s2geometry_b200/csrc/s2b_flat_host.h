@@ -17,14 +17,13 @@ struct HostFlat {
   std::vector<FlatCell> cells;
   std::vector<FlatClip> clips;
   std::vector<FlatEdge> edges;
-  std::vector<FlatEdge32> edges32;   // empty if some vertex or cell centre is not of (about) unit length
   std::vector<uint32_t> lut;   // num_buckets + 2 entries
   std::vector<uint8_t> interior_clips;  // per cell, see FlatIndexView
   uint64_t num_buckets = 0;
   int lut_shift = 0;
   FlatIndexView view(const uint64_t* cell_ids, int num_shape_ids) const {
     FlatIndexView v;
-    v.cell_ids = cell_ids; v.cells = cells.data(); v.clips = clips.data(); v.edges = edges.data(); v.edges32 = edges32.empty() ? nullptr : edges32.data(); v.lut = lut.data(); v.interior_clips = interior_clips.data();
+    v.cell_ids = cell_ids; v.cells = cells.data(); v.clips = clips.data(); v.edges = edges.data(); v.lut = lut.data(); v.interior_clips = interior_clips.data();
     v.num_cells = (uint32_t)cells.size(); v.lut_shift = lut_shift; v.num_shape_ids = num_shape_ids;
     return v;
   }
@@ -74,21 +73,6 @@ inline int pack_flat_index(const S2bFlatIndex& f, HostFlat* out, std::string* er
     out->clips[k] = FlatClip{f.clip_shape_id[k], f.clip_edge_begin[k], f.clip_edge_begin[k + 1] - f.clip_edge_begin[k], f.clip_flags[k]};
   for (uint64_t e = 0; e < E; ++e)
     out->edges[e] = FlatEdge{f.edge_v0[3 * e], f.edge_v0[3 * e + 1], f.edge_v0[3 * e + 2], f.edge_v1[3 * e], f.edge_v1[3 * e + 1], f.edge_v1[3 * e + 2]};
-  // Single-precision copy of the edges for the pass-1 filter; only valid when every vector is of (about) unit length.
-  {
-    bool unit = true;
-    auto ok = [](double x, double y, double z) { double n2 = x * x + y * y + z * z; return n2 >= 0.81 && n2 <= 1.21; };
-    for (uint64_t e = 0; e < E && unit; ++e)
-      unit = ok(f.edge_v0[3 * e], f.edge_v0[3 * e + 1], f.edge_v0[3 * e + 2]) && ok(f.edge_v1[3 * e], f.edge_v1[3 * e + 1], f.edge_v1[3 * e + 2]);
-    for (uint64_t c = 0; c < C && unit; ++c) unit = ok(out->cells[c].cx, out->cells[c].cy, out->cells[c].cz);
-    out->edges32.clear();
-    if (unit && E) {
-      out->edges32.resize(E);
-      for (uint64_t e = 0; e < E; ++e)
-        out->edges32[e] = FlatEdge32{(float)f.edge_v0[3 * e], (float)f.edge_v0[3 * e + 1], (float)f.edge_v0[3 * e + 2],
-                                     (float)f.edge_v1[3 * e], (float)f.edge_v1[3 * e + 1], (float)f.edge_v1[3 * e + 2]};
-    }
-  }
   // Cells whose clips have no edges and all contain the centre (pure interior cells) are answered without looking
   // at clips or edges when only "any"/"how many" is asked.
   for (uint64_t c = 0; c < C; ++c) {

@@ -563,7 +563,7 @@ int s2b_index_create(const S2bFlatIndex* f, S2bIndex** out) {
   auto align = [](size_t v) { return (v + 255) / 256 * 256; };
   size_t o_ids = 0, o_cells = o_ids + align(8 * (C + 1)), o_clips = o_cells + align(sizeof(FlatCell) * (C + 1)),
          o_edges = o_clips + align(sizeof(FlatClip) * (K + 1)), o_lut = o_edges + align(sizeof(FlatEdge) * (E + 1)),
-         o_kind = o_lut + align(4 * (nb + 2)), o_e32 = o_kind + align(C + 1), o_view = o_e32 + align(sizeof(FlatEdge32) * (hf.edges32.size() + 1)), total = o_view + align(sizeof(FlatIndexView));
+         o_kind = o_lut + align(4 * (nb + 2)), o_view = o_kind + align(C + 1), total = o_view + align(sizeof(FlatIndexView));
   e = cudaMalloc(&ix->blob, total);
   if (e != cudaSuccess) { delete ix; return cuda_fail(e, "cudaMalloc(index)"); }
   ix->blob_bytes = total;
@@ -575,7 +575,6 @@ int s2b_index_create(const S2bFlatIndex* f, S2bIndex** out) {
   ok &= E == 0 || cudaMemcpy(base + o_edges, edges.data(), sizeof(FlatEdge) * E, cudaMemcpyHostToDevice) == cudaSuccess;
   ok &= cudaMemcpy(base + o_lut, lut.data(), 4 * (nb + 2), cudaMemcpyHostToDevice) == cudaSuccess;
   ok &= cudaMemcpy(base + o_kind, hf.interior_clips.data(), C + 1, cudaMemcpyHostToDevice) == cudaSuccess;
-  ok &= hf.edges32.empty() || cudaMemcpy(base + o_e32, hf.edges32.data(), sizeof(FlatEdge32) * hf.edges32.size(), cudaMemcpyHostToDevice) == cudaSuccess;
   if (!ok) { e = cudaGetLastError(); cudaFree(ix->blob); delete ix; return cuda_fail(e, "cudaMemcpy(index)"); }
   ix->view.cell_ids = (const uint64_t*)(base + o_ids);
   ix->view.cells = (const FlatCell*)(base + o_cells);
@@ -583,7 +582,6 @@ int s2b_index_create(const S2bFlatIndex* f, S2bIndex** out) {
   ix->view.edges = (const FlatEdge*)(base + o_edges);
   ix->view.lut = (const uint32_t*)(base + o_lut);
   ix->view.interior_clips = (const uint8_t*)(base + o_kind);
-  ix->view.edges32 = hf.edges32.empty() ? nullptr : (const FlatEdge32*)(base + o_e32);
   ix->view.num_cells = (uint32_t)C;
   ix->view.lut_shift = lut_shift;
   ix->view.num_shape_ids = f->num_shape_ids;

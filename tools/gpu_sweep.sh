@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests/test_index_gpu.py tests/test_fuzz_gpu.py -x -q -m gpu 2>&1 | tail -4
+python -m pytest tests/test_index_gpu.py tests/test_fuzz_gpu.py -x -q -m gpu 2>&1 | tail -3
 python tools/time_query.py 2>&1 | tail -1 | tee gpurun_out/sweep.txt
