@@ -258,7 +258,4 @@ S2B_HD uint64_t cellid_from_token(const unsigned char* tok, int len) {
   return id;
 }
 
-// S2CellId::level() (s2cell_id.h:595-603): -1 is never returned here; invalid ids give whatever the formula gives.
-S2B_HD int cellid_level(uint64_t id) { return 30 - (ctz64(id | (1ull << 63) ) >> 1); }
-
 }  // namespace s2b
