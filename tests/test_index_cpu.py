@@ -222,3 +222,31 @@ def test_cells_with_hundreds_of_edges(hostsim, ref):
     for pts in (b, d):
         for m in (0, 1, 2):
             assert (hs_query(hostsim, flat, pts, m, 0)[0] == ri.contains(pts, m)).all()
+
+
+def test_degenerate_shapes(hostsim, ref):
+    """Degenerate geometry the lax shapes allow: repeated vertices (zero-length edges), two-vertex loops (an edge and its
+    reverse), a loop given twice, the full polygon (one empty chain), shapes without chains, a point shape without points."""
+    from s2geometry_b200 import synth
+    from s2geometry_b200.shapes import ShapeSoup
+    c = np.array([0.2, 0.3, 0.9])
+    loop = synth.wobbly_loop(c, 0.2, 12)
+    soup = ShapeSoup()
+    soup.add_polygon([np.concatenate([loop[:5], loop[4:5], loop[5:]])])          # repeated vertex
+    soup.add_polygon([loop[:2]])                                                  # sibling pair: zero area
+    soup.add_polygon([loop, loop])                                                # same loop twice
+    soup.add_polygon([np.zeros((0, 3))])                                          # full polygon
+    soup.add_polygon([])                                                          # empty polygon (no chains)
+    soup.add_points(np.zeros((0, 3)))
+    soup.add_polygon([loop, loop[::-1].copy()])                                   # a loop and its reverse: every edge matched
+    soup.add_polyline(loop[:1])                                                   # one-vertex polyline: no edges
+    soup = soup.freeze()
+    ri = ref.index_create(soup)
+    flat = own_flat(soup)
+    pts = np.concatenate([synth.cap_points(c, 0.3, 4000, 5), synth.sphere_points(4000, 6), synth.degenerate_points(loop)])
+    for m in (0, 1, 2):
+        assert (hs_query(hostsim, flat, pts, m, 2)[0] == ri.shape_histogram(pts, m, 1)).all(), m
+        assert (hs_query(hostsim, flat, pts, m, 0)[0] == ri.contains(pts, m, 1)).all(), m
+    rflat = flat_of(ri)
+    for m in (0, 1, 2):
+        assert (hs_query(hostsim, rflat, pts, m, 2)[0] == ri.shape_histogram(pts, m, 1)).all(), m
