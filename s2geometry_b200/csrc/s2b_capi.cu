@@ -120,13 +120,25 @@ int run_pipelined(const void* in_host, size_t in_bpp, size_t n, const OutSpec* o
   for (int j = 0; j < n_outs; ++j) out_bytes += region(j);
   int rc = t_ws.ensure(dev, in_bpp * chunk, out_bytes ? out_bytes : 256);
   if (rc) return rc;
+  // Once copies are in flight they reference the caller's buffers: on any failure drain the slot streams before
+  // returning, so nothing touches those buffers after the call has reported an error.
+  auto drain_and_return = [&](int code) {
+    for (Slot& s : t_ws.slot) cudaStreamSynchronize(s.stream);
+    cudaGetLastError();
+    return code;
+  };
+#define S2B_CUDA_DRAIN(call)                                                    \
+  do {                                                                          \
+    cudaError_t e__ = (call);                                                   \
+    if (e__ != cudaSuccess) return drain_and_return(cuda_fail(e__, #call));     \
+  } while (0)
   size_t k = 0;
   for (size_t off = 0; off < n; off += chunk, ++k) {
     Slot& s = t_ws.slot[k % 3];
     size_t cnt = n - off < chunk ? n - off : chunk;
     // the slot's previous D2H must have drained before its buffers are reused
-    if (k >= 3) S2B_CUDA(cudaStreamSynchronize(s.stream));
-    S2B_CUDA(cudaMemcpyAsync(s.in, (const char*)in_host + off * in_bpp, cnt * in_bpp, cudaMemcpyHostToDevice, s.stream));
+    if (k >= 3) S2B_CUDA_DRAIN(cudaStreamSynchronize(s.stream));
+    S2B_CUDA_DRAIN(cudaMemcpyAsync(s.in, (const char*)in_host + off * in_bpp, cnt * in_bpp, cudaMemcpyHostToDevice, s.stream));
     void* out_dev[4] = {nullptr, nullptr, nullptr, nullptr};
     char* cur = (char*)s.out;
     for (int j = 0; j < n_outs; ++j) {
@@ -134,18 +146,19 @@ int run_pipelined(const void* in_host, size_t in_bpp, size_t n, const OutSpec* o
       cur += region(j);
     }
     int lrc = launch(s.in, cnt, out_dev, s.stream);
-    if (lrc != S2B_OK) return lrc;
+    if (lrc != S2B_OK) return drain_and_return(lrc);
     for (int j = 0; j < n_outs; ++j) {
       if (!outs[j].host) continue;
       for (int a = 0; a < outs[j].arrays; ++a) {
         // device arrays are cnt apart (the kernels index array a at base + a*cnt), host arrays n apart
-        S2B_CUDA(cudaMemcpyAsync((char*)outs[j].host + ((size_t)a * n + off) * outs[j].bytes_per_point,
-                                 (char*)out_dev[j] + (size_t)a * cnt * outs[j].bytes_per_point,
-                                 cnt * outs[j].bytes_per_point, cudaMemcpyDeviceToHost, s.stream));
+        S2B_CUDA_DRAIN(cudaMemcpyAsync((char*)outs[j].host + ((size_t)a * n + off) * outs[j].bytes_per_point,
+                                       (char*)out_dev[j] + (size_t)a * cnt * outs[j].bytes_per_point,
+                                       cnt * outs[j].bytes_per_point, cudaMemcpyDeviceToHost, s.stream));
       }
     }
   }
-  for (Slot& s : t_ws.slot) S2B_CUDA(cudaStreamSynchronize(s.stream));
+  for (Slot& s : t_ws.slot) S2B_CUDA_DRAIN(cudaStreamSynchronize(s.stream));
+#undef S2B_CUDA_DRAIN
   return S2B_OK;
 }
 
