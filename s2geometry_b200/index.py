@@ -186,6 +186,21 @@ class CellUnionIndex(ShapeIndex):
         self.device = torch.cuda.current_device() if torch is not None and torch.cuda.is_available() else 0
 
 
+class _DeviceGuard:
+    """Makes the index's device current for the duration of a call (kernels run on the device that holds the replica)."""
+
+    def __init__(self, device):
+        self.ctx = torch.cuda.device(device) if torch is not None and torch.cuda.is_available() else None
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
+
+
 class ContainsPointQuery:
     """Batch form of S2ContainsPointQuery: every method takes (N,3) points (NumPy = host path, CUDA tensor = device path)."""
 
@@ -194,71 +209,80 @@ class ContainsPointQuery:
         self.model = int(vertex_model)
         self._lib = _lib.load()
 
+    def _check_device(self, p):
+        if _is_tensor(p) and p.device.index != self.index.device:
+            raise ValueError("points are on cuda:%s but the index replica lives on cuda:%s" % (p.device.index, self.index.device))
+        return _DeviceGuard(self.index.device)
+
     def contains(self, xyz):
         """S2ContainsPointQuery::Contains per point -> uint8 flags."""
         p = _points(xyz)
         n = p.shape[0]
-        if _is_tensor(p):
-            out = torch.empty(n, dtype=torch.uint8, device=p.device)
-            _lib.check(self._lib.s2b_contains_dev(self.index._h, _ptr(p), n, self.model, _ptr(out), _stream()))
+        with self._check_device(p):
+            if _is_tensor(p):
+                out = torch.empty(n, dtype=torch.uint8, device=p.device)
+                _lib.check(self._lib.s2b_contains_dev(self.index._h, _ptr(p), n, self.model, _ptr(out), _stream()))
+                return out
+            out = np.empty(n, np.uint8)
+            _lib.check(self._lib.s2b_contains(self.index._h, _ptr(p), n, self.model, _ptr(out)))
             return out
-        out = np.empty(n, np.uint8)
-        _lib.check(self._lib.s2b_contains(self.index._h, _ptr(p), n, self.model, _ptr(out)))
-        return out
 
     def shape_contains(self, shape_id, xyz):
         """S2ContainsPointQuery::ShapeContains(shape_id, p) per point -> uint8 flags."""
         p = _points(xyz)
         n = p.shape[0]
-        if _is_tensor(p):
-            out = torch.empty(n, dtype=torch.uint8, device=p.device)
-            _lib.check(self._lib.s2b_shape_contains_dev(self.index._h, int(shape_id), _ptr(p), n, self.model, _ptr(out), _stream()))
+        with self._check_device(p):
+            if _is_tensor(p):
+                out = torch.empty(n, dtype=torch.uint8, device=p.device)
+                _lib.check(self._lib.s2b_shape_contains_dev(self.index._h, int(shape_id), _ptr(p), n, self.model, _ptr(out), _stream()))
+                return out
+            out = np.empty(n, np.uint8)
+            _lib.check(self._lib.s2b_shape_contains(self.index._h, int(shape_id), _ptr(p), n, self.model, _ptr(out)))
             return out
-        out = np.empty(n, np.uint8)
-        _lib.check(self._lib.s2b_shape_contains(self.index._h, int(shape_id), _ptr(p), n, self.model, _ptr(out)))
-        return out
 
     def shape_histogram(self, xyz, counts=None):
         """Spatial join: number of points contained by each shape (VisitContainingShapeIds accumulated).
         Device path: `counts` (int64 CUDA tensor of num_shape_ids, accumulated into) may be passed to chain batches."""
         p = _points(xyz)
         n = p.shape[0]
-        S = self.index.num_shape_ids
-        if _is_tensor(p):
-            if counts is None:
-                counts = torch.zeros(S, dtype=torch.int64, device=p.device)
-            _lib.check(self._lib.s2b_shape_histogram_dev(self.index._h, _ptr(p), n, self.model, _ptr(counts), _stream()))
-            return counts
-        out = np.zeros(S, np.uint64)
-        _lib.check(self._lib.s2b_shape_histogram(self.index._h, _ptr(p), n, self.model, _ptr(out)))
-        return out
+        with self._check_device(p):
+            S = self.index.num_shape_ids
+            if _is_tensor(p):
+                if counts is None:
+                    counts = torch.zeros(S, dtype=torch.int64, device=p.device)
+                _lib.check(self._lib.s2b_shape_histogram_dev(self.index._h, _ptr(p), n, self.model, _ptr(counts), _stream()))
+                return counts
+            out = np.zeros(S, np.uint64)
+            _lib.check(self._lib.s2b_shape_histogram(self.index._h, _ptr(p), n, self.model, _ptr(out)))
+            return out
 
     def containing_shape_ids(self, xyz):
         """GetContainingShapeIds for a batch in CSR form: (offsets (N+1,), shape_ids)."""
         p = _points(xyz)
         n = p.shape[0]
-        if _is_tensor(p):
-            cnt = torch.empty(n, dtype=torch.int32, device=p.device)
-            _lib.check(self._lib.s2b_containing_shapes_count_dev(self.index._h, _ptr(p), n, self.model, _ptr(cnt), _stream()))
-            off = torch.zeros(n + 1, dtype=torch.int64, device=p.device)
-            torch.cumsum(cnt, 0, out=off[1:])
-            total = int(off[-1].item())
-            off32 = off.to(torch.int32)
-            ids = torch.empty(max(total, 1), dtype=torch.int32, device=p.device)
-            if total:
-                _lib.check(self._lib.s2b_containing_shapes_fill_dev(self.index._h, _ptr(p), n, self.model, _ptr(off32), _ptr(ids), _stream()))
-            return off32, ids[:total]
-        off = np.empty(n + 1, np.uint32)
-        total = ctypes.c_size_t(0)
-        cap = max(1024, n // 8)
-        while True:
-            ids = np.empty(cap, np.int32)
-            rc = self._lib.s2b_containing_shapes(self.index._h, _ptr(p), n, self.model, _ptr(off), _ptr(ids), cap, ctypes.byref(total))
-            if rc == -4 and total.value > cap:
-                cap = total.value
-                continue
-            _lib.check(rc)
-            return off, ids[: total.value].copy()
+        with self._check_device(p):
+            if _is_tensor(p):
+                cnt = torch.empty(n, dtype=torch.int32, device=p.device)
+                _lib.check(self._lib.s2b_containing_shapes_count_dev(self.index._h, _ptr(p), n, self.model, _ptr(cnt), _stream()))
+                off = torch.zeros(n + 1, dtype=torch.int64, device=p.device)
+                torch.cumsum(cnt, 0, out=off[1:])
+                total = int(off[-1].item())
+                off32 = off.to(torch.int32)
+                ids = torch.empty(max(total, 1), dtype=torch.int32, device=p.device)
+                if total:
+                    _lib.check(self._lib.s2b_containing_shapes_fill_dev(self.index._h, _ptr(p), n, self.model, _ptr(off32), _ptr(ids), _stream()))
+                return off32, ids[:total]
+            off = np.empty(n + 1, np.uint32)
+            total = ctypes.c_size_t(0)
+            cap = max(1024, n // 8)
+            while True:
+                ids = np.empty(cap, np.int32)
+                rc = self._lib.s2b_containing_shapes(self.index._h, _ptr(p), n, self.model, _ptr(off), _ptr(ids), cap, ctypes.byref(total))
+                if rc == -4 and total.value > cap:
+                    cap = total.value
+                    continue
+                _lib.check(rc)
+                return off, ids[: total.value].copy()
 
 
 def cell_union_contains(sorted_ids, xyz):

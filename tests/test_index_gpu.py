@@ -274,3 +274,35 @@ def test_fp32_prefilter_equals_exact_locate(torch_cuda, ref):
         finite = np.isfinite(pts).all(1)
         want = ri.contains(pts[finite], 1)
         assert (fast[0].cpu().numpy()[finite] == want).all(), name
+
+
+def test_error_paths_on_gpu(torch_cuda):
+    """Bad arguments are reported as errors (never crashes, never a silent fallback)."""
+    import ctypes
+    torch = torch_cuda
+    from s2geometry_b200 import _lib, S2BError
+    from s2geometry_b200.index import ContainsPointQuery, ShapeIndex, build_flat_index
+    lib = _lib.load()
+    t = torch.zeros(64, dtype=torch.float64, device="cuda")
+    out = torch.zeros(16, dtype=torch.int64, device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # lat/lng input must be 16-byte aligned for the vector loads
+    assert lib.s2b_encode_latlng_dev(ctypes.c_void_p(t.data_ptr() + 8), 4, 30, ctypes.c_void_p(out.data_ptr()), None, st) == -1
+    assert b"aligned" in lib.s2b_last_error()
+    assert lib.s2b_encode_points_dev(ctypes.c_void_p(t.data_ptr()), 4, 31, ctypes.c_void_p(out.data_ptr()), st) == -1
+    assert lib.s2b_encode_points_dev(None, 4, 30, ctypes.c_void_p(out.data_ptr()), st) == -1
+    soup, v = scenes.loop_scene(200)
+    ix = ShapeIndex(build_flat_index(soup))
+    assert lib.s2b_contains_dev(ix._h, ctypes.c_void_p(t.data_ptr()), 4, 7, ctypes.c_void_p(out.data_ptr()), st) == -1   # vertex model
+    assert lib.s2b_contains_dev(None, ctypes.c_void_p(t.data_ptr()), 4, 1, ctypes.c_void_p(out.data_ptr()), st) == -1
+    with pytest.raises(ValueError):
+        ContainsPointQuery(ix, 1).contains(np.zeros((4, 2)))
+    # an 8-byte aligned (not 16) xyz pointer is fine: the pre-filter's cp.async path is skipped, results identical
+    pts = torch.from_numpy(np.ascontiguousarray(scenes.loop_points(v, 1000, 50001, 3)[1])).cuda()
+    shifted = torch.empty(pts.numel() + 1, dtype=torch.float64, device="cuda")
+    shifted[1:] = pts.reshape(-1)
+    view = shifted[1:].reshape(-1, 3)
+    assert view.data_ptr() % 16 == 8
+    q = ContainsPointQuery(ix, 1)
+    assert bool((q.contains(view) == q.contains(pts)).all())
+    torch.cuda.synchronize()
