@@ -108,6 +108,11 @@ int s2b_cellid_to_token_dev(const uint64_t* ids_dev, size_t n, char* tokens16_ou
  * vector of each cell's centre, bit-exact with the reference. xyz_out = n x 3 doubles. */
 int s2b_cellid_to_point(const uint64_t* ids, size_t n, double* xyz_out);
 int s2b_cellid_to_point_dev(const uint64_t* ids_dev, size_t n, double* xyz_out_dev, void* stream);
+/* S2CellId::GetEdgeNeighbors (s2cell_id.cc:499-512): the four edge neighbours (down, right, up, left) of every VALID
+ * cell id, at the cell's own level; neighbors4_out = n x 4 ids. Neighbours across a cube-face edge are found with
+ * FromFaceIJWrap (:458-489). */
+int s2b_cellid_edge_neighbors(const uint64_t* ids, size_t n, uint64_t* neighbors4_out);
+int s2b_cellid_edge_neighbors_dev(const uint64_t* ids_dev, size_t n, uint64_t* neighbors4_out_dev, void* stream);
 /* S2CellId::FromToken (s2cell_id.cc:235-254): tokens as produced by s2b_cellid_to_token (16-byte slots + lengths);
  * malformed tokens decode to 0 (S2CellId::None()). */
 int s2b_cellid_from_token(const char* tokens16, const uint8_t* len, size_t n, uint64_t* ids_out);

@@ -207,6 +207,14 @@ void ref_cellid_from_token(const char* tokens16, const uint8_t* len, size_t n, u
   for (size_t i = 0; i < n; ++i) out[i] = S2CellId::FromToken(absl::string_view(tokens16 + 16 * i, len[i])).id();
 }
 
+void ref_edge_neighbors(const uint64_t* ids, size_t n, uint64_t* out4) {
+  for (size_t i = 0; i < n; ++i) {
+    S2CellId nb[4];
+    S2CellId(ids[i]).GetEdgeNeighbors(nb);
+    for (int k = 0; k < 4; ++k) out4[4 * i + k] = nb[k].id();
+  }
+}
+
 void ref_cellid_to_point(const uint64_t* ids, size_t n, double* xyz) {
   for (size_t i = 0; i < n; ++i) {
     S2Point p = S2CellId(ids[i]).ToPoint();

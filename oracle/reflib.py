@@ -113,6 +113,12 @@ class Ref:
         self.lib.ref_cellid_to_point(_p(ids), _sz(ids.size), _p(out))
         return out
 
+    def edge_neighbors(self, ids):
+        ids = np.ascontiguousarray(ids, np.uint64)
+        out = np.empty((ids.size, 4), np.uint64)
+        self.lib.ref_edge_neighbors(_p(ids), _sz(ids.size), _p(out))
+        return out
+
     def from_face_pos_level(self, face, pos, level):
         return int(self.lib.ref_cellid_from_face_pos_level(face, pos, level))
 

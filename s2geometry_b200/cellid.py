@@ -209,6 +209,21 @@ def to_point(ids):
     return out
 
 
+def edge_neighbors(ids):
+    """S2CellId::GetEdgeNeighbors element-wise -> (N,4) ids (down, right, up, left) at each cell's own level."""
+    lib = _lib.load()
+    if _is_tensor(ids):
+        ids = _tensor_in(ids, torch.int64, 0)
+        out = torch.empty((ids.numel(), 4), dtype=torch.int64, device=ids.device)
+        with torch.cuda.device(ids.device):
+            _lib.check(lib.s2b_cellid_edge_neighbors_dev(_ptr(ids), ids.numel(), _ptr(out), _stream()))
+        return out
+    ids = _np_in(ids, np.uint64, 0)
+    out = np.empty((ids.size, 4), dtype=np.uint64)
+    _lib.check(lib.s2b_cellid_edge_neighbors(_ptr(ids), ids.size, _ptr(out)))
+    return out
+
+
 def from_token(tokens, lengths):
     """S2CellId::FromToken element-wise: tokens (N,16) uint8 slots + lengths (N,) uint8 -> ids (0 for malformed tokens)."""
     lib = _lib.load()

@@ -313,6 +313,22 @@ int s2b_cellid_to_token_dev(const uint64_t* ids_dev, size_t n, char* tok_dev, ui
   return e == cudaSuccess ? S2B_OK : cuda_fail(e, "token launch");
 }
 
+int s2b_cellid_edge_neighbors(const uint64_t* ids, size_t n, uint64_t* neighbors4_out) {
+  if (n == 0) return S2B_OK;
+  if (!ids || !neighbors4_out) return set_error(S2B_EINVAL, "null pointer");
+  OutSpec outs[1] = {{neighbors4_out, 32, 1}};
+  return run_pipelined(ids, 8, n, outs, 1, [&](const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
+    cudaError_t e = launch_edge_neighbors((const uint64_t*)in_dev, cnt, (uint64_t*)out_dev[0], st);
+    return e == cudaSuccess ? S2B_OK : cuda_fail(e, "edge_neighbors launch");
+  });
+}
+int s2b_cellid_edge_neighbors_dev(const uint64_t* ids_dev, size_t n, uint64_t* neighbors4_out_dev, void* stream) {
+  if (n == 0) return S2B_OK;
+  if (!ids_dev || !neighbors4_out_dev) return set_error(S2B_EINVAL, "null pointer");
+  if ((uintptr_t)neighbors4_out_dev % 16) return set_error(S2B_EINVAL, "neighbors4_out_dev must be 16-byte aligned");
+  cudaError_t e = launch_edge_neighbors(ids_dev, n, neighbors4_out_dev, (cudaStream_t)stream);
+  return e == cudaSuccess ? S2B_OK : cuda_fail(e, "edge_neighbors launch");
+}
 int s2b_cellid_to_point(const uint64_t* ids, size_t n, double* xyz_out) {
   if (n == 0) return S2B_OK;
   if (!ids || !xyz_out) return set_error(S2B_EINVAL, "null pointer");

@@ -241,6 +241,43 @@ S2B_HD int cellid_to_token(uint64_t id, uint32_t out[4]) {
   return len;
 }
 
+// S2CellId::level() for a valid id (s2cell_id.h:595-603).
+S2B_HD int cellid_level(uint64_t id) { return 30 - (ctz64(id) >> 1); }
+
+// S2CellId::FromFaceIJWrap (s2cell_id.cc:458-489): (i,j) just outside a face -> the leaf cell on the adjacent face.
+template <class TableT>
+S2B_HD uint64_t from_face_ij_wrap(int face, int i, int j, const TableT* pos) {
+  const int kMaxSize = 1 << 30;
+  i = i < -1 ? -1 : (i > kMaxSize ? kMaxSize : i);
+  j = j < -1 ? -1 : (j > kMaxSize ? kMaxSize : j);
+  const double kScale = 1.0 / kMaxSize;
+  const double kLimit = 1.0 + 2.2204460492503131e-16;
+  double u = kScale * (2 * (i - kMaxSize / 2) + 1);
+  double v = kScale * (2 * (j - kMaxSize / 2) + 1);
+  u = u < -kLimit ? -kLimit : (u > kLimit ? kLimit : u);
+  v = v < -kLimit ? -kLimit : (v > kLimit ? kLimit : v);
+  const P3 p = face_uv_to_xyz(face, u, v);
+  const int f2 = xyz_to_face_uv(p, &u, &v);
+  return from_face_ij(f2, st_to_ij(0.5 * (u + 1)), st_to_ij(0.5 * (v + 1)), pos);
+}
+
+// S2CellId::GetEdgeNeighbors (s2cell_id.cc:499-512): down, right, up, left neighbours at the cell's own level.
+template <class TableT>
+S2B_HD void cellid_edge_neighbors(uint64_t id, const TableT* pos, const TableT* ij, uint64_t out[4]) {
+  const int kMaxSize = 1 << 30;
+  int i, j;
+  const int level = cellid_level(id);
+  const int size = 1 << (30 - level);
+  const int face = cellid_to_face_ij(id, ij, &i, &j);
+  const int ni[4] = {i, i + size, i, i - size};
+  const int nj[4] = {j - size, j, j + size, j};
+  const bool same[4] = {j - size >= 0, i + size < kMaxSize, j + size < kMaxSize, i - size >= 0};
+  for (int k = 0; k < 4; ++k) {
+    uint64_t leaf = same[k] ? from_face_ij(face, (uint32_t)ni[k], (uint32_t)nj[k], pos) : from_face_ij_wrap(face, ni[k], nj[k], pos);
+    out[k] = cellid_parent(leaf, level);
+  }
+}
+
 // S2CellId::FromToken (s2cell_id.cc:235-254) from a 16-byte slot + length: hex digits (either case) placed from the
 // top nibble down; any other character, or a length above 16, gives S2CellId::None() (0). "X" therefore decodes to 0.
 S2B_HD uint64_t cellid_from_token(const unsigned char* tok, int len) {

@@ -166,6 +166,28 @@ __global__ void __launch_bounds__(kThreads) to_point_kernel(const uint64_t* __re
   }
 }
 
+// S2CellId::GetEdgeNeighbors (s2cell_id.cc:499-512): out[4*i + k], k = down, right, up, left.
+__global__ void __launch_bounds__(kThreads) edge_neighbors_kernel(const uint64_t* __restrict__ ids, size_t n, uint64_t* __restrict__ out) {
+  __shared__ uint16_t s_pos[1024], s_ij[1024];
+  for (int k = threadIdx.x; k < 1024; k += kThreads) { s_pos[k] = g_hilbert.pos[k]; s_ij[k] = g_hilbert.ij[k]; }
+  __syncthreads();
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    uint64_t nb[4];
+    cellid_edge_neighbors(__ldcs(ids + i), s_pos, s_ij, nb);
+    ulonglong2* o = (ulonglong2*)(out + 4 * i);
+    __stcs(o, make_ulonglong2(nb[0], nb[1]));
+    __stcs(o + 1, make_ulonglong2(nb[2], nb[3]));
+  }
+}
+
+cudaError_t launch_edge_neighbors(const uint64_t* ids, size_t n, uint64_t* out, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  edge_neighbors_kernel<<<grid_for(n, (const void*)edge_neighbors_kernel), kThreads, 0, st>>>(ids, n, out);
+  count_launch();
+  return cudaGetLastError();
+}
+
 // S2CellId::FromToken (s2cell_id.cc:235-254).
 __global__ void __launch_bounds__(kThreads) from_token_kernel(const uint4* __restrict__ tok, const uint8_t* __restrict__ len, size_t n, uint64_t* __restrict__ ids) {
   const size_t stride = (size_t)gridDim.x * kThreads;

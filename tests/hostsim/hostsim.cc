@@ -93,3 +93,7 @@ extern "C" uint64_t hs_check_wide_hilbert(const uint32_t* ij, size_t n) {
 extern "C" void hs_cellid_from_token(const char* tok16, const uint8_t* len, size_t n, uint64_t* out) {
   for (size_t i = 0; i < n; ++i) out[i] = cellid_from_token((const unsigned char*)tok16 + 16 * i, len[i]);
 }
+
+extern "C" void hs_edge_neighbors(const uint64_t* ids, size_t n, uint64_t* out4) {
+  for (size_t i = 0; i < n; ++i) cellid_edge_neighbors(ids[i], kHilbert.pos, kHilbert.ij, out4 + 4 * i);
+}

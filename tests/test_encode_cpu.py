@@ -197,3 +197,23 @@ def test_from_token_hostsim(hostsim, ref):
     o = np.empty(1, np.uint64)
     hostsim.hs_cellid_from_token(vp(up), vp(np.array([3], np.uint8)), ctypes.c_size_t(1), vp(o))
     assert o[0] == 0x4AF0000000000000 == ref.from_token(up, np.array([3], np.uint8))[0]
+
+
+def random_ids_all_levels(ref, n, seed):
+    from s2geometry_b200 import synth
+    rng = np.random.default_rng(seed)
+    leaf = ref.encode_points(synth.sphere_points(n, seed), 30, 1)
+    lv = rng.integers(0, 31, n)
+    lsb = np.uint64(1) << (2 * (30 - lv)).astype(np.uint64)
+    ids = (leaf & (~lsb + np.uint64(1))) | lsb
+    # cells along face edges and corners (their neighbours wrap to other faces)
+    edge = np.array([ref.from_face_pos_level(f, 0, l) for f in range(6) for l in (0, 1, 5, 30)] +
+                    [ref.from_face_pos_level(f, (1 << 60) - 1, l) for f in range(6) for l in (1, 7, 30)], np.uint64)
+    return np.concatenate([ids, edge])
+
+
+def test_edge_neighbors_hostsim(hostsim, ref):
+    ids = random_ids_all_levels(ref, 200000, 17)
+    out = np.empty((len(ids), 4), np.uint64)
+    hostsim.hs_edge_neighbors(vp(ids), ctypes.c_size_t(len(ids)), vp(out))
+    assert (out == ref.edge_neighbors(ids)).all()

@@ -201,3 +201,14 @@ def test_cuda_vs_independent_restatement(torch_cuda):
     for m in (0, 1, 2):
         want = np.array([rs.polygon_contains([loop], q, m) for q in pts], np.uint8)
         assert (ContainsPointQuery(ix, m).contains(pts) == want).all(), m
+
+
+def test_edge_neighbors_on_gpu(torch_cuda, ref):
+    torch = torch_cuda
+    from s2geometry_b200 import cellid
+    from tests.test_encode_cpu import random_ids_all_levels
+    ids = random_ids_all_levels(ref, 1_000_000, 19)
+    want = ref.edge_neighbors(ids)
+    assert (cellid.edge_neighbors(ids) == want).all()
+    d = torch.from_numpy(ids.view(np.int64)).cuda()
+    assert (cellid.edge_neighbors(d).cpu().numpy().view(np.uint64) == want).all()
