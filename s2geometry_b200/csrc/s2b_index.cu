@@ -6,6 +6,7 @@
 // edges, with the Sign chain (triage -> stable -> exact superaccumulator -> symbolic) entirely on the device.
 // Index arrays are read through the read-only path; points are streamed (24 B in, 1 B / a few atomics out).
 #include <cuda_pipeline.h>
+#include <cub/device/device_scan.cuh>
 
 #include <cstdlib>
 #include <new>
@@ -316,13 +317,39 @@ locate_fast_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint3
   unc_slots.finish(uncertain, lane);
 }
 
+// Cell-major ordering of the edge-bearing hits (large indexes only). Phase B is bound by its memory access pattern: with
+// hits in point order every thread reads a different cell's record, clips and edges (L2 hit rate 59 % on the 136 MB join
+// index, 12 of 32 lanes busy because neighbouring lanes have different edge counts). A counting sort by cell index —
+// histogram with atomics, exclusive scan, scatter — makes neighbouring threads work on the same cell: coalesced index
+// reads and identical loop trip counts.
+__global__ void __launch_bounds__(kThreads)
+cell_count_kernel(const HitWork* __restrict__ work, const unsigned int* __restrict__ counters, unsigned int* __restrict__ cell_counts) {
+  const unsigned int count = counters[0];
+  for (unsigned int w = blockIdx.x * kThreads + threadIdx.x; w < count; w += gridDim.x * kThreads) {
+    const int c = work[w].cell;
+    if (c >= 0) atomicAdd(cell_counts + c, 1u);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+cell_scatter_kernel(const HitWork* __restrict__ work, const unsigned int* __restrict__ counters, unsigned int* __restrict__ cell_cursor,
+                    HitWork* __restrict__ sorted) {
+  const unsigned int count = counters[0];
+  for (unsigned int w = blockIdx.x * kThreads + threadIdx.x; w < count; w += gridDim.x * kThreads) {
+    const HitWork hw = work[w];
+    if (hw.cell >= 0) sorted[atomicAdd(cell_cursor + hw.cell, 1u)] = hw;
+  }
+}
+
 template <int kMode, int kCtasPerSm>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 process_kernel(const FlatIndexView ix, const double* __restrict__ xyz, const HitWork* __restrict__ work_base, uint32_t capacity,
                const unsigned int* __restrict__ counters, int which_list, int model, const QueryOut out) {
   // list 0: hits with edge work, stored forward from work_base[0]; list 1: interior hits, stored backward from the end
-  const unsigned int count = counters[which_list];
-  const HitWork* work = which_list == 0 ? work_base : work_base + (capacity - count);
+  // which_list == 3: the cell-sorted copy of list 0; its length is the last element of the scanned per-cell counts,
+  // which the host passes as `counters` (so counters[0] is the length)
+  const unsigned int count = which_list == 3 ? counters[0] : counters[which_list];
+  const HitWork* work = which_list == 1 ? work_base + (capacity - count) : work_base;
   const unsigned int stride = gridDim.x * kThreads;
   const unsigned lane = threadIdx.x & 31u;
   // warp-uniform trip count + __syncwarp(): lanes with long edge lists or exact-stage work rejoin every iteration
@@ -458,9 +485,23 @@ static cudaError_t launch_query_t(const FlatIndexView& ix, const double* xyz, si
   const size_t capacity = round + 4 * max_warps * kSlotChunk;
   const size_t unc_capacity = round + max_warps * kSlotChunk;
   const bool use_fast = !g_force_exact_locate && ((uintptr_t)xyz % 16 == 0);   // cp.async staging needs 16-byte alignment
-  cudaError_t e = cudaMallocAsync((void**)&work, sizeof(HitWork) * capacity + 256 + (use_fast ? sizeof(uint32_t) * unc_capacity : 0), st);
+  // cell-major ordering of the edge hits pays off when the index is too large to stay cache resident and has enough
+  // cells for the per-cell atomics not to collide (S2B_SORT_BY_CELL=0/1 overrides)
+  const size_t C = ix.num_cells;
+  bool sort_by_cell = C >= 65536;
+  if (const char* ev = getenv("S2B_SORT_BY_CELL")) sort_by_cell = atoi(ev) != 0 && C > 0;
+  size_t scan_tmp_bytes = 0;
+  if (sort_by_cell) cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp_bytes, (unsigned int*)nullptr, (unsigned int*)nullptr, (int)(C + 1), st);
+  auto up256 = [](size_t v) { return (v + 255) / 256 * 256; };
+  const size_t b_work = up256(sizeof(HitWork) * capacity), b_counter = 256, b_unc = use_fast ? up256(sizeof(uint32_t) * unc_capacity) : 0,
+               b_sorted = sort_by_cell ? up256(sizeof(HitWork) * round) : 0, b_cells = sort_by_cell ? up256(sizeof(unsigned int) * (C + 1)) : 0,
+               b_scan = sort_by_cell ? up256(scan_tmp_bytes) : 0;
+  cudaError_t e = cudaMallocAsync((void**)&work, b_work + b_counter + b_unc + b_sorted + b_cells + b_scan, st);
   if (e != cudaSuccess) return e;
-  counter = (unsigned int*)((char*)work + sizeof(HitWork) * capacity);   // 8-byte aligned tail: [0] edge slots, [1] interior slots, [2] uncertain
+  counter = (unsigned int*)((char*)work + b_work);   // [0] edge slots, [1] interior slots, [2] undecided points
+  HitWork* sorted = (HitWork*)((char*)counter + b_counter + b_unc);
+  unsigned int* cell_counts = (unsigned int*)((char*)sorted + b_sorted);
+  void* scan_tmp = (char*)cell_counts + b_cells;
   uint32_t* uncertain = (uint32_t*)((char*)counter + 256);
   const int pv = process_variant();
   void (*proc)(const FlatIndexView, const double*, const HitWork*, uint32_t, const unsigned int*, int, int, const QueryOut) =
@@ -504,7 +545,23 @@ static cudaError_t launch_query_t(const FlatIndexView& ix, const double* xyz, si
     }
 #undef S2B_LOCATE
     count_launch();
-    proc<<<proc_grid, kThreads, 0, st>>>(ix, xyz + 3 * off, work, (uint32_t)capacity, counter, 0, model, o);
+    if (sort_by_cell) {
+      // counting sort of list 0 by cell: cell_counts[C+1] -> exclusive scan (cell_counts[C] = number of valid hits) -> scatter
+      e = cudaMemsetAsync(cell_counts, 0, sizeof(unsigned int) * (C + 1), st);
+      if (e != cudaSuccess) break;
+      const int sort_grid = grid_for_ix(round, (const void*)cell_count_kernel);
+      cell_count_kernel<<<sort_grid, kThreads, 0, st>>>(work, counter, cell_counts);
+      count_launch();
+      e = cub::DeviceScan::ExclusiveSum(scan_tmp, scan_tmp_bytes, cell_counts, cell_counts, (int)(C + 1), st);
+      if (e != cudaSuccess) break;
+      count_launch();
+      // the scatter advances cell_counts[c] from the start to the end of cell c's segment; cell_counts[C] stays the total
+      cell_scatter_kernel<<<sort_grid, kThreads, 0, st>>>(work, counter, cell_counts, sorted);
+      count_launch();
+      proc<<<proc_grid, kThreads, 0, st>>>(ix, xyz + 3 * off, sorted, 0u, cell_counts + C, 3, model, o);
+    } else {
+      proc<<<proc_grid, kThreads, 0, st>>>(ix, xyz + 3 * off, work, (uint32_t)capacity, counter, 0, model, o);
+    }
     count_launch();
     if (interior_mode == 0) {
       proc<<<proc_grid, kThreads, 0, st>>>(ix, xyz + 3 * off, work, (uint32_t)capacity, counter, 1, model, o);
