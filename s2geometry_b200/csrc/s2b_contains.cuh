@@ -27,7 +27,8 @@ struct FlatIndexView {
   const FlatClip* clips;
   const FlatEdge* edges;
   const uint32_t* lut;
-  const uint8_t* interior_clips;   // per cell: k > 0 = no edges at all, k clips that all contain the centre; 0 = has edges
+  const int32_t* interior_info;    // per cell: 0 = has edges; pure interior cell (no edges, all clips contain the centre):
+                                   //   -(shape_id + 1) if it has exactly one clip, else the number of clips
   uint32_t num_cells;
   int lut_shift;
   int num_shape_ids;

@@ -18,12 +18,12 @@ struct HostFlat {
   std::vector<FlatClip> clips;
   std::vector<FlatEdge> edges;
   std::vector<uint32_t> lut;   // num_buckets + 2 entries
-  std::vector<uint8_t> interior_clips;  // per cell, see FlatIndexView
+  std::vector<int32_t> interior_info;  // per cell, see FlatIndexView
   uint64_t num_buckets = 0;
   int lut_shift = 0;
   FlatIndexView view(const uint64_t* cell_ids, int num_shape_ids) const {
     FlatIndexView v;
-    v.cell_ids = cell_ids; v.cells = cells.data(); v.clips = clips.data(); v.edges = edges.data(); v.lut = lut.data(); v.interior_clips = interior_clips.data();
+    v.cell_ids = cell_ids; v.cells = cells.data(); v.clips = clips.data(); v.edges = edges.data(); v.lut = lut.data(); v.interior_info = interior_info.data();
     v.num_cells = (uint32_t)cells.size(); v.lut_shift = lut_shift; v.num_shape_ids = num_shape_ids;
     return v;
   }
@@ -59,7 +59,7 @@ inline int pack_flat_index(const S2bFlatIndex& f, HostFlat* out, std::string* er
   out->num_buckets = nb;
   out->lut_shift = 61 - 2 * lut_level;
   try {
-    out->cells.resize(C); out->clips.resize(K); out->edges.resize(E); out->lut.resize(nb + 2); out->interior_clips.resize(C + 1);
+    out->cells.resize(C); out->clips.resize(K); out->edges.resize(E); out->lut.resize(nb + 2); out->interior_info.resize(C + 1);
   } catch (const std::bad_alloc&) {
     return fail(S2B_ENOMEM, "host allocation failed");
   }
@@ -77,10 +77,10 @@ inline int pack_flat_index(const S2bFlatIndex& f, HostFlat* out, std::string* er
   // at clips or edges when only "any"/"how many" is asked.
   for (uint64_t c = 0; c < C; ++c) {
     uint32_t b = f.cell_clip_begin[c], e = f.cell_clip_begin[c + 1];
-    bool pure = e > b && e - b <= 255;
+    bool pure = e > b;
     for (uint32_t k = b; k < e && pure; ++k)
       pure = f.clip_edge_begin[k + 1] == f.clip_edge_begin[k] && (f.clip_flags[k] & 1);
-    out->interior_clips[c] = pure ? (uint8_t)(e - b) : 0;
+    out->interior_info[c] = !pure ? 0 : (e - b == 1 ? -(f.clip_shape_id[b] + 1) : (int32_t)(e - b));
   }
   // lut[b] = number of cells whose range_max < first leaf id of bucket b (the first cell a leaf of bucket b can be
   // in), tagged with the bucket kind (s2b_contains.cuh): empty / entirely inside that cell / mixed.

@@ -55,11 +55,6 @@ struct QueryOut {
 //                     of lanes that hit, and does not cap the occupancy of phase A.
 struct HitWork { uint32_t point; int32_t cell; };
 
-// interior_mode: what phase A may answer by itself for points in pure interior cells (no edges, every clip contains the
-// centre): 0 nothing (all hits go to the work lists), 1 "any" (flag = 1), 2 "count" (per-point count = number of clips).
-// Hits that need edge work are appended at the front of `work` (count in counters[0]); interior hits that still
-// need per-shape output (histogram / fill / one shape) are appended from the back (count in counters[1]), so phase B
-// runs over two homogeneous lists.
 // Work-list slots are reserved per warp in chunks of kSlotChunk with ONE global atomicAdd per chunk (a same-address
 // atomic per warp iteration serialises at the L2: ~600k of them per 20M points when most warps see a hit). Unused slots
 // of a chunk are filled with a sentinel (cell = -1) that phase B skips.
@@ -92,16 +87,51 @@ struct WarpSlots {
   }
 };
 
-// interior_mode: what phase A may answer by itself for points in pure interior cells (no edges, every clip contains the
-// centre): 0 nothing (all hits go to the work lists), 1 "any" (flag = 1), 2 "count" (per-point count = number of clips).
-// Hits that need edge work are appended at the front of `work` (slots reserved in counters[0]); interior hits that
-// still need per-shape output (histogram / fill / one shape) are appended from the back (counters[1]), so phase B runs
-// over two homogeneous lists.
-template <int kCtasPerSm, int kPointsPerThread>
+// What phase A does with a located point. interior_mode says what may be answered on the spot for points in pure
+// interior cells (no edges, every clip contains the centre):
+//   0 nothing (fill)      1 "any": flag = 1      2 "count": per-point count = number of clips
+//   3 histogram: cells with a single clip add 1 to that shape's counter right here
+//   4 one shape: cells with a single clip compare its shape id with the target
+// Everything else goes to the work lists: edge-bearing hits at the front of `work` (and, if cell_counts != nullptr, into the
+// per-cell histogram of the counting sort), interior hits that still need per-shape output at the back.
+struct PhaseAOut {
+  HitWork* work; uint32_t capacity; unsigned int* counters;
+  uint8_t* flags; uint32_t* counts;
+  unsigned long long* hist; int target_shape; unsigned int* cell_counts;
+};
+
+template <int kInteriorMode>
+__device__ __forceinline__ void route_located(const FlatIndexView& ix, const PhaseAOut& o, bool write_outputs, uint32_t i, int c,
+                                              WarpSlots& edge_slots, WarpSlots& interior_slots, unsigned lane) {
+  int info = 0;
+  if (c >= 0) info = ix.interior_info[c];
+  uint8_t flag = 0;
+  uint32_t cnt = 0;
+  const bool to_edges = c >= 0 && info == 0;
+  bool to_interior = false;
+  if (c >= 0 && info != 0) {
+    const int single_shape = info < 0 ? -info - 1 : -1;
+    if (kInteriorMode == 1) flag = 1;
+    else if (kInteriorMode == 2) cnt = info < 0 ? 1u : (uint32_t)info;
+    else if (kInteriorMode == 3 && single_shape >= 0) atomicAdd(o.hist + single_shape, 1ull);
+    else if (kInteriorMode == 4 && single_shape >= 0) flag = single_shape == o.target_shape;
+    else to_interior = true;
+  }
+  if (write_outputs) {
+    if (o.flags) o.flags[i] = flag;
+    if (o.counts) o.counts[i] = cnt;
+  }
+  if (to_edges && o.cell_counts) atomicAdd(o.cell_counts + c, 1u);
+  edge_slots.append(to_edges, HitWork{i, c}, o.work, o.capacity, o.counters, +1, lane);
+  if (kInteriorMode != 1 && kInteriorMode != 2) interior_slots.append(to_interior, HitWork{i, c}, o.work, o.capacity, o.counters + 1, -1, lane);
+}
+
+// Phase A, exact: FP64 K1 + Locate, then route_located.
+template <int kInteriorMode, int kCtasPerSm, int kPointsPerThread>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 locate_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint32_t n_points, const uint32_t* __restrict__ list,
-              HitWork* __restrict__ work, uint32_t capacity, unsigned int* __restrict__ counters, int interior_mode,
-              uint8_t* __restrict__ flags, uint32_t* __restrict__ counts) {
+              const PhaseAOut o) {
+  unsigned int* const counters = o.counters;
   // list == nullptr: points 0..n_points-1. Otherwise: the points whose indices are list[0..counters[2]) (entries equal
   // to 0xFFFFFFFF are unused reservation slots) — the ones the FP32 pre-filter could not decide.
   const uint32_t n = list ? counters[2] : n_points;
@@ -139,28 +169,11 @@ locate_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint32_t n
     for (int t = 0; t < kPointsPerThread; ++t) {
       const uint32_t i = idx[t];
       const bool valid = i != 0xFFFFFFFFu;
-      const int c = valid ? cell[t] : -1;
-      uint32_t interior = 0;
-      if (c >= 0) interior = ix.interior_clips[c];
-      uint8_t flag = 0;
-      uint32_t cnt = 0;
-      const bool to_edges = c >= 0 && interior == 0;
-      bool to_interior = false;
-      if (c >= 0 && interior != 0) {
-        if (interior_mode == 1) flag = 1;
-        else if (interior_mode == 2) cnt = interior;
-        else to_interior = true;
-      }
-      if (valid) {
-        if (flags) flags[i] = flag;
-        if (counts) counts[i] = cnt;
-      }
-      edge_slots.append(to_edges, HitWork{i, c}, work, capacity, counters, +1, lane);
-      if (interior_mode == 0) interior_slots.append(to_interior, HitWork{i, c}, work, capacity, counters + 1, -1, lane);
+      route_located<kInteriorMode>(ix, o, valid, i, valid ? cell[t] : -1, edge_slots, interior_slots, lane);
     }
   }
-  edge_slots.finish(work, capacity, +1, lane);
-  interior_slots.finish(work, capacity, -1, lane);
+  edge_slots.finish(o.work, o.capacity, +1, lane);
+  interior_slots.finish(o.work, o.capacity, -1, lane);
 }
 
 // Phase A0: FP32 pre-filter for Locate. Most points are nowhere near a boundary that matters, so the face, (i,j) and
@@ -206,11 +219,10 @@ __device__ __forceinline__ int approx_leaf_coord(float w) {   // w = u or v  -> 
 // in flight while tile k is processed, so the bytes in flight do not occupy registers (with ~150 instructions per point
 // a register-staged version of this kernel was DRAM-latency-bound at 2.0 TB/s: profiles/r1_query_prefilter_ncu.json).
 // Tile = kThreads * kPointsPerThread points = 12 KB for 2 points per thread; requires xyz to be 16-byte aligned.
-template <int kPointsPerThread>
+template <int kInteriorMode, int kPointsPerThread>
 __global__ void __launch_bounds__(kThreads, 6)
-locate_fast_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint32_t n, HitWork* __restrict__ work, uint32_t capacity,
-                   unsigned int* __restrict__ counters, uint32_t* __restrict__ uncertain, int interior_mode,
-                   uint8_t* __restrict__ flags, uint32_t* __restrict__ counts) {
+locate_fast_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint32_t n, uint32_t* __restrict__ uncertain, const PhaseAOut o) {
+  unsigned int* const counters = o.counters;
   constexpr uint32_t kTilePoints = kThreads * kPointsPerThread;
   constexpr uint32_t kTileBytes = kTilePoints * 24;
   constexpr uint32_t kChunks = kTileBytes / 16;                 // 16-byte cp.async chunks per tile
@@ -290,47 +302,23 @@ locate_fast_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint3
         if (kind == kLutInside) c = (int)(e0 & kLutIndexMask);
         else if (kind != kLutEmpty) certain = false;
       }
-      uint32_t interior = 0;
-      if (certain && c >= 0) interior = ix.interior_clips[c];
-      uint8_t flag = 0;
-      uint32_t cnt = 0;
-      const bool to_edges = certain && c >= 0 && interior == 0;
-      bool to_interior = false;
-      if (certain && c >= 0 && interior != 0) {
-        if (interior_mode == 1) flag = 1;
-        else if (interior_mode == 2) cnt = interior;
-        else to_interior = true;
-      }
-      if (valid && certain) {          // undecided points are written by the exact kernel
-        if (flags) flags[i] = flag;
-        if (counts) counts[i] = cnt;
-      }
-      edge_slots.append(to_edges, HitWork{i, c}, work, capacity, counters, +1, lane);
-      if (interior_mode == 0) interior_slots.append(to_interior, HitWork{i, c}, work, capacity, counters + 1, -1, lane);
+      // undecided points are routed (and their outputs written) by the exact kernel
+      route_located<kInteriorMode>(ix, o, valid && certain, i, certain ? c : -1, edge_slots, interior_slots, lane);
       unc_slots.append(valid && !certain, i, uncertain, counters + 2, lane);
     }
     __syncthreads();                                            // everyone is done with this stage before it is refilled
   }
   __pipeline_wait_prior(0);
-  edge_slots.finish(work, capacity, +1, lane);
-  interior_slots.finish(work, capacity, -1, lane);
+  edge_slots.finish(o.work, o.capacity, +1, lane);
+  interior_slots.finish(o.work, o.capacity, -1, lane);
   unc_slots.finish(uncertain, lane);
 }
 
 // Cell-major ordering of the edge-bearing hits (large indexes only). Phase B is bound by its memory access pattern: with
 // hits in point order every thread reads a different cell's record, clips and edges (L2 hit rate 59 % on the 136 MB join
 // index, 12 of 32 lanes busy because neighbouring lanes have different edge counts). A counting sort by cell index —
-// histogram with atomics, exclusive scan, scatter — makes neighbouring threads work on the same cell: coalesced index
+// per-cell hit counts (accumulated by phase A as it appends), exclusive scan, scatter — makes neighbouring threads work on the same cell: coalesced index
 // reads and identical loop trip counts.
-__global__ void __launch_bounds__(kThreads)
-cell_count_kernel(const HitWork* __restrict__ work, const unsigned int* __restrict__ counters, unsigned int* __restrict__ cell_counts) {
-  const unsigned int count = counters[0];
-  for (unsigned int w = blockIdx.x * kThreads + threadIdx.x; w < count; w += gridDim.x * kThreads) {
-    const int c = work[w].cell;
-    if (c >= 0) atomicAdd(cell_counts + c, 1u);
-  }
-}
-
 __global__ void __launch_bounds__(kThreads)
 cell_scatter_kernel(const HitWork* __restrict__ work, const unsigned int* __restrict__ counters, unsigned int* __restrict__ cell_cursor,
                     HitWork* __restrict__ sorted) {
@@ -441,33 +429,9 @@ static void keep_pool_memory_once() {
 // Diagnostics (s2b_diag_force_exact_locate): skip the FP32 pre-filter, every point goes through the FP64 Locate.
 static bool g_force_exact_locate = false;
 
-// Tuning knob (env S2B_LOCATE_VARIANT): CTAs per SM x points per thread of phase A. 0 = default.
-static int locate_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("S2B_LOCATE_VARIANT");
-    v = e ? atoi(e) : 2;   // measured best overall on B200: 4 CTAs/SM x 2 points per thread
-  }
-  return v;
-}
-
-static int fast_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("S2B_FAST_VARIANT");
-    v = e ? atoi(e) : 2;
-  }
-  return v;
-}
-
-static int process_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("S2B_PROCESS_VARIANT");
-    v = e ? atoi(e) : 2;
-  }
-  return v;
-}
+// Launch shapes, fixed after measurement on B200 (DESIGN.md "Measured and rejected" lists the alternatives): exact Locate
+// 4 CTAs/SM x 2 points per thread, FP32 pre-filter 2 points per thread, phase B 2 CTAs/SM.
+constexpr int kLocateCtas = 4, kLocatePoints = 2, kFastPoints = 2, kProcessCtas = 2;
 
 template <int kMode>
 static cudaError_t launch_query_t(const FlatIndexView& ix, const double* xyz, size_t n, int model, const QueryOut& out, cudaStream_t st) {
@@ -503,12 +467,11 @@ static cudaError_t launch_query_t(const FlatIndexView& ix, const double* xyz, si
   unsigned int* cell_counts = (unsigned int*)((char*)sorted + b_sorted);
   void* scan_tmp = (char*)cell_counts + b_cells;
   uint32_t* uncertain = (uint32_t*)((char*)counter + 256);
-  const int pv = process_variant();
-  void (*proc)(const FlatIndexView, const double*, const HitWork*, uint32_t, const unsigned int*, int, int, const QueryOut) =
-      pv == 3 ? process_kernel<kMode, 3> : (pv == 4 ? process_kernel<kMode, 4> : process_kernel<kMode, 2>);
+  constexpr int kInteriorMode = kMode == kModeAny ? 1 : (kMode == kModeCount ? 2 : (kMode == kModeHistogram ? 3 : (kMode == kModeShape ? 4 : 0)));
+  const auto proc = process_kernel<kMode, kProcessCtas>;
+  const auto fast = locate_fast_kernel<kInteriorMode, kFastPoints>;
+  const auto exact = locate_kernel<kInteriorMode, kLocateCtas, kLocatePoints>;
   const int proc_grid = grid_for_ix(round, (const void*)proc);
-  const int interior_mode = kMode == kModeAny ? 1 : (kMode == kModeCount ? 2 : 0);
-  const int variant = locate_variant();
   for (size_t off = 0; off < n && e == cudaSuccess; off += round) {
     const size_t cnt = n - off < round ? n - off : round;
     e = cudaMemsetAsync(counter, 0, 4 * sizeof(unsigned int), st);
@@ -519,39 +482,23 @@ static cudaError_t launch_query_t(const FlatIndexView& ix, const double* xyz, si
     if (o.offsets) o.offsets += off;
     uint8_t* fl = (kMode == kModeAny || kMode == kModeShape) ? o.flags : nullptr;
     uint32_t* pc = kMode == kModeCount ? o.per_point : nullptr;
+    if (sort_by_cell) {
+      // counting sort of list 0 by cell; the per-cell hit counts are accumulated by phase A itself
+      e = cudaMemsetAsync(cell_counts, 0, sizeof(unsigned int) * (C + 1), st);
+      if (e != cudaSuccess) break;
+    }
+    const PhaseAOut pa{work, (uint32_t)capacity, counter, fl, pc, o.counts, o.shape_id, sort_by_cell ? cell_counts : nullptr};
     const uint32_t* list = nullptr;
     if (use_fast) {
-#define S2B_FAST(P)                                                                                                   \
-  locate_fast_kernel<P><<<grid_for_ix((cnt + P - 1) / P, (const void*)locate_fast_kernel<P>), kThreads, 0, st>>>(        \
-      ix, xyz + 3 * off, (uint32_t)cnt, work, (uint32_t)capacity, counter, uncertain, interior_mode, fl, pc)
-      switch (fast_variant()) {
-        case 1: S2B_FAST(1); break;
-        case 3: S2B_FAST(3); break;
-        default: S2B_FAST(2); break;
-      }
-#undef S2B_FAST
+      fast<<<grid_for_ix((cnt + kFastPoints - 1) / kFastPoints, (const void*)fast), kThreads, 0, st>>>(ix, xyz + 3 * off, (uint32_t)cnt, uncertain, pa);
       count_launch();
       list = uncertain;
     }
-#define S2B_LOCATE(C, P)                                                                                             \
-  locate_kernel<C, P><<<grid_for_ix((cnt + P - 1) / P, (const void*)locate_kernel<C, P>), kThreads, 0, st>>>(            \
-      ix, xyz + 3 * off, (uint32_t)cnt, list, work, (uint32_t)capacity, counter, interior_mode, fl, pc)
-    switch (variant) {
-      case 0: S2B_LOCATE(6, 1); break;
-      case 1: S2B_LOCATE(8, 1); break;
-      case 3: S2B_LOCATE(6, 2); break;
-      case 4: S2B_LOCATE(3, 4); break;
-      default: S2B_LOCATE(4, 2); break;
-    }
-#undef S2B_LOCATE
+    exact<<<grid_for_ix((cnt + kLocatePoints - 1) / kLocatePoints, (const void*)exact), kThreads, 0, st>>>(ix, xyz + 3 * off, (uint32_t)cnt, list, pa);
     count_launch();
     if (sort_by_cell) {
-      // counting sort of list 0 by cell: cell_counts[C+1] -> exclusive scan (cell_counts[C] = number of valid hits) -> scatter
-      e = cudaMemsetAsync(cell_counts, 0, sizeof(unsigned int) * (C + 1), st);
-      if (e != cudaSuccess) break;
-      const int sort_grid = grid_for_ix(round, (const void*)cell_count_kernel);
-      cell_count_kernel<<<sort_grid, kThreads, 0, st>>>(work, counter, cell_counts);
-      count_launch();
+      // cell_counts[C+1] -> exclusive scan (cell_counts[C] = number of valid hits) -> scatter
+      const int sort_grid = grid_for_ix(round, (const void*)cell_scatter_kernel);
       e = cub::DeviceScan::ExclusiveSum(scan_tmp, scan_tmp_bytes, cell_counts, cell_counts, (int)(C + 1), st);
       if (e != cudaSuccess) break;
       count_launch();
@@ -563,7 +510,7 @@ static cudaError_t launch_query_t(const FlatIndexView& ix, const double* xyz, si
       proc<<<proc_grid, kThreads, 0, st>>>(ix, xyz + 3 * off, work, (uint32_t)capacity, counter, 0, model, o);
     }
     count_launch();
-    if (interior_mode == 0) {
+    if (kInteriorMode != 1 && kInteriorMode != 2) {
       proc<<<proc_grid, kThreads, 0, st>>>(ix, xyz + 3 * off, work, (uint32_t)capacity, counter, 1, model, o);
       count_launch();
     }
@@ -620,7 +567,7 @@ int s2b_index_create(const S2bFlatIndex* f, S2bIndex** out) {
   auto align = [](size_t v) { return (v + 255) / 256 * 256; };
   size_t o_ids = 0, o_cells = o_ids + align(8 * (C + 1)), o_clips = o_cells + align(sizeof(FlatCell) * (C + 1)),
          o_edges = o_clips + align(sizeof(FlatClip) * (K + 1)), o_lut = o_edges + align(sizeof(FlatEdge) * (E + 1)),
-         o_kind = o_lut + align(4 * (nb + 2)), o_view = o_kind + align(C + 1), total = o_view + align(sizeof(FlatIndexView));
+         o_kind = o_lut + align(4 * (nb + 2)), o_view = o_kind + align(4 * (C + 1)), total = o_view + align(sizeof(FlatIndexView));
   e = cudaMalloc(&ix->blob, total);
   if (e != cudaSuccess) { delete ix; return cuda_fail(e, "cudaMalloc(index)"); }
   ix->blob_bytes = total;
@@ -631,14 +578,14 @@ int s2b_index_create(const S2bFlatIndex* f, S2bIndex** out) {
   ok &= K == 0 || cudaMemcpy(base + o_clips, clips.data(), sizeof(FlatClip) * K, cudaMemcpyHostToDevice) == cudaSuccess;
   ok &= E == 0 || cudaMemcpy(base + o_edges, edges.data(), sizeof(FlatEdge) * E, cudaMemcpyHostToDevice) == cudaSuccess;
   ok &= cudaMemcpy(base + o_lut, lut.data(), 4 * (nb + 2), cudaMemcpyHostToDevice) == cudaSuccess;
-  ok &= cudaMemcpy(base + o_kind, hf.interior_clips.data(), C + 1, cudaMemcpyHostToDevice) == cudaSuccess;
+  ok &= cudaMemcpy(base + o_kind, hf.interior_info.data(), 4 * (C + 1), cudaMemcpyHostToDevice) == cudaSuccess;
   if (!ok) { e = cudaGetLastError(); cudaFree(ix->blob); delete ix; return cuda_fail(e, "cudaMemcpy(index)"); }
   ix->view.cell_ids = (const uint64_t*)(base + o_ids);
   ix->view.cells = (const FlatCell*)(base + o_cells);
   ix->view.clips = (const FlatClip*)(base + o_clips);
   ix->view.edges = (const FlatEdge*)(base + o_edges);
   ix->view.lut = (const uint32_t*)(base + o_lut);
-  ix->view.interior_clips = (const uint8_t*)(base + o_kind);
+  ix->view.interior_info = (const int32_t*)(base + o_kind);
   ix->view.num_cells = (uint32_t)C;
   ix->view.lut_shift = lut_shift;
   ix->view.num_shape_ids = f->num_shape_ids;
