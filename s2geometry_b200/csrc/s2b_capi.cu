@@ -239,6 +239,24 @@ int s2b_device_count(void) {
 uint64_t s2b_launch_count(void) { return g_launches.load(); }
 int s2b_diag_force_correctly_rounded(int on) { return g_force_cr.exchange(on ? 1 : 0); }
 
+int s2b_diag_filter_deviation_dev(const double* latlng_dev, size_t n, double* max_deviation_out, uint64_t* unflagged_face_flips_out, void* stream) {
+  if (!max_deviation_out || !unflagged_face_flips_out || (n && !latlng_dev)) return set_error(S2B_EINVAL, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* d = nullptr;
+  cudaError_t e = cudaMallocAsync((void**)&d, 16, st);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync");
+  e = cudaMemsetAsync(d, 0, 16, st);
+  if (e == cudaSuccess) e = launch_filter_deviation(latlng_dev, n, d, st);
+  unsigned long long h[2] = {0, 0};
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFreeAsync(d, st);
+  if (e != cudaSuccess) return cuda_fail(e, "filter deviation");
+  memcpy(max_deviation_out, &h[0], 8);
+  *unflagged_face_flips_out = h[1];
+  return S2B_OK;
+}
+
 int s2b_encode_points(const double* xyz, size_t n, int level, uint64_t* ids_out) {
   return encode_host(kInXYZ, xyz, 24, n, &level, 1, ids_out, nullptr);
 }

@@ -208,16 +208,28 @@ S2B_HD bool cellid_contains(uint64_t a, uint64_t b) { return b >= cellid_range_m
 // S2CellId::ToToken (s2cell_id.cc:217-233): the 16-digit lowercase hex of the id without its trailing '0'
 // digits ("X" for id 0), written as a fixed 16-byte slot (four little-endian 32-bit words, NUL padded). Returns strlen.
 // Works on 16-bit chunks in 32-bit registers (64-bit SWAR costs twice the instructions on the GPU).
+S2B_HD uint32_t ascii_hex4(uint32_t v) {  // 4 bytes holding 0..15 each -> their lowercase hex digits
+  uint32_t ge10 = ((v + 0x06060606u) >> 4) & 0x01010101u;
+  return v + 0x30303030u + ge10 * 39u;                 // '0'.. or 'a'.. ('a' - '0' - 10 = 39)
+}
 S2B_HD uint32_t hex4(uint32_t x) {  // 4 nibbles (16 bits) -> 4 ASCII bytes, most significant nibble in the lowest byte
   uint32_t v = (x | (x << 8)) & 0x00FF00FFu;
   v = (v | (v << 4)) & 0x0F0F0F0Fu;                    // byte b = nibble b
+  v = (v >> 24) | ((v >> 8) & 0xFF00u) | ((v << 8) & 0xFF0000u) | (v << 24);   // reverse the bytes
+  return ascii_hex4(v);
+}
+// The 8 hex digits of a 32-bit word as two ASCII words (digits 7..4 and 3..0, most significant digit in the lowest
+// byte). On the device one byte permute places each source byte twice, in output order, and two logic ops split it into
+// nibbles: 9 instructions per word.
+S2B_HD void hex8(uint32_t x, uint32_t* hi4, uint32_t* lo4) {
 #if defined(__CUDA_ARCH__)
-  v = __byte_perm(v, 0, 0x0123);                       // reverse the bytes
+  const uint32_t th = __byte_perm(x, 0, 0x2233), tl = __byte_perm(x, 0, 0x0011);   // [B3 B3 B2 B2] / [B1 B1 B0 B0], low byte first
+  *hi4 = ascii_hex4(((th >> 4) & 0x000F000Fu) | (th & 0x0F000F00u));
+  *lo4 = ascii_hex4(((tl >> 4) & 0x000F000Fu) | (tl & 0x0F000F00u));
 #else
-  v = (v >> 24) | ((v >> 8) & 0xFF00u) | ((v << 8) & 0xFF0000u) | (v << 24);
+  *hi4 = hex4(x >> 16);
+  *lo4 = hex4(x & 0xFFFFu);
 #endif
-  uint32_t ge10 = ((v + 0x06060606u) >> 4) & 0x01010101u;
-  return v + 0x30303030u + ge10 * 39u;                 // '0'.. or 'a'.. ('a' - '0' - 10 = 39)
 }
 S2B_HD int ctz64(uint64_t v) {
 #if defined(__CUDA_ARCH__)
@@ -230,7 +242,9 @@ S2B_HD int cellid_to_token(uint64_t id, uint32_t out[4]) {
   if (id == 0) { out[0] = 0x58; out[1] = out[2] = out[3] = 0; return 1; }  // "X"
   const int len = 16 - (ctz64(id) >> 2);
   const uint32_t hi = (uint32_t)(id >> 32), lo = (uint32_t)id;
-  uint32_t w[4] = {hex4(hi >> 16), hex4(hi & 0xFFFFu), hex4(lo >> 16), hex4(lo & 0xFFFFu)};
+  uint32_t w[4];
+  hex8(hi, &w[0], &w[1]);
+  hex8(lo, &w[2], &w[3]);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif

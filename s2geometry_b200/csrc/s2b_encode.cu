@@ -38,34 +38,41 @@ static_assert(sc_tab::kTableSize == 105, "table rows are spelled out above");
 
 constexpr int kThreads = 256;
 
-// levels live in kernel parameter space; a switch keeps them out of local memory (dynamic indexing would copy them).
-__device__ __forceinline__ int level_at(const LevelSpec& l, int k) {
-  return k == 0 ? l.level[0] : (k == 1 ? l.level[1] : (k == 2 ? l.level[2] : l.level[3]));
-}
+// What one launch emits, with everything that is the same for all points worked out on the host: per-level output
+// bases and parent() masks (parent(level) = (id & -lsb) | lsb, s2cell_id.h:662-668; for level 30 the masks are ~0 and 1),
+// and for the token its length and the byte mask of the 16-byte slot — a level-L id has exactly (30 - L) / 2 trailing
+// zero hex digits (ToToken strips them, s2cell_id.cc:217-233), and encoded ids are never 0.
+struct EncodeArgs {
+  uint64_t* ids[4];
+  uint64_t and_mask[4], or_mask[4];
+  uint8_t* flags;          // nullable
+  uint4* tokens16;         // token slots (kToken kernels only)
+  uint8_t* token_len;      // nullable
+  uint64_t tok_and, tok_or;
+  uint32_t tok_keep[4];
+  uint32_t tok_len;
+  int force_cr;
+};
 
-// Epilogue shared by the encode kernels: parent() at each requested level and, optionally, one token — in the same
-// pass, so ids are never re-read.
-__device__ __forceinline__ void emit_ids_and_token(uint64_t id, size_t i, size_t n, const EncodeOut& o) {
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if (k < o.levels.n) {
-      // parent(level): (id & -lsb) | lsb; for level 30 lsb = 1 and the id (odd) is unchanged (s2cell_id.h:662-668)
-      const uint64_t lsb = lsb_for_level(level_at(o.levels, k));
-      __stcs(o.ids + (size_t)k * n + i, (id & (~lsb + 1)) | lsb);
-    }
-  }
-  if (o.token_level_index >= 0) {
-    int L = level_at(o.levels, o.token_level_index);
-    uint32_t w[4];
-    int len = cellid_to_token(L < 30 ? cellid_parent(id, L) : id, w);
-    __stcs((uint4*)o.tokens16 + i, make_uint4(w[0], w[1], w[2], w[3]));
-    if (o.token_len) o.token_len[i] = (uint8_t)len;
-  }
-}
+template <int kKind> struct RawPoint;
+template <> struct RawPoint<kInXYZ> { double x, y, z; };
+template <> struct RawPoint<kInLatLngRad> { double2 ll; };
+template <> struct RawPoint<kInLatLngE7> { int2 e7; };
 
-template <int kKind>
+__device__ __forceinline__ RawPoint<kInXYZ> load_raw(const void* in, uint32_t i, RawPoint<kInXYZ>*) {
+  const double* q = (const double*)in + 3 * (size_t)i;
+  return {__ldcs(q), __ldcs(q + 1), __ldcs(q + 2)};
+}
+__device__ __forceinline__ RawPoint<kInLatLngRad> load_raw(const void* in, uint32_t i, RawPoint<kInLatLngRad>*) { return {__ldcs((const double2*)in + i)}; }
+__device__ __forceinline__ RawPoint<kInLatLngE7> load_raw(const void* in, uint32_t i, RawPoint<kInLatLngE7>*) { return {__ldcs((const int2*)in + i)}; }
+
+// One thread per point, persistent grid. The input of the NEXT iteration is loaded before the current point is
+// processed, so no warp ever waits for DRAM with nothing to do (without it 29 % of the issue slots were empty and the
+// top stall was the long scoreboard on the input load: profiles/r1_encode_latlng_final_ncu.json).
+// n < 2^32 per launch (the launcher splits larger batches), so indices are 32-bit and every address is one IMAD.WIDE.
+template <int kKind, int kLevels, bool kToken>
 __global__ void __launch_bounds__(kThreads, 6)
-encode_kernel(const void* __restrict__ in, size_t n, const EncodeOut o) {
+encode_kernel(const void* __restrict__ in, uint32_t n, const EncodeArgs a) {
   __shared__ uint16_t s_pos[16384];   // 6-bit Hilbert table: 5 dependent lookups per point
   __shared__ double s_sc[kKind == kInXYZ ? 1 : sc_tab::kTableSize][4];
   for (int k = threadIdx.x; k < 16384 / 8; k += kThreads) ((uint4*)s_pos)[k] = ((const uint4*)g_hilbert_wide)[k];
@@ -76,35 +83,51 @@ encode_kernel(const void* __restrict__ in, size_t n, const EncodeOut o) {
 
   // Warp-uniform trip count + __syncwarp() at the end of every iteration: lanes that took a rare path (double-double
   // sin/cos, division/sqrt slow paths) rejoin their warp instead of running the rest of the loop on their own.
-  const size_t stride = (size_t)gridDim.x * kThreads;
-  const unsigned lane = threadIdx.x & 31u;
-  for (size_t base = (size_t)blockIdx.x * kThreads + (threadIdx.x & ~31u); base < n; base += stride, __syncwarp()) {
-    const size_t i = base + lane;
-    if (i >= n) continue;
-    P3 p;
-    double fi, fj;
-    int face;
-    bool sensitive = false;
-    if (kKind == kInXYZ) {
-      const double* q = (const double*)in + 3 * i;
-      p.x = __ldcs(q); p.y = __ldcs(q + 1); p.z = __ldcs(q + 2);
-    } else {
-      double lat, lng;
-      if (kKind == kInLatLngRad) {
-        double2 ll = __ldcs((const double2*)in + i);
-        lat = ll.x; lng = ll.y;
+  using Raw = RawPoint<kKind>;
+  const uint32_t stride = gridDim.x * kThreads;
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+  Raw cur{};
+  if (i < n) cur = load_raw(in, i, (Raw*)nullptr);
+  while (i - lane < n) {
+    const uint32_t i_next = i + stride;    // n <= 2^31 and stride < 2^20: no wrap-around
+    Raw nxt{};
+    if (i_next < n) nxt = load_raw(in, i_next, (Raw*)nullptr);
+    if (i < n) {
+      P3 p;
+      double fi, fj;
+      int face;
+      bool sensitive = false;
+      if constexpr (kKind == kInXYZ) {
+        p = P3{cur.x, cur.y, cur.z};
+        face = point_to_face_fij(p, &fi, &fj);
       } else {
-        int2 e7 = __ldcs((const int2*)in + i);
-        // S1Angle::E7 = Degrees(1e-7 * e7) = (M_PI / 180) * (1e-7 * e7)   (s1angle.h:363-377)
-        lat = (M_PI / 180) * (1e-7 * (double)e7.x);
-        lng = (M_PI / 180) * (1e-7 * (double)e7.y);
+        double lat, lng;
+        if constexpr (kKind == kInLatLngRad) {
+          lat = cur.ll.x; lng = cur.ll.y;
+        } else {
+          // S1Angle::E7 = Degrees(1e-7 * e7) = (M_PI / 180) * (1e-7 * e7)   (s1angle.h:363-377)
+          lat = (M_PI / 180) * (1e-7 * (double)cur.e7.x);
+          lng = (M_PI / 180) * (1e-7 * (double)cur.e7.y);
+        }
+        face = latlng_to_face_fij(lat, lng, s_sc, a.force_cr != 0, &p, &fi, &fj, &sensitive);
       }
-      face = latlng_to_face_fij(lat, lng, s_sc, o.force_cr != 0, &p, &fi, &fj, &sensitive);
+      const uint64_t id = from_face_ij_wide(face, fij_to_ij(fi), fij_to_ij(fj), s_pos);
+#pragma unroll
+      for (int k = 0; k < kLevels; ++k) __stcs(a.ids[k] + i, (id & a.and_mask[k]) | a.or_mask[k]);
+      if constexpr (kToken) {
+        const uint64_t tid = (id & a.tok_and) | a.tok_or;
+        uint32_t w[4];
+        hex8((uint32_t)(tid >> 32), &w[0], &w[1]);
+        hex8((uint32_t)tid, &w[2], &w[3]);
+        __stcs(a.tokens16 + i, make_uint4(w[0] & a.tok_keep[0], w[1] & a.tok_keep[1], w[2] & a.tok_keep[2], w[3] & a.tok_keep[3]));
+        if (a.token_len) a.token_len[i] = (uint8_t)a.tok_len;
+      }
+      if (a.flags) a.flags[i] = (kKind == kInXYZ || sensitive) && near_cell_boundary(fi, fj, kFlagTolIj) ? 1 : 0;
     }
-    if (kKind == kInXYZ) face = point_to_face_fij(p, &fi, &fj);
-    const uint64_t id = from_face_ij_wide(face, fij_to_ij(fi), fij_to_ij(fj), s_pos);
-    emit_ids_and_token(id, i, n, o);
-    if (o.flags) o.flags[i] = (kKind == kInXYZ || sensitive) && near_cell_boundary(fi, fj, kFlagTolIj) ? 1 : 0;
+    cur = nxt;
+    i = i_next;
+    __syncwarp();
   }
 }
 
@@ -117,23 +140,101 @@ static int grid_for(size_t n, const void* kernel) {
   return (int)(want < cap ? (want ? want : 1) : cap);
 }
 
-template <int kKind>
-static cudaError_t launch_encode_k(const void* in, size_t n, const EncodeOut& o, cudaStream_t st) {
-  auto kern = encode_kernel<kKind>;
-  kern<<<grid_for(n, (const void*)kern), kThreads, 0, st>>>(in, n, o);
+template <int kKind, int kLevels, bool kToken>
+static cudaError_t launch_encode_k(const void* in, uint32_t n, const EncodeArgs& a, cudaStream_t st) {
+  auto kern = encode_kernel<kKind, kLevels, kToken>;
+  kern<<<grid_for(n, (const void*)kern), kThreads, 0, st>>>(in, n, a);
   count_launch();
   return cudaGetLastError();
 }
 
+template <int kKind>
+static cudaError_t launch_encode_kind(const void* in, uint32_t n, int levels, bool token, const EncodeArgs& a, cudaStream_t st) {
+  switch (levels * 2 + (token ? 1 : 0)) {
+    case 2: return launch_encode_k<kKind, 1, false>(in, n, a, st);
+    case 3: return launch_encode_k<kKind, 1, true>(in, n, a, st);
+    case 4: return launch_encode_k<kKind, 2, false>(in, n, a, st);
+    case 5: return launch_encode_k<kKind, 2, true>(in, n, a, st);
+    case 6: return launch_encode_k<kKind, 3, false>(in, n, a, st);
+    case 7: return launch_encode_k<kKind, 3, true>(in, n, a, st);
+    case 8: return launch_encode_k<kKind, 4, false>(in, n, a, st);
+    case 9: return launch_encode_k<kKind, 4, true>(in, n, a, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 cudaError_t launch_encode(InputKind kind, const void* in, size_t n, const EncodeOut& o, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
+  if (o.levels.n < 1 || o.levels.n > 4) return cudaErrorInvalidValue;
   cudaError_t te = ensure_wide_table();
   if (te != cudaSuccess) return te;
-  switch (kind) {
-    case kInXYZ: return launch_encode_k<kInXYZ>(in, n, o, st);
-    case kInLatLngRad: return launch_encode_k<kInLatLngRad>(in, n, o, st);
-    default: return launch_encode_k<kInLatLngE7>(in, n, o, st);
+  const bool token = o.token_level_index >= 0;
+  const size_t in_stride = kind == kInXYZ ? 24 : (kind == kInLatLngRad ? 16 : 8);
+  constexpr size_t kMaxLaunchPoints = (size_t)1 << 31;
+  for (size_t off = 0; off < n; off += kMaxLaunchPoints) {
+    const uint32_t cnt = (uint32_t)(n - off < kMaxLaunchPoints ? n - off : kMaxLaunchPoints);
+    EncodeArgs a{};
+    for (int k = 0; k < o.levels.n; ++k) {
+      const uint64_t lsb = lsb_for_level(o.levels.level[k]);
+      a.ids[k] = o.ids + (size_t)k * n + off;
+      a.and_mask[k] = ~lsb + 1;
+      a.or_mask[k] = lsb;
+    }
+    a.flags = o.flags ? o.flags + off : nullptr;
+    a.force_cr = o.force_cr;
+    if (token) {
+      const int L = o.levels.level[o.token_level_index];
+      const uint64_t lsb = lsb_for_level(L);
+      a.tok_and = ~lsb + 1;
+      a.tok_or = lsb;
+      a.tok_len = 16u - (uint32_t)((30 - L) >> 1);
+      for (int k = 0; k < 4; ++k) {
+        const int keep = (int)a.tok_len - 4 * k;
+        a.tok_keep[k] = keep >= 4 ? 0xFFFFFFFFu : (keep <= 0 ? 0u : (1u << (8 * keep)) - 1u);
+      }
+      a.tokens16 = (uint4*)o.tokens16 + off;
+      a.token_len = o.token_len ? o.token_len + off : nullptr;
+    }
+    const void* src = (const char*)in + off * in_stride;
+    cudaError_t e;
+    switch (kind) {
+      case kInXYZ: e = launch_encode_kind<kInXYZ>(src, cnt, o.levels.n, token, a, st); break;
+      case kInLatLngRad: e = launch_encode_kind<kInLatLngRad>(src, cnt, o.levels.n, token, a, st); break;
+      default: e = launch_encode_kind<kInLatLngE7>(src, cnt, o.levels.n, token, a, st); break;
+    }
+    if (e != cudaSuccess) return e;
   }
+  return cudaSuccess;
+}
+
+// Diagnostics (s2b_diag_filter_deviation_dev): how far the filter path's (fi, fj) are from the correctly rounded path's,
+// in leaf cells — the quantity kFilterTolIj must dominate. Points whose two paths disagree on the face are counted
+// separately; they must all be ones the filter sends to the correctly rounded path anyway (count in out[1] otherwise).
+__global__ void __launch_bounds__(kThreads) filter_deviation_kernel(const double2* __restrict__ ll, size_t n, unsigned long long* __restrict__ out) {
+  double worst = 0.0;
+  unsigned long long unflagged_face_flips = 0;
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    const double2 a = ll[i];
+    if (!(fabs(a.x) < 1048576.0 && fabs(a.y) < 1048576.0)) continue;
+    double fi0, fj0, fi1, fj1;
+    const int f0 = point_to_face_fij_filter(latlng_to_point_fast(a.x, a.y), &fi0, &fj0);
+    const int f1 = point_to_face_fij(latlng_to_point(a.x, a.y, g_sincos_tab), &fi1, &fj1);
+    if (f0 != f1) {
+      if (!near_cell_boundary(fi0, fj0, kFilterTolIj)) ++unflagged_face_flips;
+      continue;
+    }
+    worst = fmax(worst, fmax(fabs(fi0 - fi1), fabs(fj0 - fj1)));
+  }
+  atomicMax(out, (unsigned long long)__double_as_longlong(worst));   // non-negative doubles order like their bit patterns
+  if (unflagged_face_flips) atomicAdd(out + 1, unflagged_face_flips);
+}
+
+cudaError_t launch_filter_deviation(const double* ll, size_t n, unsigned long long* out2_dev, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  filter_deviation_kernel<<<grid_for(n, (const void*)filter_deviation_kernel), kThreads, 0, st>>>((const double2*)ll, n, out2_dev);
+  count_launch();
+  return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------------

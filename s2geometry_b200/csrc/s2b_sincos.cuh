@@ -211,6 +211,15 @@ static constexpr double kFastCoefHost[18] = S2B_FAST_COEFS;
 #define S2B_FC(i) kFastCoefHost[i]
 #endif
 
+// -x or x: an integer XOR on the sign bit (the FP64 negate-and-select sequence costs a DADD and two FSELs).
+S2B_HD double flip_sign_if(double x, bool flip) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(__double2hiint(x) ^ (flip ? (int)0x80000000 : 0), __double2loint(x));
+#else
+  return flip ? -x : x;
+#endif
+}
+
 // This routine is a filter, not part of the bit-exact path, so fused multiply-adds are used freely.
 S2B_HD SinCos sincos_fast(double x) {  // requires |x| < 2^20
   double kd = rint(x * S2B_FC(14));
@@ -236,8 +245,8 @@ S2B_HD SinCos sincos_fast(double x) {  // requires |x| < 2^20
   // quadrant: swap for odd k, negate sin for k = 2,3 (mod 4), cos for k = 1,2
   double s0 = (q & 1) ? cr : sr, c0 = (q & 1) ? sr : cr;
   SinCos out;
-  out.s = (q & 2) ? -s0 : s0;
-  out.c = ((q + 1) & 2) ? -c0 : c0;
+  out.s = flip_sign_if(s0, (q & 2) != 0);
+  out.c = flip_sign_if(c0, ((q + 1) & 2) != 0);
   return out;
 }
 
@@ -245,6 +254,50 @@ S2B_HD P3 latlng_to_point_fast(double lat, double lng) {
   SinCos phi = sincos_fast(lat);
   SinCos theta = sincos_fast(lng);
   return P3{theta.c * phi.c, theta.s * phi.c, phi.s};
+}
+
+// Reciprocal and reciprocal square root for the filter path: hardware seed (MUFU.RCP64H / RSQ64H, ~2^-20 relative) and
+// one third-order step, relative error < 2^-57 before the final rounding. No special-case handling: callers pass normal,
+// finite arguments of moderate magnitude (the major axis of a unit vector; 1 + 3|u| in [1, 4]).
+S2B_HD double rcp_filter(double m) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(m));
+  const double e = fma(-m, r, 1.0);
+  return fma(r, fma(e, e, e), r);
+#else
+  return 1.0 / m;
+#endif
+}
+S2B_HD double rsqrt_filter(double x) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x * y, y, 1.0);
+  return fma(fma(e, 0.375, 0.5), y * e, y);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+
+// point_to_face_fij for the filter path: same face selection, but u, v, s, t are computed with the approximations above
+// and fused multiply-adds (one shared reciprocal, no IEEE division / square root sequences): 2^30 * s is off by at most
+// ~5e-7 leaf cells more than with the IEEE operations (u: <= 2 ulp instead of 0.5; sqrt: <= 2 ulp), see the budget below.
+S2B_HD int point_to_face_fij_filter(const P3& p, double* fi, double* fj) {
+  const double ax = fabs(p.x), ay = fabs(p.y), az = fabs(p.z);
+  const int axis = ax > ay ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
+  const double m = axis == 0 ? p.x : (axis == 1 ? p.y : p.z);
+  const bool neg = m < 0;
+  const double a = axis == 0 ? p.y : -p.x;
+  const double b = axis == 2 ? -p.y : p.z;
+  const double r = rcp_filter(m);
+  const double u = (neg ? b : a) * r, v = (neg ? a : b) * r;
+  // 2^30 * s = u >= 0 ? 2^29 * sqrt(w) : 2^30 - 2^29 * sqrt(w),  w = 1 + 3|u|,  sqrt(w) = w * rsqrt(w)
+  const double wu = fma(3.0, fabs(u), 1.0), wv = fma(3.0, fabs(v), 1.0);
+  const double su = wu * rsqrt_filter(wu), sv = wv * rsqrt_filter(wv);
+  *fi = u >= 0 ? 536870912.0 * su : fma(-536870912.0, su, 1073741824.0);
+  *fj = v >= 0 ? 536870912.0 * sv : fma(-536870912.0, sv, 1073741824.0);
+  return axis + (neg ? 3 : 0);
 }
 
 // S2LatLng::ToPoint (s2latlng.cc:68-77): (cos(lng)*cos(lat), sin(lng)*cos(lat), sin(lat)).
@@ -258,13 +311,15 @@ S2B_HD P3 latlng_to_point(double lat, double lng, const double (*tab)[4], int* n
 // correctly rounded sin/cos). With |error| <= e in each of the four sin/cos values: x,y are off by <= 2e + 1.2e-16,
 // z by <= e; u,v by <= (3e + 2.4e-16)/0.577 + 1.2e-16 (the major axis is >= 1/sqrt(3)); s,t by <= 0.75 of that + 2e-16;
 // i.e. in units of leaf cells (x 2^30):  e = 4.5e-16 (fast sin/cos) -> 3.1e-6 ;  e = 1.1e-16 (1 ulp) -> 1.1e-6.
+// The filter path's approximate reciprocal / square root (point_to_face_fij_filter) add <= 3.3e-16 to u,v and
+// <= 2.2e-16 to s,t: + 5e-7 leaf cells, 3.6e-6 in total (measured maximum on the GPU: tests/test_encode_gpu.py).
 S2B_HD bool near_cell_boundary(double fi, double fj, double tol_ij) {
   // A face flip needs two |components| to (nearly) tie, i.e. |u| or |v| within ~1e-14 of 1 on the chosen face, i.e.
   // fi or fj within ~4e-6 of 0 or 2^30: already covered by the distance-to-integer test below (tolerances >= 4e-6).
-  double di = fi - floor(fi), dj = fj - floor(fj);
-  return !(di > tol_ij && di < 1 - tol_ij && dj > tol_ij && dj < 1 - tol_ij);   // NaN -> true
+  const double di = fabs(fi - rint(fi)), dj = fabs(fj - rint(fj));
+  return !(di > tol_ij && dj > tol_ij);   // NaN -> true
 }
-static constexpr double kFilterTolIj = 1.6e-5;   // fast-path filter: 5x the 3.1e-6 bound
+static constexpr double kFilterTolIj = 1.6e-5;   // fast-path filter: 4.4x the 3.6e-6 bound
 static constexpr double kFlagTolIj = 4e-6;      // user-visible flag: 1-ulp sin/cos changes, 3.5x margin
 
 // lat/lng -> (face, fi, fj) with the filter described above. *sensitive reports whether the correctly rounded path ran.
@@ -274,7 +329,7 @@ S2B_HD int latlng_to_face_fij(double lat, double lng, const double (*tab)[4], bo
   bool sens = !(fabs(lat) < 1048576.0 && fabs(lng) < 1048576.0) || force_cr;
   if (!sens) {
     *p = latlng_to_point_fast(lat, lng);
-    face = point_to_face_fij(*p, fi, fj);
+    face = point_to_face_fij_filter(*p, fi, fj);
     sens = near_cell_boundary(*fi, *fj, kFilterTolIj);
   }
   if (sens) {

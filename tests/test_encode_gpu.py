@@ -158,6 +158,30 @@ def test_fast_filter_equals_correctly_rounded_on_device(torch_cuda, ref):
     assert (flags_b.cpu().numpy()[bad] == 1).all()
 
 
+def test_filter_deviation_is_far_below_the_filter_tolerance(torch_cuda, ref):
+    """The filter path (fast sin/cos, approximate reciprocal / square root) must stay within a fraction of kFilterTolIj
+    (1.6e-5 leaf cells) of the correctly rounded path, and never pick another face unnoticed: 200M uniform points, points
+    on cell boundaries, tiny and huge (but in-domain) angles."""
+    import ctypes
+    torch = torch_cuda
+    from s2geometry_b200 import _lib, synth
+    from tests.test_encode_cpu import boundary_latlngs
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    special = np.concatenate([boundary_latlngs(ref, 20000, 11),
+                              np.stack([rng.uniform(-1.6, 1.6, 200000), rng.uniform(-3.2, 3.2, 200000)], 1),
+                              np.stack([10.0 ** rng.uniform(-300, 0, 100000), 10.0 ** rng.uniform(-300, 0, 100000)], 1),
+                              rng.uniform(-1e6, 1e6, (100000, 2))])
+    worst = 0.0
+    for ll in (synth.sphere_latlng_cuda(200_000_000, 9, "cuda"), torch.from_numpy(np.ascontiguousarray(special)).cuda()):
+        dev, flips = ctypes.c_double(0), ctypes.c_uint64(0)
+        rc = lib.s2b_diag_filter_deviation_dev(ll.data_ptr(), ll.shape[0], ctypes.byref(dev), ctypes.byref(flips), None)
+        assert rc == 0 and flips.value == 0
+        worst = max(worst, dev.value)
+    print("max filter deviation [leaf cells]:", worst)
+    assert worst < 4e-6, worst          # kFilterTolIj / 4
+
+
 def test_to_point_and_from_token(torch_cuda, ref):
     """Batched inverses (SURVEY.md §8f rank 2): S2CellId::ToPoint bit-exact, FromToken, token round trip."""
     torch = torch_cuda
