@@ -54,11 +54,13 @@ int s2b_diag_fp64_peak(double* dfma_per_second_out);
  * point take the correctly rounded routine, which must give identical ids (tests check it). Returns the old setting. */
 int s2b_diag_force_correctly_rounded(int on);
 
-/* Diagnostic: the largest distance (in leaf cells, over the n device-resident lat/lng pairs) between the (i, j)
- * coordinates computed by the filter path and by the correctly rounded path — the quantity the filter tolerance must
- * dominate — and the number of points whose two paths pick different faces without the filter noticing
- * (must be 0). Synchronises the stream. */
-int s2b_diag_filter_deviation_dev(const double* latlng_dev, size_t n, double* max_deviation_out,
+/* Diagnostic: the encoders first evaluate (face, i, j) with bounded-error arithmetic and repeat the evaluation with the
+ * exact sequence (IEEE division / square root; for lat/lng also correctly rounded sin/cos) only where the leaf cell
+ * could depend on the difference. This call measures what that rests on: the largest distance, in leaf
+ * cells, between the two evaluations over n device-resident inputs (input_kind 0: xyz triples, 1: lat/lng radian
+ * pairs), and the number of points for which they pick different faces without the filter noticing (must be 0).
+ * Synchronises the stream. */
+int s2b_diag_filter_deviation_dev(int input_kind, const double* in_dev, size_t n, double* max_deviation_out,
                                   uint64_t* unflagged_face_flips_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

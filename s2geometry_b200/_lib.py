@@ -20,7 +20,7 @@ SIGNATURES = {
     "s2b_launch_count": (_u64, []),
     "s2b_diag_fp64_peak": (_i, [_vp]),
     "s2b_diag_force_correctly_rounded": (_i, [_i]),
-    "s2b_diag_filter_deviation_dev": (_i, [_vp, _sz, _vp, _vp, _vp]),
+    "s2b_diag_filter_deviation_dev": (_i, [_i, _vp, _sz, _vp, _vp, _vp]),
     "s2b_encode_points": (_i, [_vp, _sz, _i, _vp]),
     "s2b_encode_points_dev": (_i, [_vp, _sz, _i, _vp, _vp]),
     "s2b_encode_latlng": (_i, [_vp, _sz, _i, _vp, _vp]),

@@ -239,14 +239,15 @@ int s2b_device_count(void) {
 uint64_t s2b_launch_count(void) { return g_launches.load(); }
 int s2b_diag_force_correctly_rounded(int on) { return g_force_cr.exchange(on ? 1 : 0); }
 
-int s2b_diag_filter_deviation_dev(const double* latlng_dev, size_t n, double* max_deviation_out, uint64_t* unflagged_face_flips_out, void* stream) {
-  if (!max_deviation_out || !unflagged_face_flips_out || (n && !latlng_dev)) return set_error(S2B_EINVAL, "null argument");
+int s2b_diag_filter_deviation_dev(int input_kind, const double* in_dev, size_t n, double* max_deviation_out, uint64_t* unflagged_face_flips_out, void* stream) {
+  if (!max_deviation_out || !unflagged_face_flips_out || (n && !in_dev)) return set_error(S2B_EINVAL, "null argument");
+  if (input_kind != 0 && input_kind != 1) return set_error(S2B_EINVAL, "input_kind must be 0 (xyz) or 1 (lat/lng radians)");
   cudaStream_t st = (cudaStream_t)stream;
   unsigned long long* d = nullptr;
   cudaError_t e = cudaMallocAsync((void**)&d, 16, st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync");
   e = cudaMemsetAsync(d, 0, 16, st);
-  if (e == cudaSuccess) e = launch_filter_deviation(latlng_dev, n, d, st);
+  if (e == cudaSuccess) e = launch_filter_deviation(input_kind == 0 ? kInXYZ : kInLatLngRad, in_dev, n, d, st);
   unsigned long long h[2] = {0, 0};
   if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);

@@ -37,6 +37,9 @@ __device__ const double g_sincos_tab[sc_tab::kTableSize][4] = {
 static_assert(sc_tab::kTableSize == 105, "table rows are spelled out above");
 
 constexpr int kThreads = 256;
+// Resident CTAs per SM of the encode kernels. With the input prefetch 5 x 8 warps (48 registers, no spills) measured
+// 81 Gpts/s on the fused lat/lng step, 6 (40 registers, two spilled values) 79, 4 (64 registers) 81.
+constexpr int kEncodeCtas = 5;
 
 // What one launch emits, with everything that is the same for all points worked out on the host: per-level output
 // bases and parent() masks (parent(level) = (id & -lsb) | lsb, s2cell_id.h:662-668; for level 30 the masks are ~0 and 1),
@@ -67,11 +70,12 @@ __device__ __forceinline__ RawPoint<kInLatLngRad> load_raw(const void* in, uint3
 __device__ __forceinline__ RawPoint<kInLatLngE7> load_raw(const void* in, uint32_t i, RawPoint<kInLatLngE7>*) { return {__ldcs((const int2*)in + i)}; }
 
 // One thread per point, persistent grid. The input of the NEXT iteration is loaded before the current point is
-// processed, so no warp ever waits for DRAM with nothing to do (without it 29 % of the issue slots were empty and the
-// top stall was the long scoreboard on the input load: profiles/r1_encode_latlng_final_ncu.json).
+// processed, so a warp does not sit on the long scoreboard at the top of every iteration.
+// (Handing out work dynamically — 256-point chunks per warp from a global cursor — was measured and made no
+// difference: 80.6 vs 81.2 Gpts/s. The kernel is bound by instruction issue: 316 instructions per point, 0.71 IPC.)
 // n < 2^32 per launch (the launcher splits larger batches), so indices are 32-bit and every address is one IMAD.WIDE.
 template <int kKind, int kLevels, bool kToken>
-__global__ void __launch_bounds__(kThreads, 6)
+__global__ void __launch_bounds__(kThreads, kEncodeCtas)
 encode_kernel(const void* __restrict__ in, uint32_t n, const EncodeArgs a) {
   __shared__ uint16_t s_pos[16384];   // 6-bit Hilbert table: 5 dependent lookups per point
   __shared__ double s_sc[kKind == kInXYZ ? 1 : sc_tab::kTableSize][4];
@@ -100,7 +104,7 @@ encode_kernel(const void* __restrict__ in, uint32_t n, const EncodeArgs a) {
       bool sensitive = false;
       if constexpr (kKind == kInXYZ) {
         p = P3{cur.x, cur.y, cur.z};
-        face = point_to_face_fij(p, &fi, &fj);
+        face = a.force_cr ? point_to_face_fij(p, &fi, &fj) : point_to_face_fij_checked(p, &fi, &fj);
       } else {
         double lat, lng;
         if constexpr (kKind == kInLatLngRad) {
@@ -210,16 +214,26 @@ cudaError_t launch_encode(InputKind kind, const void* in, size_t n, const Encode
 // Diagnostics (s2b_diag_filter_deviation_dev): how far the filter path's (fi, fj) are from the correctly rounded path's,
 // in leaf cells — the quantity kFilterTolIj must dominate. Points whose two paths disagree on the face are counted
 // separately; they must all be ones the filter sends to the correctly rounded path anyway (count in out[1] otherwise).
-__global__ void __launch_bounds__(kThreads) filter_deviation_kernel(const double2* __restrict__ ll, size_t n, unsigned long long* __restrict__ out) {
+template <int kKind>
+__global__ void __launch_bounds__(kThreads) filter_deviation_kernel(const double* __restrict__ in, size_t n, unsigned long long* __restrict__ out) {
   double worst = 0.0;
   unsigned long long unflagged_face_flips = 0;
   const size_t stride = (size_t)gridDim.x * kThreads;
   for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
-    const double2 a = ll[i];
-    if (!(fabs(a.x) < 1048576.0 && fabs(a.y) < 1048576.0)) continue;
     double fi0, fj0, fi1, fj1;
-    const int f0 = point_to_face_fij_filter(latlng_to_point_fast(a.x, a.y), &fi0, &fj0);
-    const int f1 = point_to_face_fij(latlng_to_point(a.x, a.y, g_sincos_tab), &fi1, &fj1);
+    int f0, f1;
+    if (kKind == kInXYZ) {
+      const P3 p{in[3 * i], in[3 * i + 1], in[3 * i + 2]};
+      const double m = fmax(fmax(fabs(p.x), fabs(p.y)), fabs(p.z));
+      if (!(m > 3.0549363634996047e-151 && m < 3.2733906078961419e+150)) continue;
+      f0 = point_to_face_fij_filter(p, &fi0, &fj0);
+      f1 = point_to_face_fij(p, &fi1, &fj1);
+    } else {
+      const double lat = in[2 * i], lng = in[2 * i + 1];
+      if (!(fabs(lat) < 1048576.0 && fabs(lng) < 1048576.0)) continue;
+      f0 = point_to_face_fij_filter(latlng_to_point_fast(lat, lng), &fi0, &fj0);
+      f1 = point_to_face_fij(latlng_to_point(lat, lng, g_sincos_tab), &fi1, &fj1);
+    }
     if (f0 != f1) {
       if (!near_cell_boundary(fi0, fj0, kFilterTolIj)) ++unflagged_face_flips;
       continue;
@@ -230,9 +244,10 @@ __global__ void __launch_bounds__(kThreads) filter_deviation_kernel(const double
   if (unflagged_face_flips) atomicAdd(out + 1, unflagged_face_flips);
 }
 
-cudaError_t launch_filter_deviation(const double* ll, size_t n, unsigned long long* out2_dev, cudaStream_t st) {
+cudaError_t launch_filter_deviation(InputKind kind, const double* in, size_t n, unsigned long long* out2_dev, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
-  filter_deviation_kernel<<<grid_for(n, (const void*)filter_deviation_kernel), kThreads, 0, st>>>((const double2*)ll, n, out2_dev);
+  if (kind == kInXYZ) filter_deviation_kernel<kInXYZ><<<grid_for(n, (const void*)filter_deviation_kernel<kInXYZ>), kThreads, 0, st>>>(in, n, out2_dev);
+  else filter_deviation_kernel<kInLatLngRad><<<grid_for(n, (const void*)filter_deviation_kernel<kInLatLngRad>), kThreads, 0, st>>>(in, n, out2_dev);
   count_launch();
   return cudaGetLastError();
 }

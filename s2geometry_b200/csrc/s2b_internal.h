@@ -25,7 +25,7 @@ enum InputKind { kInXYZ = 0, kInLatLngRad = 1, kInLatLngE7 = 2 };
 // Kernel launchers (device pointers, enqueue only). Return cudaGetLastError() of the launch.
 cudaError_t launch_encode(InputKind kind, const void* in_dev, size_t n, const EncodeOut& out, cudaStream_t stream);
 cudaError_t launch_parent(const uint64_t* ids_dev, size_t n, int level, uint64_t* out_dev, cudaStream_t stream);
-cudaError_t launch_filter_deviation(const double* latlng_dev, size_t n, unsigned long long* out2_dev, cudaStream_t stream);
+cudaError_t launch_filter_deviation(InputKind kind, const double* in_dev, size_t n, unsigned long long* out2_dev, cudaStream_t stream);
 cudaError_t launch_edge_neighbors(const uint64_t* ids_dev, size_t n, uint64_t* out4_dev, cudaStream_t stream);
 cudaError_t launch_to_point(const uint64_t* ids_dev, size_t n, double* xyz_dev, cudaStream_t stream);
 cudaError_t launch_from_token(const char* tokens16_dev, const uint8_t* len_dev, size_t n, uint64_t* ids_dev, cudaStream_t stream);

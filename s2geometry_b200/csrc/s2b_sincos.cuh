@@ -190,7 +190,8 @@ S2B_HD SinCos sincos_cr(double x, const double (*tab)[4], int* n_slow = nullptr)
 // are re-evaluated with sincos_cr (s2b_encode.cu). So the ids are those of the correctly rounded definition, at a
 // third of the FP64 work.
 //   reduction: x - k*pi/2 with three Cody-Waite parts in plain double (error <= 0.5 ulp(r) + k*2^-120)
-//   sin(r), cos(r): Taylor through r^15 / r^16 on |r| <= pi/4 (truncation < 5e-17), Horner in r^2
+//   sin(r), cos(r): degree-13 / degree-14 minimax polynomials on |r| <= pi/4 (the classic fdlibm kernel coefficients,
+//   approximation error < 2^-58), Horner in r^2
 // Absolute error bound assumed by the encoder: kFastSinCosAbsErr = 4.5e-16 (about twice the measured maximum,
 // tests/test_encode_cpu.py::test_fast_sincos_error_bound).
 static constexpr double kFastSinCosAbsErr = 4.5e-16;
@@ -198,13 +199,15 @@ static constexpr double kFastSinCosAbsErr = 4.5e-16;
 // Coefficients live in constant memory on the device so that DFMA reads them as c[bank][offset] operands; as
 // immediates each would cost two IMAD.MOV per use (measured: 175 IMAD/point before, see profiles/).
 #define S2B_FAST_COEFS { \
-  -1.0 / 6.0, 1.0 / 120.0, -1.0 / 5040.0, 1.0 / 362880.0, -1.0 / 39916800.0, 1.0 / 6227020800.0, -1.0 / 1307674368000.0, \
-  1.0 / 24.0, -1.0 / 720.0, 1.0 / 40320.0, -1.0 / 3628800.0, 1.0 / 479001600.0, -1.0 / 87178291200.0, 1.0 / 20922789888000.0, \
+  -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04, 2.75573137070700676789e-06, \
+  -2.50507602534068634195e-08, 1.58969099521155010221e-10, \
+  4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05, -2.75573143513906633035e-07, \
+  2.08757232129817482790e-09, -1.13596475577881948265e-11, \
   sc_tab::kTwoOverPi, -sc_tab::kPio2_1, -sc_tab::kPio2_2, -sc_tab::kPio2_3 }
 #if defined(__CUDACC__)
-__constant__ double c_fast_coef[18] = S2B_FAST_COEFS;
+__constant__ double c_fast_coef[16] = S2B_FAST_COEFS;
 #endif
-static constexpr double kFastCoefHost[18] = S2B_FAST_COEFS;
+static constexpr double kFastCoefHost[16] = S2B_FAST_COEFS;
 #if defined(__CUDA_ARCH__)
 #define S2B_FC(i) c_fast_coef[i]
 #else
@@ -222,24 +225,22 @@ S2B_HD double flip_sign_if(double x, bool flip) {
 
 // This routine is a filter, not part of the bit-exact path, so fused multiply-adds are used freely.
 S2B_HD SinCos sincos_fast(double x) {  // requires |x| < 2^20
-  double kd = rint(x * S2B_FC(14));
-  double r = fma(kd, S2B_FC(17), fma(kd, S2B_FC(16), fma(kd, S2B_FC(15), x)));
+  double kd = rint(x * S2B_FC(12));
+  double r = fma(kd, S2B_FC(15), fma(kd, S2B_FC(14), fma(kd, S2B_FC(13), x)));
   double z = r * r;
-  double ps = S2B_FC(6);
-  ps = fma(ps, z, S2B_FC(5));
+  double ps = S2B_FC(5);
   ps = fma(ps, z, S2B_FC(4));
   ps = fma(ps, z, S2B_FC(3));
   ps = fma(ps, z, S2B_FC(2));
   ps = fma(ps, z, S2B_FC(1));
   ps = fma(ps, z, S2B_FC(0));
   double sr = fma(r * z, ps, r);
-  double pc = S2B_FC(13);
-  pc = fma(pc, z, S2B_FC(12));
-  pc = fma(pc, z, S2B_FC(11));
+  double pc = S2B_FC(11);
   pc = fma(pc, z, S2B_FC(10));
   pc = fma(pc, z, S2B_FC(9));
   pc = fma(pc, z, S2B_FC(8));
   pc = fma(pc, z, S2B_FC(7));
+  pc = fma(pc, z, S2B_FC(6));
   double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
   int q = (int)kd;
   // quadrant: swap for odd k, negate sin for k = 2,3 (mod 4), cos for k = 1,2
@@ -337,6 +338,20 @@ S2B_HD int latlng_to_face_fij(double lat, double lng, const double (*tab)[4], bo
     face = point_to_face_fij(*p, fi, fj);
   }
   *sensitive = sens;
+  return face;
+}
+
+// S2Point -> (face, fi, fj) with the same idea applied to the IEEE division / square root sequences of
+// point_to_face_fij: the approximate version is exact about the face (same comparisons) and within a few ulps of
+// 2^30 (7e-7 leaf cells; measured maximum in tests/test_encode_gpu.py) in fi and fj, so unless fi or fj is within
+// kXyzFilterTolIj of an integer the leaf cell — floor(fi), floor(fj) — is the one the IEEE sequence gives. Points that
+// are closer (about 3e-5 of all points), non-finite input and major axes outside [2^-500, 2^500] take the IEEE path.
+static constexpr double kXyzFilterTolIj = 8e-6;   // > kFlagTolIj, so boundary flags are always computed from IEEE values
+S2B_HD int point_to_face_fij_checked(const P3& p, double* fi, double* fj) {
+  int face = point_to_face_fij_filter(p, fi, fj);
+  const double m = fmax(fmax(fabs(p.x), fabs(p.y)), fabs(p.z));
+  const bool trust = m > 3.0549363634996047e-151 && m < 3.2733906078961419e+150 && !near_cell_boundary(*fi, *fj, kXyzFilterTolIj);
+  if (!trust) face = point_to_face_fij(p, fi, fj);
   return face;
 }
 

@@ -89,6 +89,27 @@ def test_config1_10M_points_vs_reference(torch_cuda, ref):
     assert (got == want).all()
 
 
+def test_points_on_leaf_cell_boundaries_vs_reference(torch_cuda, ref):
+    """S2Point encoding where it is most sensitive: 4M points on / within 1e-8..1e-4 leaf cells of cell boundaries (unit
+    and unnormalised), plus scaled and tiny-component vectors. Production path (bounded-error filter + IEEE sequence
+    where it matters) == reference, at levels 30 and 7, and == the all-IEEE diagnostic mode."""
+    from s2geometry_b200 import _lib, cellid, synth
+    lib = _lib.load()
+    rng = np.random.default_rng(8)
+    u = synth.sphere_points(1_000_000, 3)
+    p = np.concatenate([util.leaf_boundary_points(4_000_000, 2), u * 10.0 ** rng.uniform(-200, 200, (len(u), 1)),
+                        u * np.array([1.0, 1e-170, 1e-300]), u * np.array([1e-310, 1.0, 1e-20])])
+    for level in (30, 7):
+        got = cellid.from_points(p, level)
+        assert (got == ref.encode_points(p, level)).all()
+    try:
+        lib.s2b_diag_force_correctly_rounded(1)
+        exact = cellid.from_points(p, 30)
+    finally:
+        lib.s2b_diag_force_correctly_rounded(0)
+    assert (exact == cellid.from_points(p, 30)).all()
+
+
 def test_latlng_5M_vs_reference_and_flags(torch_cuda, ref):
     """lat/lng ids use correctly-rounded sin/cos; glibc is not correctly rounded, so a mismatch is possible only
     where the boundary flag is set. Expected mismatches at 5M points: ~0.01."""
@@ -175,11 +196,26 @@ def test_filter_deviation_is_far_below_the_filter_tolerance(torch_cuda, ref):
     worst = 0.0
     for ll in (synth.sphere_latlng_cuda(200_000_000, 9, "cuda"), torch.from_numpy(np.ascontiguousarray(special)).cuda()):
         dev, flips = ctypes.c_double(0), ctypes.c_uint64(0)
-        rc = lib.s2b_diag_filter_deviation_dev(ll.data_ptr(), ll.shape[0], ctypes.byref(dev), ctypes.byref(flips), None)
+        rc = lib.s2b_diag_filter_deviation_dev(1, ll.data_ptr(), ll.shape[0], ctypes.byref(dev), ctypes.byref(flips), None)
         assert rc == 0 and flips.value == 0
         worst = max(worst, dev.value)
-    print("max filter deviation [leaf cells]:", worst)
+    print("max filter deviation, lat/lng [leaf cells]:", worst)
     assert worst < 4e-6, worst          # kFilterTolIj / 4
+    # S2Point input: approximate vs IEEE division / square root (kXyzFilterTolIj = 8e-6). Unit vectors, scaled vectors,
+    # points on cell boundaries and axis-aligned / tiny-component points.
+    u = synth.sphere_points_cuda(200_000_000, 4, "cuda")
+    edge = torch.from_numpy(util.leaf_boundary_points(2_000_000, 5)).cuda()
+    scaled = u[:1_000_000] * torch.from_numpy(10.0 ** rng.uniform(-140, 140, (1_000_000, 1))).cuda()
+    tiny = u[:1_000_000].clone()
+    tiny[:, 1] *= 1e-200
+    worst = 0.0
+    for pts in (u, edge, scaled.contiguous(), tiny):
+        dev, flips = ctypes.c_double(0), ctypes.c_uint64(0)
+        rc = lib.s2b_diag_filter_deviation_dev(0, pts.data_ptr(), pts.shape[0], ctypes.byref(dev), ctypes.byref(flips), None)
+        assert rc == 0 and flips.value == 0
+        worst = max(worst, dev.value)
+    print("max filter deviation, xyz [leaf cells]:", worst)
+    assert worst < 2e-6, worst          # kXyzFilterTolIj / 4
 
 
 def test_to_point_and_from_token(torch_cuda, ref):
