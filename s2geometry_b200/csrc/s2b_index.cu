@@ -5,7 +5,6 @@
 // an index cell, the crossing test of s2b_contains.cuh from the precomputed cell centre over that cell's clipped
 // edges, with the Sign chain (triage -> stable -> exact superaccumulator -> symbolic) entirely on the device.
 // Index arrays are read through the read-only path; points are streamed (24 B in, 1 B / a few atomics out).
-#include <cuda_pipeline.h>
 #include <cub/device/device_scan.cuh>
 
 #include <cstdlib>
@@ -183,8 +182,8 @@ locate_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint32_t n
 //   bucket kind INSIDE (whole bucket inside index cell c), same margin -> certain hit of cell c
 //   anything else (mixed bucket, near a bucket/face boundary, NaN, ...) -> index appended to the "uncertain" list, which
 //   the exact FP64 kernel (locate_kernel) then processes. Results are therefore exactly those of the FP64 path.
-// Error budget: double->float inputs 2^-24 each, approximate division <= 2 ulp, sqrt 1 ulp, a few roundings: |u| error
-// < 5e-7, s error < 6e-7, i.e. < 650 leaf cells at 2^30; kFastRadius = 2048 leaves 3x margin. A wrong face choice needs
+// Error budget: double->float inputs 2^-24 each, hardware approximate reciprocal and square root <= 2 ulp each, a few
+// roundings: |u| error < 5e-7, s error < 7.5e-7, i.e. < 800 leaf cells at 2^30; kFastRadius = 2048 leaves 2.5x margin. A wrong face choice needs
 // two |components| within 6e-8 of each other, which puts (i,j) within ~60 leaf cells of a face edge: inside the radius.
 constexpr int kFastRadius = 2048;
 
@@ -209,26 +208,59 @@ struct U32Slots {   // like WarpSlots, for a list of point indices (sentinel 0xF
   }
 };
 
-__device__ __forceinline__ int approx_leaf_coord(float w) {   // w = u or v  ->  approximate leaf index (may be off by < 650)
-  const float r = 0.5f * __fsqrt_rn(1.0f + fabsf(3.0f * w));
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+__device__ __forceinline__ int approx_leaf_coord(float w) {   // w = u or v  ->  approximate leaf index (may be off by < 800)
+  const float r = 0.5f * sqrt_approx(fmaf(3.0f, fabsf(w), 1.0f));
   const float s = w >= 0.0f ? r : 1.0f - r;
   return __float2int_rz(1073741824.0f * s);                     // saturating; NaN -> 0
 }
 
-// The point stream is staged through shared memory with cp.async (LDGSTS), double buffered: the copy of tile k+1 is
-// in flight while tile k is processed, so the bytes in flight do not occupy registers (with ~150 instructions per point
-// a register-staged version of this kernel was DRAM-latency-bound at 2.0 TB/s: profiles/r1_query_prefilter_ncu.json).
-// Tile = kThreads * kPointsPerThread points = 12 KB for 2 points per thread; requires xyz to be 16-byte aligned.
+// mbarrier + 1-D bulk copy (TMA) helpers: one thread moves a whole tile with a single instruction.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)), "l"(src),
+               "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done)
+                 : "r"(smem_addr(bar)), "r"(parity)
+                 : "memory");
+  }
+}
+
+// The point stream is staged through shared memory by the TMA unit, double buffered: one thread issues one bulk copy per
+// 12 KB tile (kThreads * kPointsPerThread points) and the tile after the current one is in flight while the current one
+// is processed, so the bytes in flight occupy neither registers nor issue slots. (History: with register staging this
+// kernel was DRAM-latency-bound at 2.0 TB/s; with per-thread cp.async the copy loop itself cost ~35 instructions per
+// point.) Requires xyz to be 16-byte aligned; an odd point count leaves 8 bytes that the issuing thread copies itself.
 template <int kInteriorMode, int kPointsPerThread>
 __global__ void __launch_bounds__(kThreads, 6)
 locate_fast_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint32_t n, uint32_t* __restrict__ uncertain, const PhaseAOut o) {
   unsigned int* const counters = o.counters;
   constexpr uint32_t kTilePoints = kThreads * kPointsPerThread;
   constexpr uint32_t kTileBytes = kTilePoints * 24;
-  constexpr uint32_t kChunks = kTileBytes / 16;                 // 16-byte cp.async chunks per tile
   __shared__ uint16_t s_pos[1024];                              // 4-bit Hilbert table: three steps give the top 12 levels
-  __shared__ __align__(16) double s_tile[2][kTilePoints * 3];
+  __shared__ __align__(128) double s_tile[2][kTilePoints * 3];
+  __shared__ __align__(8) uint64_t s_bar[2];
   for (int k = threadIdx.x; k < 1024; k += kThreads) s_pos[k] = g_hilbert_ix.pos[k];
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
   const unsigned lane = threadIdx.x & 31u;
   const int lut_level = (61 - ix.lut_shift) >> 1;               // 2..10
   const int bucket_bits = 30 - lut_level;                       // log2 of the bucket size in leaf cells (>= 20)
@@ -238,27 +270,25 @@ locate_fast_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint3
   WarpSlots edge_slots, interior_slots;
   U32Slots unc_slots;
 
-  auto issue_tile = [&](uint32_t tile, int stage) {
+  auto issue_tile = [&](uint32_t tile, int stage) {             // thread 0 only
     const uint64_t tile_byte0 = (uint64_t)tile * kTileBytes;
-    const char* src = (const char*)xyz + tile_byte0;
-    char* dst = (char*)s_tile[stage];
-#pragma unroll
-    for (uint32_t c = threadIdx.x; c < kChunks; c += kThreads) {
-      const uint64_t off = (uint64_t)c * 16;
-      if (tile_byte0 + off + 16 <= total_bytes) __pipeline_memcpy_async(dst + off, src + off, 16);
-      else if (tile_byte0 + off + 8 <= total_bytes) __pipeline_memcpy_async(dst + off, src + off, 8);   // n odd: last 8 bytes
-    }
-    __pipeline_commit();
+    const uint64_t left = total_bytes - tile_byte0;
+    const uint32_t bytes = left >= kTileBytes ? kTileBytes : (uint32_t)left;
+    const uint32_t bulk = bytes & ~15u;
+    if (bytes != bulk) s_tile[stage][bulk / 8] = xyz[(tile_byte0 + bulk) / 8];   // made visible to the waiters by the arrive below
+    mbar_expect_tx(&s_bar[stage], bulk);
+    if (bulk) bulk_copy_g2s(s_tile[stage], (const char*)xyz + tile_byte0, bulk, &s_bar[stage]);
   };
 
   uint32_t tile = blockIdx.x;
   int stage = 0;
-  if (tile < num_tiles) issue_tile(tile, 0);
+  uint32_t parity_bits = 0;                                     // bit s = phase parity of stage s's barrier
+  if (tile < num_tiles && threadIdx.x == 0) issue_tile(tile, 0);
   for (; tile < num_tiles; tile += gridDim.x, stage ^= 1) {
     const uint32_t next = tile + gridDim.x;
-    if (next < num_tiles) issue_tile(next, stage ^ 1); else __pipeline_commit();
-    __pipeline_wait_prior(1);                                   // this tile's copies have landed (the next may still fly)
-    __syncthreads();
+    if (next < num_tiles && threadIdx.x == 0) issue_tile(next, stage ^ 1);   // that buffer was released by the barrier below
+    mbar_wait(&s_bar[stage], (parity_bits >> stage) & 1u);
+    parity_bits ^= 1u << stage;
     const double* pts = s_tile[stage];
     const uint32_t tile_point0 = tile * kTilePoints;
 #pragma unroll
@@ -274,7 +304,7 @@ locate_fast_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint3
       const bool neg = m < 0.0f;
       const float a = axis == 0 ? y : -x;
       const float b = axis == 2 ? -y : z;
-      const float inv = __frcp_rn(m);
+      const float inv = rcp_approx(m);
       const int fi = approx_leaf_coord((neg ? b : a) * inv);
       const int fj = approx_leaf_coord((neg ? a : b) * inv);
       const int face = axis + (neg ? 3 : 0);
@@ -308,7 +338,6 @@ locate_fast_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint3
     }
     __syncthreads();                                            // everyone is done with this stage before it is refilled
   }
-  __pipeline_wait_prior(0);
   edge_slots.finish(o.work, o.capacity, +1, lane);
   interior_slots.finish(o.work, o.capacity, -1, lane);
   unc_slots.finish(uncertain, lane);
