@@ -9,8 +9,11 @@
 //   cells[C]     cell centre (= S2CellId::ToPoint(), precomputed) + range of clipped shapes   32 B
 //   clips[K]     shape id, first clipped edge, edge count, flags (bit0 contains_center, bits1-2 dimension)   16 B
 //   edges[E]     both endpoints of every clipped edge, materialised so no shape is dereferenced          48 B
-//   lut[B+1]     bucket = leaf id >> lut_shift (face + 2*lut_level position bits) -> first candidate cell index,
-//                which turns Seek's O(log C) binary search into one table read plus 0-3 probes.
+//   lut[B]       bucket = the level-lut_level cell containing the leaf, addressed by (face, i >> s, j >> s) — NOT by
+//                Hilbert position, so the table is read before (and mostly instead of) the Hilbert encoding —
+//                -> bucket kind + cell index; turns Seek's O(log C) binary search into one table read plus, for
+//                buckets holding several cells, one range read and 0-3 probes.
+//   mixed[M]     candidate cell range [lo, hi] of every bucket of kind "mixed"                           8 B
 #pragma once
 #include "s2b_core.cuh"
 #include "s2b_predicates.cuh"
@@ -21,48 +24,66 @@ struct FlatCell { double cx, cy, cz; uint32_t clip_begin, clip_count; };
 struct FlatClip { int32_t shape_id; uint32_t edge_begin; uint32_t num_edges; uint32_t flags; };
 struct FlatEdge { double v0x, v0y, v0z, v1x, v1y, v1z; };
 
+struct LutRange { uint32_t lo, hi; };
+
 struct FlatIndexView {
   const uint64_t* cell_ids;
   const FlatCell* cells;
   const FlatClip* clips;
   const FlatEdge* edges;
   const uint32_t* lut;
+  const LutRange* mixed;
   const int32_t* interior_info;    // per cell: 0 = has edges; pure interior cell (no edges, all clips contain the centre):
                                    //   -(shape_id + 1) if it has exactly one clip, else the number of clips
   uint32_t num_cells;
-  int lut_shift;
+  int lut_level;                   // 2..10: buckets are the cells of this level
   int num_shape_ids;
 };
 
 enum VertexModel { kOpen = 0, kSemiOpen = 1, kClosed = 2 };
 
-// Lookup-table entry: bits 29..0 = index of the first candidate cell of the bucket; bits 31..30 = what the bucket
-// (a cell of level lut_level, i.e. a contiguous range of leaf ids) looks like:
-//   kLutMixed  several index cells and/or gaps start inside the bucket: probe cell_ids[lo .. next bucket's lo]
+// Lookup-table entry: bits 31..30 = what the bucket (a cell of level lut_level, i.e. a contiguous range of leaf ids)
+// looks like; bits 29..0 = payload:
+//   kLutMixed  several index cells and/or gaps start inside the bucket: payload = index into mixed[], whose entry is
+//              the range of cell_ids to probe
 //   kLutEmpty  no index cell intersects the bucket: every leaf of it is a miss          (decided with ONE load)
-//   kLutInside the whole bucket lies inside index cell `lo`: every leaf of it is a hit   (decided with ONE load)
+//   kLutInside the whole bucket lies inside index cell `payload`: every leaf is a hit    (decided with ONE load)
 constexpr uint32_t kLutIndexMask = 0x3FFFFFFFu;
 constexpr uint32_t kLutMixed = 0u, kLutEmpty = 1u << 30, kLutInside = 2u << 30;
 
-// Index of the cell containing the leaf id, or -1. Equivalent to LocateImpl (s2cell_iterator.h:137-155): the index
-// cells are disjoint, so the only candidate is the last cell whose range_min <= leaf.
-S2B_HD int locate_cell(const FlatIndexView& ix, uint64_t leaf) {
+S2B_HD uint32_t lut_bucket(int lut_level, int face, uint32_t i, uint32_t j) {
+  const int s = 30 - lut_level;
+  return ((uint32_t)face << (2 * lut_level)) | ((i >> s) << lut_level) | (j >> s);
+}
+
+// Index of the cell containing the leaf cell (face, i, j), or -1. Equivalent to LocateImpl (s2cell_iterator.h:137-155):
+// the index cells are disjoint, so the only candidate is the last cell whose range_min <= leaf. `leaf_id()` yields
+// the leaf's S2CellId (the Hilbert encoding); it is only evaluated for mixed buckets.
+template <class LeafFn>
+S2B_HD int locate_cell(const FlatIndexView& ix, int face, uint32_t i, uint32_t j, LeafFn leaf_id) {
   if (ix.num_cells == 0) return -1;
-  const uint64_t bucket = leaf >> ix.lut_shift;
-  const uint32_t e0 = ix.lut[bucket];
-  uint32_t lo = e0 & kLutIndexMask;
+  const uint32_t e0 = ix.lut[lut_bucket(ix.lut_level, face, i, j)];
   const uint32_t kind = e0 & ~kLutIndexMask;
   if (kind == kLutEmpty) return -1;
-  if (kind == kLutInside) return (int)lo;
-  uint32_t hi = ix.lut[bucket + 1] & kLutIndexMask;
-  if (lo >= ix.num_cells) return -1;
-  if (hi >= ix.num_cells) hi = ix.num_cells - 1;
+  if (kind == kLutInside) return (int)(e0 & kLutIndexMask);
+  const LutRange r = ix.mixed[e0 & kLutIndexMask];
+  const uint64_t leaf = leaf_id();
+  uint32_t lo = r.lo, hi = r.hi;
   while (lo < hi) {
     uint32_t mid = (lo + hi + 1) >> 1;
     if (cellid_range_min(ix.cell_ids[mid]) <= leaf) lo = mid; else hi = mid - 1;
   }
   uint64_t id = ix.cell_ids[lo];
   return (cellid_range_min(id) <= leaf && leaf <= cellid_range_max(id)) ? (int)lo : -1;
+}
+
+// Locate for a point (4-bit Hilbert table), used by the host-side simulation and the generic visitor.
+template <class HilbertT>
+S2B_HD int locate_point(const FlatIndexView& ix, const P3& p, const HilbertT* hilbert_pos) {
+  double fi, fj;
+  const int face = point_to_face_fij(p, &fi, &fj);
+  const uint32_t i = fij_to_ij(fi), j = fij_to_ij(fj);
+  return locate_cell(ix, face, i, j, [&] { return from_face_ij(face, i, j, hilbert_pos); });
 }
 
 S2B_HD P3 edge_v0(const FlatEdge& e) { return P3{e.v0x, e.v0y, e.v0z}; }
@@ -145,8 +166,7 @@ S2B_HD bool clip_contains(const FlatIndexView& ix, const FlatClip& clip, const P
 // Returns the located cell index (or -1).
 template <class HilbertT, class Visit>
 S2B_HD int visit_containing_shapes(const FlatIndexView& ix, const P3& p, const HilbertT* hilbert_pos, int model, Visit visit) {
-  uint64_t leaf = cellid_from_point(p, hilbert_pos);
-  int cell = locate_cell(ix, leaf);
+  int cell = locate_point(ix, p, hilbert_pos);
   if (cell < 0) return cell;
   FlatCell fc = ix.cells[cell];
   P3 a{fc.cx, fc.cy, fc.cz};

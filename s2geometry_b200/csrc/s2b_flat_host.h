@@ -17,14 +17,15 @@ struct HostFlat {
   std::vector<FlatCell> cells;
   std::vector<FlatClip> clips;
   std::vector<FlatEdge> edges;
-  std::vector<uint32_t> lut;   // num_buckets + 2 entries
+  std::vector<uint32_t> lut;   // num_buckets entries, (face, i, j) order
+  std::vector<LutRange> mixed; // one per mixed bucket (at least one entry, so the array is never empty)
   std::vector<int32_t> interior_info;  // per cell, see FlatIndexView
   uint64_t num_buckets = 0;
-  int lut_shift = 0;
+  int lut_level = 0;
   FlatIndexView view(const uint64_t* cell_ids, int num_shape_ids) const {
     FlatIndexView v;
-    v.cell_ids = cell_ids; v.cells = cells.data(); v.clips = clips.data(); v.edges = edges.data(); v.lut = lut.data(); v.interior_info = interior_info.data();
-    v.num_cells = (uint32_t)cells.size(); v.lut_shift = lut_shift; v.num_shape_ids = num_shape_ids;
+    v.cell_ids = cell_ids; v.cells = cells.data(); v.clips = clips.data(); v.edges = edges.data(); v.lut = lut.data(); v.mixed = mixed.data(); v.interior_info = interior_info.data();
+    v.num_cells = (uint32_t)cells.size(); v.lut_level = lut_level; v.num_shape_ids = num_shape_ids;
     return v;
   }
 };
@@ -57,9 +58,10 @@ inline int pack_flat_index(const S2bFlatIndex& f, HostFlat* out, std::string* er
   while (lut_level < 10 && (6ull << (2 * lut_level)) < lut_factor * C) ++lut_level;
   const uint64_t nb = 6ull << (2 * lut_level);
   out->num_buckets = nb;
-  out->lut_shift = 61 - 2 * lut_level;
+  out->lut_level = lut_level;
+  const int lut_shift = 61 - 2 * lut_level;   // Hilbert-order bucket of a leaf id = id >> lut_shift
   try {
-    out->cells.resize(C); out->clips.resize(K); out->edges.resize(E); out->lut.resize(nb + 2); out->interior_info.resize(C + 1);
+    out->cells.resize(C); out->clips.resize(K); out->edges.resize(E); out->lut.resize(nb); out->interior_info.resize(C + 1);
   } catch (const std::bad_alloc&) {
     return fail(S2B_ENOMEM, "host allocation failed");
   }
@@ -82,23 +84,29 @@ inline int pack_flat_index(const S2bFlatIndex& f, HostFlat* out, std::string* er
       pure = f.clip_edge_begin[k + 1] == f.clip_edge_begin[k] && (f.clip_flags[k] & 1);
     out->interior_info[c] = !pure ? 0 : (e - b == 1 ? -(f.clip_shape_id[b] + 1) : (int32_t)(e - b));
   }
-  // lut[b] = number of cells whose range_max < first leaf id of bucket b (the first cell a leaf of bucket b can be
-  // in), tagged with the bucket kind (s2b_contains.cuh): empty / entirely inside that cell / mixed.
+  // Walk the buckets in Hilbert order (b = leaf id >> lut_shift) with c = number of cells whose range_max < first leaf
+  // of the bucket (the first cell a leaf of bucket b can be in), classify each (s2b_contains.cuh: empty / entirely
+  // inside cell c / mixed) and store the entry at the bucket's (face, i, j) address.
   if (C > kLutIndexMask) return fail(S2B_EINVAL, "index too large for the 30-bit lookup-table entries");
+  out->mixed.clear();
   uint64_t c = 0;
-  for (uint64_t b = 0; b <= nb; ++b) {
-    const uint64_t first = b << out->lut_shift;
+  for (uint64_t b = 0; b < nb; ++b) {
+    const uint64_t first = b << lut_shift, last = ((b + 1) << lut_shift) - 1;
     while (c < C && cellid_range_max(f.cell_ids[c]) < first) ++c;
-    if (b == nb) c = C;
-    uint32_t kind = kLutMixed;
-    if (b < nb) {
-      const uint64_t last = ((b + 1) << out->lut_shift) - 1;
-      if (c == C || cellid_range_min(f.cell_ids[c]) > last) kind = kLutEmpty;
-      else if (cellid_range_min(f.cell_ids[c]) <= first && cellid_range_max(f.cell_ids[c]) >= last) kind = kLutInside;
+    uint32_t entry;
+    if (c == C || cellid_range_min(f.cell_ids[c]) > last) entry = kLutEmpty;
+    else if (cellid_range_min(f.cell_ids[c]) <= first && cellid_range_max(f.cell_ids[c]) >= last) entry = kLutInside | (uint32_t)c;
+    else {
+      uint64_t h = c;   // last cell starting inside the bucket
+      while (h + 1 < C && cellid_range_min(f.cell_ids[h + 1]) <= last) ++h;
+      entry = kLutMixed | (uint32_t)out->mixed.size();
+      out->mixed.push_back(LutRange{(uint32_t)c, (uint32_t)h});
     }
-    out->lut[b] = (uint32_t)c | kind;
+    int bi, bj;
+    const int face = cellid_to_face_ij(first | 1, kHilbert.ij, &bi, &bj);   // the bucket's first leaf cell
+    out->lut[lut_bucket(lut_level, face, (uint32_t)bi, (uint32_t)bj)] = entry;
   }
-  out->lut[nb + 1] = (uint32_t)C;
+  if (out->mixed.empty()) out->mixed.push_back(LutRange{0, 0});
   return S2B_OK;
 }
 

@@ -162,7 +162,8 @@ locate_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint32_t n
     for (int t = 0; t < kPointsPerThread; ++t) {
       double fi, fj;
       const int face = point_to_face_fij(p[t], &fi, &fj);
-      cell[t] = locate_cell(ix, from_face_ij_wide(face, fij_to_ij(fi), fij_to_ij(fj), s_pos));
+      const uint32_t ci = fij_to_ij(fi), cj = fij_to_ij(fj);
+      cell[t] = locate_cell(ix, face, ci, cj, [&] { return from_face_ij_wide(face, ci, cj, s_pos); });
     }
 #pragma unroll
     for (int t = 0; t < kPointsPerThread; ++t) {
@@ -251,10 +252,8 @@ locate_fast_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint3
   unsigned int* const counters = o.counters;
   constexpr uint32_t kTilePoints = kThreads * kPointsPerThread;
   constexpr uint32_t kTileBytes = kTilePoints * 24;
-  __shared__ uint16_t s_pos[1024];                              // 4-bit Hilbert table: three steps give the top 12 levels
   __shared__ __align__(128) double s_tile[2][kTilePoints * 3];
   __shared__ __align__(8) uint64_t s_bar[2];
-  for (int k = threadIdx.x; k < 1024; k += kThreads) s_pos[k] = g_hilbert_ix.pos[k];
   if (threadIdx.x == 0) {
     mbar_init(&s_bar[0], 1);
     mbar_init(&s_bar[1], 1);
@@ -262,7 +261,7 @@ locate_fast_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint3
   }
   __syncthreads();
   const unsigned lane = threadIdx.x & 31u;
-  const int lut_level = (61 - ix.lut_shift) >> 1;               // 2..10
+  const int lut_level = ix.lut_level;                           // 2..10
   const int bucket_bits = 30 - lut_level;                       // log2 of the bucket size in leaf cells (>= 20)
   const int bucket_mask = (1 << bucket_bits) - 1;
   const uint64_t total_bytes = (uint64_t)n * 24;
@@ -313,18 +312,8 @@ locate_fast_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint3
       const int ri = fi & bucket_mask, rj = fj & bucket_mask;
       bool certain = valid && fi >= 0 && fj >= 0 && fi < (1 << 30) && fj < (1 << 30) &&
                      ri >= kFastRadius && ri <= bucket_mask - kFastRadius && rj >= kFastRadius && rj <= bucket_mask - kFastRadius;
-      // position bits of the top 12 levels (three 4-bit table steps), then the bucket = top lut_level levels
-      uint32_t bits = (uint32_t)face & 1u, pos24 = 0;
-#pragma unroll
-      for (int k = 7; k >= 5; --k) {       // i,j bits 29..18 (the top step holds only 2 bits of each)
-        bits += (((uint32_t)fi >> (4 * k)) & 15u) << 6;
-        bits += (((uint32_t)fj >> (4 * k)) & 15u) << 2;
-        bits = s_pos[bits & 1023u];
-        pos24 = (pos24 << 8) | (bits >> 2);
-        bits &= 3u;
-      }
-      // the three steps produced 4 + 8 + 8 position bits = levels 1..10 exactly (top step = 2 levels): pos20
-      const uint32_t bucket = (((uint32_t)face << 20) | (pos24 & 0xFFFFFu)) >> (20 - 2 * lut_level);
+      // the table is addressed by (face, i, j) of the bucket: no Hilbert encoding on this path
+      const uint32_t bucket = lut_bucket(lut_level, face, (uint32_t)fi & 0x3FFFFFFFu, (uint32_t)fj & 0x3FFFFFFFu);
       int c = -1;
       if (certain) {
         const uint32_t e0 = ix.lut[bucket];
@@ -583,7 +572,7 @@ int s2b_index_create(const S2bFlatIndex* f, S2bIndex** out) {
   int prc = pack_flat_index(*f, &hf, &err);
   if (prc != S2B_OK) return set_error(prc, "%s", err.c_str());
   const uint64_t C = f->num_cells, K = f->num_clips, E = f->num_edges, nb = hf.num_buckets;
-  const int lut_shift = hf.lut_shift;
+  const uint64_t M = hf.mixed.size();
   std::vector<FlatCell>& cells = hf.cells;
   std::vector<FlatClip>& clips = hf.clips;
   std::vector<FlatEdge>& edges = hf.edges;
@@ -596,7 +585,8 @@ int s2b_index_create(const S2bFlatIndex* f, S2bIndex** out) {
   auto align = [](size_t v) { return (v + 255) / 256 * 256; };
   size_t o_ids = 0, o_cells = o_ids + align(8 * (C + 1)), o_clips = o_cells + align(sizeof(FlatCell) * (C + 1)),
          o_edges = o_clips + align(sizeof(FlatClip) * (K + 1)), o_lut = o_edges + align(sizeof(FlatEdge) * (E + 1)),
-         o_kind = o_lut + align(4 * (nb + 2)), o_view = o_kind + align(4 * (C + 1)), total = o_view + align(sizeof(FlatIndexView));
+         o_mixed = o_lut + align(4 * nb), o_kind = o_mixed + align(sizeof(LutRange) * M), o_view = o_kind + align(4 * (C + 1)),
+         total = o_view + align(sizeof(FlatIndexView));
   e = cudaMalloc(&ix->blob, total);
   if (e != cudaSuccess) { delete ix; return cuda_fail(e, "cudaMalloc(index)"); }
   ix->blob_bytes = total;
@@ -606,7 +596,8 @@ int s2b_index_create(const S2bFlatIndex* f, S2bIndex** out) {
   ok &= C == 0 || cudaMemcpy(base + o_cells, cells.data(), sizeof(FlatCell) * C, cudaMemcpyHostToDevice) == cudaSuccess;
   ok &= K == 0 || cudaMemcpy(base + o_clips, clips.data(), sizeof(FlatClip) * K, cudaMemcpyHostToDevice) == cudaSuccess;
   ok &= E == 0 || cudaMemcpy(base + o_edges, edges.data(), sizeof(FlatEdge) * E, cudaMemcpyHostToDevice) == cudaSuccess;
-  ok &= cudaMemcpy(base + o_lut, lut.data(), 4 * (nb + 2), cudaMemcpyHostToDevice) == cudaSuccess;
+  ok &= cudaMemcpy(base + o_lut, lut.data(), 4 * nb, cudaMemcpyHostToDevice) == cudaSuccess;
+  ok &= cudaMemcpy(base + o_mixed, hf.mixed.data(), sizeof(LutRange) * M, cudaMemcpyHostToDevice) == cudaSuccess;
   ok &= cudaMemcpy(base + o_kind, hf.interior_info.data(), 4 * (C + 1), cudaMemcpyHostToDevice) == cudaSuccess;
   if (!ok) { e = cudaGetLastError(); cudaFree(ix->blob); delete ix; return cuda_fail(e, "cudaMemcpy(index)"); }
   ix->view.cell_ids = (const uint64_t*)(base + o_ids);
@@ -614,9 +605,10 @@ int s2b_index_create(const S2bFlatIndex* f, S2bIndex** out) {
   ix->view.clips = (const FlatClip*)(base + o_clips);
   ix->view.edges = (const FlatEdge*)(base + o_edges);
   ix->view.lut = (const uint32_t*)(base + o_lut);
+  ix->view.mixed = (const LutRange*)(base + o_mixed);
   ix->view.interior_info = (const int32_t*)(base + o_kind);
   ix->view.num_cells = (uint32_t)C;
-  ix->view.lut_shift = lut_shift;
+  ix->view.lut_level = hf.lut_level;
   ix->view.num_shape_ids = f->num_shape_ids;
   ix->num_clips = K; ix->num_edges = E;
   if (cudaMemcpy(base + o_view, &ix->view, sizeof(FlatIndexView), cudaMemcpyHostToDevice) != cudaSuccess) {

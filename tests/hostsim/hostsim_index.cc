@@ -33,7 +33,7 @@ int hs_index_query(const S2bFlatIndex* f, const double* xyz, size_t n, int model
     } else if (mode == 2) {
       visit_containing_shapes(ix, p, kHilbert.pos, model, [&](int id) { ++counts[id]; return true; });
     } else if (mode == 3) {
-      out32[i] = locate_cell(ix, cellid_from_point(p, kHilbert.pos));
+      out32[i] = locate_point(ix, p, kHilbert.pos);
     } else {
       int c = 0;
       visit_containing_shapes(ix, p, kHilbert.pos, model, [&](int) { ++c; return true; });
