@@ -90,6 +90,17 @@ class DeviceShapeIndex {
     s2b_built_index_destroy(built);
     return ok;
   }
+  // The counterpart of MutableS2ShapeIndex::Init(Decoder*, ShapeFactory) (mutable_s2shape_index.cc:2011-2040): `encoded`
+  // is the output of MutableS2ShapeIndex::Encode, the shape arrays stand in for the ShapeFactory.
+  bool InitFromEncoded(const void* encoded, size_t len, int num_shapes, const int8_t* shape_dim, const uint32_t* shape_chain_begin,
+                       const uint32_t* chain_vertex_begin, const double* vertices) {
+    S2bBuiltIndex* built = nullptr;
+    if (s2b_index_decode(encoded, len, num_shapes, shape_dim, shape_chain_begin, chain_vertex_begin, vertices, &built, nullptr, nullptr) != S2B_OK) return false;
+    S2bFlatIndex flat;
+    bool ok = s2b_built_index_flat(built, &flat, nullptr) == S2B_OK && Init(flat);
+    s2b_built_index_destroy(built);
+    return ok;
+  }
   bool ok() const { return h_ != nullptr; }
   int num_shape_ids() const { int32_t s = 0; if (h_) s2b_index_info(h_, nullptr, nullptr, nullptr, &s, nullptr); return s; }
   const S2bIndex* handle() const { return h_; }

@@ -172,6 +172,23 @@ int s2b_index_build(int num_shapes, const int8_t* shape_dim, const uint32_t* sha
 int s2b_built_index_flat(const S2bBuiltIndex* built, S2bFlatIndex* flat_out, const int32_t** edge_id_out);
 void s2b_built_index_destroy(S2bBuiltIndex* built);
 
+/* Reads the reference's serialized index: the bytes written by MutableS2ShapeIndex::Encode
+ * (mutable_s2shape_index.cc:1988-2009; cells: S2ShapeIndexCell::Encode s2shape_index.cc:69-195; cell ids:
+ * EncodeS2CellIdVector encoded_s2cell_id_vector.cc:42-95), i.e. what MutableS2ShapeIndex::Init
+ * (mutable_s2shape_index.cc:2011-2040) / EncodedS2ShapeIndex::Init consume. That format holds cells, clipped shapes
+ * and edge ids only; the geometry is supplied as the same shape soup s2b_index_build takes (shape ids = positions in
+ * the soup, edge ids numbered as S2LaxPolygonShape / S2LaxPolylineShape / S2PointVectorShape number them). The result
+ * has exactly the reference index's cells. Malformed input fails with S2B_EINVAL (never crashes), like Init's `false`.
+ * max_edges_per_cell_out / consumed_out (bytes read) are optional. */
+int s2b_index_decode(const void* bytes, size_t len, int num_shapes, const int8_t* shape_dim, const uint32_t* shape_chain_begin,
+                     const uint32_t* chain_vertex_begin, const double* vertices, S2bBuiltIndex** built_out,
+                     int* max_edges_per_cell_out, size_t* consumed_out);
+/* Writes a flat index in that format, byte-identical to MutableS2ShapeIndex::Encode for an index with the same cells;
+ * edge_id[E] = shape-local id of every clipped edge (s2b_built_index_flat's edge_id_out). *size_out receives the
+ * encoded size; if it exceeds `capacity` (or out is NULL) nothing is written and S2B_ECAPACITY is returned. */
+int s2b_index_encode(const S2bFlatIndex* flat, const int32_t* edge_id, int max_edges_per_cell, void* out, size_t capacity,
+                     size_t* size_out);
+
 typedef struct S2bIndex S2bIndex;
 
 /* Uploads the index to the CURRENT CUDA device (one replica per GPU: call once per process/device). */

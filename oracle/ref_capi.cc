@@ -36,6 +36,7 @@
 #include "s2/s2shape.h"
 #include "s2/s2shapeutil_contains_brute_force.h"
 #include "s2/s2shapeutil_get_reference_point.h"
+#include "s2/util/coding/coder.h"
 
 namespace {
 
@@ -331,6 +332,52 @@ void ref_index_flatten(void* h, uint64_t* cell_ids, double* cell_center, uint32_
   }
   cell_clip_begin[c] = (uint32_t)k;
   clip_edge_begin[k] = (uint32_t)e;
+}
+
+// MutableS2ShapeIndex::Encode (mutable_s2shape_index.cc:1988-2009). Returns the encoded size; writes if it fits.
+size_t ref_index_encode(void* h, uint8_t* out, size_t capacity) {
+  Encoder enc;
+  ((RefIndex*)h)->index.Encode(&enc);
+  if (out && enc.length() <= capacity) memcpy(out, enc.base(), enc.length());
+  return enc.length();
+}
+
+// Round trip through the reference's own decoder: MutableS2ShapeIndex::Init over `bytes` with the shapes of `h` is
+// rebuilt and its cells compared with h's. Returns 1 if Init succeeds and every cell/clip/edge id matches, else 0.
+int ref_index_init_matches(void* h, const uint8_t* bytes, size_t len) {
+  auto& index = ((RefIndex*)h)->index;
+  struct Borrowed : public S2Shape {
+    const S2Shape* s;
+    explicit Borrowed(const S2Shape* s) : s(s) {}
+    int num_edges() const override { return s->num_edges(); }
+    Edge edge(int e) const override { return s->edge(e); }
+    int dimension() const override { return s->dimension(); }
+    ReferencePoint GetReferencePoint() const override { return s->GetReferencePoint(); }
+    int num_chains() const override { return s->num_chains(); }
+    Chain chain(int i) const override { return s->chain(i); }
+    Edge chain_edge(int i, int j) const override { return s->chain_edge(i, j); }
+    ChainPosition chain_position(int e) const override { return s->chain_position(e); }
+  };
+  struct Factory : public S2ShapeIndex::ShapeFactory {
+    const MutableS2ShapeIndex* src;
+    explicit Factory(const MutableS2ShapeIndex* src) : src(src) {}
+    int size() const override { return src->num_shape_ids(); }
+    std::unique_ptr<S2Shape> operator[](int i) const override { return std::make_unique<Borrowed>(src->shape(i)); }
+    std::unique_ptr<ShapeFactory> Clone() const override { return std::make_unique<Factory>(src); }
+  } factory(&index);
+  MutableS2ShapeIndex copy;
+  Decoder dec(bytes, len);
+  if (!copy.Init(&dec, factory)) return 0;
+  MutableS2ShapeIndex::Iterator a(&index, S2ShapeIndex::BEGIN), b(&copy, S2ShapeIndex::BEGIN);
+  for (; !a.done() && !b.done(); a.Next(), b.Next()) {
+    if (a.id() != b.id() || a.cell().num_clipped() != b.cell().num_clipped()) return 0;
+    for (int i = 0; i < a.cell().num_clipped(); ++i) {
+      const S2ClippedShape &x = a.cell().clipped(i), &y = b.cell().clipped(i);
+      if (x.shape_id() != y.shape_id() || x.contains_center() != y.contains_center() || x.num_edges() != y.num_edges()) return 0;
+      for (int j = 0; j < x.num_edges(); ++j) if (x.edge(j) != y.edge(j)) return 0;
+    }
+  }
+  return a.done() && b.done();
 }
 
 int ref_index_num_shape_ids(void* h) { return ((RefIndex*)h)->index.num_shape_ids(); }

@@ -206,6 +206,19 @@ class RefIndex:
                                    _p(f["edge_id"]), _p(f["edge_v0"]), _p(f["edge_v1"]))
         return f
 
+    def encode(self):
+        """MutableS2ShapeIndex::Encode -> bytes."""
+        self.lib.ref_index_encode.restype = _sz
+        n = int(self.lib.ref_index_encode(_vp(self.h), None, _sz(0)))
+        out = np.zeros(max(n, 1), np.uint8)
+        self.lib.ref_index_encode(_vp(self.h), _p(out), _sz(out.size))
+        return out[:n].tobytes()
+
+    def init_matches(self, data):
+        """True if MutableS2ShapeIndex::Init accepts `data` (with this index's shapes) and reproduces this index's cells."""
+        buf = np.frombuffer(bytes(data), np.uint8)
+        return bool(self.lib.ref_index_init_matches(_vp(self.h), _p(buf), _sz(buf.size)))
+
     def contains(self, xyz, model=1, threads=0):
         xyz = np.ascontiguousarray(xyz, np.float64)
         out = np.empty(len(xyz), np.uint8)

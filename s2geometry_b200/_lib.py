@@ -45,6 +45,8 @@ SIGNATURES = {
     "s2b_index_build": (_i, [_i, _vp, _vp, _vp, _vp, _i, _vp]),
     "s2b_built_index_flat": (_i, [_vp, _vp, _vp]),
     "s2b_built_index_destroy": (None, [_vp]),
+    "s2b_index_decode": (_i, [_vp, _sz, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "s2b_index_encode": (_i, [_vp, _vp, _i, _vp, _sz, _vp]),
     "s2b_index_create": (_i, [_vp, _vp]),
     "s2b_index_create_from_cellunion": (_i, [_vp, _sz, _vp]),
     "s2b_index_destroy": (None, [_vp]),
@@ -63,6 +65,9 @@ SIGNATURES = {
     "s2b_cellunion_contains": (_i, [_vp, _sz, _vp, _sz, _vp]),
     "s2b_cellunion_contains_dev": (_i, [_vp, _sz, _vp, _sz, _vp, _vp]),
 }
+
+
+S2B_OK, S2B_EINVAL, S2B_ECUDA, S2B_ENOMEM, S2B_ECAPACITY = 0, -1, -2, -3, -4   # include/s2b_capi.h
 
 
 class S2BError(RuntimeError):

@@ -4,6 +4,7 @@
 
 #include "../../include/s2b_capi.h"
 #include "s2b_index_builder.h"
+#include "s2b_index_wire.h"
 
 namespace s2b { int set_error(int code, const char* fmt, ...); }
 
@@ -38,5 +39,44 @@ int s2b_built_index_flat(const S2bBuiltIndex* built, S2bFlatIndex* flat_out, con
 }
 
 void s2b_built_index_destroy(S2bBuiltIndex* built) { delete built; }
+
+int s2b_index_decode(const void* bytes, size_t len, int num_shapes, const int8_t* shape_dim, const uint32_t* shape_chain_begin,
+                     const uint32_t* chain_vertex_begin, const double* vertices, S2bBuiltIndex** out, int* max_edges_per_cell_out,
+                     size_t* consumed_out) {
+  if (!out) return s2b::set_error(S2B_EINVAL, "null output");
+  *out = nullptr;
+  S2bBuiltIndex* b = new (std::nothrow) S2bBuiltIndex();
+  if (!b) return s2b::set_error(S2B_ENOMEM, "host allocation failed");
+  std::string err;
+  int rc;
+  try {
+    rc = s2b::decode_index_wire((const uint8_t*)bytes, len, num_shapes, shape_dim, shape_chain_begin, chain_vertex_begin, vertices,
+                                &b->data, max_edges_per_cell_out, consumed_out, &err);
+  } catch (const std::bad_alloc&) {
+    delete b;
+    return s2b::set_error(S2B_ENOMEM, "host allocation failed while decoding the index");
+  }
+  if (rc != S2B_OK) { delete b; return s2b::set_error(rc, "%s", err.c_str()); }
+  *out = b;
+  return S2B_OK;
+}
+
+int s2b_index_encode(const S2bFlatIndex* flat, const int32_t* edge_id, int max_edges_per_cell, void* out, size_t capacity,
+                     size_t* size_out) {
+  if (!flat || !size_out) return s2b::set_error(S2B_EINVAL, "null argument");
+  std::vector<uint8_t> bytes;
+  std::string err;
+  int rc;
+  try {
+    rc = s2b::encode_index_wire(*flat, edge_id, max_edges_per_cell, &bytes, &err);
+  } catch (const std::bad_alloc&) {
+    return s2b::set_error(S2B_ENOMEM, "host allocation failed while encoding the index");
+  }
+  if (rc != S2B_OK) return s2b::set_error(rc, "%s", err.c_str());
+  *size_out = bytes.size();
+  if (!out || capacity < bytes.size()) return s2b::set_error(S2B_ECAPACITY, "index encode: %zu bytes needed", bytes.size());
+  if (!bytes.empty()) std::memcpy(out, bytes.data(), bytes.size());
+  return S2B_OK;
+}
 
 }  // extern "C"

@@ -97,6 +97,11 @@ def build_flat_index(soup, max_edges_per_cell=0):
     keep = (soup.shape_dim, soup.shape_chain_begin, soup.chain_vertex_begin, soup.vertices)
     _lib.check(lib.s2b_index_build(int(soup.num_shapes), keep[0].ctypes.data, keep[1].ctypes.data, keep[2].ctypes.data,
                                    keep[3].ctypes.data if keep[3].size else None, int(max_edges_per_cell), ctypes.byref(h)))
+    return _take_built(lib, h)
+
+
+def _take_built(lib, h):
+    """Copies a S2bBuiltIndex into a FlatIndex (with .edge_id) and destroys the handle."""
     try:
         st = S2bFlatIndexStruct()
         eid = ctypes.c_void_p()
@@ -114,6 +119,41 @@ def build_flat_index(soup, max_edges_per_cell=0):
         return flat
     finally:
         lib.s2b_built_index_destroy(h)
+
+
+def decode_index(data, soup):
+    """Reads the reference's serialized index (the bytes of MutableS2ShapeIndex::Encode) into a FlatIndex; `soup` supplies
+    the geometry the edge ids refer to (the counterpart of MutableS2ShapeIndex::Init's ShapeFactory). Returns
+    (flat_index, max_edges_per_cell, bytes_consumed)."""
+    lib = _lib.load()
+    soup = soup.freeze()
+    buf = np.frombuffer(bytes(data), np.uint8)
+    h = ctypes.c_void_p()
+    max_edges = ctypes.c_int(0)
+    used = ctypes.c_size_t(0)
+    keep = (soup.shape_dim, soup.shape_chain_begin, soup.chain_vertex_begin, soup.vertices)
+    _lib.check(lib.s2b_index_decode(buf.ctypes.data if buf.size else None, int(buf.size), int(soup.num_shapes), keep[0].ctypes.data,
+                                    keep[1].ctypes.data, keep[2].ctypes.data, keep[3].ctypes.data if keep[3].size else None,
+                                    ctypes.byref(h), ctypes.byref(max_edges), ctypes.byref(used)))
+    return _take_built(lib, h), int(max_edges.value), int(used.value)
+
+
+def encode_index(flat, max_edges_per_cell=0):
+    """Serializes a FlatIndex (which must carry .edge_id) in the reference's index format (MutableS2ShapeIndex::Encode)."""
+    lib = _lib.load()
+    eid = getattr(flat, "edge_id", None)
+    if eid is None:
+        raise ValueError("encode_index needs flat.edge_id (shape-local edge ids)")
+    eid = np.ascontiguousarray(eid, np.int32)
+    st = flat.as_struct()
+    size = ctypes.c_size_t(0)
+    rc = lib.s2b_index_encode(ctypes.byref(st), eid.ctypes.data if eid.size else None, int(max_edges_per_cell), None, 0, ctypes.byref(size))
+    if rc != _lib.S2B_ECAPACITY:
+        _lib.check(rc)
+    out = np.zeros(max(int(size.value), 1), np.uint8)
+    _lib.check(lib.s2b_index_encode(ctypes.byref(st), eid.ctypes.data if eid.size else None, int(max_edges_per_cell), out.ctypes.data,
+                                    int(out.size), ctypes.byref(size)))
+    return out[:int(size.value)].tobytes()
 
 
 def _is_tensor(x):

@@ -72,9 +72,29 @@ def index_fixture(ref):
         len(f["cell_ids"]), len(f["clip_shape_id"]), len(f["edge_v0"]), len(q), out["contains_SEMI_OPEN"].sum()))
 
 
+def wire_fixture(ref):
+    """Bytes of MutableS2ShapeIndex::Encode for two small scenes (single-shape and multi-shape with points and polylines)
+    + the reference's own flattening of the same indexes: pins s2b_index_decode / s2b_index_encode."""
+    from tests import scenes
+    from tests.test_index_wire import wire_scenes
+    out = {}
+    for name, soup, mepc in wire_scenes(small_only=True):
+        ri = ref.index_create(soup, mepc)
+        f = ri.flatten()
+        out[name + "__bytes"] = np.frombuffer(ri.encode(), np.uint8)
+        out[name + "__max_edges_per_cell"] = np.int32(mepc if mepc > 0 else 10)
+        for k in ("shape_dim", "shape_chain_begin", "chain_vertex_begin", "vertices"):
+            out[name + "__soup_" + k] = getattr(soup, k)
+        for k in ("cell_ids", "cell_center", "cell_clip_begin", "clip_shape_id", "clip_flags", "clip_edge_begin", "edge_id", "edge_v0", "edge_v1"):
+            out[name + "__" + k] = f[k]
+        print("index_wire", name, "bytes=%d cells=%d" % (len(out[name + "__bytes"]), len(f["cell_ids"])))
+    np.savez_compressed(os.path.join(G, "index_wire.npz"), **out)
+
+
 if __name__ == "__main__":
     ref = reflib.load()
     encode_fixture(ref)
     index_fixture(ref)
+    wire_fixture(ref)
     if len(sys.argv) > 1 and sys.argv[1] == "all":
         pass
