@@ -122,6 +122,19 @@ int s2b_cellid_to_point_dev(const uint64_t* ids_dev, size_t n, double* xyz_out_d
  * FromFaceIJWrap (:458-489). */
 int s2b_cellid_edge_neighbors(const uint64_t* ids, size_t n, uint64_t* neighbors4_out);
 int s2b_cellid_edge_neighbors_dev(const uint64_t* ids_dev, size_t n, uint64_t* neighbors4_out_dev, void* stream);
+/* S2CellId::AppendVertexNeighbors(level) (s2cell_id.cc:514-556): the cells of `level` around the vertex of
+ * parent(level) closest to the cell, in the reference's order: neighbors4_out[4*i + k], count_out[i] = 3 (cube vertex)
+ * or 4; unused slots are 0. Requires level < level(ids[i]) (as the reference does); otherwise count 0. */
+int s2b_cellid_vertex_neighbors(const uint64_t* ids, size_t n, int level, uint64_t* neighbors4_out, uint8_t* count_out);
+int s2b_cellid_vertex_neighbors_dev(const uint64_t* ids_dev, size_t n, int level, uint64_t* neighbors4_out_dev,
+                                    uint8_t* count_out_dev, void* stream);
+/* S2CellId::AppendAllNeighbors(nbr_level) (s2cell_id.cc:558-598): all cells of nbr_level (>= level(ids[i])) adjacent
+ * to the cell, in the reference's order, at out[i*out_stride ...]; count_out[i] = 4 * 2^(nbr_level - level) + 4 (8 for
+ * nbr_level == level). Entries beyond out_stride are dropped, unused slots are 0. */
+int s2b_cellid_all_neighbors(const uint64_t* ids, size_t n, int nbr_level, uint64_t* out, size_t out_stride, uint32_t* count_out);
+int s2b_cellid_all_neighbors_dev(const uint64_t* ids_dev, size_t n, int nbr_level, uint64_t* out_dev, size_t out_stride,
+                                 uint32_t* count_out_dev, void* stream);
+
 /* S2CellId::FromToken (s2cell_id.cc:235-254): tokens as produced by s2b_cellid_to_token (16-byte slots + lengths);
  * malformed tokens decode to 0 (S2CellId::None()). */
 int s2b_cellid_from_token(const char* tokens16, const uint8_t* len, size_t n, uint64_t* ids_out);
@@ -240,6 +253,17 @@ int s2b_diag_force_exact_locate(int on);
  * last reset, summed over all launches of this process on the current device. Resets the counter when reset != 0.
  * There is no CPU stage behind it: this is purely a statistic. */
 int s2b_exact_stage_count(uint64_t* count_out, int reset);
+
+/* S2CellUnion::Normalize (s2cell_union.cc:171-199) on the GPU: sorts, drops duplicates and cells contained in other
+ * cells, and replaces complete sibling quads by their parent until none is left. out has room for m ids;
+ * *count_out (host) receives the number of cells. The _dev form synchronises the stream to report the count. */
+int s2b_cellunion_normalize(const uint64_t* ids, size_t m, uint64_t* out, size_t* count_out);
+int s2b_cellunion_normalize_dev(const uint64_t* ids_dev, size_t m, uint64_t* out_dev, size_t* count_out, void* stream);
+/* S2CellUnion::Contains(S2CellId) and ::Intersects(S2CellId) (s2cell_union.cc:285-309) for a batch of cell ids against
+ * one union (sorted, non-overlapping): out[i] bit0 = contains, bit1 = intersects. */
+int s2b_cellunion_contains_cells(const uint64_t* sorted_ids, size_t m, const uint64_t* ids, size_t n, uint8_t* out);
+int s2b_cellunion_contains_cells_dev(const uint64_t* sorted_ids_dev, size_t m, const uint64_t* ids_dev, size_t n,
+                                     uint8_t* out_dev, void* stream);
 
 /* S2CellUnion::Contains(const S2Point&) (s2cell_union.cc:285-300,564-566): sorted_ids are the union's cell ids
  * (S2CellUnion::cell_ids(): sorted, non-overlapping), out[i] = 1 if the union contains point i. */

@@ -216,6 +216,26 @@ void ref_edge_neighbors(const uint64_t* ids, size_t n, uint64_t* out4) {
   }
 }
 
+// AppendVertexNeighbors(level): out4 (unused = 0) + count.
+void ref_vertex_neighbors(const uint64_t* ids, size_t n, int level, uint64_t* out4, uint8_t* count) {
+  for (size_t i = 0; i < n; ++i) {
+    std::vector<S2CellId> v;
+    S2CellId(ids[i]).AppendVertexNeighbors(level, &v);
+    for (int k = 0; k < 4; ++k) out4[4 * i + k] = k < (int)v.size() ? v[k].id() : 0;
+    count[i] = (uint8_t)v.size();
+  }
+}
+
+// AppendAllNeighbors(nbr_level): first `stride` neighbours (unused = 0) + full count.
+void ref_all_neighbors(const uint64_t* ids, size_t n, int nbr_level, uint64_t* out, size_t stride, uint32_t* count) {
+  for (size_t i = 0; i < n; ++i) {
+    std::vector<S2CellId> v;
+    S2CellId(ids[i]).AppendAllNeighbors(nbr_level, &v);
+    for (size_t k = 0; k < stride; ++k) out[stride * i + k] = k < v.size() ? v[k].id() : 0;
+    count[i] = (uint32_t)v.size();
+  }
+}
+
 void ref_cellid_to_point(const uint64_t* ids, size_t n, double* xyz) {
   for (size_t i = 0; i < n; ++i) {
     S2Point p = S2CellId(ids[i]).ToPoint();
@@ -447,6 +467,14 @@ void ref_cellunion_contains(const uint64_t* ids, size_t m, const double* xyz, si
 }
 
 // S2CellUnion normalisation (sort + merge) of arbitrary ids; returns count written.
+// S2CellUnion::Contains(S2CellId) (bit0) and ::Intersects(S2CellId) (bit1).
+void ref_cellunion_contains_cells(const uint64_t* u, size_t m, const uint64_t* ids, size_t n, uint8_t* out) {
+  std::vector<S2CellId> v(m);
+  for (size_t i = 0; i < m; ++i) v[i] = S2CellId(u[i]);
+  S2CellUnion cu = S2CellUnion::FromVerbatim(std::move(v));
+  for (size_t i = 0; i < n; ++i) out[i] = (uint8_t)((cu.Contains(S2CellId(ids[i])) ? 1 : 0) | (cu.Intersects(S2CellId(ids[i])) ? 2 : 0));
+}
+
 size_t ref_cellunion_normalize(const uint64_t* ids, size_t m, uint64_t* out) {
   std::vector<S2CellId> v(m);
   for (size_t i = 0; i < m; ++i) v[i] = S2CellId(ids[i]);

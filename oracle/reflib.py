@@ -119,6 +119,24 @@ class Ref:
         self.lib.ref_edge_neighbors(_p(ids), _sz(ids.size), _p(out))
         return out
 
+    def vertex_neighbors(self, ids, level):
+        ids = np.ascontiguousarray(ids, np.uint64)
+        out = np.empty((ids.size, 4), np.uint64); cnt = np.empty(ids.size, np.uint8)
+        self.lib.ref_vertex_neighbors(_p(ids), _sz(ids.size), int(level), _p(out), _p(cnt))
+        return out, cnt
+
+    def all_neighbors(self, ids, nbr_level, stride=8):
+        ids = np.ascontiguousarray(ids, np.uint64)
+        out = np.empty((ids.size, stride), np.uint64); cnt = np.empty(ids.size, np.uint32)
+        self.lib.ref_all_neighbors(_p(ids), _sz(ids.size), int(nbr_level), _p(out), _sz(stride), _p(cnt))
+        return out, cnt
+
+    def cellunion_contains_cells(self, union_ids, ids):
+        u = np.ascontiguousarray(union_ids, np.uint64); ids = np.ascontiguousarray(ids, np.uint64)
+        out = np.empty(ids.size, np.uint8)
+        self.lib.ref_cellunion_contains_cells(_p(u), _sz(u.size), _p(ids), _sz(ids.size), _p(out))
+        return (out & 1) != 0, (out & 2) != 0
+
     def from_face_pos_level(self, face, pos, level):
         return int(self.lib.ref_cellid_from_face_pos_level(face, pos, level))
 

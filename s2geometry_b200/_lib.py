@@ -42,6 +42,14 @@ SIGNATURES = {
     "s2b_cellid_to_point_dev": (_i, [_vp, _sz, _vp, _vp]),
     "s2b_cellid_from_token": (_i, [_vp, _vp, _sz, _vp]),
     "s2b_cellid_from_token_dev": (_i, [_vp, _vp, _sz, _vp, _vp]),
+    "s2b_cellid_vertex_neighbors": (_i, [_vp, _sz, _i, _vp, _vp]),
+    "s2b_cellid_vertex_neighbors_dev": (_i, [_vp, _sz, _i, _vp, _vp, _vp]),
+    "s2b_cellid_all_neighbors": (_i, [_vp, _sz, _i, _vp, _sz, _vp]),
+    "s2b_cellid_all_neighbors_dev": (_i, [_vp, _sz, _i, _vp, _sz, _vp, _vp]),
+    "s2b_cellunion_normalize": (_i, [_vp, _sz, _vp, _vp]),
+    "s2b_cellunion_normalize_dev": (_i, [_vp, _sz, _vp, _vp, _vp]),
+    "s2b_cellunion_contains_cells": (_i, [_vp, _sz, _vp, _sz, _vp]),
+    "s2b_cellunion_contains_cells_dev": (_i, [_vp, _sz, _vp, _sz, _vp, _vp]),
     "s2b_index_build": (_i, [_i, _vp, _vp, _vp, _vp, _i, _vp]),
     "s2b_built_index_flat": (_i, [_vp, _vp, _vp]),
     "s2b_built_index_destroy": (None, [_vp]),

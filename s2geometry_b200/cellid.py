@@ -224,6 +224,77 @@ def edge_neighbors(ids):
     return out
 
 
+def vertex_neighbors(ids, level):
+    """S2CellId::AppendVertexNeighbors(level) element-wise -> ((N,4) ids, (N,) counts): 3 or 4 cells of `level` around the
+    closest vertex of parent(level), reference order, unused slots 0. Requires level < level(id)."""
+    lib = _lib.load()
+    if _is_tensor(ids):
+        ids = _tensor_in(ids, torch.int64, 0)
+        out = torch.empty((ids.numel(), 4), dtype=torch.int64, device=ids.device)
+        cnt = torch.empty(ids.numel(), dtype=torch.uint8, device=ids.device)
+        with torch.cuda.device(ids.device):
+            _lib.check(lib.s2b_cellid_vertex_neighbors_dev(_ptr(ids), ids.numel(), int(level), _ptr(out), _ptr(cnt), _stream()))
+        return out, cnt
+    ids = _np_in(ids, np.uint64, 0)
+    out = np.empty((ids.size, 4), dtype=np.uint64)
+    cnt = np.empty(ids.size, dtype=np.uint8)
+    _lib.check(lib.s2b_cellid_vertex_neighbors(_ptr(ids), ids.size, int(level), _ptr(out), _ptr(cnt)))
+    return out, cnt
+
+
+def all_neighbors(ids, nbr_level, stride=None):
+    """S2CellId::AppendAllNeighbors(nbr_level) element-wise -> ((N,stride) ids, (N,) counts), reference order, unused slots
+    0. stride defaults to 8 (enough when nbr_level equals every id's level); counts[i] = 4 * 2^(nbr_level - level) + 4."""
+    lib = _lib.load()
+    stride = 8 if stride is None else int(stride)
+    if _is_tensor(ids):
+        ids = _tensor_in(ids, torch.int64, 0)
+        out = torch.empty((ids.numel(), stride), dtype=torch.int64, device=ids.device)
+        cnt = torch.empty(ids.numel(), dtype=torch.int32, device=ids.device)
+        with torch.cuda.device(ids.device):
+            _lib.check(lib.s2b_cellid_all_neighbors_dev(_ptr(ids), ids.numel(), int(nbr_level), _ptr(out), stride, _ptr(cnt), _stream()))
+        return out, cnt
+    ids = _np_in(ids, np.uint64, 0)
+    out = np.empty((ids.size, stride), dtype=np.uint64)
+    cnt = np.empty(ids.size, dtype=np.uint32)
+    _lib.check(lib.s2b_cellid_all_neighbors(_ptr(ids), ids.size, int(nbr_level), _ptr(out), stride, _ptr(cnt)))
+    return out, cnt
+
+
+def cell_union_normalize(ids):
+    """S2CellUnion::Normalize on the GPU: sorted, non-overlapping, sibling quads merged."""
+    lib = _lib.load()
+    import ctypes
+    count = ctypes.c_size_t(0)
+    if _is_tensor(ids):
+        ids = _tensor_in(ids, torch.int64, 0)
+        out = torch.empty(ids.numel(), dtype=torch.int64, device=ids.device)
+        with torch.cuda.device(ids.device):
+            _lib.check(lib.s2b_cellunion_normalize_dev(_ptr(ids), ids.numel(), _ptr(out), ctypes.byref(count), _stream()))
+        return out[: count.value]
+    ids = _np_in(ids, np.uint64, 0)
+    out = np.empty(ids.size, dtype=np.uint64)
+    _lib.check(lib.s2b_cellunion_normalize(_ptr(ids), ids.size, _ptr(out), ctypes.byref(count)))
+    return out[: count.value].copy()
+
+
+def cell_union_contains_cells(sorted_ids, ids):
+    """S2CellUnion::Contains(S2CellId) / Intersects(S2CellId) for a batch of ids -> (contains, intersects) bool arrays."""
+    lib = _lib.load()
+    if _is_tensor(ids):
+        ids = _tensor_in(ids, torch.int64, 0)
+        u = _tensor_in(sorted_ids, torch.int64, 0)
+        out = torch.empty(ids.numel(), dtype=torch.uint8, device=ids.device)
+        with torch.cuda.device(ids.device):
+            _lib.check(lib.s2b_cellunion_contains_cells_dev(_ptr(u), u.numel(), _ptr(ids), ids.numel(), _ptr(out), _stream()))
+        return (out & 1) != 0, (out & 2) != 0
+    ids = _np_in(ids, np.uint64, 0)
+    u = _np_in(sorted_ids, np.uint64, 0)
+    out = np.empty(ids.size, dtype=np.uint8)
+    _lib.check(lib.s2b_cellunion_contains_cells(_ptr(u), u.size, _ptr(ids), ids.size, _ptr(out)))
+    return (out & 1) != 0, (out & 2) != 0
+
+
 def from_token(tokens, lengths):
     """S2CellId::FromToken element-wise: tokens (N,16) uint8 slots + lengths (N,) uint8 -> ids (0 for malformed tokens)."""
     lib = _lib.load()
