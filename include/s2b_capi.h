@@ -117,6 +117,11 @@ int s2b_cellid_to_token_dev(const uint64_t* ids_dev, size_t n, char* tokens16_ou
  * vector of each cell's centre, bit-exact with the reference. xyz_out = n x 3 doubles. */
 int s2b_cellid_to_point(const uint64_t* ids, size_t n, double* xyz_out);
 int s2b_cellid_to_point_dev(const uint64_t* ids_dev, size_t n, double* xyz_out_dev, void* stream);
+/* S2CellId::ToLatLng (s2cell_id.cc:381 = S2LatLng(ToPointRaw()), s2latlng.h:235-250): (lat, lng) in radians, 2 doubles
+ * per id. Floating-point output: atan2 comes from the CUDA math library (<= 2 ulp), the reference's from the host libm,
+ * so results agree to a few ulp rather than bit for bit (ids and booleans elsewhere in this API are exact). */
+int s2b_cellid_to_latlng(const uint64_t* ids, size_t n, double* latlng_rad_out);
+int s2b_cellid_to_latlng_dev(const uint64_t* ids_dev, size_t n, double* latlng_rad_out_dev, void* stream);
 /* S2CellId::GetEdgeNeighbors (s2cell_id.cc:499-512): the four edge neighbours (down, right, up, left) of every VALID
  * cell id, at the cell's own level; neighbors4_out = n x 4 ids. Neighbours across a cube-face edge are found with
  * FromFaceIJWrap (:458-489). */

@@ -216,6 +216,13 @@ void ref_edge_neighbors(const uint64_t* ids, size_t n, uint64_t* out4) {
   }
 }
 
+void ref_cellid_to_latlng(const uint64_t* ids, size_t n, double* latlng) {
+  for (size_t i = 0; i < n; ++i) {
+    S2LatLng ll = S2CellId(ids[i]).ToLatLng();
+    latlng[2 * i] = ll.lat().radians(); latlng[2 * i + 1] = ll.lng().radians();
+  }
+}
+
 // AppendVertexNeighbors(level): out4 (unused = 0) + count.
 void ref_vertex_neighbors(const uint64_t* ids, size_t n, int level, uint64_t* out4, uint8_t* count) {
   for (size_t i = 0; i < n; ++i) {

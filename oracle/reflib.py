@@ -119,6 +119,12 @@ class Ref:
         self.lib.ref_edge_neighbors(_p(ids), _sz(ids.size), _p(out))
         return out
 
+    def cellid_to_latlng(self, ids):
+        ids = np.ascontiguousarray(ids, np.uint64)
+        out = np.empty((ids.size, 2), np.float64)
+        self.lib.ref_cellid_to_latlng(_p(ids), _sz(ids.size), _p(out))
+        return out
+
     def vertex_neighbors(self, ids, level):
         ids = np.ascontiguousarray(ids, np.uint64)
         out = np.empty((ids.size, 4), np.uint64); cnt = np.empty(ids.size, np.uint8)

@@ -209,6 +209,21 @@ def to_point(ids):
     return out
 
 
+def to_lat_lng(ids):
+    """S2CellId::ToLatLng element-wise -> (N,2) float64 radians (lat, lng); agrees with the reference to a few ulp."""
+    lib = _lib.load()
+    if _is_tensor(ids):
+        ids = _tensor_in(ids, torch.int64, 0)
+        out = torch.empty((ids.numel(), 2), dtype=torch.float64, device=ids.device)
+        with torch.cuda.device(ids.device):
+            _lib.check(lib.s2b_cellid_to_latlng_dev(_ptr(ids), ids.numel(), _ptr(out), _stream()))
+        return out
+    ids = _np_in(ids, np.uint64, 0)
+    out = np.empty((ids.size, 2), dtype=np.float64)
+    _lib.check(lib.s2b_cellid_to_latlng(_ptr(ids), ids.size, _ptr(out)))
+    return out
+
+
 def edge_neighbors(ids):
     """S2CellId::GetEdgeNeighbors element-wise -> (N,4) ids (down, right, up, left) at each cell's own level."""
     lib = _lib.load()

@@ -363,6 +363,22 @@ int s2b_cellid_to_point_dev(const uint64_t* ids_dev, size_t n, double* xyz_out_d
   cudaError_t e = launch_to_point(ids_dev, n, xyz_out_dev, (cudaStream_t)stream);
   return e == cudaSuccess ? S2B_OK : cuda_fail(e, "to_point launch");
 }
+int s2b_cellid_to_latlng(const uint64_t* ids, size_t n, double* latlng_rad_out) {
+  if (n == 0) return S2B_OK;
+  if (!ids || !latlng_rad_out) return set_error(S2B_EINVAL, "null pointer");
+  OutSpec outs[1] = {{latlng_rad_out, 16, 1}};
+  return run_pipelined(ids, 8, n, outs, 1, [&](const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
+    cudaError_t e = launch_to_latlng((const uint64_t*)in_dev, cnt, (double*)out_dev[0], st);
+    return e == cudaSuccess ? S2B_OK : cuda_fail(e, "to_latlng launch");
+  });
+}
+int s2b_cellid_to_latlng_dev(const uint64_t* ids_dev, size_t n, double* latlng_rad_out_dev, void* stream) {
+  if (n == 0) return S2B_OK;
+  if (!ids_dev || !latlng_rad_out_dev) return set_error(S2B_EINVAL, "null pointer");
+  if ((uintptr_t)latlng_rad_out_dev % 16) return set_error(S2B_EINVAL, "latlng_rad_out_dev must be 16-byte aligned");
+  cudaError_t e = launch_to_latlng(ids_dev, n, latlng_rad_out_dev, (cudaStream_t)stream);
+  return e == cudaSuccess ? S2B_OK : cuda_fail(e, "to_latlng launch");
+}
 int s2b_cellid_from_token_dev(const char* tokens16_dev, const uint8_t* len_dev, size_t n, uint64_t* ids_out_dev, void* stream) {
   if (n == 0) return S2B_OK;
   if (!tokens16_dev || !len_dev || !ids_out_dev) return set_error(S2B_EINVAL, "null pointer");

@@ -182,7 +182,7 @@ S2B_HD P3 face_uv_to_xyz(int face, double u, double v) {
 
 // S2CellId::ToPoint: GetCenterSiTi (s2cell_id.h:555-581) -> FaceSiTitoXYZ (s2coords.cc:68-72) -> Normalize.
 template <class TableT>
-S2B_HD P3 cellid_to_point(uint64_t id, const TableT* ij) {
+S2B_HD P3 cellid_to_point_raw(uint64_t id, const TableT* ij) {   // S2CellId::ToPointRaw: not normalised
   int i, j;
   int face = cellid_to_face_ij(id, ij, &i, &j);
   bool is_leaf = (id & 1) != 0;
@@ -190,8 +190,10 @@ S2B_HD P3 cellid_to_point(uint64_t id, const TableT* ij) {
   unsigned si = (unsigned)(2 * i + delta), ti = (unsigned)(2 * j + delta);
   double u = st_to_uv((1.0 / 2147483648.0) * si);
   double v = st_to_uv((1.0 / 2147483648.0) * ti);
-  return normalize(face_uv_to_xyz(face, u, v));
+  return face_uv_to_xyz(face, u, v);
 }
+template <class TableT>
+S2B_HD P3 cellid_to_point(uint64_t id, const TableT* ij) { return normalize(cellid_to_point_raw(id, ij)); }
 
 // ---------------------------------------------------------------------------------------------------
 // Cell id algebra (s2cell_id.h:583-668).

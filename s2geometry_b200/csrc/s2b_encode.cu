@@ -282,6 +282,29 @@ __global__ void __launch_bounds__(kThreads) to_point_kernel(const uint64_t* __re
   }
 }
 
+// S2CellId::ToLatLng = S2LatLng(ToPointRaw()) (s2cell_id.cc:381, s2latlng.h:235-250): (lat, lng) radians. atan2 is the CUDA
+// math library's (documented max error 2 ulp); the reference uses the host libm, so this output is equal within a few ulp,
+// not bit for bit (it is a floating-point result, not an id).
+__global__ void __launch_bounds__(kThreads) to_latlng_kernel(const uint64_t* __restrict__ ids, size_t n, double* __restrict__ latlng) {
+  __shared__ uint16_t s_ij[1024];
+  for (int k = threadIdx.x; k < 1024; k += kThreads) s_ij[k] = g_hilbert.ij[k];
+  __syncthreads();
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    const P3 p = cellid_to_point_raw(__ldcs(ids + i), s_ij);
+    const double lat = atan2(p.z + 0.0, sqrt(p.x * p.x + p.y * p.y));
+    const double lng = atan2(p.y + 0.0, p.x + 0.0);
+    __stcs((double2*)(latlng + 2 * i), make_double2(lat, lng));
+  }
+}
+
+cudaError_t launch_to_latlng(const uint64_t* ids, size_t n, double* latlng, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  to_latlng_kernel<<<grid_for(n, (const void*)to_latlng_kernel), kThreads, 0, st>>>(ids, n, latlng);
+  count_launch();
+  return cudaGetLastError();
+}
+
 // S2CellId::GetEdgeNeighbors (s2cell_id.cc:499-512): out[4*i + k], k = down, right, up, left.
 __global__ void __launch_bounds__(kThreads) edge_neighbors_kernel(const uint64_t* __restrict__ ids, size_t n, uint64_t* __restrict__ out) {
   __shared__ uint16_t s_pos[1024], s_ij[1024];

@@ -28,6 +28,7 @@ cudaError_t launch_parent(const uint64_t* ids_dev, size_t n, int level, uint64_t
 cudaError_t launch_filter_deviation(InputKind kind, const double* in_dev, size_t n, unsigned long long* out2_dev, cudaStream_t stream);
 cudaError_t launch_edge_neighbors(const uint64_t* ids_dev, size_t n, uint64_t* out4_dev, cudaStream_t stream);
 cudaError_t launch_to_point(const uint64_t* ids_dev, size_t n, double* xyz_dev, cudaStream_t stream);
+cudaError_t launch_to_latlng(const uint64_t* ids_dev, size_t n, double* latlng_dev, cudaStream_t stream);
 cudaError_t launch_from_token(const char* tokens16_dev, const uint8_t* len_dev, size_t n, uint64_t* ids_dev, cudaStream_t stream);
 cudaError_t launch_to_token(const uint64_t* ids_dev, size_t n, char* tokens16_dev, uint8_t* len_dev, cudaStream_t stream);
 

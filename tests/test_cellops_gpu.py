@@ -157,3 +157,24 @@ def test_cell_union_contains_cells_matches_reference(torch_cuda, ref):
             assert wc.any() and (wi & ~wc).any()
             dc, di = cellid.cell_union_contains_cells(torch.from_numpy(u.view(np.int64)).cuda(), torch.from_numpy(q.view(np.int64)).cuda())
             assert (dc.cpu().numpy() == wc).all() and (di.cpu().numpy() == wi).all()
+
+
+def test_to_lat_lng_within_ulps_of_reference(torch_cuda, ref):
+    """S2CellId::ToLatLng. Floating-point output through atan2: CUDA's is documented <= 2 ulp, glibc's < 1 ulp, so the
+    stated tolerance is 4 ulp (of the result, with pi/2 resp. pi as the scale near zero crossings of the other argument)."""
+    torch = torch_cuda
+    from s2geometry_b200 import cellid
+    from tests.test_encode_cpu import random_ids_all_levels
+    ids = random_ids_all_levels(ref, 1_000_000, 41)
+    want = ref.cellid_to_latlng(ids)
+    got = cellid.to_lat_lng(ids)
+    ulp = np.spacing(np.maximum(np.abs(want), 1e-300))
+    assert (np.abs(got - want) <= 4 * ulp).all()
+    assert (got == want).mean() > 0.9                                  # and most are identical
+    assert (np.signbit(got) == np.signbit(want)).all()
+    d = cellid.to_lat_lng(torch.from_numpy(ids.view(np.int64)).cuda()).cpu().numpy()
+    assert (d == got).all()
+    # round trip: the cell of the returned lat/lng at the id's level is the id itself
+    lsb = ids & (~ids + np.uint64(1))
+    leaf = cellid.from_lat_lng(got)
+    assert (((leaf & (~lsb + np.uint64(1))) | lsb) == ids).mean() > 0.999   # (centres of coarse cells sit on leaf boundaries)

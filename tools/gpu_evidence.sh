@@ -12,5 +12,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 $CMD --no-pip --no-join > gpurun_out/plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:encode_kernel -s 3 -c 1 -o gpurun_out/prof_encode_final $CMD --no-pip --no-join > gpurun_out/ncu_full.log 2>&1
 python tools/prof_query.py > gpurun_out/plain3.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"locate|process_kernel" -s 11 -c 11 -o gpurun_out/prof_query_final python tools/prof_query.py > gpurun_out/ncu_full2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"locate|process_kernel|cell_scatter" -s 11 -c 11 -o gpurun_out/prof_query_final python tools/prof_query.py > gpurun_out/ncu_full2.log 2>&1
 ls -la gpurun_out | tail -6
