@@ -259,6 +259,32 @@ int s2b_diag_force_exact_locate(int on);
  * There is no CPU stage behind it: this is purely a statistic. */
 int s2b_exact_stage_count(uint64_t* count_out, int reset);
 
+/* --------------------------------------------------------------------------------------------------
+ * S2PointIndex + S2ClosestPointQuery, batch form (s2point_index.h, s2closest_point_query.h; the radius join of
+ * doc/examples/point_index.cc:25-52). The index holds m points with data = their position in `xyz`
+ * (S2PointIndex<int>::Add(xyz[i], i)), sorted by leaf cell id on the current device.
+ * Distances are S1ChordAngle values passed as their squared chord length: max_length2 =
+ * S1ChordAngle(S1Angle::Radians(r)).length2() = (2 sin(r/2))^2 (s1chord_angle.h:339-350); INFINITY = no limit.
+ * As in the reference, max_distance is exclusive (distance < limit).
+ *   s2b_closest_points_count: counts_out[i] = FindClosestPoints(PointTarget(targets[i])).size() with
+ *                             options.max_distance = the limit and unlimited max_results
+ *   s2b_closest_point:        FindClosestPoint(PointTarget(targets[i])): data_out[i] = data of the nearest index point
+ *                             within the limit or -1, length2_out[i] (nullable) = its S1ChordAngle length2 (INFINITY if
+ *                             none). Among equidistant points the smallest data value is returned.
+ * Results are exact: the distance of every candidate is S1ChordAngle(point, target) evaluated as the reference does.
+ * -------------------------------------------------------------------------------------------------- */
+typedef struct S2bPointIndex S2bPointIndex;
+int s2b_point_index_create(const double* xyz, size_t m, S2bPointIndex** index_out);
+void s2b_point_index_destroy(S2bPointIndex* index);
+size_t s2b_point_index_size(const S2bPointIndex* index);
+int s2b_closest_points_count(const S2bPointIndex* index, const double* targets_xyz, size_t n, double max_length2, uint32_t* counts_out);
+int s2b_closest_points_count_dev(const S2bPointIndex* index, const double* targets_xyz_dev, size_t n, double max_length2,
+                                 uint32_t* counts_out_dev, void* stream);
+int s2b_closest_point(const S2bPointIndex* index, const double* targets_xyz, size_t n, double max_length2, int32_t* data_out,
+                      double* length2_out);
+int s2b_closest_point_dev(const S2bPointIndex* index, const double* targets_xyz_dev, size_t n, double max_length2,
+                          int32_t* data_out_dev, double* length2_out_dev, void* stream);
+
 /* S2CellUnion::Normalize (s2cell_union.cc:171-199) on the GPU: sorts, drops duplicates and cells contained in other
  * cells, and replaces complete sibling quads by their parent until none is left. out has room for m ids;
  * *count_out (host) receives the number of cells. The _dev form synchronises the stream to report the count. */

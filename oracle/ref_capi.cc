@@ -24,6 +24,8 @@
 #include "s2/s2cap.h"
 #include "s2/s2cell_id.h"
 #include "s2/s2cell_union.h"
+#include "s2/s2closest_point_query.h"
+#include "s2/s2point_index.h"
 #include "s2/s2contains_point_query.h"
 #include "s2/s2edge_crosser.h"
 #include "s2/s2edge_crossings.h"
@@ -474,6 +476,42 @@ void ref_cellunion_contains(const uint64_t* ids, size_t m, const double* xyz, si
 }
 
 // S2CellUnion normalisation (sort + merge) of arbitrary ids; returns count written.
+// ---------------------------------------------------------------- S2PointIndex / S2ClosestPointQuery
+struct RefPointIndex { S2PointIndex<int> index; };
+void* ref_point_index_create(const double* xyz, size_t m) {
+  auto* r = new RefPointIndex();
+  for (size_t i = 0; i < m; ++i) r->index.Add(P(xyz + 3 * i), (int)i);
+  return r;
+}
+void ref_point_index_destroy(void* h) { delete (RefPointIndex*)h; }
+// FindClosestPoints(PointTarget) with options.max_distance = S1Angle::Radians(r) (negative r = no limit): result size.
+void ref_closest_points_count(void* h, const double* targets, size_t n, double max_distance_rad, uint32_t* counts, int threads) {
+  auto* index = &((RefPointIndex*)h)->index;
+  ParallelFor(n, threads, [&](size_t b, size_t e, int) {
+    S2ClosestPointQuery<int> query(index);
+    if (max_distance_rad >= 0) query.mutable_options()->set_max_distance(S1Angle::Radians(max_distance_rad));
+    for (size_t i = b; i < e; ++i) {
+      S2ClosestPointQuery<int>::PointTarget target(P(targets + 3 * i));
+      counts[i] = (uint32_t)query.FindClosestPoints(&target).size();
+    }
+  });
+}
+// FindClosestPoint(PointTarget): data (-1 if none) and the S1ChordAngle length2 of the result.
+void ref_closest_point(void* h, const double* targets, size_t n, double max_distance_rad, int32_t* data, double* length2, int threads) {
+  auto* index = &((RefPointIndex*)h)->index;
+  ParallelFor(n, threads, [&](size_t b, size_t e, int) {
+    S2ClosestPointQuery<int> query(index);
+    if (max_distance_rad >= 0) query.mutable_options()->set_max_distance(S1Angle::Radians(max_distance_rad));
+    for (size_t i = b; i < e; ++i) {
+      S2ClosestPointQuery<int>::PointTarget target(P(targets + 3 * i));
+      auto r = query.FindClosestPoint(&target);
+      data[i] = r.is_empty() ? -1 : r.data();
+      length2[i] = r.is_empty() ? HUGE_VAL : r.distance().length2();
+    }
+  });
+}
+double ref_chord_length2(double angle_rad) { return S1ChordAngle(S1Angle::Radians(angle_rad)).length2(); }
+
 // S2CellUnion::Contains(S2CellId) (bit0) and ::Intersects(S2CellId) (bit1).
 void ref_cellunion_contains_cells(const uint64_t* u, size_t m, const uint64_t* ids, size_t n, uint8_t* out) {
   std::vector<S2CellId> v(m);

@@ -172,6 +172,13 @@ class Ref:
         return out
 
     # ---- index
+    def point_index(self, points):
+        return RefPointIndex(self, points)
+
+    def chord_length2(self, angle_rad):
+        self.lib.ref_chord_length2.restype = ctypes.c_double
+        return float(self.lib.ref_chord_length2(ctypes.c_double(angle_rad)))
+
     def index_create(self, soup, max_edges_per_cell=0):
         return RefIndex(self, soup, max_edges_per_cell)
 
@@ -194,6 +201,36 @@ class Ref:
         k = self.lib.ref_cover_cap(_p(center), ctypes.c_double(radius_rad), max_cells, min_level, max_level, _p(out), _sz(out.size))
         assert k <= out.size
         return out[:k].copy()
+
+
+class RefPointIndex:
+    """S2PointIndex<int> with data = position, queried through S2ClosestPointQuery<int> (the reference's own)."""
+
+    def __init__(self, ref, points):
+        self.lib = ref.lib
+        self.lib.ref_point_index_create.restype = _vp
+        pts = np.ascontiguousarray(points, np.float64).reshape(-1, 3)
+        self.h = self.lib.ref_point_index_create(_p(pts), _sz(len(pts)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.ref_point_index_destroy(_vp(self.h))
+                self.h = None
+        except Exception:
+            pass
+
+    def count(self, targets, max_distance_rad=-1.0, threads=0):
+        t = np.ascontiguousarray(targets, np.float64).reshape(-1, 3)
+        out = np.zeros(len(t), np.uint32)
+        self.lib.ref_closest_points_count(_vp(self.h), _p(t), _sz(len(t)), ctypes.c_double(max_distance_rad), _p(out), int(threads))
+        return out
+
+    def closest(self, targets, max_distance_rad=-1.0, threads=0):
+        t = np.ascontiguousarray(targets, np.float64).reshape(-1, 3)
+        data = np.zeros(len(t), np.int32); l2 = np.zeros(len(t), np.float64)
+        self.lib.ref_closest_point(_vp(self.h), _p(t), _sz(len(t)), ctypes.c_double(max_distance_rad), _p(data), _p(l2), int(threads))
+        return data, l2
 
 
 class RefIndex:

@@ -52,6 +52,13 @@ SIGNATURES = {
     "s2b_cellunion_normalize_dev": (_i, [_vp, _sz, _vp, _vp, _vp]),
     "s2b_cellunion_contains_cells": (_i, [_vp, _sz, _vp, _sz, _vp]),
     "s2b_cellunion_contains_cells_dev": (_i, [_vp, _sz, _vp, _sz, _vp, _vp]),
+    "s2b_point_index_create": (_i, [_vp, _sz, _vp]),
+    "s2b_point_index_destroy": (None, [_vp]),
+    "s2b_point_index_size": (_sz, [_vp]),
+    "s2b_closest_points_count": (_i, [_vp, _vp, _sz, ctypes.c_double, _vp]),
+    "s2b_closest_points_count_dev": (_i, [_vp, _vp, _sz, ctypes.c_double, _vp, _vp]),
+    "s2b_closest_point": (_i, [_vp, _vp, _sz, ctypes.c_double, _vp, _vp]),
+    "s2b_closest_point_dev": (_i, [_vp, _vp, _sz, ctypes.c_double, _vp, _vp, _vp]),
     "s2b_index_build": (_i, [_i, _vp, _vp, _vp, _vp, _i, _vp]),
     "s2b_built_index_flat": (_i, [_vp, _vp, _vp]),
     "s2b_built_index_destroy": (None, [_vp]),

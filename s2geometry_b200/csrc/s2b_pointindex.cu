@@ -1,0 +1,374 @@
+// s2b_pointindex.cu — batched S2ClosestPointQuery over an S2PointIndex (the nearest-point /
+// radius joins callers pair with point-in-polygon; doc/examples/point_index.cc:25-52 is exactly the radius join).
+//   S2PointIndex<Data>::Add(point, data)                       s2point_index.h       (index = points keyed by leaf cell id)
+//   S2ClosestPointQuery<Data>::FindClosestPoints(PointTarget)   s2closest_point_query.h, s2closest_point_query_base.h
+//     with options.max_distance (exclusive) / max_results = 1 (FindClosestPoint)
+//   distance = S1ChordAngle(p, target) = min(4, |p - target|^2)  s1chord_angle.h:352-359, compared as length2
+//   candidate cells = S2Cap::GetCellUnionBound                  s2cap.cc:202-223 (4 vertex neighbours at the level whose
+//                                                               cells are at least twice as wide as the cap radius)
+// The result of a query is a pure function of the pairwise chord distances, so any search order gives the reference's
+// answer; here the index is a cell-id-sorted point array on the device and each target scans the <= 4 id ranges of its
+// covering. Exactness: the candidate test is the reference's own expression, evaluated in the same order, no FMA.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <cmath>
+#include <new>
+
+#include "../../include/s2b_capi.h"
+#include "s2b_core.cuh"
+#include "s2b_hilbert.h"
+#include "s2b_internal.h"
+
+struct S2bPointIndex {
+  int device = 0;
+  size_t m = 0;
+  void* blob = nullptr;
+  const uint64_t* ids = nullptr;     // sorted leaf cell ids
+  const double* pts = nullptr;       // the points in that order (3 doubles each)
+  const int32_t* data = nullptr;     // original position of each sorted point (the index's "data")
+};
+
+namespace s2b {
+
+int set_error(int code, const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+namespace {
+
+constexpr int kThreads = 256;
+__device__ const HilbertTables g_hilbert_pi = kHilbert;
+
+int grid_for_pi(size_t n, const void* kernel) {
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
+  if (per_sm < 1) per_sm = 1;
+  size_t want = (n + kThreads - 1) / kThreads;
+  size_t cap = (size_t)sm_count() * per_sm;
+  return (int)(want < cap ? (want ? want : 1) : cap);
+}
+
+__global__ void iota_kernel(int32_t* v, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) v[i] = (int32_t)i;
+}
+
+__global__ void gather_points_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ order, size_t n, double* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double* q = xyz + 3 * (size_t)order[i];
+    out[3 * i] = q[0]; out[3 * i + 1] = q[1]; out[3 * i + 2] = q[2];
+  }
+}
+
+struct IndexView { const uint64_t* ids; const double* pts; const int32_t* data; uint32_t m; };
+
+// [first, last) of the sorted ids inside cell `c` (an id at `level`)
+__device__ __forceinline__ void cell_range(const IndexView& ix, uint64_t c, uint32_t* first, uint32_t* last) {
+  const uint64_t lo_id = cellid_range_min(c), hi_id = cellid_range_max(c);
+  uint32_t lo = 0, hi = ix.m;
+  while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (ix.ids[mid] < lo_id) lo = mid + 1; else hi = mid; }
+  *first = lo;
+  hi = ix.m;
+  while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (ix.ids[mid] <= hi_id) lo = mid + 1; else hi = mid; }
+  *last = lo;
+}
+
+// The covering of S2Cap::GetCellUnionBound for a cap centred on the leaf cell (face, i, j): AppendVertexNeighbors(level)
+// (s2cell_id.cc:514-556). level < 0: the six face cells. Returns the number of cells (3, 4 or 6).
+__device__ __forceinline__ int covering_cells(int face, int i, int j, int level, const uint16_t* pos, uint64_t cells[6]) {
+  if (level < 0) {
+    for (int f = 0; f < 6; ++f) cells[f] = ((uint64_t)f << 61) | (1ull << 60);
+    return 6;
+  }
+  const int kMaxSize = 1 << 30;
+  const int halfsize = 1 << (30 - (level + 1));
+  const int size = halfsize << 1;
+  bool isame, jsame;
+  int ioffset, joffset;
+  if (i & halfsize) { ioffset = size; isame = (i + size) < kMaxSize; } else { ioffset = -size; isame = (i - size) >= 0; }
+  if (j & halfsize) { joffset = size; jsame = (j + size) < kMaxSize; } else { joffset = -size; jsame = (j - size) >= 0; }
+  auto at = [&](int ii, int jj, bool same) {
+    return cellid_parent(same ? from_face_ij(face, (uint32_t)ii, (uint32_t)jj, pos) : from_face_ij_wrap(face, ii, jj, pos), level);
+  };
+  cells[0] = at(i, j, true);
+  cells[1] = at(i + ioffset, j, isame);
+  cells[2] = at(i, j + joffset, jsame);
+  int n = 3;
+  if (isame || jsame) cells[n++] = at(i + ioffset, j + joffset, isame && jsame);
+  return n;
+}
+
+__device__ __forceinline__ double chord_length2(const P3& p, const P3& q) {   // S1ChordAngle(p, q).length2()
+  const double d = norm2(sub(p, q));
+  return d < 4.0 ? d : 4.0;
+}
+
+// counts[t] = |{ index points with S1ChordAngle(point, target_t) < limit }|. kWarp: one warp per target (lanes stride
+// over the candidates, coalesced) for coverings holding many points; else one thread per target.
+template <bool kWarp>
+__global__ void __launch_bounds__(kThreads)
+radius_count_kernel(const IndexView ix, const double* __restrict__ targets, size_t n, int level, double limit2, uint32_t* __restrict__ counts) {
+  __shared__ uint16_t s_pos[1024];
+  for (int k = threadIdx.x; k < 1024; k += kThreads) s_pos[k] = g_hilbert_pi.pos[k];
+  __syncthreads();
+  const unsigned lane = threadIdx.x & 31u;
+  const size_t tid = (size_t)blockIdx.x * kThreads + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * kThreads / (kWarp ? 32 : 1);
+  for (size_t t = kWarp ? tid / 32 : tid; t < n; t += stride) {
+    const double* tq = targets + 3 * t;
+    const P3 q{tq[0], tq[1], tq[2]};
+    double fi, fj;
+    const int face = point_to_face_fij(q, &fi, &fj);
+    uint64_t cells[6];
+    const int nc = covering_cells(face, (int)fij_to_ij(fi), (int)fij_to_ij(fj), level, s_pos, cells);
+    uint32_t cnt = 0;
+    for (int k = 0; k < nc; ++k) {
+      uint32_t first, last;
+      cell_range(ix, cells[k], &first, &last);
+      for (uint32_t c = first + (kWarp ? lane : 0u); c < last; c += (kWarp ? 32u : 1u)) {
+        const double* pp = ix.pts + 3 * (size_t)c;
+        if (chord_length2(P3{pp[0], pp[1], pp[2]}, q) < limit2) ++cnt;
+      }
+    }
+    if (kWarp) {
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      if (lane == 0) counts[t] = cnt;
+    } else {
+      counts[t] = cnt;
+    }
+  }
+}
+
+// FindClosestPoint: the nearest index point within `limit2` (exclusive), or data = -1. The search starts at
+// `start_level` and coarsens: a best distance found inside the covering of level L is final as soon as it is below
+// the cap radius that covering is guaranteed to contain (the minimum width of a level L+1 cell); at level -1 the
+// covering is the whole sphere. Ties in distance go to the smaller data value.
+__global__ void __launch_bounds__(kThreads)
+closest_point_kernel(const IndexView ix, const double* __restrict__ targets, size_t n, int start_level, double limit2,
+                     const double* __restrict__ covered_length2 /* [31]: entry L+1 = chord^2 of the cap radius covered at level L */,
+                     int32_t* __restrict__ data_out, double* __restrict__ length2_out) {
+  __shared__ uint16_t s_pos[1024];
+  __shared__ double s_cov[31];
+  for (int k = threadIdx.x; k < 1024; k += kThreads) s_pos[k] = g_hilbert_pi.pos[k];
+  if (threadIdx.x < 31) s_cov[threadIdx.x] = covered_length2[threadIdx.x];
+  __syncthreads();
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < n; t += stride) {
+    const double* tq = targets + 3 * t;
+    const P3 q{tq[0], tq[1], tq[2]};
+    double fi, fj;
+    const int face = point_to_face_fij(q, &fi, &fj);
+    const int i = (int)fij_to_ij(fi), j = (int)fij_to_ij(fj);
+    double best = limit2;
+    int32_t best_data = -1;
+    for (int level = start_level;; --level) {
+      uint64_t cells[6];
+      const int nc = covering_cells(face, i, j, level, s_pos, cells);
+      best = limit2;
+      best_data = -1;
+      for (int k = 0; k < nc; ++k) {
+        uint32_t first, last;
+        cell_range(ix, cells[k], &first, &last);
+        for (uint32_t c = first; c < last; ++c) {
+          const double* pp = ix.pts + 3 * (size_t)c;
+          const double d = chord_length2(P3{pp[0], pp[1], pp[2]}, q);
+          const int32_t dv = ix.data[c];
+          if (d < best || (d == best && best_data >= 0 && dv < best_data)) { best = d; best_data = dv; }
+        }
+      }
+      if (level < 0) break;                                   // whole sphere scanned
+      const double covered = s_cov[level + 1];
+      if (best_data >= 0 && best < covered) break;            // nothing outside the covering can be closer
+      if (covered >= limit2) break;                           // everything within the distance limit was covered
+    }
+    data_out[t] = best_data;
+    if (length2_out) length2_out[t] = best_data >= 0 ? best : HUGE_VAL;
+  }
+}
+
+// kMinWidth (quadratic projection, s2metrics.cc:54-58) and Metric::GetLevelForMinValue (s2metrics.h:185-200).
+const double kMinWidthDeriv = 2 * std::sqrt(2.0) / 3;
+int level_for_min_width(double value) {
+  if (!(value > 0)) return 30;
+  int level = std::ilogb(kMinWidthDeriv / value);
+  return level < 0 ? 0 : (level > 30 ? 30 : level);
+}
+// angle of a chord^2, slightly inflated so that the covering level is chosen conservatively
+double angle_of_length2(double l2) {
+  if (l2 >= 4.0) return M_PI;
+  return 2 * std::asin(0.5 * std::sqrt(l2)) * (1 + 1e-9) + 1e-300;
+}
+
+}  // namespace
+}  // namespace s2b
+
+using namespace s2b;
+
+extern "C" {
+
+int s2b_point_index_create(const double* xyz, size_t m, S2bPointIndex** out) {
+  if (!out) return set_error(S2B_EINVAL, "null output");
+  *out = nullptr;
+  if (m && !xyz) return set_error(S2B_EINVAL, "null points");
+  if (m > 0x7FFFFFF0ull) return set_error(S2B_EINVAL, "point index too large (max 2^31 points)");
+  S2bPointIndex* ix = new (std::nothrow) S2bPointIndex();
+  if (!ix) return set_error(S2B_ENOMEM, "host allocation failed");
+  cudaError_t e = cudaGetDevice(&ix->device);
+  if (e != cudaSuccess) { delete ix; return cuda_fail(e, "cudaGetDevice"); }
+  ix->m = m;
+  auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+  const size_t b_ids = up(8 * (m + 1)), b_pts = up(24 * (m + 1)), b_data = up(4 * (m + 1));
+  e = cudaMalloc(&ix->blob, b_ids + b_pts + b_data);
+  if (e != cudaSuccess) { delete ix; return cuda_fail(e, "cudaMalloc(point index)"); }
+  char* base = (char*)ix->blob;
+  ix->ids = (const uint64_t*)base;
+  ix->pts = (const double*)(base + b_ids);
+  ix->data = (const int32_t*)(base + b_ids + b_pts);
+  if (m == 0) { *out = ix; return S2B_OK; }
+  // temporaries: raw points, unsorted ids, iota, sort scratch
+  size_t t_sort = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, t_sort, (uint64_t*)nullptr, (uint64_t*)nullptr, (int32_t*)nullptr, (int32_t*)nullptr, (int)m);
+  char* tmp = nullptr;
+  const size_t o_ids = up(24 * m), o_iota = o_ids + up(8 * m), o_sort = o_iota + up(4 * m);
+  e = cudaMalloc((void**)&tmp, o_sort + up(t_sort));
+  int rc = S2B_OK;
+  if (e != cudaSuccess) rc = cuda_fail(e, "cudaMalloc(point index build)");
+  if (rc == S2B_OK && (e = cudaMemcpy(tmp, xyz, 24 * m, cudaMemcpyHostToDevice)) != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy(points)");
+  if (rc == S2B_OK) {
+    EncodeOut eo{};
+    eo.levels.n = 1; eo.levels.level[0] = 30;
+    eo.ids = (uint64_t*)(tmp + o_ids);
+    eo.flags = nullptr; eo.token_level_index = -1; eo.tokens16 = nullptr; eo.token_len = nullptr;
+    e = launch_encode(kInXYZ, tmp, m, eo, nullptr);                      // S2CellId(point) for every index point (K1)
+    if (e == cudaSuccess) {
+      iota_kernel<<<grid_for_pi(m, (const void*)iota_kernel), kThreads>>>((int32_t*)(tmp + o_iota), m);
+      count_launch();
+      e = cub::DeviceRadixSort::SortPairs(tmp + o_sort, t_sort, (const uint64_t*)(tmp + o_ids), (uint64_t*)ix->ids,
+                                          (const int32_t*)(tmp + o_iota), (int32_t*)ix->data, (int)m);
+      count_launch();
+    }
+    if (e == cudaSuccess) {
+      gather_points_kernel<<<grid_for_pi(m, (const void*)gather_points_kernel), kThreads>>>((const double*)tmp, ix->data, m, (double*)ix->pts);
+      count_launch();
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) rc = cuda_fail(e, "point index build");
+  }
+  if (tmp) cudaFree(tmp);
+  if (rc != S2B_OK) { cudaFree(ix->blob); delete ix; return rc; }
+  *out = ix;
+  return S2B_OK;
+}
+
+void s2b_point_index_destroy(S2bPointIndex* ix) {
+  if (!ix) return;
+  if (ix->blob) cudaFree(ix->blob);
+  delete ix;
+}
+
+size_t s2b_point_index_size(const S2bPointIndex* ix) { return ix ? ix->m : 0; }
+
+static int check_index_device(const S2bPointIndex* ix) {
+  if (!ix) return set_error(S2B_EINVAL, "null point index");
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  if (dev != ix->device) return set_error(S2B_EINVAL, "the point index lives on device %d but the current device is %d", ix->device, dev);
+  return S2B_OK;
+}
+
+int s2b_closest_points_count_dev(const S2bPointIndex* ix, const double* targets_dev, size_t n, double max_length2, uint32_t* counts_out_dev, void* stream) {
+  int rc = check_index_device(ix);
+  if (rc != S2B_OK) return rc;
+  if (n == 0) return S2B_OK;
+  if (!targets_dev || !counts_out_dev) return set_error(S2B_EINVAL, "null pointer");
+  if (std::isnan(max_length2)) return set_error(S2B_EINVAL, "max_length2 is NaN");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ix->m == 0 || !(max_length2 > 0)) {            // nothing is at a distance < 0 (S1ChordAngle::Negative/Zero limits)
+    cudaError_t e = cudaMemsetAsync(counts_out_dev, 0, 4 * n, st);
+    return e == cudaSuccess ? S2B_OK : cuda_fail(e, "cudaMemsetAsync");
+  }
+  const int level = level_for_min_width(angle_of_length2(max_length2)) - 1;
+  const IndexView v{ix->ids, ix->pts, ix->data, (uint32_t)ix->m};
+  // expected index points per covering: 4 cells of `level` out of 6 * 4^level
+  const double per_cover = level < 0 ? (double)ix->m : 4.0 * (double)ix->m / (6.0 * std::ldexp(1.0, 2 * level));
+  if (per_cover >= 64.0) {
+    const auto k = radius_count_kernel<true>;
+    k<<<grid_for_pi(n * 32, (const void*)k), kThreads, 0, st>>>(v, targets_dev, n, level, max_length2, counts_out_dev);
+  } else {
+    const auto k = radius_count_kernel<false>;
+    k<<<grid_for_pi(n, (const void*)k), kThreads, 0, st>>>(v, targets_dev, n, level, max_length2, counts_out_dev);
+  }
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? S2B_OK : cuda_fail(e, "radius_count launch");
+}
+
+int s2b_closest_point_dev(const S2bPointIndex* ix, const double* targets_dev, size_t n, double max_length2, int32_t* data_out_dev,
+                          double* length2_out_dev, void* stream) {
+  int rc = check_index_device(ix);
+  if (rc != S2B_OK) return rc;
+  if (n == 0) return S2B_OK;
+  if (!targets_dev || !data_out_dev) return set_error(S2B_EINVAL, "null pointer");
+  if (std::isnan(max_length2)) return set_error(S2B_EINVAL, "max_length2 is NaN");
+  cudaStream_t st = (cudaStream_t)stream;
+  // chord^2 of the cap radius the covering of level L is guaranteed to contain: min width of a level L+1 cell, shrunk a
+  // little (entry 0 = level -1 = the whole sphere)
+  double cov[31];
+  cov[0] = HUGE_VAL;
+  for (int L = 0; L < 30; ++L) {
+    const double r = std::ldexp(kMinWidthDeriv, -(L + 1)) * (1 - 1e-9);
+    const double len = 2 * std::sin(0.5 * r);
+    cov[L + 1] = len * len * (1 - 1e-9);
+  }
+  double* cov_dev = nullptr;
+  cudaError_t e = cudaMallocAsync((void**)&cov_dev, sizeof(cov), st);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync");
+  e = cudaMemcpyAsync(cov_dev, cov, sizeof(cov), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);                    // cov[] is a stack array
+  if (e != cudaSuccess) { cudaFreeAsync(cov_dev, st); return cuda_fail(e, "cudaMemcpyAsync"); }
+  // start where a covering holds ~16 index points on average
+  int start = -1;
+  if (ix->m > 0) {
+    start = (int)std::floor(0.5 * std::log2((double)ix->m * 4.0 / (6.0 * 16.0)));
+    start = start < -1 ? -1 : (start > 29 ? 29 : start);
+  }
+  const IndexView v{ix->ids, ix->pts, ix->data, (uint32_t)ix->m};
+  closest_point_kernel<<<grid_for_pi(n, (const void*)closest_point_kernel), kThreads, 0, st>>>(v, targets_dev, n, start, max_length2, cov_dev, data_out_dev, length2_out_dev);
+  count_launch();
+  e = cudaGetLastError();
+  cudaFreeAsync(cov_dev, st);
+  return e == cudaSuccess ? S2B_OK : cuda_fail(e, "closest_point launch");
+}
+
+// Host-pointer forms (whole-array copies).
+int s2b_closest_points_count(const S2bPointIndex* ix, const double* targets, size_t n, double max_length2, uint32_t* counts_out) {
+  if (n == 0) return S2B_OK;
+  if (!targets || !counts_out) return set_error(S2B_EINVAL, "null pointer");
+  void *t = nullptr, *c = nullptr;
+  cudaError_t e = cudaMalloc(&t, 24 * n);
+  if (e == cudaSuccess) e = cudaMalloc(&c, 4 * n);
+  if (e == cudaSuccess) e = cudaMemcpy(t, targets, 24 * n, cudaMemcpyHostToDevice);
+  int rc = e == cudaSuccess ? s2b_closest_points_count_dev(ix, (const double*)t, n, max_length2, (uint32_t*)c, nullptr) : cuda_fail(e, "cudaMalloc/cudaMemcpy");
+  if (rc == S2B_OK && (e = cudaMemcpy(counts_out, c, 4 * n, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy");
+  cudaFree(t); cudaFree(c);
+  return rc;
+}
+
+int s2b_closest_point(const S2bPointIndex* ix, const double* targets, size_t n, double max_length2, int32_t* data_out, double* length2_out) {
+  if (n == 0) return S2B_OK;
+  if (!targets || !data_out) return set_error(S2B_EINVAL, "null pointer");
+  void *t = nullptr, *d = nullptr, *l = nullptr;
+  cudaError_t e = cudaMalloc(&t, 24 * n);
+  if (e == cudaSuccess) e = cudaMalloc(&d, 4 * n);
+  if (e == cudaSuccess) e = cudaMalloc(&l, 8 * n);
+  if (e == cudaSuccess) e = cudaMemcpy(t, targets, 24 * n, cudaMemcpyHostToDevice);
+  int rc = e == cudaSuccess ? s2b_closest_point_dev(ix, (const double*)t, n, max_length2, (int32_t*)d, (double*)l, nullptr) : cuda_fail(e, "cudaMalloc/cudaMemcpy");
+  if (rc == S2B_OK && (e = cudaMemcpy(data_out, d, 4 * n, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy");
+  if (rc == S2B_OK && length2_out && (e = cudaMemcpy(length2_out, l, 8 * n, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy");
+  cudaFree(t); cudaFree(d); cudaFree(l);
+  return rc;
+}
+
+}  // extern "C"

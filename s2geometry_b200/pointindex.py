@@ -1,0 +1,90 @@
+"""S2PointIndex + S2ClosestPointQuery, batch form (src/s2/s2point_index.h, s2closest_point_query.h), over the C ABI.
+
+    index = PointIndex(points)                       # S2PointIndex<int>: Add(points[i], i)
+    q = ClosestPointQuery(index, max_distance_rad=r) # options.max_distance = S1Angle::Radians(r) (exclusive)
+    q.count(targets)                                 # len(FindClosestPoints(PointTarget(t))) per target  (radius join)
+    q.closest(targets)                               # FindClosestPoint: (data, length2) per target, data = -1 if none
+
+NumPy arrays take the host path; CUDA tensors are used in place on the index's device.
+"""
+import ctypes
+import math
+
+import numpy as np
+
+from . import _lib
+
+try:
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+def chord_length2(angle_rad):
+    """S1ChordAngle(S1Angle::Radians(a)).length2() (s1chord_angle.h:339-350); inf stays inf (no limit)."""
+    if math.isinf(angle_rad) and angle_rad > 0:
+        return math.inf
+    if angle_rad < 0:
+        return -1.0
+    length = 2 * math.sin(0.5 * min(math.pi, angle_rad))
+    return length * length
+
+
+def _is_tensor(x):
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class PointIndex:
+    def __init__(self, points):
+        self._lib = _lib.load()
+        pts = np.ascontiguousarray(points.detach().cpu().numpy() if _is_tensor(points) else points, np.float64).reshape(-1, 3)
+        h = ctypes.c_void_p()
+        _lib.check(self._lib.s2b_point_index_create(pts.ctypes.data if pts.size else None, len(pts), ctypes.byref(h)))
+        self._h = h
+        self.num_points = len(pts)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.s2b_point_index_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ClosestPointQuery:
+    def __init__(self, index, max_distance_rad=math.inf):
+        self.index = index
+        self._lib = index._lib
+        self.max_length2 = chord_length2(max_distance_rad)
+
+    def count(self, targets):
+        if _is_tensor(targets):
+            t = targets.contiguous()
+            out = torch.empty(t.shape[0], dtype=torch.int32, device=t.device)
+            _lib.check(self._lib.s2b_closest_points_count_dev(self.index._h, t.data_ptr(), t.shape[0], self.max_length2, out.data_ptr(), _stream()))
+            return out
+        t = np.ascontiguousarray(targets, np.float64).reshape(-1, 3)
+        out = np.zeros(len(t), np.uint32)
+        _lib.check(self._lib.s2b_closest_points_count(self.index._h, t.ctypes.data if t.size else None, len(t), self.max_length2, out.ctypes.data))
+        return out
+
+    def closest(self, targets):
+        if _is_tensor(targets):
+            t = targets.contiguous()
+            data = torch.empty(t.shape[0], dtype=torch.int32, device=t.device)
+            l2 = torch.empty(t.shape[0], dtype=torch.float64, device=t.device)
+            _lib.check(self._lib.s2b_closest_point_dev(self.index._h, t.data_ptr(), t.shape[0], self.max_length2, data.data_ptr(), l2.data_ptr(), _stream()))
+            return data, l2
+        t = np.ascontiguousarray(targets, np.float64).reshape(-1, 3)
+        data = np.full(len(t), -1, np.int32)
+        l2 = np.full(len(t), np.inf, np.float64)
+        _lib.check(self._lib.s2b_closest_point(self.index._h, t.ctypes.data if t.size else None, len(t), self.max_length2, data.ctypes.data, l2.ctypes.data))
+        return data, l2

@@ -1,0 +1,104 @@
+"""GPU parity tests for the batched S2ClosestPointQuery over an S2PointIndex (s2b_pointindex.cu) against the reference's
+own S2ClosestPointQuery<int> / S2PointIndex<int> (oracle/_ref): radius counts (doc/examples/point_index.cc) and
+FindClosestPoint, with exact S1ChordAngle distances."""
+import math
+
+import numpy as np
+import pytest
+
+from s2geometry_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+def scene(seed, m=200_000, n=40_000):
+    """Index: uniform points + a dense cluster + exact duplicates. Targets: uniform, near the cluster, ON index points."""
+    rng = np.random.default_rng(seed)
+    c = np.array([0.3, -0.5, 0.8]) / np.linalg.norm([0.3, -0.5, 0.8])
+    pts = np.concatenate([synth.sphere_points(m, seed), synth.cap_points(c, 0.01, m // 4, seed + 1)])
+    pts = np.concatenate([pts, pts[:1000]])                                  # duplicates (ties in distance)
+    targets = np.concatenate([synth.sphere_points(n, seed + 2), synth.cap_points(c, 0.03, n // 4, seed + 3),
+                              pts[rng.integers(0, len(pts), 2000)],           # distance exactly 0
+                              np.array([[1.0, 0, 0], [0, 0, -1.0], [-1.0, 0, 0]]) / 1.0])
+    return pts, targets
+
+
+def test_chord_length2_matches_reference(ref):
+    from s2geometry_b200.pointindex import chord_length2
+    for a in (0.0, 1e-9, 1e-3, 0.02, 0.3, 1.0, 2.0, math.pi, 4.0):
+        assert chord_length2(a) == ref.chord_length2(a)
+
+
+def test_radius_counts_match_reference(torch_cuda, ref):
+    torch = torch_cuda
+    from s2geometry_b200.pointindex import ClosestPointQuery, PointIndex
+    pts, targets = scene(1)
+    ri = ref.point_index(pts)
+    ix = PointIndex(pts)
+    assert ix.num_points == len(pts)
+    total = 0
+    # 1 km and 100 km on the Earth, a few degrees, > 90 degrees (whole-sphere covering), and the extremes
+    # (the reference materialises every result, so large radii are checked on fewer targets)
+    for r, k in ((0.0, None), (1.57e-4, None), (1.57e-2, 20000), (0.05, 1500), (0.3, 150), (1.2, 12), (2.0, 8), (math.pi, 8)):
+        sel = targets if k is None else np.ascontiguousarray(targets[:: len(targets) // k])
+        want = ri.count(sel, r)
+        q = ClosestPointQuery(ix, r)
+        got = q.count(sel)
+        assert (got == want).all(), (r, int((got != want).sum()))
+        assert (q.count(torch.from_numpy(sel).cuda()).cpu().numpy().astype(np.uint32) == want).all(), r
+        total += int(want.sum())
+    assert total > 2 * len(targets)
+    assert (ClosestPointQuery(ix, math.pi).count(targets[:100]) <= len(pts)).all()
+    # no distance limit: every index point qualifies
+    assert (ClosestPointQuery(ix).count(targets[:50]) == len(pts)).all()
+    assert (ri.count(targets[:2]) == len(pts)).all()
+
+
+def test_closest_point_matches_reference(torch_cuda, ref):
+    torch = torch_cuda
+    from s2geometry_b200.pointindex import ClosestPointQuery, PointIndex
+    pts, targets = scene(2, m=100_000, n=30_000)
+    ri = ref.point_index(pts)
+    ix = PointIndex(pts)
+    for r in (None, 1.0, 0.01, 1e-4):
+        wd, wl = ri.closest(targets, -1.0 if r is None else r)
+        q = ClosestPointQuery(ix) if r is None else ClosestPointQuery(ix, r)
+        gd, gl = q.closest(targets)
+        assert (gl == wl).all(), r                                  # the exact S1ChordAngle of the nearest point
+        assert ((gd < 0) == (wd < 0)).all()
+        ok = gd >= 0
+        # the returned point really is at that distance (equidistant points — the duplicates — may differ in data)
+        d = pts[gd[ok]] - targets[ok]
+        l2 = np.minimum(4.0, ((0.0 + d[:, 0] * d[:, 0]) + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2])
+        assert (l2 == gl[ok]).all()
+        assert (gd[ok] == wd[ok]).mean() > 0.95
+        dd, dl = q.closest(torch.from_numpy(targets).cuda())
+        assert (dd.cpu().numpy() == gd).all() and (dl.cpu().numpy() == gl).all()
+        if r is None:
+            assert ok.all()
+        if r == 1e-4:
+            assert (~ok).any() and ok.any()
+    # a tiny index far from most targets: the search has to widen to the whole sphere
+    few = synth.cap_points(np.array([0.0, 0.0, 1.0]), 0.001, 7, 5)
+    rf = ref.point_index(few)
+    wd, wl = rf.closest(targets[:5000])
+    gd, gl = ClosestPointQuery(PointIndex(few)).closest(targets[:5000])
+    assert (gl == wl).all() and (gd == wd).all()
+
+
+def test_empty_index_and_empty_targets(torch_cuda):
+    from s2geometry_b200.pointindex import ClosestPointQuery, PointIndex
+    ix = PointIndex(np.zeros((0, 3)))
+    t = synth.sphere_points(100, 3)
+    assert (ClosestPointQuery(ix, 0.5).count(t) == 0).all()
+    d, l = ClosestPointQuery(ix).closest(t)
+    assert (d == -1).all() and np.isinf(l).all()
+    ix2 = PointIndex(t)
+    assert ClosestPointQuery(ix2, 0.5).count(np.zeros((0, 3))).size == 0
