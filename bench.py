@@ -259,6 +259,57 @@ def encode_xyz_section(args, torch, dev, rank, world):
     return out
 
 
+def radius_join_section(args, torch, dev, rank, world):
+    """SURVEY 8(f) rank 3, the radius join of the reference's doc/examples/point_index.cc: an S2PointIndex of 10M uniform
+    points, targets = this rank's share of the uniform point stream, count of index points within 10 km (Earth) of every
+    target = S2ClosestPointQuery with max_distance; plus FindClosestPoint (nearest index point) for every target."""
+    from s2geometry_b200 import synth
+    from s2geometry_b200.pointindex import ClosestPointQuery, PointIndex
+    m = 10_000_000
+    n = min(args.points, 50_000_000)
+    radius = 10.0 / 6371.01
+    index_pts = synth.sphere_points_cuda(m, 77, dev)
+    t0 = time.perf_counter()
+    ix = PointIndex(index_pts)
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    targets = synth.sphere_points_cuda(n, 200 + rank, dev)
+    q = ClosestPointQuery(ix, radius)
+    qn = ClosestPointQuery(ix)
+
+    def timed(f):
+        for _ in range(2):
+            r = f()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(max(2, args.steps // 2)):
+            r = f()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / max(2, args.steps // 2), r
+    ms_c, counts = timed(lambda: q.count(targets))
+    ms_n, (data, l2) = timed(lambda: qn.closest(targets))
+    pairs = int(counts.sum().item())
+    out = {"workload": "radius join: %d targets per GPU vs an S2PointIndex of %d uniform points, max_distance 10 km (S2ClosestPointQuery, PointTarget)" % (n, m),
+           "index_build_s": build_s, "count": {"targets_per_s": n / (ms_c * 1e-3), "ms_per_step": ms_c, "pairs_found": pairs},
+           "closest": {"targets_per_s": n / (ms_n * 1e-3), "ms_per_step": ms_n}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import reflib  # cpu_baseline leg
+            ref = reflib.load()
+            ri = ref.point_index(index_pts.cpu().numpy())
+            k = 2_000_000
+            sample = targets[:k].cpu().numpy()
+            t0 = time.perf_counter(); want = ri.count(sample, radius, ref.hardware_threads()); dt = time.perf_counter() - t0
+            t0 = time.perf_counter(); wd, wl = ri.closest(sample, -1.0, ref.hardware_threads()); dt2 = time.perf_counter() - t0
+            out["cpu_baseline"] = {"count": {"value": k / dt, "unit": "targets/s"}, "closest": {"value": k / dt2, "unit": "targets/s"},
+                                   "cores": ref.hardware_threads(), "kind": "reference", "sample": "first 2M targets, S2ClosestPointQuery<int>, one query object per thread",
+                                   "parity_on_sample": bool((counts[:k].cpu().numpy().astype(np.uint32) == want).all() and (l2[:k].cpu().numpy() == wl).all())}
+        except Exception as e:
+            out["cpu_baseline"] = {"unavailable": str(e)}
+    return out
+
+
 def join_section(args, torch, dev, rank, world):
     """BASELINE configs[3]: spatial join, `join_points` uniform points (default 1B, sharded over the ranks: strong
     scaling) vs 10k synthetic polygons -> per-polygon hit counts; the only collective is the NCCL all-reduce of the
@@ -476,6 +527,14 @@ def run_gpu(args):
             join, cellunion = join_section(args, torch, dev, rank, world)
         except Exception as e:
             join = {"error": repr(e)}
+    radius_join = None
+    if not args.no_join:
+        try:
+            torch.cuda.empty_cache()
+            radius_join = radius_join_section(args, torch, dev, rank, world)
+            torch.cuda.empty_cache()
+        except Exception as e:
+            radius_join = {"error": repr(e)}
     if rank == 0:
         hbm_peak, peak_src = peaks()
         kern_ms = float(np.mean(per_launch_ms))
@@ -510,6 +569,8 @@ def run_gpu(args):
             line["join"] = join
         if cellunion is not None:
             line["cellunion"] = cellunion
+        if radius_join is not None:
+            line["radius_join"] = radius_join
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline()
