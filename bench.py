@@ -31,6 +31,7 @@ import numpy as np  # noqa: E402
 LEVELS = [12, 20, 30]
 TOKEN_LEVEL_INDEX = 2
 N_POINTS = 100_000_000
+DEVICE_MAX_EDGES_PER_CELL = 1   # S2B_MAX_EDGES_PER_CELL_DEVICE (include/s2b_capi.h): granularity of device-resident indexes
 BYTES_PER_POINT = 16 + 8 * len(LEVELS) + 16 + 1   # algorithmic HBM bytes per point of the fused kernel
 # FP64-pipe instructions (DADD/DMUL/DFMA/DSETP) executed per point by encode_kernel<latlng>, measured with ncu's
 # per-instruction counts (profiles/r1_encode_latlng_final_ncu.json); used only for the informational fp64 roofline.
@@ -154,14 +155,23 @@ def pip_section(args, torch, dev, rank, world):
     bounding cap (the reference's own benchmark design, s2loop_test.cc:1635-1666)."""
     from s2geometry_b200 import _lib, synth
     from s2geometry_b200.index import ContainsPointQuery, FlatIndex, ShapeIndex
+    from s2geometry_b200.index import build_flat_index
+    from s2geometry_b200.shapes import ShapeSoup
     fx = np.load(os.path.join(ROOT, "tests", "golden", "index_loop10k.npz"))
-    flat = FlatIndex(**{k: fx[k] for k in FlatIndex.FIELDS}, num_shape_ids=int(fx["num_shape_ids"]))
+    flat_default = FlatIndex(**{k: fx[k] for k in FlatIndex.FIELDS}, num_shape_ids=int(fx["num_shape_ids"]))
+    # The device index is built with MutableS2ShapeIndex::Options::max_edges_per_cell = 1 instead of the CPU default 10:
+    # query results do not depend on the granularity (tests), and finer cells mean fewer points reach the edge loops.
+    # The reference-built default-granularity index (the committed fixture) is measured next to it.
+    lsoup = ShapeSoup(); lsoup.add_polygon([fx["loop_vertices"]])
+    flat = build_flat_index(lsoup.freeze(), DEVICE_MAX_EDGES_PER_CELL)
     ix = ShapeIndex(flat)
+    ix_default = ShapeIndex(flat_default)
     query = ContainsPointQuery(ix, 1)
     n = args.points
     hbm_peak, _ = peaks()
     center = np.array([0.3, -0.5, 0.8]); radius = 0.17 * 1.25
-    out = {"workload": "configs[2]: %d points vs one 10k-vertex loop (index: %d cells, %d clipped edges), SEMI_OPEN" % (n, flat.num_cells, flat.num_edges),
+    out = {"workload": "configs[2]: %d points vs one 10k-vertex loop (index with max_edges_per_cell=%d: %d cells, %d clipped edges), SEMI_OPEN" % (
+               n, DEVICE_MAX_EDGES_PER_CELL, flat.num_cells, flat.num_edges),
            "bytes_per_point": 25}
     sets = {}
     pts_u = synth.sphere_points_cuda(n, 3 + rank, dev)
@@ -179,22 +189,25 @@ def pip_section(args, torch, dev, rank, world):
     res = torch.empty(n, dtype=torch.uint8, device=dev)
     lib = _lib.load()
     import ctypes
-    for name, pts in sets.items():
-        def step():
-            _lib.check(lib.s2b_contains_dev(ix._h, ctypes.c_void_p(pts.data_ptr()), n, 1, ctypes.c_void_p(res.data_ptr()),
-                                            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
-        for _ in range(3):
-            step()
-        torch.cuda.synchronize()
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            step()
-        e1.record(); torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / args.steps
-        ach = 25 * n / (ms * 1e-3) / 1e9
-        out[name] = {"points_per_s": n / (ms * 1e-3), "ms_per_step": ms, "inside_fraction": float(res.float().mean().item()),
-                     "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak}}
+    out["default_granularity"] = {"workload": "the same loop in the reference-built index with the default max_edges_per_cell=10 (%d cells, %d clipped edges)" % (
+        flat_default.num_cells, flat_default.num_edges)}
+    for index, dest in ((ix, out), (ix_default, out["default_granularity"])):
+        for name, pts in sets.items():
+            def step():
+                _lib.check(lib.s2b_contains_dev(index._h, ctypes.c_void_p(pts.data_ptr()), n, 1, ctypes.c_void_p(res.data_ptr()),
+                                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                step()
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.steps
+            ach = 25 * n / (ms * 1e-3) / 1e9
+            dest[name] = {"points_per_s": n / (ms * 1e-3), "ms_per_step": ms, "inside_fraction": float(res.float().mean().item()),
+                          "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak}}
     # end to end through the host-pointer call (pinned input, pinned output), U set
     h_pts = torch.empty((n, 3), dtype=torch.float64, pin_memory=True); h_pts.copy_(pts_u)
     h_out = torch.empty(n, dtype=torch.uint8, pin_memory=True)
@@ -322,7 +335,7 @@ def join_section(args, torch, dev, rank, world):
         soup.add_polygon(loops)
     soup = soup.freeze()
     t0 = time.perf_counter()
-    flat = build_flat_index(soup)
+    flat = build_flat_index(soup, DEVICE_MAX_EDGES_PER_CELL)   # see pip_section: finer cells than the CPU default, same answers
     build_s = time.perf_counter() - t0
     ix = ShapeIndex(flat)
     query = ContainsPointQuery(ix, 1)
@@ -350,7 +363,7 @@ def join_section(args, torch, dev, rank, world):
     ms = float(t.item())
     hbm_peak, _ = peaks()
     ach = 24 * n_total / world / (ms * 1e-3) / 1e9   # per-GPU algorithmic bytes over the step time
-    out = {"workload": "configs[3]: %d uniform points (sharded over %d GPU(s)) vs 10k polygons (%d vertices; index %d cells, %d clipped edges, %.1f MB on device), per-polygon counts + all-reduce"
+    out = {"workload": "configs[3]: %d uniform points (sharded over %d GPU(s)) vs 10k polygons (%d vertices; index with max_edges_per_cell=1: %d cells, %d clipped edges, %.1f MB on device), per-polygon counts + all-reduce"
                        % (n_total, world, len(soup.vertices), flat.num_cells, flat.num_edges, ix.info()["device_bytes"] / 1e6),
            "scaling": "strong", "points_per_s": n_total / (ms * 1e-3), "ms_per_step": ms, "index_build_s": build_s,
            "total_hits": int(counts.sum().item()), "bytes_per_point": 24,

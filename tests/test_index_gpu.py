@@ -207,6 +207,39 @@ def test_own_builder_index_on_gpu(torch_cuda, ref):
         assert (ContainsPointQuery(ix3, m).shape_histogram(q) == ri3.shape_histogram(q, m, 1)).all()
 
 
+def test_device_granularity_index_gives_the_same_answers(torch_cuda, ref):
+    """The granularity recommended for device-resident indexes (max_edges_per_cell = 1, S2B_MAX_EDGES_PER_CELL_DEVICE):
+    far more, far smaller cells — every answer still equals the reference's over its default-granularity index, for all
+    vertex models, incl. every vertex / edge midpoint / cell centre of the loop and the exact-stage scene."""
+    from s2geometry_b200 import synth
+    from s2geometry_b200.index import ContainsPointQuery, ShapeIndex, build_flat_index
+    soup, v = scenes.loop_scene(10000)
+    fine = build_flat_index(soup, 1)
+    assert fine.num_cells > 5 * build_flat_index(soup).num_cells
+    ix = ShapeIndex(fine)
+    ri = ref.index_create(soup)
+    u, b, d = scenes.loop_points(v, 1_000_000, 2_000_000, 29)
+    centres = fine.cell_center.reshape(-1, 3)                       # the fine index's own cell centres are queries too
+    for pts in (u, b, d, centres):
+        for m in (0, 1, 2):
+            assert (ContainsPointQuery(ix, m).contains(pts) == ri.contains(pts, m)).all()
+    soup2 = scenes.polygons_scene(3000, 53, min_radius_km=100, max_radius_km=1500)
+    ix2 = ShapeIndex(build_flat_index(soup2, 1))
+    ri2 = ref.index_create(soup2)
+    pts = synth.sphere_points(3_000_000, 54)
+    for m in (0, 1, 2):
+        assert (ContainsPointQuery(ix2, m).shape_histogram(pts) == ri2.shape_histogram(pts, m)).all()
+    off, ids = ContainsPointQuery(ix2, 1).containing_shape_ids(pts[:300_000])
+    woff, wids = ri2.containing_shapes(pts[:300_000], 1)
+    assert (np.asarray(off) == woff).all() and (np.asarray(ids) == wids).all()
+    soup3 = scenes.axis_aligned_scene()
+    ix3 = ShapeIndex(build_flat_index(soup3, 1))
+    ri3 = ref.index_create(soup3)
+    q = scenes.axis_aligned_queries()
+    for m in (0, 1, 2):
+        assert (ContainsPointQuery(ix3, m).shape_histogram(q) == ri3.shape_histogram(q, m, 1)).all()
+
+
 def test_cells_with_hundreds_of_edges_on_gpu(torch_cuda, ref):
     from s2geometry_b200.index import ContainsPointQuery, ShapeIndex, build_flat_index
     soup, v = scenes.loop_scene(3000)
