@@ -214,6 +214,22 @@ int s2b_index_decode(const void* bytes, size_t len, int num_shapes, const int8_t
 int s2b_index_encode(const S2bFlatIndex* flat, const int32_t* edge_id, int max_edges_per_cell, void* out, size_t capacity,
                      size_t* size_out);
 
+/* The geometry half of a serialized index: the bytes of s2shapeutil::FastEncodeTaggedShapes / CompactEncodeTaggedShapes
+ * (s2shapeutil_coding.cc:134-156; read back there by TaggedShapeFactory, :158-172) for S2PointVectorShape (tag 3),
+ * S2LaxPolylineShape (tag 4) and S2LaxPolygonShape (tag 5), whose points are EncodedS2PointVectors in either format
+ * (UNCOMPRESSED or CELL_IDS, encoded_s2point_vector.cc). Decoding yields the shape soup s2b_index_build /
+ * s2b_index_decode take (arrays valid until s2b_shape_soup_destroy); vertices are bit-identical to the reference's
+ * decoder. Other shape types (S2Polygon::Shape, S2Polyline::Shape) and malformed input fail with S2B_EINVAL.
+ * s2b_shapes_encode writes the FAST (uncompressed) form, byte-identical to the reference; two-call capacity protocol
+ * as s2b_index_encode. */
+typedef struct S2bShapeSoup S2bShapeSoup;
+int s2b_shapes_decode(const void* bytes, size_t len, S2bShapeSoup** soup_out, size_t* consumed_out);
+int s2b_shape_soup_arrays(const S2bShapeSoup* soup, int* num_shapes, const int8_t** shape_dim, const uint32_t** shape_chain_begin,
+                          const uint32_t** chain_vertex_begin, const double** vertices, size_t* num_vertices);
+void s2b_shape_soup_destroy(S2bShapeSoup* soup);
+int s2b_shapes_encode(int num_shapes, const int8_t* shape_dim, const uint32_t* shape_chain_begin, const uint32_t* chain_vertex_begin,
+                      const double* vertices, void* out, size_t capacity, size_t* size_out);
+
 typedef struct S2bIndex S2bIndex;
 
 /* Uploads the index to the CURRENT CUDA device (one replica per GPU: call once per process/device). */

@@ -30,6 +30,10 @@
 #include "s2/s2edge_crosser.h"
 #include "s2/s2edge_crossings.h"
 #include "s2/s2latlng.h"
+#include "s2/s2lax_polygon_shape.h"
+#include "s2/s2lax_polyline_shape.h"
+#include "s2/s2point_vector_shape.h"
+#include "s2/encoded_string_vector.h"
 #include "s2/s2point.h"
 #include "s2/s2pointutil.h"
 #include "s2/s2predicates.h"
@@ -476,6 +480,72 @@ void ref_cellunion_contains(const uint64_t* ids, size_t m, const double* xyz, si
 }
 
 // S2CellUnion normalisation (sort + merge) of arbitrary ids; returns count written.
+// ---------------------------------------------------------------- tagged shapes (geometry half of a serialized index)
+// The soup as the reference's own shape classes: dim 0 -> S2PointVectorShape, dim 1 (one chain) -> S2LaxPolylineShape,
+// dim 2 -> S2LaxPolygonShape; encoded the way s2shapeutil::EncodeTaggedShapes does (s2shapeutil_coding.cc:134-148:
+// StringVectorEncoder of [varint32 type_tag, shape.Encode(hint)]) with hint 0 = FAST, 1 = COMPACT.
+static std::unique_ptr<S2Shape> SoupToLaxShape(int s, const int8_t* dim, const uint32_t* scb, const uint32_t* cvb, const double* v) {
+  std::vector<std::vector<S2Point>> chains;
+  for (uint32_t c = scb[s]; c < scb[s + 1]; ++c) {
+    std::vector<S2Point> pts;
+    for (uint32_t k = cvb[c]; k < cvb[c + 1]; ++k) pts.push_back(P(v + 3 * (size_t)k));
+    chains.push_back(std::move(pts));
+  }
+  if (dim[s] == 0) {
+    std::vector<S2Point> all;
+    for (auto& c : chains) all.insert(all.end(), c.begin(), c.end());
+    return std::make_unique<S2PointVectorShape>(std::move(all));
+  }
+  if (dim[s] == 1) return std::make_unique<S2LaxPolylineShape>(chains.empty() ? std::vector<S2Point>() : chains[0]);
+  return std::make_unique<S2LaxPolygonShape>(chains);
+}
+size_t ref_tagged_shapes_encode(int num_shapes, const int8_t* dim, const uint32_t* scb, const uint32_t* cvb, const double* v, int hint,
+                                uint8_t* out, size_t capacity) {
+  s2coding::StringVectorEncoder shape_vector;
+  for (int s = 0; s < num_shapes; ++s) {
+    auto shape = SoupToLaxShape(s, dim, scb, cvb, v);
+    Encoder* sub = shape_vector.AddViaEncoder();
+    sub->Ensure(Encoder::kVarintMax32);
+    sub->put_varint32(shape->type_tag());
+    shape->Encode(sub, hint ? s2coding::CodingHint::COMPACT : s2coding::CodingHint::FAST);
+  }
+  Encoder enc;
+  shape_vector.Encode(&enc);
+  if (out && enc.length() <= capacity) memcpy(out, enc.base(), enc.length());
+  return enc.length();
+}
+// Decodes tagged shapes with the reference's own Init methods and writes every edge of every shape (v0, v1) in edge-id
+// order: edges_out holds 6 doubles per edge, num_edges_out[s] the edge count of shape s, dims_out[s] its dimension.
+// Returns the total number of edges, or (size_t)-1 if the reference rejects the input.
+size_t ref_tagged_shapes_decode_edges(const uint8_t* bytes, size_t len, int max_shapes, int32_t* dims_out, uint32_t* num_edges_out,
+                                      double* edges_out, size_t edge_capacity, int* num_shapes_out) {
+  Decoder dec(bytes, len);
+  s2coding::EncodedStringVector sv;
+  if (!sv.Init(&dec)) return (size_t)-1;
+  *num_shapes_out = (int)sv.size();
+  size_t total = 0;
+  for (int s = 0; s < (int)sv.size() && s < max_shapes; ++s) {
+    Decoder d = sv.GetDecoder(s);
+    uint32_t tag;
+    std::unique_ptr<S2Shape> shape;
+    if (d.avail() == 0) { dims_out[s] = 0; num_edges_out[s] = 0; continue; }
+    if (!d.get_varint32(&tag)) return (size_t)-1;
+    if (tag == S2PointVectorShape::kTypeTag) { auto p = std::make_unique<S2PointVectorShape>(); if (!p->Init(&d)) return (size_t)-1; shape = std::move(p); }
+    else if (tag == S2LaxPolylineShape::kTypeTag) { auto p = std::make_unique<S2LaxPolylineShape>(); if (!p->Init(&d)) return (size_t)-1; shape = std::move(p); }
+    else if (tag == S2LaxPolygonShape::kTypeTag) { auto p = std::make_unique<S2LaxPolygonShape>(); if (!p->Init(&d)) return (size_t)-1; shape = std::move(p); }
+    else return (size_t)-1;
+    dims_out[s] = shape->dimension();
+    num_edges_out[s] = (uint32_t)shape->num_edges();
+    for (int e = 0; e < shape->num_edges(); ++e, ++total) {
+      if (total < edge_capacity) {
+        S2Shape::Edge ed = shape->edge(e);
+        for (int q = 0; q < 3; ++q) { edges_out[6 * total + q] = ed.v0[q]; edges_out[6 * total + 3 + q] = ed.v1[q]; }
+      }
+    }
+  }
+  return total;
+}
+
 // ---------------------------------------------------------------- S2PointIndex / S2ClosestPointQuery
 struct RefPointIndex { S2PointIndex<int> index; };
 void* ref_point_index_create(const double* xyz, size_t m) {

@@ -179,6 +179,31 @@ class Ref:
         self.lib.ref_chord_length2.restype = ctypes.c_double
         return float(self.lib.ref_chord_length2(ctypes.c_double(angle_rad)))
 
+    def tagged_shapes_encode(self, soup, compact=False):
+        """The soup as S2PointVectorShape / S2LaxPolylineShape / S2LaxPolygonShape, encoded as EncodeTaggedShapes does."""
+        self.lib.ref_tagged_shapes_encode.restype = _sz
+        args = (int(soup.num_shapes), _p(soup.shape_dim), _p(soup.shape_chain_begin), _p(soup.chain_vertex_begin),
+                _p(np.ascontiguousarray(soup.vertices, np.float64)), int(bool(compact)))
+        n = int(self.lib.ref_tagged_shapes_encode(*args, None, _sz(0)))
+        out = np.zeros(max(n, 1), np.uint8)
+        self.lib.ref_tagged_shapes_encode(*args, _p(out), _sz(out.size))
+        return out[:n].tobytes()
+
+    def tagged_shapes_decode_edges(self, data, max_shapes=1 << 20):
+        """Decodes with the reference's Init methods -> (dims, num_edges per shape, edges (E,6)) or None if rejected."""
+        self.lib.ref_tagged_shapes_decode_edges.restype = _sz
+        buf = np.frombuffer(bytes(data), np.uint8)
+        dims = np.zeros(max_shapes, np.int32); ne = np.zeros(max_shapes, np.uint32); ns = ctypes.c_int(0)
+        cap = 1 << 16
+        while True:
+            edges = np.zeros((cap, 6), np.float64)
+            total = self.lib.ref_tagged_shapes_decode_edges(_p(buf), _sz(buf.size), int(max_shapes), _p(dims), _p(ne), _p(edges), _sz(cap), ctypes.byref(ns))
+            if total == ctypes.c_size_t(-1).value:
+                return None
+            if total <= cap:
+                return dims[: ns.value].copy(), ne[: ns.value].copy(), edges[:total].copy()
+            cap = int(total)
+
     def index_create(self, soup, max_edges_per_cell=0):
         return RefIndex(self, soup, max_edges_per_cell)
 

@@ -1,0 +1,257 @@
+// s2b_shapes_wire.h — reader / writer for the reference's serialized shapes (host C++, no CUDA): the geometry half of
+// a serialized index (the cells are s2b_index_wire.h).
+//   s2shapeutil::EncodeTaggedShapes / TaggedShapeFactory   s2shapeutil_coding.cc:134-172  (StringVector of [varint tag, shape])
+//   S2PointVectorShape   (tag 3)  s2point_vector_shape.h:62-73     EncodedS2PointVector
+//   S2LaxPolylineShape   (tag 4)  s2lax_polyline_shape.cc:74-86    EncodedS2PointVector
+//   S2LaxPolygonShape    (tag 5)  s2lax_polygon_shape.cc:177-252   version, num_loops, EncodedS2PointVector, loop starts
+//   EncodedS2PointVector           encoded_s2point_vector.cc:121-134 (format), :205-250 (UNCOMPRESSED), :836-942 (CELL_IDS)
+// Decoding handles both point-vector formats (the CELL_IDS decoder is restated from the format description and the
+// reference decoder's arithmetic); encoding writes the UNCOMPRESSED ("FAST" hint) form, byte-identical to the reference.
+// S2Polygon::Shape (tag 1) and S2Polyline::Shape (tag 2) are not handled (S2B_EINVAL): they carry S2Loop/S2Polygon
+// state this path never uses.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "s2b_index_wire.h"
+
+namespace s2b {
+
+struct ShapeSoupData {
+  std::vector<int8_t> shape_dim;
+  std::vector<uint32_t> shape_chain_begin{0};
+  std::vector<uint32_t> chain_vertex_begin{0};
+  std::vector<double> vertices;
+};
+
+namespace wire {
+
+inline void deinterleave_bit_pairs(uint64_t code, uint32_t* val0, uint32_t* val1) {   // encoded_s2point_vector.cc:71-92
+  uint64_t v0 = code, v1 = code >> 2;
+  v0 &= 0x3333333333333333ull; v0 |= v0 >> 2;  v1 &= 0x3333333333333333ull; v1 |= v1 >> 2;
+  v0 &= 0x0f0f0f0f0f0f0f0full; v0 |= v0 >> 4;  v1 &= 0x0f0f0f0f0f0f0f0full; v1 |= v1 >> 4;
+  v0 &= 0x00ff00ff00ff00ffull; v0 |= v0 >> 8;  v1 &= 0x00ff00ff00ff00ffull; v1 |= v1 >> 8;
+  v0 &= 0x0000ffff0000ffffull; v0 |= v0 >> 16; v1 &= 0x0000ffff0000ffffull; v1 |= v1 >> 16;
+  *val0 = (uint32_t)v0; *val1 = (uint32_t)v1;
+}
+
+inline uint64_t load_le(const uint8_t* p, int n) { uint64_t v = 0; for (int k = 0; k < n; ++k) v |= (uint64_t)p[k] << (8 * k); return v; }
+
+// EncodedS2PointVector::Init + Decode: appends the points (3 doubles each) to *out.
+inline bool decode_point_vector(Reader* r, std::vector<double>* out, std::string* why) {
+  auto fail = [&](const char* m) { *why = m; return false; };
+  if (r->avail() < 1) return fail("truncated point vector");
+  const int format = *r->p & 7;
+  if (format == 0) {   // UNCOMPRESSED: varint64 (size << 3 | 0), then size * 24 raw bytes
+    uint64_t size;
+    if (!r->varint64(&size)) return fail("truncated point vector size");
+    size >>= 3;
+    if (size > 0x7FFFFFFFull || r->avail() < size * 24) return fail("truncated uncompressed points");
+    const size_t at = out->size();
+    out->resize(at + 3 * size);
+    if (size) std::memcpy(out->data() + at, r->p, size * 24);
+    r->p += size * 24;
+    return true;
+  }
+  if (format != 1) return fail("unknown point vector format");
+  // CELL_IDS: two header bytes, base, then a string vector of 16-point blocks
+  if (r->avail() < 2) return fail("truncated cell-id point vector");
+  uint32_t h1, h2;
+  r->get8(&h1); r->get8(&h2);
+  const bool have_exceptions = (h1 & 8) != 0;
+  const int last_block_count = (int)(h1 >> 4) + 1;
+  const int base_bytes = (int)(h2 & 7);
+  const int level = (int)(h2 >> 3);
+  if (level > 30) return fail("bad cell-id level");
+  uint64_t base;
+  if (!r->uint_with_length(base_bytes, &base)) return fail("truncated base");
+  const int base_shift = 2 * level + 3 - 8 * base_bytes;
+  base <<= base_shift > 0 ? base_shift : 0;
+  UintVector offsets;
+  if (!offsets.init(r)) return fail("truncated block offsets");
+  const uint64_t nblocks = offsets.size;
+  const uint64_t data_len = nblocks ? offsets[nblocks - 1] : 0;
+  if (r->avail() < data_len) return fail("truncated blocks");
+  const uint8_t* data = r->p;
+  r->p += data_len;
+  if (nblocks == 0) return fail("cell-id point vector without blocks");
+  const uint64_t size = 16 * (nblocks - 1) + (uint64_t)last_block_count;
+  if (size > 0x7FFFFFFFull) return fail("point vector too large");
+  const size_t at = out->size();
+  out->resize(at + 3 * size);
+  double* dst = out->data() + at;
+  for (uint64_t i = 0; i < size; ++i) {
+    const uint64_t b = i >> 4;
+    const uint64_t bstart = b ? offsets[b - 1] : 0, bend = offsets[b];
+    if (bend < bstart || bend > data_len || bend == bstart) return fail("invalid block");
+    const uint8_t* ptr = data + bstart;
+    const uint8_t* end = data + bend;
+    const uint8_t header = *ptr++;
+    const int overlap_nibbles = (header >> 3) & 1;
+    const int offset_bytes = (header & 7) + overlap_nibbles;
+    const int delta_nibbles = (header >> 4) + 1;
+    uint64_t offset = 0;
+    if (offset_bytes > 0) {
+      const int offset_shift = (delta_nibbles - overlap_nibbles) << 2;
+      if (offset_shift >= 64 || ptr + offset_bytes > end) return fail("invalid block offset");
+      offset = load_le(ptr, offset_bytes) << offset_shift;
+      ptr += offset_bytes;
+    }
+    const int delta_nibble_offset = (int)(i & 15) * delta_nibbles;
+    const int delta_bytes = (delta_nibbles + 1) >> 1;
+    const uint8_t* delta_ptr = ptr + (delta_nibble_offset >> 1);
+    if (delta_ptr + delta_bytes > end) return fail("invalid block delta");
+    uint64_t delta = load_le(delta_ptr, delta_bytes);
+    delta >>= (delta_nibble_offset & 1) << 2;
+    delta &= (~0ull >> (64 - (delta_nibbles << 2)));
+    if (have_exceptions) {
+      if (delta < 16) {
+        const uint64_t block_size = size - (i & ~15ull) < 16 ? size - (i & ~15ull) : 16;
+        ptr += (block_size * delta_nibbles + 1) >> 1;
+        ptr += delta * 24;
+        if (ptr + 24 > end) return fail("invalid exception");
+        std::memcpy(dst + 3 * i, ptr, 24);
+        continue;
+      }
+      delta -= 16;
+    }
+    const uint64_t value = base + offset + delta;
+    const int shift = 30 - level;
+    uint32_t sj, tj;
+    deinterleave_bit_pairs(value, &sj, &tj);
+    const int si = (int)((((sj << 1) | 1u) << shift) & 0x7fffffffu);
+    const int ti = (int)((((tj << 1) | 1u) << shift) & 0x7fffffffu);
+    const int face = (int)(((sj << shift) >> 30) | (((tj << (shift + 1)) >> 29) & 4u));
+    if (face > 5) return fail("invalid face in cell-id point");
+    const P3 p = normalize(face_uv_to_xyz(face, st_to_uv((1.0 / 2147483648.0) * (unsigned)si), st_to_uv((1.0 / 2147483648.0) * (unsigned)ti)));
+    dst[3 * i] = p.x; dst[3 * i + 1] = p.y; dst[3 * i + 2] = p.z;
+  }
+  return true;
+}
+
+}  // namespace wire
+
+// Decodes s2shapeutil::{Fast,Compact}EncodeTaggedShapes output into a shape soup (dimension-2 shapes: one chain per loop).
+inline int decode_tagged_shapes(const uint8_t* bytes, size_t len, ShapeSoupData* out, size_t* consumed, std::string* err) {
+  using namespace wire;
+  auto fail = [&](const std::string& m) { *err = "shape decode: " + m; return S2B_EINVAL; };
+  if (!bytes && len) return fail("null buffer");
+  *out = ShapeSoupData();
+  Reader r{bytes, bytes + len};
+  UintVector offsets;   // EncodedStringVector
+  if (!offsets.init(&r)) return fail("truncated shape offsets");
+  const uint64_t S = offsets.size;
+  const uint64_t data_len = S ? offsets[S - 1] : 0;
+  if (r.avail() < data_len) return fail("truncated shapes");
+  const uint8_t* data = r.p;
+  r.p += data_len;
+  if (consumed) *consumed = (size_t)(r.p - bytes);
+  if (S > 0x7FFFFFFFull) return fail("too many shapes");
+  uint64_t start = 0;
+  for (uint64_t s = 0; s < S; ++s) {
+    const uint64_t limit = offsets[s];
+    if (limit < start || limit > data_len) return fail("bad shape offsets");
+    Reader sr{data + start, data + limit};
+    start = limit;
+    const std::string where = " (shape " + std::to_string(s) + ")";
+    std::string why;
+    auto end_chain = [&]() { out->chain_vertex_begin.push_back((uint32_t)(out->vertices.size() / 3)); };
+    if (sr.avail() == 0) {               // a removed (null) shape keeps its id: an empty point set
+      out->shape_dim.push_back(0);
+      end_chain();
+    } else {
+      uint32_t tag;
+      if (!sr.varint32(&tag)) return fail("truncated type tag" + where);
+      if (tag == 3 || tag == 4) {        // S2PointVectorShape / S2LaxPolylineShape: one point vector
+        out->shape_dim.push_back(tag == 3 ? 0 : 1);
+        if (!decode_point_vector(&sr, &out->vertices, &why)) return fail(why + where);
+        end_chain();
+      } else if (tag == 5) {             // S2LaxPolygonShape
+        uint32_t version, num_loops;
+        if (!sr.get8(&version) || version != 1) return fail("bad lax polygon version" + where);
+        if (!sr.varint32(&num_loops) || num_loops > 0x7FFFFFFEu) return fail("bad loop count" + where);
+        const size_t v0 = out->vertices.size() / 3;
+        if (!decode_point_vector(&sr, &out->vertices, &why)) return fail(why + where);
+        const size_t nv = out->vertices.size() / 3 - v0;
+        out->shape_dim.push_back(2);
+        if (num_loops == 0) {
+          out->vertices.resize(3 * v0);
+        } else if (num_loops == 1) {
+          end_chain();
+        } else {
+          UintVector starts;   // EncodedUintVector<uint32_t>: the size field counts bytes of uint32
+          uint64_t size_len;
+          if (!sr.varint64(&size_len)) return fail("truncated loop starts" + where);
+          starts.size = size_len / 4; starts.len = (int)(size_len & 3) + 1;
+          if (starts.size != (uint64_t)num_loops + 1 || sr.avail() < starts.size * (uint64_t)starts.len) return fail("bad loop starts" + where);
+          starts.data = sr.p;
+          uint64_t prev = 0;
+          for (uint32_t k = 0; k <= num_loops; ++k) {
+            const uint64_t v = starts[k];
+            if (v < prev || v > nv || (k == 0 && v != 0)) return fail("loop starts out of range" + where);
+            if (k) out->chain_vertex_begin.push_back((uint32_t)(v0 + v));
+            prev = v;
+          }
+          if (prev != nv) return fail("loop starts do not cover the vertices" + where);
+        }
+      } else {
+        return fail("unsupported shape type tag " + std::to_string(tag) + where);
+      }
+    }
+    out->shape_chain_begin.push_back((uint32_t)(out->chain_vertex_begin.size() - 1));
+  }
+  return S2B_OK;
+}
+
+// Encodes a shape soup as s2shapeutil::FastEncodeTaggedShapes would encode the corresponding S2PointVectorShape /
+// S2LaxPolylineShape / S2LaxPolygonShape objects (CodingHint::FAST: uncompressed point vectors).
+inline int encode_tagged_shapes(int num_shapes, const int8_t* shape_dim, const uint32_t* shape_chain_begin, const uint32_t* chain_vertex_begin,
+                                const double* vertices, std::vector<uint8_t>* bytes, std::string* err) {
+  using namespace wire;
+  auto fail = [&](const std::string& m) { *err = "shape encode: " + m; return S2B_EINVAL; };
+  std::vector<uint8_t> records;
+  std::vector<uint64_t> ends((size_t)num_shapes);
+  Writer w{&records};
+  auto point_vector = [&](uint32_t vbegin, uint32_t vend) {   // EncodeS2PointVectorFast
+    const uint64_t n = vend - vbegin;
+    w.varint64(n << 3 | 0);
+    const uint8_t* src = (const uint8_t*)(vertices + 3 * (size_t)vbegin);
+    records.insert(records.end(), src, src + n * 24);
+  };
+  for (int s = 0; s < num_shapes; ++s) {
+    const uint32_t cb = shape_chain_begin[s], ce = shape_chain_begin[s + 1];
+    const uint32_t vb = chain_vertex_begin[cb], ve = chain_vertex_begin[ce];
+    if (shape_dim[s] == 0) {
+      w.varint32(3);
+      point_vector(vb, ve);                       // all chains of a point shape form one point list (edge ids are kept)
+    } else if (shape_dim[s] == 1) {
+      if (ce - cb > 1) return fail("a polyline shape with several chains has no S2LaxPolylineShape form (shape " + std::to_string(s) + ")");
+      w.varint32(4);
+      point_vector(vb, ve);
+    } else if (shape_dim[s] == 2) {
+      w.varint32(5);
+      w.put8(1);
+      w.varint32(ce - cb);
+      point_vector(vb, ve);
+      if (ce - cb > 1) {                          // EncodeUintVector<uint32_t>(loop_starts, num_loops + 1)
+        uint32_t one_bits = 1;
+        for (uint32_t c = cb; c <= ce; ++c) one_bits |= chain_vertex_begin[c] - vb;
+        const int len = ((31 - __builtin_clz(one_bits)) >> 3) + 1;
+        w.varint64(((uint64_t)(ce - cb + 1) * 4) | (uint64_t)(len - 1));
+        for (uint32_t c = cb; c <= ce; ++c) w.uint_with_length(chain_vertex_begin[c] - vb, len);
+      }
+    } else {
+      return fail("shape dimension must be 0, 1 or 2");
+    }
+    ends[s] = records.size();
+  }
+  bytes->clear();
+  Writer o{bytes};
+  o.uint_vector(ends);
+  bytes->insert(bytes->end(), records.begin(), records.end());
+  return S2B_OK;
+}
+
+}  // namespace s2b

@@ -71,3 +71,50 @@ class FrozenSoup:
 
     def freeze(self):
         return self
+
+
+def decode_shapes(data):
+    """Reads s2shapeutil::FastEncodeTaggedShapes / CompactEncodeTaggedShapes bytes (S2PointVectorShape, S2LaxPolylineShape,
+    S2LaxPolygonShape) into a FrozenSoup. Returns (soup, bytes_consumed)."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    buf = np.frombuffer(bytes(data), np.uint8)
+    h = ctypes.c_void_p(); used = ctypes.c_size_t(0)
+    _lib.check(lib.s2b_shapes_decode(buf.ctypes.data if buf.size else None, int(buf.size), ctypes.byref(h), ctypes.byref(used)))
+    try:
+        ns = ctypes.c_int(0); nv = ctypes.c_size_t(0)
+        pd, pc, pv, px = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        _lib.check(lib.s2b_shape_soup_arrays(h, ctypes.byref(ns), ctypes.byref(pd), ctypes.byref(pc), ctypes.byref(pv), ctypes.byref(px), ctypes.byref(nv)))
+
+        def arr(ptr, count, dtype):
+            if not ptr.value or count == 0:
+                return np.zeros(count, dtype)
+            return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(np.ctypeslib.as_ctypes_type(dtype))), shape=(count,)).copy()
+        soup = FrozenSoup.__new__(FrozenSoup)
+        soup.num_shapes = ns.value
+        soup.shape_dim = arr(pd, ns.value, np.int8)
+        soup.shape_chain_begin = arr(pc, ns.value + 1, np.uint32)
+        soup.chain_vertex_begin = arr(pv, int(soup.shape_chain_begin[-1]) + 1, np.uint32)
+        soup.vertices = arr(px, 3 * nv.value, np.float64).reshape(-1, 3)
+        return soup, int(used.value)
+    finally:
+        lib.s2b_shape_soup_destroy(h)
+
+
+def encode_shapes(soup):
+    """Serializes a soup as s2shapeutil::FastEncodeTaggedShapes would serialize the corresponding lax shapes."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    soup = soup.freeze()
+    v = np.ascontiguousarray(soup.vertices, np.float64)
+    args = (int(soup.num_shapes), soup.shape_dim.ctypes.data, soup.shape_chain_begin.ctypes.data, soup.chain_vertex_begin.ctypes.data,
+            v.ctypes.data if v.size else None)
+    size = ctypes.c_size_t(0)
+    rc = lib.s2b_shapes_encode(*args, None, 0, ctypes.byref(size))
+    if rc != _lib.S2B_ECAPACITY:
+        _lib.check(rc)
+    out = np.zeros(max(int(size.value), 1), np.uint8)
+    _lib.check(lib.s2b_shapes_encode(*args, out.ctypes.data, int(out.size), ctypes.byref(size)))
+    return out[: int(size.value)].tobytes()

@@ -1,0 +1,136 @@
+"""Reader / writer for the reference's serialized shapes (s2b_shapes_decode / s2b_shapes_encode) against the reference's
+own S2PointVectorShape / S2LaxPolylineShape / S2LaxPolygonShape encoders and decoders, in both EncodedS2PointVector
+formats (UNCOMPRESSED = FAST hint, CELL_IDS = COMPACT hint). Host-only: no GPU needed."""
+import numpy as np
+import pytest
+
+from s2geometry_b200 import _lib, synth
+from s2geometry_b200.index import build_flat_index, decode_index
+from s2geometry_b200.shapes import ShapeSoup, decode_shapes, encode_shapes
+from tests import scenes
+from tests.test_index_wire import mixed_soup
+
+
+def snap(ref, pts, level):
+    """S2CellId(p).parent(level).ToPoint(): vertices at cell centres are what the CELL_IDS format stores compactly."""
+    ids = ref.parent(ref.encode_points(pts, 30, 1), level)
+    return ref.to_point(ids)
+
+
+def edges_of(soup):
+    """All edges of a soup in (shape, edge id) order as an (E,6) array + per-shape counts (same rule as the C++ side)."""
+    out, counts = [], []
+    for s in range(soup.num_shapes):
+        n0 = len(out)
+        for c in range(soup.shape_chain_begin[s], soup.shape_chain_begin[s + 1]):
+            v = soup.vertices[soup.chain_vertex_begin[c]: soup.chain_vertex_begin[c + 1]]
+            n = len(v)
+            d = soup.shape_dim[s]
+            for k in range(n if d != 1 else max(0, n - 1)):
+                out.append(np.concatenate([v[k], v[k] if d == 0 else v[(k + 1) % n]]))
+        counts.append(len(out) - n0)
+    return (np.array(out).reshape(-1, 6), np.array(counts, np.uint32))
+
+
+def single_chain_polylines(soup):
+    return all(soup.shape_chain_begin[s + 1] - soup.shape_chain_begin[s] <= 1 for s in range(soup.num_shapes) if soup.shape_dim[s] == 1)
+
+
+def wire_soups(ref):
+    yield "mixed", mixed_soup(31, 25)
+    yield "loop10k", scenes.loop_scene(10000)[0]
+    yield "polygons", scenes.polygons_scene(200, 17)
+    # vertices snapped to cell centres (one level, so COMPACT stores cell ids) + a few unsnapped ones (exceptions)
+    for level in (30, 18, 7):
+        s = ShapeSoup()
+        rng = np.random.default_rng(level)
+        for loops in synth.many_polygons(30, 40 + level, min_vertices=3, max_vertices=70, min_radius_km=200.0, max_radius_km=900.0):
+            s.add_polygon([snap(ref, l, level) for l in loops])
+        line = snap(ref, synth.cap_points(np.array([0.0, 1.0, 0.0]), 0.2, 45, 3), level)
+        line[7] = synth.sphere_points(1, 5)[0]                                  # an exception inside a block
+        s.add_polyline(line)
+        s.add_points(snap(ref, synth.sphere_points(33, 9), level))
+        s.add_points(np.concatenate([snap(ref, synth.sphere_points(16, 10), level), synth.sphere_points(5, 11)]))
+        yield "snapped%d" % level, s.freeze()
+    e = ShapeSoup(); e.add_polygon([]); e.add_polygon([np.zeros((0, 3))]); e.add_points(np.zeros((0, 3))); e.add_polyline(np.zeros((0, 3)))
+    e.add_polyline(synth.sphere_points(1, 2)); e.add_polygon([synth.sphere_points(1, 3)])
+    yield "degenerate", e.freeze()
+    yield "empty", ShapeSoup().freeze()
+
+
+def test_decode_and_encode_match_reference(ref):
+    for name, soup in wire_soups(ref):
+        want_edges, want_counts = edges_of(soup)
+        for compact in (False, True):
+            data = ref.tagged_shapes_encode(soup, compact)
+            got, used = decode_shapes(data)
+            assert used == len(data), name
+            rd = ref.tagged_shapes_decode_edges(data)
+            assert rd is not None, name
+            dims, ne, redges = rd
+            ge, gc = edges_of(got)
+            assert got.num_shapes == soup.num_shapes and (got.shape_dim == dims).all(), (name, compact)
+            assert (gc == ne).all() and ge.shape == redges.shape, (name, compact)
+            assert (ge.view(np.uint64) == redges.view(np.uint64)).all(), (name, compact)     # bit-identical to the reference's decoder
+            if not compact:   # lossless: exactly the input geometry
+                assert (ge.view(np.uint64) == want_edges.view(np.uint64)).all() and (gc == want_counts).all(), name
+                assert (got.shape_chain_begin == soup.shape_chain_begin).all() and (got.chain_vertex_begin == soup.chain_vertex_begin).all()
+        if single_chain_polylines(soup):
+            assert encode_shapes(soup) == ref.tagged_shapes_encode(soup, False), name           # byte-identical FAST encoding
+    # the compact form really exercised the CELL_IDS format: much smaller than 24 bytes per vertex
+    soup = [s for n, s in wire_soups(ref) if n == "snapped18"][0]
+    assert len(ref.tagged_shapes_encode(soup, True)) < 0.4 * len(ref.tagged_shapes_encode(soup, False))
+
+
+def test_serialized_index_plus_shapes_round_trip(ref):
+    """What a reference user ships: shapes (compact) followed by the index. Decoding both gives a device-ready flat
+    index identical to flattening the reference's own index over the decoded geometry."""
+    from tests.test_index_wire import FLAT_KEYS, assert_flat_equal
+    soup = mixed_soup(41, 30)
+    blob = ref.tagged_shapes_encode(soup, False) + ref.index_create(soup).encode()
+    shapes, used = decode_shapes(blob)
+    flat, mepc, used2 = decode_index(blob[used:], shapes)
+    assert used + used2 == len(blob) and mepc == 10
+    assert_flat_equal(flat, ref.index_create(soup).flatten(), "mixed41")
+    own = build_flat_index(shapes)
+    assert (own.cell_ids == flat.cell_ids).all()
+
+
+def test_malformed_shapes_are_rejected_not_crashed(ref):
+    soup = [s for n, s in wire_soups(ref) if n == "snapped18"][0]
+    for compact in (False, True):
+        data = ref.tagged_shapes_encode(soup, compact)
+        for cut in list(range(0, 64)) + list(range(64, len(data), 131)):
+            with pytest.raises(_lib.S2BError):
+                decode_shapes(data[:cut])
+        rng = np.random.default_rng(3 + compact)
+        bad = 0
+        for _ in range(1500):
+            b = bytearray(data)
+            for _ in range(int(rng.integers(1, 4))):
+                b[int(rng.integers(0, min(len(b), 4000)))] = int(rng.integers(0, 256))
+            try:
+                got, _ = decode_shapes(bytes(b))
+                assert got.chain_vertex_begin[-1] == len(got.vertices)
+            except _lib.S2BError:
+                bad += 1
+        assert bad > 0
+    with pytest.raises(_lib.S2BError):          # S2Polygon::Shape (tag 1) is not a supported geometry carrier
+        decode_shapes(bytes([8, 2, 1, 0]))
+
+
+def test_golden_shapes_fixture():
+    """Committed reference output (tools/gen_golden.py::shapes_wire_fixture): runs without the reference library."""
+    from tests.util import fixture
+    z = fixture("shapes_wire.npz")
+    keys = sorted({k.split("__")[0] for k in z.files})
+    assert len(keys) == 4
+    for key in keys:
+        data = z[key + "__bytes"].tobytes()
+        got, used = decode_shapes(data)
+        assert used == len(data)
+        ge, gc = edges_of(got)
+        assert (got.shape_dim == z[key + "__dims"]).all() and (gc == z[key + "__num_edges"]).all()
+        assert (ge.view(np.uint64) == z[key + "__edges"].reshape(-1, 6).view(np.uint64)).all()
+        if key.endswith("_fast"):
+            assert encode_shapes(got) == data

@@ -91,10 +91,29 @@ def wire_fixture(ref):
     np.savez_compressed(os.path.join(G, "index_wire.npz"), **out)
 
 
+def shapes_wire_fixture(ref):
+    """Tagged-shape bytes (FAST and COMPACT hints) from the reference's own lax shape encoders for a small snapped scene +
+    the edges the reference's own decoders return: pins s2b_shapes_decode / s2b_shapes_encode without the library."""
+    from tests.test_shapes_wire import wire_soups
+    out = {}
+    for name, soup in wire_soups(ref):
+        if name not in ("snapped18", "degenerate"):
+            continue
+        for compact in (False, True):
+            data = ref.tagged_shapes_encode(soup, compact)
+            dims, ne, edges = ref.tagged_shapes_decode_edges(data)
+            key = "%s_%s" % (name, "compact" if compact else "fast")
+            out[key + "__bytes"] = np.frombuffer(data, np.uint8)
+            out[key + "__dims"] = dims; out[key + "__num_edges"] = ne; out[key + "__edges"] = edges
+            print("shapes_wire", key, "bytes=%d edges=%d" % (len(data), len(edges)))
+    np.savez_compressed(os.path.join(G, "shapes_wire.npz"), **out)
+
+
 if __name__ == "__main__":
     ref = reflib.load()
     encode_fixture(ref)
     index_fixture(ref)
     wire_fixture(ref)
+    shapes_wire_fixture(ref)
     if len(sys.argv) > 1 and sys.argv[1] == "all":
         pass
