@@ -305,6 +305,13 @@ int s2b_closest_points_count_dev(const S2bPointIndex* index, const double* targe
                                  uint32_t* counts_out_dev, void* stream);
 int s2b_closest_point(const S2bPointIndex* index, const double* targets_xyz, size_t n, double max_length2, int32_t* data_out,
                       double* length2_out);
+/* FindClosestPoints with options.max_results = k (1..32) and max_distance: row i of data_out / length2_out (n x k, nullable
+ * length2_out) holds the count_out[i] (nullable) nearest index points of target i within the limit, nearest first, padded
+ * with -1 / INFINITY; among equidistant points the smaller data value comes first. */
+int s2b_closest_points(const S2bPointIndex* index, const double* targets_xyz, size_t n, int max_results, double max_length2,
+                       int32_t* data_out, double* length2_out, uint32_t* count_out);
+int s2b_closest_points_dev(const S2bPointIndex* index, const double* targets_xyz_dev, size_t n, int max_results, double max_length2,
+                           int32_t* data_out_dev, double* length2_out_dev, uint32_t* count_out_dev, void* stream);
 int s2b_closest_point_dev(const S2bPointIndex* index, const double* targets_xyz_dev, size_t n, double max_length2,
                           int32_t* data_out_dev, double* length2_out_dev, void* stream);
 

@@ -580,6 +580,24 @@ void ref_closest_point(void* h, const double* targets, size_t n, double max_dist
     }
   });
 }
+// FindClosestPoints with max_results = k: rows of k (data, length2), padded with -1 / inf, and the result counts.
+void ref_closest_points(void* h, const double* targets, size_t n, int k, double max_distance_rad, int32_t* data, double* length2, uint32_t* counts, int threads) {
+  auto* index = &((RefPointIndex*)h)->index;
+  ParallelFor(n, threads, [&](size_t b, size_t e, int) {
+    S2ClosestPointQuery<int> query(index);
+    query.mutable_options()->set_max_results(k);
+    if (max_distance_rad >= 0) query.mutable_options()->set_max_distance(S1Angle::Radians(max_distance_rad));
+    for (size_t i = b; i < e; ++i) {
+      S2ClosestPointQuery<int>::PointTarget target(P(targets + 3 * i));
+      auto r = query.FindClosestPoints(&target);
+      counts[i] = (uint32_t)r.size();
+      for (int j = 0; j < k; ++j) {
+        data[i * k + j] = j < (int)r.size() ? r[j].data() : -1;
+        length2[i * k + j] = j < (int)r.size() ? r[j].distance().length2() : HUGE_VAL;
+      }
+    }
+  });
+}
 double ref_chord_length2(double angle_rad) { return S1ChordAngle(S1Angle::Radians(angle_rad)).length2(); }
 
 // S2CellUnion::Contains(S2CellId) (bit0) and ::Intersects(S2CellId) (bit1).

@@ -258,6 +258,16 @@ class RefPointIndex:
         return data, l2
 
 
+def _closest_k(self, targets, k, max_distance_rad=-1.0, threads=0):
+    t = np.ascontiguousarray(targets, np.float64).reshape(-1, 3)
+    data = np.zeros((len(t), k), np.int32); l2 = np.zeros((len(t), k), np.float64); cnt = np.zeros(len(t), np.uint32)
+    self.lib.ref_closest_points(_vp(self.h), _p(t), _sz(len(t)), int(k), ctypes.c_double(max_distance_rad), _p(data), _p(l2), _p(cnt), int(threads))
+    return data, l2, cnt
+
+
+RefPointIndex.closest_k = _closest_k
+
+
 class RefIndex:
     """A MutableS2ShapeIndex built by the reference from a shape soup (see s2geometry_b200.shapes.ShapeSoup)."""
 

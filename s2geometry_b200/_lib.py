@@ -57,6 +57,8 @@ SIGNATURES = {
     "s2b_point_index_size": (_sz, [_vp]),
     "s2b_closest_points_count": (_i, [_vp, _vp, _sz, ctypes.c_double, _vp]),
     "s2b_closest_points_count_dev": (_i, [_vp, _vp, _sz, ctypes.c_double, _vp, _vp]),
+    "s2b_closest_points": (_i, [_vp, _vp, _sz, _i, ctypes.c_double, _vp, _vp, _vp]),
+    "s2b_closest_points_dev": (_i, [_vp, _vp, _sz, _i, ctypes.c_double, _vp, _vp, _vp, _vp]),
     "s2b_closest_point": (_i, [_vp, _vp, _sz, ctypes.c_double, _vp, _vp]),
     "s2b_closest_point_dev": (_i, [_vp, _vp, _sz, ctypes.c_double, _vp, _vp, _vp]),
     "s2b_index_build": (_i, [_i, _vp, _vp, _vp, _vp, _i, _vp]),

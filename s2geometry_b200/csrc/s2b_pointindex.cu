@@ -207,6 +207,64 @@ closest_point_kernel(const IndexView ix, const double* __restrict__ targets, siz
   }
 }
 
+// FindClosestPoints with options.max_results = k (1..kMaxResults) and max_distance: the k nearest index points of every
+// target within the limit, nearest first (ties in distance: smaller data first). Same widening search as above, with the
+// k-th best distance in place of the best. Row t of the outputs holds count[t] results, padded with -1 / +inf.
+constexpr int kMaxResults = 32;
+__global__ void __launch_bounds__(kThreads)
+closest_points_kernel(const IndexView ix, const double* __restrict__ targets, size_t n, int k, int start_level, double limit2,
+                      const double* __restrict__ covered_length2, int32_t* __restrict__ data_out, double* __restrict__ length2_out,
+                      uint32_t* __restrict__ count_out) {
+  __shared__ uint16_t s_pos[1024];
+  __shared__ double s_cov[31];
+  for (int q = threadIdx.x; q < 1024; q += kThreads) s_pos[q] = g_hilbert_pi.pos[q];
+  if (threadIdx.x < 31) s_cov[threadIdx.x] = covered_length2[threadIdx.x];
+  __syncthreads();
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < n; t += stride) {
+    const double* tq = targets + 3 * t;
+    const P3 q{tq[0], tq[1], tq[2]};
+    double fi, fj;
+    const int face = point_to_face_fij(q, &fi, &fj);
+    const int i = (int)fij_to_ij(fi), j = (int)fij_to_ij(fj);
+    double dist[kMaxResults];
+    int32_t data[kMaxResults];
+    int cnt = 0;
+    for (int level = start_level;; --level) {
+      uint64_t cells[6];
+      const int nc = covering_cells(face, i, j, level, s_pos, cells);
+      cnt = 0;
+      for (int c6 = 0; c6 < nc; ++c6) {
+        uint32_t first, last;
+        cell_range(ix, cells[c6], &first, &last);
+        for (uint32_t c = first; c < last; ++c) {
+          const double* pp = ix.pts + 3 * (size_t)c;
+          const double d = chord_length2(P3{pp[0], pp[1], pp[2]}, q);
+          if (!(d < limit2)) continue;
+          const int32_t dv = ix.data[c];
+          if (cnt == k && !(d < dist[k - 1] || (d == dist[k - 1] && dv < data[k - 1]))) continue;
+          int pos = cnt < k ? cnt : k - 1;                    // insertion into the sorted prefix
+          while (pos > 0 && (d < dist[pos - 1] || (d == dist[pos - 1] && dv < data[pos - 1]))) {
+            dist[pos] = dist[pos - 1]; data[pos] = data[pos - 1];
+            --pos;
+          }
+          dist[pos] = d; data[pos] = dv;
+          if (cnt < k) ++cnt;
+        }
+      }
+      if (level < 0) break;
+      const double covered = s_cov[level + 1];
+      if (cnt == k && dist[k - 1] < covered) break;           // the k-th nearest lies inside the guaranteed radius
+      if (covered >= limit2) break;                           // everything within the limit was covered
+    }
+    for (int r = 0; r < k; ++r) {
+      data_out[t * (size_t)k + r] = r < cnt ? data[r] : -1;
+      if (length2_out) length2_out[t * (size_t)k + r] = r < cnt ? dist[r] : HUGE_VAL;
+    }
+    if (count_out) count_out[t] = (uint32_t)cnt;
+  }
+}
+
 // kMinWidth (quadratic projection, s2metrics.cc:54-58) and Metric::GetLevelForMinValue (s2metrics.h:185-200).
 const double kMinWidthDeriv = 2 * std::sqrt(2.0) / 3;
 int level_for_min_width(double value) {
@@ -382,7 +440,64 @@ int s2b_closest_point_dev(const S2bPointIndex* ix, const double* targets_dev, si
   return e == cudaSuccess ? S2B_OK : cuda_fail(e, "closest_point launch");
 }
 
+int s2b_closest_points_dev(const S2bPointIndex* ix, const double* targets_dev, size_t n, int max_results, double max_length2,
+                           int32_t* data_out_dev, double* length2_out_dev, uint32_t* count_out_dev, void* stream) {
+  int rc = check_index_device(ix);
+  if (rc != S2B_OK) return rc;
+  if (max_results < 1 || max_results > kMaxResults) return set_error(S2B_EINVAL, "max_results must be in [1, %d]", kMaxResults);
+  if (n == 0) return S2B_OK;
+  if (!targets_dev || !data_out_dev) return set_error(S2B_EINVAL, "null pointer");
+  if (std::isnan(max_length2)) return set_error(S2B_EINVAL, "max_length2 is NaN");
+  cudaStream_t st = (cudaStream_t)stream;
+  double cov[31];
+  cov[0] = HUGE_VAL;
+  for (int L = 0; L < 30; ++L) {
+    const double r = std::ldexp(kMinWidthDeriv, -(L + 1)) * (1 - 1e-9);
+    const double len = 2 * std::sin(0.5 * r);
+    cov[L + 1] = len * len * (1 - 1e-9);
+  }
+  double* cov_dev = nullptr;
+  cudaError_t e = cudaMallocAsync((void**)&cov_dev, sizeof(cov), st);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync");
+  e = cudaMemcpyAsync(cov_dev, cov, sizeof(cov), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { cudaFreeAsync(cov_dev, st); return cuda_fail(e, "cudaMemcpyAsync"); }
+  int start = -1;   // a covering that holds ~4k + 16 index points on average
+  if (ix->m > 0) {
+    start = (int)std::floor(0.5 * std::log2((double)ix->m * 4.0 / (6.0 * (16.0 + 4.0 * max_results))));
+    start = start < -1 ? -1 : (start > 29 ? 29 : start);
+  }
+  const IndexView v{ix->ids, ix->pts, ix->data, ix->first, (uint32_t)ix->m, 61 - 2 * ix->table_level};
+  closest_points_kernel<<<grid_for_pi(n, (const void*)closest_points_kernel), kThreads, 0, st>>>(v, targets_dev, n, max_results, start, max_length2, cov_dev,
+                                                                                               data_out_dev, length2_out_dev, count_out_dev);
+  count_launch();
+  e = cudaGetLastError();
+  cudaFreeAsync(cov_dev, st);
+  return e == cudaSuccess ? S2B_OK : cuda_fail(e, "closest_points launch");
+}
+
 // Host-pointer forms (whole-array copies).
+int s2b_closest_points(const S2bPointIndex* ix, const double* targets, size_t n, int max_results, double max_length2, int32_t* data_out,
+                       double* length2_out, uint32_t* count_out) {
+  if (max_results < 1 || max_results > kMaxResults) return set_error(S2B_EINVAL, "max_results must be in [1, %d]", kMaxResults);
+  if (n == 0) return S2B_OK;
+  if (!targets || !data_out) return set_error(S2B_EINVAL, "null pointer");
+  const size_t k = (size_t)max_results;
+  void *t = nullptr, *d = nullptr, *l = nullptr, *c = nullptr;
+  cudaError_t e = cudaMalloc(&t, 24 * n);
+  if (e == cudaSuccess) e = cudaMalloc(&d, 4 * n * k);
+  if (e == cudaSuccess) e = cudaMalloc(&l, 8 * n * k);
+  if (e == cudaSuccess) e = cudaMalloc(&c, 4 * n);
+  if (e == cudaSuccess) e = cudaMemcpy(t, targets, 24 * n, cudaMemcpyHostToDevice);
+  int rc = e == cudaSuccess ? s2b_closest_points_dev(ix, (const double*)t, n, max_results, max_length2, (int32_t*)d, (double*)l, (uint32_t*)c, nullptr)
+                            : cuda_fail(e, "cudaMalloc/cudaMemcpy");
+  if (rc == S2B_OK && (e = cudaMemcpy(data_out, d, 4 * n * k, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy");
+  if (rc == S2B_OK && length2_out && (e = cudaMemcpy(length2_out, l, 8 * n * k, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy");
+  if (rc == S2B_OK && count_out && (e = cudaMemcpy(count_out, c, 4 * n, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy");
+  cudaFree(t); cudaFree(d); cudaFree(l); cudaFree(c);
+  return rc;
+}
+
 int s2b_closest_points_count(const S2bPointIndex* ix, const double* targets, size_t n, double max_length2, uint32_t* counts_out) {
   if (n == 0) return S2B_OK;
   if (!targets || !counts_out) return set_error(S2B_EINVAL, "null pointer");

@@ -88,3 +88,22 @@ class ClosestPointQuery:
         l2 = np.full(len(t), np.inf, np.float64)
         _lib.check(self._lib.s2b_closest_point(self.index._h, t.ctypes.data if t.size else None, len(t), self.max_length2, data.ctypes.data, l2.ctypes.data))
         return data, l2
+
+    def closest_k(self, targets, k):
+        """FindClosestPoints with max_results = k: (data (N,k) padded with -1, length2 (N,k) padded with inf, counts (N,))."""
+        k = int(k)
+        if _is_tensor(targets):
+            t = targets.contiguous()
+            data = torch.empty((t.shape[0], k), dtype=torch.int32, device=t.device)
+            l2 = torch.empty((t.shape[0], k), dtype=torch.float64, device=t.device)
+            cnt = torch.empty(t.shape[0], dtype=torch.int32, device=t.device)
+            _lib.check(self._lib.s2b_closest_points_dev(self.index._h, t.data_ptr(), t.shape[0], k, self.max_length2, data.data_ptr(), l2.data_ptr(),
+                                                        cnt.data_ptr(), _stream()))
+            return data, l2, cnt
+        t = np.ascontiguousarray(targets, np.float64).reshape(-1, 3)
+        data = np.full((len(t), k), -1, np.int32)
+        l2 = np.full((len(t), k), np.inf, np.float64)
+        cnt = np.zeros(len(t), np.uint32)
+        _lib.check(self._lib.s2b_closest_points(self.index._h, t.ctypes.data if t.size else None, len(t), k, self.max_length2, data.ctypes.data,
+                                                l2.ctypes.data, cnt.ctypes.data))
+        return data, l2, cnt

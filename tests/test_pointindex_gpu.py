@@ -93,6 +93,39 @@ def test_closest_point_matches_reference(torch_cuda, ref):
     assert (gl == wl).all() and (gd == wd).all()
 
 
+def test_k_closest_points_match_reference(torch_cuda, ref):
+    """FindClosestPoints with max_results = k: the sorted distance lists equal the reference's; so do the data values
+    wherever the distances are distinct (the index holds duplicates, i.e. genuine ties)."""
+    torch = torch_cuda
+    from s2geometry_b200.pointindex import ClosestPointQuery, PointIndex
+    pts, targets = scene(3, m=100_000, n=8_000)
+    ri = ref.point_index(pts)
+    ix = PointIndex(pts)
+    for k, r in ((1, None), (5, None), (32, None), (8, 0.02), (3, 1e-4), (16, 2.0)):
+        wd, wl, wc = ri.closest_k(targets, k, -1.0 if r is None else r)
+        q = ClosestPointQuery(ix) if r is None else ClosestPointQuery(ix, r)
+        gd, gl, gc = q.closest_k(targets, k)
+        assert (gc == wc).all(), (k, r)
+        assert (gl == wl).all(), (k, r)                               # exact S1ChordAngle lists, nearest first
+        assert (np.diff(np.where(np.isinf(gl), 4.0, gl), axis=1) >= 0).all()
+        distinct = np.ones_like(gl, bool)
+        distinct[:, 1:] &= gl[:, 1:] != gl[:, :-1]
+        distinct[:, :-1] &= gl[:, :-1] != gl[:, 1:]
+        last = np.take_along_axis(gl, np.maximum(gc.astype(np.int64) - 1, 0)[:, None], axis=1)
+        distinct &= gl != last                                       # the k-th place may be tied with a point left out
+        assert (gd[distinct] == wd[distinct]).all(), (k, r)
+        assert ((gd >= 0).sum(axis=1) == gc).all()
+        dd, dl, dc = q.closest_k(torch.from_numpy(targets).cuda(), k)
+        assert (dd.cpu().numpy() == gd).all() and (dl.cpu().numpy() == gl).all() and (dc.cpu().numpy().astype(np.uint32) == gc).all()
+    # k = 1 agrees with closest()
+    d1, l1 = ClosestPointQuery(ix).closest(targets)
+    dk, lk, _ = ClosestPointQuery(ix).closest_k(targets, 1)
+    assert (l1 == lk[:, 0]).all() and (d1 == dk[:, 0]).all()
+    from s2geometry_b200 import _lib
+    with pytest.raises(_lib.S2BError):
+        ClosestPointQuery(ix).closest_k(targets[:4], 33)
+
+
 def test_empty_index_and_empty_targets(torch_cuda):
     from s2geometry_b200.pointindex import ClosestPointQuery, PointIndex
     ix = PointIndex(np.zeros((0, 3)))
