@@ -21,7 +21,7 @@ soup = ShapeSoup()
 for loops in synth.many_polygons(10000, 4):
     soup.add_polygon(loops)
 soup = soup.freeze()
-q = ContainsPointQuery(ShapeIndex(build_flat_index(soup)), 1)
+q = ContainsPointQuery(ShapeIndex(build_flat_index(soup, 1)), 1)   # device granularity (S2B_MAX_EDGES_PER_CELL_DEVICE); the reference index below keeps its default
 ri = ref.index_create(soup)
 threads = ref.hardware_threads()
 gpu_counts = torch.zeros(10000, dtype=torch.int64, device=dev)
@@ -32,10 +32,12 @@ k = 0
 while done < total:
     n = min(chunk, total - done)
     pts = synth.sphere_points_cuda(n, 5000 + k, dev)
-    torch.cuda.synchronize(); t0 = time.perf_counter()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
     q.shape_histogram(pts, counts=gpu_counts)
     flags = q.contains(pts)
-    torch.cuda.synchronize(); gpu_s += time.perf_counter() - t0
+    e1.record(); torch.cuda.synchronize(); gpu_s += e0.elapsed_time(e1) * 1e-3
     host = pts.cpu().numpy()
     t0 = time.perf_counter()
     ref_counts += ri.shape_histogram(host, 1, threads)
