@@ -239,6 +239,13 @@ int s2b_index_create(const S2bFlatIndex* flat, S2bIndex** index_out);
  * Locate path. Preferable to s2b_cellunion_contains when the same union is queried with many batches. */
 int s2b_index_create_from_cellunion(const uint64_t* sorted_ids, size_t m, S2bIndex** index_out);
 void s2b_index_destroy(S2bIndex* index);
+/* S2ShapeIndex::Iterator::Locate(S2CellId) (S2CellIterator::LocateImpl, s2cell_iterator.h:159-189) for a batch of target
+ * cells: relation_out[i] = S2CellRelation (0 INDEXED: the target is contained in index cell cell_out[i]; 1 SUBDIVIDED: it
+ * contains index cells, the first is cell_out[i]; 2 DISJOINT, cell_out[i] = -1). cell_out (nullable) indexes the flat
+ * index's cell arrays. */
+int s2b_index_locate_cells(const S2bIndex* index, const uint64_t* cell_ids, size_t n, uint8_t* relation_out, int32_t* cell_out);
+int s2b_index_locate_cells_dev(const S2bIndex* index, const uint64_t* cell_ids_dev, size_t n, uint8_t* relation_out_dev,
+                               int32_t* cell_out_dev, void* stream);
 /* Any output may be NULL. device_bytes = HBM held by the replica (ids + cells + clips + edges + lookup table). */
 int s2b_index_info(const S2bIndex* index, uint64_t* num_cells, uint64_t* num_clips, uint64_t* num_edges,
                    int32_t* num_shape_ids, uint64_t* device_bytes);

@@ -413,6 +413,18 @@ int ref_index_init_matches(void* h, const uint8_t* bytes, size_t len) {
   return a.done() && b.done();
 }
 
+// Iterator::Locate(S2CellId): relation (0 INDEXED, 1 SUBDIVIDED, 2 DISJOINT) and the id of the cell the iterator is
+// positioned at afterwards (0 for DISJOINT, where the position is unspecified).
+void ref_index_locate_cells(void* h, const uint64_t* ids, size_t n, uint8_t* relation, uint64_t* at) {
+  auto& index = ((RefIndex*)h)->index;
+  MutableS2ShapeIndex::Iterator it(&index);
+  for (size_t i = 0; i < n; ++i) {
+    S2CellRelation r = it.Locate(S2CellId(ids[i]));
+    relation[i] = (uint8_t)static_cast<int>(r);
+    at[i] = r == S2CellRelation::DISJOINT ? 0 : it.id().id();
+  }
+}
+
 int ref_index_num_shape_ids(void* h) { return ((RefIndex*)h)->index.num_shape_ids(); }
 
 // S2ContainsPointQuery::Contains, one query object per thread (s2contains_point_query.h:86-91).

@@ -302,6 +302,12 @@ class RefIndex:
                                    _p(f["edge_id"]), _p(f["edge_v0"]), _p(f["edge_v1"]))
         return f
 
+    def locate_cells(self, ids):
+        ids = np.ascontiguousarray(ids, np.uint64)
+        rel = np.empty(ids.size, np.uint8); at = np.empty(ids.size, np.uint64)
+        self.lib.ref_index_locate_cells(_vp(self.h), _p(ids), _sz(ids.size), _p(rel), _p(at))
+        return rel, at
+
     def encode(self):
         """MutableS2ShapeIndex::Encode -> bytes."""
         self.lib.ref_index_encode.restype = _sz

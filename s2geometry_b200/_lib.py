@@ -73,6 +73,8 @@ SIGNATURES = {
     "s2b_index_create": (_i, [_vp, _vp]),
     "s2b_index_create_from_cellunion": (_i, [_vp, _sz, _vp]),
     "s2b_index_destroy": (None, [_vp]),
+    "s2b_index_locate_cells": (_i, [_vp, _vp, _sz, _vp, _vp]),
+    "s2b_index_locate_cells_dev": (_i, [_vp, _vp, _sz, _vp, _vp, _vp]),
     "s2b_index_info": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "s2b_contains": (_i, [_vp, _vp, _sz, _i, _vp]),
     "s2b_contains_dev": (_i, [_vp, _vp, _sz, _i, _vp, _vp]),

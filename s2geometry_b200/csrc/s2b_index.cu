@@ -418,6 +418,32 @@ cellunion_kernel(const uint64_t* __restrict__ ids, uint32_t m, const double* __r
   }
 }
 
+// S2ShapeIndex::Iterator::Locate(S2CellId target) = S2CellIterator::LocateImpl (s2cell_iterator.h:159-189): relation of a
+// target CELL to the index cells (0 INDEXED: contained in index cell `cell`; 1 SUBDIVIDED: it contains index cells, the
+// first of them is `cell`; 2 DISJOINT, cell = -1) — the classification step of coverers and region joins.
+__global__ void __launch_bounds__(kThreads)
+locate_cells_kernel(const FlatIndexView ix, const uint64_t* __restrict__ targets, size_t n, uint8_t* __restrict__ relation, int32_t* __restrict__ cell) {
+  const uint32_t C = ix.num_cells;
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < n; t += stride) {
+    const uint64_t target = __ldcs(targets + t);
+    const uint64_t tmin = cellid_range_min(target), tmax = cellid_range_max(target);
+    uint32_t lo = 0, hi = C;                                   // Seek(target.range_min()): first index cell with id >= tmin
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (ix.cell_ids[mid] < tmin) lo = mid + 1; else hi = mid; }
+    uint8_t rel = 2;
+    int32_t at = -1;
+    bool decided = false;
+    if (lo < C) {
+      const uint64_t id = ix.cell_ids[lo];
+      if (id >= target && cellid_range_min(id) <= target) { rel = 0; at = (int32_t)lo; decided = true; }
+      else if (id <= tmax) { rel = 1; at = (int32_t)lo; decided = true; }
+    }
+    if (!decided && lo > 0 && cellid_range_max(ix.cell_ids[lo - 1]) >= target) { rel = 0; at = (int32_t)lo - 1; }
+    relation[t] = rel;
+    if (cell) cell[t] = at;
+  }
+}
+
 static int grid_for_ix(size_t n, const void* kernel) {
   int per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
@@ -654,6 +680,36 @@ int s2b_index_info(const S2bIndex* ix, uint64_t* cells, uint64_t* clips, uint64_
   if (shapes) *shapes = ix->view.num_shape_ids;
   if (bytes) *bytes = ix->blob_bytes;
   return S2B_OK;
+}
+
+int s2b_index_locate_cells_dev(const S2bIndex* ix, const uint64_t* cell_ids_dev, size_t n, uint8_t* relation_out_dev, int32_t* cell_out_dev, void* stream) {
+  if (!ix) return set_error(S2B_EINVAL, "null index");
+  if (n == 0) return S2B_OK;
+  if (!cell_ids_dev || !relation_out_dev) return set_error(S2B_EINVAL, "null pointer");
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  if (dev != ix->device) return set_error(S2B_EINVAL, "the index lives on device %d but the current device is %d", ix->device, dev);
+  locate_cells_kernel<<<grid_for_ix(n, (const void*)locate_cells_kernel), kThreads, 0, (cudaStream_t)stream>>>(ix->view, cell_ids_dev, n, relation_out_dev, cell_out_dev);
+  count_launch();
+  e = cudaGetLastError();
+  return e == cudaSuccess ? S2B_OK : cuda_fail(e, "locate_cells launch");
+}
+
+int s2b_index_locate_cells(const S2bIndex* ix, const uint64_t* cell_ids, size_t n, uint8_t* relation_out, int32_t* cell_out) {
+  if (!ix) return set_error(S2B_EINVAL, "null index");
+  if (n == 0) return S2B_OK;
+  if (!cell_ids || !relation_out) return set_error(S2B_EINVAL, "null pointer");
+  void *d_ids = nullptr, *d_rel = nullptr, *d_cell = nullptr;
+  cudaError_t e = cudaMalloc(&d_ids, 8 * n);
+  if (e == cudaSuccess) e = cudaMalloc(&d_rel, n);
+  if (e == cudaSuccess) e = cudaMalloc(&d_cell, 4 * n);
+  if (e == cudaSuccess) e = cudaMemcpy(d_ids, cell_ids, 8 * n, cudaMemcpyHostToDevice);
+  int rc = e == cudaSuccess ? s2b_index_locate_cells_dev(ix, (const uint64_t*)d_ids, n, (uint8_t*)d_rel, (int32_t*)d_cell, nullptr) : cuda_fail(e, "cudaMalloc/cudaMemcpy");
+  if (rc == S2B_OK && (e = cudaMemcpy(relation_out, d_rel, n, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy");
+  if (rc == S2B_OK && cell_out && (e = cudaMemcpy(cell_out, d_cell, 4 * n, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy");
+  cudaFree(d_ids); cudaFree(d_rel); cudaFree(d_cell);
+  return rc;
 }
 
 #define S2B_QUERY_PROLOGUE                                                            \

@@ -205,6 +205,21 @@ class ShapeIndex:
         except Exception:
             pass
 
+    def locate_cells(self, cell_ids):
+        """S2ShapeIndex::Iterator::Locate(S2CellId) for a batch: (relation uint8: 0 INDEXED / 1 SUBDIVIDED / 2 DISJOINT,
+        cell int32: position of the index cell the iterator lands on, -1 when disjoint)."""
+        if _is_tensor(cell_ids):
+            ids = cell_ids.contiguous()
+            rel = torch.empty(ids.numel(), dtype=torch.uint8, device=ids.device)
+            cell = torch.empty(ids.numel(), dtype=torch.int32, device=ids.device)
+            with torch.cuda.device(ids.device):
+                _lib.check(self._lib.s2b_index_locate_cells_dev(self._h, _ptr(ids), ids.numel(), _ptr(rel), _ptr(cell), _stream()))
+            return rel, cell
+        ids = np.ascontiguousarray(cell_ids, np.uint64)
+        rel = np.empty(ids.size, np.uint8); cell = np.empty(ids.size, np.int32)
+        _lib.check(self._lib.s2b_index_locate_cells(self._h, _ptr(ids), ids.size, _ptr(rel), _ptr(cell)))
+        return rel, cell
+
     def info(self):
         c = ctypes.c_uint64(); k = ctypes.c_uint64(); e = ctypes.c_uint64(); s = ctypes.c_int32(); b = ctypes.c_uint64()
         _lib.check(self._lib.s2b_index_info(self._h, ctypes.byref(c), ctypes.byref(k), ctypes.byref(e), ctypes.byref(s), ctypes.byref(b)))

@@ -240,6 +240,31 @@ def test_device_granularity_index_gives_the_same_answers(torch_cuda, ref):
         assert (ContainsPointQuery(ix3, m).shape_histogram(q) == ri3.shape_histogram(q, m, 1)).all()
 
 
+def test_locate_cells_matches_reference(torch_cuda, ref):
+    """Iterator::Locate(S2CellId) for a batch of target cells: relation + the cell the iterator lands on."""
+    torch = torch_cuda
+    from s2geometry_b200.index import FlatIndex, ShapeIndex
+    from tests.test_encode_cpu import random_ids_all_levels
+    for soup in (scenes.loop_scene(10000)[0], scenes.polygons_scene(2000, 61, min_radius_km=100, max_radius_km=1500)):
+        ri = ref.index_create(soup)
+        flat = FlatIndex(**ri.flatten())
+        ix = ShapeIndex(flat)
+        ids = flat.cell_ids
+        lsb = ids & (~ids + np.uint64(1))
+        ok = lsb < (np.uint64(1) << np.uint64(60))
+        parents = (ids[ok] & (~(lsb[ok] << np.uint64(2)) + np.uint64(1))) | (lsb[ok] << np.uint64(2))
+        kids = (ids[lsb > 1].astype(np.int64) + (lsb[lsb > 1] >> np.uint64(2)).astype(np.int64)).astype(np.uint64)   # child 2
+        targets = np.concatenate([random_ids_all_levels(ref, 500_000, 71), ids, parents, kids, parents[::7] + np.uint64(0)])
+        want_rel, want_at = ri.locate_cells(targets)
+        rel, cell = ix.locate_cells(targets)
+        assert (rel == want_rel).all()
+        hit = rel != 2
+        assert (cell[~hit] == -1).all() and (ids[cell[hit]] == want_at[hit]).all()
+        assert set(np.unique(rel)) == {0, 1, 2}
+        drel, dcell = ix.locate_cells(torch.from_numpy(targets.view(np.int64)).cuda())
+        assert (drel.cpu().numpy() == rel).all() and (dcell.cpu().numpy() == cell).all()
+
+
 def test_cells_with_hundreds_of_edges_on_gpu(torch_cuda, ref):
     from s2geometry_b200.index import ContainsPointQuery, ShapeIndex, build_flat_index
     soup, v = scenes.loop_scene(3000)
