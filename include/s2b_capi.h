@@ -239,6 +239,17 @@ int s2b_index_create(const S2bFlatIndex* flat, S2bIndex** index_out);
  * Locate path. Preferable to s2b_cellunion_contains when the same union is queried with many batches. */
 int s2b_index_create_from_cellunion(const uint64_t* sorted_ids, size_t m, S2bIndex** index_out);
 void s2b_index_destroy(S2bIndex* index);
+/* S2ContainsPointQuery::VisitIncidentEdges (s2contains_point_query.h:305-328): for every point, the edges of its index
+ * cell that have the point as an endpoint, as (shape id, edge id) pairs in the reference's visiting order, CSR: the pairs
+ * of point i are [offsets_out[i], offsets_out[i+1]). The flat index does not carry edge ids; attach them once with
+ * s2b_index_set_edge_ids (edge_id[E] = shape-local id of every clipped edge, e.g. s2b_built_index_flat's edge_id_out).
+ * Host form: S2B_ECAPACITY with *total_out set if `capacity` is too small. Device form: count, scan, fill. */
+int s2b_index_set_edge_ids(S2bIndex* index, const int32_t* edge_id, size_t num_edges);
+int s2b_incident_edges(const S2bIndex* index, const double* xyz, size_t n, uint32_t* offsets_out, int32_t* shape_ids_out,
+                       int32_t* edge_ids_out, size_t capacity, size_t* total_out);
+int s2b_incident_edges_count_dev(const S2bIndex* index, const double* xyz_dev, size_t n, uint32_t* counts_out_dev, void* stream);
+int s2b_incident_edges_fill_dev(const S2bIndex* index, const double* xyz_dev, size_t n, const uint32_t* offsets_dev,
+                                int32_t* shape_ids_out_dev, int32_t* edge_ids_out_dev, void* stream);
 /* S2ShapeIndex::Iterator::Locate(S2CellId) (S2CellIterator::LocateImpl, s2cell_iterator.h:159-189) for a batch of target
  * cells: relation_out[i] = S2CellRelation (0 INDEXED: the target is contained in index cell cell_out[i]; 1 SUBDIVIDED: it
  * contains index cells, the first is cell_out[i]; 2 DISJOINT, cell_out[i] = -1). cell_out (nullable) indexes the flat

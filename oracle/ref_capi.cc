@@ -458,6 +458,23 @@ void ref_shape_histogram(void* h, const double* xyz, size_t n, int vertex_model,
   for (int s = 0; s < S; ++s) { uint64_t v = 0; for (auto& l : local) v += l[s]; counts[s] = v; }
 }
 
+// VisitIncidentEdges: offsets[n+1] and (shape id, edge id) pairs per point in visiting order. Returns the total count.
+uint64_t ref_incident_edges(void* h, const double* xyz, size_t n, uint32_t* offsets, int32_t* shape_ids, int32_t* edge_ids, uint64_t capacity) {
+  auto* index = &((RefIndex*)h)->index;
+  S2ContainsPointQuery<MutableS2ShapeIndex> q(index);
+  uint64_t total = 0;
+  for (size_t i = 0; i < n; ++i) {
+    offsets[i] = (uint32_t)total;
+    q.VisitIncidentEdges(P(xyz + 3 * i), [&](const s2shapeutil::ShapeEdge& e) {
+      if (total < capacity) { shape_ids[total] = e.id().shape_id; edge_ids[total] = e.id().edge_id; }
+      ++total;
+      return true;
+    });
+  }
+  offsets[n] = (uint32_t)total;
+  return total;
+}
+
 // GetContainingShapeIds: offsets[n+1] and ascending shape ids per point (capacity-limited). Returns total count.
 uint64_t ref_containing_shapes(void* h, const double* xyz, size_t n, int vertex_model, uint32_t* offsets, int32_t* ids, uint64_t capacity) {
   auto* index = &((RefIndex*)h)->index;

@@ -350,6 +350,18 @@ class RefIndex:
                 return off, ids[:total].copy()
             cap = int(total)
 
+    def incident_edges(self, xyz):
+        xyz = np.ascontiguousarray(xyz, np.float64)
+        self.lib.ref_incident_edges.restype = ctypes.c_uint64
+        off = np.empty(len(xyz) + 1, np.uint32)
+        cap = max(1024, len(xyz))
+        while True:
+            sid = np.empty(cap, np.int32); eid = np.empty(cap, np.int32)
+            total = self.lib.ref_incident_edges(_vp(self.h), _p(xyz), _sz(len(xyz)), _p(off), _p(sid), _p(eid), ctypes.c_uint64(cap))
+            if total <= cap:
+                return off, sid[:total].copy(), eid[:total].copy()
+            cap = int(total)
+
     def brute_force_contains(self, shape_id, xyz, threads=0):
         xyz = np.ascontiguousarray(xyz, np.float64)
         out = np.empty(len(xyz), np.uint8)

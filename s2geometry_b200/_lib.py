@@ -73,6 +73,10 @@ SIGNATURES = {
     "s2b_index_create": (_i, [_vp, _vp]),
     "s2b_index_create_from_cellunion": (_i, [_vp, _sz, _vp]),
     "s2b_index_destroy": (None, [_vp]),
+    "s2b_index_set_edge_ids": (_i, [_vp, _vp, _sz]),
+    "s2b_incident_edges": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp]),
+    "s2b_incident_edges_count_dev": (_i, [_vp, _vp, _sz, _vp, _vp]),
+    "s2b_incident_edges_fill_dev": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, _vp]),
     "s2b_index_locate_cells": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "s2b_index_locate_cells_dev": (_i, [_vp, _vp, _sz, _vp, _vp, _vp]),
     "s2b_index_info": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),

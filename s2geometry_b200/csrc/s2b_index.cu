@@ -444,6 +444,41 @@ locate_cells_kernel(const FlatIndexView ix, const uint64_t* __restrict__ targets
   }
 }
 
+// S2ContainsPointQuery::VisitIncidentEdges (s2contains_point_query.h:305-328): the edges of the located cell that have
+// the query point as an endpoint (operator== on S2Point, so -0 == +0), as (shape id, edge id) pairs in the reference's
+// visiting order (clipped shapes in cell order, edges in clipped order). kFill = false: per-point counts; true: pairs
+// written at offsets[i]. One thread per point, exact FP64 Locate (this is a low-volume query next to Contains).
+template <bool kFill>
+__global__ void __launch_bounds__(kThreads)
+incident_edges_kernel(const FlatIndexView ix, const int32_t* __restrict__ edge_ids, const double* __restrict__ xyz, size_t n,
+                      uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets, int32_t* __restrict__ shape_out, int32_t* __restrict__ edge_out) {
+  __shared__ uint16_t s_pos[1024];
+  for (int k = threadIdx.x; k < 1024; k += kThreads) s_pos[k] = g_hilbert_ix.pos[k];
+  __syncthreads();
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < n; t += stride) {
+    const double* q = xyz + 3 * t;
+    const P3 p{q[0], q[1], q[2]};
+    uint32_t cnt = 0;
+    uint32_t at = kFill ? offsets[t] : 0u;
+    const int c = locate_point(ix, p, s_pos);
+    if (c >= 0) {
+      const FlatCell fc = ix.cells[c];
+      for (uint32_t k = 0; k < fc.clip_count; ++k) {
+        const FlatClip clip = ix.clips[fc.clip_begin + k];
+        for (uint32_t e = 0; e < clip.num_edges; ++e) {
+          const FlatEdge ed = ix.edges[clip.edge_begin + e];
+          if (eq(edge_v0(ed), p) || eq(edge_v1(ed), p)) {
+            if (kFill) { shape_out[at] = clip.shape_id; edge_out[at] = edge_ids[clip.edge_begin + e]; ++at; }
+            ++cnt;
+          }
+        }
+      }
+    }
+    if (!kFill) counts[t] = cnt;
+  }
+}
+
 static int grid_for_ix(size_t n, const void* kernel) {
   int per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
@@ -576,6 +611,7 @@ struct S2bIndex {
   void* blob = nullptr;   // one allocation holding every array
   size_t blob_bytes = 0;
   uint64_t num_clips = 0, num_edges = 0;
+  int32_t* edge_ids = nullptr;   // optional (s2b_index_set_edge_ids): shape-local id of every clipped edge, for VisitIncidentEdges
 };
 
 namespace s2b {
@@ -668,6 +704,7 @@ void s2b_index_destroy(S2bIndex* ix) {
   cudaGetDevice(&cur);
   if (cur != ix->device) cudaSetDevice(ix->device);
   if (ix->blob) cudaFree(ix->blob);
+  if (ix->edge_ids) cudaFree(ix->edge_ids);
   if (cur != ix->device) cudaSetDevice(cur);
   delete ix;
 }
@@ -680,6 +717,91 @@ int s2b_index_info(const S2bIndex* ix, uint64_t* cells, uint64_t* clips, uint64_
   if (shapes) *shapes = ix->view.num_shape_ids;
   if (bytes) *bytes = ix->blob_bytes;
   return S2B_OK;
+}
+
+int s2b_index_set_edge_ids(S2bIndex* ix, const int32_t* edge_id, size_t num_edges) {
+  if (!ix) return set_error(S2B_EINVAL, "null index");
+  if (num_edges != ix->num_edges) return set_error(S2B_EINVAL, "the index has %llu clipped edges, %zu edge ids were given", (unsigned long long)ix->num_edges, num_edges);
+  if (num_edges && !edge_id) return set_error(S2B_EINVAL, "null edge ids");
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  if (dev != ix->device) return set_error(S2B_EINVAL, "the index lives on device %d but the current device is %d", ix->device, dev);
+  if (ix->edge_ids) { cudaFree(ix->edge_ids); ix->edge_ids = nullptr; }
+  e = cudaMalloc((void**)&ix->edge_ids, sizeof(int32_t) * (num_edges ? num_edges : 1));
+  if (e != cudaSuccess) { ix->edge_ids = nullptr; return cuda_fail(e, "cudaMalloc(edge ids)"); }
+  if (num_edges && (e = cudaMemcpy(ix->edge_ids, edge_id, sizeof(int32_t) * num_edges, cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy(edge ids)");
+  return S2B_OK;
+}
+
+static int incident_prologue(const S2bIndex* ix) {
+  if (!ix) return set_error(S2B_EINVAL, "null index");
+  if (!ix->edge_ids) return set_error(S2B_EINVAL, "incident-edge queries need the edge ids: call s2b_index_set_edge_ids first");
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  if (dev != ix->device) return set_error(S2B_EINVAL, "the index lives on device %d but the current device is %d", ix->device, dev);
+  return S2B_OK;
+}
+
+int s2b_incident_edges_count_dev(const S2bIndex* ix, const double* xyz_dev, size_t n, uint32_t* counts_out_dev, void* stream) {
+  int rc = incident_prologue(ix);
+  if (rc != S2B_OK || n == 0) return rc;
+  if (!xyz_dev || !counts_out_dev) return set_error(S2B_EINVAL, "null pointer");
+  const auto k = incident_edges_kernel<false>;
+  k<<<grid_for_ix(n, (const void*)k), kThreads, 0, (cudaStream_t)stream>>>(ix->view, ix->edge_ids, xyz_dev, n, counts_out_dev, nullptr, nullptr, nullptr);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? S2B_OK : cuda_fail(e, "incident_edges launch");
+}
+
+int s2b_incident_edges_fill_dev(const S2bIndex* ix, const double* xyz_dev, size_t n, const uint32_t* offsets_dev, int32_t* shape_ids_out_dev,
+                                int32_t* edge_ids_out_dev, void* stream) {
+  int rc = incident_prologue(ix);
+  if (rc != S2B_OK || n == 0) return rc;
+  if (!xyz_dev || !offsets_dev || !shape_ids_out_dev || !edge_ids_out_dev) return set_error(S2B_EINVAL, "null pointer");
+  const auto k = incident_edges_kernel<true>;
+  k<<<grid_for_ix(n, (const void*)k), kThreads, 0, (cudaStream_t)stream>>>(ix->view, ix->edge_ids, xyz_dev, n, nullptr, offsets_dev, shape_ids_out_dev, edge_ids_out_dev);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? S2B_OK : cuda_fail(e, "incident_edges launch");
+}
+
+// Host-pointer form: counts, host scan, fill (whole-array copies; this is a low-volume query).
+int s2b_incident_edges(const S2bIndex* ix, const double* xyz, size_t n, uint32_t* offsets_out, int32_t* shape_ids_out, int32_t* edge_ids_out,
+                       size_t capacity, size_t* total_out) {
+  int rc = incident_prologue(ix);
+  if (rc != S2B_OK) return rc;
+  if (!offsets_out) return set_error(S2B_EINVAL, "null offsets_out");
+  if (total_out) *total_out = 0;
+  offsets_out[0] = 0;
+  if (n == 0) return S2B_OK;
+  if (!xyz) return set_error(S2B_EINVAL, "null pointer");
+  void *d_xyz = nullptr, *d_off = nullptr, *d_shape = nullptr, *d_edge = nullptr;
+  cudaError_t e = cudaMalloc(&d_xyz, 24 * n);
+  if (e == cudaSuccess) e = cudaMalloc(&d_off, 4 * (n + 1));
+  if (e == cudaSuccess) e = cudaMemcpy(d_xyz, xyz, 24 * n, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) rc = cuda_fail(e, "cudaMalloc/cudaMemcpy");
+  if (rc == S2B_OK) rc = s2b_incident_edges_count_dev(ix, (const double*)d_xyz, n, (uint32_t*)d_off, nullptr);
+  if (rc == S2B_OK && (e = cudaMemcpy(offsets_out + 1, d_off, 4 * n, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy");
+  uint64_t total = 0;
+  if (rc == S2B_OK) {
+    for (size_t i = 1; i <= n; ++i) { total += offsets_out[i]; offsets_out[i] = (uint32_t)total; }
+    if (total > 0xFFFFFFFFull) rc = set_error(S2B_ECAPACITY, "more than 2^32 incident edges: split the batch");
+  }
+  if (rc == S2B_OK && total_out) *total_out = (size_t)total;
+  if (rc == S2B_OK && total > capacity) rc = set_error(S2B_ECAPACITY, "capacity %zu < %llu incident edges", capacity, (unsigned long long)total);
+  if (rc == S2B_OK && total > 0) {
+    if (!shape_ids_out || !edge_ids_out) rc = set_error(S2B_EINVAL, "null output arrays");
+    if (rc == S2B_OK && (e = cudaMalloc(&d_shape, 4 * total)) != cudaSuccess) rc = cuda_fail(e, "cudaMalloc");
+    if (rc == S2B_OK && (e = cudaMalloc(&d_edge, 4 * total)) != cudaSuccess) rc = cuda_fail(e, "cudaMalloc");
+    if (rc == S2B_OK && (e = cudaMemcpy(d_off, offsets_out, 4 * n, cudaMemcpyHostToDevice)) != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy");
+    if (rc == S2B_OK) rc = s2b_incident_edges_fill_dev(ix, (const double*)d_xyz, n, (const uint32_t*)d_off, (int32_t*)d_shape, (int32_t*)d_edge, nullptr);
+    if (rc == S2B_OK && (e = cudaMemcpy(shape_ids_out, d_shape, 4 * total, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy");
+    if (rc == S2B_OK && (e = cudaMemcpy(edge_ids_out, d_edge, 4 * total, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy");
+  }
+  cudaFree(d_xyz); cudaFree(d_off); cudaFree(d_shape); cudaFree(d_edge);
+  return rc;
 }
 
 int s2b_index_locate_cells_dev(const S2bIndex* ix, const uint64_t* cell_ids_dev, size_t n, uint8_t* relation_out_dev, int32_t* cell_out_dev, void* stream) {

@@ -191,6 +191,10 @@ class ShapeIndex:
         st = flat.as_struct()
         _lib.check(self._lib.s2b_index_create(ctypes.byref(st), ctypes.byref(h)))
         self._h = h
+        eid = getattr(flat, "edge_id", None)
+        if eid is not None:      # optional: shape-local edge ids enable incident-edge queries
+            eid = np.ascontiguousarray(eid, np.int32)
+            _lib.check(self._lib.s2b_index_set_edge_ids(h, eid.ctypes.data if eid.size else None, eid.size))
         self.num_shape_ids = flat.num_shape_ids
         self.device = torch.cuda.current_device() if torch is not None and torch.cuda.is_available() else 0
 
@@ -310,6 +314,36 @@ class ContainsPointQuery:
             out = np.zeros(S, np.uint64)
             _lib.check(self._lib.s2b_shape_histogram(self.index._h, _ptr(p), n, self.model, _ptr(out)))
             return out
+
+    def incident_edges(self, xyz):
+        """VisitIncidentEdges for a batch in CSR form: (offsets (N+1,), shape_ids, edge_ids) — the edges of each point's
+        index cell that have the point as an endpoint. The index must have been created from a FlatIndex with .edge_id."""
+        p = _points(xyz)
+        n = p.shape[0]
+        with self._check_device(p):
+            if _is_tensor(p):
+                cnt = torch.empty(n, dtype=torch.int32, device=p.device)
+                _lib.check(self._lib.s2b_incident_edges_count_dev(self.index._h, _ptr(p), n, _ptr(cnt), _stream()))
+                off = torch.zeros(n + 1, dtype=torch.int64, device=p.device)
+                torch.cumsum(cnt, 0, out=off[1:])
+                total = int(off[-1].item())
+                off32 = off.to(torch.int32)
+                sid = torch.empty(max(total, 1), dtype=torch.int32, device=p.device)
+                eid = torch.empty(max(total, 1), dtype=torch.int32, device=p.device)
+                if total:
+                    _lib.check(self._lib.s2b_incident_edges_fill_dev(self.index._h, _ptr(p), n, _ptr(off32), _ptr(sid), _ptr(eid), _stream()))
+                return off32, sid[:total], eid[:total]
+            off = np.empty(n + 1, np.uint32)
+            total = ctypes.c_size_t(0)
+            cap = max(1024, n // 8)
+            while True:
+                sid = np.empty(cap, np.int32); eid = np.empty(cap, np.int32)
+                rc = self._lib.s2b_incident_edges(self.index._h, _ptr(p), n, _ptr(off), _ptr(sid), _ptr(eid), cap, ctypes.byref(total))
+                if rc == -4 and total.value > cap:
+                    cap = total.value
+                    continue
+                _lib.check(rc)
+                return off, sid[: total.value].copy(), eid[: total.value].copy()
 
     def containing_shape_ids(self, xyz):
         """GetContainingShapeIds for a batch in CSR form: (offsets (N+1,), shape_ids)."""

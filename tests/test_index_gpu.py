@@ -240,6 +240,39 @@ def test_device_granularity_index_gives_the_same_answers(torch_cuda, ref):
         assert (ContainsPointQuery(ix3, m).shape_histogram(q) == ri3.shape_histogram(q, m, 1)).all()
 
 
+def test_incident_edges_match_reference(torch_cuda, ref):
+    """VisitIncidentEdges: for polygon vertices (two incident edges each, more where polygons share vertices), polyline
+    ends, point shapes, -0.0 coordinates and ordinary points (none)."""
+    torch = torch_cuda
+    from s2geometry_b200 import S2BError, synth
+    from s2geometry_b200.index import ContainsPointQuery, FlatIndex, ShapeIndex, build_flat_index
+    from tests.test_index_wire import mixed_soup
+    for name, soup in (("mixed", mixed_soup(51, 40)), ("axis", scenes.axis_aligned_scene()), ("loop", scenes.loop_scene(3000)[0])):
+        ri = ref.index_create(soup)
+        verts = np.asarray(soup.vertices).reshape(-1, 3)
+        flipped = verts[:200].copy(); flipped[flipped == 0] = -0.0                # operator== treats -0 and +0 alike
+        q = np.concatenate([verts, flipped, synth.sphere_points(100_000, 5)])
+        woff, wsid, weid = ri.incident_edges(q)
+        assert len(wsid) >= len(verts)
+        for flat in (FlatIndex(**ri.flatten()), build_flat_index(soup, 1)):       # reference-built and own fine-grained index
+            flat.edge_id = np.asarray(flat.edge_id if hasattr(flat, "edge_id") else ri.flatten()["edge_id"], np.int32)
+            query = ContainsPointQuery(ShapeIndex(flat), 1)
+            off, sid, eid = query.incident_edges(q)
+            assert (off == woff).all(), name
+            # the reference visits clipped shapes in cell order and edges in clipped order: same order for the same cells;
+            # a different (finer) index may clip differently, so compare per-point sets there
+            key = lambda o, s, e: [sorted(zip(s[o[i]:o[i + 1]].tolist(), e[o[i]:o[i + 1]].tolist())) for i in range(0, len(o) - 1, 97)]
+            assert key(off, sid, eid) == key(woff, wsid, weid), name
+            d_off, d_sid, d_eid = query.incident_edges(torch.from_numpy(q).cuda())
+            assert (d_off.cpu().numpy().astype(np.uint32) == off).all() and (d_sid.cpu().numpy() == sid).all() and (d_eid.cpu().numpy() == eid).all()
+        same = FlatIndex(**ri.flatten()); same.edge_id = ri.flatten()["edge_id"]
+        off, sid, eid = ContainsPointQuery(ShapeIndex(same), 1).incident_edges(q)
+        assert (sid == wsid).all() and (eid == weid).all(), name                  # identical order over identical cells
+    bare = FlatIndex(**{k: v for k, v in ri.flatten().items() if k != "edge_id"})
+    with pytest.raises(S2BError):
+        ContainsPointQuery(ShapeIndex(bare), 1).incident_edges(q[:10])           # no edge ids attached
+
+
 def test_locate_cells_matches_reference(torch_cuda, ref):
     """Iterator::Locate(S2CellId) for a batch of target cells: relation + the cell the iterator lands on."""
     torch = torch_cuda
