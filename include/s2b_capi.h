@@ -250,6 +250,10 @@ int s2b_incident_edges(const S2bIndex* index, const double* xyz, size_t n, uint3
 int s2b_incident_edges_count_dev(const S2bIndex* index, const double* xyz_dev, size_t n, uint32_t* counts_out_dev, void* stream);
 int s2b_incident_edges_fill_dev(const S2bIndex* index, const double* xyz_dev, size_t n, const uint32_t* offsets_dev,
                                 int32_t* shape_ids_out_dev, int32_t* edge_ids_out_dev, void* stream);
+/* S2ShapeIndex::Iterator::Locate(const S2Point&) (S2CellIterator::LocateImpl, s2cell_iterator.h:137-157) as a batch query:
+ * cell_out[i] = position (in the flat index's cell arrays) of the index cell containing point i, or -1. */
+int s2b_index_locate_points(const S2bIndex* index, const double* xyz, size_t n, int32_t* cell_out);
+int s2b_index_locate_points_dev(const S2bIndex* index, const double* xyz_dev, size_t n, int32_t* cell_out_dev, void* stream);
 /* S2ShapeIndex::Iterator::Locate(S2CellId) (S2CellIterator::LocateImpl, s2cell_iterator.h:159-189) for a batch of target
  * cells: relation_out[i] = S2CellRelation (0 INDEXED: the target is contained in index cell cell_out[i]; 1 SUBDIVIDED: it
  * contains index cells, the first is cell_out[i]; 2 DISJOINT, cell_out[i] = -1). cell_out (nullable) indexes the flat

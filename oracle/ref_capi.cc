@@ -413,6 +413,15 @@ int ref_index_init_matches(void* h, const uint8_t* bytes, size_t len) {
   return a.done() && b.done();
 }
 
+// Iterator::Locate(S2Point): id of the containing index cell, or 0.
+void ref_index_locate_points(void* h, const double* xyz, size_t n, uint64_t* at, int threads) {
+  auto* index = &((RefIndex*)h)->index;
+  ParallelFor(n, threads, [&](size_t b, size_t e, int) {
+    MutableS2ShapeIndex::Iterator it(index);
+    for (size_t i = b; i < e; ++i) at[i] = it.Locate(P(xyz + 3 * i)) ? it.id().id() : 0;
+  });
+}
+
 // Iterator::Locate(S2CellId): relation (0 INDEXED, 1 SUBDIVIDED, 2 DISJOINT) and the id of the cell the iterator is
 // positioned at afterwards (0 for DISJOINT, where the position is unspecified).
 void ref_index_locate_cells(void* h, const uint64_t* ids, size_t n, uint8_t* relation, uint64_t* at) {

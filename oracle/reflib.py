@@ -302,6 +302,12 @@ class RefIndex:
                                    _p(f["edge_id"]), _p(f["edge_v0"]), _p(f["edge_v1"]))
         return f
 
+    def locate_points(self, xyz, threads=0):
+        xyz = np.ascontiguousarray(xyz, np.float64)
+        at = np.empty(len(xyz), np.uint64)
+        self.lib.ref_index_locate_points(_vp(self.h), _p(xyz), _sz(len(xyz)), _p(at), int(threads))
+        return at
+
     def locate_cells(self, ids):
         ids = np.ascontiguousarray(ids, np.uint64)
         rel = np.empty(ids.size, np.uint8); at = np.empty(ids.size, np.uint64)

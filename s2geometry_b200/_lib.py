@@ -77,6 +77,8 @@ SIGNATURES = {
     "s2b_incident_edges": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp]),
     "s2b_incident_edges_count_dev": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "s2b_incident_edges_fill_dev": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "s2b_index_locate_points": (_i, [_vp, _vp, _sz, _vp]),
+    "s2b_index_locate_points_dev": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "s2b_index_locate_cells": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "s2b_index_locate_cells_dev": (_i, [_vp, _vp, _sz, _vp, _vp, _vp]),
     "s2b_index_info": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),

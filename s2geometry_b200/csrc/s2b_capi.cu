@@ -416,6 +416,15 @@ int s2b_contains(const S2bIndex* ix, const double* xyz, size_t n, int model, uin
   });
 }
 
+int s2b_index_locate_points(const S2bIndex* ix, const double* xyz, size_t n, int32_t* cell_out) {
+  if (n && (!xyz || !cell_out)) return set_error(S2B_EINVAL, "null pointer");
+  if (n == 0) return s2b_index_locate_points_dev(ix, nullptr, 0, nullptr, nullptr);
+  OutSpec outs[1] = {{cell_out, 4, 1}};
+  return run_pipelined(xyz, 24, n, outs, 1, [&](const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
+    return s2b_index_locate_points_dev(ix, (const double*)in_dev, cnt, (int32_t*)out_dev[0], st);
+  });
+}
+
 int s2b_shape_contains(const S2bIndex* ix, int shape_id, const double* xyz, size_t n, int model, uint8_t* out) {
   if (n && (!xyz || !out)) return set_error(S2B_EINVAL, "null pointer");
   if (n == 0) return s2b_shape_contains_dev(ix, shape_id, nullptr, 0, model, nullptr, nullptr);

@@ -444,6 +444,20 @@ locate_cells_kernel(const FlatIndexView ix, const uint64_t* __restrict__ targets
   }
 }
 
+// S2ShapeIndex::Iterator::Locate(const S2Point&) (S2CellIterator::LocateImpl, s2cell_iterator.h:137-157) as a query of its
+// own: cell[i] = position of the index cell containing point i, or -1. Exact FP64 projection + the lookup table.
+__global__ void __launch_bounds__(kThreads)
+locate_points_kernel(const FlatIndexView ix, const double* __restrict__ xyz, size_t n, int32_t* __restrict__ cell) {
+  __shared__ uint16_t s_pos[1024];
+  for (int k = threadIdx.x; k < 1024; k += kThreads) s_pos[k] = g_hilbert_ix.pos[k];
+  __syncthreads();
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < n; t += stride) {
+    const double* q = xyz + 3 * t;
+    cell[t] = locate_point(ix, P3{__ldcs(q), __ldcs(q + 1), __ldcs(q + 2)}, s_pos);
+  }
+}
+
 // S2ContainsPointQuery::VisitIncidentEdges (s2contains_point_query.h:305-328): the edges of the located cell that have
 // the query point as an endpoint (operator== on S2Point, so -0 == +0), as (shape id, edge id) pairs in the reference's
 // visiting order (clipped shapes in cell order, edges in clipped order). kFill = false: per-point counts; true: pairs
@@ -717,6 +731,20 @@ int s2b_index_info(const S2bIndex* ix, uint64_t* cells, uint64_t* clips, uint64_
   if (shapes) *shapes = ix->view.num_shape_ids;
   if (bytes) *bytes = ix->blob_bytes;
   return S2B_OK;
+}
+
+int s2b_index_locate_points_dev(const S2bIndex* ix, const double* xyz_dev, size_t n, int32_t* cell_out_dev, void* stream) {
+  if (!ix) return set_error(S2B_EINVAL, "null index");
+  if (n == 0) return S2B_OK;
+  if (!xyz_dev || !cell_out_dev) return set_error(S2B_EINVAL, "null pointer");
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  if (dev != ix->device) return set_error(S2B_EINVAL, "the index lives on device %d but the current device is %d", ix->device, dev);
+  locate_points_kernel<<<grid_for_ix(n, (const void*)locate_points_kernel), kThreads, 0, (cudaStream_t)stream>>>(ix->view, xyz_dev, n, cell_out_dev);
+  count_launch();
+  e = cudaGetLastError();
+  return e == cudaSuccess ? S2B_OK : cuda_fail(e, "locate_points launch");
 }
 
 int s2b_index_set_edge_ids(S2bIndex* ix, const int32_t* edge_id, size_t num_edges) {

@@ -209,6 +209,19 @@ class ShapeIndex:
         except Exception:
             pass
 
+    def locate_points(self, xyz):
+        """S2ShapeIndex::Iterator::Locate(S2Point) for a batch: position of the containing index cell per point, or -1."""
+        p = _points(xyz)
+        n = p.shape[0]
+        if _is_tensor(p):
+            out = torch.empty(n, dtype=torch.int32, device=p.device)
+            with torch.cuda.device(p.device):
+                _lib.check(self._lib.s2b_index_locate_points_dev(self._h, _ptr(p), n, _ptr(out), _stream()))
+            return out
+        out = np.empty(n, np.int32)
+        _lib.check(self._lib.s2b_index_locate_points(self._h, _ptr(p), n, _ptr(out)))
+        return out
+
     def locate_cells(self, cell_ids):
         """S2ShapeIndex::Iterator::Locate(S2CellId) for a batch: (relation uint8: 0 INDEXED / 1 SUBDIVIDED / 2 DISJOINT,
         cell int32: position of the index cell the iterator lands on, -1 when disjoint)."""

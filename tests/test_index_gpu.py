@@ -296,6 +296,14 @@ def test_locate_cells_matches_reference(torch_cuda, ref):
         assert set(np.unique(rel)) == {0, 1, 2}
         drel, dcell = ix.locate_cells(torch.from_numpy(targets.view(np.int64)).cuda())
         assert (drel.cpu().numpy() == rel).all() and (dcell.cpu().numpy() == cell).all()
+        # Locate(S2Point): the containing index cell of every point (uniform, near the geometry, on its vertices)
+        from s2geometry_b200 import synth
+        pts = np.concatenate([synth.sphere_points(1_000_000, 73), synth.cap_points(scenes.LOOP_CENTER, 0.25, 500_000, 74),
+                              np.asarray(soup.vertices).reshape(-1, 3)[:100_000], flat.cell_center.reshape(-1, 3)])
+        want = ri.locate_points(pts)
+        got = ix.locate_points(pts)
+        assert ((got >= 0) == (want != 0)).all() and (ids[got[got >= 0]] == want[want != 0]).all()
+        assert (ix.locate_points(torch.from_numpy(pts).cuda()).cpu().numpy() == got).all()
 
 
 def test_cells_with_hundreds_of_edges_on_gpu(torch_cuda, ref):
