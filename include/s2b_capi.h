@@ -127,6 +127,11 @@ int s2b_cellid_to_latlng_dev(const uint64_t* ids_dev, size_t n, double* latlng_r
  * FromFaceIJWrap (:458-489). */
 int s2b_cellid_edge_neighbors(const uint64_t* ids, size_t n, uint64_t* neighbors4_out);
 int s2b_cellid_edge_neighbors_dev(const uint64_t* ids_dev, size_t n, uint64_t* neighbors4_out_dev, void* stream);
+/* S2CellId::is_valid / level / range_min / range_max (s2cell_id.h:583-603, 642-652) element-wise; every output is
+ * optional (NULL). level_out is -1 for invalid ids. */
+int s2b_cellid_info(const uint64_t* ids, size_t n, uint8_t* valid_out, int8_t* level_out, uint64_t* range_min_out, uint64_t* range_max_out);
+int s2b_cellid_info_dev(const uint64_t* ids_dev, size_t n, uint8_t* valid_out_dev, int8_t* level_out_dev, uint64_t* range_min_out_dev,
+                        uint64_t* range_max_out_dev, void* stream);
 /* S2CellId::AppendVertexNeighbors(level) (s2cell_id.cc:514-556): the cells of `level` around the vertex of
  * parent(level) closest to the cell, in the reference's order: neighbors4_out[4*i + k], count_out[i] = 3 (cube vertex)
  * or 4; unused slots are 0. Requires level < level(ids[i]) (as the reference does); otherwise count 0. */

@@ -239,6 +239,23 @@ def edge_neighbors(ids):
     return out
 
 
+def info(ids):
+    """S2CellId::is_valid / level / range_min / range_max element-wise -> (valid bool, level int8 (-1 if invalid), range_min, range_max)."""
+    lib = _lib.load()
+    if _is_tensor(ids):
+        ids = _tensor_in(ids, torch.int64, 0)
+        n = ids.numel()
+        v = torch.empty(n, dtype=torch.uint8, device=ids.device); l = torch.empty(n, dtype=torch.int8, device=ids.device)
+        a = torch.empty(n, dtype=torch.int64, device=ids.device); b = torch.empty(n, dtype=torch.int64, device=ids.device)
+        with torch.cuda.device(ids.device):
+            _lib.check(lib.s2b_cellid_info_dev(_ptr(ids), n, _ptr(v), _ptr(l), _ptr(a), _ptr(b), _stream()))
+        return v != 0, l, a, b
+    ids = _np_in(ids, np.uint64, 0)
+    v = np.empty(ids.size, np.uint8); l = np.empty(ids.size, np.int8); a = np.empty(ids.size, np.uint64); b = np.empty(ids.size, np.uint64)
+    _lib.check(lib.s2b_cellid_info(_ptr(ids), ids.size, _ptr(v), _ptr(l), _ptr(a), _ptr(b)))
+    return v != 0, l, a, b
+
+
 def vertex_neighbors(ids, level):
     """S2CellId::AppendVertexNeighbors(level) element-wise -> ((N,4) ids, (N,) counts): 3 or 4 cells of `level` around the
     closest vertex of parent(level), reference order, unused slots 0. Requires level < level(id)."""

@@ -139,6 +139,22 @@ union_cells_kernel(const uint64_t* __restrict__ u, size_t m, const uint64_t* __r
   }
 }
 
+// S2CellId::is_valid / level / range_min / range_max (s2cell_id.h:583-603, 642-652), any output nullable. level is -1 for
+// invalid ids (the reference's level() is undefined there).
+__global__ void __launch_bounds__(kThreads)
+cellid_info_kernel(const uint64_t* __restrict__ ids, size_t n, uint8_t* __restrict__ valid, int8_t* __restrict__ level,
+                   uint64_t* __restrict__ rmin, uint64_t* __restrict__ rmax) {
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < n; t += stride) {
+    const uint64_t id = __ldcs(ids + t);
+    const bool ok = cellid_is_valid(id);
+    if (valid) valid[t] = ok ? 1 : 0;
+    if (level) level[t] = ok ? (int8_t)cellid_level(id) : (int8_t)-1;
+    if (rmin) rmin[t] = cellid_range_min(id);
+    if (rmax) rmax[t] = cellid_range_max(id);
+  }
+}
+
 // ---- Normalize -----------------------------------------------------------------------------------------------------
 struct MaxOp { __host__ __device__ __forceinline__ uint64_t operator()(uint64_t a, uint64_t b) const { return a > b ? a : b; } };
 struct MinOp { __host__ __device__ __forceinline__ uint64_t operator()(uint64_t a, uint64_t b) const { return a < b ? a : b; } };
@@ -301,6 +317,17 @@ int s2b_cellid_vertex_neighbors_dev(const uint64_t* ids_dev, size_t n, int level
   return e == cudaSuccess ? S2B_OK : cuda_fail(e, "vertex_neighbors launch");
 }
 
+int s2b_cellid_info_dev(const uint64_t* ids_dev, size_t n, uint8_t* valid_out_dev, int8_t* level_out_dev, uint64_t* range_min_out_dev,
+                        uint64_t* range_max_out_dev, void* stream) {
+  if (n == 0) return S2B_OK;
+  if (!ids_dev) return set_error(S2B_EINVAL, "null pointer");
+  cellid_info_kernel<<<grid_for_ops(n, (const void*)cellid_info_kernel), kThreads, 0, (cudaStream_t)stream>>>(ids_dev, n, valid_out_dev, level_out_dev,
+                                                                                                            range_min_out_dev, range_max_out_dev);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? S2B_OK : cuda_fail(e, "cellid_info launch");
+}
+
 int s2b_cellid_all_neighbors_dev(const uint64_t* ids_dev, size_t n, int nbr_level, uint64_t* out_dev, size_t out_stride, uint32_t* count_out_dev, void* stream) {
   if (nbr_level < 0 || nbr_level > 30) return set_error(S2B_EINVAL, "nbr_level %d out of range [0,30]", nbr_level);
   if (n == 0) return S2B_OK;
@@ -338,6 +365,23 @@ int s2b_cellid_vertex_neighbors(const uint64_t* ids, size_t n, int level, uint64
   if (rc != S2B_OK) return rc;
   if ((e = cudaMemcpy(neighbors4_out, out.p, 32 * n, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
   if (count_out && (e = cudaMemcpy(count_out, cnt.p, n, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
+  return S2B_OK;
+}
+
+int s2b_cellid_info(const uint64_t* ids, size_t n, uint8_t* valid_out, int8_t* level_out, uint64_t* range_min_out, uint64_t* range_max_out) {
+  if (n == 0) return S2B_OK;
+  if (!ids) return set_error(S2B_EINVAL, "null pointer");
+  DevBuf in, v, l, a, b;
+  cudaError_t e;
+  if ((e = in.alloc(8 * n)) != cudaSuccess || (e = v.alloc(n)) != cudaSuccess || (e = l.alloc(n)) != cudaSuccess || (e = a.alloc(8 * n)) != cudaSuccess ||
+      (e = b.alloc(8 * n)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+  if ((e = cudaMemcpy(in.p, ids, 8 * n, cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
+  int rc = s2b_cellid_info_dev((const uint64_t*)in.p, n, (uint8_t*)v.p, (int8_t*)l.p, (uint64_t*)a.p, (uint64_t*)b.p, nullptr);
+  if (rc != S2B_OK) return rc;
+  if (valid_out && (e = cudaMemcpy(valid_out, v.p, n, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
+  if (level_out && (e = cudaMemcpy(level_out, l.p, n, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
+  if (range_min_out && (e = cudaMemcpy(range_min_out, a.p, 8 * n, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
+  if (range_max_out && (e = cudaMemcpy(range_max_out, b.p, 8 * n, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
   return S2B_OK;
 }
 

@@ -178,3 +178,19 @@ def test_to_lat_lng_within_ulps_of_reference(torch_cuda, ref):
     lsb = ids & (~ids + np.uint64(1))
     leaf = cellid.from_lat_lng(got)
     assert (((leaf & (~lsb + np.uint64(1))) | lsb) == ids).mean() > 0.999   # (centres of coarse cells sit on leaf boundaries)
+
+
+def test_cellid_info_matches_reference(torch_cuda, ref):
+    torch = torch_cuda
+    from s2geometry_b200 import cellid
+    from tests.test_encode_cpu import random_ids_all_levels
+    ids = random_ids_all_levels(ref, 500_000, 83)
+    want_level = ref.level(ids)
+    want_min, want_max = ref.id_range(ids)
+    valid, level, rmin, rmax = cellid.info(ids)
+    assert valid.all() and (level == want_level).all() and (rmin == want_min).all() and (rmax == want_max).all()
+    bad = np.array([0, 7 << 61, (6 << 61) | 1, 2, 8, (1 << 61) | 2, 0xFFFFFFFFFFFFFFFF], np.uint64)   # None, face >= 6, even lsb position
+    v2, l2, _, _ = cellid.info(bad)
+    assert (~v2).all() and (l2 == -1).all()
+    dv, dl, da, db = cellid.info(torch.from_numpy(ids.view(np.int64)).cuda())
+    assert dv.all().item() and (dl.cpu().numpy() == level).all() and (da.cpu().numpy().view(np.uint64) == rmin).all() and (db.cpu().numpy().view(np.uint64) == rmax).all()
