@@ -307,23 +307,22 @@ locate_fast_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint3
       const int fi = approx_leaf_coord((neg ? b : a) * inv);
       const int fj = approx_leaf_coord((neg ? a : b) * inv);
       const int face = axis + (neg ? 3 : 0);
-      // certain only if both coordinates are well inside their lookup-table bucket (NaN/garbage gives fi = 0 or
-      // saturated values, which fail this test)
-      const int ri = fi & bucket_mask, rj = fj & bucket_mask;
-      bool certain = valid && fi >= 0 && fj >= 0 && fi < (1 << 30) && fj < (1 << 30) &&
-                     ri >= kFastRadius && ri <= bucket_mask - kFastRadius && rj >= kFastRadius && rj <= bucket_mask - kFastRadius;
-      // the table is addressed by (face, i, j) of the bucket: no Hilbert encoding on this path
-      const uint32_t bucket = lut_bucket(lut_level, face, (uint32_t)fi & 0x3FFFFFFFu, (uint32_t)fj & 0x3FFFFFFFu);
-      int c = -1;
-      if (certain) {
-        const uint32_t e0 = ix.lut[bucket];
-        const uint32_t kind = e0 & ~kLutIndexMask;
-        if (kind == kLutInside) c = (int)(e0 & kLutIndexMask);
-        else if (kind != kLutEmpty) certain = false;
-      }
+      // certain only if both coordinates are valid and well inside their lookup-table bucket (NaN/garbage gives fi = 0 or
+      // saturated / negative values, which fail these tests). Unsigned arithmetic folds each pair of bounds into one compare.
+      const uint32_t ufi = (uint32_t)fi, ufj = (uint32_t)fj;
+      const uint32_t ri = ufi & (uint32_t)bucket_mask, rj = ufj & (uint32_t)bucket_mask;
+      const uint32_t margin_span = (uint32_t)bucket_mask - 2u * (uint32_t)kFastRadius;
+      bool certain = valid & ((ufi | ufj) < (1u << 30)) & (max(ri - (uint32_t)kFastRadius, rj - (uint32_t)kFastRadius) <= margin_span);
+      // the table is addressed by (face, i, j) of the bucket: no Hilbert encoding on this path. The masked coordinates
+      // always give a valid bucket, so the read is unconditional (no branch around it).
+      const uint32_t bucket = lut_bucket(lut_level, face, ufi & 0x3FFFFFFFu, ufj & 0x3FFFFFFFu);
+      const uint32_t e0 = ix.lut[bucket];
+      const uint32_t kind = e0 & ~kLutIndexMask;
+      const int c = (certain & (kind == kLutInside)) ? (int)(e0 & kLutIndexMask) : -1;
+      certain &= (kind == kLutInside) | (kind == kLutEmpty);
       // undecided points are routed (and their outputs written) by the exact kernel
-      route_located<kInteriorMode>(ix, o, valid && certain, i, certain ? c : -1, edge_slots, interior_slots, lane);
-      unc_slots.append(valid && !certain, i, uncertain, counters + 2, lane);
+      route_located<kInteriorMode>(ix, o, certain, i, c, edge_slots, interior_slots, lane);
+      unc_slots.append(valid & !certain, i, uncertain, counters + 2, lane);
     }
     __syncthreads();                                            // everyone is done with this stage before it is refilled
   }
