@@ -59,6 +59,45 @@ int main() {
   CHECK(closed.GetContainingShapeIds(q.data(), q.size(), &offsets, &shape_ids));
   CHECK(offsets.size() == 10 && offsets[9] == 7 && shape_ids.size() == 7 && shape_ids[0] == 0);
 
+  // serialized round trip: geometry + index to the reference's wire formats, read back, same answers
+  {
+    S2bBuiltIndex* built = nullptr;
+    CHECK(s2b_index_build(3, dims, shape_chain_begin, chain_vertex_begin, &verts[0].x, S2B_MAX_EDGES_PER_CELL_DEVICE, &built) == S2B_OK);
+    S2bFlatIndex flat;
+    const int32_t* edge_ids = nullptr;
+    CHECK(s2b_built_index_flat(built, &flat, &edge_ids) == S2B_OK);
+    size_t need = 0, need_shapes = 0;
+    CHECK(s2b_index_encode(&flat, edge_ids, S2B_MAX_EDGES_PER_CELL_DEVICE, nullptr, 0, &need) == S2B_ECAPACITY && need > 0);
+    std::vector<uint8_t> blob(need);
+    CHECK(s2b_index_encode(&flat, edge_ids, S2B_MAX_EDGES_PER_CELL_DEVICE, blob.data(), blob.size(), &need) == S2B_OK);
+    CHECK(s2b_shapes_encode(3, dims, shape_chain_begin, chain_vertex_begin, &verts[0].x, nullptr, 0, &need_shapes) == S2B_ECAPACITY);
+    std::vector<uint8_t> shape_blob(need_shapes);
+    CHECK(s2b_shapes_encode(3, dims, shape_chain_begin, chain_vertex_begin, &verts[0].x, shape_blob.data(), shape_blob.size(), &need_shapes) == S2B_OK);
+    s2b_built_index_destroy(built);
+    S2bShapeSoup* soup = nullptr;
+    CHECK(s2b_shapes_decode(shape_blob.data(), shape_blob.size(), &soup, nullptr) == S2B_OK);
+    int ns = 0; const int8_t* d2; const uint32_t *scb2, *cvb2; const double* v2; size_t nv = 0;
+    CHECK(s2b_shape_soup_arrays(soup, &ns, &d2, &scb2, &cvb2, &v2, &nv) == S2B_OK && ns == 3 && nv == 6);
+    s2b::DeviceShapeIndex index2;
+    CHECK(index2.InitFromEncoded(blob.data(), blob.size(), ns, d2, scb2, cvb2, v2));
+    s2b_shape_soup_destroy(soup);
+    CHECK(s2b::S2ContainsPointQueryBatch(&index2, s2b::S2VertexModel::CLOSED).Contains(q.data(), q.size(), out.data()));
+    CHECK(std::memcmp(out.data(), want_closed, 9) == 0);
+    uint8_t garbage[5] = {0xFF, 0xFF, 0xFF, 0xFF, 0x7F};
+    CHECK(!index2.InitFromEncoded(garbage, 5, ns, dims, shape_chain_begin, chain_vertex_begin, &verts[0].x));
+  }
+
+  // S2PointIndex + S2ClosestPointQuery: the six vertices as an index
+  {
+    S2bPointIndex* pi = nullptr;
+    CHECK(s2b_point_index_create(&verts[0].x, verts.size(), &pi) == S2B_OK && s2b_point_index_size(pi) == 6);
+    s2b::Point t = FromDegrees(0.1, 5.1);
+    int32_t data = -2; double l2 = -1; uint32_t cnt = 99;
+    CHECK(s2b_closest_point(pi, &t.x, 1, INFINITY, &data, &l2) == S2B_OK && data == 3 && l2 > 0 && l2 < 1e-4);
+    CHECK(s2b_closest_points_count(pi, &t.x, 1, 4.0 * std::sin(0.5 * 0.05) * std::sin(0.5 * 0.05), &cnt) == S2B_OK && cnt == 3);   // within 0.05 rad: 0:5, 0:7, 2:6
+    s2b_point_index_destroy(pi);
+  }
+
   // S2CellUnion::Contains: Trondheim (python/s2geometry_test.py:254-259)
   uint64_t cells[2] = {0x466D319000000000ull, 0x466D31B000000000ull};
   s2b::Point trondheim = FromDegrees(63.431052, 10.395083);
