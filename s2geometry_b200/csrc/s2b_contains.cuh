@@ -48,8 +48,10 @@ enum VertexModel { kOpen = 0, kSemiOpen = 1, kClosed = 2 };
 //              the range of cell_ids to probe
 //   kLutEmpty  no index cell intersects the bucket: every leaf of it is a miss          (decided with ONE load)
 //   kLutInside the whole bucket lies inside index cell `payload`: every leaf is a hit    (decided with ONE load)
+//   kLutInterior  like kLutInside, and that cell is a pure interior cell with a single clipped shape (no edges, the
+//              shape contains the centre): "is the point contained" / "by how many shapes" needs no second load
 constexpr uint32_t kLutIndexMask = 0x3FFFFFFFu;
-constexpr uint32_t kLutMixed = 0u, kLutEmpty = 1u << 30, kLutInside = 2u << 30;
+constexpr uint32_t kLutMixed = 0u, kLutEmpty = 1u << 30, kLutInside = 2u << 30, kLutInterior = 3u << 30;
 
 S2B_HD uint32_t lut_bucket(int lut_level, int face, uint32_t i, uint32_t j) {
   const int s = 30 - lut_level;
@@ -65,7 +67,7 @@ S2B_HD int locate_cell(const FlatIndexView& ix, int face, uint32_t i, uint32_t j
   const uint32_t e0 = ix.lut[lut_bucket(ix.lut_level, face, i, j)];
   const uint32_t kind = e0 & ~kLutIndexMask;
   if (kind == kLutEmpty) return -1;
-  if (kind == kLutInside) return (int)(e0 & kLutIndexMask);
+  if (kind == kLutInside || kind == kLutInterior) return (int)(e0 & kLutIndexMask);
   const LutRange r = ix.mixed[e0 & kLutIndexMask];
   const uint64_t leaf = leaf_id();
   uint32_t lo = r.lo, hi = r.hi;

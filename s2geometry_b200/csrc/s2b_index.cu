@@ -101,9 +101,11 @@ struct PhaseAOut {
 
 template <int kInteriorMode>
 __device__ __forceinline__ void route_located(const FlatIndexView& ix, const PhaseAOut& o, bool write_outputs, uint32_t i, int c,
-                                              WarpSlots& edge_slots, WarpSlots& interior_slots, unsigned lane) {
+                                              WarpSlots& edge_slots, WarpSlots& interior_slots, unsigned lane, bool single_interior = false) {
+  // single_interior: the lookup table already said that cell c is a pure interior cell with one clipped shape. "Any" and
+  // "count" then need nothing else; the other modes still read the cell's info for the shape id.
   int info = 0;
-  if (c >= 0) info = ix.interior_info[c];
+  if (c >= 0) info = ((kInteriorMode == 1 || kInteriorMode == 2) && single_interior) ? -1 : ix.interior_info[c];
   uint8_t flag = 0;
   uint32_t cnt = 0;
   const bool to_edges = c >= 0 && info == 0;
@@ -318,10 +320,11 @@ locate_fast_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint3
       const uint32_t bucket = lut_bucket(lut_level, face, ufi & 0x3FFFFFFFu, ufj & 0x3FFFFFFFu);
       const uint32_t e0 = ix.lut[bucket];
       const uint32_t kind = e0 & ~kLutIndexMask;
-      const int c = (certain & (kind == kLutInside)) ? (int)(e0 & kLutIndexMask) : -1;
-      certain &= (kind == kLutInside) | (kind == kLutEmpty);
+      const bool inside = (kind == kLutInside) | (kind == kLutInterior);
+      const int c = (certain & inside) ? (int)(e0 & kLutIndexMask) : -1;
+      certain &= inside | (kind == kLutEmpty);
       // undecided points are routed (and their outputs written) by the exact kernel
-      route_located<kInteriorMode>(ix, o, certain, i, c, edge_slots, interior_slots, lane);
+      route_located<kInteriorMode>(ix, o, certain, i, c, edge_slots, interior_slots, lane, kind == kLutInterior);
       unc_slots.append(valid & !certain, i, uncertain, counters + 2, lane);
     }
     __syncthreads();                                            // everyone is done with this stage before it is refilled
