@@ -118,9 +118,10 @@ __device__ __forceinline__ void route_located(const FlatIndexView& ix, const Pha
     else if (kInteriorMode == 4 && single_shape >= 0) flag = single_shape == o.target_shape;
     else to_interior = true;
   }
+  // which per-point output exists is a property of the mode (flags: any / one shape; counts: count), known at compile time
   if (write_outputs) {
-    if (o.flags) o.flags[i] = flag;
-    if (o.counts) o.counts[i] = cnt;
+    if (kInteriorMode == 1 || kInteriorMode == 4) o.flags[i] = flag;
+    if (kInteriorMode == 2) o.counts[i] = cnt;
   }
   if (to_edges && o.cell_counts) atomicAdd(o.cell_counts + c, 1u);
   edge_slots.append(to_edges, HitWork{i, c}, o.work, o.capacity, o.counters, +1, lane);
