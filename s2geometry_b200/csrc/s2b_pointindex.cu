@@ -125,7 +125,8 @@ __device__ __forceinline__ double chord_length2(const P3& p, const P3& q) {   //
 // target -> covering -> table -> candidate points of dependent loads, so the kernel is latency-bound per group.
 template <int kGroup>
 __global__ void __launch_bounds__(kThreads)
-radius_count_kernel(const IndexView ix, const double* __restrict__ targets, size_t n, int level, double limit2, uint32_t* __restrict__ counts) {
+radius_count_kernel(const IndexView ix, const double* __restrict__ targets, const uint32_t* __restrict__ order, size_t n, int level, double limit2,
+                    uint32_t* __restrict__ counts) {
   __shared__ uint16_t s_pos[1024];
   for (int k = threadIdx.x; k < 1024; k += kThreads) s_pos[k] = g_hilbert_pi.pos[k];
   __syncthreads();
@@ -134,7 +135,8 @@ radius_count_kernel(const IndexView ix, const double* __restrict__ targets, size
   const unsigned group_mask = kGroup == 32 ? 0xffffffffu : (((1u << kGroup) - 1u) << (lane & ~(unsigned)(kGroup - 1)));
   const size_t tid = (size_t)blockIdx.x * kThreads + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * kThreads / kGroup;
-  for (size_t t = tid / kGroup; t < n; t += stride) {
+  for (size_t slot = tid / kGroup; slot < n; slot += stride) {
+    const size_t t = order ? order[slot] : slot;     // spatially sorted processing order: neighbouring lanes scan the same cells
     const double* tq = targets + 3 * t;
     const P3 q{tq[0], tq[1], tq[2]};
     double fi, fj;
@@ -165,7 +167,7 @@ radius_count_kernel(const IndexView ix, const double* __restrict__ targets, size
 // the cap radius that covering is guaranteed to contain (the minimum width of a level L+1 cell); at level -1 the
 // covering is the whole sphere. Ties in distance go to the smaller data value.
 __global__ void __launch_bounds__(kThreads)
-closest_point_kernel(const IndexView ix, const double* __restrict__ targets, size_t n, int start_level, double limit2,
+closest_point_kernel(const IndexView ix, const double* __restrict__ targets, const uint32_t* __restrict__ order, size_t n, int start_level, double limit2,
                      const double* __restrict__ covered_length2 /* [31]: entry L+1 = chord^2 of the cap radius covered at level L */,
                      int32_t* __restrict__ data_out, double* __restrict__ length2_out) {
   __shared__ uint16_t s_pos[1024];
@@ -174,7 +176,8 @@ closest_point_kernel(const IndexView ix, const double* __restrict__ targets, siz
   if (threadIdx.x < 31) s_cov[threadIdx.x] = covered_length2[threadIdx.x];
   __syncthreads();
   const size_t stride = (size_t)gridDim.x * kThreads;
-  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < n; t += stride) {
+  for (size_t slot = (size_t)blockIdx.x * kThreads + threadIdx.x; slot < n; slot += stride) {
+    const size_t t = order ? order[slot] : slot;
     const double* tq = targets + 3 * t;
     const P3 q{tq[0], tq[1], tq[2]};
     double fi, fj;
@@ -212,7 +215,7 @@ closest_point_kernel(const IndexView ix, const double* __restrict__ targets, siz
 // k-th best distance in place of the best. Row t of the outputs holds count[t] results, padded with -1 / +inf.
 constexpr int kMaxResults = 32;
 __global__ void __launch_bounds__(kThreads)
-closest_points_kernel(const IndexView ix, const double* __restrict__ targets, size_t n, int k, int start_level, double limit2,
+closest_points_kernel(const IndexView ix, const double* __restrict__ targets, const uint32_t* __restrict__ order, size_t n, int k, int start_level, double limit2,
                       const double* __restrict__ covered_length2, int32_t* __restrict__ data_out, double* __restrict__ length2_out,
                       uint32_t* __restrict__ count_out) {
   __shared__ uint16_t s_pos[1024];
@@ -221,7 +224,8 @@ closest_points_kernel(const IndexView ix, const double* __restrict__ targets, si
   if (threadIdx.x < 31) s_cov[threadIdx.x] = covered_length2[threadIdx.x];
   __syncthreads();
   const size_t stride = (size_t)gridDim.x * kThreads;
-  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < n; t += stride) {
+  for (size_t slot = (size_t)blockIdx.x * kThreads + threadIdx.x; slot < n; slot += stride) {
+    const size_t t = order ? order[slot] : slot;
     const double* tq = targets + 3 * t;
     const P3 q{tq[0], tq[1], tq[2]};
     double fi, fj;
@@ -276,6 +280,41 @@ int level_for_min_width(double value) {
 double angle_of_length2(double l2) {
   if (l2 >= 4.0) return M_PI;
   return 2 * std::asin(0.5 * std::sqrt(l2)) * (1 + 1e-9) + 1e-300;
+}
+
+// Processing order for a large batch of targets: their indices sorted by leaf cell id (K1 + radix sort on the top bits),
+// so that the threads of a warp work on neighbouring targets — the same covering cells, the same candidate points (L1 hits
+// and broadcasts instead of 32 unrelated streams). The results do not depend on the order. *blob_out must be released
+// with cudaFreeAsync on the same stream after the consumer kernel has been enqueued. Small batches keep their order.
+constexpr size_t kSortTargetsFrom = size_t(1) << 18;
+cudaError_t sorted_target_order(const double* targets_dev, size_t n, cudaStream_t st, const uint32_t** order_out, void** blob_out) {
+  *order_out = nullptr;
+  *blob_out = nullptr;
+  if (n < kSortTargetsFrom || n > 0x7FFFFFFFull) return cudaSuccess;
+  size_t t_sort = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, t_sort, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 32, 64, st);
+  auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+  const size_t o_ids2 = up(8 * n), o_iota = 2 * up(8 * n), o_order = o_iota + up(4 * n), o_tmp = o_order + up(4 * n);
+  char* blob = nullptr;
+  cudaError_t e = cudaMallocAsync((void**)&blob, o_tmp + up(t_sort), st);
+  if (e != cudaSuccess) { cudaGetLastError(); return cudaSuccess; }      // no memory for the sort: keep the caller's order
+  EncodeOut eo{};
+  eo.levels.n = 1; eo.levels.level[0] = 30;
+  eo.ids = (uint64_t*)blob;
+  eo.token_level_index = -1;
+  e = launch_encode(kInXYZ, targets_dev, n, eo, st);
+  if (e == cudaSuccess) {
+    iota_kernel<<<grid_for_pi(n, (const void*)iota_kernel), kThreads, 0, st>>>((int32_t*)(blob + o_iota), n);
+    count_launch();
+    // face + the top 14 levels (bits 63..32) order the targets finely enough; half the radix passes of a full sort
+    e = cub::DeviceRadixSort::SortPairs(blob + o_tmp, t_sort, (const uint64_t*)blob, (uint64_t*)(blob + o_ids2), (const uint32_t*)(blob + o_iota),
+                                        (uint32_t*)(blob + o_order), (int)n, 32, 64, st);
+    count_launch();
+  }
+  if (e != cudaSuccess) { cudaFreeAsync(blob, st); return e; }
+  *order_out = (const uint32_t*)(blob + o_order);
+  *blob_out = blob;
+  return cudaSuccess;
 }
 
 }  // namespace
@@ -388,18 +427,23 @@ int s2b_closest_points_count_dev(const S2bPointIndex* ix, const double* targets_
   // measured on B200 (10M index points, ~100 per covering, 50M targets): 957 / 848 / 365 M targets/s with 1 / 8 / 32
   // lanes per target, so lanes are only shared once a covering holds far more points than one thread should scan
   const int group = per_cover >= 8192.0 ? 32 : (per_cover >= 1024.0 ? 8 : 1);
+  const uint32_t* order = nullptr;
+  void* order_blob = nullptr;
+  cudaError_t e = sorted_target_order(targets_dev, n, st, &order, &order_blob);
+  if (e != cudaSuccess) return cuda_fail(e, "target sort");
   if (group == 32) {
     const auto k = radius_count_kernel<32>;
-    k<<<grid_for_pi(n * 32, (const void*)k), kThreads, 0, st>>>(v, targets_dev, n, level, max_length2, counts_out_dev);
+    k<<<grid_for_pi(n * 32, (const void*)k), kThreads, 0, st>>>(v, targets_dev, order, n, level, max_length2, counts_out_dev);
   } else if (group == 8) {
     const auto k = radius_count_kernel<8>;
-    k<<<grid_for_pi(n * 8, (const void*)k), kThreads, 0, st>>>(v, targets_dev, n, level, max_length2, counts_out_dev);
+    k<<<grid_for_pi(n * 8, (const void*)k), kThreads, 0, st>>>(v, targets_dev, order, n, level, max_length2, counts_out_dev);
   } else {
     const auto k = radius_count_kernel<1>;
-    k<<<grid_for_pi(n, (const void*)k), kThreads, 0, st>>>(v, targets_dev, n, level, max_length2, counts_out_dev);
+    k<<<grid_for_pi(n, (const void*)k), kThreads, 0, st>>>(v, targets_dev, order, n, level, max_length2, counts_out_dev);
   }
   count_launch();
-  cudaError_t e = cudaGetLastError();
+  e = cudaGetLastError();
+  if (order_blob) cudaFreeAsync(order_blob, st);
   return e == cudaSuccess ? S2B_OK : cuda_fail(e, "radius_count launch");
 }
 
@@ -433,9 +477,14 @@ int s2b_closest_point_dev(const S2bPointIndex* ix, const double* targets_dev, si
     start = start < -1 ? -1 : (start > 29 ? 29 : start);
   }
   const IndexView v{ix->ids, ix->pts, ix->data, ix->first, (uint32_t)ix->m, 61 - 2 * ix->table_level};
-  closest_point_kernel<<<grid_for_pi(n, (const void*)closest_point_kernel), kThreads, 0, st>>>(v, targets_dev, n, start, max_length2, cov_dev, data_out_dev, length2_out_dev);
+  const uint32_t* order = nullptr;
+  void* order_blob = nullptr;
+  e = sorted_target_order(targets_dev, n, st, &order, &order_blob);
+  if (e != cudaSuccess) { cudaFreeAsync(cov_dev, st); return cuda_fail(e, "target sort"); }
+  closest_point_kernel<<<grid_for_pi(n, (const void*)closest_point_kernel), kThreads, 0, st>>>(v, targets_dev, order, n, start, max_length2, cov_dev, data_out_dev, length2_out_dev);
   count_launch();
   e = cudaGetLastError();
+  if (order_blob) cudaFreeAsync(order_blob, st);
   cudaFreeAsync(cov_dev, st);
   return e == cudaSuccess ? S2B_OK : cuda_fail(e, "closest_point launch");
 }
@@ -468,10 +517,15 @@ int s2b_closest_points_dev(const S2bPointIndex* ix, const double* targets_dev, s
     start = start < -1 ? -1 : (start > 29 ? 29 : start);
   }
   const IndexView v{ix->ids, ix->pts, ix->data, ix->first, (uint32_t)ix->m, 61 - 2 * ix->table_level};
-  closest_points_kernel<<<grid_for_pi(n, (const void*)closest_points_kernel), kThreads, 0, st>>>(v, targets_dev, n, max_results, start, max_length2, cov_dev,
+  const uint32_t* order = nullptr;
+  void* order_blob = nullptr;
+  e = sorted_target_order(targets_dev, n, st, &order, &order_blob);
+  if (e != cudaSuccess) { cudaFreeAsync(cov_dev, st); return cuda_fail(e, "target sort"); }
+  closest_points_kernel<<<grid_for_pi(n, (const void*)closest_points_kernel), kThreads, 0, st>>>(v, targets_dev, order, n, max_results, start, max_length2, cov_dev,
                                                                                                data_out_dev, length2_out_dev, count_out_dev);
   count_launch();
   e = cudaGetLastError();
+  if (order_blob) cudaFreeAsync(order_blob, st);
   cudaFreeAsync(cov_dev, st);
   return e == cudaSuccess ? S2B_OK : cuda_fail(e, "closest_points launch");
 }

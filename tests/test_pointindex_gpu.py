@@ -126,6 +126,28 @@ def test_k_closest_points_match_reference(torch_cuda, ref):
         ClosestPointQuery(ix).closest_k(targets[:4], 33)
 
 
+def test_large_batches_take_the_sorted_order_path(torch_cuda, ref):
+    """Batches of >= 2^18 targets are processed in cell-sorted order internally; the results stay in the caller's order."""
+    torch = torch_cuda
+    from s2geometry_b200.pointindex import ClosestPointQuery, PointIndex
+    pts, _ = scene(4, m=150_000, n=10)
+    targets = np.concatenate([synth.sphere_points(300_000, 91), pts[::3][:40_000]])
+    assert len(targets) >= 1 << 18
+    ri = ref.point_index(pts)
+    ix = PointIndex(pts)
+    td = torch.from_numpy(targets).cuda()
+    for r in (3e-3, 0.03):
+        want = ri.count(targets, r)
+        q = ClosestPointQuery(ix, r)
+        assert (q.count(targets) == want).all() and (q.count(td).cpu().numpy().astype(np.uint32) == want).all(), r
+    wd, wl = ri.closest(targets)
+    gd, gl = ClosestPointQuery(ix).closest(td)
+    assert (gl.cpu().numpy() == wl).all() and ((gd.cpu().numpy() == wd).mean() > 0.95)
+    kd, kl, kc = ri.closest_k(targets, 4, 0.01)
+    gd4, gl4, gc4 = ClosestPointQuery(ix, 0.01).closest_k(targets, 4)
+    assert (gl4 == kl).all() and (gc4 == kc).all()
+
+
 def test_empty_index_and_empty_targets(torch_cuda):
     from s2geometry_b200.pointindex import ClosestPointQuery, PointIndex
     ix = PointIndex(np.zeros((0, 3)))
