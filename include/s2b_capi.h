@@ -342,6 +342,54 @@ int s2b_closest_points_dev(const S2bPointIndex* index, const double* targets_xyz
 int s2b_closest_point_dev(const S2bPointIndex* index, const double* targets_xyz_dev, size_t n, double max_length2,
                           int32_t* data_out_dev, double* length2_out_dev, void* stream);
 
+/* --------------------------------------------------------------------------------------------------
+ * S2CellIndex joins, batch form (s2cell_index.h:113-441, s2cell_index.cc:71-163) and the S2RegionSharder built on it
+ * (s2region_sharder.cc:35-140). The index holds m (cell_id, label) pairs — S2CellIndex::Add(cell_ids[i], labels[i]) followed
+ * by Build() — on the current device; cells may overlap and repeat, labels are >= 0 (invalid ids / negative labels:
+ * S2B_EINVAL, the reference DCHECKs them).
+ * Targets are S2CellUnions in CSR form: target t = target_ids[target_offsets[t] .. target_offsets[t+1]), cells sorted and
+ * non-overlapping as S2CellUnion requires; target_offsets == NULL means T single-cell targets. Invalid target ids report
+ * nothing. Results are CSR too (offsets_out has T + 1 slots); S2B_ECAPACITY with *total_out set (offsets filled) if
+ * `capacity` is too small.
+ *   s2b_cell_index_intersecting_cells   VisitIntersectingCells(target): every indexed (cell_id, label) pair whose cell
+ *                                       intersects the target, once per copy in the index, in unspecified order as in the
+ *                                       reference; cell_ids_out / labels_out are each nullable
+ *   s2b_cell_index_intersecting_labels  GetIntersectingLabels(target): the distinct labels, ascending
+ *   s2b_cell_index_most_intersecting_label  S2RegionSharder(shards).GetMostIntersectingShard(region, default_label)
+ *                                       (s2region_sharder.cc:35-140) over an index with label s on the cells of shard s (each
+ *                                       shard a normalized S2CellUnion). Per region the caller passes `bound` = the normalized
+ *                                       region.GetCellUnionBound() covering (CSR) and, optionally, the region itself as an
+ *                                       S2CellUnion (CSR, region_ids NULL = the bound is the region): a shard's score is the
+ *                                       sum of lsb() over the cells of (shard ∩ bound) that intersect the region
+ *                                       (region.MayIntersect for an S2CellUnion region); a single candidate shard wins
+ *                                       outright, otherwise the largest score, the smaller label on ties, default_label if none
+ *   s2b_cell_index_point_histogram      for every point, the pairs VisitIntersectingCells reports for its leaf cell
+ *                                       S2CellId(point): counts[label] += 1 per pair (num_labels = max label + 1 slots).
+ *                                       Host form overwrites counts, the _dev form ADDS (zero it first; all-reduce across GPUs)
+ * The _dev forms take device pointers, run on `stream`, and (except the histogram) synchronise it to size their scratch.
+ * -------------------------------------------------------------------------------------------------- */
+typedef struct S2bCellIndex S2bCellIndex;
+int s2b_cell_index_create(const uint64_t* cell_ids, const int32_t* labels, size_t m, S2bCellIndex** index_out);
+void s2b_cell_index_destroy(S2bCellIndex* index);
+int s2b_cell_index_info(const S2bCellIndex* index, uint64_t* num_cells, int32_t* num_labels, uint64_t* device_bytes);
+int s2b_cell_index_intersecting_cells(const S2bCellIndex* index, const uint64_t* target_ids, const uint32_t* target_offsets, size_t T,
+                                      uint32_t* offsets_out, uint64_t* cell_ids_out, int32_t* labels_out, size_t capacity, size_t* total_out);
+int s2b_cell_index_intersecting_cells_dev(const S2bCellIndex* index, const uint64_t* target_ids_dev, const uint32_t* target_offsets_dev, size_t T,
+                                          uint32_t* offsets_out_dev, uint64_t* cell_ids_out_dev, int32_t* labels_out_dev, size_t capacity,
+                                          size_t* total_out, void* stream);
+int s2b_cell_index_intersecting_labels(const S2bCellIndex* index, const uint64_t* target_ids, const uint32_t* target_offsets, size_t T,
+                                       uint32_t* offsets_out, int32_t* labels_out, size_t capacity, size_t* total_out);
+int s2b_cell_index_intersecting_labels_dev(const S2bCellIndex* index, const uint64_t* target_ids_dev, const uint32_t* target_offsets_dev, size_t T,
+                                           uint32_t* offsets_out_dev, int32_t* labels_out_dev, size_t capacity, size_t* total_out, void* stream);
+int s2b_cell_index_most_intersecting_label(const S2bCellIndex* index, const uint64_t* bound_ids, const uint32_t* bound_offsets,
+                                           const uint64_t* region_ids, const uint32_t* region_offsets, size_t T, int32_t default_label,
+                                           int32_t* out);
+int s2b_cell_index_most_intersecting_label_dev(const S2bCellIndex* index, const uint64_t* bound_ids_dev, const uint32_t* bound_offsets_dev,
+                                               const uint64_t* region_ids_dev, const uint32_t* region_offsets_dev, size_t T,
+                                               int32_t default_label, int32_t* out_dev, void* stream);
+int s2b_cell_index_point_histogram(const S2bCellIndex* index, const double* xyz, size_t n, uint64_t* counts);
+int s2b_cell_index_point_histogram_dev(const S2bCellIndex* index, const double* xyz_dev, size_t n, uint64_t* counts_dev, void* stream);
+
 /* S2CellUnion::Normalize (s2cell_union.cc:171-199) on the GPU: sorts, drops duplicates and cells contained in other
  * cells, and replaces complete sibling quads by their parent until none is left. out has room for m ids;
  * *count_out (host) receives the number of cells. The _dev form synchronises the stream to report the count. */

@@ -14,7 +14,7 @@ s2cell_union s2shape_index mutable_s2shape_index s2memory_tracker s2shapeutil_co
 s2shapeutil_get_reference_point s2contains_vertex_query encoded_s2cell_id_vector encoded_string_vector
 util/coding/coder util/coding/varint util/math/mathutil util/math/exactfloat/exactfloat util/math/exactfloat/bignum
 base/malloc_extension s2region_coverer s2closest_point_query s2min_distance_targets s2closest_edge_query
-s2closest_cell_query s2cell_index s2lax_polygon_shape s2lax_polyline_shape encoded_s2point_vector"
+s2closest_cell_query s2cell_index s2region_sharder s2lax_polygon_shape s2lax_polyline_shape encoded_s2point_vector"
 CXXFLAGS="-std=c++20 -O2 -DNDEBUG -w -fPIC -ffunction-sections -fdata-sections -I$HERE/absl_shim -I$REF"
 pids=()
 for t in $TUS; do

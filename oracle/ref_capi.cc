@@ -23,7 +23,9 @@
 #include "s2/s1angle.h"
 #include "s2/s2cap.h"
 #include "s2/s2cell_id.h"
+#include "s2/s2cell_index.h"
 #include "s2/s2cell_union.h"
+#include "s2/s2region_sharder.h"
 #include "s2/s2closest_point_query.h"
 #include "s2/s2point_index.h"
 #include "s2/s2contains_point_query.h"
@@ -666,6 +668,106 @@ size_t ref_cover_cap(const double* center, double radius_rad, int max_cells, int
   S2CellUnion u = coverer.GetCovering(cap);
   size_t k = 0;
   for (S2CellId id : u.cell_ids()) { if (k < capacity) out[k] = id.id(); ++k; }
+  return k;
+}
+
+// ---------------------------------------------------------------- S2CellIndex (s2cell_index.h) / S2RegionSharder
+struct RefCellIndex { S2CellIndex index; };
+void* ref_cell_index_create(const uint64_t* ids, const int32_t* labels, size_t m) {
+  auto* r = new RefCellIndex();
+  for (size_t i = 0; i < m; ++i) r->index.Add(S2CellId(ids[i]), labels[i]);
+  r->index.Build();
+  return r;
+}
+void ref_cell_index_destroy(void* h) { delete (RefCellIndex*)h; }
+// VisitIntersectingCells for T target unions (CSR: ids[offsets[t]..offsets[t+1])); results CSR, each target's pairs sorted by
+// (cell id, label) so the visiting order does not matter. Returns the total (only the first `capacity` pairs are written).
+uint64_t ref_cell_index_visit(void* h, const uint64_t* target_ids, const uint64_t* offsets, size_t T, uint64_t* out_offsets,
+                              uint64_t* out_cells, int32_t* out_labels, uint64_t capacity) {
+  const S2CellIndex& index = ((RefCellIndex*)h)->index;
+  uint64_t total = 0;
+  out_offsets[0] = 0;
+  std::vector<S2CellIndex::LabelledCell> got;
+  for (size_t t = 0; t < T; ++t) {
+    std::vector<S2CellId> v;
+    for (uint64_t k = offsets[t]; k < offsets[t + 1]; ++k) v.push_back(S2CellId(target_ids[k]));
+    S2CellUnion target = S2CellUnion::FromVerbatim(std::move(v));
+    got.clear();
+    index.VisitIntersectingCells(target, [&](S2CellId id, S2CellIndex::Label label) {
+      got.push_back({id, label});
+      return true;
+    });
+    std::sort(got.begin(), got.end());
+    for (const auto& lc : got) {
+      if (total < capacity) { out_cells[total] = lc.cell_id.id(); out_labels[total] = lc.label; }
+      ++total;
+    }
+    out_offsets[t + 1] = total;
+  }
+  return total;
+}
+// GetIntersectingLabels per target union: distinct labels, ascending.
+uint64_t ref_cell_index_labels(void* h, const uint64_t* target_ids, const uint64_t* offsets, size_t T, uint64_t* out_offsets,
+                               int32_t* out_labels, uint64_t capacity) {
+  const S2CellIndex& index = ((RefCellIndex*)h)->index;
+  uint64_t total = 0;
+  out_offsets[0] = 0;
+  for (size_t t = 0; t < T; ++t) {
+    std::vector<S2CellId> v;
+    for (uint64_t k = offsets[t]; k < offsets[t + 1]; ++k) v.push_back(S2CellId(target_ids[k]));
+    S2CellUnion target = S2CellUnion::FromVerbatim(std::move(v));
+    auto labels = index.GetIntersectingLabels(target);
+    std::vector<int32_t> sorted(labels.begin(), labels.end());
+    std::sort(sorted.begin(), sorted.end());
+    for (int32_t l : sorted) { if (total < capacity) out_labels[total] = l; ++total; }
+    out_offsets[t + 1] = total;
+  }
+  return total;
+}
+// Per-label histogram of the (point, indexed cell) pairs VisitIntersectingCells reports for the leaf cell of every point.
+void ref_cell_index_point_histogram(void* h, const double* xyz, size_t n, uint64_t* counts, int num_labels, int threads) {
+  const S2CellIndex& index = ((RefCellIndex*)h)->index;
+  int T = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+  if (T < 1) T = 1;
+  std::vector<std::vector<uint64_t>> local(T, std::vector<uint64_t>(num_labels, 0));
+  ParallelFor(n, T, [&](size_t b, size_t e, int tid) {
+    auto& c = local[tid];
+    for (size_t i = b; i < e; ++i) {
+      S2CellUnion target = S2CellUnion::FromVerbatim({S2CellId(P(xyz + 3 * i))});
+      index.VisitIntersectingCells(target, [&](S2CellId, S2CellIndex::Label label) { ++c[label]; return true; });
+    }
+  });
+  for (int l = 0; l < num_labels; ++l) { counts[l] = 0; for (int t = 0; t < T; ++t) counts[l] += local[t][l]; }
+}
+// S2RegionSharder over shard coverings (CSR) queried with S2CellUnion regions (CSR): GetMostIntersectingShard.
+void ref_sharder_most_intersecting(const uint64_t* shard_ids, const uint64_t* shard_offsets, size_t num_shards,
+                                   const uint64_t* region_ids, const uint64_t* region_offsets, size_t T, int default_shard,
+                                   int32_t* out) {
+  std::vector<S2CellUnion> shards;
+  for (size_t s = 0; s < num_shards; ++s) {
+    std::vector<S2CellId> v;
+    for (uint64_t k = shard_offsets[s]; k < shard_offsets[s + 1]; ++k) v.push_back(S2CellId(shard_ids[k]));
+    shards.push_back(S2CellUnion::FromVerbatim(std::move(v)));
+  }
+  S2RegionSharder sharder(shards);
+  for (size_t t = 0; t < T; ++t) {
+    std::vector<S2CellId> v;
+    for (uint64_t k = region_offsets[t]; k < region_offsets[t + 1]; ++k) v.push_back(S2CellId(region_ids[k]));
+    S2CellUnion region = S2CellUnion::FromVerbatim(std::move(v));
+    out[t] = sharder.GetMostIntersectingShard(region, default_shard);
+  }
+}
+
+// The covering S2RegionSharder derives from an S2CellUnion region: S2CellUnion(region.GetCellUnionBound()) (normalized).
+size_t ref_cellunion_cell_union_bound(const uint64_t* ids, size_t m, uint64_t* out, size_t capacity) {
+  std::vector<S2CellId> v(m);
+  for (size_t i = 0; i < m; ++i) v[i] = S2CellId(ids[i]);
+  S2CellUnion region = S2CellUnion::FromVerbatim(std::move(v));
+  std::vector<S2CellId> bound;
+  region.GetCellUnionBound(&bound);
+  S2CellUnion covering(std::move(bound));
+  size_t k = 0;
+  for (S2CellId id : covering.cell_ids()) { if (k < capacity) out[k] = id.id(); ++k; }
   return k;
 }
 

@@ -387,3 +387,87 @@ def load():
             raise RuntimeError("oracle/_ref/libs2ref.so is missing and the reference sources are not available to build it")
         _ref = Ref(ctypes.CDLL(LIB))
     return _ref
+
+
+def _csr(targets):
+    """list of uint64 arrays (or one array of single-cell targets) -> (ids, uint64 offsets)"""
+    if isinstance(targets, np.ndarray) and targets.ndim == 1:
+        ids = np.ascontiguousarray(targets, np.uint64)
+        return ids, np.arange(len(ids) + 1, dtype=np.uint64)
+    lens = [len(t) for t in targets]
+    ids = np.ascontiguousarray(np.concatenate([np.asarray(t, np.uint64) for t in targets]) if lens else np.zeros(0, np.uint64), np.uint64)
+    return ids, np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+
+
+class RefCellIndex:
+    """S2CellIndex (the reference's own, s2cell_index.h) over (cell_id, label) pairs."""
+
+    def __init__(self, ref, cell_ids, labels):
+        self.lib = ref.lib
+        self.lib.ref_cell_index_create.restype = _vp
+        self.lib.ref_cell_index_visit.restype = ctypes.c_uint64
+        self.lib.ref_cell_index_labels.restype = ctypes.c_uint64
+        ids = np.ascontiguousarray(cell_ids, np.uint64)
+        lab = np.ascontiguousarray(labels, np.int32)
+        self.num_labels = int(lab.max()) + 1 if lab.size else 0
+        self.h = self.lib.ref_cell_index_create(_p(ids), _p(lab), _sz(len(ids)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.ref_cell_index_destroy(_vp(self.h))
+                self.h = None
+        except Exception:
+            pass
+
+    def visit(self, targets):
+        """VisitIntersectingCells per target -> (offsets, cells, labels), each target's pairs sorted by (cell, label)."""
+        ids, off = _csr(targets)
+        T = len(off) - 1
+        out_off = np.zeros(T + 1, np.uint64)
+        cap = 1 << 16
+        while True:
+            cells = np.empty(cap, np.uint64); labels = np.empty(cap, np.int32)
+            total = self.lib.ref_cell_index_visit(_vp(self.h), _p(ids), _p(off), _sz(T), _p(out_off), _p(cells), _p(labels), ctypes.c_uint64(cap))
+            if total <= cap:
+                return out_off, cells[:total].copy(), labels[:total].copy()
+            cap = int(total)
+
+    def labels(self, targets):
+        """GetIntersectingLabels per target -> (offsets, labels ascending)."""
+        ids, off = _csr(targets)
+        T = len(off) - 1
+        out_off = np.zeros(T + 1, np.uint64)
+        cap = 1 << 16
+        while True:
+            labels = np.empty(cap, np.int32)
+            total = self.lib.ref_cell_index_labels(_vp(self.h), _p(ids), _p(off), _sz(T), _p(out_off), _p(labels), ctypes.c_uint64(cap))
+            if total <= cap:
+                return out_off, labels[:total].copy()
+            cap = int(total)
+
+    def point_histogram(self, xyz, threads=0):
+        xyz = np.ascontiguousarray(xyz, np.float64).reshape(-1, 3)
+        counts = np.zeros(max(self.num_labels, 1), np.uint64)
+        self.lib.ref_cell_index_point_histogram(_vp(self.h), _p(xyz), _sz(len(xyz)), _p(counts), int(self.num_labels), int(threads))
+        return counts[: self.num_labels]
+
+
+def ref_sharder_most_intersecting(ref, shards, regions, default_shard=-1):
+    """S2RegionSharder(shards).GetMostIntersectingShard(S2CellUnion region, default) for every region."""
+    s_ids, s_off = _csr(shards)
+    r_ids, r_off = _csr(regions)
+    out = np.empty(len(r_off) - 1, np.int32)
+    ref.lib.ref_sharder_most_intersecting(_p(s_ids), _p(s_off), _sz(len(s_off) - 1), _p(r_ids), _p(r_off), _sz(len(r_off) - 1),
+                                          int(default_shard), _p(out))
+    return out
+
+
+def ref_cellunion_bound(ref, region):
+    """S2CellUnion(region.GetCellUnionBound()) for an S2CellUnion region: the covering S2RegionSharder queries its index with."""
+    ids = np.ascontiguousarray(region, np.uint64)
+    out = np.empty(64, np.uint64)
+    ref.lib.ref_cellunion_cell_union_bound.restype = _sz
+    k = ref.lib.ref_cellunion_cell_union_bound(_p(ids), _sz(len(ids)), _p(out), _sz(out.size))
+    assert k <= out.size
+    return out[:k].copy()

@@ -63,6 +63,17 @@ SIGNATURES = {
     "s2b_closest_points_dev": (_i, [_vp, _vp, _sz, _i, ctypes.c_double, _vp, _vp, _vp, _vp]),
     "s2b_closest_point": (_i, [_vp, _vp, _sz, ctypes.c_double, _vp, _vp]),
     "s2b_closest_point_dev": (_i, [_vp, _vp, _sz, ctypes.c_double, _vp, _vp, _vp]),
+    "s2b_cell_index_create": (_i, [_vp, _vp, _sz, _vp]),
+    "s2b_cell_index_destroy": (None, [_vp]),
+    "s2b_cell_index_info": (_i, [_vp, _vp, _vp, _vp]),
+    "s2b_cell_index_intersecting_cells": (_i, [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp]),
+    "s2b_cell_index_intersecting_cells_dev": (_i, [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "s2b_cell_index_intersecting_labels": (_i, [_vp, _vp, _vp, _sz, _vp, _vp, _sz, _vp]),
+    "s2b_cell_index_intersecting_labels_dev": (_i, [_vp, _vp, _vp, _sz, _vp, _vp, _sz, _vp, _vp]),
+    "s2b_cell_index_most_intersecting_label": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _c.c_int32, _vp]),
+    "s2b_cell_index_most_intersecting_label_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _c.c_int32, _vp, _vp]),
+    "s2b_cell_index_point_histogram": (_i, [_vp, _vp, _sz, _vp]),
+    "s2b_cell_index_point_histogram_dev": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "s2b_index_build": (_i, [_i, _vp, _vp, _vp, _vp, _i, _vp]),
     "s2b_built_index_flat": (_i, [_vp, _vp, _vp]),
     "s2b_built_index_destroy": (None, [_vp]),
