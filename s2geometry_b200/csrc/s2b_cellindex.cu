@@ -65,7 +65,7 @@ ci_count_kernel(CellIndexView ix, Targets tg, bool all_pairs, uint32_t* __restri
     unsigned long long c = 0;
     for (uint32_t k = b; k < e; ++k) {
       if (all_pairs) st.cutoff = -1;
-      c += ci_visit_cell(ix, tg.ids[k], st, [](uint32_t) {});
+      c += ci_visit_cell(ix, tg.ids[k], st, [](const CiNode&) {});
     }
     counts[t] = (uint32_t)(c > 0xFFFFFFFFull ? 0xFFFFFFFFull : c);
     mine += c;
@@ -90,12 +90,11 @@ ci_fill_kernel(CellIndexView ix, Targets tg, Targets flt, const uint32_t* __rest
     for (uint32_t k = b; k < e; ++k) {
       const uint64_t target = tg.ids[k];
       if (weight_out) st.cutoff = -1;   // all_pairs mode of the count pass
-      ci_visit_cell(ix, target, st, [&](uint32_t pos) {
-        const uint64_t id = ix.ids[pos];
-        if (cells_out) cells_out[w] = id;
-        if (labels_out) labels_out[w] = ix.labels[pos];
+      ci_visit_cell(ix, target, st, [&](const CiNode& nd) {
+        if (cells_out) cells_out[w] = nd.id;
+        if (labels_out) labels_out[w] = nd.label;
         if (weight_out) {
-          const uint64_t c = ci_overlap_cell(id, target);
+          const uint64_t c = ci_overlap_cell(nd.id, target);
           weight_out[w] = (!flt.ids || ci_union_intersects(flt.ids + fb, fe - fb, c)) ? cellid_lsb(c) : 0;
         }
         ++w;
@@ -141,18 +140,63 @@ ci_best_label_kernel(const int32_t* __restrict__ sorted, const uint64_t* __restr
   }
 }
 
-// Fused point form: S2CellId(point) with K1's arithmetic, then the pairs containing that leaf cell.
+// Fused point form: S2CellId(point) with K1's arithmetic, then the pairs containing that leaf cell. Every lookup is a
+// dependent, scattered load (bucket table -> range record -> overflow labels), so the kernel is bound by load latency:
+// each thread carries kPts points through the stages together to keep that many loads in flight.
+// kSharedHist: the per-label counters of a CTA live in shared memory (num_labels 32-bit slots after the Hilbert table) and
+// are added to the global 64-bit histogram once at the end — hot labels (large cells) would otherwise serialise on L2 atomics.
+constexpr int kPts = 2;
+template <bool kSharedHist>
 __global__ void __launch_bounds__(kThreads)
-ci_point_histogram_kernel(CellIndexView ix, const double* __restrict__ xyz, size_t n, unsigned long long* __restrict__ counts) {
-  __shared__ uint16_t s_pos[1024];
+ci_point_histogram_kernel(CellIndexView ix, const double* __restrict__ xyz, size_t n, int num_labels, unsigned long long* __restrict__ counts) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  uint16_t* s_pos = reinterpret_cast<uint16_t*>(s_raw);
+  uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_raw + 2048);
   for (int k = threadIdx.x; k < 1024; k += kThreads) s_pos[k] = g_hilbert_ci.pos[k];
+  if (kSharedHist) for (int k = threadIdx.x; k < num_labels; k += kThreads) s_hist[k] = 0;
   __syncthreads();
-  const size_t stride = (size_t)gridDim.x * kThreads;
-  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < n; t += stride) {
-    const P3 p{__ldcs(xyz + 3 * t), __ldcs(xyz + 3 * t + 1), __ldcs(xyz + 3 * t + 2)};
-    const uint64_t leaf = cellid_from_point(p, s_pos);
-    CiUnionState st;
-    ci_visit_cell(ix, leaf, st, [&](uint32_t pos) { atomicAdd(counts + ix.labels[pos], 1ull); });
+  auto hit = [&](int32_t label) {
+    if (kSharedHist) atomicAdd(s_hist + label, 1u); else atomicAdd(counts + label, 1ull);
+  };
+  const size_t stride = (size_t)gridDim.x * kThreads * kPts;
+  for (size_t base = (size_t)blockIdx.x * kThreads * kPts + threadIdx.x; base < n; base += stride) {
+    P3 p[kPts];
+    bool live[kPts];
+#pragma unroll
+    for (int q = 0; q < kPts; ++q) {
+      const size_t t = base + (size_t)q * kThreads;
+      live[q] = t < n;
+      const size_t tt = live[q] ? t : base;
+      p[q] = P3{__ldcs(xyz + 3 * tt), __ldcs(xyz + 3 * tt + 1), __ldcs(xyz + 3 * tt + 2)};
+    }
+    uint64_t leaf[kPts];
+    uint32_t lo[kPts], hi[kPts];
+#pragma unroll
+    for (int q = 0; q < kPts; ++q) {
+      leaf[q] = cellid_from_point(p[q], s_pos);
+      const uint64_t b = leaf[q] >> ix.rshift;
+      lo[q] = __ldg(ix.rfirst + b);
+      hi[q] = __ldg(ix.rfirst + b + 1);
+    }
+    CiRangeRec rec[kPts];
+#pragma unroll
+    for (int q = 0; q < kPts; ++q) {
+      while (lo[q] < hi[q]) {   // upper_bound inside the bucket (rare: most buckets hold no range start)
+        const uint32_t mid = lo[q] + ((hi[q] - lo[q]) >> 1);
+        if (__ldg(ix.rstart + mid) <= leaf[q]) lo[q] = mid + 1; else hi[q] = mid;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kPts; ++q) rec[q] = ci_load_rec(ix.rrec + (lo[q] - 1));
+#pragma unroll
+    for (int q = 0; q < kPts; ++q) if (live[q]) ci_emit_rec_labels(ix, rec[q], hit);
+  }
+  if (kSharedHist) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < num_labels; k += kThreads) {
+      const uint32_t c = s_hist[k];
+      if (c) atomicAdd(counts + k, (unsigned long long)c);
+    }
   }
 }
 
@@ -299,21 +343,23 @@ int s2b_cell_index_create(const uint64_t* cell_ids, const int32_t* labels, size_
   cudaError_t e = cudaGetDevice(&ix->device);
   if (e != cudaSuccess) { delete ix; return cuda_fail(e, "cudaGetDevice"); }
   auto up = [](size_t v) { return (v + 255) / 256 * 256; };
-  const size_t b_ids = up(8 * (m + 1)), b_lab = up(4 * (m + 1)), b_par = up(4 * (m + 1)), b_first = up(4 * h.first.size());
-  ix->blob_bytes = b_ids + b_lab + b_par + b_first;
-  e = cudaMalloc(&ix->blob, ix->blob_bytes);
+  const size_t R = h.rstart.size();
+  const size_t sizes[6] = {sizeof(CiNode) * (m + 1), 4 * h.first.size(), 8 * R, 4 * h.rfirst.size(), sizeof(CiRangeRec) * R, 4 * (h.llabels.size() + 1)};
+  const void* src[6] = {h.nodes.data(), h.first.data(), h.rstart.data(), h.rfirst.data(), h.rrec.data(), h.llabels.data()};
+  const size_t copy[6] = {sizeof(CiNode) * m, 4 * h.first.size(), 8 * R, 4 * h.rfirst.size(), sizeof(CiRangeRec) * R, 4 * h.llabels.size()};
+  size_t off[7] = {0};
+  for (int k = 0; k < 6; ++k) off[k + 1] = off[k] + up(sizes[k]);
+  ix->blob_bytes = off[6];
+  e = cudaMalloc(&ix->blob, ix->blob_bytes ? ix->blob_bytes : 256);
   if (e != cudaSuccess) { delete ix; return cuda_fail(e, "cudaMalloc(cell index)"); }
   char* base = (char*)ix->blob;
-  if (m) {
-    e = cudaMemcpy(base, h.ids.data(), 8 * m, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(base + b_ids, h.labels.data(), 4 * m, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(base + b_ids + b_lab, h.parent.data(), 4 * m, cudaMemcpyHostToDevice);
-  }
-  if (e == cudaSuccess) e = cudaMemcpy(base + b_ids + b_lab + b_par, h.first.data(), 4 * h.first.size(), cudaMemcpyHostToDevice);
+  for (int k = 0; k < 6 && e == cudaSuccess; ++k)
+    if (copy[k]) e = cudaMemcpy(base + off[k], src[k], copy[k], cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { cudaFree(ix->blob); delete ix; return cuda_fail(e, "cudaMemcpy(cell index)"); }
   ix->num_labels = h.num_labels;
-  ix->view = CellIndexView{(const uint64_t*)base, (const int32_t*)(base + b_ids), (const int32_t*)(base + b_ids + b_lab),
-                           (const uint32_t*)(base + b_ids + b_lab + b_par), (uint32_t)m, 61 - 2 * h.table_level, (uint32_t)(6u << (2 * h.table_level))};
+  ix->view = CellIndexView{(const CiNode*)base, (const uint32_t*)(base + off[1]), (uint32_t)m, 61 - 2 * h.table_level,
+                           (uint32_t)(6u << (2 * h.table_level)), (const uint64_t*)(base + off[2]), (const uint32_t*)(base + off[3]),
+                           (const CiRangeRec*)(base + off[4]), (const int32_t*)(base + off[5]), (uint32_t)R, 61 - 2 * h.range_table_level};
   *out = ix;
   return S2B_OK;
 }
@@ -421,8 +467,21 @@ int s2b_cell_index_point_histogram_dev(const S2bCellIndex* ix, const double* xyz
   if (rc != S2B_OK) return rc;
   if (n == 0) return S2B_OK;
   if (!xyz_dev || (ix->num_labels && !counts_dev)) return set_error(S2B_EINVAL, "null pointer");
-  ci_point_histogram_kernel<<<grid_for_ci(n, (const void*)ci_point_histogram_kernel), kThreads, 0, (cudaStream_t)stream>>>(
-      ix->view, xyz_dev, n, (unsigned long long*)counts_dev);
+  // up to 16K labels the CTA-private histogram fits next to the Hilbert table (<= 66 KB, 3+ CTAs per SM)
+  const bool shared_hist = ix->num_labels <= 16384;
+  const size_t smem = 2048 + (shared_hist ? 4 * (size_t)ix->num_labels : 0);
+  const void* kernel = shared_hist ? (const void*)ci_point_histogram_kernel<true> : (const void*)ci_point_histogram_kernel<false>;
+  cudaError_t ea = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (ea != cudaSuccess) return cuda_fail(ea, "cudaFuncSetAttribute");
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem);
+  if (per_sm < 1) per_sm = 1;
+  const size_t want = (n + kThreads * kPts - 1) / (kThreads * kPts), cap = (size_t)sm_count() * per_sm;
+  const int grid = (int)(want < cap ? want : cap);
+  if (shared_hist)
+    ci_point_histogram_kernel<true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(ix->view, xyz_dev, n, ix->num_labels, (unsigned long long*)counts_dev);
+  else
+    ci_point_histogram_kernel<false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(ix->view, xyz_dev, n, ix->num_labels, (unsigned long long*)counts_dev);
   count_launch();
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? S2B_OK : cuda_fail(e, "ci_point_histogram launch");

@@ -26,7 +26,7 @@ uint64_t hs_cell_index_visit(const uint64_t* ids, const int32_t* labels, size_t 
     const uint32_t b = target_offsets ? target_offsets[t] : (uint32_t)t, e = target_offsets ? target_offsets[t + 1] : (uint32_t)t + 1;
     CiUnionState st;
     got.clear();
-    for (uint32_t k = b; k < e; ++k) ci_visit_cell(ix, target_ids[k], st, [&](uint32_t pos) { got.push_back({ix.ids[pos], ix.labels[pos]}); });
+    for (uint32_t k = b; k < e; ++k) ci_visit_cell(ix, target_ids[k], st, [&](const CiNode& nd) { got.push_back({nd.id, nd.label}); });
     std::sort(got.begin(), got.end());
     for (auto& g : got) {
       if (total < capacity) { out_cells[total] = g.first; out_labels[total] = g.second; }
@@ -50,10 +50,10 @@ void hs_cell_index_best_label(const uint64_t* ids, const int32_t* labels, size_t
     for (uint32_t k = bound_offsets[t]; k < bound_offsets[t + 1]; ++k) {
       const uint64_t target = bound_ids[k];
       st.cutoff = -1;   // every (shard cell, bound cell) overlap counts
-      ci_visit_cell(ix, target, st, [&](uint32_t pos) {
-        const uint64_t c = ci_overlap_cell(ix.ids[pos], target);
+      ci_visit_cell(ix, target, st, [&](const CiNode& nd) {
+        const uint64_t c = ci_overlap_cell(nd.id, target);
         const bool hit = !region_ids || ci_union_intersects(region_ids + region_offsets[t], region_offsets[t + 1] - region_offsets[t], c);
-        got.push_back({ix.labels[pos], hit ? cellid_lsb(c) : 0});
+        got.push_back({nd.label, hit ? cellid_lsb(c) : 0});
       });
     }
     std::stable_sort(got.begin(), got.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
@@ -62,6 +62,27 @@ void hs_cell_index_best_label(const uint64_t* ids, const int32_t* labels, size_t
     for (auto& g : got) { sl.push_back(g.first); sw.push_back(g.second); }
     out[t] = ci_best_label(sl.data(), sw.data(), 0, (uint32_t)sl.size(), fallback);
   }
+}
+
+// The point path: labels of the pairs containing each leaf (range table + flat lists or chain walk), sorted per leaf.
+// force_chain != 0 drops the flat lists. Returns the total; writes at most `capacity` labels.
+uint64_t hs_cell_index_leaf_labels(const uint64_t* ids, const int32_t* labels, size_t m, const uint64_t* leaves, size_t T, int force_chain,
+                                   uint64_t* out_offsets, int32_t* out_labels, uint64_t capacity) {
+  CellIndexHost h;
+  if (!build_cell_index_host(ids, labels, m, &h)) return ~0ull;
+  if (force_chain) h.make_records(false);
+  const CellIndexView ix = h.view();
+  uint64_t total = 0;
+  out_offsets[0] = 0;
+  std::vector<int32_t> got;
+  for (size_t t = 0; t < T; ++t) {
+    got.clear();
+    ci_visit_leaf_labels(ix, leaves[t], [&](int32_t l) { got.push_back(l); });
+    std::sort(got.begin(), got.end());
+    for (int32_t l : got) { if (total < capacity) out_labels[total] = l; ++total; }
+    out_offsets[t + 1] = total;
+  }
+  return total;
 }
 
 }  // extern "C"

@@ -137,3 +137,28 @@ def hs_best(hs, shards, bounds, regions, default):
     hs.hs_cell_index_best_label(vp(ids), vp(labels), ctypes.c_size_t(len(ids)), vp(b_ids), vp(b_off), vp(r_ids), vp(r_off),
                                 ctypes.c_size_t(len(regions)), int(default), vp(out))
     return out
+
+
+def test_leaf_path_matches_visit(hostsim, ref):
+    """The point path (leaf range table + flat label lists / chain walk) reports the labels VisitIntersectingCells gives for
+    the leaf cell, on scenes with nesting, duplicates, leaf-level pairs and range boundaries."""
+    rng = np.random.default_rng(13)
+    hostsim.hs_cell_index_leaf_labels.restype = ctypes.c_uint64
+    for ids, labels in (cs.clustered_scene(rng, 20000, 500), cs.clustered_scene(rng, 300, 7, n_seeds=3),
+                        (np.array([cs.debug_id("1/")], np.uint64), np.array([4], np.int32)), (np.zeros(0, np.uint64), np.zeros(0, np.int32))):
+        ids = np.ascontiguousarray(ids, np.uint64); labels = np.ascontiguousarray(labels, np.int32)
+        lsb = ids & (~ids + np.uint64(1))
+        edges = np.concatenate([ids - (lsb - np.uint64(1)), ids + (lsb - np.uint64(1))])           # first / last leaf of every cell
+        nxt = edges[edges < np.uint64(0xBFFFFFFFFFFFFFFF)] + np.uint64(2)
+        prv = edges[edges > np.uint64(1)] - np.uint64(2)
+        leaves = np.concatenate([cs.random_leaves(rng, 5000), edges, nxt, prv, np.array([1, 0xBFFFFFFFFFFFFFFF], np.uint64)])
+        w_off, w_cells, w_labels = RefCellIndex(ref, ids, labels).visit(leaves)
+        for t in range(len(leaves)):                                                                   # canonical order: by label
+            w_labels[int(w_off[t]):int(w_off[t + 1])].sort()
+        for force_chain in (0, 1):
+            off = np.zeros(len(leaves) + 1, np.uint64)
+            out = np.empty(max(1, len(w_labels)), np.int32)
+            total = hostsim.hs_cell_index_leaf_labels(vp(ids), vp(labels), ctypes.c_size_t(len(ids)), vp(leaves), ctypes.c_size_t(len(leaves)),
+                                                      force_chain, vp(off), vp(out), ctypes.c_uint64(len(out)))
+            assert total == len(w_labels)
+            assert (off == w_off).all() and (out[:total] == w_labels).all()

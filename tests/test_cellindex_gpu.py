@@ -135,3 +135,7 @@ def test_point_histogram_vs_reference(ref):
     assert (got == want).all() and want.sum() > 100000
     dev = ix.point_histogram(torch.from_numpy(pts).cuda())
     assert (dev.cpu().numpy().astype(np.uint64) == want).all()
+    # more labels than the CTA-private histogram holds: the global-atomics variant
+    big = CellIndex(ids, labels + 30000)
+    got = big.point_histogram(pts)
+    assert len(got) == 32000 and (got[30000:] == want).all() and not got[:30000].any()

@@ -10,3 +10,6 @@ dev = torch.device("cuda:0")
 print(json.dumps(bench.cell_index_join_section(args, torch, dev, 0, 1)))
 PY
 echo "bench exit $?"; tail -3 gpurun_out/cellindex_bench.err; cat gpurun_out/cellindex_bench.json
+python tools/prof_cellindex.py > gpurun_out/prof_cellindex_plain.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:ci_point_histogram -s 3 -c 1 -o gpurun_out/prof_cellindex python tools/prof_cellindex.py > gpurun_out/ncu_cellindex.log 2>&1
+tail -2 gpurun_out/ncu_cellindex.log
