@@ -15,6 +15,7 @@
 #include "s2b_core.cuh"
 #include "s2b_hilbert.h"
 #include "s2b_internal.h"
+#include "s2b_sincos.cuh"
 
 struct S2bCellIndex {
   int device = 0;
@@ -159,37 +160,54 @@ ci_point_histogram_kernel(CellIndexView ix, const double* __restrict__ xyz, size
     if (kSharedHist) atomicAdd(s_hist + label, 1u); else atomicAdd(counts + label, 1ull);
   };
   const size_t stride = (size_t)gridDim.x * kThreads * kPts;
-  for (size_t base = (size_t)blockIdx.x * kThreads * kPts + threadIdx.x; base < n; base += stride) {
-    P3 p[kPts];
-    bool live[kPts];
+  auto load_points = [&](size_t base, P3* p) {   // a dead slot (past n) re-reads the thread's first point; it is never used
 #pragma unroll
     for (int q = 0; q < kPts; ++q) {
       const size_t t = base + (size_t)q * kThreads;
-      live[q] = t < n;
-      const size_t tt = live[q] ? t : base;
+      const size_t tt = t < n ? t : base;
       p[q] = P3{__ldcs(xyz + 3 * tt), __ldcs(xyz + 3 * tt + 1), __ldcs(xyz + 3 * tt + 2)};
     }
-    uint64_t leaf[kPts];
-    uint32_t lo[kPts], hi[kPts];
+  };
+  size_t base = (size_t)blockIdx.x * kThreads * kPts + threadIdx.x;
+  P3 p[kPts], p_next[kPts];
+  if (base < n) load_points(base, p);
+  for (; base < n; base += stride) {
+    const size_t next = base + stride;
+    if (next < n) load_points(next, p_next);   // the DRAM latency of the next points hides behind this iteration's lookups
+    bool live[kPts];
+#pragma unroll
+    for (int q = 0; q < kPts; ++q) live[q] = base + (size_t)q * kThreads < n;
+    // (face, i, j) with K1's filtered projection (IEEE division / square root only near a leaf boundary), then just the three
+    // leading steps of FromFaceIJ: enough to name the bucket. The id is finished only if the bucket has to be searched.
+    uint32_t pi[kPts], pj[kPts], lo[kPts], hi[kPts];
+    HilbertState hs[kPts];
 #pragma unroll
     for (int q = 0; q < kPts; ++q) {
-      leaf[q] = cellid_from_point(p[q], s_pos);
-      const uint64_t b = leaf[q] >> ix.rshift;
+      double fi, fj;
+      const int face = point_to_face_fij_checked(p[q], &fi, &fj);
+      pi[q] = fij_to_ij(fi); pj[q] = fij_to_ij(fj);
+      hs[q] = hilbert_steps<7, 5>(hilbert_begin(face), pi[q], pj[q], s_pos);
+      const uint64_t b = hs[q].n >> (ix.rshift - 1);   // id = 2n + 1, so id >> rshift == n >> (rshift - 1)
       lo[q] = __ldg(ix.rfirst + b);
       hi[q] = __ldg(ix.rfirst + b + 1);
     }
     CiRangeRec rec[kPts];
 #pragma unroll
     for (int q = 0; q < kPts; ++q) {
-      while (lo[q] < hi[q]) {   // upper_bound inside the bucket (rare: most buckets hold no range start)
-        const uint32_t mid = lo[q] + ((hi[q] - lo[q]) >> 1);
-        if (__ldg(ix.rstart + mid) <= leaf[q]) lo[q] = mid + 1; else hi[q] = mid;
+      if (lo[q] < hi[q]) {   // upper_bound inside the bucket (rare: most buckets hold no range start)
+        const uint64_t leaf = hilbert_steps<4, 0>(hs[q], pi[q], pj[q], s_pos).n * 2 + 1;
+        do {
+          const uint32_t mid = lo[q] + ((hi[q] - lo[q]) >> 1);
+          if (__ldg(ix.rstart + mid) <= leaf) lo[q] = mid + 1; else hi[q] = mid;
+        } while (lo[q] < hi[q]);
       }
     }
 #pragma unroll
     for (int q = 0; q < kPts; ++q) rec[q] = ci_load_rec(ix.rrec + (lo[q] - 1));
 #pragma unroll
     for (int q = 0; q < kPts; ++q) if (live[q]) ci_emit_rec_labels(ix, rec[q], hit);
+#pragma unroll
+    for (int q = 0; q < kPts; ++q) p[q] = p_next[q];
   }
   if (kSharedHist) {
     __syncthreads();

@@ -317,7 +317,9 @@ inline bool build_cell_index_host(const uint64_t* cell_ids, const int32_t* label
       out->rcontents[r] = top;
     }
   }
-  out->range_table_level = ci_bucket_table(rs, 8.0, 11, &out->rfirst);   // fine buckets: most hold no range start, so no probes
+  // fine buckets: most hold no range start, so no probes. Level <= 10: a bucket is named by the first three 4-bit steps of
+  // FromFaceIJ (24 position bits), which is all the point kernel computes before it looks the bucket up.
+  out->range_table_level = ci_bucket_table(rs, 8.0, 10, &out->rfirst);
   out->make_records(true);
   return true;
 }

@@ -100,6 +100,25 @@ S2B_HD uint64_t from_face_ij(int face, uint32_t i, uint32_t j, const TableT* pos
   return n * 2 + 1;
 }
 
+// FromFaceIJ in two parts: steps kHi..kLo of the loop above on a carried state, so a caller that only needs the leading
+// digits of the Hilbert position (a bucket of a coarse table) can stop early and finish the id only when it has to.
+struct HilbertState { uint64_t n; uint32_t bits; };
+S2B_HD HilbertState hilbert_begin(int face) { return HilbertState{(uint64_t)face << 60, (uint32_t)face & 1u}; }
+template <int kHi, int kLo, class TableT>
+S2B_HD HilbertState hilbert_steps(HilbertState st, uint32_t i, uint32_t j, const TableT* pos) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = kHi; k >= kLo; --k) {
+    st.bits += ((i >> (4 * k)) & 15u) << 6;
+    st.bits += ((j >> (4 * k)) & 15u) << 2;
+    st.bits = pos[st.bits];
+    st.n |= (uint64_t)(st.bits >> 2) << (8 * k);
+    st.bits &= 3u;
+  }
+  return st;
+}
+
 // The projection half of S2CellId(S2Point): face and the UNTRUNCATED leaf coordinates fi = 2^30 * s, fj = 2^30 * t.
 S2B_HD int point_to_face_fij(const P3& p, double* fi, double* fj) {
   double u, v;

@@ -139,3 +139,20 @@ def test_point_histogram_vs_reference(ref):
     big = CellIndex(ids, labels + 30000)
     got = big.point_histogram(pts)
     assert len(got) == 32000 and (got[30000:] == want).all() and not got[:30000].any()
+
+
+def test_point_histogram_on_leaf_boundaries(ref):
+    """Points on / within 1e-8..1e-4 leaf cells of leaf-cell boundaries (where the filtered projection must fall back to the
+    IEEE sequence) against an index whose cells are the fine ancestors of those very leaves: range boundaries coincide
+    with the boundaries the points sit on."""
+    from s2geometry_b200.cellindex import CellIndex
+    from tests.util import leaf_boundary_points
+    rng = np.random.default_rng(31)
+    pts = leaf_boundary_points(400_000, 17)
+    leaves = ref.encode_points(pts, 30, 0)
+    k = 150_000
+    ids = np.concatenate([cs.parent(leaves[:k], rng.integers(22, 31, k)), cs.parent(leaves[:k], rng.integers(2, 22, k))])
+    labels = rng.integers(0, 700, len(ids)).astype(np.int32)
+    want = RefCellIndex(ref, ids, labels).point_histogram(pts)
+    got = CellIndex(ids, labels).point_histogram(pts)
+    assert (got == want).all() and want.sum() > 2 * k
