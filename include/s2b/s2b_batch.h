@@ -6,6 +6,7 @@
 //   S2ContainsPointQuery<Index>::Contains / ShapeContains / VisitContainingShapeIds / GetContainingShapeIds
 //                                                              src/s2/s2contains_point_query.h:92-186
 //   S2CellUnion::Contains(const S2Point&)                      src/s2/s2cell_union.cc:564-566
+//   S2CellIndex::Add/Build/VisitIntersectingCells/GetIntersectingLabels   src/s2/s2cell_index.h:143-195
 // The batch forms below take spans of the same value types (layout compatible: S2Point = 3 doubles, S2CellId = one
 // uint64, S2LatLng = 2 doubles in radians) and run on the GPU. Errors: the reference's path has no error returns
 // (DCHECK only); here every call returns false on failure and s2b::LastError() explains (no exceptions).
@@ -150,6 +151,69 @@ class S2ContainsPointQueryBatch {
 inline bool S2CellUnionContainsBatch(const uint64_t* cell_ids, size_t num_cells, const Point* points, size_t n, uint8_t* out) {
   return s2b_cellunion_contains(cell_ids, num_cells, &points->x, n, out) == S2B_OK;
 }
+
+// ---- S2CellIndex, batch form ---------------------------------------------------------------------------------------
+// Add() collects (cell_id, label) pairs on the host, Build() uploads the index to the current CUDA device; the queries take a
+// batch of targets. Targets are S2CellUnions in CSR form (cell ids sorted and non-overlapping per target).
+class S2CellIndexBatch {
+ public:
+  S2CellIndexBatch() = default;
+  S2CellIndexBatch(const S2CellIndexBatch&) = delete;
+  S2CellIndexBatch& operator=(const S2CellIndexBatch&) = delete;
+  ~S2CellIndexBatch() { s2b_cell_index_destroy(h_); }
+  void Add(uint64_t cell_id, int32_t label) { ids_.push_back(cell_id); labels_.push_back(label); }
+  void Add(const std::vector<uint64_t>& cell_union, int32_t label) { for (uint64_t id : cell_union) Add(id, label); }
+  int num_cells() const { return (int)ids_.size(); }
+  bool Build() {
+    s2b_cell_index_destroy(h_);
+    h_ = nullptr;
+    return s2b_cell_index_create(ids_.data(), labels_.data(), ids_.size(), &h_) == S2B_OK;
+  }
+  void Clear() { s2b_cell_index_destroy(h_); h_ = nullptr; ids_.clear(); labels_.clear(); }
+  // VisitIntersectingCells for every target: pairs of target t are (cell_ids, labels)[offsets[t] .. offsets[t+1]).
+  bool GetIntersectingCells(const std::vector<uint64_t>& target_ids, const std::vector<uint32_t>& target_offsets,
+                            std::vector<uint32_t>* offsets, std::vector<uint64_t>* cell_ids, std::vector<int32_t>* labels) const {
+    const size_t T = target_offsets.empty() ? 0 : target_offsets.size() - 1;
+    offsets->assign(T + 1, 0);
+    size_t total = 0;
+    int rc = s2b_cell_index_intersecting_cells(h_, target_ids.data(), target_offsets.data(), T, offsets->data(), nullptr, nullptr, 0, &total);
+    if (rc != S2B_OK && rc != S2B_ECAPACITY) return false;
+    cell_ids->resize(total);
+    labels->resize(total);
+    if (total == 0) return true;
+    return s2b_cell_index_intersecting_cells(h_, target_ids.data(), target_offsets.data(), T, offsets->data(), cell_ids->data(), labels->data(), total,
+                                             &total) == S2B_OK;
+  }
+  // GetIntersectingLabels for every target: distinct labels, ascending.
+  bool GetIntersectingLabels(const std::vector<uint64_t>& target_ids, const std::vector<uint32_t>& target_offsets,
+                             std::vector<uint32_t>* offsets, std::vector<int32_t>* labels) const {
+    const size_t T = target_offsets.empty() ? 0 : target_offsets.size() - 1;
+    offsets->assign(T + 1, 0);
+    labels->resize(2 * T + 1024);
+    size_t total = 0;
+    int rc = s2b_cell_index_intersecting_labels(h_, target_ids.data(), target_offsets.data(), T, offsets->data(), labels->data(), labels->size(), &total);
+    if (rc == S2B_ECAPACITY && total > labels->size()) {
+      labels->resize(total);
+      rc = s2b_cell_index_intersecting_labels(h_, target_ids.data(), target_offsets.data(), T, offsets->data(), labels->data(), labels->size(), &total);
+    }
+    if (rc != S2B_OK) return false;
+    labels->resize(total);
+    return true;
+  }
+  // counts[label] = number of (point, indexed cell) pairs whose cell contains the point (VisitIntersectingCells on the leaf cell).
+  bool CountPointsPerLabel(const Point* points, size_t n, std::vector<uint64_t>* counts) const {
+    int32_t num_labels = 0;
+    if (s2b_cell_index_info(h_, nullptr, &num_labels, nullptr) != S2B_OK) return false;
+    counts->assign((size_t)num_labels, 0);
+    return s2b_cell_index_point_histogram(h_, &points->x, n, counts->data()) == S2B_OK;
+  }
+  const S2bCellIndex* handle() const { return h_; }
+
+ private:
+  std::vector<uint64_t> ids_;
+  std::vector<int32_t> labels_;
+  S2bCellIndex* h_ = nullptr;
+};
 
 }  // namespace s2b
 

@@ -98,6 +98,26 @@ int main() {
     s2b_point_index_destroy(pi);
   }
 
+  // S2CellIndex: IntersectionOptimization scene (s2cell_index_test.cc:387-398): 1/001 -> 1, 1/333 -> 2, 2/00 -> 3, 2/0232 -> 4
+  {
+    auto child = [](uint64_t id, int k) { uint64_t nl = (id & (~id + 1)) >> 2; return id + (uint64_t)(2 * k + 1 - 4) * nl; };
+    auto cell = [&](int face, const char* digits) { uint64_t id = ((uint64_t)face << 61) | (1ull << 60); for (const char* d = digits; *d; ++d) id = child(id, *d - '0'); return id; };
+    s2b::S2CellIndexBatch ci;
+    ci.Add(cell(1, "001"), 1); ci.Add(cell(1, "333"), 2); ci.Add(cell(2, "00"), 3); ci.Add(cell(2, "0232"), 4);
+    CHECK(ci.Build());
+    std::vector<uint64_t> targets = {cell(1, "010"), cell(1, "3"), cell(2, "010"), cell(2, "011"), cell(2, "02")};
+    std::vector<uint32_t> toff = {0, 2, 5}, off;
+    std::vector<int32_t> labels;
+    CHECK(ci.GetIntersectingLabels(targets, toff, &off, &labels));
+    CHECK(off.size() == 3 && off[1] == 1 && off[2] == 2 && labels.size() == 2 && labels[0] == 2 && labels[1] == 4);   // the reference's answer
+    std::vector<uint64_t> cells_out;
+    CHECK(ci.GetIntersectingCells(targets, toff, &off, &cells_out, &labels) && cells_out.size() == 2 && cells_out[0] == cell(1, "333") &&
+          cells_out[1] == cell(2, "0232"));
+    std::vector<uint64_t> counts;
+    s2b::Point on_face2 = {0.0, 0.0, 1.0};   // the centre of face 2 lies in none of the four cells
+    CHECK(ci.CountPointsPerLabel(&on_face2, 1, &counts) && counts.size() == 5 && counts[1] + counts[2] + counts[3] + counts[4] == 0);
+  }
+
   // S2CellUnion::Contains: Trondheim (python/s2geometry_test.py:254-259)
   uint64_t cells[2] = {0x466D319000000000ull, 0x466D31B000000000ull};
   s2b::Point trondheim = FromDegrees(63.431052, 10.395083);
