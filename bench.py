@@ -324,57 +324,78 @@ def radius_join_section(args, torch, dev, rank, world):
 
 
 def cell_index_join_section(args, torch, dev, rank, world):
-    """S2CellIndex join. 10k labelled coverings (a level-5..11 cell and its AppendAllNeighbors ring, built
-    with the library's own cell algebra) indexed in an S2CellIndex; every point of this rank's share of the stream reports the
-    (cell, label) pairs VisitIntersectingCells gives for its leaf cell -> per-label hit histogram (fused encode + traversal)."""
+    """S2CellIndex join. 10k labelled coverings (a cell and its AppendAllNeighbors ring, built with the
+    library's own cell algebra) indexed in an S2CellIndex; every point of this rank's share of the stream reports the
+    (cell, label) pairs VisitIntersectingCells gives for its leaf cell -> per-label hit histogram (fused encode + lookup),
+    all-reduced over the ranks. Two scenes: dense (cells of levels 5..11, ~2.9 pairs per point) and sparse (levels 9..13)."""
+    import torch.distributed as dist
     from s2geometry_b200 import cellid, synth
     from s2geometry_b200.cellindex import CellIndex
-    rng = np.random.default_rng(123)
     num_labels = 10000
     centers = synth.sphere_points(num_labels, 55)
     leaves = cellid.from_points(centers, 30)
-    label_level = rng.integers(5, 12, num_labels)
-    ids, labels = [], []
-    for level in range(5, 12):
-        sel = np.nonzero(label_level == level)[0]
-        c = cellid.parent(leaves[sel], level)
-        nb, cnt = cellid.all_neighbors(c, level)
-        for k, lab in enumerate(sel):
-            cells = np.concatenate([c[k:k + 1], nb[k, :cnt[k]]])
-            ids.append(cells); labels.append(np.full(len(cells), lab, np.int32))
-    ids, labels = np.concatenate(ids).astype(np.uint64), np.concatenate(labels).astype(np.int32)
-    t0 = time.perf_counter()
-    ix = CellIndex(ids, labels)
-    build_s = time.perf_counter() - t0
     n = args.points
     pts = synth.sphere_points_cuda(n, 300 + rank, dev)
-    for _ in range(3):
-        counts = ix.point_histogram(pts)
-    torch.cuda.synchronize()
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        counts = ix.point_histogram(pts)
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
     hbm_peak, _ = peaks()
-    ach = 24 * n / (ms * 1e-3) / 1e9
-    out = {"workload": "S2CellIndex join: %d uniform points per GPU vs %d (cell, label) pairs of %d labels, per-label hit histogram" % (n, len(ids), num_labels),
-           "points_per_s": n / (ms * 1e-3), "ms_per_step": ms, "index_build_s": build_s, "pairs_found": int(counts.sum().item()), "bytes_per_point": 24,
-           "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak}}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        try:
-            from oracle import reflib  # cpu_baseline leg
-            ref = reflib.load()
-            k = min(n, 20_000_000)
-            sample = pts[:k].cpu().numpy()
-            ri = reflib.RefCellIndex(ref, ids, labels)
-            t0 = time.perf_counter(); want = ri.point_histogram(sample, ref.hardware_threads()); dt = time.perf_counter() - t0
-            got = ix.point_histogram(pts[:k]).cpu().numpy().astype(np.uint64)
-            out["cpu_baseline"] = {"value": k / dt, "unit": "points/s", "cores": ref.hardware_threads(), "kind": "reference",
-                                   "sample": "first %d points, S2CellIndex::VisitIntersectingCells per point" % k, "parity_on_sample": bool((got == want).all())}
-        except Exception as e:
-            out["cpu_baseline"] = {"unavailable": str(e)}
+
+    def scene(level_lo, level_hi):
+        rng = np.random.default_rng(123)
+        label_level = rng.integers(level_lo, level_hi + 1, num_labels)
+        ids, labels = [], []
+        for level in range(level_lo, level_hi + 1):
+            sel = np.nonzero(label_level == level)[0]
+            c = cellid.parent(leaves[sel], level)
+            nb, cnt = cellid.all_neighbors(c, level)
+            for k, lab in enumerate(sel):
+                cells = np.concatenate([c[k:k + 1], nb[k, :cnt[k]]])
+                ids.append(cells); labels.append(np.full(len(cells), lab, np.int32))
+        return np.concatenate(ids).astype(np.uint64), np.concatenate(labels).astype(np.int32)
+
+    def run(level_lo, level_hi, with_cpu):
+        ids, labels = scene(level_lo, level_hi)
+        t0 = time.perf_counter()
+        ix = CellIndex(ids, labels)
+        build_s = time.perf_counter() - t0
+
+        def step():
+            counts = ix.point_histogram(pts)
+            if world > 1:
+                dist.all_reduce(counts)
+            return counts
+        for _ in range(3):
+            counts = step()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            counts = step()
+        e1.record(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        ach = 24 * n / (ms * 1e-3) / 1e9
+        out = {"workload": "S2CellIndex join: %d uniform points per GPU vs %d (cell, label) pairs of %d labels (cells of levels %d..%d), per-label hit histogram"
+                           % (n, len(ids), num_labels, level_lo, level_hi),
+               "points_per_s": world * n / (ms * 1e-3), "ms_per_step": ms, "index_build_s": build_s, "pairs_found": int(counts.sum().item()),
+               "bytes_per_point": 24, "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "note": "per GPU"}}
+        if with_cpu and rank == 0 and world == 1 and not args.no_cpu_baseline:
+            try:
+                from oracle import reflib  # cpu_baseline leg
+                ref = reflib.load()
+                k = min(n, 20_000_000)
+                sample = pts[:k].cpu().numpy()
+                ri = reflib.RefCellIndex(ref, ids, labels)
+                t0 = time.perf_counter(); want = ri.point_histogram(sample, ref.hardware_threads()); dt = time.perf_counter() - t0
+                got = ix.point_histogram(pts[:k]).cpu().numpy().astype(np.uint64)
+                out["cpu_baseline"] = {"value": k / dt, "unit": "points/s", "cores": ref.hardware_threads(), "kind": "reference",
+                                       "sample": "first %d points, S2CellIndex::VisitIntersectingCells per point" % k, "parity_on_sample": bool((got == want).all())}
+            except Exception as e:
+                out["cpu_baseline"] = {"unavailable": str(e)}
+        ix.close()
+        return out
+    out = run(5, 11, True)
+    out["sparse"] = run(9, 13, True)
     return out
 
 
