@@ -396,6 +396,34 @@ def cell_index_join_section(args, torch, dev, rank, world):
         return out
     out = run(5, 11, True)
     out["sparse"] = run(9, 13, True)
+    if rank == 0 and world == 1:
+        # Cell targets through the host-pointer API (copies included): VisitIntersectingCells for 10M cells of levels 8..16.
+        ids, labels = scene(5, 11)
+        ix = CellIndex(ids, labels)
+        m = min(n, 10_000_000)
+        tl = cellid.from_points(pts[:m], 30).cpu().numpy().view(np.uint64)
+        targets = tl.copy()
+        lv = np.random.default_rng(5).integers(8, 17, m).astype(np.uint64)
+        lsb = np.uint64(1) << (np.uint64(2) * (np.uint64(30) - lv))
+        targets = (tl & (~lsb + np.uint64(1))) | lsb
+        ix.intersecting_cells(targets[:100000])
+        t0 = time.perf_counter(); off, cells, labs = ix.intersecting_cells(targets); dt = time.perf_counter() - t0
+        ct = {"workload": "VisitIntersectingCells for %d single-cell targets (levels 8..16) through host buffers, CSR of (cell, label) pairs out" % m,
+              "targets_per_s": m / dt, "pairs_found": int(off[-1]), "seconds": dt}
+        if not args.no_cpu_baseline:
+            try:
+                from oracle import reflib  # cpu_baseline leg
+                ref = reflib.load()
+                k = 1_000_000
+                ri = reflib.RefCellIndex(ref, ids, labels)
+                t0 = time.perf_counter(); w_off, w_cells, w_labels = ri.visit(targets[:k]); dtc = time.perf_counter() - t0
+                ct["cpu_baseline"] = {"value": k / dtc, "unit": "targets/s", "cores": 1, "kind": "reference", "sample": "first %d targets" % k,
+                                      "parity_on_sample": bool((off[:k + 1].astype(np.uint64) == w_off).all()
+                                                               and np.array_equal(np.sort(labs[:int(off[k])]), np.sort(w_labels)))}
+            except Exception as e:
+                ct["cpu_baseline"] = {"unavailable": str(e)}
+        out["cell_targets"] = ct
+        ix.close()
     return out
 
 
