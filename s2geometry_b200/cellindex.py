@@ -63,6 +63,8 @@ class CellIndex:
     def intersecting_cells(self, targets):
         """VisitIntersectingCells (s2cell_index.h:619-647) per target: (offsets[T+1], cell_ids, labels); order within a
         target is unspecified, as in the reference."""
+        if torch is not None and isinstance(targets, torch.Tensor):
+            return self._intersecting_cells_dev(targets)
         ids, off, T = _csr(targets)
         out_off = np.zeros(T + 1, np.uint32)
         total = ctypes.c_size_t(0)
@@ -76,6 +78,25 @@ class CellIndex:
             _lib.check(self._lib.s2b_cell_index_intersecting_cells(self._h, _ptr(ids), _ptr(off) if off is not None else None, T, out_off.ctypes.data,
                                                                    cells.ctypes.data, labels.ctypes.data, total.value, ctypes.byref(total)))
         return out_off, cells, labels
+
+    def _intersecting_cells_dev(self, targets):
+        """Device path: `targets` = int64 CUDA tensor of single-cell targets; returns CUDA tensors (offsets int32, cells int64, labels int32)."""
+        t = targets.contiguous()
+        T = t.numel()
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        off = torch.zeros(T + 1, dtype=torch.int32, device=t.device)
+        total = ctypes.c_size_t(0)
+        cap = max(1024, 4 * T)
+        while True:
+            cells = torch.empty(cap, dtype=torch.int64, device=t.device)
+            labels = torch.empty(cap, dtype=torch.int32, device=t.device)
+            rc = self._lib.s2b_cell_index_intersecting_cells_dev(self._h, t.data_ptr(), None, T, off.data_ptr(), cells.data_ptr(), labels.data_ptr(), cap,
+                                                                 ctypes.byref(total), st)
+            if rc == _lib.S2B_ECAPACITY and total.value > cap:
+                cap = total.value
+                continue
+            _lib.check(rc)
+            return off, cells[: total.value], labels[: total.value]
 
     def intersecting_labels(self, targets):
         """GetIntersectingLabels (s2cell_index.cc:148-163) per target: (offsets[T+1], labels ascending, distinct)."""

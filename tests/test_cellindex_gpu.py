@@ -73,6 +73,20 @@ def test_clustered_scene(ref):
     check_scene(ref, ids, labels, unions)
 
 
+def test_device_path_matches_host_path(ref):
+    import torch
+    from s2geometry_b200.cellindex import CellIndex
+    rng = np.random.default_rng(17)
+    ids, labels = cs.clustered_scene(rng, 50000, 900, n_seeds=100)
+    ix = CellIndex(ids, labels)
+    targets = np.concatenate([cs.random_cells(rng, 20000), ids[:20000], cs.random_leaves(rng, 5000)])
+    off, cells, labs = ix.intersecting_cells(targets)
+    d_off, d_cells, d_labs = ix.intersecting_cells(torch.from_numpy(targets.view(np.int64)).cuda())
+    assert (d_off.cpu().numpy().astype(np.uint32) == off).all()
+    assert (d_cells.cpu().numpy().view(np.uint64) == cells).all() and (d_labs.cpu().numpy() == labs).all()
+    assert off[-1] > 4 * len(targets)          # the first capacity guess was too small: the retry path ran
+
+
 def test_invalid_inputs(ref):
     from s2geometry_b200 import _lib
     from s2geometry_b200.cellindex import CellIndex
