@@ -427,6 +427,66 @@ def cell_index_join_section(args, torch, dev, rank, world):
     return out
 
 
+def region_cells_section(args, torch, dev, rank, world):
+    """S2ShapeIndexRegion cell tests, the calls an S2RegionCoverer makes on an index region. Targets:
+    cells of levels 6..20 containing points drawn in the 10k-vertex loop's bounding cap (so many of them meet the
+    boundary), classified with MayIntersect(S2Cell) and Contains(S2Cell) against the reference-built default-granularity
+    index (the answers depend on the index's cells, so the reference's own index is the one to compare on)."""
+    import ctypes
+    from s2geometry_b200 import _lib, cellid, synth
+    from s2geometry_b200.index import FlatIndex, ShapeIndex, ShapeIndexRegion
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "index_loop10k.npz"))
+    flat = FlatIndex(**{k: fx[k] for k in FlatIndex.FIELDS}, num_shape_ids=int(fx["num_shape_ids"]))
+    region = ShapeIndexRegion(ShapeIndex(flat))
+    m = min(args.points, 20_000_000)
+    g = torch.Generator(device=dev); g.manual_seed(77 + rank)
+    center = np.array([0.3, -0.5, 0.8]); radius = 0.17 * 1.25
+    x, y, z = [torch.from_numpy(v).to(dev) for v in synth.frame(center)]
+    h = torch.rand(m, dtype=torch.float64, device=dev, generator=g) * (1 - np.cos(radius))
+    t = torch.rand(m, dtype=torch.float64, device=dev, generator=g) * (2 * np.pi)
+    cz = 1 - h; sz = torch.sqrt(torch.clamp(1 - cz * cz, min=0))
+    pts = cz[:, None] * z + sz[:, None] * (torch.cos(t)[:, None] * x + torch.sin(t)[:, None] * y)
+    pts /= pts.norm(dim=1, keepdim=True)
+    leaf = cellid.from_points(pts, 30)
+    level = torch.randint(6, 21, (m,), device=dev, generator=g, dtype=torch.int64)
+    lsb = torch.ones_like(level) << (2 * (30 - level))
+    targets = ((leaf & -lsb) | lsb).contiguous()
+    del pts, h, t, cz, sz, leaf, level, lsb
+    out = {"workload": "S2ShapeIndexRegion cell tests: %d target cells (levels 6..20, in the bounding cap of the 10k-vertex loop) per GPU vs the "
+                       "reference-built index (%d cells, %d clipped edges)" % (m, flat.num_cells, flat.num_edges)}
+    for name, fn in (("may_intersect", region.may_intersect), ("contains_cell", region.contains_cells)):
+        for _ in range(3):
+            res = fn(targets)
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            res = fn(targets)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        out[name] = {"targets_per_s": world * m / (ms * 1e-3), "ms_per_step": ms, "true_fraction": float(res.float().mean().item())}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import reflib  # cpu_baseline leg
+            from s2geometry_b200.shapes import ShapeSoup
+            ref = reflib.load()
+            soup = ShapeSoup(); soup.add_polygon([fx["loop_vertices"]])
+            ri = ref.index_create(soup.freeze())
+            k = min(m, 1_000_000)
+            sample = targets[:k].cpu().numpy().view(np.uint64)
+            base = {"cores": 1, "kind": "reference", "sample": "first %d targets, one S2ShapeIndexRegion" % k, "unit": "targets/s"}
+            ok = True
+            for mode, name, fn in ((0, "may_intersect", region.may_intersect), (1, "contains_cell", region.contains_cells)):
+                t0 = time.perf_counter(); want = ri.region_cells(sample, mode); dt = time.perf_counter() - t0
+                base[name] = k / dt
+                ok = ok and bool((fn(targets[:k]).cpu().numpy() == want).all())
+            base["parity_on_sample"] = ok
+            out["cpu_baseline"] = base
+        except Exception as e:
+            out["cpu_baseline"] = {"unavailable": str(e)}
+    return out
+
+
 def join_section(args, torch, dev, rank, world):
     """BASELINE configs[3]: spatial join, `join_points` uniform points (default 1B, sharded over the ranks: strong
     scaling) vs 10k synthetic polygons -> per-polygon hit counts; the only collective is the NCCL all-reduce of the
@@ -659,6 +719,13 @@ def run_gpu(args):
             torch.cuda.empty_cache()
         except Exception as e:
             cell_index_join = {"error": repr(e)}
+    region_cells = None
+    if not args.no_join:
+        try:
+            region_cells = region_cells_section(args, torch, dev, rank, world)
+            torch.cuda.empty_cache()
+        except Exception as e:
+            region_cells = {"error": repr(e)}
     if rank == 0:
         hbm_peak, peak_src = peaks()
         kern_ms = float(np.mean(per_launch_ms))
@@ -697,6 +764,8 @@ def run_gpu(args):
             line["radius_join"] = radius_join
         if cell_index_join is not None:
             line["cell_index_join"] = cell_index_join
+        if region_cells is not None:
+            line["region_cells"] = region_cells
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline()

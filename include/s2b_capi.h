@@ -32,6 +32,7 @@ extern "C" {
 #define S2B_ECUDA (-2)   /* CUDA runtime / launch failure, or no usable device */
 #define S2B_ENOMEM (-3)  /* host or device allocation failed */
 #define S2B_ECAPACITY (-4) /* caller-provided output capacity too small; required size is reported */
+#define S2B_EUNSUPPORTED (-5) /* the input needs a stage this library does not run on the device (stated per function) */
 
 /* S2VertexModel (s2contains_point_query.h:54) */
 #define S2B_VERTEX_MODEL_OPEN 0
@@ -266,6 +267,28 @@ int s2b_index_locate_points_dev(const S2bIndex* index, const double* xyz_dev, si
 int s2b_index_locate_cells(const S2bIndex* index, const uint64_t* cell_ids, size_t n, uint8_t* relation_out, int32_t* cell_out);
 int s2b_index_locate_cells_dev(const S2bIndex* index, const uint64_t* cell_ids_dev, size_t n, uint8_t* relation_out_dev,
                                int32_t* cell_out_dev, void* stream);
+
+/* S2ShapeIndexRegion's cell tests (s2shape_index_region.h) for a batch of target cells: what an S2RegionCoverer, or a
+ * cell-vs-polygon classification join, asks of an index region. One target per thread: Locate(S2CellId), then for a
+ * target inside an index cell AnyEdgeIntersects (:447-465: S2::ClipToPaddedFace + S2::IntersectsRect,
+ * s2edge_clipping.cc:323-384, padded by kFaceClipErrorUVCoord + kIntersectsRectErrorUVDist) and ShapeContains of the
+ * target's centre (SEMI_OPEN). Results depend on the index's cell structure exactly as the reference's do (a target that
+ * is SUBDIVIDED "may intersect"), so they are identical to the reference's over an index with the same cells.
+ *   s2b_region_may_intersect_cells  S2ShapeIndexRegion::MayIntersect(const S2Cell&)  :344-371
+ *   s2b_region_contains_cells       S2ShapeIndexRegion::Contains(const S2Cell&)      :313-342
+ * S2::RobustCrossProd (s2edge_crossings.cc:147-177) is evaluated in double precision, which decides every edge whose
+ * endpoints are further apart than ~9 * DBL_EPSILON (and a == b, which yields Ortho(a)). An index holding an edge that
+ * would need the reference's long double / exact stages is refused with S2B_EUNSUPPORTED by these functions. */
+int s2b_region_may_intersect_cells(const S2bIndex* index, const uint64_t* cell_ids, size_t n, uint8_t* out);
+int s2b_region_may_intersect_cells_dev(const S2bIndex* index, const uint64_t* cell_ids_dev, size_t n, uint8_t* out_dev, void* stream);
+int s2b_region_contains_cells(const S2bIndex* index, const uint64_t* cell_ids, size_t n, uint8_t* out);
+int s2b_region_contains_cells_dev(const S2bIndex* index, const uint64_t* cell_ids_dev, size_t n, uint8_t* out_dev, void* stream);
+/* S2ShapeIndexRegion::VisitIntersectingShapeIds (:373-424) as a CSR: the pairs of target i are
+ * [offsets_out[i], offsets_out[i+1]) of (shape_ids_out, contains_out), ascending by shape id (the reference visits a
+ * SUBDIVIDED target's shapes in hash-map order, i.e. unspecified). contains_out = 1 when the shape contains the whole
+ * target cell. *total_out (nullable) = number of pairs; S2B_ECAPACITY after filling offsets_out if capacity is smaller. */
+int s2b_region_intersecting_shapes(const S2bIndex* index, const uint64_t* cell_ids, size_t n, uint32_t* offsets_out,
+                                   int32_t* shape_ids_out, uint8_t* contains_out, size_t capacity, size_t* total_out);
 /* Any output may be NULL. device_bytes = HBM held by the replica (ids + cells + clips + edges + lookup table). */
 int s2b_index_info(const S2bIndex* index, uint64_t* num_cells, uint64_t* num_clips, uint64_t* num_edges,
                    int32_t* num_shape_ids, uint64_t* device_bytes);

@@ -42,6 +42,9 @@
 #include "s2/s2predicates_internal.h"
 #include "s2/s2region_coverer.h"
 #include "s2/s2shape.h"
+#include "s2/s2cell.h"
+#include "s2/s2edge_clipping.h"
+#include "s2/s2shape_index_region.h"
 #include "s2/s2shapeutil_contains_brute_force.h"
 #include "s2/s2shapeutil_get_reference_point.h"
 #include "s2/util/coding/coder.h"
@@ -433,6 +436,54 @@ void ref_index_locate_cells(void* h, const uint64_t* ids, size_t n, uint8_t* rel
     S2CellRelation r = it.Locate(S2CellId(ids[i]));
     relation[i] = (uint8_t)static_cast<int>(r);
     at[i] = r == S2CellRelation::DISJOINT ? 0 : it.id().id();
+  }
+}
+
+// S2ShapeIndexRegion::MayIntersect(S2Cell) (mode 0) / Contains(S2Cell) (mode 1) per target cell.
+void ref_region_cells(void* h, const uint64_t* ids, size_t n, int mode, uint8_t* out) {
+  auto& index = ((RefIndex*)h)->index;
+  S2ShapeIndexRegion<MutableS2ShapeIndex> region(&index);
+  for (size_t i = 0; i < n; ++i) {
+    S2Cell cell{S2CellId(ids[i])};
+    out[i] = mode == 0 ? region.MayIntersect(cell) : region.Contains(cell);
+  }
+}
+
+// S2ShapeIndexRegion::VisitIntersectingShapeIds per target cell, pairs sorted by shape id (the visiting order of a
+// SUBDIVIDED target is the hash map's). Returns the number of pairs; writes them when capacity suffices.
+size_t ref_region_intersecting_shapes(void* h, const uint64_t* ids, size_t n, uint32_t* offsets, int32_t* shape_ids,
+                                      uint8_t* contains, size_t capacity) {
+  auto& index = ((RefIndex*)h)->index;
+  S2ShapeIndexRegion<MutableS2ShapeIndex> region(&index);
+  size_t total = 0;
+  std::vector<std::pair<int, bool>> found;
+  for (size_t i = 0; i < n; ++i) {
+    offsets[i] = (uint32_t)total;
+    found.clear();
+    region.VisitIntersectingShapeIds(S2Cell(S2CellId(ids[i])), [&](int id, bool c) { found.emplace_back(id, c); return true; });
+    std::sort(found.begin(), found.end());
+    for (auto& f : found) {
+      if (total < capacity) { shape_ids[total] = f.first; contains[total] = f.second; }
+      ++total;
+    }
+  }
+  offsets[n] = (uint32_t)total;
+  return total;
+}
+
+// S2::ClipToPaddedFace + S2::IntersectsRect on raw inputs: out_uv = (a.u, a.v, b.u, b.v) per edge, ok = return value.
+void ref_clip_to_padded_face(const double* a, const double* b, const int32_t* face, size_t n, double padding, double* out_uv, uint8_t* ok) {
+  for (size_t i = 0; i < n; ++i) {
+    R2Point p0(0, 0), p1(0, 0);
+    ok[i] = S2::ClipToPaddedFace(P(a + 3 * i), P(b + 3 * i), face[i], padding, &p0, &p1);
+    out_uv[4 * i] = p0[0]; out_uv[4 * i + 1] = p0[1]; out_uv[4 * i + 2] = p1[0]; out_uv[4 * i + 3] = p1[1];
+  }
+}
+void ref_intersects_rect(const double* uv4, const double* rect4, size_t n, uint8_t* out) {
+  for (size_t i = 0; i < n; ++i) {
+    const double* r = rect4 + 4 * i;
+    out[i] = S2::IntersectsRect(R2Point(uv4[4 * i], uv4[4 * i + 1]), R2Point(uv4[4 * i + 2], uv4[4 * i + 3]),
+                                R2Rect(R1Interval(r[0], r[1]), R1Interval(r[2], r[3])));
   }
 }
 

@@ -207,6 +207,19 @@ class Ref:
     def index_create(self, soup, max_edges_per_cell=0):
         return RefIndex(self, soup, max_edges_per_cell)
 
+    # ---- edge clipping (S2ShapeIndexRegion::AnyEdgeIntersects)
+    def clip_to_padded_face(self, a, b, face, padding):
+        a = np.ascontiguousarray(a, np.float64); b = np.ascontiguousarray(b, np.float64); face = np.ascontiguousarray(face, np.int32)
+        uv = np.zeros((len(a), 4)); ok = np.zeros(len(a), np.uint8)
+        self.lib.ref_clip_to_padded_face(_p(a), _p(b), _p(face), _sz(len(a)), ctypes.c_double(padding), _p(uv), _p(ok))
+        return uv, ok
+
+    def intersects_rect(self, uv4, rect4):
+        uv4 = np.ascontiguousarray(uv4, np.float64); rect4 = np.ascontiguousarray(rect4, np.float64)
+        out = np.zeros(len(uv4), np.uint8)
+        self.lib.ref_intersects_rect(_p(uv4), _p(rect4), _sz(len(uv4)), _p(out))
+        return out
+
     # ---- cell unions
     def cellunion_contains(self, ids, xyz, threads=0):
         ids = np.ascontiguousarray(ids, np.uint64); xyz = np.ascontiguousarray(xyz, np.float64)
@@ -313,6 +326,23 @@ class RefIndex:
         rel = np.empty(ids.size, np.uint8); at = np.empty(ids.size, np.uint64)
         self.lib.ref_index_locate_cells(_vp(self.h), _p(ids), _sz(ids.size), _p(rel), _p(at))
         return rel, at
+
+    def region_cells(self, ids, mode):
+        """S2ShapeIndexRegion::MayIntersect (mode 0) / Contains (mode 1) of S2Cell(ids[i])."""
+        ids = np.ascontiguousarray(ids, np.uint64)
+        out = np.empty(ids.size, np.uint8)
+        self.lib.ref_region_cells(_vp(self.h), _p(ids), _sz(ids.size), int(mode), _p(out))
+        return out
+
+    def region_intersecting_shapes(self, ids):
+        """S2ShapeIndexRegion::VisitIntersectingShapeIds per target: (offsets, shape ids, contains flags), sorted by shape id."""
+        ids = np.ascontiguousarray(ids, np.uint64)
+        self.lib.ref_region_intersecting_shapes.restype = _sz
+        off = np.zeros(ids.size + 1, np.uint32)
+        total = int(self.lib.ref_region_intersecting_shapes(_vp(self.h), _p(ids), _sz(ids.size), _p(off), None, None, _sz(0)))
+        shp = np.zeros(max(total, 1), np.int32); con = np.zeros(max(total, 1), np.uint8)
+        self.lib.ref_region_intersecting_shapes(_vp(self.h), _p(ids), _sz(ids.size), _p(off), _p(shp), _p(con), _sz(total))
+        return off, shp[:total], con[:total]
 
     def encode(self):
         """MutableS2ShapeIndex::Encode -> bytes."""

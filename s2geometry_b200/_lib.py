@@ -94,6 +94,11 @@ SIGNATURES = {
     "s2b_index_locate_points_dev": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "s2b_index_locate_cells": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "s2b_index_locate_cells_dev": (_i, [_vp, _vp, _sz, _vp, _vp, _vp]),
+    "s2b_region_may_intersect_cells": (_i, [_vp, _vp, _sz, _vp]),
+    "s2b_region_may_intersect_cells_dev": (_i, [_vp, _vp, _sz, _vp, _vp]),
+    "s2b_region_contains_cells": (_i, [_vp, _vp, _sz, _vp]),
+    "s2b_region_contains_cells_dev": (_i, [_vp, _vp, _sz, _vp, _vp]),
+    "s2b_region_intersecting_shapes": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp]),
     "s2b_index_info": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "s2b_contains": (_i, [_vp, _vp, _sz, _i, _vp]),
     "s2b_contains_dev": (_i, [_vp, _vp, _sz, _i, _vp, _vp]),
@@ -111,7 +116,7 @@ SIGNATURES = {
 }
 
 
-S2B_OK, S2B_EINVAL, S2B_ECUDA, S2B_ENOMEM, S2B_ECAPACITY = 0, -1, -2, -3, -4   # include/s2b_capi.h
+S2B_OK, S2B_EINVAL, S2B_ECUDA, S2B_ENOMEM, S2B_ECAPACITY, S2B_EUNSUPPORTED = 0, -1, -2, -3, -4, -5   # include/s2b_capi.h
 
 
 class S2BError(RuntimeError):

@@ -15,6 +15,8 @@
 #include "s2b_contains.cuh"
 #include "s2b_flat_host.h"
 #include "s2b_hilbert.h"
+#include "s2b_index_handle.h"
+#include "s2b_region.cuh"
 #include "s2b_internal.h"
 
 namespace s2b {
@@ -621,15 +623,6 @@ static cudaError_t launch_query_t(const FlatIndexView& ix, const double* xyz, si
 using namespace s2b;
 
 // ---------------------------------------------------------------------------------------------------
-struct S2bIndex {
-  int device = 0;
-  FlatIndexView view{};
-  const FlatIndexView* view_dev = nullptr;   // the same view, stored at the end of the device blob
-  void* blob = nullptr;   // one allocation holding every array
-  size_t blob_bytes = 0;
-  uint64_t num_clips = 0, num_edges = 0;
-  int32_t* edge_ids = nullptr;   // optional (s2b_index_set_edge_ids): shape-local id of every clipped edge, for VisitIncidentEdges
-};
 
 namespace s2b {
 int set_error(int code, const char* fmt, ...);
@@ -690,6 +683,8 @@ int s2b_index_create(const S2bFlatIndex* f, S2bIndex** out) {
   ix->view.lut_level = hf.lut_level;
   ix->view.num_shape_ids = f->num_shape_ids;
   ix->num_clips = K; ix->num_edges = E;
+  for (const FlatEdge& ed : edges)
+    if (!region_edge_is_supported(edge_v0(ed), edge_v1(ed))) ++ix->unsupported_region_edges;
   if (cudaMemcpy(base + o_view, &ix->view, sizeof(FlatIndexView), cudaMemcpyHostToDevice) != cudaSuccess) {
     e = cudaGetLastError(); cudaFree(ix->blob); delete ix; return cuda_fail(e, "cudaMemcpy(view)");
   }

@@ -1,0 +1,17 @@
+// s2b_index_handle.h — the opaque S2bIndex of include/s2b_capi.h, shared by the translation units that query it.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include "s2b_contains.cuh"
+
+struct S2bIndex {
+  int device = 0;
+  s2b::FlatIndexView view{};
+  const s2b::FlatIndexView* view_dev = nullptr;   // the same view, stored at the end of the device blob
+  void* blob = nullptr;   // one allocation holding every array
+  size_t blob_bytes = 0;
+  uint64_t num_clips = 0, num_edges = 0;
+  int32_t* edge_ids = nullptr;   // optional (s2b_index_set_edge_ids): shape-local id of every clipped edge, for VisitIncidentEdges
+  uint64_t unsupported_region_edges = 0;   // edges whose RobustCrossProd needs the stages s2b_region.cuh does not restate
+};

@@ -1,0 +1,280 @@
+// s2b_region.cu — batched S2ShapeIndexRegion cell tests: the calls an S2RegionCoverer or a
+// cell-vs-polygon classification join makes on an index region, one target cell per thread.
+//   S2ShapeIndexRegion::MayIntersect(S2Cell)        s2shape_index_region.h:344-371
+//   S2ShapeIndexRegion::Contains(S2Cell)            s2shape_index_region.h:313-342
+//   S2ShapeIndexRegion::VisitIntersectingShapeIds   s2shape_index_region.h:373-424
+// Per-target arithmetic is in s2b_region.cuh. The visitor becomes a CSR of (shape id, contains_target) pairs: raw
+// (target, shape, not_contains) tuples are emitted, radix-sorted and reduced per (target, shape), which is what the
+// reference's hash map does for a target that spans several index cells.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+
+#include "../../include/s2b_capi.h"
+#include "s2b_hilbert.h"
+#include "s2b_index_handle.h"
+#include "s2b_internal.h"
+#include "s2b_region.cuh"
+
+using namespace s2b;
+
+namespace s2b {
+int set_error(int code, const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+}
+
+#ifndef S2B_EUNSUPPORTED
+#error "S2B_EUNSUPPORTED must be declared in s2b_capi.h"
+#endif
+
+namespace {
+
+constexpr int kThreads = 128;   // long per-thread edge loops with ~100 live registers: small CTAs spread them over the SMs
+__device__ const HilbertTables g_hilbert_rg = kHilbert;
+
+__device__ __forceinline__ void stage_ij(uint16_t* s_ij) {
+  for (int k = threadIdx.x; k < 1024; k += kThreads) s_ij[k] = g_hilbert_rg.ij[k];
+  __syncthreads();
+}
+
+// kMode 0: MayIntersect(S2Cell), 1: Contains(S2Cell).
+template <int kMode>
+__global__ void __launch_bounds__(kThreads)
+region_cells_kernel(const FlatIndexView ix, const uint64_t* __restrict__ targets, size_t n, uint8_t* __restrict__ out) {
+  __shared__ uint16_t s_ij[1024];
+  stage_ij(s_ij);
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < n; t += stride) {
+    const uint64_t target = __ldcs(targets + t);
+    out[t] = (kMode == 0 ? region_may_intersect(ix, target, s_ij) : region_contains_cell(ix, target, s_ij)) ? 1 : 0;
+  }
+}
+
+// Index cells [at, end) lie inside a SUBDIVIDED target: end = first cell past target.range_max().
+__device__ __forceinline__ uint32_t subdivided_end(const FlatIndexView& ix, uint64_t target, uint32_t at) {
+  const uint64_t tmax = cellid_range_max(target);
+  uint32_t lo = at, hi = ix.num_cells;
+  while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (ix.cell_ids[mid] <= tmax) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
+// Tuple key: target index (31 bits) | shape id (32 bits) | not_contains (1 bit). After sorting, the last tuple of every
+// (target, shape) run carries the OR of the run's not_contains bits.
+__device__ __forceinline__ uint64_t tuple_key(size_t t, int32_t shape, bool not_contains) {
+  return ((uint64_t)t << 33) | ((uint64_t)(uint32_t)shape << 1) | (not_contains ? 1u : 0u);
+}
+
+// kFill = false: raw tuple count per target; true: tuples written at raw_offsets[t].
+template <bool kFill>
+__global__ void __launch_bounds__(kThreads)
+region_shapes_kernel(const FlatIndexView ix, const uint64_t* __restrict__ targets, size_t n, uint64_t* __restrict__ counts,
+                     const uint64_t* __restrict__ raw_offsets, uint64_t* __restrict__ tuples) {
+  __shared__ uint16_t s_ij[1024];
+  stage_ij(s_ij);
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < n; t += stride) {
+    const uint64_t target = __ldcs(targets + t);
+    int32_t at;
+    const int rel = locate_target(ix, target, &at);
+    uint32_t cnt = 0;
+    uint64_t* dst = kFill ? tuples + raw_offsets[t] : nullptr;
+    if (rel == 1) {
+      const uint32_t end = subdivided_end(ix, target, (uint32_t)at);
+      const uint32_t k0 = ix.cells[at].clip_begin, k1 = ix.cells[end - 1].clip_begin + ix.cells[end - 1].clip_count;
+      cnt = k1 - k0;
+      if (kFill) {
+        for (uint32_t k = k0; k < k1; ++k) {
+          const FlatClip clip = ix.clips[k];
+          dst[k - k0] = tuple_key(t, clip.shape_id, clip.num_edges > 0 || !(clip.flags & 1u));
+        }
+      }
+    } else if (rel == 0) {
+      const FlatCell fc = ix.cells[at];
+      const bool same = ix.cell_ids[at] == target;
+      TargetCell tc{};
+      const P3 a{fc.cx, fc.cy, fc.cz};
+      P3 centre{0, 0, 0}, a_cross_b{0, 0, 0};
+      if (!same) {
+        tc = target_cell(target, s_ij);
+        centre = cellid_to_point(target, s_ij);
+        a_cross_b = cross(a, centre);
+      }
+      for (uint32_t k = 0; k < fc.clip_count; ++k) {
+        const FlatClip clip = ix.clips[fc.clip_begin + k];
+        const int r = region_clip_relation(ix, clip, same, tc, a, centre, a_cross_b);
+        if (r == 0) continue;
+        if (kFill) dst[cnt] = tuple_key(t, clip.shape_id, r != 2);
+        ++cnt;
+      }
+    }
+    if (!kFill) counts[t] = cnt;
+  }
+}
+
+__global__ void run_tail_flags_kernel(const uint64_t* __restrict__ keys, size_t m, uint8_t* __restrict__ flags) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) flags[i] = (i + 1 == m || (keys[i] >> 1) != (keys[i + 1] >> 1)) ? 1 : 0;
+}
+
+// offsets[t] = first compacted pair of target t (lower bound of t << 33); pairs unpacked in the same launch.
+__global__ void region_pairs_kernel(const uint64_t* __restrict__ keys, size_t m, size_t n, uint32_t* __restrict__ offsets,
+                                    int32_t* __restrict__ shape_ids, uint8_t* __restrict__ contains) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) {
+    const uint64_t k = keys[i];
+    shape_ids[i] = (int32_t)(uint32_t)(k >> 1);
+    contains[i] = (k & 1) ? 0 : 1;
+  }
+  if (i <= n) {
+    const uint64_t want = (uint64_t)i << 33;
+    size_t lo = 0, hi = m;
+    while (lo < hi) { const size_t mid = (lo + hi) >> 1; if (keys[mid] < want) lo = mid + 1; else hi = mid; }
+    offsets[i] = (uint32_t)lo;
+  }
+}
+
+int grid_for(size_t n, const void* kernel) {
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
+  if (per_sm < 1) per_sm = 1;
+  const size_t want = (n + kThreads - 1) / kThreads, cap = (size_t)sm_count() * per_sm;
+  return (int)(want < cap ? (want ? want : 1) : cap);
+}
+
+int check_region_index(const S2bIndex* ix) {
+  if (!ix) return set_error(S2B_EINVAL, "null index");
+  if (ix->unsupported_region_edges)
+    return set_error(S2B_EUNSUPPORTED, "%llu edge(s) of this index have endpoints closer than 9 * DBL_EPSILON (or antipodal): "
+                     "RobustCrossProd's extended-precision stages are not available on the device",
+                     (unsigned long long)ix->unsupported_region_edges);
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  if (dev != ix->device) return set_error(S2B_EINVAL, "the index lives on device %d but the current device is %d", ix->device, dev);
+  return S2B_OK;
+}
+
+template <int kMode>
+int region_cells_dev(const S2bIndex* ix, const uint64_t* ids_dev, size_t n, uint8_t* out_dev, void* stream) {
+  int rc = check_region_index(ix);
+  if (rc != S2B_OK) return rc;
+  if (n == 0) return S2B_OK;
+  if (!ids_dev || !out_dev) return set_error(S2B_EINVAL, "null pointer");
+  auto k = region_cells_kernel<kMode>;
+  k<<<grid_for(n, (const void*)k), kThreads, 0, (cudaStream_t)stream>>>(ix->view, ids_dev, n, out_dev);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? S2B_OK : cuda_fail(e, "region cells launch");
+}
+
+template <int kMode>
+int region_cells_host(const S2bIndex* ix, const uint64_t* ids, size_t n, uint8_t* out) {
+  int rc = check_region_index(ix);
+  if (rc != S2B_OK) return rc;
+  if (n == 0) return S2B_OK;
+  if (!ids || !out) return set_error(S2B_EINVAL, "null pointer");
+  void *d_ids = nullptr, *d_out = nullptr;
+  cudaError_t e = cudaMalloc(&d_ids, 8 * n);
+  if (e == cudaSuccess) e = cudaMalloc(&d_out, n);
+  if (e == cudaSuccess) e = cudaMemcpy(d_ids, ids, 8 * n, cudaMemcpyHostToDevice);
+  rc = e == cudaSuccess ? region_cells_dev<kMode>(ix, (const uint64_t*)d_ids, n, (uint8_t*)d_out, nullptr) : cuda_fail(e, "cudaMalloc/cudaMemcpy");
+  if (rc == S2B_OK && (e = cudaMemcpy(out, d_out, n, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy");
+  cudaFree(d_ids); cudaFree(d_out);
+  return rc;
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+  template <class T> T* as() const { return (T*)p; }
+};
+
+}  // namespace
+
+extern "C" {
+
+int s2b_region_may_intersect_cells_dev(const S2bIndex* ix, const uint64_t* cell_ids_dev, size_t n, uint8_t* out_dev, void* stream) {
+  return region_cells_dev<0>(ix, cell_ids_dev, n, out_dev, stream);
+}
+int s2b_region_may_intersect_cells(const S2bIndex* ix, const uint64_t* cell_ids, size_t n, uint8_t* out) {
+  return region_cells_host<0>(ix, cell_ids, n, out);
+}
+int s2b_region_contains_cells_dev(const S2bIndex* ix, const uint64_t* cell_ids_dev, size_t n, uint8_t* out_dev, void* stream) {
+  return region_cells_dev<1>(ix, cell_ids_dev, n, out_dev, stream);
+}
+int s2b_region_contains_cells(const S2bIndex* ix, const uint64_t* cell_ids, size_t n, uint8_t* out) {
+  return region_cells_host<1>(ix, cell_ids, n, out);
+}
+
+int s2b_region_intersecting_shapes(const S2bIndex* ix, const uint64_t* cell_ids, size_t n, uint32_t* offsets_out, int32_t* shape_ids_out,
+                                   uint8_t* contains_out, size_t capacity, size_t* total_out) {
+  int rc = check_region_index(ix);
+  if (rc != S2B_OK) return rc;
+  if (!offsets_out) return set_error(S2B_EINVAL, "null offsets_out");
+  if (total_out) *total_out = 0;
+  if (n == 0) { offsets_out[0] = 0; return S2B_OK; }
+  if (!cell_ids) return set_error(S2B_EINVAL, "null pointer");
+  if (n >= (size_t(1) << 31)) return set_error(S2B_EINVAL, "at most 2^31 - 1 targets per call");
+  DevBuf ids, counts, raw_off, temp, tuples, sorted, flags, compact, n_sel, off, shp, con;
+  cudaError_t e = ids.alloc(8 * n);
+  if (e == cudaSuccess) e = counts.alloc(8 * (n + 1));
+  if (e == cudaSuccess) e = raw_off.alloc(8 * (n + 1));
+  if (e == cudaSuccess) e = cudaMemcpy(ids.p, cell_ids, 8 * n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(counts.p, 0, 8 * (n + 1));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc/cudaMemcpy");
+  auto kc = region_shapes_kernel<false>;
+  auto kf = region_shapes_kernel<true>;
+  kc<<<grid_for(n, (const void*)kc), kThreads>>>(ix->view, ids.as<uint64_t>(), n, counts.as<uint64_t>(), nullptr, nullptr);
+  count_launch();
+  size_t temp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, counts.as<uint64_t>(), raw_off.as<uint64_t>(), n + 1);
+  if ((e = temp.alloc(temp_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+  cub::DeviceScan::ExclusiveSum(temp.p, temp_bytes, counts.as<uint64_t>(), raw_off.as<uint64_t>(), n + 1);
+  count_launch();
+  uint64_t raw_total = 0;
+  if ((e = cudaMemcpy(&raw_total, raw_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "region shapes count");
+  if (raw_total >= (uint64_t(1) << 31)) return set_error(S2B_ECAPACITY, "%llu raw (target, shape) tuples: split the batch", (unsigned long long)raw_total);
+  const size_t m = (size_t)raw_total;
+  size_t total = 0;
+  if (m > 0) {
+    e = tuples.alloc(8 * m);
+    if (e == cudaSuccess) e = sorted.alloc(8 * m);
+    if (e == cudaSuccess) e = flags.alloc(m);
+    if (e == cudaSuccess) e = compact.alloc(8 * m);
+    if (e == cudaSuccess) e = n_sel.alloc(8);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    kf<<<grid_for(n, (const void*)kf), kThreads>>>(ix->view, ids.as<uint64_t>(), n, nullptr, raw_off.as<uint64_t>(), tuples.as<uint64_t>());
+    count_launch();
+    DevBuf temp2;
+    size_t sort_bytes = 0, sel_bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, tuples.as<uint64_t>(), sorted.as<uint64_t>(), m);
+    cub::DeviceSelect::Flagged(nullptr, sel_bytes, sorted.as<uint64_t>(), flags.as<uint8_t>(), compact.as<uint64_t>(), n_sel.as<uint64_t>(), m);
+    if ((e = temp2.alloc(sort_bytes > sel_bytes ? sort_bytes : sel_bytes)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    cub::DeviceRadixSort::SortKeys(temp2.p, sort_bytes, tuples.as<uint64_t>(), sorted.as<uint64_t>(), m);
+    run_tail_flags_kernel<<<(unsigned)((m + 255) / 256), 256>>>(sorted.as<uint64_t>(), m, flags.as<uint8_t>());
+    cub::DeviceSelect::Flagged(temp2.p, sel_bytes, sorted.as<uint64_t>(), flags.as<uint8_t>(), compact.as<uint64_t>(), n_sel.as<uint64_t>(), m);
+    count_launch(); count_launch(); count_launch();
+    uint64_t sel = 0;
+    if ((e = cudaMemcpy(&sel, n_sel.p, 8, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "region shapes reduce");
+    total = (size_t)sel;
+  }
+  if (total_out) *total_out = total;
+  e = off.alloc(4 * (n + 1));
+  if (e == cudaSuccess) e = shp.alloc(4 * total);
+  if (e == cudaSuccess) e = con.alloc(total);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+  const size_t work = (total > n + 1 ? total : n + 1);
+  region_pairs_kernel<<<(unsigned)((work + 255) / 256), 256>>>(compact.as<uint64_t>(), total, n, off.as<uint32_t>(), shp.as<int32_t>(), con.as<uint8_t>());
+  count_launch();
+  if ((e = cudaMemcpy(offsets_out, off.p, 4 * (n + 1), cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "region shapes offsets");
+  if (total > capacity) return set_error(S2B_ECAPACITY, "%zu (cell, shape) pairs but capacity is %zu", total, capacity);
+  if (total > 0) {
+    if (!shape_ids_out || !contains_out) return set_error(S2B_EINVAL, "null output arrays");
+    if ((e = cudaMemcpy(shape_ids_out, shp.p, 4 * total, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
+    if ((e = cudaMemcpy(contains_out, con.p, total, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
+  }
+  return S2B_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,272 @@
+// s2b_region.cuh — S2ShapeIndexRegion's cell tests over the flattened index (host-compilable for tests/hostsim).
+// Restates, per target cell:
+//   S2ShapeIndexRegion::Contains(S2Cell)      s2shape_index_region.h:313-342
+//   S2ShapeIndexRegion::MayIntersect(S2Cell)  s2shape_index_region.h:344-371
+//   S2ShapeIndexRegion::AnyEdgeIntersects     s2shape_index_region.h:447-465
+//   S2::ClipToPaddedFace / IntersectsRect     s2edge_clipping.cc:64-144,271-384
+//   S2::RobustCrossProd (double stage)        s2edge_crossings.cc:97-177
+//   S2Cell(S2CellId) bound / centre           s2cell.cc:64-71, s2cell_id.cc:395-405, s2cell.h:217
+//   S2CellIterator::LocateImpl(S2CellId)      s2cell_iterator.h:159-189
+// These are the calls an S2RegionCoverer makes on an index region, batched: one target cell per thread.
+//
+// RobustCrossProd: the double-precision stage decides unless the endpoints are closer than ~9 * DBL_EPSILON (or
+// antipodal). a == b returns Ortho(a) like the reference. The reference's two further stages (x87 long double, then
+// exact arithmetic with symbolic perturbation) are not restated: `region_edge_is_supported` identifies such edges when
+// the index is created, and the region queries refuse an index that holds one (S2B_EUNSUPPORTED) instead of guessing.
+#pragma once
+#include <float.h>
+
+#include "s2b_contains.cuh"
+
+namespace s2b {
+
+struct Uv { double u, v; };
+struct UvRect { double ulo, uhi, vlo, vhi; };
+
+// kFaceClipErrorUVCoord + kIntersectsRectErrorUVDist (s2edge_clipping.h:101,113; summed at s2shape_index_region.h:450).
+S2B_HD double region_max_error() { return 9 * 0.70710678118654752440 * DBL_EPSILON + 3 * 1.41421356237309504880 * DBL_EPSILON; }
+
+S2B_HD P3 add(const P3& a, const P3& b) { return P3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+
+// S2::FaceXYZtoUVW (s2coords.cc:27-40).
+S2B_HD P3 face_xyz_to_uvw(int face, const P3& p) {
+  switch (face) {
+    case 0: return P3{p.y, p.z, p.x};
+    case 1: return P3{-p.x, p.z, p.y};
+    case 2: return P3{-p.x, -p.y, p.z};
+    case 3: return P3{-p.z, -p.y, -p.x};
+    case 4: return P3{-p.z, p.x, -p.y};
+    default: return P3{p.y, p.x, -p.z};
+  }
+}
+
+// S2::GetFace (s2coords.h:409-413).
+S2B_HD int get_face(const P3& p) {
+  const int k = largest_abs_component(p);
+  return comp(p, k) < 0 ? k + 3 : k;
+}
+
+// S2::ValidFaceXYZtoUV (s2coords.h:389-403) = (u, v) of FaceXYZtoUVW divided by w.
+S2B_HD Uv valid_face_xyz_to_uv(int face, const P3& p) {
+  const P3 q = face_xyz_to_uvw(face, p);
+  // The reference divides by the signed major axis: faces 0-2 by +p[axis] (= w), faces 3-5 by p[axis] = -w with
+  // the numerators' signs folded in. x / w == (-x) / (-w) exactly in IEEE arithmetic, so one form serves all six.
+  return Uv{q.x / q.z, q.y / q.z};
+}
+
+// GetStableCrossProd<double> (s2edge_crossings.cc:97-136): (a - b) x (a + b), accepted when long enough.
+S2B_HD bool stable_cross_prod(const P3& a, const P3& b, P3* out) {
+  const double kSqrt3 = 1.7320508075688772935;
+  const double kErr = DBL_EPSILON / 2;   // rounding_epsilon<double>() = DBL_ERR
+  const double kMinNorm = (32 * kSqrt3 * kErr) / ((6 * kErr) / kErr - (1 + 2 * kSqrt3));
+  *out = cross(sub(a, b), add(a, b));
+  return norm2(*out) >= kMinNorm * kMinNorm;
+}
+
+// True when RobustCrossProd(a, b) is decided by the stages restated here (stable double product, or a == b).
+S2B_HD bool region_edge_is_supported(const P3& a, const P3& b) {
+  P3 n;
+  return stable_cross_prod(a, b, &n) || eq(a, b);
+}
+
+S2B_HD P3 robust_cross_prod(const P3& a, const P3& b) {
+  P3 n;
+  if (stable_cross_prod(a, b, &n)) return n;
+  return ortho(a);   // a == b (s2edge_crossings.cc:164-166); other inputs are excluded when the index is created
+}
+
+// IntersectsFace / IntersectsOppositeEdges / GetExitAxis / GetExitPoint (s2edge_clipping.cc:71-136); n is the line's
+// normal in the face's (u, v, w) frame.
+S2B_HD bool clip_intersects_face(const P3& n) {
+  const double u = fabs(n.x), v = fabs(n.y), w = fabs(n.z);
+  return (v >= w - u) && (u >= w - v);
+}
+S2B_HD bool clip_intersects_opposite_edges(const P3& n) {
+  const double u = fabs(n.x), v = fabs(n.y), w = fabs(n.z);
+  if (fabs(u - v) != w) return fabs(u - v) >= w;
+  return (u >= v) ? (u - w >= v) : (v - w >= u);
+}
+S2B_HD int clip_exit_axis(const P3& n) {
+  if (clip_intersects_opposite_edges(n)) return (fabs(n.x) >= fabs(n.y)) ? 1 : 0;
+  const int negatives = (signbit(n.x) ? 1 : 0) ^ (signbit(n.y) ? 1 : 0) ^ (signbit(n.z) ? 1 : 0);
+  return negatives == 0 ? 1 : 0;
+}
+S2B_HD Uv clip_exit_point(const P3& n, int axis) {
+  if (axis == 0) {
+    const double u = (n.y > 0) ? 1.0 : -1.0;
+    return Uv{u, (-u * n.x - n.z) / n.y};
+  }
+  const double v = (n.x < 0) ? 1.0 : -1.0;
+  return Uv{(-v * n.y - n.z) / n.x, v};
+}
+
+// ClipDestination (s2edge_clipping.cc:271-321): clips endpoint B of AB to the padded face; returns the score.
+S2B_HD int clip_destination(const P3& a, const P3& b, const P3& scaled_n, const P3& a_tangent, const P3& b_tangent,
+                            double scale_uv, Uv* uv) {
+  const double kMaxSafeUVCoord = 1 - 9 * 0.70710678118654752440 * DBL_EPSILON;
+  if (b.z > 0) {
+    *uv = Uv{b.x / b.z, b.y / b.z};
+    const double mu = fabs(uv->u), mv = fabs(uv->v);
+    if ((mu > mv ? mu : mv) <= kMaxSafeUVCoord) return 0;
+  }
+  const Uv e = clip_exit_point(scaled_n, clip_exit_axis(scaled_n));
+  *uv = Uv{scale_uv * e.u, scale_uv * e.v};
+  const P3 p{uv->u, uv->v, 1.0};
+  int score = 0;
+  if (dot(sub(p, a), a_tangent) < 0) score = 2;
+  else if (dot(sub(p, b), b_tangent) < 0) score = 1;
+  if (score > 0) {
+    if (b.z <= 0) score = 3;
+    else *uv = Uv{b.x / b.z, b.y / b.z};
+  }
+  return score;
+}
+
+// S2::ClipToPaddedFace (s2edge_clipping.cc:323-362).
+S2B_HD bool clip_to_padded_face(const P3& a_xyz, const P3& b_xyz, int face, double padding, Uv* a_uv, Uv* b_uv) {
+  if (get_face(a_xyz) == face && get_face(b_xyz) == face) {
+    *a_uv = valid_face_xyz_to_uv(face, a_xyz);
+    *b_uv = valid_face_xyz_to_uv(face, b_xyz);
+    return true;
+  }
+  P3 n = face_xyz_to_uvw(face, robust_cross_prod(a_xyz, b_xyz));
+  const P3 a = face_xyz_to_uvw(face, a_xyz);
+  const P3 b = face_xyz_to_uvw(face, b_xyz);
+  const double scale_uv = 1 + padding;
+  const P3 scaled_n{scale_uv * n.x, scale_uv * n.y, n.z};
+  if (!clip_intersects_face(scaled_n)) return false;
+  n = normalize(n);
+  const P3 a_tangent = cross(n, a);
+  const P3 b_tangent = cross(b, n);
+  const int a_score = clip_destination(b, a, neg(scaled_n), b_tangent, a_tangent, scale_uv, a_uv);
+  const int b_score = clip_destination(a, b, scaled_n, a_tangent, b_tangent, scale_uv, b_uv);
+  return a_score + b_score < 3;
+}
+
+// R1Interval::Intersects (r1interval.h:128-134).
+S2B_HD bool interval_intersects(double lo, double hi, double ylo, double yhi) {
+  if (lo <= ylo) return ylo <= hi && ylo <= yhi;
+  return lo <= yhi && lo <= hi;
+}
+
+// S2::IntersectsRect (s2edge_clipping.cc:364-384).
+S2B_HD bool intersects_rect(const Uv& a, const Uv& b, const UvRect& r) {
+  const double xlo = a.u <= b.u ? a.u : b.u, xhi = a.u <= b.u ? b.u : a.u;
+  const double ylo = a.v <= b.v ? a.v : b.v, yhi = a.v <= b.v ? b.v : a.v;
+  if (!(interval_intersects(r.ulo, r.uhi, xlo, xhi) && interval_intersects(r.vlo, r.vhi, ylo, yhi))) return false;
+  const double nx = -(b.v - a.v), ny = b.u - a.u;   // (b - a).Ortho()
+  const bool i = nx >= 0, j = ny >= 0;
+  const double mx = (i ? r.uhi : r.ulo) - a.u, my = (j ? r.vhi : r.vlo) - a.v;
+  const double lx = (i ? r.ulo : r.uhi) - a.u, ly = (j ? r.vlo : r.vhi) - a.v;
+  const double mx_dot = (0.0 + nx * mx) + ny * my;
+  const double mn_dot = (0.0 + nx * lx) + ny * ly;
+  return (mx_dot >= 0) && (mn_dot <= 0);
+}
+
+// What S2Cell(S2CellId) precomputes and the region tests read: face, (u, v) bound, centre.
+struct TargetCell { uint64_t id; int face; UvRect bound; };
+
+template <class TableT>
+S2B_HD TargetCell target_cell(uint64_t id, const TableT* ij_table) {
+  TargetCell t;
+  t.id = id;
+  int i, j;
+  t.face = cellid_to_face_ij(id, ij_table, &i, &j);
+  const int size = 1 << (30 - cellid_level(id));                 // GetSizeIJ(level)
+  const int ilo = i & -size, jlo = j & -size;
+  const double k = 1.0 / 1073741824.0;                           // IJtoSTMin (s2coords.h:340-343)
+  t.bound = UvRect{st_to_uv(k * ilo), st_to_uv(k * (ilo + size)), st_to_uv(k * jlo), st_to_uv(k * (jlo + size))};
+  return t;
+}
+
+// S2ShapeIndexRegion::AnyEdgeIntersects over one clipped shape's edges.
+S2B_HD bool any_edge_intersects(const FlatIndexView& ix, const FlatClip& clip, const TargetCell& t) {
+  const double max_error = region_max_error();
+  const UvRect padded{t.bound.ulo - max_error, t.bound.uhi + max_error, t.bound.vlo - max_error, t.bound.vhi + max_error};
+  const FlatEdge* edges = ix.edges + clip.edge_begin;
+  for (uint32_t e = 0; e < clip.num_edges; ++e) {
+    const FlatEdge ed = edges[e];
+    Uv p0, p1;
+    if (clip_to_padded_face(edge_v0(ed), edge_v1(ed), t.face, max_error, &p0, &p1) && intersects_rect(p0, p1, padded)) return true;
+  }
+  return false;
+}
+
+// Iterator::Locate(S2CellId) (s2cell_iterator.h:159-189). Returns 0 INDEXED (target inside index cell *at),
+// 1 SUBDIVIDED (*at = first index cell inside the target), 2 DISJOINT.
+S2B_HD int locate_target(const FlatIndexView& ix, uint64_t target, int32_t* at) {
+  const uint32_t C = ix.num_cells;
+  const uint64_t tmin = cellid_range_min(target), tmax = cellid_range_max(target);
+  uint32_t lo = 0, hi = C;
+  while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (ix.cell_ids[mid] < tmin) lo = mid + 1; else hi = mid; }
+  if (lo < C) {
+    const uint64_t id = ix.cell_ids[lo];
+    if (id >= target && cellid_range_min(id) <= target) { *at = (int32_t)lo; return 0; }
+    if (id <= tmax) { *at = (int32_t)lo; return 1; }
+  }
+  if (lo > 0 && cellid_range_max(ix.cell_ids[lo - 1]) >= target) { *at = (int32_t)lo - 1; return 0; }
+  *at = -1;
+  return 2;
+}
+
+// ShapeContains(iter.id(), clipped, target.GetCenter()) with the SEMI_OPEN model of S2ShapeIndexRegion's query.
+S2B_HD bool clip_contains_centre(const FlatIndexView& ix, const FlatClip& clip, const P3& cell_centre, const P3& centre,
+                                 const P3& cross_ab) {
+  return clip_contains(ix, clip, cell_centre, centre, cross_ab, kSemiOpen);
+}
+
+template <class TableT>
+S2B_HD bool region_may_intersect(const FlatIndexView& ix, uint64_t target, const TableT* ij_table) {
+  int32_t at;
+  const int rel = locate_target(ix, target, &at);
+  if (rel == 2) return false;
+  if (rel == 1) return true;
+  if (ix.cell_ids[at] == target) return true;
+  const FlatCell fc = ix.cells[at];
+  const TargetCell t = target_cell(target, ij_table);
+  const P3 a{fc.cx, fc.cy, fc.cz};
+  const P3 centre = cellid_to_point(target, ij_table);
+  const P3 a_cross_b = cross(a, centre);
+  for (uint32_t k = 0; k < fc.clip_count; ++k) {
+    const FlatClip clip = ix.clips[fc.clip_begin + k];
+    if (any_edge_intersects(ix, clip, t)) return true;
+    if (clip_contains_centre(ix, clip, a, centre, a_cross_b)) return true;
+  }
+  return false;
+}
+
+template <class TableT>
+S2B_HD bool region_contains_cell(const FlatIndexView& ix, uint64_t target, const TableT* ij_table) {
+  int32_t at;
+  if (locate_target(ix, target, &at) != 0) return false;
+  const FlatCell fc = ix.cells[at];
+  const bool same = ix.cell_ids[at] == target;
+  TargetCell t{};
+  P3 a{fc.cx, fc.cy, fc.cz}, centre{0, 0, 0}, a_cross_b{0, 0, 0};
+  if (!same) {
+    t = target_cell(target, ij_table);
+    centre = cellid_to_point(target, ij_table);
+    a_cross_b = cross(a, centre);
+  }
+  for (uint32_t k = 0; k < fc.clip_count; ++k) {
+    const FlatClip clip = ix.clips[fc.clip_begin + k];
+    if (same) {
+      if (clip.num_edges == 0 && (clip.flags & 1u)) return true;
+    } else if (((clip.flags >> 1) & 3u) == 2 && !any_edge_intersects(ix, clip, t) &&
+               clip_contains_centre(ix, clip, a, centre, a_cross_b)) {
+      return true;
+    }
+  }
+  return false;
+}
+
+// One entry of VisitIntersectingShapeIds (s2shape_index_region.h:373-424) for the INDEXED case: 0 = the clipped shape
+// is disjoint from the target, 1 = intersects, 2 = contains the target.
+S2B_HD int region_clip_relation(const FlatIndexView& ix, const FlatClip& clip, bool same, const TargetCell& t, const P3& a,
+                                const P3& centre, const P3& a_cross_b) {
+  if (same) return (clip.num_edges == 0 && (clip.flags & 1u)) ? 2 : 1;
+  if (any_edge_intersects(ix, clip, t)) return 1;
+  return clip_contains_centre(ix, clip, a, centre, a_cross_b) ? 2 : 0;
+}
+
+}  // namespace s2b

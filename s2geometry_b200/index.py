@@ -243,6 +243,56 @@ class ShapeIndex:
         return dict(num_cells=c.value, num_clips=k.value, num_edges=e.value, num_shape_ids=s.value, device_bytes=b.value)
 
 
+class ShapeIndexRegion:
+    """S2ShapeIndexRegion (s2shape_index_region.h) over a device-resident index, for batches of target cells: the
+    S2Region interface an S2RegionCoverer drives, and VisitIntersectingShapeIds. numpy arrays go through the host-pointer
+    C ABI, CUDA tensors through the `_dev` one."""
+
+    def __init__(self, index):
+        self.index = index
+        self._lib = index._lib
+
+    def _cells(self, cell_ids, host_fn, dev_fn):
+        h = self.index._h
+        if _is_tensor(cell_ids):
+            ids = cell_ids.contiguous()
+            out = torch.empty(ids.numel(), dtype=torch.uint8, device=ids.device)
+            with torch.cuda.device(ids.device):
+                _lib.check(dev_fn(h, _ptr(ids), ids.numel(), _ptr(out), _stream()))
+            return out
+        ids = np.ascontiguousarray(cell_ids, np.uint64)
+        out = np.empty(ids.size, np.uint8)
+        _lib.check(host_fn(h, _ptr(ids), ids.size, _ptr(out)))
+        return out
+
+    def may_intersect(self, cell_ids):
+        """S2ShapeIndexRegion::MayIntersect(S2Cell(id)) per id (s2shape_index_region.h:344-371)."""
+        return self._cells(cell_ids, self._lib.s2b_region_may_intersect_cells, self._lib.s2b_region_may_intersect_cells_dev)
+
+    def contains_cells(self, cell_ids):
+        """S2ShapeIndexRegion::Contains(S2Cell(id)) per id (s2shape_index_region.h:313-342)."""
+        return self._cells(cell_ids, self._lib.s2b_region_contains_cells, self._lib.s2b_region_contains_cells_dev)
+
+    def contains(self, xyz):
+        """S2ShapeIndexRegion::Contains(S2Point) = S2ContainsPointQuery(SEMI_OPEN)::Contains (:437-445)."""
+        return ContainsPointQuery(self.index, 1).contains(xyz)
+
+    def intersecting_shapes(self, cell_ids):
+        """VisitIntersectingShapeIds per target cell (:373-424) as (offsets uint32[n+1], shape_ids int32, contains uint8),
+        pairs ascending by shape id within a target."""
+        ids = np.ascontiguousarray(cell_ids, np.uint64)
+        off = np.zeros(ids.size + 1, np.uint32)
+        total = ctypes.c_size_t(0)
+        rc = self._lib.s2b_region_intersecting_shapes(self.index._h, _ptr(ids), ids.size, _ptr(off), None, None, 0, ctypes.byref(total))
+        if rc != _lib.S2B_ECAPACITY:
+            _lib.check(rc)
+            return off, np.zeros(0, np.int32), np.zeros(0, np.uint8)
+        shp = np.empty(total.value, np.int32); con = np.empty(total.value, np.uint8)
+        _lib.check(self._lib.s2b_region_intersecting_shapes(self.index._h, _ptr(ids), ids.size, _ptr(off), _ptr(shp), _ptr(con),
+                                                           total.value, ctypes.byref(total)))
+        return off, shp, con
+
+
 class CellUnionIndex(ShapeIndex):
     """An S2CellUnion resident on the device as an index of interior cells: ContainsPointQuery(CellUnionIndex(ids)).contains(p)
     is S2CellUnion::Contains(S2Point) per point, on the fast Locate path."""

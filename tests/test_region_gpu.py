@@ -1,0 +1,63 @@
+"""GPU parity tests for the batched S2ShapeIndexRegion cell tests (s2b_region.cu) through the C ABI against the
+reference's own S2ShapeIndexRegion (oracle/_ref): MayIntersect(S2Cell), Contains(S2Cell), VisitIntersectingShapeIds."""
+import numpy as np
+import pytest
+import torch
+
+from tests import region_scenes, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def test_region_cell_tests_vs_reference(ref):
+    from s2geometry_b200 import _lib
+    from s2geometry_b200.index import FlatIndex, ShapeIndex, ShapeIndexRegion
+    for name, soup in region_scenes.region_scene_list():
+        ri = ref.index_create(soup)
+        flat = FlatIndex(**ri.flatten())
+        region = ShapeIndexRegion(ShapeIndex(flat))
+        targets = region_scenes.region_targets(ref, flat.cell_ids, soup.vertices, 5)
+        before = _lib.launch_count()
+        want_may, want_con = ri.region_cells(targets, 0), ri.region_cells(targets, 1)
+        assert (region.may_intersect(targets) == want_may).all(), name
+        assert (region.contains_cells(targets) == want_con).all(), name
+        t = torch.from_numpy(targets.view(np.int64)).cuda()
+        assert (region.may_intersect(t).cpu().numpy() == want_may).all(), name
+        assert (region.contains_cells(t).cpu().numpy() == want_con).all(), name
+        off, shp, con = region.intersecting_shapes(targets)
+        woff, wshp, wcon = ri.region_intersecting_shapes(targets)
+        assert (off == woff).all() and (shp == wshp).all() and (con == wcon).all(), name
+        assert _lib.launch_count() >= before + 8
+        # empty batch and a batch of one DISJOINT / one face cell
+        assert len(region.may_intersect(np.zeros(0, np.uint64))) == 0
+        off0, shp0, con0 = region.intersecting_shapes(np.zeros(0, np.uint64))
+        assert list(off0) == [0] and len(shp0) == 0
+
+
+def test_region_over_the_device_granularity_index(ref):
+    """A finer index (max_edges_per_cell = 1) changes which targets are SUBDIVIDED, exactly as it does for the reference
+    built with the same option: the answers are compared against the reference index of that granularity."""
+    from s2geometry_b200.index import FlatIndex, ShapeIndex, ShapeIndexRegion
+    soup, _ = scenes.loop_scene(3000)
+    ri = ref.index_create(soup, 1)
+    flat = FlatIndex(**ri.flatten())
+    region = ShapeIndexRegion(ShapeIndex(flat))
+    targets = region_scenes.region_targets(ref, flat.cell_ids, soup.vertices, 6)
+    assert (region.may_intersect(targets) == ri.region_cells(targets, 0)).all()
+    assert (region.contains_cells(targets) == ri.region_cells(targets, 1)).all()
+
+
+def test_unsupported_edge_is_refused_loudly():
+    """An edge whose endpoints are ~1 ulp apart needs RobustCrossProd's extended-precision stages: the region queries
+    refuse the index (S2B_EUNSUPPORTED) instead of answering approximately; point queries are unaffected."""
+    from s2geometry_b200 import _lib
+    from s2geometry_b200.index import ContainsPointQuery, ShapeIndex, ShapeIndexRegion, build_flat_index
+    from s2geometry_b200.shapes import ShapeSoup
+    a = scenes._norm(np.array([[1.0, 1e-3, 0.0], [1.0, 1e-3, 0.0], [1.0, 0.2, 0.1], [1.0, 0.0, 0.3]]))
+    a[1, 1] += 2e-16
+    soup = ShapeSoup(); soup.add_polygon([a]); soup = soup.freeze()
+    index = ShapeIndex(build_flat_index(soup, 0))
+    with pytest.raises(_lib.S2BError) as e:
+        ShapeIndexRegion(index).may_intersect(np.array([0x1000000000000000], np.uint64))
+    assert e.value.code == _lib.S2B_EUNSUPPORTED
+    assert ContainsPointQuery(index, 1).contains(a).shape == (4,)
