@@ -146,6 +146,44 @@ class S2ContainsPointQueryBatch {
   int model_;
 };
 
+// ---- S2ShapeIndexRegion, batch form (s2shape_index_region.h) --------------------------------------------------------
+// The S2Region interface of an indexed set of shapes, asked about many cells at once (what an S2RegionCoverer does one
+// cell at a time): MayIntersect(S2Cell), Contains(S2Cell), VisitIntersectingShapeIds. Cells are passed as S2CellIds.
+class S2ShapeIndexRegionBatch {
+ public:
+  explicit S2ShapeIndexRegionBatch(const DeviceShapeIndex* index) : index_(index) {}
+  // out[i] = MayIntersect(S2Cell(cell_ids[i]))
+  bool MayIntersect(const uint64_t* cell_ids, size_t n, uint8_t* out) const {
+    return s2b_region_may_intersect_cells(index_->handle(), cell_ids, n, out) == S2B_OK;
+  }
+  // out[i] = Contains(S2Cell(cell_ids[i]))
+  bool Contains(const uint64_t* cell_ids, size_t n, uint8_t* out) const {
+    return s2b_region_contains_cells(index_->handle(), cell_ids, n, out) == S2B_OK;
+  }
+  // out[i] = Contains(points[i])  (SEMI_OPEN, dimension-2 shapes; s2shape_index_region.h:437-445)
+  bool Contains(const Point* points, size_t n, uint8_t* out) const {
+    return s2b_contains(index_->handle(), &points->x, n, S2B_VERTEX_MODEL_SEMI_OPEN, out) == S2B_OK;
+  }
+  // VisitIntersectingShapeIds for every cell, CSR: pairs of cell i are [offsets[i], offsets[i+1]) of (shape_ids, contains),
+  // ascending by shape id; contains[k] = 1 when the shape contains the whole cell.
+  bool GetIntersectingShapeIds(const uint64_t* cell_ids, size_t n, std::vector<uint32_t>* offsets, std::vector<int32_t>* shape_ids,
+                               std::vector<uint8_t>* contains) const {
+    offsets->resize(n + 1);
+    size_t total = 0;
+    int rc = s2b_region_intersecting_shapes(index_->handle(), cell_ids, n, offsets->data(), nullptr, nullptr, 0, &total);
+    if (rc == S2B_ECAPACITY) {
+      shape_ids->resize(total); contains->resize(total);
+      rc = s2b_region_intersecting_shapes(index_->handle(), cell_ids, n, offsets->data(), shape_ids->data(), contains->data(), total, &total);
+    } else {
+      shape_ids->clear(); contains->clear();
+    }
+    return rc == S2B_OK;
+  }
+
+ private:
+  const DeviceShapeIndex* index_;
+};
+
 // ---- S2CellUnion::Contains(S2Point), batch form ------------------------------------------------------------------
 // cell_ids = S2CellUnion::cell_ids() (sorted, non-overlapping).
 inline bool S2CellUnionContainsBatch(const uint64_t* cell_ids, size_t num_cells, const Point* points, size_t n, uint8_t* out) {

@@ -58,6 +58,23 @@ int main() {
   std::vector<int32_t> shape_ids;
   CHECK(closed.GetContainingShapeIds(q.data(), q.size(), &offsets, &shape_ids));
   CHECK(offsets.size() == 10 && offsets[9] == 7 && shape_ids.size() == 7 && shape_ids[0] == 0);
+  {
+    // S2ShapeIndexRegion over the same index: the six face cells cover the sphere, so some of them must intersect; a leaf cell
+    // far below an index cell is contained by a polygon exactly when MayIntersect and the point query agree.
+    s2b::S2ShapeIndexRegionBatch region(&index);
+    std::vector<uint64_t> faces;
+    for (uint64_t f = 0; f < 6; ++f) faces.push_back((f << 61) | (1ull << 60));
+    std::vector<uint8_t> may(6), con(6);
+    CHECK(region.MayIntersect(faces.data(), faces.size(), may.data()));
+    CHECK(region.Contains(faces.data(), faces.size(), con.data()));
+    int any = 0;
+    for (int f = 0; f < 6; ++f) { any += may[f]; CHECK(!con[f] || may[f]); }
+    CHECK(any > 0);
+    std::vector<uint32_t> roff; std::vector<int32_t> rshape; std::vector<uint8_t> rcon;
+    CHECK(region.GetIntersectingShapeIds(faces.data(), faces.size(), &roff, &rshape, &rcon));
+    CHECK(roff.size() == 7 && roff[6] == rshape.size() && rshape.size() == rcon.size() && !rshape.empty());
+    for (int f = 0; f < 6; ++f) CHECK((roff[f + 1] > roff[f]) == (may[f] != 0));
+  }
 
   // serialized round trip: geometry + index to the reference's wire formats, read back, same answers
   {
