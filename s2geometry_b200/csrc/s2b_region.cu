@@ -37,16 +37,82 @@ __device__ __forceinline__ void stage_ij(uint16_t* s_ij) {
   __syncthreads();
 }
 
-// kMode 0: MayIntersect(S2Cell), 1: Contains(S2Cell).
+// kMode 0: MayIntersect(S2Cell), 1: Contains(S2Cell). Two launches per batch, like K3's Locate / process split:
+// `region_classify_kernel` answers every target that needs no edge test — DISJOINT, SUBDIVIDED, a target that IS an index
+// cell, and a target inside a pure interior cell (no edges, every clipped shape contains the centre: AnyEdgeIntersects is
+// false and ShapeContains returns contains_center) — and appends the others to a work list; `region_process_kernel` runs
+// the edge tests with one work item per thread, so warps are not left with a quarter of their lanes in the edge loops.
+// Work item: target position (32 bits) | index cell (32 bits).
+template <int kMode>
+__global__ void __launch_bounds__(256)
+region_classify_kernel(const FlatIndexView ix, const uint64_t* __restrict__ targets, uint32_t n, uint8_t* __restrict__ out,
+                       uint64_t* __restrict__ work, unsigned int* __restrict__ work_count) {
+  const uint32_t stride = gridDim.x * 256u;
+  const unsigned lane = threadIdx.x & 31u;
+  for (uint64_t base = (uint64_t)blockIdx.x * 256u + (threadIdx.x & ~31u); base < n; base += stride) {
+    const uint64_t t = base + lane;
+    bool hard = false;
+    int32_t at = -1;
+    if (t < n) {
+      const uint64_t target = __ldcs(targets + t);
+      const int rel = locate_target(ix, target, &at);
+      uint8_t r = 0;
+      if (rel == 1) r = kMode == 0;
+      else if (rel == 0) {
+        const bool same = ix.cell_ids[at] == target;
+        if (same && kMode == 0) r = 1;
+        else if (ix.interior_info[at] != 0) r = 1;      // pure interior cell: contained and intersecting, same or not
+        else if (same) r = 0;                            // Contains(S2Cell): an index cell with edges (or a clip missing the centre) ...
+        else hard = true;
+        if (same && kMode == 1 && ix.interior_info[at] == 0) {
+          // ... unless one of its clips has no edges and contains the centre (s2shape_index_region.h:330-331)
+          const FlatCell fc = ix.cells[at];
+          for (uint32_t k = 0; k < fc.clip_count; ++k) {
+            const FlatClip clip = ix.clips[fc.clip_begin + k];
+            if (clip.num_edges == 0 && (clip.flags & 1u)) r = 1;
+          }
+        }
+      }
+      if (!hard) out[t] = r;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, hard);
+    if (m) {
+      unsigned first = 0;
+      if (lane == 0) first = atomicAdd(work_count, (unsigned)__popc(m));
+      first = __shfl_sync(0xffffffffu, first, 0);
+      if (hard) work[first + __popc(m & ((1u << lane) - 1))] = (t << 32) | (uint32_t)at;
+    }
+  }
+}
+
 template <int kMode>
 __global__ void __launch_bounds__(kThreads)
-region_cells_kernel(const FlatIndexView ix, const uint64_t* __restrict__ targets, size_t n, uint8_t* __restrict__ out) {
+region_process_kernel(const FlatIndexView ix, const uint64_t* __restrict__ targets, const uint64_t* __restrict__ work,
+                      const unsigned int* __restrict__ work_count, uint8_t* __restrict__ out) {
   __shared__ uint16_t s_ij[1024];
   stage_ij(s_ij);
-  const size_t stride = (size_t)gridDim.x * kThreads;
-  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < n; t += stride) {
-    const uint64_t target = __ldcs(targets + t);
-    out[t] = (kMode == 0 ? region_may_intersect(ix, target, s_ij) : region_contains_cell(ix, target, s_ij)) ? 1 : 0;
+  const unsigned count = *work_count;
+  const unsigned stride = gridDim.x * kThreads;
+  for (unsigned w = blockIdx.x * kThreads + threadIdx.x; w < count; w += stride) {
+    const uint64_t item = work[w];
+    const uint64_t t = item >> 32;
+    const uint32_t at = (uint32_t)item;
+    const uint64_t target = targets[t];
+    const FlatCell fc = ix.cells[at];
+    const TargetCell tc = target_cell(target, s_ij);
+    const P3 a{fc.cx, fc.cy, fc.cz};
+    const P3 centre = cellid_to_point(target, s_ij);
+    const P3 a_cross_b = cross(a, centre);
+    bool r = false;
+    for (uint32_t k = 0; k < fc.clip_count && !r; ++k) {
+      const FlatClip clip = ix.clips[fc.clip_begin + k];
+      if (kMode == 0) {
+        r = any_edge_intersects(ix, clip, tc) || clip_contains_centre(ix, clip, a, centre, a_cross_b);
+      } else {
+        r = ((clip.flags >> 1) & 3u) == 2 && !any_edge_intersects(ix, clip, tc) && clip_contains_centre(ix, clip, a, centre, a_cross_b);
+      }
+    }
+    out[t] = r ? 1 : 0;
   }
 }
 
@@ -154,16 +220,39 @@ int check_region_index(const S2bIndex* ix) {
   return S2B_OK;
 }
 
+// Targets per classify/process round: bounds the work list (8 B per target in the worst case) at 1 GB and keeps target
+// positions in 32 bits.
+constexpr size_t kRegionRound = size_t(1) << 27;
+
 template <int kMode>
 int region_cells_dev(const S2bIndex* ix, const uint64_t* ids_dev, size_t n, uint8_t* out_dev, void* stream) {
   int rc = check_region_index(ix);
   if (rc != S2B_OK) return rc;
   if (n == 0) return S2B_OK;
   if (!ids_dev || !out_dev) return set_error(S2B_EINVAL, "null pointer");
-  auto k = region_cells_kernel<kMode>;
-  k<<<grid_for(n, (const void*)k), kThreads, 0, (cudaStream_t)stream>>>(ix->view, ids_dev, n, out_dev);
-  count_launch();
-  cudaError_t e = cudaGetLastError();
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t round = n < kRegionRound ? n : kRegionRound;
+  void* scratch = nullptr;
+  cudaError_t e = cudaMallocAsync(&scratch, 8 * round + 256, st);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync(region work list)");
+  uint64_t* work = (uint64_t*)((char*)scratch + 256);
+  unsigned int* work_count = (unsigned int*)scratch;
+  auto kc = region_classify_kernel<kMode>;
+  auto kp = region_process_kernel<kMode>;
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kc, 256, 0);
+  if (per_sm < 1) per_sm = 1;
+  for (size_t off = 0; off < n && e == cudaSuccess; off += round) {
+    const size_t cnt = n - off < round ? n - off : round;
+    e = cudaMemsetAsync(work_count, 0, sizeof(unsigned int), st);
+    if (e != cudaSuccess) break;
+    const size_t want = (cnt + 255) / 256, cap = (size_t)sm_count() * per_sm;
+    kc<<<(int)(want < cap ? want : cap), 256, 0, st>>>(ix->view, ids_dev + off, (uint32_t)cnt, out_dev + off, work, work_count);
+    kp<<<grid_for(cnt, (const void*)kp), kThreads, 0, st>>>(ix->view, ids_dev + off, work, work_count, out_dev + off);
+    count_launch(); count_launch();
+    e = cudaGetLastError();
+  }
+  cudaFreeAsync(scratch, st);
   return e == cudaSuccess ? S2B_OK : cuda_fail(e, "region cells launch");
 }
 
