@@ -463,7 +463,11 @@ def region_cells_section(args, torch, dev, rank, world):
         for _ in range(args.steps):
             res = fn(targets)
         e1.record(); torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / args.steps
+        tm = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms = float(tm.item())
         out[name] = {"targets_per_s": world * m / (ms * 1e-3), "ms_per_step": ms, "true_fraction": float(res.float().mean().item())}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
