@@ -289,6 +289,9 @@ int s2b_region_contains_cells_dev(const S2bIndex* index, const uint64_t* cell_id
  * target cell. *total_out (nullable) = number of pairs; S2B_ECAPACITY after filling offsets_out if capacity is smaller. */
 int s2b_region_intersecting_shapes(const S2bIndex* index, const uint64_t* cell_ids, size_t n, uint32_t* offsets_out,
                                    int32_t* shape_ids_out, uint8_t* contains_out, size_t capacity, size_t* total_out);
+/* S2ShapeIndexRegion::GetCellUnionBound (:232-305): at most 6 cells covering the index (what a coverer starts from). Host
+ * logic over the index's cell ids (one device-to-host copy of them per call). */
+int s2b_region_cell_union_bound(const S2bIndex* index, uint64_t cell_ids_out[6], int* count_out);
 /* Any output may be NULL. device_bytes = HBM held by the replica (ids + cells + clips + edges + lookup table). */
 int s2b_index_info(const S2bIndex* index, uint64_t* num_cells, uint64_t* num_clips, uint64_t* num_edges,
                    int32_t* num_shape_ids, uint64_t* device_bytes);

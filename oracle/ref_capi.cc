@@ -471,6 +471,16 @@ size_t ref_region_intersecting_shapes(void* h, const uint64_t* ids, size_t n, ui
   return total;
 }
 
+// S2ShapeIndexRegion::GetCellUnionBound: returns the number of cells (at most 6) written to out.
+int ref_region_cell_union_bound(void* h, uint64_t* out) {
+  auto& index = ((RefIndex*)h)->index;
+  S2ShapeIndexRegion<MutableS2ShapeIndex> region(&index);
+  std::vector<S2CellId> cells;
+  region.GetCellUnionBound(&cells);
+  for (size_t i = 0; i < cells.size(); ++i) out[i] = cells[i].id();
+  return (int)cells.size();
+}
+
 // S2::ClipToPaddedFace + S2::IntersectsRect on raw inputs: out_uv = (a.u, a.v, b.u, b.v) per edge, ok = return value.
 void ref_clip_to_padded_face(const double* a, const double* b, const int32_t* face, size_t n, double padding, double* out_uv, uint8_t* ok) {
   for (size_t i = 0; i < n; ++i) {

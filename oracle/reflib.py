@@ -334,6 +334,11 @@ class RefIndex:
         self.lib.ref_region_cells(_vp(self.h), _p(ids), _sz(ids.size), int(mode), _p(out))
         return out
 
+    def region_cell_union_bound(self):
+        out = np.zeros(8, np.uint64)
+        n = int(self.lib.ref_region_cell_union_bound(_vp(self.h), _p(out)))
+        return out[:n].copy()
+
     def region_intersecting_shapes(self, ids):
         """S2ShapeIndexRegion::VisitIntersectingShapeIds per target: (offsets, shape ids, contains flags), sorted by shape id."""
         ids = np.ascontiguousarray(ids, np.uint64)

@@ -10,6 +10,8 @@
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 
+#include <vector>
+
 #include "../../include/s2b_capi.h"
 #include "s2b_hilbert.h"
 #include "s2b_index_handle.h"
@@ -363,6 +365,19 @@ int s2b_region_intersecting_shapes(const S2bIndex* ix, const uint64_t* cell_ids,
     if ((e = cudaMemcpy(shape_ids_out, shp.p, 4 * total, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
     if ((e = cudaMemcpy(contains_out, con.p, total, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
   }
+  return S2B_OK;
+}
+
+int s2b_region_cell_union_bound(const S2bIndex* ix, uint64_t cell_ids_out[6], int* count_out) {
+  if (!ix) return set_error(S2B_EINVAL, "null index");
+  if (!cell_ids_out || !count_out) return set_error(S2B_EINVAL, "null pointer");
+  *count_out = 0;
+  const size_t C = ix->view.num_cells;
+  if (C == 0) return S2B_OK;
+  std::vector<uint64_t> ids(C);
+  cudaError_t e = cudaMemcpy(ids.data(), ix->view.cell_ids, 8 * C, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(cell ids)");
+  *count_out = region_cell_union_bound(ids.data(), C, cell_ids_out);
   return S2B_OK;
 }
 

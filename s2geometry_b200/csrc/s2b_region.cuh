@@ -269,4 +269,45 @@ S2B_HD int region_clip_relation(const FlatIndexView& ix, const FlatClip& clip, b
   return clip_contains_centre(ix, clip, a, centre, a_cross_b) ? 2 : 0;
 }
 
+// S2CellId::GetCommonAncestorLevel (s2cell_id.cc:193-207): -1 when the cells are on different faces.
+S2B_HD int cellid_common_ancestor_level(uint64_t a, uint64_t b) {
+  uint64_t bits = a ^ b;
+  const uint64_t la = cellid_lsb(a), lb = cellid_lsb(b);
+  if (la > bits) bits = la;
+  if (lb > bits) bits = lb;
+  int width = 0;
+  while (bits) { ++width; bits >>= 1; }
+  const int v = 61 - width;
+  return (v < -1 ? -1 : v) >> 1;
+}
+
+// S2ShapeIndexRegion::GetCellUnionBound (s2shape_index_region.h:232-305) over the sorted index cell ids: at most six
+// cells (one per face the index touches, or the up-to-four children of the smallest cell holding a single-face index,
+// each shrunk to the index cells inside it). Host logic (a handful of binary searches); returns the number of cells.
+inline int region_cell_union_bound(const uint64_t* ids, size_t num_cells, uint64_t out[6]) {
+  if (num_cells == 0) return 0;
+  int count = 0;
+  auto cover_range = [&](uint64_t first, uint64_t last) {
+    if (count >= 6) return;
+    out[count++] = first == last ? first : cellid_parent(first, cellid_common_ancestor_level(first, last));
+  };
+  const uint64_t last_index_id = ids[num_cells - 1];
+  size_t it = 0;
+  if (ids[0] != last_index_id) {
+    const int level = cellid_common_ancestor_level(ids[0], last_index_id) + 1;
+    const uint64_t last_id = cellid_parent(last_index_id, level);
+    for (uint64_t id = cellid_parent(ids[0], level); id != last_id; id += cellid_lsb(id) << 1) {
+      if (cellid_range_max(id) < ids[it]) continue;
+      const uint64_t first = ids[it];
+      const uint64_t past = cellid_range_max(id) + 2;               // range_max().next(): the leaf after the cell
+      size_t lo = it, hi = num_cells;                               // Seek(past)
+      while (lo < hi) { const size_t mid = (lo + hi) >> 1; if (ids[mid] < past) lo = mid + 1; else hi = mid; }
+      cover_range(first, ids[lo - 1]);
+      it = lo;
+    }
+  }
+  cover_range(ids[it], last_index_id);
+  return count;
+}
+
 }  // namespace s2b

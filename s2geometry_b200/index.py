@@ -277,6 +277,13 @@ class ShapeIndexRegion:
         """S2ShapeIndexRegion::Contains(S2Point) = S2ContainsPointQuery(SEMI_OPEN)::Contains (:437-445)."""
         return ContainsPointQuery(self.index, 1).contains(xyz)
 
+    def cell_union_bound(self):
+        """S2ShapeIndexRegion::GetCellUnionBound (:232-305): at most six cell ids covering the index."""
+        out = np.zeros(6, np.uint64)
+        cnt = ctypes.c_int(0)
+        _lib.check(self._lib.s2b_region_cell_union_bound(self.index._h, _ptr(out), ctypes.byref(cnt)))
+        return out[: cnt.value].copy()
+
     def intersecting_shapes(self, cell_ids):
         """VisitIntersectingShapeIds per target cell (:373-424) as (offsets uint32[n+1], shape_ids int32, contains uint8),
         pairs ascending by shape id within a target."""

@@ -124,4 +124,6 @@ void hs_intersects_rect(const double* uv4, const double* rect4, size_t n, uint8_
   }
 }
 
+int hs_region_cell_union_bound(const uint64_t* ids, size_t n, uint64_t* out6) { return region_cell_union_bound(ids, n, out6); }
+
 }  // extern "C"

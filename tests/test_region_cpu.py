@@ -106,3 +106,25 @@ def test_region_cell_tests_over_the_librarys_own_builder(hostsim, ref):
         for mode in (0, 1):
             got, bad = hs_region_cells(hostsim, flat, targets, mode)
             assert bad == 0 and (got == ri.region_cells(targets, mode)).all(), (name, mode)
+
+
+def test_cell_union_bound_matches_reference(hostsim, ref):
+    """GetCellUnionBound: single-face indexes (children of the smallest enclosing cell), multi-face ones, one cell, one
+    cell per face."""
+    from s2geometry_b200.shapes import ShapeSoup
+    from s2geometry_b200 import synth
+    cases = [soup for _, soup in region_scenes.region_scene_list()]
+    for centre, radius, nv in (([1, 0.01, 0.02], 1e-3, 12), ([1, 1, 1], 0.3, 30), ([0.2, -0.9, 0.1], 1e-6, 5), ([0, 0, 1], 1.4, 40)):
+        s = ShapeSoup(); s.add_polygon([synth.wobbly_loop(np.array(centre, float), radius, nv)]); cases.append(s.freeze())
+    s = ShapeSoup(); s.add_points(scenes._norm(np.array([[1, 0.3, 0.2]], float))); cases.append(s.freeze())
+    s = ShapeSoup(); s.add_points(scenes._norm(np.array([[1, .1, .1], [-1, .1, .1], [.1, 1, .1], [.1, -1, .1], [.1, .1, 1], [.1, .1, -1]], float))); cases.append(s.freeze())
+    seen = set()
+    for soup in cases:
+        ri = ref.index_create(soup)
+        ids = np.ascontiguousarray(ri.flatten()["cell_ids"], np.uint64)
+        out = np.zeros(6, np.uint64)
+        n = hostsim.hs_region_cell_union_bound(vp(ids), ctypes.c_size_t(len(ids)), vp(out))
+        want = ri.region_cell_union_bound()
+        assert n == len(want) and (out[:n] == want).all()
+        seen.add(n)
+    assert {1, 4, 6} & seen and len(seen) >= 3

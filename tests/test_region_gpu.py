@@ -28,6 +28,7 @@ def test_region_cell_tests_vs_reference(ref):
         woff, wshp, wcon = ri.region_intersecting_shapes(targets)
         assert (off == woff).all() and (shp == wshp).all() and (con == wcon).all(), name
         assert _lib.launch_count() >= before + 8
+        assert (region.cell_union_bound() == ri.region_cell_union_bound()).all(), name
         # empty batch and a batch of one DISJOINT / one face cell
         assert len(region.may_intersect(np.zeros(0, np.uint64))) == 0
         off0, shp0, con0 = region.intersecting_shapes(np.zeros(0, np.uint64))
