@@ -292,6 +292,12 @@ int s2b_region_intersecting_shapes(const S2bIndex* index, const uint64_t* cell_i
 /* S2ShapeIndexRegion::GetCellUnionBound (:232-305): at most 6 cells covering the index (what a coverer starts from). Host
  * logic over the index's cell ids (one device-to-host copy of them per call). */
 int s2b_region_cell_union_bound(const S2bIndex* index, uint64_t cell_ids_out[6], int* count_out);
+/* The S2RegionCoverer loop (s2region_coverer.cc:GetCoveringInternal) for a fixed level, run on the device level by level:
+ * starting from GetCellUnionBound, every frontier cell is tested with MayIntersect, survivors are subdivided until `level`.
+ * The result is the covering S2RegionCoverer::GetCovering(S2ShapeIndexRegion) returns with min_level = max_level = level
+ * (where max_cells does not bind): sorted level-`level` cell ids. *total_out = their number; S2B_ECAPACITY if it exceeds
+ * capacity (nothing written). */
+int s2b_region_covering_at_level(const S2bIndex* index, int level, uint64_t* cell_ids_out, size_t capacity, size_t* total_out);
 /* Any output may be NULL. device_bytes = HBM held by the replica (ids + cells + clips + edges + lookup table). */
 int s2b_index_info(const S2bIndex* index, uint64_t* num_cells, uint64_t* num_clips, uint64_t* num_edges,
                    int32_t* num_shape_ids, uint64_t* device_bytes);

@@ -732,6 +732,20 @@ size_t ref_cover_cap(const double* center, double radius_rad, int max_cells, int
   return k;
 }
 
+// S2RegionCoverer::GetCovering(S2ShapeIndexRegion) with min_level = max_level = level; returns the number of cells.
+size_t ref_region_covering(void* h, int level, uint64_t* out, size_t capacity) {
+  auto& index = ((RefIndex*)h)->index;
+  S2ShapeIndexRegion<MutableS2ShapeIndex> region(&index);
+  S2RegionCoverer::Options opt;
+  opt.set_min_level(level);
+  opt.set_max_level(level);
+  S2RegionCoverer coverer(opt);
+  S2CellUnion u = coverer.GetCovering(region);
+  size_t k = 0;
+  for (S2CellId id : u.cell_ids()) { if (k < capacity) out[k] = id.id(); ++k; }
+  return k;
+}
+
 // ---------------------------------------------------------------- S2CellIndex (s2cell_index.h) / S2RegionSharder
 struct RefCellIndex { S2CellIndex index; };
 void* ref_cell_index_create(const uint64_t* ids, const int32_t* labels, size_t m) {

@@ -339,6 +339,14 @@ class RefIndex:
         n = int(self.lib.ref_region_cell_union_bound(_vp(self.h), _p(out)))
         return out[:n].copy()
 
+    def region_covering(self, level):
+        """S2RegionCoverer (min_level = max_level = level) over S2ShapeIndexRegion -> sorted cell ids."""
+        self.lib.ref_region_covering.restype = _sz
+        n = int(self.lib.ref_region_covering(_vp(self.h), int(level), None, _sz(0)))
+        out = np.zeros(max(n, 1), np.uint64)
+        self.lib.ref_region_covering(_vp(self.h), int(level), _p(out), _sz(n))
+        return out[:n]
+
     def region_intersecting_shapes(self, ids):
         """S2ShapeIndexRegion::VisitIntersectingShapeIds per target: (offsets, shape ids, contains flags), sorted by shape id."""
         ids = np.ascontiguousarray(ids, np.uint64)

@@ -100,6 +100,7 @@ SIGNATURES = {
     "s2b_region_contains_cells_dev": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "s2b_region_intersecting_shapes": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp]),
     "s2b_region_cell_union_bound": (_i, [_vp, _vp, _vp]),
+    "s2b_region_covering_at_level": (_i, [_vp, _i, _vp, _sz, _vp]),
     "s2b_index_info": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "s2b_contains": (_i, [_vp, _vp, _sz, _i, _vp]),
     "s2b_contains_dev": (_i, [_vp, _vp, _sz, _i, _vp, _vp]),

@@ -10,6 +10,8 @@
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 
+#include <algorithm>
+#include <cstring>
 #include <vector>
 
 #include "../../include/s2b_capi.h"
@@ -201,6 +203,41 @@ __global__ void region_pairs_kernel(const uint64_t* __restrict__ keys, size_t m,
   }
 }
 
+// One step of the fixed-level covering: kept cells (MayIntersect) at the target level go to `done`, shallower ones hand
+// their four children (S2CellId::child, s2cell_id.h:670-676) to the next frontier. One atomicAdd per warp and list.
+__global__ void __launch_bounds__(256)
+covering_expand_kernel(const uint64_t* __restrict__ ids, const uint8_t* __restrict__ keep, uint32_t n, int level,
+                       uint64_t* __restrict__ next, uint64_t* __restrict__ done, unsigned int* __restrict__ counters) {
+  const unsigned lane = threadIdx.x & 31u;
+  const uint32_t stride = gridDim.x * 256u;
+  for (uint64_t base = (uint64_t)blockIdx.x * 256u + (threadIdx.x & ~31u); base < n; base += stride) {
+    const uint64_t t = base + lane;
+    uint64_t id = 0;
+    bool to_next = false, to_done = false;
+    if (t < n && keep[t]) {
+      id = ids[t];
+      to_done = cellid_level(id) >= level;
+      to_next = !to_done;
+    }
+    const unsigned mn = __ballot_sync(0xffffffffu, to_next), md = __ballot_sync(0xffffffffu, to_done);
+    unsigned bn = 0, bd = 0;
+    if (lane == 0) {
+      if (mn) bn = atomicAdd(counters, (unsigned)__popc(mn));
+      if (md) bd = atomicAdd(counters + 1, (unsigned)__popc(md));
+    }
+    bn = __shfl_sync(0xffffffffu, bn, 0);
+    bd = __shfl_sync(0xffffffffu, bd, 0);
+    const unsigned below = (1u << lane) - 1u;
+    if (to_done) done[bd + __popc(md & below)] = id;
+    if (to_next) {
+      const uint64_t child_lsb = cellid_lsb(id) >> 2;
+      uint64_t* dst = next + 4ull * (bn + __popc(mn & below));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) dst[k] = id + (uint64_t)(int64_t)(2 * k + 1 - 4) * child_lsb;
+    }
+  }
+}
+
 int grid_for(size_t n, const void* kernel) {
   int per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
@@ -378,6 +415,58 @@ int s2b_region_cell_union_bound(const S2bIndex* ix, uint64_t cell_ids_out[6], in
   cudaError_t e = cudaMemcpy(ids.data(), ix->view.cell_ids, 8 * C, cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(cell ids)");
   *count_out = region_cell_union_bound(ids.data(), C, cell_ids_out);
+  return S2B_OK;
+}
+
+int s2b_region_covering_at_level(const S2bIndex* ix, int level, uint64_t* cell_ids_out, size_t capacity, size_t* total_out) {
+  int rc = check_region_index(ix);
+  if (rc != S2B_OK) return rc;
+  if (level < 0 || level > 30) return set_error(S2B_EINVAL, "level must be in [0, 30]");
+  if (total_out) *total_out = 0;
+  uint64_t start[6];
+  int num_start = 0;
+  if ((rc = s2b_region_cell_union_bound(ix, start, &num_start)) != S2B_OK) return rc;
+  std::vector<uint64_t> frontier;
+  for (int k = 0; k < num_start; ++k) frontier.push_back(cellid_level(start[k]) > level ? cellid_parent(start[k], level) : start[k]);
+  std::sort(frontier.begin(), frontier.end());
+  frontier.erase(std::unique(frontier.begin(), frontier.end()), frontier.end());
+  std::vector<uint64_t> result;
+  DevBuf cur, counters;
+  cudaError_t e = counters.alloc(8);
+  size_t n = frontier.size();
+  if (e == cudaSuccess) e = cur.alloc(8 * n);
+  if (e == cudaSuccess && n) e = cudaMemcpy(cur.p, frontier.data(), 8 * n, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc/cudaMemcpy");
+  while (n > 0) {
+    if (n >= (size_t(1) << 29)) return set_error(S2B_ECAPACITY, "covering frontier of %zu cells: choose a coarser level", n);
+    DevBuf next_buf, done_buf, keep_buf;
+    e = next_buf.alloc(32 * n);
+    if (e == cudaSuccess) e = done_buf.alloc(8 * n);
+    if (e == cudaSuccess) e = keep_buf.alloc(n);
+    if (e == cudaSuccess) e = cudaMemset(counters.p, 0, 8);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(covering frontier)");
+    if ((rc = region_cells_dev<0>(ix, cur.as<uint64_t>(), n, keep_buf.as<uint8_t>(), nullptr)) != S2B_OK) return rc;
+    const size_t want = (n + 255) / 256, cap = (size_t)sm_count() * 8;
+    covering_expand_kernel<<<(int)(want < cap ? want : cap), 256>>>(cur.as<uint64_t>(), keep_buf.as<uint8_t>(), (uint32_t)n, level,
+                                                                   next_buf.as<uint64_t>(), done_buf.as<uint64_t>(), counters.as<unsigned int>());
+    count_launch();
+    unsigned int cnt[2] = {0, 0};
+    if ((e = cudaMemcpy(cnt, counters.p, 8, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "covering step");
+    if (cnt[1]) {
+      const size_t old = result.size();
+      result.resize(old + cnt[1]);
+      if ((e = cudaMemcpy(result.data() + old, done_buf.p, 8ull * cnt[1], cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
+    }
+    n = 4ull * cnt[0];
+    std::swap(cur.p, next_buf.p);   // next_buf's destructor frees the old frontier
+  }
+  std::sort(result.begin(), result.end());
+  if (total_out) *total_out = result.size();
+  if (result.size() > capacity) return set_error(S2B_ECAPACITY, "%zu covering cells but capacity is %zu", result.size(), capacity);
+  if (!result.empty()) {
+    if (!cell_ids_out) return set_error(S2B_EINVAL, "null cell_ids_out");
+    std::memcpy(cell_ids_out, result.data(), 8 * result.size());
+  }
   return S2B_OK;
 }
 

@@ -284,6 +284,18 @@ class ShapeIndexRegion:
         _lib.check(self._lib.s2b_region_cell_union_bound(self.index._h, _ptr(out), ctypes.byref(cnt)))
         return out[: cnt.value].copy()
 
+    def covering_at_level(self, level):
+        """S2RegionCoverer::GetCovering(region) with min_level = max_level = level: the sorted level-`level` cells that may
+        intersect the index, found by subdividing from cell_union_bound() with batched MayIntersect tests on the device."""
+        total = ctypes.c_size_t(0)
+        rc = self._lib.s2b_region_covering_at_level(self.index._h, int(level), None, 0, ctypes.byref(total))
+        if rc != _lib.S2B_ECAPACITY:
+            _lib.check(rc)
+            return np.zeros(0, np.uint64)
+        out = np.empty(total.value, np.uint64)
+        _lib.check(self._lib.s2b_region_covering_at_level(self.index._h, int(level), _ptr(out), out.size, ctypes.byref(total)))
+        return out
+
     def intersecting_shapes(self, cell_ids):
         """VisitIntersectingShapeIds per target cell (:373-424) as (offsets uint32[n+1], shape_ids int32, contains uint8),
         pairs ascending by shape id within a target."""

@@ -62,3 +62,19 @@ def test_unsupported_edge_is_refused_loudly():
         ShapeIndexRegion(index).may_intersect(np.array([0x1000000000000000], np.uint64))
     assert e.value.code == _lib.S2B_EUNSUPPORTED
     assert ContainsPointQuery(index, 1).contains(a).shape == (4,)
+
+
+def test_fixed_level_covering_equals_the_reference_coverer(ref):
+    """The device-side subdivision loop (GetCellUnionBound -> MayIntersect -> children ...) returns the covering
+    S2RegionCoverer::GetCovering(S2ShapeIndexRegion) gives with min_level = max_level = level."""
+    from s2geometry_b200.index import FlatIndex, ShapeIndex, ShapeIndexRegion
+    total = 0
+    for name, soup in region_scenes.region_scene_list():
+        ri = ref.index_create(soup)
+        region = ShapeIndexRegion(ShapeIndex(FlatIndex(**ri.flatten())))
+        for level in (0, 2, 5, 8, 10):
+            want = ri.region_covering(level)
+            got = region.covering_at_level(level)
+            assert len(got) == len(want) and (got == want).all(), (name, level, len(got), len(want))
+            total += len(want)
+    assert total > 10000
