@@ -246,6 +246,20 @@ int grid_for(size_t n, const void* kernel) {
   return (int)(want < cap ? (want ? want : 1) : cap);
 }
 
+// Stream-ordered scratch stays cached across synchronisations (the default release threshold of 0 hands freed blocks back
+// to the driver at every sync, which costs milliseconds per call); same setting as the point queries make.
+void keep_pool_memory_once() {
+  static thread_local int done_for_device = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for_device) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  done_for_device = dev;
+}
+
 int check_region_index(const S2bIndex* ix) {
   if (!ix) return set_error(S2B_EINVAL, "null index");
   if (ix->unsupported_region_edges)
@@ -262,6 +276,7 @@ int check_region_index(const S2bIndex* ix) {
 // Targets per classify/process round: bounds the work list (8 B per target in the worst case) at 1 GB and keeps target
 // positions in 32 bits.
 constexpr size_t kRegionRound = size_t(1) << 27;
+constexpr unsigned int kRegionSortMin = 1u << 16;   // below this the sort costs more than the divergence it removes
 
 template <int kMode>
 int region_cells_dev(const S2bIndex* ix, const uint64_t* ids_dev, size_t n, uint8_t* out_dev, void* stream) {
@@ -270,6 +285,7 @@ int region_cells_dev(const S2bIndex* ix, const uint64_t* ids_dev, size_t n, uint
   if (n == 0) return S2B_OK;
   if (!ids_dev || !out_dev) return set_error(S2B_EINVAL, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  keep_pool_memory_once();
   const size_t round = n < kRegionRound ? n : kRegionRound;
   void* scratch = nullptr;
   cudaError_t e = cudaMallocAsync(&scratch, 8 * round + 256, st);
@@ -281,16 +297,43 @@ int region_cells_dev(const S2bIndex* ix, const uint64_t* ids_dev, size_t n, uint
   int per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kc, 256, 0);
   if (per_sm < 1) per_sm = 1;
+  // The work list is sorted by index cell before the edge tests (radix sort on the low log2(num_cells) bits of the items),
+  // so the lanes of a warp read the same cell's clips and edges and run the same trip counts. Needs the item count on the
+  // host: one 4-byte copy + stream synchronisation per round.
+  int cell_bits = 1;
+  while ((1ull << cell_bits) < ix->view.num_cells) ++cell_bits;
+  void* sort_tmp = nullptr;
+  uint64_t* sorted = nullptr;
+  size_t sort_bytes = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, work, work, round, 0, cell_bits, st);
   for (size_t off = 0; off < n && e == cudaSuccess; off += round) {
     const size_t cnt = n - off < round ? n - off : round;
     e = cudaMemsetAsync(work_count, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess) break;
     const size_t want = (cnt + 255) / 256, cap = (size_t)sm_count() * per_sm;
     kc<<<(int)(want < cap ? want : cap), 256, 0, st>>>(ix->view, ids_dev + off, (uint32_t)cnt, out_dev + off, work, work_count);
-    kp<<<grid_for(cnt, (const void*)kp), kThreads, 0, st>>>(ix->view, ids_dev + off, work, work_count, out_dev + off);
-    count_launch(); count_launch();
+    count_launch();
+    unsigned int hard = 0;
+    e = cudaMemcpyAsync(&hard, work_count, sizeof hard, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess || hard == 0) continue;
+    const uint64_t* items = work;
+    if (hard >= kRegionSortMin) {
+      if (!sorted) {
+        e = cudaMallocAsync(&sort_tmp, sort_bytes + 8 * round + 256, st);
+        if (e != cudaSuccess) break;
+        sorted = (uint64_t*)((char*)sort_tmp + ((sort_bytes + 255) / 256) * 256);
+      }
+      e = cub::DeviceRadixSort::SortKeys(sort_tmp, sort_bytes, work, sorted, (size_t)hard, 0, cell_bits, st);
+      if (e != cudaSuccess) break;
+      count_launch();
+      items = sorted;
+    }
+    kp<<<grid_for(hard, (const void*)kp), kThreads, 0, st>>>(ix->view, ids_dev + off, items, work_count, out_dev + off);
+    count_launch();
     e = cudaGetLastError();
   }
+  if (sort_tmp) cudaFreeAsync(sort_tmp, st);
   cudaFreeAsync(scratch, st);
   return e == cudaSuccess ? S2B_OK : cuda_fail(e, "region cells launch");
 }
