@@ -124,7 +124,7 @@ def run_reference(args):
                          "sample": "%d of 100M lat/lng points per step, %d threads" % (sample, threads)},
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    _emit(line)
     return 0
 
 
@@ -775,13 +775,30 @@ def run_gpu(args):
                 line["cpu_baseline"] = cpu_baseline()
             except Exception as e:  # the oracle library is test infrastructure; its absence must not hide the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": "points/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_JSON_FD = None
+
+
+def _emit(line):
+    """The ONE JSON line goes to the process's original stdout; everything else that writes to fd 1 (NCCL's version
+    banner at N > 1, library chatter) was pointed at stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
