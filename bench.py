@@ -36,7 +36,10 @@ BYTES_PER_POINT = 16 + 8 * len(LEVELS) + 16 + 1   # algorithmic HBM bytes per po
 # FP64-pipe instructions (DADD/DMUL/DFMA/DSETP) executed per point by encode_kernel<latlng>, measured with ncu's
 # per-instruction counts (profiles/r1_encode_latlng_final_ncu.json); used only for the informational fp64 roofline.
 FP64_INSTR_PER_POINT = 109
+DRAM_BYTES_PER_POINT = 54.14      # ncu dram__bytes_read.sum + dram__bytes_write.sum of the encode kernel, per point
+PROFILE_SOURCE = "profiles/r1_encode_latlng_final_ncu.json"
 METRIC = "points/sec (S2CellId encode, lat/lng -> levels 12/20/30 + ToToken)"
+WORKLOAD = "configs[1]: 100M lat/lng (radians, uniform on sphere) per GPU -> S2CellId at levels 12/20/30 + ToToken(level 30)"
 
 
 def peaks():
@@ -94,8 +97,12 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+STREAM_LATLNG = 2   # seed of the headline lat/lng stream (s2geometry_b200/synth.py: point i = f(seed, i), any host or GPU)
+
+
 def run_reference(args):
-    """The reference's own CPU implementation of the step on this box's host cores, on a bounded sample."""
+    """The reference's own CPU implementation of the step on this box's host cores: the same 100M-point stream the
+    GPU arm encodes (counter-based generator: identical bits on the host), all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -103,8 +110,8 @@ def run_reference(args):
     from s2geometry_b200 import synth
     ref = reflib.load()
     threads = ref.hardware_threads()
-    sample = 20_000_000
-    ll = synth.sphere_latlng(sample, 2)
+    n = args.points
+    ll = synth.stream_sphere_latlng(STREAM_LATLNG, 0, n)
     times = []
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
@@ -113,39 +120,43 @@ def run_reference(args):
         if it >= args.warmup:
             times.append(dt)
     ms = 1e3 * sum(times) / len(times)
-    value = sample / (ms * 1e-3)
+    value = n / (ms * 1e-3)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[1]: lat/lng -> S2CellId levels 12/20/30 + ToToken(level 30)", "points_per_step": sample,
-                   "note": "bounded sample of the 100M-point workload; unmodified reference sources + abseil stand-in, -O2"},
+        "config": {"workload": WORKLOAD, "points_per_gpu": n, "levels": LEVELS, "points_per_step": n,
+                   "note": "unmodified reference sources + abseil stand-in, -O2, %d host threads; one GPU's share of the stream per step" % threads},
         "cpu_baseline": {"value": value, "unit": "points/s", "cores": threads, "kind": "reference",
-                         "sample": "%d of 100M lat/lng points per step, %d threads" % (sample, threads)},
+                         "sample": "all %d lat/lng points of stream %d per step, %d threads" % (n, STREAM_LATLNG, threads)},
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     _emit(line)
     return 0
 
 
-def cpu_baseline():
+def cpu_baseline(ll_dev, ids_dev, tok_dev, len_dev):
+    """Headline cpu_baseline leg: the reference on the host cores over the SAME points the GPU just encoded (copied back
+    from the device: the stream is bit-reproducible, tests/test_synth_*), timed, and every id / token compared."""
     from oracle import reflib  # cpu_baseline leg
-    from s2geometry_b200 import synth
     ref = reflib.load()
     threads = ref.hardware_threads()
-    probe = synth.sphere_latlng(2_000_000, 2)
-    t0 = time.perf_counter()
-    ref.encode_latlng_levels_tokens(probe, LEVELS, TOKEN_LEVEL_INDEX, threads)
-    rate = len(probe) / (time.perf_counter() - t0)
-    sample = int(min(N_POINTS, max(4_000_000, rate * 4)))   # ~4 s per pass, 3 passes
-    ll = synth.sphere_latlng(sample, 2)
+    n = ll_dev.shape[0]
+    sample = n if threads >= 8 else min(n, 25_000_000)
+    ll = ll_dev[:sample].cpu().numpy()
     best = 1e30
     for _ in range(3):
         t0 = time.perf_counter()
-        ref.encode_latlng_levels_tokens(ll, LEVELS, TOKEN_LEVEL_INDEX, threads)
+        w_ids, w_tok, w_len = ref.encode_latlng_levels_tokens(ll, LEVELS, TOKEN_LEVEL_INDEX, threads)
         best = min(best, time.perf_counter() - t0)
+    mismatches = 0
+    for k in range(len(LEVELS)):
+        mismatches += int((ids_dev[k, :sample].cpu().numpy().view(np.uint64) != w_ids[k]).sum())
+    mismatches += int((tok_dev[:sample].cpu().numpy() != w_tok).any(axis=1).sum()) + int((len_dev[:sample].cpu().numpy() != w_len).sum())
     return {"value": sample / best, "unit": "points/s", "cores": threads, "kind": "reference",
-            "sample": "%d of 100M lat/lng points, best of 3, %d threads (reference sources + abseil stand-in)" % (sample, threads)}
+            "sample": "%d of %d lat/lng points, best of 3, %d threads (reference sources + abseil stand-in)" % (sample, n, threads),
+            "parity_on_sample": mismatches == 0, "mismatches": mismatches,
+            "compared": "ids at levels %s + tokens + token lengths of all %d sample points" % (LEVELS, sample)}
 
 
 def pip_section(args, torch, dev, rank, world):
@@ -174,18 +185,10 @@ def pip_section(args, torch, dev, rank, world):
                n, DEVICE_MAX_EDGES_PER_CELL, flat.num_cells, flat.num_edges),
            "bytes_per_point": 25}
     sets = {}
-    pts_u = synth.sphere_points_cuda(n, 3 + rank, dev)
+    # this rank's slices of the global streams 3 (uniform on the sphere) and 7 (uniform in the loop's bounding cap)
+    pts_u = synth.stream_sphere_points_cuda(3, rank * n, n, dev)
     sets["uniform"] = pts_u
-    # B: uniform in the bounding cap, generated on the device
-    g = torch.Generator(device=dev); g.manual_seed(7 + rank)
-    x, y, z = [torch.from_numpy(v).to(dev) for v in synth.frame(center)]
-    h = torch.rand(n, dtype=torch.float64, device=dev, generator=g) * (1 - np.cos(radius))
-    t = torch.rand(n, dtype=torch.float64, device=dev, generator=g) * (2 * np.pi)
-    cz = 1 - h; sz = torch.sqrt(torch.clamp(1 - cz * cz, min=0))
-    pts_b = cz[:, None] * z + sz[:, None] * (torch.cos(t)[:, None] * x + torch.sin(t)[:, None] * y)
-    pts_b /= pts_b.norm(dim=1, keepdim=True)
-    del h, t, cz, sz
-    sets["near"] = pts_b
+    sets["near"] = synth.stream_cap_points_cuda(7, rank * n, n, center, radius, dev)
     res = torch.empty(n, dtype=torch.uint8, device=dev)
     lib = _lib.load()
     import ctypes
@@ -244,7 +247,7 @@ def encode_xyz_section(args, torch, dev, rank, world):
     """BASELINE configs[0] on the GPU: S2Points -> level-30 S2CellId (32 algorithmic bytes per point)."""
     from s2geometry_b200 import cellid, synth
     n = args.points
-    pts = synth.sphere_points_cuda(n, 1 + rank, dev)
+    pts = synth.stream_sphere_points_cuda(1, rank * n, n, dev)
     ids = None
     for _ in range(3):
         ids = cellid.from_points(pts, 30)
@@ -281,12 +284,12 @@ def radius_join_section(args, torch, dev, rank, world):
     m = 10_000_000
     n = min(args.points, 50_000_000)
     radius = 10.0 / 6371.01
-    index_pts = synth.sphere_points_cuda(m, 77, dev)
+    index_pts = synth.stream_sphere_points_cuda(77, 0, m, dev)
     t0 = time.perf_counter()
     ix = PointIndex(index_pts)
     torch.cuda.synchronize()
     build_s = time.perf_counter() - t0
-    targets = synth.sphere_points_cuda(n, 200 + rank, dev)
+    targets = synth.stream_sphere_points_cuda(200, rank * n, n, dev)
     q = ClosestPointQuery(ix, radius)
     qn = ClosestPointQuery(ix)
 
@@ -335,7 +338,7 @@ def cell_index_join_section(args, torch, dev, rank, world):
     centers = synth.sphere_points(num_labels, 55)
     leaves = cellid.from_points(centers, 30)
     n = args.points
-    pts = synth.sphere_points_cuda(n, 300 + rank, dev)
+    pts = synth.stream_sphere_points_cuda(300, rank * n, n, dev)
     hbm_peak, _ = peaks()
 
     def scene(level_lo, level_hi):
@@ -439,19 +442,13 @@ def region_cells_section(args, torch, dev, rank, world):
     flat = FlatIndex(**{k: fx[k] for k in FlatIndex.FIELDS}, num_shape_ids=int(fx["num_shape_ids"]))
     region = ShapeIndexRegion(ShapeIndex(flat))
     m = min(args.points, 20_000_000)
-    g = torch.Generator(device=dev); g.manual_seed(77 + rank)
     center = np.array([0.3, -0.5, 0.8]); radius = 0.17 * 1.25
-    x, y, z = [torch.from_numpy(v).to(dev) for v in synth.frame(center)]
-    h = torch.rand(m, dtype=torch.float64, device=dev, generator=g) * (1 - np.cos(radius))
-    t = torch.rand(m, dtype=torch.float64, device=dev, generator=g) * (2 * np.pi)
-    cz = 1 - h; sz = torch.sqrt(torch.clamp(1 - cz * cz, min=0))
-    pts = cz[:, None] * z + sz[:, None] * (torch.cos(t)[:, None] * x + torch.sin(t)[:, None] * y)
-    pts /= pts.norm(dim=1, keepdim=True)
+    pts = synth.stream_cap_points_cuda(78, rank * m, m, center, radius, dev)
     leaf = cellid.from_points(pts, 30)
-    level = torch.randint(6, 21, (m,), device=dev, generator=g, dtype=torch.int64)
+    level = 6 + ((leaf >> 3) & 0xFFFF) % 15          # levels 6..20, a deterministic function of the point
     lsb = torch.ones_like(level) << (2 * (30 - level))
     targets = ((leaf & -lsb) | lsb).contiguous()
-    del pts, h, t, cz, sz, leaf, level, lsb
+    del pts, leaf, level, lsb
     out = {"workload": "S2ShapeIndexRegion cell tests: %d target cells (levels 6..20, in the bounding cap of the 10k-vertex loop) per GPU vs the "
                        "reference-built index (%d cells, %d clipped edges)" % (m, flat.num_cells, flat.num_edges)}
     for name, fn in (("may_intersect", region.may_intersect), ("contains_cell", region.contains_cells)):
@@ -507,10 +504,13 @@ def join_section(args, torch, dev, rank, world):
     build_s = time.perf_counter() - t0
     ix = ShapeIndex(flat)
     query = ContainsPointQuery(ix, 1)
-    n_total = args.join_points   # each rank draws its own shard (independent seeds): a statistically equivalent global set
+    n_total = args.join_points
     lo, hi = sdist.shard_range(n_total, rank, world)
     n = hi - lo
-    pts = synth.sphere_points_cuda(n, 1000 + rank, dev)
+    # This rank's slice [lo, hi) of ONE global stream of n_total points (counter-based: point i = f(seed, i)), so the
+    # histogram is the same array at 1, 2, 4 and 8 GPUs and its sample can be checked against the reference at every N.
+    JOIN_STREAM = 1000
+    pts = synth.stream_sphere_points_cuda(JOIN_STREAM, lo, n, dev)
     counts = torch.zeros(flat.num_shape_ids, dtype=torch.int64, device=dev)
 
     def step():
@@ -531,36 +531,46 @@ def join_section(args, torch, dev, rank, world):
     ms = float(t.item())
     hbm_peak, _ = peaks()
     ach = 24 * n_total / world / (ms * 1e-3) / 1e9   # per-GPU algorithmic bytes over the step time
-    out = {"workload": "configs[3]: %d uniform points (sharded over %d GPU(s)) vs 10k polygons (%d vertices; index with max_edges_per_cell=1: %d cells, %d clipped edges, %.1f MB on device), per-polygon counts + all-reduce"
-                       % (n_total, world, len(soup.vertices), flat.num_cells, flat.num_edges, ix.info()["device_bytes"] / 1e6),
+    hist = counts.cpu().numpy().astype(np.uint64)
+    checksum = int((hist * (np.arange(len(hist), dtype=np.uint64) * np.uint64(2654435761) + np.uint64(1))).sum() & np.uint64(0xFFFFFFFFFFFFFFFF))
+    out = {"workload": "configs[3]: %d uniform points (stream %d, sharded over %d GPU(s)) vs 10k polygons (%d vertices; index with max_edges_per_cell=1: %d cells, %d clipped edges, %.1f MB on device), per-polygon counts + all-reduce"
+                       % (n_total, JOIN_STREAM, world, len(soup.vertices), flat.num_cells, flat.num_edges, ix.info()["device_bytes"] / 1e6),
            "scaling": "strong", "points_per_s": n_total / (ms * 1e-3), "ms_per_step": ms, "index_build_s": build_s,
-           "total_hits": int(counts.sum().item()), "bytes_per_point": 24,
+           "total_hits": int(hist.sum()), "histogram_checksum": "%016x" % checksum, "bytes_per_point": 24,
            "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "note": "per GPU"}}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    # Parity against the reference at EVERY N: the first `k` points of the global stream live on rank 0 for any N; the GPU
+    # histogram of exactly those points must equal the reference's VisitContainingShapeIds histogram of the same points.
+    if rank == 0 and not args.no_cpu_baseline:
         try:
             from oracle import reflib  # cpu_baseline leg
             ref = reflib.load()
             t0 = time.perf_counter(); ri = ref.index_create(soup); ref_build_s = time.perf_counter() - t0
             threads = ref.hardware_threads()
-            sample = pts[:20_000_000].cpu().numpy()
+            k = min(n, 20_000_000)
+            sample = pts[:k].cpu().numpy()
+            assert np.array_equal(sample[:100_000], synth.stream_sphere_points(JOIN_STREAM, 0, 100_000)), "device stream != host stream"
             best = 1e30
-            for _ in range(2):
+            for _ in range(2 if world == 1 else 1):
                 t0 = time.perf_counter(); want = ri.shape_histogram(sample, 1, threads); best = min(best, time.perf_counter() - t0)
-            got = query.shape_histogram(pts[:20_000_000]).cpu().numpy().view(np.uint64)
+            got = query.shape_histogram(pts[:k]).cpu().numpy().view(np.uint64)
+            out["parity_vs_reference"] = bool((got == want).all())
             out["cpu_baseline"] = {"value": len(sample) / best, "unit": "points/s", "cores": threads, "kind": "reference",
-                                   "sample": "first 20M points, VisitContainingShapeIds histogram, best of 2", "index_build_s": ref_build_s,
+                                   "sample": "first %d points of the global stream, VisitContainingShapeIds histogram" % k, "index_build_s": ref_build_s,
                                    "parity_on_sample": bool((got == want).all())}
         except Exception as e:
             out["cpu_baseline"] = {"unavailable": str(e)}
+    sdist.barrier()
     del pts
-    # ---- configs[4]: S2CellUnion containment (<= 1000 cells) of the same number of points, global hit count
+    # ---- configs[4]: S2CellUnion containment of the same number of points against an S2RegionCoverer covering
+    # (max_cells = 1000) of the 10k-vertex loop, computed by the reference's own coverer (tests/golden/covering_loop10k.npz,
+    # tools/gen_golden.py covering); global hit count = one-element all-reduce inside the step.
     from s2geometry_b200.index import cell_union_contains
-    loop = synth.wobbly_loop(np.array([0.3, -0.5, 0.8]), 0.17, 10000)
-    lsoup = ShapeSoup(); lsoup.add_polygon([loop])
-    union_ids = build_flat_index(lsoup.freeze(), 32).cell_ids      # covering of the loop: interior + boundary cells
+    union_ids = np.load(os.path.join(ROOT, "tests", "golden", "covering_loop10k.npz"))["cell_ids"].astype(np.uint64)
     d_ids = torch.from_numpy(union_ids.view(np.int64)).to(dev)
-    pts = synth.sphere_points_cuda(n, 2000 + rank, dev)
+    UNION_STREAM = 2000
+    pts = synth.stream_sphere_points_cuda(UNION_STREAM, lo, n, dev)
     res = None
+    hits_dev = torch.zeros(1, dtype=torch.int64, device=dev)
 
     from s2geometry_b200.index import CellUnionIndex
     uq = ContainsPointQuery(CellUnionIndex(union_ids), 1)   # the union replicated on this GPU as an index of interior cells
@@ -568,7 +578,8 @@ def join_section(args, torch, dev, rank, world):
     def ustep():
         nonlocal res
         res = uq.contains(pts)
-        return sdist.sharded_count(0, dev)   # scalar all-reduce inside the step (the hit count is reduced after timing)
+        hits_dev[0] = res.sum(dtype=torch.int64)                # device-side count, no host synchronisation in the step
+        sdist.all_reduce_sum_(hits_dev)
 
     for _ in range(3):
         ustep()
@@ -580,23 +591,27 @@ def join_section(args, torch, dev, rank, world):
     t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
     sdist.all_reduce_max_(t)
     ums = float(t.item())
-    hits = sdist.sharded_count(int(res.sum().item()), dev)
+    hits = int(hits_dev.item())
     same_as_direct_kernel = bool((cell_union_contains(d_ids, pts) == res).all())   # the plain binary-search kernel agrees
     uach = 25 * n_total / world / (ums * 1e-3) / 1e9
-    cu = {"workload": "configs[4]: S2CellUnion (%d cells) containment of %d uniform points over %d GPU(s)" % (len(union_ids), n_total, world),
+    cu = {"workload": "configs[4]: S2CellUnion = S2RegionCoverer(max_cells=1000) covering of the 10k-vertex loop (%d cells, reference-built fixture), containment of %d uniform points (stream %d) over %d GPU(s), global hit count"
+                      % (len(union_ids), n_total, UNION_STREAM, world),
           "scaling": "strong", "points_per_s": n_total / (ums * 1e-3), "ms_per_step": ums, "hits": hits, "bytes_per_point": 25,
           "path": "s2b_index_create_from_cellunion + s2b_contains_dev", "matches_cellunion_kernel": same_as_direct_kernel,
           "roofline": {"bound": "hbm", "achieved": uach, "peak": hbm_peak, "unit": "GB/s", "frac": uach / hbm_peak, "note": "per GPU"}}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline:
         try:
             from oracle import reflib  # cpu_baseline leg
             ref = reflib.load()
-            sample = pts[:20_000_000].cpu().numpy()
+            k = min(n, 20_000_000)
+            sample = pts[:k].cpu().numpy()
             t0 = time.perf_counter(); want = ref.cellunion_contains(union_ids, sample, ref.hardware_threads()); dt = time.perf_counter() - t0
+            cu["parity_vs_reference"] = bool((res[:k].cpu().numpy() == want).all())
             cu["cpu_baseline"] = {"value": len(sample) / dt, "unit": "points/s", "cores": ref.hardware_threads(), "kind": "reference",
-                                  "sample": "first 20M points", "parity_on_sample": bool((res[:20_000_000].cpu().numpy() == want).all())}
+                                  "sample": "first %d points of the global stream" % k, "parity_on_sample": cu["parity_vs_reference"]}
         except Exception as e:
             cu["cpu_baseline"] = {"unavailable": str(e)}
+    sdist.barrier()
     return out, cu
 
 
@@ -612,19 +627,21 @@ def run_gpu(args):
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    numa_node = None
+    from s2geometry_b200 import dist as sdist_
+    placement = sdist_.bind_to_gpu_numa_node(local_rank) if world > 1 else {"bound": False, "why": "single process"}
     if world > 1:
-        from s2geometry_b200 import dist as sdist_
-        numa_node = sdist_.bind_to_gpu_numa_node(local_rank)
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
     n = args.points
-    ll = synth.sphere_latlng_cuda(n, 2 + rank, dev)
+    # this rank's slice of the global lat/lng stream (weak scaling: rank r encodes points [r*n, (r+1)*n))
+    ll = synth.stream_sphere_latlng_cuda(STREAM_LATLNG, rank * n, n, dev)
     ids = torch.empty((len(LEVELS), n), dtype=torch.int64, device=dev)
     tok = torch.empty((n, 16), dtype=torch.uint8, device=dev)
     ln = torch.empty(n, dtype=torch.uint8, device=dev)
 
+    # One step = the strict call (S2B_LATLNG_HOST_LIBM, the default): ONE kernel launch, then the ~1.6e-5 of points whose
+    # leaf cell depends on the libm are re-evaluated with the host's sin/cos inside the call (s2b_encode_latlng_strict_dev).
     def step():
         cellid.from_lat_lng_levels_tokens(ll, LEVELS, TOKEN_LEVEL_INDEX, out_ids=ids, out_tokens=tok, out_len=ln)
 
@@ -641,6 +658,7 @@ def run_gpu(args):
         sampler.start()
         time.sleep(0.3)
     launches0 = _lib.launch_count()
+    cellid.lat_lng_strict_stats(reset=True)
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
     evs[0].record()
@@ -649,8 +667,8 @@ def run_gpu(args):
         evs[k + 1].record()
     barrier()
     launches = _lib.launch_count() - launches0
+    strict_reevaluated, strict_changed = cellid.lat_lng_strict_stats()
     total_ms = evs[0].elapsed_time(evs[-1])
-    per_launch_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -658,38 +676,82 @@ def run_gpu(args):
     clocks = sampler.stop() if rank == 0 else None
     value = world * n / (ms_per_step * 1e-3)
 
-    # ---- end to end through the host-pointer C ABI call with pinned host buffers
-    def run_e2e(m):
-        h_ll = torch.empty((m, 2), dtype=torch.float64, pin_memory=True)
-        h_ll.copy_(ll[:m])
-        h_ids = torch.empty((len(LEVELS), m), dtype=torch.int64, pin_memory=True)
-        h_tok = torch.empty((m, 16), dtype=torch.uint8, pin_memory=True)
-        h_len = torch.empty(m, dtype=torch.uint8, pin_memory=True)
-        a_ll, a_ids, a_tok, a_len = h_ll.numpy(), h_ids.numpy().view(np.uint64), h_tok.numpy(), h_len.numpy()
-        steps = max(1, min(args.steps, 3))
-        cellid.from_lat_lng_levels_tokens(a_ll, LEVELS, TOKEN_LEVEL_INDEX, out_ids=a_ids, out_tokens=a_tok, out_len=a_len)  # warm-up
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            cellid.from_lat_lng_levels_tokens(a_ll, LEVELS, TOKEN_LEVEL_INDEX, out_ids=a_ids, out_tokens=a_tok, out_len=a_len)
-        barrier()
-        return (time.perf_counter() - t0) / steps, h_ids
+    # The dominant kernel alone (roofline.achieved): the same launch through the enqueue-only entry point, CUDA events
+    # on the launching stream around each launch.
+    import ctypes
+    lv = (ctypes.c_int * len(LEVELS))(*LEVELS)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
-    e2e_n = n
-    try:
-        e2e_s, h_ids = run_e2e(e2e_n)
-    except RuntimeError:   # not enough pinnable host memory for the full batch on this box: measure on a quarter of it
-        torch.cuda.empty_cache()
-        e2e_n = n // 4
-        e2e_s, h_ids = run_e2e(e2e_n)
+    def kernel_only():
+        _lib.check(lib.s2b_encode_latlng_levels_tokens_dev(ctypes.c_void_p(ll.data_ptr()), n, lv, len(LEVELS), ctypes.c_void_p(ids.data_ptr()),
+                                                           TOKEN_LEVEL_INDEX, ctypes.c_void_p(tok.data_ptr()), ctypes.c_void_p(ln.data_ptr()), st))
+    for _ in range(3):
+        kernel_only()
+    torch.cuda.synchronize()
+    kevs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    kevs[0].record()
+    for k in range(args.steps):
+        kernel_only()
+        kevs[k + 1].record()
+    torch.cuda.synchronize()
+    per_launch_ms = [kevs[k].elapsed_time(kevs[k + 1]) for k in range(args.steps)]
+    step()   # leave the strict results in ids / tok / ln for the parity check below
+    torch.cuda.synchronize()
+
+    # ---- end to end through the host-pointer C ABI call with pinned host buffers
+    h_ll = torch.empty((n, 2), dtype=torch.float64, pin_memory=True)
+    h_ids = torch.empty((len(LEVELS), n), dtype=torch.int64, pin_memory=True)
+    h_tok = torch.empty((n, 16), dtype=torch.uint8, pin_memory=True)
+    h_len = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    h_ll.copy_(ll)
+    a_ll, a_ids, a_tok, a_len = h_ll.numpy(), h_ids.numpy().view(np.uint64), h_tok.numpy(), h_len.numpy()
+    e2e_steps = max(1, min(args.steps, 3))
+    cellid.from_lat_lng_levels_tokens(a_ll, LEVELS, TOKEN_LEVEL_INDEX, out_ids=a_ids, out_tokens=a_tok, out_len=a_len)  # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        cellid.from_lat_lng_levels_tokens(a_ll, LEVELS, TOKEN_LEVEL_INDEX, out_ids=a_ids, out_tokens=a_tok, out_len=a_len)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * e2e_n / float(t.item())
-    # the e2e result equals the device-resident result
-    same = bool((h_ids[2, :1_000_000].to(dev) == ids[2, :1_000_000]).all())
-    del h_ids
+    e2e_s = float(t.item())
+    e2e_value = world * n / e2e_s
+    # the e2e result equals the device-resident result (every id of every level)
+    same = bool((h_ids.to(dev) == ids).all())
 
+    # Host-link ceiling for the same bytes: every rank at once copies the step's input H2D and the step's outputs D2H
+    # with plain cudaMemcpyAsync (one call per array, two streams, nothing else): what the host side of this box can move.
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def copies_only():
+        with torch.cuda.stream(s_in):
+            ll.copy_(h_ll, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            h_ids.copy_(ids, non_blocking=True); h_tok.copy_(tok, non_blocking=True); h_len.copy_(ln, non_blocking=True)
+    copies_only(); barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        copies_only()
+    barrier()
+    link_s = (time.perf_counter() - t0) / e2e_steps
+    t = torch.tensor([link_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    link_s = float(t.item())
+    e2e_bytes = (16 + 8 * len(LEVELS) + 17) * n
+    host_link = {"points_per_s": world * n / link_s, "ms_per_step": 1e3 * link_s, "gb_per_s_all_ranks": world * e2e_bytes / link_s / 1e9,
+                 "e2e_fraction_of_ceiling": link_s / e2e_s,
+                 "how": "same bytes per rank, plain cudaMemcpyAsync H2D (input) and D2H (outputs) on two streams, all ranks at once"}
+    del h_ll, h_ids, h_tok, h_len, a_ll, a_ids, a_tok, a_len
+
+    headline_cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            headline_cpu = cpu_baseline(ll, ids, tok, ln)
+        except Exception as e:  # the oracle library is test infrastructure; its absence must not hide the GPU number
+            headline_cpu = {"value": None, "unit": "points/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
     del ids, tok, ln, ll
     torch.cuda.empty_cache()
     pip = None
@@ -739,42 +801,65 @@ def run_gpu(args):
         if lib.s2b_diag_fp64_peak(_lib.ctypes.byref(dfma)) == 0 and dfma.value > 0:
             fp64_ach = FP64_INSTR_PER_POINT * n / (kern_ms * 1e-3)
             fp64 = {"peak_dfma_per_s": dfma.value, "peak_tflops": 2 * dfma.value / 1e12, "fp64_instr_per_point": FP64_INSTR_PER_POINT,
-                    "achieved_instr_per_s": fp64_ach, "frac": fp64_ach / dfma.value, "peak_source": "measured live (s2b_diag_fp64_peak)"}
+                    "fp64_instr_source": PROFILE_SOURCE, "achieved_instr_per_s": fp64_ach, "frac": fp64_ach / dfma.value,
+                    "peak_source": "measured live (s2b_diag_fp64_peak)"}
+
+        def brief(sec, *path):
+            try:
+                for k in path:
+                    sec = sec[k]
+                return sec
+            except Exception:
+                return None
+
+        def gpts(v):
+            return None if v is None else round(v / 1e9, 2)
+
+        def frac(v):
+            return None if v is None else round(v, 3)
+        # compact secondary results in a key the driver keeps (the full sections follow at the end of the line)
+        summary = {
+            "encode_latlng_Gpts": gpts(value), "encode_latlng_hbm_frac": frac(achieved / hbm_peak), "encode_latlng_fp64_frac": frac(brief(fp64, "frac")),
+            "encode_latlng_parity": brief(headline_cpu, "parity_on_sample"),
+            "strict_reevaluated_per_step": strict_reevaluated / max(1, args.steps), "strict_changed_per_step": strict_changed / max(1, args.steps),
+            "encode_xyz_Gpts": gpts(brief(enc_xyz, "points_per_s")), "encode_xyz_hbm_frac": frac(brief(enc_xyz, "roofline", "frac")),
+            "pip_uniform_Gpts": gpts(brief(pip, "uniform", "points_per_s")), "pip_uniform_hbm_frac": frac(brief(pip, "uniform", "roofline", "frac")),
+            "pip_near_Gpts": gpts(brief(pip, "near", "points_per_s")), "pip_near_hbm_frac": frac(brief(pip, "near", "roofline", "frac")),
+            "pip_parity": None if brief(pip, "cpu_baseline", "uniform") is None else bool(brief(pip, "cpu_baseline", "uniform", "parity_on_sample") and brief(pip, "cpu_baseline", "near", "parity_on_sample")),
+            "join_Gpts": gpts(brief(join, "points_per_s")), "join_hbm_frac": frac(brief(join, "roofline", "frac")),
+            "join_total_hits": brief(join, "total_hits"), "join_histogram_checksum": brief(join, "histogram_checksum"),
+            "join_parity": brief(join, "parity_vs_reference"),
+            "cellunion_Gpts": gpts(brief(cellunion, "points_per_s")), "cellunion_hbm_frac": frac(brief(cellunion, "roofline", "frac")),
+            "cellunion_hits": brief(cellunion, "hits"), "cellunion_parity": brief(cellunion, "parity_vs_reference"),
+            "cell_index_join_Gpts": gpts(brief(cell_index_join, "points_per_s")), "cell_index_join_hbm_frac": frac(brief(cell_index_join, "roofline", "frac")),
+        }
         line = {
             "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "configs[1]: 100M lat/lng (radians, uniform on sphere) per GPU -> S2CellId at levels 12/20/30 + ToToken(level 30)",
+            "config": {"workload": WORKLOAD,
                        "points_per_gpu": n, "levels": LEVELS, "l2_policy": "inputs (1.6 GB) and outputs (4.1 GB) per step exceed the 126 MB L2",
-                       "kernel": "encode_kernel<latlng> (1 launch per step: fast sin/cos filter + correctly rounded path for boundary-sensitive points, fused parent/ToToken epilogues)"},
+                       "input": "counter-based stream %d, rank r encodes points [r*n, (r+1)*n) (s2geometry_b200/synth.py)" % STREAM_LATLNG,
+                       "step": "s2b_encode_latlng_strict_dev: encode_kernel<latlng> (1 launch: fast sin/cos filter + correctly rounded path for boundary-sensitive points, fused parent/ToToken epilogues) + host-libm re-evaluation of the libm-sensitive points (S2B_LATLNG_HOST_LIBM)",
+                       "summary": summary},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from ncu --set full
-                         # (profiles/r1_encode_latlng_final_ncu.json: 54.1 B/point at 20M points), scaled to this launch
-                         "traffic": 54.14 * n, "traffic_unit": "bytes per launch (ncu dram read+write, 54.14 B/point)", "peak_source": peak_src, "bytes_per_point": BYTES_PER_POINT, "kernel_ms": kern_ms, "fp64": fp64},
-            "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": 16 * e2e_n, "d2h_bytes_per_step": (8 * len(LEVELS) + 17) * e2e_n, "points_per_gpu": e2e_n,
-                    "ms_per_step": 1e3 * float(t.item()), "matches_device_result": same, "numa_node_rank0": numa_node},
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from ncu --set full, scaled to this launch
+                         "traffic": DRAM_BYTES_PER_POINT * n, "traffic_source": "profile: " + PROFILE_SOURCE,
+                         "traffic_unit": "bytes per launch (ncu dram read+write, %.2f B/point)" % DRAM_BYTES_PER_POINT,
+                         "peak_source": peak_src, "bytes_per_point": BYTES_PER_POINT, "kernel_ms": kern_ms,
+                         "kernel": "encode_kernel<latlng,3 levels,token>, timed alone (enqueue-only entry point, CUDA events per launch)",
+                         "fp64": fp64},
+            "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": (8 * len(LEVELS) + 17) * n, "points_per_gpu": n,
+                    "ms_per_step": 1e3 * e2e_s, "matches_device_result": same, "host_link_ceiling": host_link, "host_placement": placement},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        if enc_xyz is not None:
-            line["encode_xyz"] = enc_xyz
-        if pip is not None:
-            line["pip"] = pip
-        if join is not None:
-            line["join"] = join
-        if cellunion is not None:
-            line["cellunion"] = cellunion
-        if radius_join is not None:
-            line["radius_join"] = radius_join
-        if cell_index_join is not None:
-            line["cell_index_join"] = cell_index_join
-        if region_cells is not None:
-            line["region_cells"] = region_cells
-        if world == 1 and not args.no_cpu_baseline:
-            try:
-                line["cpu_baseline"] = cpu_baseline()
-            except Exception as e:  # the oracle library is test infrastructure; its absence must not hide the GPU number
-                line["cpu_baseline"] = {"value": None, "unit": "points/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
+        if headline_cpu is not None:
+            line["cpu_baseline"] = headline_cpu
+        for name, sec in (("encode_xyz", enc_xyz), ("pip", pip), ("join", join), ("cellunion", cellunion), ("radius_join", radius_join),
+                          ("cell_index_join", cell_index_join), ("region_cells", region_cells)):
+            if sec is not None:
+                line[name] = sec
         _emit(line)
     if world > 1:
         dist.destroy_process_group()

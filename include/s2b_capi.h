@@ -64,6 +64,17 @@ int s2b_diag_force_correctly_rounded(int on);
 int s2b_diag_filter_deviation_dev(int input_kind, const double* in_dev, size_t n, double* max_deviation_out,
                                   uint64_t* unflagged_face_flips_out, void* stream);
 
+/* Benchmark / test support: counter-based synthetic inputs. Point i of the stream `seed` is a pure
+ * function of (seed, first_index + i) built from integer hashing and + - * / sqrt only, so any host (NumPy restatement:
+ * s2geometry_b200/synth.py) and any GPU produce the same bits; ranks generate their slice of one global stream.
+ *   sphere_points: uniform on the unit sphere (Marsaglia), n x 3 doubles
+ *   sphere_latlng: (lat, lng) radians, uniform on the sphere, n x 2 doubles
+ *   cap_points:    uniform in the cap of height `height` = 1 - cos(radius) around frame9[6..8]; frame9 = orthonormal x, y, z rows */
+int s2b_synth_sphere_points_dev(uint64_t seed, uint64_t first_index, size_t n, double* xyz_out_dev, void* stream);
+int s2b_synth_sphere_latlng_dev(uint64_t seed, uint64_t first_index, size_t n, double* latlng_out_dev, void* stream);
+int s2b_synth_cap_points_dev(uint64_t seed, uint64_t first_index, size_t n, const double* frame9, double height,
+                             double* xyz_out_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Cell-id encoding.  Replaces the per-point constructors
  *   S2CellId::S2CellId(const S2Point&)   s2cell_id.cc:309-315  (XYZtoFaceUV s2coords.h:389-419,
@@ -75,9 +86,31 @@ int s2b_diag_filter_deviation_dev(int input_kind, const double* in_dev, size_t n
 int s2b_encode_points(const double* xyz, size_t n, int level, uint64_t* ids_out);
 int s2b_encode_points_dev(const double* xyz_dev, size_t n, int level, uint64_t* ids_out_dev, void* stream);
 
-/* lat/lng in radians. sin/cos are evaluated on the device, correctly rounded (DESIGN.md "lat/lng").
- * boundary_flag_out (nullable): 1 where a ±1-ulp change of sin/cos results could move the leaf cell, i.e.
- * where a host libm that is not correctly rounded (glibc: ~0.13% of arguments) may legitimately differ. */
+/* lat/lng in radians. S2LatLng::ToPoint calls the platform libm's sin and cos (s2latlng.cc:68-77, s1angle.h:343-357), so
+ * the reference's id for a point within ~1e-6 leaf cells of a cell boundary depends on which libm ran (glibc is < 1 ulp
+ * but not correctly rounded for ~0.13% of arguments). Two modes, process-wide (s2b_set_latlng_mode):
+ *   S2B_LATLNG_HOST_LIBM (default)  ids equal the reference's evaluated in the CALLING PROCESS, bit for bit, for every
+ *       input: the device evaluates correctly rounded sin/cos and hands back every point whose leaf cell could change
+ *       under a <= 1 ulp change of a sin/cos value (~1.6e-5 of uniform input; plus angles with |x| >= 2^20 or non-finite);
+ *       exactly those points are re-evaluated with this process's sin/cos before the call returns. Applies to the
+ *       host-pointer calls and to s2b_encode_latlng_strict_dev.
+ *   S2B_LATLNG_CORRECTLY_ROUNDED    ids are those of correctly rounded sin/cos: platform independent, device only.
+ * The plain `_dev` calls only enqueue work and therefore always produce the correctly rounded ids; boundary_flag_out
+ * (nullable, all forms): 1 where a ±1-ulp change of a sin/cos result could move the leaf cell, i.e. exactly the points
+ * the strict mode re-evaluates. */
+#define S2B_LATLNG_HOST_LIBM 0
+#define S2B_LATLNG_CORRECTLY_ROUNDED 1
+/* Returns the previous mode (or S2B_EINVAL). */
+int s2b_set_latlng_mode(int mode);
+/* Points re-evaluated on the host by the strict mode, and how many of them changed id, since the last reset. */
+int s2b_latlng_strict_stats(uint64_t* reevaluated_out, uint64_t* changed_out, int reset);
+/* Device-pointer encode with the strict guarantee: input_kind 1 = (lat, lng) radian pairs, 2 = E7 int32 pairs; outputs
+ * as s2b_encode_latlng_levels_tokens_dev (boundary_flag_out_dev, tokens16_out_dev / len_out_dev nullable; no token when
+ * token_level_index < 0). In S2B_LATLNG_HOST_LIBM mode it SYNCHRONISES `stream`: kernel -> list of sensitive points
+ * (32 bytes each) to the host -> host sin/cos -> the ids that differ are patched on the device. */
+int s2b_encode_latlng_strict_dev(int input_kind, const void* latlng_dev, size_t n, const int* levels, int num_levels,
+                                 uint64_t* ids_out_dev, uint8_t* boundary_flag_out_dev, int token_level_index,
+                                 char* tokens16_out_dev, uint8_t* len_out_dev, void* stream);
 int s2b_encode_latlng(const double* latlng_rad, size_t n, int level, uint64_t* ids_out, uint8_t* boundary_flag_out);
 int s2b_encode_latlng_dev(const double* latlng_rad_dev, size_t n, int level, uint64_t* ids_out_dev,
                           uint8_t* boundary_flag_out_dev, void* stream);

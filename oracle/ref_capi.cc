@@ -732,6 +732,20 @@ size_t ref_cover_cap(const double* center, double radius_rad, int max_cells, int
   return k;
 }
 
+// S2RegionCoverer(max_cells).GetCovering(S2ShapeIndexRegion(index)) with default levels (s2region_coverer.h:106):
+// BASELINE configs[4]'s "S2RegionCoverer covering (max 1000 cells)". Returns the number of cells.
+size_t ref_index_covering(void* h, int max_cells, uint64_t* out, size_t capacity) {
+  auto& index = ((RefIndex*)h)->index;
+  S2ShapeIndexRegion<MutableS2ShapeIndex> region(&index);
+  S2RegionCoverer::Options opt;
+  opt.set_max_cells(max_cells);
+  S2RegionCoverer coverer(opt);
+  S2CellUnion u = coverer.GetCovering(region);
+  size_t k = 0;
+  for (S2CellId id : u.cell_ids()) { if (k < capacity) out[k] = id.id(); ++k; }
+  return k;
+}
+
 // S2RegionCoverer::GetCovering(S2ShapeIndexRegion) with min_level = max_level = level; returns the number of cells.
 size_t ref_region_covering(void* h, int level, uint64_t* out, size_t capacity) {
   auto& index = ((RefIndex*)h)->index;

@@ -347,6 +347,14 @@ class RefIndex:
         self.lib.ref_region_covering(_vp(self.h), int(level), _p(out), _sz(n))
         return out[:n]
 
+    def covering(self, max_cells):
+        """S2RegionCoverer(max_cells).GetCovering(S2ShapeIndexRegion(index)) -> sorted cell ids (an S2CellUnion)."""
+        self.lib.ref_index_covering.restype = _sz
+        out = np.zeros(4 * max_cells + 64, np.uint64)
+        n = int(self.lib.ref_index_covering(_vp(self.h), int(max_cells), _p(out), _sz(out.size)))
+        assert n <= out.size
+        return out[:n].copy()
+
     def region_intersecting_shapes(self, ids):
         """S2ShapeIndexRegion::VisitIntersectingShapeIds per target: (offsets, shape ids, contains flags), sorted by shape id."""
         ids = np.ascontiguousarray(ids, np.uint64)

@@ -21,6 +21,12 @@ SIGNATURES = {
     "s2b_diag_fp64_peak": (_i, [_vp]),
     "s2b_diag_force_correctly_rounded": (_i, [_i]),
     "s2b_diag_filter_deviation_dev": (_i, [_i, _vp, _sz, _vp, _vp, _vp]),
+    "s2b_synth_sphere_points_dev": (_i, [_u64, _u64, _sz, _vp, _vp]),
+    "s2b_synth_sphere_latlng_dev": (_i, [_u64, _u64, _sz, _vp, _vp]),
+    "s2b_synth_cap_points_dev": (_i, [_u64, _u64, _sz, _vp, _c.c_double, _vp, _vp]),
+    "s2b_set_latlng_mode": (_i, [_i]),
+    "s2b_latlng_strict_stats": (_i, [_vp, _vp, _i]),
+    "s2b_encode_latlng_strict_dev": (_i, [_i, _vp, _sz, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "s2b_encode_points": (_i, [_vp, _sz, _i, _vp]),
     "s2b_encode_points_dev": (_i, [_vp, _sz, _i, _vp, _vp]),
     "s2b_encode_latlng": (_i, [_vp, _sz, _i, _vp, _vp]),

@@ -56,6 +56,32 @@ def _levels_arg(levels):
     return (ctypes.c_int * len(lv))(*lv), len(lv)
 
 
+LATLNG_HOST_LIBM, LATLNG_CORRECTLY_ROUNDED = 0, 1   # include/s2b_capi.h
+
+
+def set_lat_lng_mode(mode):
+    """Process-wide definition of S2CellId(S2LatLng): LATLNG_HOST_LIBM (default; ids equal the reference's evaluated
+    with this process's libm, bit for bit) or LATLNG_CORRECTLY_ROUNDED (platform independent). Returns the old mode."""
+    old = _lib.load().s2b_set_latlng_mode(int(mode))
+    if old < 0:
+        _lib.check(old)
+    return old
+
+
+def lat_lng_strict_stats(reset=False):
+    """(points re-evaluated with the host libm, points whose id changed) since the last reset."""
+    a, b = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    _lib.check(_lib.load().s2b_latlng_strict_stats(ctypes.byref(a), ctypes.byref(b), 1 if reset else 0))
+    return int(a.value), int(b.value)
+
+
+def _strict_dev(lib, kind, ll, n, lv, nl, ids, flags, token_level_index, tok, ln):
+    # device path with the host-libm guarantee: synchronises the current stream (s2b_encode_latlng_strict_dev)
+    _lib.check(lib.s2b_encode_latlng_strict_dev(kind, _ptr(ll), n, lv, nl, _ptr(ids), _ptr(flags) if flags is not None else None,
+                                                int(token_level_index), _ptr(tok) if tok is not None else None,
+                                                _ptr(ln) if ln is not None else None, _stream()))
+
+
 def from_points(xyz, level=30):
     """S2CellId(S2Point) for every row of xyz (N,3) float64 -> uint64 ids at `level` (int64 tensor on the device path)."""
     lib = _lib.load()
@@ -80,8 +106,8 @@ def from_lat_lng(latlng_rad, level=30, return_boundary_flags=False):
         out = torch.empty(n, dtype=torch.int64, device=ll.device)
         flags = torch.empty(n, dtype=torch.uint8, device=ll.device) if return_boundary_flags else None
         with torch.cuda.device(ll.device):
-            _lib.check(lib.s2b_encode_latlng_dev(_ptr(ll), n, int(level), _ptr(out),
-                                                 _ptr(flags) if flags is not None else None, _stream()))
+            lv, nl = _levels_arg([level])
+            _strict_dev(lib, 1, ll, n, lv, nl, out, flags, -1, None, None)
         return (out, flags) if return_boundary_flags else out
     ll = _np_in(latlng_rad, np.float64, 2)
     n = ll.shape[0]
@@ -98,7 +124,8 @@ def from_lat_lng_e7(latlng_e7, level=30):
         ll = _tensor_in(latlng_e7, torch.int32, 2)
         out = torch.empty(ll.shape[0], dtype=torch.int64, device=ll.device)
         with torch.cuda.device(ll.device):
-            _lib.check(lib.s2b_encode_latlng_e7_dev(_ptr(ll), ll.shape[0], int(level), _ptr(out), None, _stream()))
+            lv, nl = _levels_arg([level])
+            _strict_dev(lib, 2, ll, ll.shape[0], lv, nl, out, None, -1, None, None)
         return out
     ll = _np_in(latlng_e7, np.int32, 2)
     out = np.empty(ll.shape[0], dtype=np.uint64)
@@ -116,7 +143,7 @@ def from_lat_lng_levels(latlng_rad, levels, out=None):
         if out is None:
             out = torch.empty((nl, n), dtype=torch.int64, device=ll.device)
         with torch.cuda.device(ll.device):
-            _lib.check(lib.s2b_encode_latlng_levels_dev(_ptr(ll), n, lv, nl, _ptr(out), _stream()))
+            _strict_dev(lib, 1, ll, n, lv, nl, out, None, -1, None, None)
         return out
     ll = _np_in(latlng_rad, np.float64, 2)
     n = ll.shape[0]
@@ -138,8 +165,7 @@ def from_lat_lng_levels_tokens(latlng_rad, levels, token_level_index, out_ids=No
         tok = out_tokens if out_tokens is not None else torch.empty((n, 16), dtype=torch.uint8, device=ll.device)
         ln = out_len if out_len is not None else torch.empty(n, dtype=torch.uint8, device=ll.device)
         with torch.cuda.device(ll.device):
-            _lib.check(lib.s2b_encode_latlng_levels_tokens_dev(_ptr(ll), n, lv, nl, _ptr(ids), int(token_level_index),
-                                                               _ptr(tok), _ptr(ln), _stream()))
+            _strict_dev(lib, 1, ll, n, lv, nl, ids, None, token_level_index, tok, ln)
         return ids, tok, ln
     ll = _np_in(latlng_rad, np.float64, 2)
     n = ll.shape[0]

@@ -7,9 +7,11 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/s2b_capi.h"
+#include "s2b_core.cuh"
 #include "s2b_hilbert.h"
 #include "s2b_internal.h"
 
@@ -18,6 +20,8 @@ namespace s2b {
 static thread_local char t_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_force_cr{0};
+static std::atomic<int> g_latlng_mode{S2B_LATLNG_HOST_LIBM};
+static std::atomic<uint64_t> g_strict_reevaluated{0}, g_strict_changed{0};
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
@@ -109,9 +113,15 @@ constexpr size_t kChunk = size_t(1) << 22;  // points per chunk (4 Mi): 64-100 M
 // number of arrays laid out n apart on the host but chunk-size apart in the device slot.
 struct OutSpec { void* host; size_t bytes_per_point; int arrays; };
 
+struct NoChunkHook {
+  int operator()(int, size_t, size_t, const void*, void**, cudaStream_t) const { return S2B_OK; }
+};
+
 // launch(in_dev, count, out_dev[], stream): out_dev[j] points at the slot region for OutSpec j.
-template <class Launch>
-int run_pipelined(const void* in_host, size_t in_bpp, size_t n, const OutSpec* outs, int n_outs, Launch launch) {
+// done(slot, off, count, in_dev, out_dev[], stream) runs on the host once chunk [off, off + count) has fully landed in
+// the caller's buffers (its slot stream is idle and its device buffers are still intact), in chunk order.
+template <class Launch, class Done = NoChunkHook>
+int run_pipelined(const void* in_host, size_t in_bpp, size_t n, const OutSpec* outs, int n_outs, Launch launch, Done done = Done()) {
   int dev = 0;
   S2B_CUDA(cudaGetDevice(&dev));
   size_t chunk = n < kChunk ? n : kChunk;
@@ -132,20 +142,37 @@ int run_pipelined(const void* in_host, size_t in_bpp, size_t n, const OutSpec* o
     cudaError_t e__ = (call);                                                   \
     if (e__ != cudaSuccess) return drain_and_return(cuda_fail(e__, #call));     \
   } while (0)
-  size_t k = 0;
-  for (size_t off = 0; off < n; off += chunk, ++k) {
-    Slot& s = t_ws.slot[k % 3];
-    size_t cnt = n - off < chunk ? n - off : chunk;
-    // the slot's previous D2H must have drained before its buffers are reused
-    if (k >= 3) S2B_CUDA_DRAIN(cudaStreamSynchronize(s.stream));
-    S2B_CUDA_DRAIN(cudaMemcpyAsync(s.in, (const char*)in_host + off * in_bpp, cnt * in_bpp, cudaMemcpyHostToDevice, s.stream));
-    void* out_dev[4] = {nullptr, nullptr, nullptr, nullptr};
+  struct Pending { bool live = false; size_t off = 0, cnt = 0; } pending[3];
+  auto slot_regions = [&](Slot& s, void** out_dev) {
     char* cur = (char*)s.out;
     for (int j = 0; j < n_outs; ++j) {
       out_dev[j] = cur;
       cur += region(j);
     }
-    int lrc = launch(s.in, cnt, out_dev, s.stream);
+  };
+  auto complete = [&](int si) -> int {   // slot stream already synchronised
+    if (!pending[si].live) return S2B_OK;
+    pending[si].live = false;
+    void* out_dev[4] = {nullptr, nullptr, nullptr, nullptr};
+    slot_regions(t_ws.slot[si], out_dev);
+    return done(si, pending[si].off, pending[si].cnt, t_ws.slot[si].in, out_dev, t_ws.slot[si].stream);
+  };
+  size_t k = 0;
+  for (size_t off = 0; off < n; off += chunk, ++k) {
+    const int si = (int)(k % 3);
+    Slot& s = t_ws.slot[si];
+    size_t cnt = n - off < chunk ? n - off : chunk;
+    // the slot's previous D2H must have drained before its buffers are reused
+    if (k >= 3) {
+      S2B_CUDA_DRAIN(cudaStreamSynchronize(s.stream));
+      int drc = complete(si);
+      if (drc != S2B_OK) return drain_and_return(drc);
+    }
+    S2B_CUDA_DRAIN(cudaMemcpyAsync(s.in, (const char*)in_host + off * in_bpp, cnt * in_bpp, cudaMemcpyHostToDevice, s.stream));
+    void* out_dev[4] = {nullptr, nullptr, nullptr, nullptr};
+    slot_regions(s, out_dev);
+    pending[si].live = true; pending[si].off = off; pending[si].cnt = cnt;
+    int lrc = launch(si, s.in, cnt, out_dev, s.stream);
     if (lrc != S2B_OK) return drain_and_return(lrc);
     for (int j = 0; j < n_outs; ++j) {
       if (!outs[j].host) continue;
@@ -157,7 +184,13 @@ int run_pipelined(const void* in_host, size_t in_bpp, size_t n, const OutSpec* o
       }
     }
   }
-  for (Slot& s : t_ws.slot) S2B_CUDA_DRAIN(cudaStreamSynchronize(s.stream));
+  // drain in chunk order: the oldest pending chunk sits in slot k % 3
+  for (size_t d = 0; d < 3; ++d) {
+    const int si = (int)((k + d) % 3);
+    S2B_CUDA_DRAIN(cudaStreamSynchronize(t_ws.slot[si].stream));
+    int drc = complete(si);
+    if (drc != S2B_OK) return drain_and_return(drc);
+  }
 #undef S2B_CUDA_DRAIN
   return S2B_OK;
 }
@@ -173,6 +206,147 @@ static int check_levels(const int* levels, int num_levels, LevelSpec* out) {
   return S2B_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Strict host-libm mode for lat/lng input (S2B_LATLNG_HOST_LIBM, the default).
+//
+// S2CellId(S2LatLng) is defined through the platform libm: S2LatLng::ToPoint calls sin and cos (s2latlng.cc:68-77,
+// s1angle.h:343-357). glibc's are accurate to < 1 ulp but not correctly rounded, so for a few points in 10^5 the leaf
+// cell depends on WHICH libm ran. The device cannot know that; it evaluates the correctly rounded values and reports every
+// point whose leaf cell could move under a <= 1 ulp change of one of its four sin/cos values (kFlagTolIj: 3.5x margin
+// over the propagated bound, s2b_sincos.cuh) plus every angle outside the device routines' domain. Those points — and
+// only those — are re-evaluated here with the calling process's sin/cos and the same IEEE projection, which by
+// construction is the value the reference computes in this process. Everything else is provably libm-independent.
+struct FixBuf {
+  FixRecord* d_list = nullptr;
+  uint32_t* d_count = nullptr;
+  FixPatch* d_patch = nullptr;
+  FixRecord* h_list = nullptr;   // pinned
+  uint32_t* h_count = nullptr;   // pinned
+  uint32_t cap = 0, patch_cap = 0;
+  int device = -1;
+  void release() {
+    if (d_list) cudaFree(d_list);
+    if (d_count) cudaFree(d_count);
+    if (d_patch) cudaFree(d_patch);
+    if (h_list) cudaFreeHost(h_list);
+    if (h_count) cudaFreeHost(h_count);
+    *this = FixBuf();
+  }
+  int ensure(int dev, uint32_t want) {
+    if (device == dev && cap >= want) return S2B_OK;
+    release();
+    device = dev;
+    S2B_CUDA(cudaMalloc(&d_list, sizeof(FixRecord) * (size_t)want));
+    S2B_CUDA(cudaMalloc(&d_count, sizeof(uint32_t)));
+    S2B_CUDA(cudaMallocHost(&h_list, sizeof(FixRecord) * (size_t)want));
+    S2B_CUDA(cudaMallocHost(&h_count, sizeof(uint32_t)));
+    cap = want;
+    return S2B_OK;
+  }
+  int ensure_patches(uint32_t want) {
+    if (patch_cap >= want) return S2B_OK;
+    if (d_patch) cudaFree(d_patch);
+    d_patch = nullptr; patch_cap = 0;
+    S2B_CUDA(cudaMalloc(&d_patch, sizeof(FixPatch) * (size_t)want));
+    patch_cap = want;
+    return S2B_OK;
+  }
+};
+static thread_local FixBuf t_fix_slot[3];   // host-pointer pipeline: one per slot
+static thread_local FixBuf t_fix_dev;       // s2b_encode_latlng_strict_dev
+
+// S2CellId(S2LatLng::FromRadians(lat, lng)) with THIS process's libm: S2LatLng::ToPoint (s2latlng.cc:68-77; SinCos() =
+// {sin(x), cos(x)}, s1angle.h:343-357) then S2CellId(S2Point) (s2cell_id.cc:309-315). Only ever applied to the
+// boundary-sensitive points the device hands back.
+static uint64_t leaf_id_host_libm(double lat, double lng) {
+  const double sin_phi = sin(lat), cos_phi = cos(lat);
+  const double sin_theta = sin(lng), cos_theta = cos(lng);
+  const P3 p{cos_theta * cos_phi, sin_theta * cos_phi, sin_phi};
+  return cellid_from_point(p, kHilbert.pos);
+}
+
+// Re-evaluates `c` records and appends the ones whose leaf id changes.
+static void reevaluate(const FixRecord* recs, size_t c, std::vector<FixPatch>* changed) {
+  g_strict_reevaluated.fetch_add(c, std::memory_order_relaxed);
+  const size_t before = changed->size();
+  unsigned hw = std::thread::hardware_concurrency();
+  const size_t threads = c < (1u << 15) ? 1 : (hw ? (hw > 32 ? 32 : hw) : 1);
+  if (threads <= 1) {
+    for (size_t i = 0; i < c; ++i) {
+      const uint64_t id = leaf_id_host_libm(recs[i].lat, recs[i].lng);
+      if (id != recs[i].id) changed->push_back(FixPatch{recs[i].index, id});
+    }
+  } else {   // degenerate input (e.g. every point on a cell boundary): spread the libm calls over the host cores
+    std::vector<std::vector<FixPatch>> part(threads);
+    std::vector<std::thread> pool;
+    for (size_t t = 0; t < threads; ++t)
+      pool.emplace_back([&, t] {
+        for (size_t i = c * t / threads; i < c * (t + 1) / threads; ++i) {
+          const uint64_t id = leaf_id_host_libm(recs[i].lat, recs[i].lng);
+          if (id != recs[i].id) part[t].push_back(FixPatch{recs[i].index, id});
+        }
+      });
+    for (auto& th : pool) th.join();
+    for (auto& v : part) changed->insert(changed->end(), v.begin(), v.end());
+  }
+  g_strict_changed.fetch_add(changed->size() - before, std::memory_order_relaxed);
+}
+
+// Gathers the patches of points [0, n) of a device-resident batch. `o` describes where the kernel writes (device
+// pointers; fix fields are filled in here). launched: the full-range kernel already ran with fb's list attached and
+// *fb.h_count holds its counter (records beyond `have` still to be fetched). Synchronises `st`.
+static int collect_patches(InputKind kind, const void* in_dev, size_t in_bpp, size_t n, EncodeOut o, cudaStream_t st, FixBuf& fb,
+                           bool launched, uint32_t have, std::vector<FixPatch>* changed) {
+  const size_t stride = o.ids_stride ? o.ids_stride : n;
+  const uint64_t base = o.index_base;
+  o.ids_stride = stride;
+  o.fix_list = fb.d_list; o.fix_count = fb.d_count; o.fix_cap = fb.cap;
+  if (!launched) {
+    S2B_CUDA(cudaMemsetAsync(fb.d_count, 0, sizeof(uint32_t), st));
+    cudaError_t e = launch_encode(kind, in_dev, n, o, st);
+    if (e != cudaSuccess) return cuda_fail(e, "encode launch");
+    S2B_CUDA(cudaMemcpyAsync(fb.h_count, fb.d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    S2B_CUDA(cudaStreamSynchronize(st));
+    have = 0;
+  }
+  const uint32_t c = *fb.h_count;
+  if (c <= fb.cap) {
+    if (c > have) {
+      S2B_CUDA(cudaMemcpyAsync(fb.h_list + have, fb.d_list + have, sizeof(FixRecord) * (size_t)(c - have), cudaMemcpyDeviceToHost, st));
+      S2B_CUDA(cudaStreamSynchronize(st));
+    }
+    reevaluate(fb.h_list, c, changed);
+    return S2B_OK;
+  }
+  // More sensitive points than the list holds (input concentrated on cell boundaries): redo the range in pieces of
+  // fb.cap points, each of which fits by construction. The kernel rewrites identical outputs.
+  for (size_t off = 0; off < n; off += fb.cap) {
+    const size_t cnt = n - off < fb.cap ? n - off : fb.cap;
+    EncodeOut q = o;
+    q.ids = o.ids + off;
+    q.flags = o.flags ? o.flags + off : nullptr;
+    q.tokens16 = o.tokens16 ? o.tokens16 + 16 * off : nullptr;
+    q.token_len = o.token_len ? o.token_len + off : nullptr;
+    q.index_base = base + off;
+    S2B_CUDA(cudaMemsetAsync(fb.d_count, 0, sizeof(uint32_t), st));
+    cudaError_t e = launch_encode(kind, (const char*)in_dev + off * in_bpp, cnt, q, st);
+    if (e != cudaSuccess) return cuda_fail(e, "encode launch");
+    S2B_CUDA(cudaMemcpyAsync(fb.h_count, fb.d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    S2B_CUDA(cudaStreamSynchronize(st));
+    const uint32_t cc = *fb.h_count;
+    if (cc == 0) continue;
+    S2B_CUDA(cudaMemcpyAsync(fb.h_list, fb.d_list, sizeof(FixRecord) * (size_t)cc, cudaMemcpyDeviceToHost, st));
+    S2B_CUDA(cudaStreamSynchronize(st));
+    reevaluate(fb.h_list, cc, changed);
+  }
+  return S2B_OK;
+}
+
+static bool strict_latlng(InputKind kind) { return kind != kInXYZ && g_latlng_mode.load() == S2B_LATLNG_HOST_LIBM; }
+
+constexpr uint32_t kFixCapChunk = 1u << 16;   // list capacity per 4Mi-point chunk of the host pipeline (1000x the uniform rate)
+constexpr uint32_t kFixEager = 1u << 12;      // records copied back with the chunk without waiting for the count
+
 // tok_level_index < 0: no tokens.
 static int encode_host(InputKind kind, const void* in, size_t in_bpp, size_t n, const int* levels, int num_levels,
                        uint64_t* ids_out, uint8_t* flags_out, int tok_level_index = -1, char* tok_out = nullptr,
@@ -183,8 +357,16 @@ static int encode_host(InputKind kind, const void* in, size_t in_bpp, size_t n, 
   if (tok_level_index >= num_levels) return set_error(S2B_EINVAL, "token_level_index out of range");
   if (n == 0) return S2B_OK;
   if (!in || !ids_out || (tok_level_index >= 0 && !tok_out)) return set_error(S2B_EINVAL, "null input or output pointer");
-  OutSpec outs[4] = {{ids_out, 8, num_levels}, {flags_out, 1, 1}, {tok_out, 16, 1}, {tok_len_out, 1, 1}};
-  return run_pipelined(in, in_bpp, n, outs, 4, [&](const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
+  const bool strict = strict_latlng(kind);
+  if (strict) {
+    int dev = 0;
+    S2B_CUDA(cudaGetDevice(&dev));
+    for (FixBuf& fb : t_fix_slot) {
+      rc = fb.ensure(dev, kFixCapChunk);
+      if (rc) return rc;
+    }
+  }
+  auto make_out = [&](void** out_dev) {
     EncodeOut o;
     o.levels = lv;
     o.ids = (uint64_t*)out_dev[0];
@@ -193,14 +375,53 @@ static int encode_host(InputKind kind, const void* in, size_t in_bpp, size_t n, 
     o.tokens16 = tok_level_index >= 0 ? (char*)out_dev[2] : nullptr;
     o.token_len = tok_level_index >= 0 && tok_len_out ? (uint8_t*)out_dev[3] : nullptr;
     o.force_cr = g_force_cr.load();
-    cudaError_t e = launch_encode(kind, in_dev, cnt, o, st);
-    return e == cudaSuccess ? S2B_OK : cuda_fail(e, "encode launch");
-  });
+    return o;
+  };
+  std::vector<FixPatch> changed;
+  OutSpec outs[4] = {{ids_out, 8, num_levels}, {flags_out, 1, 1}, {tok_out, 16, 1}, {tok_len_out, 1, 1}};
+  return run_pipelined(
+      in, in_bpp, n, outs, 4,
+      [&](int si, const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
+        EncodeOut o = make_out(out_dev);
+        if (strict) {
+          FixBuf& fb = t_fix_slot[si];
+          o.fix_list = fb.d_list; o.fix_count = fb.d_count; o.fix_cap = fb.cap;
+          S2B_CUDA(cudaMemsetAsync(fb.d_count, 0, sizeof(uint32_t), st));
+        }
+        cudaError_t e = launch_encode(kind, in_dev, cnt, o, st);
+        if (e != cudaSuccess) return cuda_fail(e, "encode launch");
+        if (strict) {
+          FixBuf& fb = t_fix_slot[si];
+          S2B_CUDA(cudaMemcpyAsync(fb.h_count, fb.d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+          S2B_CUDA(cudaMemcpyAsync(fb.h_list, fb.d_list, sizeof(FixRecord) * kFixEager, cudaMemcpyDeviceToHost, st));
+        }
+        return S2B_OK;
+      },
+      [&](int si, size_t off, size_t cnt, const void* in_dev, void** out_dev, cudaStream_t st) {
+        if (!strict) return S2B_OK;
+        FixBuf& fb = t_fix_slot[si];
+        if (*fb.h_count == 0) return S2B_OK;
+        changed.clear();
+        int crc = collect_patches(kind, in_dev, in_bpp, cnt, make_out(out_dev), st, fb, true, kFixEager, &changed);
+        if (crc) return crc;
+        // records carry chunk-local indices (index_base 0); the chunk's results are already in the caller's arrays
+        for (const FixPatch& p : changed) {
+          const size_t i = off + (size_t)p.index;
+          for (int k = 0; k < num_levels; ++k) ids_out[(size_t)k * n + i] = cellid_parent(p.id, lv.level[k]);
+          if (tok_level_index >= 0) {
+            uint32_t w[4];
+            const int len = cellid_to_token(cellid_parent(p.id, lv.level[tok_level_index]), w);
+            memcpy(tok_out + 16 * i, w, 16);
+            if (tok_len_out) tok_len_out[i] = (uint8_t)len;
+          }
+        }
+        return S2B_OK;
+      });
 }
 
 static int encode_dev(InputKind kind, const void* in, size_t n, const int* levels, int num_levels, uint64_t* ids_out,
                       uint8_t* flags_out, void* stream, int tok_level_index = -1, char* tok_out = nullptr,
-                      uint8_t* tok_len_out = nullptr) {
+                      uint8_t* tok_len_out = nullptr, bool strict = false) {
   LevelSpec lv;
   int rc = check_levels(levels, num_levels, &lv);
   if (rc) return rc;
@@ -218,8 +439,30 @@ static int encode_dev(InputKind kind, const void* in, size_t n, const int* level
   o.tokens16 = tok_out;
   o.token_len = tok_len_out;
   o.force_cr = g_force_cr.load();
-  cudaError_t e = launch_encode(kind, in, n, o, (cudaStream_t)stream);
-  if (e != cudaSuccess) return cuda_fail(e, "encode launch");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!(strict && strict_latlng(kind))) {
+    cudaError_t e = launch_encode(kind, in, n, o, st);
+    if (e != cudaSuccess) return cuda_fail(e, "encode launch");
+    return S2B_OK;
+  }
+  // Strict: kernel + the list of boundary-sensitive points -> host libm -> patch kernel for the ids that differ.
+  int dev = 0;
+  S2B_CUDA(cudaGetDevice(&dev));
+  const size_t want = n / 128 < (1u << 16) ? (1u << 16) : (n / 128 > (1u << 24) ? (1u << 24) : n / 128);
+  rc = t_fix_dev.ensure(dev, (uint32_t)want);
+  if (rc) return rc;
+  std::vector<FixPatch> changed;
+  rc = collect_patches(kind, in, kind == kInLatLngRad ? 16 : 8, n, o, st, t_fix_dev, false, 0, &changed);
+  if (rc) return rc;
+  for (size_t off = 0; off < changed.size(); off += (1u << 20)) {
+    const uint32_t m = (uint32_t)(changed.size() - off < (1u << 20) ? changed.size() - off : (1u << 20));
+    rc = t_fix_dev.ensure_patches(m);
+    if (rc) return rc;
+    S2B_CUDA(cudaMemcpyAsync(t_fix_dev.d_patch, changed.data() + off, sizeof(FixPatch) * m, cudaMemcpyHostToDevice, st));
+    cudaError_t e = launch_encode_patch(t_fix_dev.d_patch, m, o, n, st);
+    if (e != cudaSuccess) return cuda_fail(e, "patch launch");
+    S2B_CUDA(cudaStreamSynchronize(st));   // `changed` is pageable host memory
+  }
   return S2B_OK;
 }
 
@@ -238,6 +481,24 @@ int s2b_device_count(void) {
 }
 uint64_t s2b_launch_count(void) { return g_launches.load(); }
 int s2b_diag_force_correctly_rounded(int on) { return g_force_cr.exchange(on ? 1 : 0); }
+int s2b_set_latlng_mode(int mode) {
+  if (mode != S2B_LATLNG_HOST_LIBM && mode != S2B_LATLNG_CORRECTLY_ROUNDED) return set_error(S2B_EINVAL, "unknown lat/lng mode %d", mode);
+  return g_latlng_mode.exchange(mode);
+}
+int s2b_latlng_strict_stats(uint64_t* reevaluated_out, uint64_t* changed_out, int reset) {
+  if (reevaluated_out) *reevaluated_out = reset ? g_strict_reevaluated.exchange(0) : g_strict_reevaluated.load();
+  if (changed_out) *changed_out = reset ? g_strict_changed.exchange(0) : g_strict_changed.load();
+  if (reset && !reevaluated_out) g_strict_reevaluated.store(0);
+  if (reset && !changed_out) g_strict_changed.store(0);
+  return S2B_OK;
+}
+int s2b_encode_latlng_strict_dev(int input_kind, const void* latlng_dev, size_t n, const int* levels, int num_levels,
+                                 uint64_t* ids_out_dev, uint8_t* boundary_flag_out_dev, int token_level_index,
+                                 char* tokens16_out_dev, uint8_t* len_out_dev, void* stream) {
+  if (input_kind != 1 && input_kind != 2) return set_error(S2B_EINVAL, "input_kind must be 1 (lat/lng radians) or 2 (lat/lng E7)");
+  return encode_dev(input_kind == 1 ? kInLatLngRad : kInLatLngE7, latlng_dev, n, levels, num_levels, ids_out_dev,
+                    boundary_flag_out_dev, stream, token_level_index < 0 ? -1 : token_level_index, tokens16_out_dev, len_out_dev, true);
+}
 
 int s2b_diag_filter_deviation_dev(int input_kind, const double* in_dev, size_t n, double* max_deviation_out, uint64_t* unflagged_face_flips_out, void* stream) {
   if (!max_deviation_out || !unflagged_face_flips_out || (n && !in_dev)) return set_error(S2B_EINVAL, "null argument");
@@ -302,7 +563,7 @@ int s2b_cellid_parent(const uint64_t* ids, size_t n, int level, uint64_t* out) {
   if (n == 0) return S2B_OK;
   if (!ids || !out) return set_error(S2B_EINVAL, "null pointer");
   OutSpec outs[1] = {{out, 8, 1}};
-  return run_pipelined(ids, 8, n, outs, 1, [&](const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
+  return run_pipelined(ids, 8, n, outs, 1, [&](int, const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
     cudaError_t e = launch_parent((const uint64_t*)in_dev, cnt, level, (uint64_t*)out_dev[0], st);
     return e == cudaSuccess ? S2B_OK : cuda_fail(e, "parent launch");
   });
@@ -319,7 +580,7 @@ int s2b_cellid_to_token(const uint64_t* ids, size_t n, char* tokens16_out, uint8
   if (n == 0) return S2B_OK;
   if (!ids || !tokens16_out) return set_error(S2B_EINVAL, "null pointer");
   OutSpec outs[2] = {{tokens16_out, 16, 1}, {len_out, 1, 1}};
-  return run_pipelined(ids, 8, n, outs, 2, [&](const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
+  return run_pipelined(ids, 8, n, outs, 2, [&](int, const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
     cudaError_t e = launch_to_token((const uint64_t*)in_dev, cnt, (char*)out_dev[0], len_out ? (uint8_t*)out_dev[1] : nullptr, st);
     return e == cudaSuccess ? S2B_OK : cuda_fail(e, "token launch");
   });
@@ -336,7 +597,7 @@ int s2b_cellid_edge_neighbors(const uint64_t* ids, size_t n, uint64_t* neighbors
   if (n == 0) return S2B_OK;
   if (!ids || !neighbors4_out) return set_error(S2B_EINVAL, "null pointer");
   OutSpec outs[1] = {{neighbors4_out, 32, 1}};
-  return run_pipelined(ids, 8, n, outs, 1, [&](const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
+  return run_pipelined(ids, 8, n, outs, 1, [&](int, const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
     cudaError_t e = launch_edge_neighbors((const uint64_t*)in_dev, cnt, (uint64_t*)out_dev[0], st);
     return e == cudaSuccess ? S2B_OK : cuda_fail(e, "edge_neighbors launch");
   });
@@ -352,7 +613,7 @@ int s2b_cellid_to_point(const uint64_t* ids, size_t n, double* xyz_out) {
   if (n == 0) return S2B_OK;
   if (!ids || !xyz_out) return set_error(S2B_EINVAL, "null pointer");
   OutSpec outs[1] = {{xyz_out, 24, 1}};
-  return run_pipelined(ids, 8, n, outs, 1, [&](const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
+  return run_pipelined(ids, 8, n, outs, 1, [&](int, const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
     cudaError_t e = launch_to_point((const uint64_t*)in_dev, cnt, (double*)out_dev[0], st);
     return e == cudaSuccess ? S2B_OK : cuda_fail(e, "to_point launch");
   });
@@ -367,7 +628,7 @@ int s2b_cellid_to_latlng(const uint64_t* ids, size_t n, double* latlng_rad_out) 
   if (n == 0) return S2B_OK;
   if (!ids || !latlng_rad_out) return set_error(S2B_EINVAL, "null pointer");
   OutSpec outs[1] = {{latlng_rad_out, 16, 1}};
-  return run_pipelined(ids, 8, n, outs, 1, [&](const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
+  return run_pipelined(ids, 8, n, outs, 1, [&](int, const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
     cudaError_t e = launch_to_latlng((const uint64_t*)in_dev, cnt, (double*)out_dev[0], st);
     return e == cudaSuccess ? S2B_OK : cuda_fail(e, "to_latlng launch");
   });
@@ -411,7 +672,7 @@ int s2b_contains(const S2bIndex* ix, const double* xyz, size_t n, int model, uin
   if (n && (!xyz || !out)) return set_error(S2B_EINVAL, "null pointer");
   if (n == 0) return s2b_contains_dev(ix, nullptr, 0, model, nullptr, nullptr);
   OutSpec outs[1] = {{out, 1, 1}};
-  return run_pipelined(xyz, 24, n, outs, 1, [&](const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
+  return run_pipelined(xyz, 24, n, outs, 1, [&](int, const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
     return s2b_contains_dev(ix, (const double*)in_dev, cnt, model, (uint8_t*)out_dev[0], st);
   });
 }
@@ -420,7 +681,7 @@ int s2b_index_locate_points(const S2bIndex* ix, const double* xyz, size_t n, int
   if (n && (!xyz || !cell_out)) return set_error(S2B_EINVAL, "null pointer");
   if (n == 0) return s2b_index_locate_points_dev(ix, nullptr, 0, nullptr, nullptr);
   OutSpec outs[1] = {{cell_out, 4, 1}};
-  return run_pipelined(xyz, 24, n, outs, 1, [&](const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
+  return run_pipelined(xyz, 24, n, outs, 1, [&](int, const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
     return s2b_index_locate_points_dev(ix, (const double*)in_dev, cnt, (int32_t*)out_dev[0], st);
   });
 }
@@ -429,7 +690,7 @@ int s2b_shape_contains(const S2bIndex* ix, int shape_id, const double* xyz, size
   if (n && (!xyz || !out)) return set_error(S2B_EINVAL, "null pointer");
   if (n == 0) return s2b_shape_contains_dev(ix, shape_id, nullptr, 0, model, nullptr, nullptr);
   OutSpec outs[1] = {{out, 1, 1}};
-  return run_pipelined(xyz, 24, n, outs, 1, [&](const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
+  return run_pipelined(xyz, 24, n, outs, 1, [&](int, const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
     return s2b_shape_contains_dev(ix, shape_id, (const double*)in_dev, cnt, model, (uint8_t*)out_dev[0], st);
   });
 }
@@ -446,7 +707,7 @@ int s2b_shape_histogram(const S2bIndex* ix, const double* xyz, size_t n, int mod
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   int rc = e == cudaSuccess ? S2B_OK : cuda_fail(e, "cudaMemset");
   if (rc == S2B_OK && n)
-    rc = run_pipelined(xyz, 24, n, nullptr, 0, [&](const void* in_dev, size_t cnt, void**, cudaStream_t st) {
+    rc = run_pipelined(xyz, 24, n, nullptr, 0, [&](int, const void* in_dev, size_t cnt, void**, cudaStream_t st) {
       return s2b_shape_histogram_dev(ix, (const double*)in_dev, cnt, model, d_counts, st);
     });
   if (rc == S2B_OK && S > 0) {
@@ -466,7 +727,7 @@ int s2b_containing_shapes(const S2bIndex* ix, const double* xyz, size_t n, int m
   if (n == 0) return S2B_OK;
   // pass 1: per-point counts land in offsets_out[1..n], then an exclusive scan on the host
   OutSpec outs[1] = {{offsets_out + 1, 4, 1}};
-  int rc = run_pipelined(xyz, 24, n, outs, 1, [&](const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
+  int rc = run_pipelined(xyz, 24, n, outs, 1, [&](int, const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
     return s2b_containing_shapes_count_dev(ix, (const double*)in_dev, cnt, model, (uint32_t*)out_dev[0], st);
   });
   if (rc) return rc;
@@ -527,7 +788,7 @@ int s2b_cellunion_contains(const uint64_t* sorted_ids, size_t m, const double* x
   int rc = e == cudaSuccess ? S2B_OK : cuda_fail(e, "cudaMemcpy(ids)");
   if (rc == S2B_OK) {
     OutSpec outs[1] = {{out, 1, 1}};
-    rc = run_pipelined(xyz, 24, n, outs, 1, [&](const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
+    rc = run_pipelined(xyz, 24, n, outs, 1, [&](int, const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
       return s2b_cellunion_contains_dev(d_ids, m, (const double*)in_dev, cnt, (uint8_t*)out_dev[0], st);
     });
   }

@@ -55,6 +55,10 @@ struct EncodeArgs {
   uint32_t tok_keep[4];
   uint32_t tok_len;
   int force_cr;
+  FixRecord* fix_list;     // nullable: strict host-libm mode (s2b_internal.h)
+  uint32_t* fix_count;
+  uint32_t fix_cap;
+  uint64_t index_base;
 };
 
 template <int kKind> struct RawPoint;
@@ -68,6 +72,16 @@ __device__ __forceinline__ RawPoint<kInXYZ> load_raw(const void* in, uint32_t i,
 }
 __device__ __forceinline__ RawPoint<kInLatLngRad> load_raw(const void* in, uint32_t i, RawPoint<kInLatLngRad>*) { return {__ldcs((const double2*)in + i)}; }
 __device__ __forceinline__ RawPoint<kInLatLngE7> load_raw(const void* in, uint32_t i, RawPoint<kInLatLngE7>*) { return {__ldcs((const int2*)in + i)}; }
+
+// Strict host-libm mode, rare path (out of line so that it costs the main loop no registers).
+__device__ __noinline__ void append_fix(FixRecord* list, uint32_t* count, uint32_t cap, uint64_t index, double lat, double lng, uint64_t id) {
+  const uint32_t slot = atomicAdd(count, 1u);
+  if (slot < cap) {
+    ulonglong2* r = (ulonglong2*)(list + slot);
+    r[0] = make_ulonglong2(index, (unsigned long long)__double_as_longlong(lat));
+    r[1] = make_ulonglong2((unsigned long long)__double_as_longlong(lng), id);
+  }
+}
 
 // One thread per point, persistent grid. The input of the NEXT iteration is loaded before the current point is
 // processed, so a warp does not sit on the long scoreboard at the top of every iteration.
@@ -128,6 +142,23 @@ encode_kernel(const void* __restrict__ in, uint32_t n, const EncodeArgs a) {
         if (a.token_len) a.token_len[i] = (uint8_t)a.tok_len;
       }
       if (a.flags) a.flags[i] = (kKind == kInXYZ || sensitive) && near_cell_boundary(fi, fj, kFlagTolIj) ? 1 : 0;
+      if constexpr (kKind != kInXYZ) {
+        // Strict mode: hand every point whose leaf cell a <= 1 ulp change of sin/cos could move (and every angle the
+        // device routines do not cover) to the host, which re-evaluates it with its own libm. ~1.6e-5 of uniform input.
+        if (sensitive && a.fix_list != nullptr) {
+          // the input is read again here (rare) rather than kept live in registers across the whole iteration
+          const Raw again = load_raw(in, i, (Raw*)nullptr);
+          double lat, lng;
+          if constexpr (kKind == kInLatLngRad) {
+            lat = again.ll.x; lng = again.ll.y;
+          } else {
+            lat = (M_PI / 180) * (1e-7 * (double)again.e7.x);
+            lng = (M_PI / 180) * (1e-7 * (double)again.e7.y);
+          }
+          if (near_cell_boundary(fi, fj, kFlagTolIj) || !(fabs(lat) < 1048576.0 && fabs(lng) < 1048576.0))
+            append_fix(a.fix_list, a.fix_count, a.fix_cap, a.index_base + i, lat, lng, id);
+        }
+      }
     }
     cur = nxt;
     i = i_next;
@@ -174,18 +205,23 @@ cudaError_t launch_encode(InputKind kind, const void* in, size_t n, const Encode
   if (te != cudaSuccess) return te;
   const bool token = o.token_level_index >= 0;
   const size_t in_stride = kind == kInXYZ ? 24 : (kind == kInLatLngRad ? 16 : 8);
+  const size_t ids_stride = o.ids_stride ? o.ids_stride : n;
   constexpr size_t kMaxLaunchPoints = (size_t)1 << 31;
   for (size_t off = 0; off < n; off += kMaxLaunchPoints) {
     const uint32_t cnt = (uint32_t)(n - off < kMaxLaunchPoints ? n - off : kMaxLaunchPoints);
     EncodeArgs a{};
     for (int k = 0; k < o.levels.n; ++k) {
       const uint64_t lsb = lsb_for_level(o.levels.level[k]);
-      a.ids[k] = o.ids + (size_t)k * n + off;
+      a.ids[k] = o.ids + (size_t)k * ids_stride + off;
       a.and_mask[k] = ~lsb + 1;
       a.or_mask[k] = lsb;
     }
     a.flags = o.flags ? o.flags + off : nullptr;
     a.force_cr = o.force_cr;
+    a.fix_list = kind == kInXYZ ? nullptr : o.fix_list;
+    a.fix_count = o.fix_count;
+    a.fix_cap = o.fix_cap;
+    a.index_base = o.index_base + off;
     if (token) {
       const int L = o.levels.level[o.token_level_index];
       const uint64_t lsb = lsb_for_level(L);
@@ -209,6 +245,45 @@ cudaError_t launch_encode(InputKind kind, const void* in, size_t n, const Encode
     if (e != cudaSuccess) return e;
   }
   return cudaSuccess;
+}
+
+// Strict host-libm mode: the host re-evaluated the boundary-sensitive points and found `m` whose leaf id differs under
+// its libm; rewrite their outputs (every level + token) in place. m is tiny (usually 0: then this is not launched).
+__global__ void __launch_bounds__(kThreads) encode_patch_kernel(const FixPatch* __restrict__ patches, uint32_t m, const EncodeArgs a, int levels, bool token) {
+  const uint32_t k = blockIdx.x * kThreads + threadIdx.x;
+  if (k >= m) return;
+  const uint64_t i = patches[k].index - a.index_base, id = patches[k].id;
+  for (int l = 0; l < levels; ++l) a.ids[l][i] = (id & a.and_mask[l]) | a.or_mask[l];
+  if (token) {
+    uint32_t w[4];
+    const int len = cellid_to_token((id & a.tok_and) | a.tok_or, w);
+    a.tokens16[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    if (a.token_len) a.token_len[i] = (uint8_t)len;
+  }
+}
+
+cudaError_t launch_encode_patch(const FixPatch* patches_dev, uint32_t m, const EncodeOut& o, size_t n, cudaStream_t st) {
+  if (m == 0) return cudaSuccess;
+  const size_t ids_stride = o.ids_stride ? o.ids_stride : n;
+  EncodeArgs a{};
+  for (int k = 0; k < o.levels.n; ++k) {
+    const uint64_t lsb = lsb_for_level(o.levels.level[k]);
+    a.ids[k] = o.ids + (size_t)k * ids_stride;
+    a.and_mask[k] = ~lsb + 1;
+    a.or_mask[k] = lsb;
+  }
+  a.index_base = o.index_base;
+  const bool token = o.token_level_index >= 0;
+  if (token) {
+    const uint64_t lsb = lsb_for_level(o.levels.level[o.token_level_index]);
+    a.tok_and = ~lsb + 1;
+    a.tok_or = lsb;
+    a.tokens16 = (uint4*)o.tokens16;
+    a.token_len = o.token_len;
+  }
+  encode_patch_kernel<<<(m + kThreads - 1) / kThreads, kThreads, 0, st>>>(patches_dev, m, a, o.levels.n, token);
+  count_launch();
+  return cudaGetLastError();
 }
 
 // Diagnostics (s2b_diag_filter_deviation_dev): how far the filter path's (fi, fj) are from the correctly rounded path's,

@@ -95,7 +95,7 @@ inline int pack_flat_index(const S2bFlatIndex& f, HostFlat* out, std::string* er
     while (c < C && cellid_range_max(f.cell_ids[c]) < first) ++c;
     uint32_t entry;
     if (c == C || cellid_range_min(f.cell_ids[c]) > last) entry = kLutEmpty;
-    else if (cellid_range_min(f.cell_ids[c]) <= first && cellid_range_max(f.cell_ids[c]) >= last)
+    else if (cellid_range_min(f.cell_ids[c]) <= (first | 1) && cellid_range_max(f.cell_ids[c]) >= last)   // first | 1: the bucket's first LEAF id (leaf ids are odd)
       entry = (out->interior_info[c] < 0 ? kLutInterior : kLutInside) | (uint32_t)c;
     else {
       uint64_t h = c;   // last cell starting inside the bucket

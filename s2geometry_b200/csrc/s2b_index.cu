@@ -79,7 +79,7 @@ struct WarpSlots {
     }
     if (want) {
       const uint32_t s = next + (uint32_t)__popc(m & ((1u << lane) - 1u));
-      work[dir > 0 ? s : capacity - 1 - s] = value;
+      if (s < capacity) work[dir > 0 ? s : capacity - 1 - s] = value;   // never false: see work_list_capacity()
     }
     next += k;
   }
@@ -87,6 +87,16 @@ struct WarpSlots {
     for (uint32_t s = next + lane; s < end; s += 32) work[dir > 0 ? s : capacity - 1 - s] = HitWork{0u, -1};
   }
 };
+
+// Slots a list can consume for `entries` appended items, written by `warps` warps: an append that does not fit retires
+// the rest of its chunk (at most 31 slots, since an append holds at most 32 entries) and takes a new one, so a chunk
+// holds at least kSlotChunk - 31 entries, and every warp leaves at most one partly used chunk at the end:
+//   slots <= kSlotChunk * (entries / (kSlotChunk - 31) + 1 + warps)  <=  1.32 * entries + kSlotChunk * (warps + 1).
+// The edge list and the interior list share one buffer from its two ends and a point is in at most one of them, so
+// `entries` is bounded by the points of the round for the pair.
+static size_t work_list_capacity(size_t entries, size_t warps) {
+  return kSlotChunk * (entries / (kSlotChunk - 31) + 2 + warps);
+}
 
 // What phase A does with a located point. interior_mode says what may be answered on the spot for points in pure
 // interior cells (no edges, every clip contains the centre):
@@ -542,10 +552,11 @@ static cudaError_t launch_query_t(const FlatIndexView& ix, const double* xyz, si
   const size_t round = n < kRoundPoints ? n : kRoundPoints;
   HitWork* work = nullptr;
   unsigned int* counter = nullptr;
-  // every warp of phase A (two kernels) can leave at most one partly used chunk per list
+  // worst-case slot consumption (work_list_capacity): two lists x the warps of the two phase-A kernels (<= 6 + 4 CTAs
+  // per SM); the undecided list is written by the pre-filter's warps only
   const size_t max_warps = (size_t)sm_count() * 8 * (kThreads / 32);
-  const size_t capacity = round + 4 * max_warps * kSlotChunk;
-  const size_t unc_capacity = round + max_warps * kSlotChunk;
+  const size_t capacity = work_list_capacity(round, 4 * max_warps);
+  const size_t unc_capacity = work_list_capacity(round, max_warps);
   const bool use_fast = !g_force_exact_locate && ((uintptr_t)xyz % 16 == 0);   // cp.async staging needs 16-byte alignment
   // cell-major ordering of the edge hits pays off when the index is too large to stay cache resident and has enough
   // cells for the per-cell atomics not to collide (S2B_SORT_BY_CELL=0/1 overrides)
@@ -627,6 +638,7 @@ using namespace s2b;
 namespace s2b {
 int set_error(int code, const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
+cudaError_t region_exact_stage_count(unsigned long long* count, bool reset);   // s2b_region.cu
 }
 
 static int check_model(int m) {
@@ -863,7 +875,11 @@ int s2b_index_locate_cells(const S2bIndex* ix, const uint64_t* cell_ids, size_t 
 #define S2B_QUERY_PROLOGUE                                                            \
   if (!ix) return set_error(S2B_EINVAL, "null index");                                \
   { int rc__ = check_model(model); if (rc__) return rc__; }                           \
-  if (n == 0) return S2B_OK;
+  if (n == 0) return S2B_OK;                                                          \
+  { int dev__ = -1;                                                                   \
+    cudaError_t de__ = cudaGetDevice(&dev__);                                         \
+    if (de__ != cudaSuccess) return cuda_fail(de__, "cudaGetDevice");                 \
+    if (dev__ != ix->device) return set_error(S2B_EINVAL, "the index lives on device %d but the current device is %d", ix->device, dev__); }
 
 int s2b_contains_dev(const S2bIndex* ix, const double* xyz, size_t n, int model, uint8_t* out, void* stream) {
   S2B_QUERY_PROLOGUE
@@ -913,10 +929,11 @@ int s2b_diag_force_exact_locate(int on) {
 }
 
 int s2b_exact_stage_count(uint64_t* count_out, int reset) {
-  unsigned long long v = 0;
+  unsigned long long v = 0, vr = 0;
   cudaError_t e = cudaMemcpyFromSymbol(&v, g_exact_count, sizeof v);
+  if (e == cudaSuccess) e = region_exact_stage_count(&vr, reset != 0);   // s2b_region.cu's copy of the counter
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyFromSymbol");
-  if (count_out) *count_out = v;
+  if (count_out) *count_out = v + vr;
   if (reset) {
     v = 0;
     e = cudaMemcpyToSymbol(g_exact_count, &v, sizeof v);

@@ -140,14 +140,17 @@ struct SoupEdges {
   }
 };
 
-inline bool decode_edges(Reader* r, uint32_t num_edges, std::vector<int32_t>* ids) {   // s2shape_index.cc:325-375
+// `limit` = number of edges of the shape: counts and ids beyond it are rejected BEFORE anything is materialised, so a
+// malformed record cannot force large allocations.
+inline bool decode_edges(Reader* r, uint32_t num_edges, uint64_t limit, std::vector<int32_t>* ids) {   // s2shape_index.cc:325-375
+  if (num_edges > limit) return false;
   int64_t edge_id = 0;
   for (uint32_t i = 0; i < num_edges;) {
     uint32_t delta = 0;
     if (!r->varint32(&delta)) return false;
     if (i + 1 == num_edges) {
       edge_id += delta;
-      if (edge_id > INT32_MAX) return false;
+      if (edge_id > INT32_MAX || (uint64_t)edge_id >= limit) return false;
       ids->push_back((int32_t)edge_id);
       ++i;
     } else {
@@ -159,7 +162,7 @@ inline bool decode_edges(Reader* r, uint32_t num_edges, std::vector<int32_t>* id
       }
       if ((uint64_t)i + count > num_edges) return false;
       edge_id += delta;
-      if (edge_id + count > INT32_MAX) return false;
+      if (edge_id + count > INT32_MAX || (uint64_t)edge_id + count > limit) return false;
       for (uint32_t k = 0; k < count; ++k) ids->push_back((int32_t)(edge_id + k));
       i += count;
       edge_id += count;
@@ -275,7 +278,7 @@ inline int decode_index_wire(const uint8_t* bytes, size_t len, int num_shapes, c
       } else {
         cc = (header & 4) != 0;
         const uint64_t n = header >> 3;
-        if (n > (uint64_t)INT32_MAX || !decode_edges(&cr, (uint32_t)n, &ids)) return fail("bad edge list" + where);
+        if (n > (uint64_t)INT32_MAX || !decode_edges(&cr, (uint32_t)n, soup.shape_num_edges[0], &ids)) return fail("bad edge list" + where);
       }
       if (!add_clip(0, cc, ids)) return fail("shape or edge id out of range" + where);
     } else {
@@ -310,7 +313,8 @@ inline int decode_index_wire(const uint8_t* bytes, size_t len, int num_shapes, c
           shape_id += shape_delta;
           const uint32_t n = (header >> 3) + 1;
           cc = (header & 4) != 0;
-          if (!decode_edges(&cr, n, &ids)) return fail("bad edge list" + where);
+          if (shape_id >= num_shapes) return fail("shape id out of range" + where);
+          if (!decode_edges(&cr, n, soup.shape_num_edges[shape_id], &ids)) return fail("bad edge list" + where);
         }
         if (!add_clip(shape_id, cc, ids)) return fail("shape or edge id out of range" + where);
       }

@@ -8,6 +8,11 @@ namespace s2b {
 
 struct LevelSpec { int n; int level[4]; };
 
+// One boundary-sensitive lat/lng point: its index in the caller's batch, the angles in radians as the device evaluated
+// them (for E7 input: (M_PI / 180) * (1e-7 * e7), s1angle.h:363-377) and the leaf id the device computed.
+struct FixRecord { uint64_t index; double lat, lng; uint64_t id; };
+struct FixPatch { uint64_t index, id; };
+
 // Everything the encode kernel can emit for a point. ids: `levels.n` arrays of n ids (array k at ids + k*n).
 // tokens (optional): ToToken of the id at levels.level[token_level_index], 16-byte slots + strlen bytes.
 struct EncodeOut {
@@ -18,12 +23,21 @@ struct EncodeOut {
   char* tokens16;       // nullable unless token_level_index >= 0
   uint8_t* token_len;   // nullable
   int force_cr = 0;     // diagnostics: 1 = always use the correctly rounded sin/cos (skip the fast filter)
+  // Strict host-libm mode (lat/lng input): points whose leaf cell could change under a <= 1 ulp change of a sin/cos value
+  // (and angles outside the device routines' domain) are appended to fix_list for re-evaluation with the host's libm.
+  FixRecord* fix_list = nullptr;   // nullable
+  uint32_t* fix_count = nullptr;          // device counter, incremented past fix_cap on overflow
+  uint32_t fix_cap = 0;
+  uint64_t index_base = 0;                // index of point 0 of this launch in the caller's batch
+  size_t ids_stride = 0;                  // distance between the per-level id arrays; 0 = n
 };
 
 enum InputKind { kInXYZ = 0, kInLatLngRad = 1, kInLatLngE7 = 2 };
 
 // Kernel launchers (device pointers, enqueue only). Return cudaGetLastError() of the launch.
 cudaError_t launch_encode(InputKind kind, const void* in_dev, size_t n, const EncodeOut& out, cudaStream_t stream);
+// Overwrites the outputs of the points in `patches` (leaf ids under the host libm) at every level + token of `out`.
+cudaError_t launch_encode_patch(const FixPatch* patches_dev, uint32_t m, const EncodeOut& out, size_t n, cudaStream_t stream);
 cudaError_t launch_parent(const uint64_t* ids_dev, size_t n, int level, uint64_t* out_dev, cudaStream_t stream);
 cudaError_t launch_filter_deviation(InputKind kind, const double* in_dev, size_t n, unsigned long long* out2_dev, cudaStream_t stream);
 cudaError_t launch_edge_neighbors(const uint64_t* ids_dev, size_t n, uint64_t* out4_dev, cudaStream_t stream);

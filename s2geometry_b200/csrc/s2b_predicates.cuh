@@ -23,7 +23,9 @@ namespace s2b {
 
 // Statistic only: how many predicate evaluations reached the exact stage (s2b_exact_stage_count in the C ABI).
 #if defined(__CUDACC__)
-__device__ unsigned long long g_exact_count = 0;  // this header is included by exactly one .cu file (s2b_index.cu)
+// One copy per translation unit that includes this header (s2b_index.cu: point queries; s2b_region.cu: region cell
+// tests); s2b_exact_stage_count sums them.
+static __device__ unsigned long long g_exact_count = 0;
 #endif
 #if defined(__CUDA_ARCH__)
 #define S2B_NOTE_EXACT() atomicAdd(&::s2b::g_exact_count, 1ull)

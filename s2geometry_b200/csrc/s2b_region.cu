@@ -24,6 +24,16 @@ using namespace s2b;
 
 namespace s2b {
 int set_error(int code, const char* fmt, ...);
+
+// This translation unit's copy of the exact-stage counter (s2b_predicates.cuh), read by s2b_exact_stage_count.
+cudaError_t region_exact_stage_count(unsigned long long* count, bool reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(count, g_exact_count, sizeof *count);
+  if (e == cudaSuccess && reset) {
+    const unsigned long long zero = 0;
+    e = cudaMemcpyToSymbol(g_exact_count, &zero, sizeof zero);
+  }
+  return e;
+}
 int cuda_fail(cudaError_t e, const char* what);
 }
 

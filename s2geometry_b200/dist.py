@@ -37,29 +37,54 @@ def init(backend=None):
     return rank, world, device
 
 
+def _cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if part:
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
 def bind_to_gpu_numa_node(local_rank):
-    """Pins this process to the CPUs of the NUMA node its GPU hangs off, so that pinned host buffers (first touch) and
-    the staging threads sit next to the GPU's PCIe root. Matters for the host-pointer (end-to-end) path when 8 ranks
-    stream through host memory at once. Best effort: returns the node or None."""
+    """Pins this process to the CPUs next to its GPU, so that pinned host buffers (first touch after the bind) and the
+    staging threads sit on the GPU's PCIe root. Matters for the host-pointer (end-to-end) path when 8 ranks stream through
+    host memory at once. Sources, in order: the GPU's sysfs numa_node, then NVML's ideal CPU affinity
+    (nvmlDeviceGetCpuAffinity, what `nvidia-smi topo -m` prints). Returns a dict describing what was done and why —
+    including the common VM case where the box exposes ONE NUMA node and there is nothing to bind to."""
+    import glob
+    info = {"bound": False, "numa_nodes": len(glob.glob("/sys/devices/system/node/node[0-9]*")), "cpus_allowed": len(os.sched_getaffinity(0))}
     try:
         props = torch.cuda.get_device_properties(local_rank)
         bus = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
         with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
             node = int(f.read().strip())
-        if node < 0:
-            return None
-        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
-            cpus = set()
-            for part in f.read().strip().split(","):
-                a, _, b = part.partition("-")
-                cpus.update(range(int(a), int(b or a) + 1))
+        info["sysfs_numa_node"] = node
+        if node >= 0:
+            with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+                allowed = os.sched_getaffinity(0) & _cpulist(f.read())
+            if allowed and allowed != os.sched_getaffinity(0):
+                os.sched_setaffinity(0, allowed)
+                info.update(bound=True, how="sysfs numa_node %d" % node, cpus_bound=len(allowed))
+                return info
+    except Exception as e:
+        info["sysfs_error"] = repr(e)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
         allowed = os.sched_getaffinity(0) & cpus
-        if allowed:
+        info["nvml_affinity_cpus"] = len(cpus)
+        if allowed and allowed != os.sched_getaffinity(0):
             os.sched_setaffinity(0, allowed)
-            return node
-    except Exception:
-        pass
-    return None
+            info.update(bound=True, how="NVML ideal CPU affinity", cpus_bound=len(allowed))
+            return info
+        info["why"] = "the GPU's ideal CPU set is every allowed CPU (one NUMA node exposed): nothing to bind"
+    except Exception as e:
+        info["nvml_error"] = repr(e)
+    return info
 
 
 def shard_range(n, rank, world):

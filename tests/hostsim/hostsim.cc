@@ -97,3 +97,41 @@ extern "C" void hs_cellid_from_token(const char* tok16, const uint8_t* len, size
 extern "C" void hs_edge_neighbors(const uint64_t* ids, size_t n, uint64_t* out4) {
   for (size_t i = 0; i < n; ++i) cellid_edge_neighbors(ids[i], kHilbert.pos, kHilbert.ij, out4 + 4 * i);
 }
+
+// ---- counter-based synthetic streams (s2b_synth.cuh) and the strict host-libm lat/lng mode, host compilation ----
+#include <math.h>
+#include "s2b_synth.cuh"
+
+extern "C" {
+
+void hs_synth_sphere_points(uint64_t seed, uint64_t first, size_t n, double* out) {
+  for (size_t i = 0; i < n; ++i) { P3 p = synth_sphere_point(seed, first + i); out[3 * i] = p.x; out[3 * i + 1] = p.y; out[3 * i + 2] = p.z; }
+}
+void hs_synth_sphere_latlng(uint64_t seed, uint64_t first, size_t n, double* out) {
+  for (size_t i = 0; i < n; ++i) synth_sphere_latlng(seed, first + i, &out[2 * i], &out[2 * i + 1]);
+}
+void hs_synth_cap_points(uint64_t seed, uint64_t first, size_t n, const double* frame9, double height, double* out) {
+  for (size_t i = 0; i < n; ++i) { P3 p = synth_cap_point(seed, first + i, frame9, height); out[3 * i] = p.x; out[3 * i + 1] = p.y; out[3 * i + 2] = p.z; }
+}
+
+// What the encode kernel + the strict completion do per point (s2b_encode.cu / s2b_capi.cu): the device id, and for the
+// points the kernel would hand back (sensitive && near a boundary at kFlagTolIj, or out-of-domain angles) the id from this
+// host's sin/cos. *n_reeval counts the latter.
+void hs_encode_latlng_strict(const double* ll, size_t n, uint64_t* out, uint64_t* n_reeval) {
+  uint64_t nr = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const double lat = ll[2 * i], lng = ll[2 * i + 1];
+    P3 p; double fi, fj; bool sens;
+    int face = latlng_to_face_fij(lat, lng, sc_tab::kSinCosTable, false, &p, &fi, &fj, &sens);
+    uint64_t id = from_face_ij(face, fij_to_ij(fi), fij_to_ij(fj), kHilbert.pos);
+    if (sens && (near_cell_boundary(fi, fj, kFlagTolIj) || !(fabs(lat) < 1048576.0 && fabs(lng) < 1048576.0))) {
+      ++nr;
+      const double sp = sin(lat), cp = cos(lat), st = sin(lng), ct = cos(lng);
+      id = cellid_from_point(P3{ct * cp, st * cp, sp}, kHilbert.pos);
+    }
+    out[i] = id;
+  }
+  if (n_reeval) *n_reeval = nr;
+}
+
+}  // extern "C"

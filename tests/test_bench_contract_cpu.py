@@ -33,7 +33,7 @@ def _check_reference_line(stdout):
 
 @needs_ref
 def test_reference_arm_prints_one_json_line():
-    r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "1"], cwd=ROOT,
+    r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "1", "--points", "4000000"], cwd=ROOT,
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert _check_reference_line(r.stdout)["n_gpus"] == 1
@@ -43,7 +43,7 @@ def test_reference_arm_prints_one_json_line():
 def test_reference_arm_under_torchrun_reports_from_rank_0_only():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                         "127.0.0.1", "--master-port", str(_free_port()), "bench.py", "--impl", "reference", "--gpus", "2",
-                        "--steps", "1", "--warmup", "1"], cwd=ROOT, capture_output=True, text=True, timeout=600)
+                        "--steps", "1", "--warmup", "1", "--points", "4000000"], cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert _check_reference_line(r.stdout)["n_gpus"] == 2
 

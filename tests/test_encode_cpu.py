@@ -217,3 +217,26 @@ def test_edge_neighbors_hostsim(hostsim, ref):
     out = np.empty((len(ids), 4), np.uint64)
     hostsim.hs_edge_neighbors(vp(ids), ctypes.c_size_t(len(ids)), vp(out))
     assert (out == ref.edge_neighbors(ids)).all()
+
+
+def test_strict_host_libm_mode_logic_equals_reference(hostsim, ref):
+    """The strict lat/lng mode (kernel filter -> correctly rounded ids -> host libm for the points whose leaf cell a 1-ulp
+    change of sin/cos could move), restated on the host from the same headers: ids == the reference's S2CellId(S2LatLng)
+    for every point, while only ~1e-5 of uniform points are re-evaluated. 16M uniform points, points on / next to cell
+    boundaries, and angles outside the device routines' domain."""
+    import ctypes
+    from s2geometry_b200 import synth
+    rng = np.random.default_rng(23)
+    sets = [synth.stream_sphere_latlng(9, 0, 16_000_000), boundary_latlngs(ref, 20000, 12),
+            np.concatenate([rng.uniform(-4e6, 4e6, (50000, 2)), 10.0 ** rng.uniform(6, 300, (5000, 2)),
+                            np.array([[np.inf, 1.0], [np.nan, 0.5], [0.5, np.nan], [0.0, 0.0], [np.pi / 2, 0.0], [0.0, np.pi / 4]])])]
+    for k, ll in enumerate(sets):
+        ll = np.ascontiguousarray(ll)
+        out = np.empty(len(ll), np.uint64)
+        nre = ctypes.c_uint64(0)
+        hostsim.hs_encode_latlng_strict(util.vp(ll), ctypes.c_size_t(len(ll)), util.vp(out), ctypes.byref(nre))
+        assert (out != ref.encode_latlng(ll, 30)).sum() == 0
+        if k == 0:
+            assert 0 < nre.value < 1e-4 * len(ll)
+        else:
+            assert nre.value > 0.1 * len(ll)

@@ -111,18 +111,87 @@ def test_points_on_leaf_cell_boundaries_vs_reference(torch_cuda, ref):
 
 
 def test_latlng_5M_vs_reference_and_flags(torch_cuda, ref):
-    """lat/lng ids use correctly-rounded sin/cos; glibc is not correctly rounded, so a mismatch is possible only
-    where the boundary flag is set. Expected mismatches at 5M points: ~0.01."""
+    """Default (S2B_LATLNG_HOST_LIBM) mode: lat/lng ids equal the reference's, evaluated with this process's libm, bit for
+    bit at every level. In S2B_LATLNG_CORRECTLY_ROUNDED mode the ids are those of correctly rounded sin/cos; glibc is not
+    correctly rounded, so a mismatch is possible only where the boundary flag is set."""
     from s2geometry_b200 import cellid, synth
     ll = synth.sphere_latlng(5_000_000, 2)
+    cellid.lat_lng_strict_stats(reset=True)
     got, flags = cellid.from_lat_lng(ll, return_boundary_flags=True)
     want = ref.encode_latlng(ll, 30)
-    bad = got != want
-    assert bad.sum() <= 2
-    assert (flags[bad] == 1).all()
-    assert flags.mean() < 1e-4
+    assert (got != want).sum() == 0
+    reevaluated, changed = cellid.lat_lng_strict_stats()
+    assert reevaluated == int(flags.sum()) and 0 < reevaluated < 1e-4 * len(ll)
     for lvl in (12, 20):
-        assert (cellid.from_lat_lng(ll, lvl) == ref.encode_latlng(ll, lvl)).sum() >= len(ll) - 1
+        assert (cellid.from_lat_lng(ll, lvl) != ref.encode_latlng(ll, lvl)).sum() == 0
+    old = cellid.set_lat_lng_mode(cellid.LATLNG_CORRECTLY_ROUNDED)
+    try:
+        cr, flags_cr = cellid.from_lat_lng(ll, return_boundary_flags=True)
+    finally:
+        cellid.set_lat_lng_mode(old)
+    bad = cr != want
+    assert bad.sum() <= 2 and (flags_cr[bad] == 1).all() and (flags_cr == flags).all()
+    assert (cr != got).sum() == bad.sum()
+
+
+def test_config2_100M_latlng_strict_vs_reference(torch_cuda, ref):
+    """BASELINE configs[1] at full size: 100M lat/lng -> ids at levels 12/20/30 + ToToken(level 30), EVERY id, token and
+    token length compared with the reference's S2CellId(S2LatLng) / parent / ToToken on the host: 0 mismatches, through the
+    host-pointer call and through the device-pointer strict call."""
+    torch = torch_cuda
+    from s2geometry_b200 import cellid, synth
+    n = 100_000_000
+    ll = synth.sphere_latlng(n, 2)
+    w_ids, w_tok, w_len = ref.encode_latlng_levels_tokens(ll, [12, 20, 30], 2, ref.hardware_threads())
+    cellid.lat_lng_strict_stats(reset=True)
+    ids, tok, ln = cellid.from_lat_lng_levels_tokens(ll, [12, 20, 30], 2)
+    reevaluated, changed = cellid.lat_lng_strict_stats(reset=True)
+    print("strict mode, 100M points: %d re-evaluated with the host libm, %d ids changed" % (reevaluated, changed))
+    for k in range(3):
+        assert int((ids[k] != w_ids[k]).sum()) == 0
+    assert int((tok != w_tok).sum()) == 0 and int((ln != w_len).sum()) == 0
+    assert 0 < reevaluated < 1e-4 * n
+    del ids, tok, ln
+    d_ids, d_tok, d_len = cellid.from_lat_lng_levels_tokens(torch.from_numpy(ll).cuda(), [12, 20, 30], 2)
+    assert cellid.lat_lng_strict_stats()[0] == reevaluated
+    for k in range(3):
+        assert bool((d_ids[k].cpu() == torch.from_numpy(w_ids[k].view(np.int64))).all())
+    assert bool((d_tok.cpu() == torch.from_numpy(w_tok)).all()) and bool((d_len.cpu() == torch.from_numpy(w_len)).all())
+
+
+def test_latlng_strict_on_cell_boundaries_and_odd_angles(torch_cuda, ref):
+    """The inputs where the libm matters most, all through the strict mode: 400k points ON leaf / face boundaries and a
+    few ulps off them (more sensitive points than the per-chunk list holds: the piecewise fallback runs), E7 input,
+    angles far outside S2LatLng::is_valid (|x| up to 1e300), infinities and NaN. Ids == the reference's in this process."""
+    torch = torch_cuda
+    from s2geometry_b200 import cellid
+    from tests.test_encode_cpu import boundary_latlngs
+    rng = np.random.default_rng(17)
+    bl = boundary_latlngs(ref, 20000, 10)
+    odd = np.concatenate([rng.uniform(-1e6, 1e6, (50000, 2)), rng.uniform(-4e6, 4e6, (50000, 2)),
+                          10.0 ** rng.uniform(6, 300, (20000, 2)) * rng.choice([-1.0, 1.0], (20000, 2)),
+                          np.array([[np.inf, 0.3], [0.3, -np.inf], [np.nan, 1.0], [1.0, np.nan], [0.0, 0.0], [-0.0, np.pi],
+                                    [np.pi / 2, 0.0], [-np.pi / 2, 2.0], [0.0, np.pi / 2], [0.0, -np.pi / 2], [0.0, np.pi / 4]])])
+    for ll in (bl, odd, np.tile(bl, (12, 1))):
+        want = ref.encode_latlng(ll, 30)
+        cellid.lat_lng_strict_stats(reset=True)
+        assert (cellid.from_lat_lng(ll, 30) != want).sum() == 0                                          # host-pointer path
+        host_stats = cellid.lat_lng_strict_stats(reset=True)
+        assert (cellid.from_lat_lng(torch.from_numpy(ll).cuda(), 30).cpu().numpy().view(np.uint64) != want).sum() == 0   # device path
+        assert cellid.lat_lng_strict_stats() == host_stats and host_stats[0] > 0.1 * len(bl)
+        w3, wt, wl = ref.encode_latlng_levels_tokens(ll, [5, 17, 30], 1, 0)
+        for src in (ll, torch.from_numpy(ll).cuda()):
+            g3, gt, gl = cellid.from_lat_lng_levels_tokens(src, [5, 17, 30], 1)
+            if not isinstance(g3, np.ndarray):
+                g3, gt, gl = g3.cpu().numpy().view(np.uint64), gt.cpu().numpy(), gl.cpu().numpy()
+            assert (g3 != w3).sum() == 0 and (gt != wt).sum() == 0 and (gl != wl).sum() == 0
+    e7 = np.concatenate([np.round(np.degrees(bl[:100000]) * 1e7).astype(np.int32),
+                         rng.integers(-1800000000, 1800000001, (400000, 2)).astype(np.int32),
+                         np.array([[0, 0], [900000000, 0], [-900000000, 1800000000], [450000000, 450000000], [0, 900000000],
+                                   [0, -900000000], [353000000, 450000000]], np.int32)])
+    want = ref.encode_latlng_e7(e7, 30)
+    assert (cellid.from_lat_lng_e7(e7) != want).sum() == 0
+    assert (cellid.from_lat_lng_e7(torch.from_numpy(e7).cuda()).cpu().numpy().view(np.uint64) != want).sum() == 0
 
 
 def test_full_size_properties(torch_cuda):
@@ -161,6 +230,7 @@ def test_fast_filter_equals_correctly_rounded_on_device(torch_cuda, ref):
     lib = _lib.load()
     ll = synth.sphere_latlng_cuda(100_000_000, 5, "cuda")
     bl = torch.from_numpy(boundary_latlngs(ref, 20000, 10)).cuda()
+    old_mode = cellid.set_lat_lng_mode(cellid.LATLNG_CORRECTLY_ROUNDED)   # this test is about the device's own definition
     try:
         fast = cellid.from_lat_lng(ll, 30)
         fast_b, flags_b = cellid.from_lat_lng(bl, 30, return_boundary_flags=True)
@@ -169,6 +239,7 @@ def test_fast_filter_equals_correctly_rounded_on_device(torch_cuda, ref):
         exact_b, flags_b2 = cellid.from_lat_lng(bl, 30, return_boundary_flags=True)
     finally:
         lib.s2b_diag_force_correctly_rounded(0)
+        cellid.set_lat_lng_mode(old_mode)
     assert bool((fast == exact).all())
     assert bool((fast_b == exact_b).all()) and bool((flags_b == flags_b2).all())
     assert float(flags_b.float().mean()) > 0.1
@@ -272,3 +343,15 @@ def test_edge_neighbors_on_gpu(torch_cuda, ref):
     assert (cellid.edge_neighbors(ids) == want).all()
     d = torch.from_numpy(ids.view(np.int64)).cuda()
     assert (cellid.edge_neighbors(d).cpu().numpy().view(np.uint64) == want).all()
+
+
+def test_synthetic_streams_device_equals_host(torch_cuda):
+    """The counter-based generators (bench.py's inputs) give the same bits on the device as the NumPy restatement, for
+    arbitrary slices of the stream: what makes the multi-GPU results comparable across N and with the reference arm."""
+    from s2geometry_b200 import synth
+    c = np.array([0.3, -0.5, 0.8])
+    for seed, first, n in ((2, 0, 300_000), (1000, 999_999_000, 100_000), (2**63 + 11, 2**45, 4097)):
+        assert np.array_equal(synth.stream_sphere_points_cuda(seed, first, n, "cuda").cpu().numpy(), synth.stream_sphere_points(seed, first, n))
+        assert np.array_equal(synth.stream_sphere_latlng_cuda(seed, first, n, "cuda").cpu().numpy(), synth.stream_sphere_latlng(seed, first, n))
+        assert np.array_equal(synth.stream_cap_points_cuda(seed, first, n, c, 0.2125, "cuda").cpu().numpy(), synth.stream_cap_points(seed, first, n, c, 0.2125))
+    assert synth.stream_sphere_points_cuda(1, 0, 0, "cuda").shape == (0, 3)

@@ -405,3 +405,50 @@ def test_error_paths_on_gpu(torch_cuda):
     q = ContainsPointQuery(ix, 1)
     assert bool((q.contains(view) == q.contains(pts)).all())
     torch.cuda.synchronize()
+
+
+def test_work_lists_hold_the_worst_case_mix_of_edge_and_interior_hits(torch_cuda):
+    """2^25 + 12345 uniform points in ONE round against an index that covers the whole sphere with 80 % edge-bearing and
+    20 % multi-clip interior cells: nearly every warp step appends to both work lists (which share one buffer from its two
+    ends) and keeps retiring partly used reservation chunks — the case the list capacity has to be sized for
+    (work_list_capacity in s2b_index.cu). Count / fill / histogram / per-shape results must equal what the cell of each
+    point implies, for every point."""
+    torch = torch_cuda
+    from s2geometry_b200 import cellid, synth
+    from s2geometry_b200.index import ContainsPointQuery, FlatIndex, ShapeIndex
+    level = 2
+    ids = []
+    for face in range(6):
+        for pos in range(4 ** level):
+            ids.append((face << 61) | (pos << (61 - 2 * level)) | (1 << (60 - 2 * level)))
+    ids = np.array(sorted(ids), np.uint64)
+    face_center = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [-1, 0, 0], [0, -1, 0], [0, 0, -1]], float)
+    clip_begin, shape, flags, edge_begin, v0, v1 = [0], [], [], [0], [], []
+    interior = np.arange(len(ids)) % 5 == 0
+    for k, cid in enumerate(ids):
+        if interior[k]:           # two clipped shapes, both containing the centre, no edges: an "interior list" hit
+            shape += [0, 1]; flags += [1 | (2 << 1)] * 2; edge_begin += [edge_begin[-1]] * 2
+        else:                     # one clipped shape with one (far away, tiny) edge: an "edge list" hit that crosses nothing
+            far = face_center[(int(cid >> np.uint64(61)) + 3) % 6]
+            a = far + np.array([1e-3, 2e-3, 3e-3]); b = far + np.array([2e-3, 1e-3, 3e-3])
+            v0.append(a / np.linalg.norm(a)); v1.append(b / np.linalg.norm(b))
+            shape += [0]; flags += [1 | (2 << 1)]; edge_begin += [edge_begin[-1] + 1]
+        clip_begin.append(len(shape))
+    flat = FlatIndex(2, ids, clip_begin, shape, flags, edge_begin, np.array(v0), np.array(v1))
+    ix = ShapeIndex(flat)
+    q = ContainsPointQuery(ix, 1)
+    n = (1 << 25) + 12345
+    pts = synth.stream_sphere_points_cuda(31, 0, n, "cuda")
+    cell = ix.locate_points(pts).long()
+    assert bool((cell >= 0).all())
+    is_interior = torch.from_numpy(interior).cuda()[cell]
+    want_count = torch.where(is_interior, 2, 1).to(torch.int32)
+    off, got_ids = q.containing_shape_ids(pts)
+    assert bool(((off[1:] - off[:-1]) == want_count).all())
+    assert bool((got_ids[off[:-1].long()] == 0).all())                                   # first id of every point is shape 0
+    second = (off[:-1].long() + 1)[is_interior]
+    assert bool((got_ids[second] == 1).all())
+    hist = q.shape_histogram(pts).cpu().numpy()
+    assert hist[0] == n and hist[1] == int(is_interior.sum())
+    assert bool((q.shape_contains(1, pts) == is_interior.to(torch.uint8)).all())
+    assert bool((q.contains(pts) == 1).all())

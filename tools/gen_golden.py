@@ -109,8 +109,25 @@ def shapes_wire_fixture(ref):
     np.savez_compressed(os.path.join(G, "shapes_wire.npz"), **out)
 
 
+def covering_fixture(ref):
+    """BASELINE configs[4]: the S2RegionCoverer covering (max_cells = 1000, default levels) of the 10k-vertex loop, computed
+    by the reference's own coverer over S2ShapeIndexRegion(MutableS2ShapeIndex{loop}); + the reference's answers for a fixed
+    query set (S2CellUnion::Contains(S2Point))."""
+    from tests import scenes
+    soup, v = scenes.loop_scene(10000)
+    ri = ref.index_create(soup)
+    ids = ri.covering(1000)
+    u, b, d = scenes.loop_points(v, 20000, 40000, 78)
+    q = np.concatenate([u, b, d])
+    np.savez_compressed(os.path.join(G, "covering_loop10k.npz"), cell_ids=ids, queries=q, contains=ref.cellunion_contains(ids, q, 1))
+    print("covering_loop10k.npz cells=%d queries=%d inside=%d" % (len(ids), len(q), ref.cellunion_contains(ids, q, 1).sum()))
+
+
 if __name__ == "__main__":
     ref = reflib.load()
+    if len(sys.argv) > 1 and sys.argv[1] == "covering":
+        covering_fixture(ref)
+        sys.exit(0)
     encode_fixture(ref)
     index_fixture(ref)
     wire_fixture(ref)
