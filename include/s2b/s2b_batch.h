@@ -102,6 +102,10 @@ class DeviceShapeIndex {
     s2b_built_index_destroy(built);
     return ok;
   }
+  // Multi-GPU (one process): copies the index onto every listed CUDA device; the batch queries below then shard their
+  // points over all replicas and all-reduce the per-shape counts (NCCL, or the library's own peer-memory reduction).
+  bool Replicate(const std::vector<int>& devices) { return h_ && s2b_index_replicate(h_, devices.data(), (int)devices.size()) == S2B_OK; }
+  int num_replicas() const { return s2b_index_num_replicas(h_); }
   bool ok() const { return h_ != nullptr; }
   int num_shape_ids() const { int32_t s = 0; if (h_) s2b_index_info(h_, nullptr, nullptr, nullptr, &s, nullptr); return s; }
   const S2bIndex* handle() const { return h_; }
@@ -116,7 +120,7 @@ class S2ContainsPointQueryBatch {
   explicit S2ContainsPointQueryBatch(const DeviceShapeIndex* index, S2VertexModel model = S2VertexModel::SEMI_OPEN)
       : index_(index), model_((int)model) {}
   // out[i] = Contains(points[i])
-  bool Contains(const Point* points, size_t n, uint8_t* out) const { return s2b_contains(index_->handle(), &points->x, n, model_, out) == S2B_OK; }
+  bool Contains(const Point* points, size_t n, uint8_t* out) const { return s2b_contains_multi(index_->handle(), &points->x, n, model_, out) == S2B_OK; }
   // out[i] = ShapeContains(shape_id, points[i])
   bool ShapeContains(int shape_id, const Point* points, size_t n, uint8_t* out) const {
     return s2b_shape_contains(index_->handle(), shape_id, &points->x, n, model_, out) == S2B_OK;
@@ -124,7 +128,7 @@ class S2ContainsPointQueryBatch {
   // counts[s] = |{ i : shape s contains points[i] }|  — VisitContainingShapeIds accumulated per shape (spatial join)
   bool CountContainingShapes(const Point* points, size_t n, std::vector<uint64_t>* counts) const {
     counts->assign((size_t)index_->num_shape_ids(), 0);
-    return s2b_shape_histogram(index_->handle(), &points->x, n, model_, counts->data()) == S2B_OK;
+    return s2b_shape_histogram_multi(index_->handle(), &points->x, n, model_, counts->data()) == S2B_OK;
   }
   // GetContainingShapeIds for every point, CSR: ids of point i are shape_ids[offsets[i] .. offsets[i+1])
   bool GetContainingShapeIds(const Point* points, size_t n, std::vector<uint32_t>* offsets, std::vector<int32_t>* shape_ids) const {

@@ -364,6 +364,42 @@ int s2b_containing_shapes_count_dev(const S2bIndex* index, const double* xyz_dev
 int s2b_containing_shapes_fill_dev(const S2bIndex* index, const double* xyz_dev, size_t n, int vertex_model,
                                    const uint32_t* offsets_dev, int32_t* shape_ids_out_dev, void* stream);
 
+/* --------------------------------------------------------------------------------------------------
+ * Multi-GPU driver (one process, every GPU of the box). The reference has no multi-device path; points
+ * are independent, so batches are sharded by contiguous range (shard k of R gets [k*n/R, (k+1)*n/R), sizes differing by
+ * at most one), the index is replicated, and the only exchange is the all-reduce of the uint64[num_shape_ids] hit
+ * histogram over NVLink.
+ *   s2b_index_replicate     copies the index GPU-to-GPU onto every listed device that does not hold it yet (the index's own
+ *                           device is replica 0 whether or not it is listed), creates one stream per replica, an NCCL
+ *                           communicator over the replica devices (ncclCommInitAll; NCCL is bound at run time) and enables
+ *                           peer access between them. Replicas are owned by `index` and freed by s2b_index_destroy.
+ *   s2b_index_set_reduce_mode  S2B_REDUCE_NCCL: ncclAllReduce(uint64, sum) on every replica's stream (the default when NCCL
+ *                           loaded); S2B_REDUCE_PEER: the library's own reduction — one small kernel per GPU that sums the
+ *                           peers' partial histograms with direct loads over NVLink peer memory, ordered behind the
+ *                           peers' query kernels with events. Returns the previous mode, or S2B_EUNSUPPORTED.
+ *   s2b_shape_histogram_multi / s2b_contains_multi   the host-pointer calls of the same name without _multi, sharded over
+ *                           the replicas (one pipeline and worker thread per GPU); without replicas they are the
+ *                           single-GPU calls.
+ *   s2b_shape_histogram_multi_dev   device-resident shards: shard k = n[k] points at xyz_dev[k] on replica k's device
+ *                           (s2b_index_replica_devices gives the order). Enqueues the query on each replica's own stream,
+ *                           then the all-reduce; counts_out_dev[k] (array and entries nullable) receives the GLOBAL
+ *                           histogram on device k. synchronize != 0 waits for all replicas' streams.
+ *   s2b_encode_*_multi      encoding sharded over `devices` (no index, no exchange); lat/lng follows s2b_set_latlng_mode. */
+#define S2B_REDUCE_NCCL 0
+#define S2B_REDUCE_PEER 1
+int s2b_index_replicate(S2bIndex* index, const int* devices, int ndev);
+int s2b_index_num_replicas(const S2bIndex* index);
+int s2b_index_replica_devices(const S2bIndex* index, int* devices_out, int capacity);
+int s2b_index_set_reduce_mode(S2bIndex* index, int mode);
+int s2b_shape_histogram_multi(const S2bIndex* index, const double* xyz, size_t n, int vertex_model, uint64_t* counts);
+int s2b_shape_histogram_multi_dev(const S2bIndex* index, const double* const* xyz_dev, const size_t* n, int vertex_model,
+                                  uint64_t* const* counts_out_dev, int synchronize);
+int s2b_contains_multi(const S2bIndex* index, const double* xyz, size_t n, int vertex_model, uint8_t* out);
+int s2b_encode_points_multi(const int* devices, int ndev, const double* xyz, size_t n, int level, uint64_t* ids_out);
+int s2b_encode_latlng_levels_tokens_multi(const int* devices, int ndev, const double* latlng_rad, size_t n, const int* levels,
+                                          int num_levels, uint64_t* ids_out, int token_level_index, char* tokens16_out,
+                                          uint8_t* len_out);
+
 /* Diagnostic: the index queries locate points with a single-precision pre-filter and fall back to the double-
  * precision Locate for every point the filter cannot decide with certainty (DESIGN.md K3 phase A0). on != 0 sends all
  * points through the double-precision path, which must give identical results (tests check it). Returns the old value. */

@@ -117,6 +117,15 @@ SIGNATURES = {
     "s2b_containing_shapes": (_i, [_vp, _vp, _sz, _i, _vp, _vp, _sz, _vp]),
     "s2b_containing_shapes_count_dev": (_i, [_vp, _vp, _sz, _i, _vp, _vp]),
     "s2b_containing_shapes_fill_dev": (_i, [_vp, _vp, _sz, _i, _vp, _vp, _vp]),
+    "s2b_index_replicate": (_i, [_vp, _vp, _i]),
+    "s2b_index_num_replicas": (_i, [_vp]),
+    "s2b_index_replica_devices": (_i, [_vp, _vp, _i]),
+    "s2b_index_set_reduce_mode": (_i, [_vp, _i]),
+    "s2b_shape_histogram_multi": (_i, [_vp, _vp, _sz, _i, _vp]),
+    "s2b_shape_histogram_multi_dev": (_i, [_vp, _vp, _vp, _i, _vp, _i]),
+    "s2b_contains_multi": (_i, [_vp, _vp, _sz, _i, _vp]),
+    "s2b_encode_points_multi": (_i, [_vp, _i, _vp, _sz, _i, _vp]),
+    "s2b_encode_latlng_levels_tokens_multi": (_i, [_vp, _i, _vp, _sz, _vp, _i, _vp, _i, _vp, _vp]),
     "s2b_exact_stage_count": (_i, [_vp, _i]),
     "s2b_diag_force_exact_locate": (_i, [_i]),
     "s2b_cellunion_contains": (_i, [_vp, _sz, _vp, _sz, _vp]),

@@ -14,6 +14,7 @@
 #include "s2b_core.cuh"
 #include "s2b_hilbert.h"
 #include "s2b_internal.h"
+#include "s2b_pipeline.h"
 
 namespace s2b {
 
@@ -42,12 +43,6 @@ int cuda_fail(cudaError_t e, const char* what) {
   return set_error(e == cudaErrorMemoryAllocation ? S2B_ENOMEM : S2B_ECUDA, "%s: %s", what, cudaGetErrorString(e));
 }
 
-#define S2B_CUDA(call)                                   \
-  do {                                                   \
-    cudaError_t e__ = (call);                            \
-    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
-  } while (0)
-
 int sm_count() {
   static thread_local int cached_dev = -1, cached = 0;
   int dev = 0;
@@ -59,140 +54,6 @@ int sm_count() {
     cached_dev = dev;
   }
   return cached;
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Chunked host<->device pipeline. One workspace per (thread, device): three slots of device buffers + streams.
-struct Slot {
-  cudaStream_t stream = nullptr;
-  void* in = nullptr;
-  void* out = nullptr;
-  size_t in_cap = 0, out_cap = 0;
-};
-
-struct Workspace {
-  int device = -1;
-  Slot slot[3];
-  int ensure(int dev, size_t in_bytes, size_t out_bytes) {
-    if (device != dev) {
-      release();
-      device = dev;
-    }
-    for (Slot& s : slot) {
-      if (!s.stream) S2B_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-      if (s.in_cap < in_bytes) {
-        if (s.in) cudaFree(s.in);
-        s.in = nullptr; s.in_cap = 0;
-        S2B_CUDA(cudaMalloc(&s.in, in_bytes));
-        s.in_cap = in_bytes;
-      }
-      if (s.out_cap < out_bytes) {
-        if (s.out) cudaFree(s.out);
-        s.out = nullptr; s.out_cap = 0;
-        S2B_CUDA(cudaMalloc(&s.out, out_bytes));
-        s.out_cap = out_bytes;
-      }
-    }
-    return S2B_OK;
-  }
-  void release() {
-    for (Slot& s : slot) {
-      if (s.in) cudaFree(s.in);
-      if (s.out) cudaFree(s.out);
-      if (s.stream) cudaStreamDestroy(s.stream);
-      s = Slot();
-    }
-  }
-};
-
-static thread_local Workspace t_ws;
-
-constexpr size_t kChunk = size_t(1) << 22;  // points per chunk (4 Mi): 64-100 MB per slot, >> launch overheads
-
-// One output stream of a pipelined call: host base pointer, bytes per point, and (for multi-array outputs) the
-// number of arrays laid out n apart on the host but chunk-size apart in the device slot.
-struct OutSpec { void* host; size_t bytes_per_point; int arrays; };
-
-struct NoChunkHook {
-  int operator()(int, size_t, size_t, const void*, void**, cudaStream_t) const { return S2B_OK; }
-};
-
-// launch(in_dev, count, out_dev[], stream): out_dev[j] points at the slot region for OutSpec j.
-// done(slot, off, count, in_dev, out_dev[], stream) runs on the host once chunk [off, off + count) has fully landed in
-// the caller's buffers (its slot stream is idle and its device buffers are still intact), in chunk order.
-template <class Launch, class Done = NoChunkHook>
-int run_pipelined(const void* in_host, size_t in_bpp, size_t n, const OutSpec* outs, int n_outs, Launch launch, Done done = Done()) {
-  int dev = 0;
-  S2B_CUDA(cudaGetDevice(&dev));
-  size_t chunk = n < kChunk ? n : kChunk;
-  size_t out_bytes = 0;
-  auto region = [&](int j) { return outs[j].host ? ((outs[j].bytes_per_point * outs[j].arrays * chunk + 255) / 256) * 256 : size_t(0); };
-  for (int j = 0; j < n_outs; ++j) out_bytes += region(j);
-  int rc = t_ws.ensure(dev, in_bpp * chunk, out_bytes ? out_bytes : 256);
-  if (rc) return rc;
-  // Once copies are in flight they reference the caller's buffers: on any failure drain the slot streams before
-  // returning, so nothing touches those buffers after the call has reported an error.
-  auto drain_and_return = [&](int code) {
-    for (Slot& s : t_ws.slot) cudaStreamSynchronize(s.stream);
-    cudaGetLastError();
-    return code;
-  };
-#define S2B_CUDA_DRAIN(call)                                                    \
-  do {                                                                          \
-    cudaError_t e__ = (call);                                                   \
-    if (e__ != cudaSuccess) return drain_and_return(cuda_fail(e__, #call));     \
-  } while (0)
-  struct Pending { bool live = false; size_t off = 0, cnt = 0; } pending[3];
-  auto slot_regions = [&](Slot& s, void** out_dev) {
-    char* cur = (char*)s.out;
-    for (int j = 0; j < n_outs; ++j) {
-      out_dev[j] = cur;
-      cur += region(j);
-    }
-  };
-  auto complete = [&](int si) -> int {   // slot stream already synchronised
-    if (!pending[si].live) return S2B_OK;
-    pending[si].live = false;
-    void* out_dev[4] = {nullptr, nullptr, nullptr, nullptr};
-    slot_regions(t_ws.slot[si], out_dev);
-    return done(si, pending[si].off, pending[si].cnt, t_ws.slot[si].in, out_dev, t_ws.slot[si].stream);
-  };
-  size_t k = 0;
-  for (size_t off = 0; off < n; off += chunk, ++k) {
-    const int si = (int)(k % 3);
-    Slot& s = t_ws.slot[si];
-    size_t cnt = n - off < chunk ? n - off : chunk;
-    // the slot's previous D2H must have drained before its buffers are reused
-    if (k >= 3) {
-      S2B_CUDA_DRAIN(cudaStreamSynchronize(s.stream));
-      int drc = complete(si);
-      if (drc != S2B_OK) return drain_and_return(drc);
-    }
-    S2B_CUDA_DRAIN(cudaMemcpyAsync(s.in, (const char*)in_host + off * in_bpp, cnt * in_bpp, cudaMemcpyHostToDevice, s.stream));
-    void* out_dev[4] = {nullptr, nullptr, nullptr, nullptr};
-    slot_regions(s, out_dev);
-    pending[si].live = true; pending[si].off = off; pending[si].cnt = cnt;
-    int lrc = launch(si, s.in, cnt, out_dev, s.stream);
-    if (lrc != S2B_OK) return drain_and_return(lrc);
-    for (int j = 0; j < n_outs; ++j) {
-      if (!outs[j].host) continue;
-      for (int a = 0; a < outs[j].arrays; ++a) {
-        // device arrays are cnt apart (the kernels index array a at base + a*cnt), host arrays n apart
-        S2B_CUDA_DRAIN(cudaMemcpyAsync((char*)outs[j].host + ((size_t)a * n + off) * outs[j].bytes_per_point,
-                                       (char*)out_dev[j] + (size_t)a * cnt * outs[j].bytes_per_point,
-                                       cnt * outs[j].bytes_per_point, cudaMemcpyDeviceToHost, s.stream));
-      }
-    }
-  }
-  // drain in chunk order: the oldest pending chunk sits in slot k % 3
-  for (size_t d = 0; d < 3; ++d) {
-    const int si = (int)((k + d) % 3);
-    S2B_CUDA_DRAIN(cudaStreamSynchronize(t_ws.slot[si].stream));
-    int drc = complete(si);
-    if (drc != S2B_OK) return drain_and_return(drc);
-  }
-#undef S2B_CUDA_DRAIN
-  return S2B_OK;
 }
 
 static int check_levels(const int* levels, int num_levels, LevelSpec* out) {
@@ -216,30 +77,35 @@ static int check_levels(const int* levels, int num_levels, LevelSpec* out) {
 // over the propagated bound, s2b_sincos.cuh) plus every angle outside the device routines' domain. Those points — and
 // only those — are re-evaluated here with the calling process's sin/cos and the same IEEE projection, which by
 // construction is the value the reference computes in this process. Everything else is provably libm-independent.
+// One list of boundary-sensitive points: device buffer = 32-byte header (the counter) + cap records, and a pinned host
+// mirror, so the counter and the first records come back in ONE copy.
+constexpr size_t kFixHeader = 32;
 struct FixBuf {
-  FixRecord* d_list = nullptr;
-  uint32_t* d_count = nullptr;
+  char* d = nullptr;
+  char* h = nullptr;             // pinned
   FixPatch* d_patch = nullptr;
-  FixRecord* h_list = nullptr;   // pinned
-  uint32_t* h_count = nullptr;   // pinned
+  cudaEvent_t ev = nullptr;
   uint32_t cap = 0, patch_cap = 0;
   int device = -1;
+  uint32_t* d_count() const { return (uint32_t*)d; }
+  FixRecord* d_list() const { return (FixRecord*)(d + kFixHeader); }
+  uint32_t h_count() const { return *(const volatile uint32_t*)h; }
+  FixRecord* h_list() const { return (FixRecord*)(h + kFixHeader); }
   void release() {
-    if (d_list) cudaFree(d_list);
-    if (d_count) cudaFree(d_count);
+    if (d) cudaFree(d);
     if (d_patch) cudaFree(d_patch);
-    if (h_list) cudaFreeHost(h_list);
-    if (h_count) cudaFreeHost(h_count);
+    if (h) cudaFreeHost(h);
+    if (ev) cudaEventDestroy(ev);
     *this = FixBuf();
   }
   int ensure(int dev, uint32_t want) {
     if (device == dev && cap >= want) return S2B_OK;
     release();
     device = dev;
-    S2B_CUDA(cudaMalloc(&d_list, sizeof(FixRecord) * (size_t)want));
-    S2B_CUDA(cudaMalloc(&d_count, sizeof(uint32_t)));
-    S2B_CUDA(cudaMallocHost(&h_list, sizeof(FixRecord) * (size_t)want));
-    S2B_CUDA(cudaMallocHost(&h_count, sizeof(uint32_t)));
+    const size_t bytes = kFixHeader + sizeof(FixRecord) * (size_t)want;
+    S2B_CUDA(cudaMalloc((void**)&d, bytes));
+    S2B_CUDA(cudaMallocHost((void**)&h, bytes));
+    S2B_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     cap = want;
     return S2B_OK;
   }
@@ -251,9 +117,15 @@ struct FixBuf {
     patch_cap = want;
     return S2B_OK;
   }
+  void attach(EncodeOut* o) const { o->fix_list = d_list(); o->fix_count = d_count(); o->fix_cap = cap; }
+  // after the kernel: counter + the first `eager` records to the host, in one copy
+  cudaError_t fetch(uint32_t eager, cudaStream_t st) const {
+    return cudaMemcpyAsync(h, d, kFixHeader + sizeof(FixRecord) * (size_t)(eager < cap ? eager : cap), cudaMemcpyDeviceToHost, st);
+  }
 };
-static thread_local FixBuf t_fix_slot[3];   // host-pointer pipeline: one per slot
-static thread_local FixBuf t_fix_dev;       // s2b_encode_latlng_strict_dev
+constexpr int kFixSubBatches = 8;
+static thread_local FixBuf t_fix_slot[3];                 // host-pointer pipeline: one per slot
+static thread_local FixBuf t_fix_dev[kFixSubBatches];     // s2b_encode_latlng_strict_dev: one per sub-batch
 
 // S2CellId(S2LatLng::FromRadians(lat, lng)) with THIS process's libm: S2LatLng::ToPoint (s2latlng.cc:68-77; SinCos() =
 // {sin(x), cos(x)}, s1angle.h:343-357) then S2CellId(S2Point) (s2cell_id.cc:309-315). Only ever applied to the
@@ -264,6 +136,8 @@ static uint64_t leaf_id_host_libm(double lat, double lng) {
   const P3 p{cos_theta * cos_phi, sin_theta * cos_phi, sin_phi};
   return cellid_from_point(p, kHilbert.pos);
 }
+
+constexpr uint32_t kFixEagerPiece = 1u << 10;
 
 // Re-evaluates `c` records and appends the ones whose leaf id changes.
 static void reevaluate(const FixRecord* recs, size_t c, std::vector<FixPatch>* changed) {
@@ -292,34 +166,27 @@ static void reevaluate(const FixRecord* recs, size_t c, std::vector<FixPatch>* c
   g_strict_changed.fetch_add(changed->size() - before, std::memory_order_relaxed);
 }
 
-// Gathers the patches of points [0, n) of a device-resident batch. `o` describes where the kernel writes (device
-// pointers; fix fields are filled in here). launched: the full-range kernel already ran with fb's list attached and
-// *fb.h_count holds its counter (records beyond `have` still to be fetched). Synchronises `st`.
+// Turns the list of one launch over points [0, n) of `in_dev` into patches. On entry the launch has completed and
+// fb.h holds its counter and the first `eager` records (FixBuf::fetch). `o` describes where that launch wrote (device
+// pointers). May enqueue further copies / launches on `st` and synchronise it.
 static int collect_patches(InputKind kind, const void* in_dev, size_t in_bpp, size_t n, EncodeOut o, cudaStream_t st, FixBuf& fb,
-                           bool launched, uint32_t have, std::vector<FixPatch>* changed) {
-  const size_t stride = o.ids_stride ? o.ids_stride : n;
-  const uint64_t base = o.index_base;
-  o.ids_stride = stride;
-  o.fix_list = fb.d_list; o.fix_count = fb.d_count; o.fix_cap = fb.cap;
-  if (!launched) {
-    S2B_CUDA(cudaMemsetAsync(fb.d_count, 0, sizeof(uint32_t), st));
-    cudaError_t e = launch_encode(kind, in_dev, n, o, st);
-    if (e != cudaSuccess) return cuda_fail(e, "encode launch");
-    S2B_CUDA(cudaMemcpyAsync(fb.h_count, fb.d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    S2B_CUDA(cudaStreamSynchronize(st));
-    have = 0;
-  }
-  const uint32_t c = *fb.h_count;
+                           uint32_t eager, std::vector<FixPatch>* changed) {
+  const uint32_t c = fb.h_count();
+  if (c == 0) return S2B_OK;
   if (c <= fb.cap) {
-    if (c > have) {
-      S2B_CUDA(cudaMemcpyAsync(fb.h_list + have, fb.d_list + have, sizeof(FixRecord) * (size_t)(c - have), cudaMemcpyDeviceToHost, st));
+    if (c > eager) {
+      S2B_CUDA(cudaMemcpyAsync(fb.h_list() + eager, fb.d_list() + eager, sizeof(FixRecord) * (size_t)(c - eager), cudaMemcpyDeviceToHost, st));
       S2B_CUDA(cudaStreamSynchronize(st));
     }
-    reevaluate(fb.h_list, c, changed);
+    reevaluate(fb.h_list(), c, changed);
     return S2B_OK;
   }
   // More sensitive points than the list holds (input concentrated on cell boundaries): redo the range in pieces of
   // fb.cap points, each of which fits by construction. The kernel rewrites identical outputs.
+  const size_t stride = o.ids_stride ? o.ids_stride : n;
+  const uint64_t base = o.index_base;
+  o.ids_stride = stride;
+  fb.attach(&o);
   for (size_t off = 0; off < n; off += fb.cap) {
     const size_t cnt = n - off < fb.cap ? n - off : fb.cap;
     EncodeOut q = o;
@@ -328,16 +195,17 @@ static int collect_patches(InputKind kind, const void* in_dev, size_t in_bpp, si
     q.tokens16 = o.tokens16 ? o.tokens16 + 16 * off : nullptr;
     q.token_len = o.token_len ? o.token_len + off : nullptr;
     q.index_base = base + off;
-    S2B_CUDA(cudaMemsetAsync(fb.d_count, 0, sizeof(uint32_t), st));
+    S2B_CUDA(cudaMemsetAsync(fb.d_count(), 0, sizeof(uint32_t), st));
     cudaError_t e = launch_encode(kind, (const char*)in_dev + off * in_bpp, cnt, q, st);
     if (e != cudaSuccess) return cuda_fail(e, "encode launch");
-    S2B_CUDA(cudaMemcpyAsync(fb.h_count, fb.d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    S2B_CUDA(fb.fetch(kFixEagerPiece, st));
     S2B_CUDA(cudaStreamSynchronize(st));
-    const uint32_t cc = *fb.h_count;
-    if (cc == 0) continue;
-    S2B_CUDA(cudaMemcpyAsync(fb.h_list, fb.d_list, sizeof(FixRecord) * (size_t)cc, cudaMemcpyDeviceToHost, st));
-    S2B_CUDA(cudaStreamSynchronize(st));
-    reevaluate(fb.h_list, cc, changed);
+    const uint32_t cc = fb.h_count();
+    if (cc > kFixEagerPiece) {
+      S2B_CUDA(cudaMemcpyAsync(fb.h_list() + kFixEagerPiece, fb.d_list() + kFixEagerPiece, sizeof(FixRecord) * (size_t)(cc - kFixEagerPiece), cudaMemcpyDeviceToHost, st));
+      S2B_CUDA(cudaStreamSynchronize(st));
+    }
+    reevaluate(fb.h_list(), cc, changed);
   }
   return S2B_OK;
 }
@@ -347,10 +215,11 @@ static bool strict_latlng(InputKind kind) { return kind != kInXYZ && g_latlng_mo
 constexpr uint32_t kFixCapChunk = 1u << 16;   // list capacity per 4Mi-point chunk of the host pipeline (1000x the uniform rate)
 constexpr uint32_t kFixEager = 1u << 12;      // records copied back with the chunk without waiting for the count
 
-// tok_level_index < 0: no tokens.
-static int encode_host(InputKind kind, const void* in, size_t in_bpp, size_t n, const int* levels, int num_levels,
-                       uint64_t* ids_out, uint8_t* flags_out, int tok_level_index = -1, char* tok_out = nullptr,
-                       uint8_t* tok_len_out = nullptr) {
+// tok_level_index < 0: no tokens. ids_stride: points between the per-level id arrays in ids_out (0 = n; the multi-GPU
+// driver passes the whole batch's size while each GPU fills its own range).
+int encode_host(InputKind kind, const void* in, size_t in_bpp, size_t n, const int* levels, int num_levels,
+                uint64_t* ids_out, uint8_t* flags_out, int tok_level_index, char* tok_out, uint8_t* tok_len_out, size_t ids_stride) {
+  if (ids_stride == 0) ids_stride = n;
   LevelSpec lv;
   int rc = check_levels(levels, num_levels, &lv);
   if (rc) return rc;
@@ -378,36 +247,32 @@ static int encode_host(InputKind kind, const void* in, size_t in_bpp, size_t n, 
     return o;
   };
   std::vector<FixPatch> changed;
-  OutSpec outs[4] = {{ids_out, 8, num_levels}, {flags_out, 1, 1}, {tok_out, 16, 1}, {tok_len_out, 1, 1}};
+  OutSpec outs[4] = {{ids_out, 8, num_levels, ids_stride}, {flags_out, 1, 1}, {tok_out, 16, 1}, {tok_len_out, 1, 1}};
   return run_pipelined(
       in, in_bpp, n, outs, 4,
       [&](int si, const void* in_dev, size_t cnt, void** out_dev, cudaStream_t st) {
         EncodeOut o = make_out(out_dev);
         if (strict) {
           FixBuf& fb = t_fix_slot[si];
-          o.fix_list = fb.d_list; o.fix_count = fb.d_count; o.fix_cap = fb.cap;
-          S2B_CUDA(cudaMemsetAsync(fb.d_count, 0, sizeof(uint32_t), st));
+          fb.attach(&o);
+          S2B_CUDA(cudaMemsetAsync(fb.d_count(), 0, sizeof(uint32_t), st));
         }
         cudaError_t e = launch_encode(kind, in_dev, cnt, o, st);
         if (e != cudaSuccess) return cuda_fail(e, "encode launch");
-        if (strict) {
-          FixBuf& fb = t_fix_slot[si];
-          S2B_CUDA(cudaMemcpyAsync(fb.h_count, fb.d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-          S2B_CUDA(cudaMemcpyAsync(fb.h_list, fb.d_list, sizeof(FixRecord) * kFixEager, cudaMemcpyDeviceToHost, st));
-        }
+        if (strict) S2B_CUDA(t_fix_slot[si].fetch(kFixEager, st));
         return S2B_OK;
       },
       [&](int si, size_t off, size_t cnt, const void* in_dev, void** out_dev, cudaStream_t st) {
         if (!strict) return S2B_OK;
         FixBuf& fb = t_fix_slot[si];
-        if (*fb.h_count == 0) return S2B_OK;
+        if (fb.h_count() == 0) return S2B_OK;
         changed.clear();
-        int crc = collect_patches(kind, in_dev, in_bpp, cnt, make_out(out_dev), st, fb, true, kFixEager, &changed);
+        int crc = collect_patches(kind, in_dev, in_bpp, cnt, make_out(out_dev), st, fb, kFixEager, &changed);
         if (crc) return crc;
         // records carry chunk-local indices (index_base 0); the chunk's results are already in the caller's arrays
         for (const FixPatch& p : changed) {
           const size_t i = off + (size_t)p.index;
-          for (int k = 0; k < num_levels; ++k) ids_out[(size_t)k * n + i] = cellid_parent(p.id, lv.level[k]);
+          for (int k = 0; k < num_levels; ++k) ids_out[(size_t)k * ids_stride + i] = cellid_parent(p.id, lv.level[k]);
           if (tok_level_index >= 0) {
             uint32_t w[4];
             const int len = cellid_to_token(cellid_parent(p.id, lv.level[tok_level_index]), w);
@@ -445,21 +310,56 @@ static int encode_dev(InputKind kind, const void* in, size_t n, const int* level
     if (e != cudaSuccess) return cuda_fail(e, "encode launch");
     return S2B_OK;
   }
-  // Strict: kernel + the list of boundary-sensitive points -> host libm -> patch kernel for the ids that differ.
+  // Strict: kernel -> list of boundary-sensitive points -> host libm -> patch kernel for the ids that differ. The batch
+  // is cut into up to kFixSubBatches launches enqueued back to back; while the GPU runs launch s + 1 the host
+  // re-evaluates the list of launch s, so only the last list's host work (and one small copy) is exposed.
   int dev = 0;
   S2B_CUDA(cudaGetDevice(&dev));
-  const size_t want = n / 128 < (1u << 16) ? (1u << 16) : (n / 128 > (1u << 24) ? (1u << 24) : n / 128);
-  rc = t_fix_dev.ensure(dev, (uint32_t)want);
-  if (rc) return rc;
+  const size_t in_bpp = kind == kInLatLngRad ? 16 : 8;
+  size_t subs = (n + ((size_t)1 << 23) - 1) >> 23;
+  if (subs > (size_t)kFixSubBatches) subs = kFixSubBatches;
+  const size_t sub = ((n + subs - 1) / subs + 255) / 256 * 256;
+  const size_t want = sub / 128 < (1u << 14) ? (1u << 14) : sub / 128;
+  o.ids_stride = n;
+  auto sub_out = [&](size_t off) {
+    EncodeOut q = o;
+    q.ids = o.ids + off;
+    q.flags = o.flags ? o.flags + off : nullptr;
+    q.tokens16 = o.tokens16 ? o.tokens16 + 16 * off : nullptr;
+    q.token_len = o.token_len ? o.token_len + off : nullptr;
+    q.index_base = off;
+    return q;
+  };
+  size_t launched = 0;
+  for (size_t off = 0; off < n; off += sub, ++launched) {
+    FixBuf& fb = t_fix_dev[launched];
+    rc = fb.ensure(dev, (uint32_t)want);
+    if (rc) return rc;
+    EncodeOut q = sub_out(off);
+    fb.attach(&q);
+    S2B_CUDA(cudaMemsetAsync(fb.d_count(), 0, sizeof(uint32_t), st));
+    cudaError_t e = launch_encode(kind, (const char*)in + off * in_bpp, n - off < sub ? n - off : sub, q, st);
+    if (e != cudaSuccess) return cuda_fail(e, "encode launch");
+    S2B_CUDA(fb.fetch(kFixEager, st));
+    S2B_CUDA(cudaEventRecord(fb.ev, st));
+  }
   std::vector<FixPatch> changed;
-  rc = collect_patches(kind, in, kind == kInLatLngRad ? 16 : 8, n, o, st, t_fix_dev, false, 0, &changed);
-  if (rc) return rc;
+  size_t k = 0;
+  for (size_t off = 0; off < n; off += sub, ++k) {
+    FixBuf& fb = t_fix_dev[k];
+    S2B_CUDA(cudaEventSynchronize(fb.ev));
+    rc = collect_patches(kind, (const char*)in + off * in_bpp, in_bpp, n - off < sub ? n - off : sub, sub_out(off), st, fb, kFixEager, &changed);
+    if (rc) return rc;
+  }
+  FixBuf& pb = t_fix_dev[0];
   for (size_t off = 0; off < changed.size(); off += (1u << 20)) {
     const uint32_t m = (uint32_t)(changed.size() - off < (1u << 20) ? changed.size() - off : (1u << 20));
-    rc = t_fix_dev.ensure_patches(m);
+    rc = pb.ensure_patches(m);
     if (rc) return rc;
-    S2B_CUDA(cudaMemcpyAsync(t_fix_dev.d_patch, changed.data() + off, sizeof(FixPatch) * m, cudaMemcpyHostToDevice, st));
-    cudaError_t e = launch_encode_patch(t_fix_dev.d_patch, m, o, n, st);
+    S2B_CUDA(cudaMemcpyAsync(pb.d_patch, changed.data() + off, sizeof(FixPatch) * m, cudaMemcpyHostToDevice, st));
+    EncodeOut whole = o;
+    whole.index_base = 0;
+    cudaError_t e = launch_encode_patch(pb.d_patch, m, whole, n, st);
     if (e != cudaSuccess) return cuda_fail(e, "patch launch");
     S2B_CUDA(cudaStreamSynchronize(st));   // `changed` is pageable host memory
   }

@@ -10,6 +10,8 @@
 // pre-filter of s2b_index.cu.)
 //
 // Algorithmic traffic per point: xyz 24 B in + 8 B per level out; lat/lng 16 B (E7: 8 B) in + 8 B per level out.
+#include <atomic>
+
 #include "s2b_core.cuh"
 #include "s2b_hilbert.h"
 #include "s2b_internal.h"
@@ -21,12 +23,12 @@ __device__ const HilbertTables g_hilbert = kHilbert;
 __device__ uint16_t g_hilbert_wide[16384];   // uploaded on first use per device (ensure_wide_table)
 
 static cudaError_t ensure_wide_table() {
-  static thread_local int done_for_device = -1;
+  static std::atomic<uint64_t> done_mask{0};   // bit d: device d holds the table (one host thread may drive several GPUs)
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess || dev == done_for_device) return e;
+  if (e != cudaSuccess || (dev < 64 && ((done_mask.load(std::memory_order_acquire) >> dev) & 1))) return e;
   e = cudaMemcpyToSymbol(g_hilbert_wide, wide_hilbert_host(), 16384 * sizeof(uint16_t));
-  if (e == cudaSuccess) done_for_device = dev;
+  if (e == cudaSuccess && dev < 64) done_mask.fetch_or(1ull << dev, std::memory_order_release);
   return e;
 }
 __device__ const double g_sincos_tab[sc_tab::kTableSize][4] = {

@@ -7,6 +7,7 @@
 // Index arrays are read through the read-only path; points are streamed (24 B in, 1 B / a few atomics out).
 #include <cub/device/device_scan.cuh>
 
+#include <atomic>
 #include <cstdlib>
 #include <new>
 #include <vector>
@@ -25,12 +26,12 @@ __device__ const HilbertTables g_hilbert_ix = kHilbert;
 __device__ uint16_t g_hilbert_wide_ix[16384];   // uploaded on first use per device
 
 static cudaError_t ensure_wide_table_ix() {
-  static thread_local int done_for_device = -1;
+  static std::atomic<uint64_t> done_mask{0};   // bit d: device d holds the table (one host thread may drive several GPUs)
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess || dev == done_for_device) return e;
+  if (e != cudaSuccess || (dev < 64 && ((done_mask.load(std::memory_order_acquire) >> dev) & 1))) return e;
   e = cudaMemcpyToSymbol(g_hilbert_wide_ix, wide_hilbert_host(), 16384 * sizeof(uint16_t));
-  if (e == cudaSuccess) done_for_device = dev;
+  if (e == cudaSuccess && dev < 64) done_mask.fetch_or(1ull << dev, std::memory_order_release);
   return e;
 }
 
@@ -523,15 +524,15 @@ constexpr size_t kRoundPoints = size_t(1) << 26;
 // The work list comes from the stream-ordered allocator; keep freed blocks cached in the pool (the default release
 // threshold of 0 hands them back to the driver at every synchronisation, which costs milliseconds per call).
 static void keep_pool_memory_once() {
-  static thread_local int done_for_device = -1;
+  static std::atomic<uint64_t> done_mask{0};
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for_device) return;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev >= 64 || ((done_mask.load() >> dev) & 1)) return;
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
     unsigned long long keep = ~0ull;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
   }
-  done_for_device = dev;
+  done_mask.fetch_or(1ull << dev);
 }
 
 // Diagnostics (s2b_diag_force_exact_locate): skip the FP32 pre-filter, every point goes through the FP64 Locate.
@@ -724,6 +725,7 @@ int s2b_index_create_from_cellunion(const uint64_t* sorted_ids, size_t m, S2bInd
 
 void s2b_index_destroy(S2bIndex* ix) {
   if (!ix) return;
+  if (ix->replicas) { s2b_replica_set_destroy(ix->replicas); ix->replicas = nullptr; }
   int cur = 0;
   cudaGetDevice(&cur);
   if (cur != ix->device) cudaSetDevice(ix->device);

@@ -5,6 +5,9 @@
 
 #include "s2b_contains.cuh"
 
+struct S2bReplicaSet;                            // s2b_multi.cu: the copies of this index on other GPUs + the reduction plumbing
+void s2b_replica_set_destroy(S2bReplicaSet* set);
+
 struct S2bIndex {
   int device = 0;
   s2b::FlatIndexView view{};
@@ -13,5 +16,6 @@ struct S2bIndex {
   size_t blob_bytes = 0;
   uint64_t num_clips = 0, num_edges = 0;
   int32_t* edge_ids = nullptr;   // optional (s2b_index_set_edge_ids): shape-local id of every clipped edge, for VisitIncidentEdges
+  S2bReplicaSet* replicas = nullptr;             // set by s2b_index_replicate (owned by the primary index)
   uint64_t unsupported_region_edges = 0;   // edges whose RobustCrossProd needs the stages s2b_region.cuh does not restate
 };

@@ -46,6 +46,10 @@ cudaError_t launch_to_latlng(const uint64_t* ids_dev, size_t n, double* latlng_d
 cudaError_t launch_from_token(const char* tokens16_dev, const uint8_t* len_dev, size_t n, uint64_t* ids_dev, cudaStream_t stream);
 cudaError_t launch_to_token(const uint64_t* ids_dev, size_t n, char* tokens16_dev, uint8_t* len_dev, cudaStream_t stream);
 
+// The host-pointer encode pipeline (s2b_capi.cu), shared with the multi-GPU driver. tok_level_index < 0: no tokens.
+int encode_host(InputKind kind, const void* in, size_t in_bpp, size_t n, const int* levels, int num_levels, uint64_t* ids_out,
+                uint8_t* flags_out, int tok_level_index = -1, char* tok_out = nullptr, uint8_t* tok_len_out = nullptr, size_t ids_stride = 0);
+
 void count_launch();
 // Host copy of the 16384-entry 6-bit Hilbert table (built once); each .cu uploads it to its own __device__ array.
 const uint16_t* wide_hilbert_host();

@@ -5,6 +5,8 @@
 #include <cstring>
 #include <vector>
 
+#include <cuda_runtime_api.h>
+
 #include "s2b/s2b_batch.h"
 
 #define CHECK(c) do { if (!(c)) { std::fprintf(stderr, "CHECK failed %s:%d: %s (%s)\n", __FILE__, __LINE__, #c, s2b::LastError()); return 1; } } while (0)
@@ -133,6 +135,92 @@ int main() {
     std::vector<uint64_t> counts;
     s2b::Point on_face2 = {0.0, 0.0, 1.0};   // the centre of face 2 lies in none of the four cells
     CHECK(ci.CountPointsPerLabel(&on_face2, 1, &counts) && counts.size() == 5 && counts[1] + counts[2] + counts[3] + counts[4] == 0);
+  }
+
+  // Multi-GPU driver behind the C ABI: shard over every visible GPU (2 on the test box; 1 still runs every code path but
+  // the exchange), results must equal the single-GPU calls; both reductions (NCCL and the library's peer-memory kernel).
+  {
+    const int ngpu = s2b_device_count() < 8 ? s2b_device_count() : 8;
+    CHECK(ngpu >= 1);
+    std::vector<int> devices;
+    for (int d = 0; d < ngpu; ++d) devices.push_back(d);
+    // a scene with some weight: 300 small squares on a grid, 3,000,001 pseudo-random points (splitmix-style hash)
+    std::vector<s2b::Point> v;
+    std::vector<int8_t> dim; std::vector<uint32_t> scb = {0}, cvb = {0};
+    for (int a = 0; a < 20; ++a)
+      for (int b = 0; b < 15; ++b) {
+        const double lat = -60 + 8.0 * b, lng = -170 + 17.0 * a, h = 3.0;
+        v.push_back(FromDegrees(lat, lng)); v.push_back(FromDegrees(lat, lng + h)); v.push_back(FromDegrees(lat + h, lng + h)); v.push_back(FromDegrees(lat + h, lng));
+        dim.push_back(2); scb.push_back((uint32_t)dim.size()); cvb.push_back((uint32_t)v.size());
+      }
+    s2b::DeviceShapeIndex big;
+    CHECK(big.InitFromShapes((int)dim.size(), dim.data(), scb.data(), cvb.data(), &v[0].x));
+    const size_t n = 3000001;
+    std::vector<s2b::Point> p(n);
+    std::vector<s2b::LatLng> pll(n);
+    uint64_t st = 12345;
+    auto next = [&] { uint64_t z = (st += 0x9E3779B97F4A7C15ull); z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return (double)((z ^ (z >> 31)) >> 11) * (1.0 / 9007199254740992.0); };
+    for (size_t i = 0; i < n; ++i) {
+      const double z = 2 * next() - 1, t = 2 * M_PI * next(), r = std::sqrt(1 - z * z);
+      p[i] = s2b::Point{r * std::cos(t), r * std::sin(t), z};
+      pll[i] = s2b::LatLng{std::asin(z), t - M_PI};
+    }
+    s2b::S2ContainsPointQueryBatch query(&big);
+    std::vector<uint64_t> single, multi;
+    std::vector<uint8_t> in1(n), inN(n);
+    CHECK(query.CountContainingShapes(p.data(), n, &single));         // no replicas yet: the single-GPU path
+    CHECK(query.Contains(p.data(), n, in1.data()));
+    CHECK(big.Replicate(devices) && big.num_replicas() == ngpu);
+    uint64_t hits = 0;
+    for (uint64_t c : single) hits += c;
+    CHECK(hits > 1000);
+    for (int mode : {S2B_REDUCE_NCCL, S2B_REDUCE_PEER}) {
+      if (ngpu > 1) {
+        int rc = s2b_index_set_reduce_mode(const_cast<S2bIndex*>(big.handle()), mode);
+        if (rc == S2B_EUNSUPPORTED) { std::printf("reduce mode %d unavailable: %s\n", mode, s2b::LastError()); continue; }
+        CHECK(rc >= 0);
+      }
+      CHECK(query.CountContainingShapes(p.data(), n, &multi));
+      CHECK(multi == single);
+      // device-resident shards: the same points, uploaded to each replica's GPU by hand
+      int rdev[8];
+      CHECK(s2b_index_replica_devices(big.handle(), rdev, 8) == S2B_OK);
+      std::vector<double*> d_pts(ngpu);
+      std::vector<uint64_t*> d_counts(ngpu);
+      std::vector<size_t> cnt(ngpu);
+      for (int k = 0; k < ngpu; ++k) {
+        const size_t lo = n * k / ngpu, hi = n * (k + 1) / ngpu;   // any partition will do: the histogram is a sum
+        cnt[k] = hi - lo;
+        CHECK(cudaSetDevice(rdev[k]) == cudaSuccess);
+        CHECK(cudaMalloc((void**)&d_pts[k], 24 * cnt[k] + 24) == cudaSuccess && cudaMalloc((void**)&d_counts[k], 8 * single.size()) == cudaSuccess);
+        CHECK(cudaMemcpy(d_pts[k], &p[lo].x, 24 * cnt[k], cudaMemcpyHostToDevice) == cudaSuccess);
+      }
+      for (int rep = 0; rep < 3; ++rep)   // repeated calls reuse the partial buffers: ordering between reads and the next memset
+        CHECK(s2b_shape_histogram_multi_dev(big.handle(), (const double* const*)d_pts.data(), cnt.data(), S2B_VERTEX_MODEL_SEMI_OPEN, d_counts.data(), rep == 2) == S2B_OK);
+      for (int k = 0; k < ngpu; ++k) {
+        std::vector<uint64_t> got(single.size());
+        CHECK(cudaSetDevice(rdev[k]) == cudaSuccess);
+        CHECK(cudaMemcpy(got.data(), d_counts[k], 8 * got.size(), cudaMemcpyDeviceToHost) == cudaSuccess);
+        CHECK(got == single);                                    // every GPU holds the global histogram
+        cudaFree(d_pts[k]); cudaFree(d_counts[k]);
+      }
+      CHECK(cudaSetDevice(0) == cudaSuccess);
+    }
+    CHECK(query.Contains(p.data(), n, inN.data()));
+    CHECK(in1 == inN);
+    std::vector<uint64_t> ids1(n), idsN(n);
+    CHECK(s2b_encode_points(&p[0].x, n, 30, ids1.data()) == S2B_OK);
+    CHECK(s2b_encode_points_multi(devices.data(), ngpu, &p[0].x, n, 30, idsN.data()) == S2B_OK && ids1 == idsN);
+    const int levels[3] = {12, 20, 30};
+    std::vector<uint64_t> l1(3 * n), lN(3 * n);
+    std::vector<char> t1(16 * n), tN(16 * n);
+    std::vector<uint8_t> len1(n), lenN(n);
+    CHECK(s2b_encode_latlng_levels_tokens(&pll[0].lat_rad, n, levels, 3, l1.data(), 2, t1.data(), len1.data()) == S2B_OK);
+    CHECK(s2b_encode_latlng_levels_tokens_multi(devices.data(), ngpu, &pll[0].lat_rad, n, levels, 3, lN.data(), 2, tN.data(), lenN.data()) == S2B_OK);
+    CHECK(l1 == lN && t1 == tN && len1 == lenN);
+    const int twice[2] = {0, 0};
+    CHECK(s2b_encode_points_multi(twice, 2, &p[0].x, n, 30, idsN.data()) == S2B_EINVAL);
+    std::printf("multi-GPU driver: %d GPU(s), %llu hits, histograms / flags / ids equal to the single-GPU calls\n", ngpu, (unsigned long long)hits);
   }
 
   // S2CellUnion::Contains: Trondheim (python/s2geometry_test.py:254-259)

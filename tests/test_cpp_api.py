@@ -11,8 +11,10 @@ EXE = os.path.join(ROOT, "tests", "cpp", "test_batch_api")
 def build_exe():
     from s2geometry_b200 import build
     lib = build.build()
-    cmd = ["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "test_batch_api.cc"),
-           "-o", EXE, lib, "-Wl,-rpath," + os.path.dirname(lib)]
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    cmd = ["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include"),
+           os.path.join(ROOT, "tests", "cpp", "test_batch_api.cc"), "-o", EXE, lib, "-Wl,-rpath," + os.path.dirname(lib),
+           "-L", os.path.join(cuda, "lib64"), "-lcudart", "-Wl,-rpath," + os.path.join(cuda, "lib64")]
     subprocess.check_call(cmd)
     return EXE
 
