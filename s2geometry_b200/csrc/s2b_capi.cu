@@ -123,9 +123,46 @@ struct FixBuf {
     return cudaMemcpyAsync(h, d, kFixHeader + sizeof(FixRecord) * (size_t)(eager < cap ? eager : cap), cudaMemcpyDeviceToHost, st);
   }
 };
-constexpr int kFixSubBatches = 8;
-static thread_local FixBuf t_fix_slot[3];                 // host-pointer pipeline: one per slot
-static thread_local FixBuf t_fix_dev[kFixSubBatches];     // s2b_encode_latlng_strict_dev: one per sub-batch
+static thread_local FixBuf t_fix_slot[3];   // host-pointer pipeline: one per slot
+static thread_local FixBuf t_fix_dev;       // s2b_encode_latlng_strict_dev: the piecewise fallback
+
+// The list of s2b_encode_latlng_strict_dev: records go straight into MAPPED pinned host memory and the host re-evaluates
+// them while the kernel is still running (the marker of a record is its id field, written last and never 0), so the
+// host's libm work overlaps the launch and only the last few records are left when it ends.
+struct LiveList {
+  FixRecord* h = nullptr;        // cudaHostAlloc(mapped); device alias below
+  FixRecord* d_alias = nullptr;
+  uint32_t* d_count = nullptr;   // device counter
+  uint32_t* h_count = nullptr;   // pinned copy of the final count
+  cudaEvent_t ev = nullptr;
+  uint32_t cap = 0;
+  int device = -1;
+  bool dirty = false;
+  std::vector<FixRecord> seen;
+  std::vector<uint64_t> host_id;
+  void release() {
+    if (h) cudaFreeHost(h);
+    if (d_count) cudaFree(d_count);
+    if (h_count) cudaFreeHost(h_count);
+    if (ev) cudaEventDestroy(ev);
+    h = nullptr; d_alias = nullptr; d_count = nullptr; h_count = nullptr; ev = nullptr; cap = 0; device = -1; dirty = false;
+  }
+  int ensure(int dev, uint32_t want) {
+    if (device == dev && cap >= want) return S2B_OK;
+    release();
+    device = dev;
+    S2B_CUDA(cudaHostAlloc((void**)&h, sizeof(FixRecord) * (size_t)want, cudaHostAllocMapped));
+    memset(h, 0, sizeof(FixRecord) * (size_t)want);
+    S2B_CUDA(cudaHostGetDevicePointer((void**)&d_alias, h, 0));
+    S2B_CUDA(cudaMalloc((void**)&d_count, sizeof(uint32_t)));
+    S2B_CUDA(cudaMallocHost((void**)&h_count, sizeof(uint32_t)));
+    S2B_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    cap = want;
+    return S2B_OK;
+  }
+};
+static thread_local LiveList t_live;
+constexpr uint32_t kLiveCap = 1u << 16;   // 2 MB of pinned memory; 40x the uniform rate at 100M points
 
 // S2CellId(S2LatLng::FromRadians(lat, lng)) with THIS process's libm: S2LatLng::ToPoint (s2latlng.cc:68-77; SinCos() =
 // {sin(x), cos(x)}, s1angle.h:343-357) then S2CellId(S2Point) (s2cell_id.cc:309-315). Only ever applied to the
@@ -310,56 +347,99 @@ static int encode_dev(InputKind kind, const void* in, size_t n, const int* level
     if (e != cudaSuccess) return cuda_fail(e, "encode launch");
     return S2B_OK;
   }
-  // Strict: kernel -> list of boundary-sensitive points -> host libm -> patch kernel for the ids that differ. The batch
-  // is cut into up to kFixSubBatches launches enqueued back to back; while the GPU runs launch s + 1 the host
-  // re-evaluates the list of launch s, so only the last list's host work (and one small copy) is exposed.
+  // Strict: ONE launch whose list of boundary-sensitive points lands in mapped host memory; the host re-evaluates the
+  // records with its libm as they arrive, so when the kernel ends only the stragglers are left; ids that differ are then
+  // patched on the device.
   int dev = 0;
   S2B_CUDA(cudaGetDevice(&dev));
   const size_t in_bpp = kind == kInLatLngRad ? 16 : 8;
-  size_t subs = (n + ((size_t)1 << 23) - 1) >> 23;
-  if (subs > (size_t)kFixSubBatches) subs = kFixSubBatches;
-  const size_t sub = ((n + subs - 1) / subs + 255) / 256 * 256;
-  const size_t want = sub / 128 < (1u << 14) ? (1u << 14) : sub / 128;
+  LiveList& live = t_live;
+  rc = live.ensure(dev, kLiveCap);
+  if (rc) return rc;
+  if (live.dirty) {   // a previous call failed half way: stale markers may be left
+    S2B_CUDA(cudaStreamSynchronize(st));
+    memset(live.h, 0, sizeof(FixRecord) * (size_t)live.cap);
+    live.dirty = false;
+  }
   o.ids_stride = n;
-  auto sub_out = [&](size_t off) {
-    EncodeOut q = o;
-    q.ids = o.ids + off;
-    q.flags = o.flags ? o.flags + off : nullptr;
-    q.tokens16 = o.tokens16 ? o.tokens16 + 16 * off : nullptr;
-    q.token_len = o.token_len ? o.token_len + off : nullptr;
-    q.index_base = off;
-    return q;
+  o.index_base = 0;
+  o.fix_list = live.d_alias; o.fix_count = live.d_count; o.fix_cap = live.cap;
+  S2B_CUDA(cudaMemsetAsync(live.d_count, 0, sizeof(uint32_t), st));
+  cudaError_t e = launch_encode(kind, in, n, o, st);
+  if (e != cudaSuccess) return cuda_fail(e, "encode launch");
+  S2B_CUDA(cudaMemcpyAsync(live.h_count, live.d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  S2B_CUDA(cudaEventRecord(live.ev, st));
+  std::vector<FixPatch> changed;
+  std::vector<FixRecord>& seen = live.seen;   // the records as consumed (id = the device's id) ...
+  std::vector<uint64_t>& host_id = live.host_id;   // ... and the id this host's libm gives
+  seen.clear(); host_id.clear();
+  uint32_t k = 0;
+  auto consume_ready = [&](uint32_t limit) {   // records [k, limit) whose marker has arrived, in slot order
+    while (k < limit) {
+      volatile FixRecord* r = live.h + k;
+      const uint64_t id = r->id;
+      if (id == 0) break;
+      __atomic_thread_fence(__ATOMIC_ACQUIRE);
+      FixRecord rec;
+      rec.index = r->index; rec.lat = r->lat; rec.lng = r->lng; rec.id = id;
+      r->id = 0;                               // the slot is clean for the next call
+      seen.push_back(rec);
+      host_id.push_back(leaf_id_host_libm(rec.lat, rec.lng));
+      ++k;
+    }
   };
-  size_t launched = 0;
-  for (size_t off = 0; off < n; off += sub, ++launched) {
-    FixBuf& fb = t_fix_dev[launched];
+  live.dirty = true;
+  for (;;) {
+    consume_ready(live.cap);
+    cudaError_t q = cudaEventQuery(live.ev);
+    if (q == cudaSuccess) break;
+    if (q != cudaErrorNotReady) return cuda_fail(q, "encode kernel");
+  }
+  const uint32_t early = k;
+  const uint32_t c = *(volatile uint32_t*)live.h_count;
+  if (c <= live.cap) {
+    consume_ready(c);   // the kernel has completed: every record below c is in host memory
+    if (k != c) return set_error(S2B_ECUDA, "strict lat/lng list: %u of %u records arrived", k, c);
+    // Records consumed while the kernel was running were read behind a marker; now that the launch has completed their
+    // payload is visible by definition — make sure it is what was used (it always is when stores land in order).
+    for (uint32_t s = 0; s < early; ++s) {
+      const FixRecord& now = live.h[s];
+      if (now.index != seen[s].index || now.lat != seen[s].lat || now.lng != seen[s].lng) {
+        seen[s].index = now.index; seen[s].lat = now.lat; seen[s].lng = now.lng;
+        host_id[s] = leaf_id_host_libm(now.lat, now.lng);
+      }
+    }
+    for (uint32_t s = 0; s < c; ++s)
+      if (host_id[s] != seen[s].id) changed.push_back(FixPatch{seen[s].index, host_id[s]});
+    g_strict_reevaluated.fetch_add(c, std::memory_order_relaxed);
+    g_strict_changed.fetch_add(changed.size(), std::memory_order_relaxed);
+    live.dirty = false;
+  } else {
+    // More sensitive points than the live list holds (input concentrated on cell boundaries): wipe it and redo the
+    // batch piecewise through a device-side list (collect_patches' fallback), which counts and patches everything.
+    for (uint32_t s = 0; s < live.cap; ++s) live.h[s].id = 0;
+    live.dirty = false;
+    changed.clear();
+    FixBuf& fb = t_fix_dev;
+    const size_t want = n / 128 < (1u << 16) ? (1u << 16) : (n / 128 > (1u << 24) ? (1u << 24) : n / 128);
     rc = fb.ensure(dev, (uint32_t)want);
     if (rc) return rc;
-    EncodeOut q = sub_out(off);
-    fb.attach(&q);
-    S2B_CUDA(cudaMemsetAsync(fb.d_count(), 0, sizeof(uint32_t), st));
-    cudaError_t e = launch_encode(kind, (const char*)in + off * in_bpp, n - off < sub ? n - off : sub, q, st);
-    if (e != cudaSuccess) return cuda_fail(e, "encode launch");
-    S2B_CUDA(fb.fetch(kFixEager, st));
-    S2B_CUDA(cudaEventRecord(fb.ev, st));
-  }
-  std::vector<FixPatch> changed;
-  size_t k = 0;
-  for (size_t off = 0; off < n; off += sub, ++k) {
-    FixBuf& fb = t_fix_dev[k];
-    S2B_CUDA(cudaEventSynchronize(fb.ev));
-    rc = collect_patches(kind, (const char*)in + off * in_bpp, in_bpp, n - off < sub ? n - off : sub, sub_out(off), st, fb, kFixEager, &changed);
+    *(volatile uint32_t*)fb.h = 0xFFFFFFFFu;   // "overflowed": collect_patches goes piecewise
+    EncodeOut q = o;
+    q.fix_list = nullptr; q.fix_count = nullptr; q.fix_cap = 0;
+    rc = collect_patches(kind, in, in_bpp, n, q, st, fb, 0, &changed);
     if (rc) return rc;
   }
-  FixBuf& pb = t_fix_dev[0];
+  FixBuf& pb = t_fix_dev;
   for (size_t off = 0; off < changed.size(); off += (1u << 20)) {
     const uint32_t m = (uint32_t)(changed.size() - off < (1u << 20) ? changed.size() - off : (1u << 20));
+    pb.device = dev;
     rc = pb.ensure_patches(m);
     if (rc) return rc;
     S2B_CUDA(cudaMemcpyAsync(pb.d_patch, changed.data() + off, sizeof(FixPatch) * m, cudaMemcpyHostToDevice, st));
     EncodeOut whole = o;
     whole.index_base = 0;
-    cudaError_t e = launch_encode_patch(pb.d_patch, m, whole, n, st);
+    e = launch_encode_patch(pb.d_patch, m, whole, n, st);
     if (e != cudaSuccess) return cuda_fail(e, "patch launch");
     S2B_CUDA(cudaStreamSynchronize(st));   // `changed` is pageable host memory
   }

@@ -79,9 +79,14 @@ __device__ __forceinline__ RawPoint<kInLatLngE7> load_raw(const void* in, uint32
 __device__ __noinline__ void append_fix(FixRecord* list, uint32_t* count, uint32_t cap, uint64_t index, double lat, double lng, uint64_t id) {
   const uint32_t slot = atomicAdd(count, 1u);
   if (slot < cap) {
-    ulonglong2* r = (ulonglong2*)(list + slot);
-    r[0] = make_ulonglong2(index, (unsigned long long)__double_as_longlong(lat));
-    r[1] = make_ulonglong2((unsigned long long)__double_as_longlong(lng), id);
+    // The list may live in mapped host memory that the host reads WHILE this kernel runs (s2b_capi.cu, LiveList): the id
+    // (never 0) is the "record complete" marker and is written last, behind a system-scope fence.
+    volatile unsigned long long* r = (volatile unsigned long long*)(list + slot);
+    r[0] = index;
+    r[1] = (unsigned long long)__double_as_longlong(lat);
+    r[2] = (unsigned long long)__double_as_longlong(lng);
+    __threadfence_system();
+    r[3] = id;
   }
 }
 
