@@ -136,6 +136,7 @@ struct LiveList {
   uint32_t* h_count = nullptr;   // pinned copy of the final count
   cudaEvent_t ev = nullptr;
   uint32_t cap = 0;
+  uint32_t base = 0;             // the device counter is never reset: records of a launch start at slot (count - base)
   int device = -1;
   bool dirty = false;
   std::vector<FixRecord> seen;
@@ -155,9 +156,11 @@ struct LiveList {
     memset(h, 0, sizeof(FixRecord) * (size_t)want);
     S2B_CUDA(cudaHostGetDevicePointer((void**)&d_alias, h, 0));
     S2B_CUDA(cudaMalloc((void**)&d_count, sizeof(uint32_t)));
+    S2B_CUDA(cudaMemset(d_count, 0, sizeof(uint32_t)));
     S2B_CUDA(cudaMallocHost((void**)&h_count, sizeof(uint32_t)));
     S2B_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     cap = want;
+    base = 0;
     return S2B_OK;
   }
 };
@@ -359,12 +362,12 @@ static int encode_dev(InputKind kind, const void* in, size_t n, const int* level
   if (live.dirty) {   // a previous call failed half way: stale markers may be left
     S2B_CUDA(cudaStreamSynchronize(st));
     memset(live.h, 0, sizeof(FixRecord) * (size_t)live.cap);
+    S2B_CUDA(cudaMemcpy(&live.base, live.d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost));
     live.dirty = false;
   }
   o.ids_stride = n;
   o.index_base = 0;
-  o.fix_list = live.d_alias; o.fix_count = live.d_count; o.fix_cap = live.cap;
-  S2B_CUDA(cudaMemsetAsync(live.d_count, 0, sizeof(uint32_t), st));
+  o.fix_list = live.d_alias; o.fix_count = live.d_count; o.fix_cap = live.cap; o.fix_base = live.base;
   cudaError_t e = launch_encode(kind, in, n, o, st);
   if (e != cudaSuccess) return cuda_fail(e, "encode launch");
   S2B_CUDA(cudaMemcpyAsync(live.h_count, live.d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -396,7 +399,8 @@ static int encode_dev(InputKind kind, const void* in, size_t n, const int* level
     if (q != cudaErrorNotReady) return cuda_fail(q, "encode kernel");
   }
   const uint32_t early = k;
-  const uint32_t c = *(volatile uint32_t*)live.h_count;
+  const uint32_t c = *(volatile uint32_t*)live.h_count - live.base;
+  live.base += c;
   if (c <= live.cap) {
     consume_ready(c);   // the kernel has completed: every record below c is in host memory
     if (k != c) return set_error(S2B_ECUDA, "strict lat/lng list: %u of %u records arrived", k, c);
@@ -426,7 +430,7 @@ static int encode_dev(InputKind kind, const void* in, size_t n, const int* level
     if (rc) return rc;
     *(volatile uint32_t*)fb.h = 0xFFFFFFFFu;   // "overflowed": collect_patches goes piecewise
     EncodeOut q = o;
-    q.fix_list = nullptr; q.fix_count = nullptr; q.fix_cap = 0;
+    q.fix_list = nullptr; q.fix_count = nullptr; q.fix_cap = 0; q.fix_base = 0;
     rc = collect_patches(kind, in, in_bpp, n, q, st, fb, 0, &changed);
     if (rc) return rc;
   }

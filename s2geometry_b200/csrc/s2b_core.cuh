@@ -159,6 +159,33 @@ S2B_HD uint64_t from_face_ij_wide(int face, uint32_t i, uint32_t j, const TableT
   return n * 2 + 1;
 }
 
+// The same encoding with the table laid out for the dependent chain of the encode kernel: entry = (pos12 << 3) |
+// (orientation << 1), i.e. the orientation bits sit where the BYTE offset of the next lookup needs them, so one step is
+// "offset = precomputed (i6, j6) offset | (entry & 6); entry = table[offset]" — one logic op + one load on the critical
+// path instead of four. `tab` = the 16384 x 16-bit table as bytes (staged in shared memory by the kernel).
+S2B_HD uint32_t hilbert_chain_entry(const unsigned char* tab, uint32_t byte_offset) {
+  return *(const uint16_t*)(tab + byte_offset);
+}
+S2B_HD uint16_t hilbert_chain_repack(uint16_t e) { return (uint16_t)(((e >> 2) << 3) | ((e & 3u) << 1)); }   // from the pos6 layout
+S2B_HD uint64_t from_face_ij_chain(int face, uint32_t i, uint32_t j, const unsigned char* tab) {
+  // byte offsets of the five (i6, j6) pairs: (i6 << 9) | (j6 << 3), most significant first
+  const uint32_t o4 = ((i >> 15) & 0x7E00u) | ((j >> 21) & 0x1F8u);
+  const uint32_t o3 = ((i >> 9) & 0x7E00u) | ((j >> 15) & 0x1F8u);
+  const uint32_t o2 = ((i >> 3) & 0x7E00u) | ((j >> 9) & 0x1F8u);
+  const uint32_t o1 = ((i << 3) & 0x7E00u) | ((j >> 3) & 0x1F8u);
+  const uint32_t o0 = ((i << 9) & 0x7E00u) | ((j << 3) & 0x1F8u);
+  const uint32_t e4 = hilbert_chain_entry(tab, o4 | (((uint32_t)face & 1u) << 1));
+  const uint32_t e3 = hilbert_chain_entry(tab, o3 | (e4 & 6u));
+  const uint32_t e2 = hilbert_chain_entry(tab, o2 | (e3 & 6u));
+  const uint32_t e1 = hilbert_chain_entry(tab, o1 | (e2 & 6u));
+  const uint32_t e0 = hilbert_chain_entry(tab, o0 | (e1 & 6u));
+  // id = face << 61 | pos4 << 49 | pos3 << 37 | pos2 << 25 | pos1 << 13 | pos0 << 1 | 1, with pos_k = e_k >> 3
+  const uint32_t p2 = e2 >> 3;
+  const uint32_t lo = 1u | ((e0 >> 3) << 1) | ((e1 >> 3) << 13) | (p2 << 25);
+  const uint32_t hi = (p2 >> 7) | ((e3 >> 3) << 5) | ((e4 >> 3) << 17) | ((uint32_t)face << 29);
+  return ((uint64_t)hi << 32) | lo;
+}
+
 // S2CellId(const S2Point&) (s2cell_id.cc:309-315).
 template <class TableT>
 S2B_HD uint64_t cellid_from_point(const P3& p, const TableT* pos) {

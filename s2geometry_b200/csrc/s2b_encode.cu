@@ -21,6 +21,7 @@ namespace s2b {
 
 __device__ const HilbertTables g_hilbert = kHilbert;
 __device__ uint16_t g_hilbert_wide[16384];   // uploaded on first use per device (ensure_wide_table)
+__device__ double g_sincos512[512][2];       // sin, cos of k*pi/256 (uploaded with it)
 
 static cudaError_t ensure_wide_table() {
   static std::atomic<uint64_t> done_mask{0};   // bit d: device d holds the table (one host thread may drive several GPUs)
@@ -28,6 +29,7 @@ static cudaError_t ensure_wide_table() {
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess || (dev < 64 && ((done_mask.load(std::memory_order_acquire) >> dev) & 1))) return e;
   e = cudaMemcpyToSymbol(g_hilbert_wide, wide_hilbert_host(), 16384 * sizeof(uint16_t));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_sincos512, sc_tab::kSinCos512, sizeof(sc_tab::kSinCos512));
   if (e == cudaSuccess && dev < 64) done_mask.fetch_or(1ull << dev, std::memory_order_release);
   return e;
 }
@@ -59,7 +61,7 @@ struct EncodeArgs {
   int force_cr;
   FixRecord* fix_list;     // nullable: strict host-libm mode (s2b_internal.h)
   uint32_t* fix_count;
-  uint32_t fix_cap;
+  uint32_t fix_cap, fix_base;
   uint64_t index_base;
 };
 
@@ -76,8 +78,8 @@ __device__ __forceinline__ RawPoint<kInLatLngRad> load_raw(const void* in, uint3
 __device__ __forceinline__ RawPoint<kInLatLngE7> load_raw(const void* in, uint32_t i, RawPoint<kInLatLngE7>*) { return {__ldcs((const int2*)in + i)}; }
 
 // Strict host-libm mode, rare path (out of line so that it costs the main loop no registers).
-__device__ __noinline__ void append_fix(FixRecord* list, uint32_t* count, uint32_t cap, uint64_t index, double lat, double lng, uint64_t id) {
-  const uint32_t slot = atomicAdd(count, 1u);
+__device__ __noinline__ void append_fix(FixRecord* list, uint32_t* count, uint32_t cap, uint32_t base, uint64_t index, double lat, double lng, uint64_t id) {
+  const uint32_t slot = atomicAdd(count, 1u) - base;   // unsigned arithmetic: correct across a wrap of the counter
   if (slot < cap) {
     // The list may live in mapped host memory that the host reads WHILE this kernel runs (s2b_capi.cu, LiveList): the id
     // (never 0) is the "record complete" marker and is written last, behind a system-scope fence.
@@ -98,11 +100,17 @@ __device__ __noinline__ void append_fix(FixRecord* list, uint32_t* count, uint32
 template <int kKind, int kLevels, bool kToken>
 __global__ void __launch_bounds__(kThreads, kEncodeCtas)
 encode_kernel(const void* __restrict__ in, uint32_t n, const EncodeArgs a) {
-  __shared__ uint16_t s_pos[16384];   // 6-bit Hilbert table: 5 dependent lookups per point
-  __shared__ double s_sc[kKind == kInXYZ ? 1 : sc_tab::kTableSize][4];
-  for (int k = threadIdx.x; k < 16384 / 8; k += kThreads) ((uint4*)s_pos)[k] = ((const uint4*)g_hilbert_wide)[k];
+  // 6-bit Hilbert table (5 dependent lookups per point), repacked for the lookup chain (from_face_ij_chain)
+  __shared__ __align__(16) uint16_t s_pos[16384];
+  __shared__ double s_sc[kKind == kInXYZ ? 1 : sc_tab::kTableSize][4];       // correctly rounded path (rare)
+  __shared__ __align__(16) double s_sc512[kKind == kInXYZ ? 1 : 512][2];     // the filter's sin/cos table
+  for (int k = threadIdx.x; k < 16384 / 2; k += kThreads) {
+    const uint32_t w = ((const uint32_t*)g_hilbert_wide)[k];
+    ((uint32_t*)s_pos)[k] = (uint32_t)hilbert_chain_repack((uint16_t)w) | ((uint32_t)hilbert_chain_repack((uint16_t)(w >> 16)) << 16);
+  }
   if (kKind != kInXYZ) {
     for (int k = threadIdx.x; k < sc_tab::kTableSize * 4; k += kThreads) (&s_sc[0][0])[k] = (&g_sincos_tab[0][0])[k];
+    for (int k = threadIdx.x; k < 512; k += kThreads) ((double2*)s_sc512)[k] = ((const double2*)g_sincos512)[k];
   }
   __syncthreads();
 
@@ -135,9 +143,9 @@ encode_kernel(const void* __restrict__ in, uint32_t n, const EncodeArgs a) {
           lat = (M_PI / 180) * (1e-7 * (double)cur.e7.x);
           lng = (M_PI / 180) * (1e-7 * (double)cur.e7.y);
         }
-        face = latlng_to_face_fij(lat, lng, s_sc, a.force_cr != 0, &p, &fi, &fj, &sensitive);
+        face = latlng_to_face_fij(lat, lng, s_sc, s_sc512, a.force_cr != 0, &p, &fi, &fj, &sensitive);
       }
-      const uint64_t id = from_face_ij_wide(face, fij_to_ij(fi), fij_to_ij(fj), s_pos);
+      const uint64_t id = from_face_ij_chain(face, fij_to_ij(fi), fij_to_ij(fj), (const unsigned char*)s_pos);
 #pragma unroll
       for (int k = 0; k < kLevels; ++k) __stcs(a.ids[k] + i, (id & a.and_mask[k]) | a.or_mask[k]);
       if constexpr (kToken) {
@@ -163,7 +171,7 @@ encode_kernel(const void* __restrict__ in, uint32_t n, const EncodeArgs a) {
             lng = (M_PI / 180) * (1e-7 * (double)again.e7.y);
           }
           if (near_cell_boundary(fi, fj, kFlagTolIj) || !(fabs(lat) < 1048576.0 && fabs(lng) < 1048576.0))
-            append_fix(a.fix_list, a.fix_count, a.fix_cap, a.index_base + i, lat, lng, id);
+            append_fix(a.fix_list, a.fix_count, a.fix_cap, a.fix_base, a.index_base + i, lat, lng, id);
         }
       }
     }
@@ -228,6 +236,7 @@ cudaError_t launch_encode(InputKind kind, const void* in, size_t n, const Encode
     a.fix_list = kind == kInXYZ ? nullptr : o.fix_list;
     a.fix_count = o.fix_count;
     a.fix_cap = o.fix_cap;
+    a.fix_base = o.fix_base;
     a.index_base = o.index_base + off;
     if (token) {
       const int L = o.levels.level[o.token_level_index];
@@ -313,7 +322,7 @@ __global__ void __launch_bounds__(kThreads) filter_deviation_kernel(const double
     } else {
       const double lat = in[2 * i], lng = in[2 * i + 1];
       if (!(fabs(lat) < 1048576.0 && fabs(lng) < 1048576.0)) continue;
-      f0 = point_to_face_fij_filter(latlng_to_point_fast(lat, lng), &fi0, &fj0);
+      f0 = point_to_face_fij_filter(latlng_to_point_fast(lat, lng, g_sincos512), &fi0, &fj0);
       f1 = point_to_face_fij(latlng_to_point(lat, lng, g_sincos_tab), &fi1, &fj1);
     }
     if (f0 != f1) {

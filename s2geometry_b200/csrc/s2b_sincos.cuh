@@ -13,6 +13,7 @@
 #pragma once
 #include "s2b_core.cuh"
 #include "s2b_sincos_tables.h"
+#include "s2b_sincos_tab512.h"
 
 namespace s2b {
 
@@ -251,9 +252,36 @@ S2B_HD SinCos sincos_fast(double x) {  // requires |x| < 2^20
   return out;
 }
 
-S2B_HD P3 latlng_to_point_fast(double lat, double lng) {
-  SinCos phi = sincos_fast(lat);
-  SinCos theta = sincos_fast(lng);
+// The filter the encoder actually uses: the same contract as sincos_fast (|error| <= kFastSinCosAbsErr, requires
+// |x| < 2^20) at about half the instructions. x = k * (pi/256) + d with |d| <= pi/512 (three-part Cody-Waite reduction, the
+// first step exact); sin and cos of k * pi/256 come from a table of the WHOLE circle (512 x 16 bytes, shared memory on the
+// device), so there is no quadrant logic at all; sin(d) and cos(d) - 1 need only d^5 and d^6 terms (remainders < 7e-20):
+//   sin x = S + (S * (cos d - 1) + C * sin d),   cos x = C + (C * (cos d - 1) - S * sin d).
+// Error: table rounding <= 5.6e-17, final addition <= 5.6e-17, everything else < 3e-18: <= 1.2e-16 in total (measured
+// 1.1e-16 against mpmath, tests/test_encode_cpu.py::test_fast_sincos_error_bound).
+S2B_HD SinCos sincos_tab(double x, const double (*tab512)[2]) {
+  using namespace sc_tab;
+  const double kd = rint(x * k256OverPi);
+  const double d = fma(kd, -kPi256_3, fma(kd, -kPi256_2, fma(kd, -kPi256_1, x)));
+  const int k = (int)kd & 511;
+#if defined(__CUDA_ARCH__)
+  const double2 sc = *(const double2*)tab512[k];
+  const double S = sc.x, C = sc.y;
+#else
+  const double S = tab512[k][0], C = tab512[k][1];
+#endif
+  const double d2 = d * d;
+  const double sd = fma(d * d2, fma(d2, 1.0 / 120, -1.0 / 6), d);                 // sin d
+  const double cm = d2 * fma(d2, fma(d2, -1.0 / 720, 1.0 / 24), -0.5);            // cos d - 1
+  SinCos out;
+  out.s = S + fma(S, cm, C * sd);
+  out.c = C + fma(C, cm, -(S * sd));
+  return out;
+}
+
+S2B_HD P3 latlng_to_point_fast(double lat, double lng, const double (*tab512)[2]) {
+  SinCos phi = sincos_tab(lat, tab512);
+  SinCos theta = sincos_tab(lng, tab512);
   return P3{theta.c * phi.c, theta.s * phi.c, phi.s};
 }
 
@@ -324,12 +352,12 @@ static constexpr double kFilterTolIj = 1.6e-5;   // fast-path filter: 4.4x the 3
 static constexpr double kFlagTolIj = 4e-6;      // user-visible flag: 1-ulp sin/cos changes, 3.5x margin
 
 // lat/lng -> (face, fi, fj) with the filter described above. *sensitive reports whether the correctly rounded path ran.
-S2B_HD int latlng_to_face_fij(double lat, double lng, const double (*tab)[4], bool force_cr, P3* p, double* fi, double* fj, bool* sensitive) {
+S2B_HD int latlng_to_face_fij(double lat, double lng, const double (*tab)[4], const double (*tab512)[2], bool force_cr, P3* p, double* fi, double* fj, bool* sensitive) {
   int face = 0;
   // out-of-domain angles (|x| >= 2^20, inf, NaN) always take the correctly-rounded path, which handles them
   bool sens = !(fabs(lat) < 1048576.0 && fabs(lng) < 1048576.0) || force_cr;
   if (!sens) {
-    *p = latlng_to_point_fast(lat, lng);
+    *p = latlng_to_point_fast(lat, lng, tab512);
     face = point_to_face_fij_filter(*p, fi, fj);
     sens = near_cell_boundary(*fi, *fj, kFilterTolIj);
   }

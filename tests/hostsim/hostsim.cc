@@ -24,7 +24,7 @@ void hs_encode_latlng_filtered(const double* ll, size_t n, int level, int force_
   uint64_t ns = 0;
   for (size_t i = 0; i < n; ++i) {
     P3 p; double fi, fj; bool sens;
-    int face = latlng_to_face_fij(ll[2 * i], ll[2 * i + 1], sc_tab::kSinCosTable, force_cr != 0, &p, &fi, &fj, &sens);
+    int face = latlng_to_face_fij(ll[2 * i], ll[2 * i + 1], sc_tab::kSinCosTable, sc_tab::kSinCos512, force_cr != 0, &p, &fi, &fj, &sens);
     ns += sens;
     uint64_t id = from_face_ij(face, fij_to_ij(fi), fij_to_ij(fj), kHilbert.pos);
     out[i] = level < 30 ? cellid_parent(id, level) : id;
@@ -34,6 +34,9 @@ void hs_encode_latlng_filtered(const double* ll, size_t n, int level, int force_
 
 void hs_sincos_fast(const double* x, size_t n, double* s, double* c) {
   for (size_t i = 0; i < n; ++i) { SinCos r = sincos_fast(x[i]); s[i] = r.s; c[i] = r.c; }
+}
+void hs_sincos_tab(const double* x, size_t n, double* s, double* c) {
+  for (size_t i = 0; i < n; ++i) { SinCos r = sincos_tab(x[i], sc_tab::kSinCos512); s[i] = r.s; c[i] = r.c; }
 }
 
 void hs_encode_latlng(const double* ll, size_t n, int level, uint64_t* out, uint64_t* n_slow) {
@@ -82,11 +85,14 @@ void hs_cellid_to_token(const uint64_t* ids, size_t n, char* tok16, uint8_t* len
 extern "C" uint64_t hs_check_wide_hilbert(const uint32_t* ij, size_t n) {
   static uint16_t wide[16384];
   static bool init = false;
-  if (!init) { MakeWideHilbert(wide); init = true; }
+  static uint16_t chain[16384];   // the encode kernel's repacked copy (from_face_ij_chain)
+  if (!init) { MakeWideHilbert(wide); for (int k = 0; k < 16384; ++k) chain[k] = hilbert_chain_repack(wide[k]); init = true; }
   uint64_t bad = 0;
   for (size_t k = 0; k < n; ++k)
-    for (int face = 0; face < 6; ++face)
+    for (int face = 0; face < 6; ++face) {
       bad += from_face_ij(face, ij[2 * k], ij[2 * k + 1], kHilbert.pos) != from_face_ij_wide(face, ij[2 * k], ij[2 * k + 1], wide);
+      bad += from_face_ij(face, ij[2 * k], ij[2 * k + 1], kHilbert.pos) != from_face_ij_chain(face, ij[2 * k], ij[2 * k + 1], (const unsigned char*)chain);
+    }
   return bad;
 }
 
@@ -122,7 +128,7 @@ void hs_encode_latlng_strict(const double* ll, size_t n, uint64_t* out, uint64_t
   for (size_t i = 0; i < n; ++i) {
     const double lat = ll[2 * i], lng = ll[2 * i + 1];
     P3 p; double fi, fj; bool sens;
-    int face = latlng_to_face_fij(lat, lng, sc_tab::kSinCosTable, false, &p, &fi, &fj, &sens);
+    int face = latlng_to_face_fij(lat, lng, sc_tab::kSinCosTable, sc_tab::kSinCos512, false, &p, &fi, &fj, &sens);
     uint64_t id = from_face_ij(face, fij_to_ij(fi), fij_to_ij(fj), kHilbert.pos);
     if (sens && (near_cell_boundary(fi, fj, kFlagTolIj) || !(fabs(lat) < 1048576.0 && fabs(lng) < 1048576.0))) {
       ++nr;

@@ -99,12 +99,18 @@ def test_fast_sincos_error_bound(hostsim):
     rng = np.random.default_rng(12)
     x = np.concatenate([rng.uniform(-np.pi, np.pi, 40000), rng.uniform(-2000, 2000, 5000), rng.uniform(-1e6, 1e6, 3000),
                         np.pi / 2 * np.arange(-8, 9), np.pi / 4 * np.arange(-9, 10) * (1 + 1e-16), [0.0, 1e-300, -1e-10]])
-    s = np.empty_like(x); c = np.empty_like(x)
-    hostsim.hs_sincos_fast(vp(x), ctypes.c_size_t(len(x)), vp(s), vp(c))
-    worst = 0.0
-    for i in range(len(x)):
-        worst = max(worst, abs(float(mp.sin(mp.mpf(x[i])) - mp.mpf(s[i]))), abs(float(mp.cos(mp.mpf(x[i])) - mp.mpf(c[i]))))
-    assert worst < 2.3e-16, worst     # half of the bound the encoder budgets for
+    # arguments next to the table nodes k*pi/256 and half way between them (largest |d|), over the whole supported range
+    k = rng.integers(-600, 600, 6000)
+    x = np.concatenate([x, k * (np.pi / 256) * (1 + rng.uniform(-2e-16, 2e-16, len(k))), (k + 0.5) * (np.pi / 256),
+                        (rng.integers(-2**27, 2**27, 4000) + rng.choice([0.0, 0.5, 0.4999999], 4000)) * (np.pi / 256)])
+    x = x[np.abs(x) < 2.0 ** 20]
+    for fn, limit in ((hostsim.hs_sincos_fast, 2.3e-16), (hostsim.hs_sincos_tab, 1.3e-16)):
+        s = np.empty_like(x); c = np.empty_like(x)
+        fn(vp(x), ctypes.c_size_t(len(x)), vp(s), vp(c))
+        worst = 0.0
+        for i in range(len(x)):
+            worst = max(worst, abs(float(mp.sin(mp.mpf(x[i])) - mp.mpf(s[i]))), abs(float(mp.cos(mp.mpf(x[i])) - mp.mpf(c[i]))))
+        assert worst < limit, worst     # the encoder budgets 4.5e-16 (kFastSinCosAbsErr); the table routine is the one in use
 
 
 def boundary_latlngs(ref, n, seed):
