@@ -92,6 +92,11 @@ __device__ __noinline__ void append_fix(FixRecord* list, uint32_t* count, uint32
   }
 }
 
+template <class Raw>
+__device__ __forceinline__ void prefetch_l2(const void* in, uint32_t i, Raw*) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)in + (size_t)i * sizeof(Raw)));
+}
+
 // One thread per point, persistent grid. The input of the NEXT iteration is loaded before the current point is
 // processed, so a warp does not sit on the long scoreboard at the top of every iteration.
 // (Handing out work dynamically — 256-point chunks per warp from a global cursor — was measured and made no
@@ -117,15 +122,21 @@ encode_kernel(const void* __restrict__ in, uint32_t n, const EncodeArgs a) {
   // Warp-uniform trip count + __syncwarp() at the end of every iteration: lanes that took a rare path (double-double
   // sin/cos, division/sqrt slow paths) rejoin their warp instead of running the rest of the loop on their own.
   using Raw = RawPoint<kKind>;
-  const uint32_t stride = gridDim.x * kThreads;
-  const uint32_t lane = threadIdx.x & 31u;
   uint32_t i = blockIdx.x * kThreads + threadIdx.x;
   Raw cur{};
   if (i < n) cur = load_raw(in, i, (Raw*)nullptr);
-  while (i - lane < n) {
+  // (i & ~31) is the warp's first index (the stride is a multiple of 256), so the trip count is warp-uniform without
+  // keeping the lane id around; the grid size is re-read from its constant-bank slot every iteration instead of living
+  // in (and being spilled from) a register.
+  while ((i & ~31u) < n) {
+    uint32_t nctas;
+    asm volatile("mov.u32 %0, %%nctaid.x;" : "=r"(nctas));
+    const uint32_t stride = nctas * kThreads;
     const uint32_t i_next = i + stride;    // n <= 2^31 and stride < 2^20: no wrap-around
     Raw nxt{};
     if (i_next < n) nxt = load_raw(in, i_next, (Raw*)nullptr);
+    // the iteration after next: pull its line into the L2 now, so that the register prefetch above finds it there
+    if (i_next + stride < n) prefetch_l2(in, i_next + stride, (Raw*)nullptr);
     if (i < n) {
       P3 p;
       double fi, fj;

@@ -205,8 +205,18 @@ static constexpr double kFastSinCosAbsErr = 4.5e-16;
   4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05, -2.75573143513906633035e-07, \
   2.08757232129817482790e-09, -1.13596475577881948265e-11, \
   sc_tab::kTwoOverPi, -sc_tab::kPio2_1, -sc_tab::kPio2_2, -sc_tab::kPio2_3 }
+// sincos_tab: 256/pi, -pi/256 in three parts, then the sin / cos series coefficients
+#define S2B_TAB_COEFS { sc_tab::k256OverPi, -sc_tab::kPi256_1, -sc_tab::kPi256_2, -sc_tab::kPi256_3, \
+  1.0 / 120, -1.0 / 6, -1.0 / 720, 1.0 / 24 }
 #if defined(__CUDACC__)
 __constant__ double c_fast_coef[16] = S2B_FAST_COEFS;
+__constant__ double c_tab_coef[8] = S2B_TAB_COEFS;
+#endif
+static constexpr double kTabCoefHost[8] = S2B_TAB_COEFS;
+#if defined(__CUDA_ARCH__)
+#define S2B_TC(i) c_tab_coef[i]
+#else
+#define S2B_TC(i) kTabCoefHost[i]
 #endif
 static constexpr double kFastCoefHost[16] = S2B_FAST_COEFS;
 #if defined(__CUDA_ARCH__)
@@ -260,9 +270,9 @@ S2B_HD SinCos sincos_fast(double x) {  // requires |x| < 2^20
 // Error: table rounding <= 5.6e-17, final addition <= 5.6e-17, everything else < 3e-18: <= 1.2e-16 in total (measured
 // 1.1e-16 against mpmath, tests/test_encode_cpu.py::test_fast_sincos_error_bound).
 S2B_HD SinCos sincos_tab(double x, const double (*tab512)[2]) {
-  using namespace sc_tab;
-  const double kd = rint(x * k256OverPi);
-  const double d = fma(kd, -kPi256_3, fma(kd, -kPi256_2, fma(kd, -kPi256_1, x)));
+  // constants come from the constant bank (as immediates each costs two uniform moves per use)
+  const double kd = rint(x * S2B_TC(0));
+  const double d = fma(kd, S2B_TC(3), fma(kd, S2B_TC(2), fma(kd, S2B_TC(1), x)));
   const int k = (int)kd & 511;
 #if defined(__CUDA_ARCH__)
   const double2 sc = *(const double2*)tab512[k];
@@ -271,8 +281,8 @@ S2B_HD SinCos sincos_tab(double x, const double (*tab512)[2]) {
   const double S = tab512[k][0], C = tab512[k][1];
 #endif
   const double d2 = d * d;
-  const double sd = fma(d * d2, fma(d2, 1.0 / 120, -1.0 / 6), d);                 // sin d
-  const double cm = d2 * fma(d2, fma(d2, -1.0 / 720, 1.0 / 24), -0.5);            // cos d - 1
+  const double sd = fma(d * d2, fma(d2, S2B_TC(4), S2B_TC(5)), d);                // sin d
+  const double cm = d2 * fma(d2, fma(d2, S2B_TC(6), S2B_TC(7)), -0.5);            // cos d - 1
   SinCos out;
   out.s = S + fma(S, cm, C * sd);
   out.c = C + fma(C, cm, -(S * sd));
