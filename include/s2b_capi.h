@@ -32,7 +32,7 @@ extern "C" {
 #define S2B_ECUDA (-2)   /* CUDA runtime / launch failure, or no usable device */
 #define S2B_ENOMEM (-3)  /* host or device allocation failed */
 #define S2B_ECAPACITY (-4) /* caller-provided output capacity too small; required size is reported */
-#define S2B_EUNSUPPORTED (-5) /* the input needs a stage this library does not run on the device (stated per function) */
+#define S2B_EUNSUPPORTED (-5) /* the requested mode is not available in this process (e.g. NCCL missing); stated per function */
 
 /* S2VertexModel (s2contains_point_query.h:54) */
 #define S2B_VERTEX_MODEL_OPEN 0
@@ -309,9 +309,9 @@ int s2b_index_locate_cells_dev(const S2bIndex* index, const uint64_t* cell_ids_d
  * is SUBDIVIDED "may intersect"), so they are identical to the reference's over an index with the same cells.
  *   s2b_region_may_intersect_cells  S2ShapeIndexRegion::MayIntersect(const S2Cell&)  :344-371
  *   s2b_region_contains_cells       S2ShapeIndexRegion::Contains(const S2Cell&)      :313-342
- * S2::RobustCrossProd (s2edge_crossings.cc:147-177) is evaluated in double precision, which decides every edge whose
- * endpoints are further apart than ~9 * DBL_EPSILON (and a == b, which yields Ortho(a)). An index holding an edge that
- * would need the reference's long double / exact stages is refused with S2B_EUNSUPPORTED by these functions. */
+ * S2::RobustCrossProd (s2edge_crossings.cc:147-359) runs with all of its stages on the device: the double-precision
+ * product, the x87 long double product the reference uses on x86-64 (emulated bit for bit), exact arithmetic and symbolic
+ * perturbation — edges shorter than 9 * DBL_EPSILON, antipodal and exactly proportional endpoints included. */
 int s2b_region_may_intersect_cells(const S2bIndex* index, const uint64_t* cell_ids, size_t n, uint8_t* out);
 int s2b_region_may_intersect_cells_dev(const S2bIndex* index, const uint64_t* cell_ids_dev, size_t n, uint8_t* out_dev, void* stream);
 int s2b_region_contains_cells(const S2bIndex* index, const uint64_t* cell_ids, size_t n, uint8_t* out);

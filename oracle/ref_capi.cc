@@ -732,6 +732,14 @@ size_t ref_cover_cap(const double* center, double radius_rad, int max_cells, int
   return k;
 }
 
+// S2::RobustCrossProd (s2edge_crossings.cc:147-177) element-wise, all of its stages as this platform runs them.
+void ref_robust_cross_prod(const double* a, const double* b, size_t n, double* out) {
+  for (size_t i = 0; i < n; ++i) {
+    const S2Point r = S2::RobustCrossProd(P(a + 3 * i), P(b + 3 * i));
+    out[3 * i] = r[0]; out[3 * i + 1] = r[1]; out[3 * i + 2] = r[2];
+  }
+}
+
 // S2RegionCoverer(max_cells).GetCovering(S2ShapeIndexRegion(index)) with default levels (s2region_coverer.h:106):
 // BASELINE configs[4]'s "S2RegionCoverer covering (max 1000 cells)". Returns the number of cells.
 size_t ref_index_covering(void* h, int max_cells, uint64_t* out, size_t capacity) {

@@ -71,6 +71,12 @@ class Ref:
         self.lib.ref_encode_latlng_levels_tokens(_p(ll), _sz(n), lv, len(levels), _p(ids), token_level_index, _p(tok), _p(ln), threads)
         return ids, tok, ln
 
+    def robust_cross_prod(self, a, b):
+        a = np.ascontiguousarray(a, np.float64).reshape(-1, 3); b = np.ascontiguousarray(b, np.float64).reshape(-1, 3)
+        out = np.empty_like(a)
+        self.lib.ref_robust_cross_prod(_p(a), _p(b), _sz(len(a)), _p(out))
+        return out
+
     def latlng_to_point(self, ll):
         ll = np.ascontiguousarray(ll, np.float64)
         out = np.empty((len(ll), 3), np.float64)

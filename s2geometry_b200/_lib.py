@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libs2b.so")
+LIB_PATH = os.environ.get("S2B_LIB_PATH") or os.path.join(_HERE, "libs2b.so")   # the override is for kernel experiments
 
 _c = ctypes
 _vp, _sz, _i, _u64 = _c.c_void_p, _c.c_size_t, _c.c_int, _c.c_uint64

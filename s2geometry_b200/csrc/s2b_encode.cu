@@ -43,7 +43,13 @@ static_assert(sc_tab::kTableSize == 105, "table rows are spelled out above");
 constexpr int kThreads = 256;
 // Resident CTAs per SM of the encode kernels. With the input prefetch 5 x 8 warps (48 registers, no spills) measured
 // 81 Gpts/s on the fused lat/lng step, 6 (40 registers, two spilled values) 79, 4 (64 registers) 81.
-constexpr int kEncodeCtas = 5;
+#ifndef S2B_ENCODE_CTAS
+#define S2B_ENCODE_CTAS 5
+#endif
+#ifndef S2B_PREFETCH_DIST
+#define S2B_PREFETCH_DIST 1   // iterations beyond the register prefetch that the L2 prefetch runs ahead
+#endif
+constexpr int kEncodeCtas = S2B_ENCODE_CTAS;
 
 // What one launch emits, with everything that is the same for all points worked out on the host: per-level output
 // bases and parent() masks (parent(level) = (id & -lsb) | lsb, s2cell_id.h:662-668; for level 30 the masks are ~0 and 1),
@@ -136,7 +142,7 @@ encode_kernel(const void* __restrict__ in, uint32_t n, const EncodeArgs a) {
     Raw nxt{};
     if (i_next < n) nxt = load_raw(in, i_next, (Raw*)nullptr);
     // the iteration after next: pull its line into the L2 now, so that the register prefetch above finds it there
-    if (i_next + stride < n) prefetch_l2(in, i_next + stride, (Raw*)nullptr);
+    if (i_next + S2B_PREFETCH_DIST * stride < n) prefetch_l2(in, i_next + S2B_PREFETCH_DIST * stride, (Raw*)nullptr);
     if (i < n) {
       P3 p;
       double fi, fj;

@@ -697,7 +697,7 @@ int s2b_index_create(const S2bFlatIndex* f, S2bIndex** out) {
   ix->view.num_shape_ids = f->num_shape_ids;
   ix->num_clips = K; ix->num_edges = E;
   for (const FlatEdge& ed : edges)
-    if (!region_edge_is_supported(edge_v0(ed), edge_v1(ed))) ++ix->unsupported_region_edges;
+    if (!region_edge_is_plain(edge_v0(ed), edge_v1(ed))) ++ix->extended_region_edges;
   if (cudaMemcpy(base + o_view, &ix->view, sizeof(FlatIndexView), cudaMemcpyHostToDevice) != cudaSuccess) {
     e = cudaGetLastError(); cudaFree(ix->blob); delete ix; return cuda_fail(e, "cudaMemcpy(view)");
   }

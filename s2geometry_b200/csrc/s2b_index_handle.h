@@ -17,5 +17,5 @@ struct S2bIndex {
   uint64_t num_clips = 0, num_edges = 0;
   int32_t* edge_ids = nullptr;   // optional (s2b_index_set_edge_ids): shape-local id of every clipped edge, for VisitIncidentEdges
   S2bReplicaSet* replicas = nullptr;             // set by s2b_index_replicate (owned by the primary index)
-  uint64_t unsupported_region_edges = 0;   // edges whose RobustCrossProd needs the stages s2b_region.cuh does not restate
+  uint64_t extended_region_edges = 0;   // statistic: edges whose RobustCrossProd goes beyond the double-precision stage
 };

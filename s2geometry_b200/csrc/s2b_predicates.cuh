@@ -164,6 +164,49 @@ struct ExactAcc {
     for (int i = kAccLimbs - 1; i >= 0; --i) if (w[i] != 0) return 1;
     return 0;
   }
+  // The exact value as ExactFloat::ToDouble would report it (util/math/exactfloat/exactfloat.cc:131-161): the magnitude
+  // rounded to 53 bits, ties to even, as mant * 2^exp2 (mant < 2^53 after renormalisation), plus ExactFloat::exp() of the
+  // UNROUNDED value (|v| in [2^(top-1), 2^top)). Destroys the register when the value is negative (it is negated in place).
+  struct Read { int sign; uint64_t mant; int exp2; int top; };
+  S2B_HD Read read() {
+    Read r{0, 0, 0, 0};
+    r.sign = sign();
+    if (r.sign == 0) return r;
+    if (r.sign < 0) {   // two's complement negate
+      uint64_t carry = 1;
+      for (int i = 0; i < kAccLimbs; ++i) { const uint64_t v = ~w[i] + carry; carry = (carry && v == 0) ? 1 : 0; w[i] = v; }
+    }
+    int hi = kAccLimbs - 1;
+    while (w[hi] == 0) --hi;
+    int lz = 0;
+    for (uint64_t t = w[hi]; !(t >> 63); t <<= 1) ++lz;
+    const int top_bit = hi * 64 + 63 - lz;                 // index of the leading one; weight 2^(top_bit - kAccBias)
+    r.top = top_bit - kAccBias + 1;
+    // the 64 bits starting at the leading one, and whether anything non-zero lies below them
+    auto bit_window = [&](int from_bit) -> uint64_t {      // bits [from_bit, from_bit + 64) of the register (may start below 0)
+      if (from_bit <= -64) return 0;
+      if (from_bit < 0) return w[0] << (-from_bit);
+      const int l = from_bit >> 6, sft = from_bit & 63;
+      uint64_t v = w[l] >> sft;
+      if (sft && l + 1 < kAccLimbs) v |= w[l + 1] << (64 - sft);
+      return v;
+    };
+    const int lsb = top_bit - 63;                          // register bit that lands in bit 0 of `top64`
+    const uint64_t top64 = bit_window(lsb);
+    bool sticky = false;
+    if (lsb > 0) {
+      const int l = lsb >> 6, sft = lsb & 63;
+      if (sft && (w[l] << (64 - sft)) != 0) sticky = true;
+      for (int i = l - 1; i >= 0 && !sticky; --i) sticky = w[i] != 0;
+    }
+    uint64_t mant = top64 >> 11;
+    const uint64_t rest = top64 & 0x7FF;
+    int exp2 = (top_bit - 52) - kAccBias;
+    if (rest > 0x400 || (rest == 0x400 && (sticky || (mant & 1)))) ++mant;
+    if (mant >> 53) { mant >>= 1; ++exp2; }
+    r.mant = mant; r.exp2 = exp2;
+    return r;
+  }
 };
 
 // sign(p*q - r*s), exact.

@@ -37,9 +37,6 @@ cudaError_t region_exact_stage_count(unsigned long long* count, bool reset) {
 int cuda_fail(cudaError_t e, const char* what);
 }
 
-#ifndef S2B_EUNSUPPORTED
-#error "S2B_EUNSUPPORTED must be declared in s2b_capi.h"
-#endif
 
 namespace {
 
@@ -272,10 +269,6 @@ void keep_pool_memory_once() {
 
 int check_region_index(const S2bIndex* ix) {
   if (!ix) return set_error(S2B_EINVAL, "null index");
-  if (ix->unsupported_region_edges)
-    return set_error(S2B_EUNSUPPORTED, "%llu edge(s) of this index have endpoints closer than 9 * DBL_EPSILON (or antipodal): "
-                     "RobustCrossProd's extended-precision stages are not available on the device",
-                     (unsigned long long)ix->unsupported_region_edges);
   int dev = -1;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");

@@ -4,19 +4,20 @@
 //   S2ShapeIndexRegion::MayIntersect(S2Cell)  s2shape_index_region.h:344-371
 //   S2ShapeIndexRegion::AnyEdgeIntersects     s2shape_index_region.h:447-465
 //   S2::ClipToPaddedFace / IntersectsRect     s2edge_clipping.cc:64-144,271-384
-//   S2::RobustCrossProd (double stage)        s2edge_crossings.cc:97-177
+//   S2::RobustCrossProd (all stages)          s2edge_crossings.cc:97-359
 //   S2Cell(S2CellId) bound / centre           s2cell.cc:64-71, s2cell_id.cc:395-405, s2cell.h:217
 //   S2CellIterator::LocateImpl(S2CellId)      s2cell_iterator.h:159-189
 // These are the calls an S2RegionCoverer makes on an index region, batched: one target cell per thread.
 //
 // RobustCrossProd: the double-precision stage decides unless the endpoints are closer than ~9 * DBL_EPSILON (or
-// antipodal). a == b returns Ortho(a) like the reference. The reference's two further stages (x87 long double, then
-// exact arithmetic with symbolic perturbation) are not restated: `region_edge_is_supported` identifies such edges when
-// the index is created, and the region queries refuse an index that holds one (S2B_EUNSUPPORTED) instead of guessing.
+// antipodal); a == b returns Ortho(a). The reference's two further stages run here too, on the device: the x87 long
+// double product (emulated operation by operation, s2b_ext80.cuh) and exact arithmetic (the superaccumulator of
+// s2b_predicates.cuh read back as ExactFloat::ToDouble would) with symbolic perturbation — no index is refused.
 #pragma once
 #include <float.h>
 
 #include "s2b_contains.cuh"
+#include "s2b_ext80.cuh"
 
 namespace s2b {
 
@@ -63,16 +64,98 @@ S2B_HD bool stable_cross_prod(const P3& a, const P3& b, P3* out) {
   return norm2(*out) >= kMinNorm * kMinNorm;
 }
 
-// True when RobustCrossProd(a, b) is decided by the stages restated here (stable double product, or a == b).
-S2B_HD bool region_edge_is_supported(const P3& a, const P3& b) {
+// GetStableCrossProd<long double> (s2edge_crossings.cc:97-136) as the x87 evaluates it (s2b_ext80.cuh): every
+// subtraction, addition and product of (a - b) x (a + b) and of its squared norm rounded to a 64-bit significand, the
+// test against kMinNorm^2 for T = long double (the constant below is that expression evaluated by the same compiler:
+// 0xAACA6DBF0CAB2C09 * 2^-185; tests/test_region_cpu.py recomputes it), and Vector3_d::Cast of the result.
+S2B_HD_NOINLINE bool stable_cross_prod_ld(const P3& a, const P3& b, P3* out) {
+  const X80 ax = x80_from_double(a.x), ay = x80_from_double(a.y), az = x80_from_double(a.z);
+  const X80 bx = x80_from_double(b.x), by = x80_from_double(b.y), bz = x80_from_double(b.z);
+  const X80 dx = x80_add(ax, bx, true), dy = x80_add(ay, by, true), dz = x80_add(az, bz, true);   // a - b
+  const X80 sx = x80_add(ax, bx), sy = x80_add(ay, by), sz = x80_add(az, bz);                     // a + b
+  // Vector3::CrossProd (util/math/vector.h:474-478): (y * v.z - z * v.y, z * v.x - x * v.z, x * v.y - y * v.x)
+  const X80 nx = x80_add(x80_mul(dy, sz), x80_mul(dz, sy), true);
+  const X80 ny = x80_add(x80_mul(dz, sx), x80_mul(dx, sz), true);
+  const X80 nz = x80_add(x80_mul(dx, sy), x80_mul(dy, sx), true);
+  // Norm2 = ((0 + x*x) + y*y) + z*z
+  const X80 n2 = x80_add(x80_add(x80_mul(nx, nx), x80_mul(ny, ny)), x80_mul(nz, nz));
+  *out = P3{x80_to_double(nx), x80_to_double(ny), x80_to_double(nz)};
+  const X80 kMinNorm2{0xAACA6DBF0CAB2C09ull, -185 + 63, false};
+  return x80_ge(n2, kMinNorm2);
+}
+
+// Exact (a x b)[k] = p*q - r*s read back the way ExactFloat reports it.
+// A zero result carries the sign IEEE 754 (and ExactFloat::SignedSum) gives it: (-0) - (+0) = -0, every other
+// combination of zero products and every exact cancellation +0; it is reported in `top` (1 = negative zero).
+S2B_HD_NOINLINE ExactAcc::Read exact_minor(double p, double q, double r, double s) {
+  ExactAcc acc;
+  acc.clear();
+  acc.add_product(p, q, 1.0, 1);
+  acc.add_product(r, s, 1.0, -1);
+  ExactAcc::Read v = acc.read();
+  if (v.sign == 0) {
+    const bool pq_zero = p == 0 || q == 0, rs_zero = r == 0 || s == 0;
+    const bool pq_neg = signbit(p) != signbit(q), rs_neg = signbit(r) != signbit(s);
+    v.top = (pq_zero && rs_zero && pq_neg && !rs_neg) ? 1 : 0;
+  }
+  return v;
+}
+S2B_HD double exact_read_to_double(const ExactAcc::Read& v, int scale_exp) {   // ToDouble(ldexp(value, -scale_exp))
+  if (v.sign == 0) return v.top ? -0.0 : 0.0;
+  const double d = ldexp((double)v.mant, v.exp2 - scale_exp);
+  return v.sign < 0 ? -d : d;
+}
+
+// IsNormalizable / EnsureNormalizable (s2edge_crossings.cc:268-303).
+S2B_HD bool is_normalizable(const P3& p) { return fmax(fabs(p.x), fmax(fabs(p.y), fabs(p.z))) >= 0x1p-242; }
+S2B_HD P3 ensure_normalizable(const P3& p) {
+  if (is_normalizable(p)) return p;
+  const double p_max = fmax(fabs(p.x), fmax(fabs(p.y), fabs(p.z)));
+  const double f = ldexp(2.0, -1 - ilogb(p_max));
+  return P3{f * p.x, f * p.y, f * p.z};
+}
+
+// SymbolicCrossProdSorted (s2edge_crossings.cc:183-265), requires a < b lexicographically and a x b == 0 exactly.
+S2B_HD P3 symbolic_cross_prod_sorted(const P3& a, const P3& b) {
+  if (b.x != 0 || b.y != 0) return P3{-b.y, b.x, 0};
+  if (b.z != 0) return P3{b.z, 0, 0};
+  if (a.x != 0 || a.y != 0) return P3{a.y, -a.x, 0};
+  return P3{1, 0, 0};
+}
+
+// internal::ExactCrossProd (s2edge_crossings.cc:345-358) incl. NormalizableFromExact (:305-330). Requires a != b.
+S2B_HD_NOINLINE P3 exact_cross_prod(const P3& a, const P3& b) {
+  const ExactAcc::Read x = exact_minor(a.y, b.z, a.z, b.y), y = exact_minor(a.z, b.x, a.x, b.z), z = exact_minor(a.x, b.y, a.y, b.x);
+  if (x.sign != 0 || y.sign != 0 || z.sign != 0) {
+    const P3 d{exact_read_to_double(x, 0), exact_read_to_double(y, 0), exact_read_to_double(z, 0)};
+    if (is_normalizable(d)) return d;
+    // scale so that the largest component magnitude is in [0.5, 1): exp = the largest ExactFloat::exp() of the components
+    int e = -(1 << 30);
+    if (x.sign != 0 && x.top > e) e = x.top;
+    if (y.sign != 0 && y.top > e) e = y.top;
+    if (z.sign != 0 && z.top > e) e = z.top;
+    return P3{exact_read_to_double(x, e), exact_read_to_double(y, e), exact_read_to_double(z, e)};
+  }
+  // exactly proportional: symbolic perturbation (SymbolicCrossProd :334-343 applied as ExactCrossProd :352-357 does)
+  if (lex_less(a, b)) return ensure_normalizable(ensure_normalizable(symbolic_cross_prod_sorted(a, b)));
+  return neg(ensure_normalizable(ensure_normalizable(symbolic_cross_prod_sorted(b, a))));
+}
+
+// Statistic: true when RobustCrossProd(a, b) is decided by its double-precision stage (or a == b), i.e. for all but
+// edges shorter than ~9 * DBL_EPSILON or nearly antipodal.
+S2B_HD bool region_edge_is_plain(const P3& a, const P3& b) {
   P3 n;
   return stable_cross_prod(a, b, &n) || eq(a, b);
 }
 
+// S2::RobustCrossProd (s2edge_crossings.cc:147-177), every stage: stable double product; a == b -> Ortho(a); the x87
+// long double product (the reference on x86-64: s2pred::kHasLongDouble); exact arithmetic; symbolic perturbation.
 S2B_HD P3 robust_cross_prod(const P3& a, const P3& b) {
   P3 n;
   if (stable_cross_prod(a, b, &n)) return n;
-  return ortho(a);   // a == b (s2edge_crossings.cc:164-166); other inputs are excluded when the index is created
+  if (eq(a, b)) return ortho(a);
+  if (stable_cross_prod_ld(a, b, &n)) return n;
+  return exact_cross_prod(a, b);
 }
 
 // IntersectsFace / IntersectsOppositeEdges / GetExitAxis / GetExitPoint (s2edge_clipping.cc:71-136); n is the line's

@@ -59,7 +59,7 @@ int hs_region_cells(const S2bFlatIndex* f, const uint64_t* ids, size_t n, int mo
   if (rc) return rc;
   FlatIndexView ix = hf.view(f->cell_ids, f->num_shape_ids);
   uint64_t bad = 0;
-  for (const FlatEdge& ed : hf.edges) if (!region_edge_is_supported(edge_v0(ed), edge_v1(ed))) ++bad;
+  for (const FlatEdge& ed : hf.edges) if (!region_edge_is_plain(edge_v0(ed), edge_v1(ed))) ++bad;   // statistic only
   if (unsupported_edges) *unsupported_edges = bad;
   for (size_t i = 0; i < n; ++i)
     out[i] = mode == 0 ? region_may_intersect(ix, ids[i], kHilbert.ij) : region_contains_cell(ix, ids[i], kHilbert.ij);
@@ -112,8 +112,8 @@ void hs_clip_to_padded_face(const double* a, const double* b, const int32_t* fac
   for (size_t i = 0; i < n; ++i) {
     const P3 pa{a[3 * i], a[3 * i + 1], a[3 * i + 2]}, pb{b[3 * i], b[3 * i + 1], b[3 * i + 2]};
     Uv p0{0, 0}, p1{0, 0};
-    supported[i] = region_edge_is_supported(pa, pb);
-    ok[i] = supported[i] && clip_to_padded_face(pa, pb, face[i], padding, &p0, &p1);
+    supported[i] = region_edge_is_plain(pa, pb);   // 0: RobustCrossProd went beyond its double-precision stage
+    ok[i] = clip_to_padded_face(pa, pb, face[i], padding, &p0, &p1);
     out_uv[4 * i] = p0.u; out_uv[4 * i + 1] = p0.v; out_uv[4 * i + 2] = p1.u; out_uv[4 * i + 3] = p1.v;
   }
 }
@@ -121,6 +121,17 @@ void hs_intersects_rect(const double* uv4, const double* rect4, size_t n, uint8_
   for (size_t i = 0; i < n; ++i) {
     const double* r = rect4 + 4 * i;
     out[i] = intersects_rect(Uv{uv4[4 * i], uv4[4 * i + 1]}, Uv{uv4[4 * i + 2], uv4[4 * i + 3]}, UvRect{r[0], r[1], r[2], r[3]});
+  }
+}
+
+// S2::RobustCrossProd, all stages. stage[i]: 0 double, 1 a == b, 2 long double, 3 exact / symbolic.
+void hs_robust_cross_prod(const double* a, const double* b, size_t n, double* out, uint8_t* stage) {
+  for (size_t i = 0; i < n; ++i) {
+    const P3 pa{a[3 * i], a[3 * i + 1], a[3 * i + 2]}, pb{b[3 * i], b[3 * i + 1], b[3 * i + 2]};
+    const P3 r = robust_cross_prod(pa, pb);
+    out[3 * i] = r.x; out[3 * i + 1] = r.y; out[3 * i + 2] = r.z;
+    P3 t;
+    stage[i] = stable_cross_prod(pa, pb, &t) ? 0 : (eq(pa, pb) ? 1 : (stable_cross_prod_ld(pa, pb, &t) ? 2 : 3));
   }
 }
 

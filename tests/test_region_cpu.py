@@ -2,6 +2,8 @@
 S2ShapeIndexRegion, S2::ClipToPaddedFace and S2::IntersectsRect."""
 import ctypes
 
+import pytest
+
 import numpy as np
 
 from s2geometry_b200 import synth
@@ -84,13 +86,84 @@ def test_region_cell_tests_match_reference(hostsim, ref):
         assert 0 < wcon.sum() < len(wcon), name
 
 
-def test_unsupported_edges_are_detected(hostsim, ref):
-    """Edges whose RobustCrossProd needs the extended-precision stages are counted (the C ABI refuses such an index)."""
-    a = scenes._norm(np.array([[1.0, 1e-3, 0.0]]))
-    b = a.copy(); b[0, 1] += 2e-16
-    uv = np.zeros((1, 4)); ok = np.zeros(1, np.uint8); sup = np.ones(1, np.uint8)
-    hostsim.hs_clip_to_padded_face(vp(a), vp(b), vp(np.array([0], np.int32)), ctypes.c_size_t(1), ctypes.c_double(0.0), vp(uv), vp(ok), vp(sup))
-    assert sup[0] == 0
+def _nudge(p, k):
+    """p with every coordinate moved by k[i] ulps."""
+    q = p.copy()
+    for _ in range(int(np.abs(k).max())):
+        q = np.where(k > 0, np.nextafter(q, np.inf), np.where(k < 0, np.nextafter(q, -np.inf), q))
+        k = k - np.sign(k)
+    return q
+
+
+def robust_cross_prod_cases(seed=5, n=20000):
+    """Pairs that reach every stage of S2::RobustCrossProd: endpoints 0..40 ulps apart (long double stage), further apart
+    (double stage), identical, nearly and exactly antipodal, exactly proportional (symbolic), with zero components,
+    and on the coordinate axes."""
+    rng = np.random.default_rng(seed)
+    a = scenes._norm(rng.standard_normal((n, 3)))
+    a[::7, rng.integers(0, 3)] = 0.0
+    a = scenes._norm(a)
+    k = rng.integers(-40, 41, a.shape); k[::3] = rng.integers(-2, 3, (len(k[::3]), 3))
+    near = _nudge(a, k)
+    anti = -_nudge(a, rng.integers(-30, 31, a.shape))
+    axes = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [-1, 0, 0], [0, -1, 0], [0, 0, -1]], float)
+    ax_a = np.repeat(axes, 6, 0); ax_b = np.tile(axes, (6, 1))
+    prop = a * (1 + 2.0 ** -rng.integers(20, 52, (n, 1)))                      # (1 + eps) * a: often exactly proportional
+    pow2 = np.array([[1, 0.5, 0.25], [0.5, 0.5, 0], [0, 0.75, 0.75], [0.375, 0, 0]])
+    pa = np.concatenate([pow2, pow2, -pow2, pow2]); pb = np.concatenate([2 * pow2, -pow2, -4 * pow2, pow2 * 1.5])   # exactly proportional
+    m = n // 8
+    A = np.concatenate([a, a, a, ax_a, a, pa, a[:2000], a[:m], a[:m], a[:m], a[:m], a[:m], a[:m] * 2.0 ** -200])
+    B = np.concatenate([near, a, anti, ax_b, prop, pb, scenes._norm(a[:2000] + 1e-9 * rng.standard_normal((2000, 3))),
+                        -a[:m], 2 * a[:m], -0.25 * a[:m], a[:m] * 2.0 ** -600,       # exactly (anti)parallel: exact + symbolic stage
+                        near[:m] * 2.0 ** -600, near[:m] * 2.0 ** -300])             # tiny non-zero exact products: NormalizableFromExact's scaling
+    return np.ascontiguousarray(A), np.ascontiguousarray(B)
+
+
+def hs_robust_cross_prod(hostsim, a, b):
+    out = np.empty_like(a); stage = np.empty(len(a), np.uint8)
+    hostsim.hs_robust_cross_prod(vp(a), vp(b), ctypes.c_size_t(len(a)), vp(out), vp(stage))
+    return out, stage
+
+
+def test_robust_cross_prod_every_stage_matches_reference(hostsim, ref):
+    """S2::RobustCrossProd restated with all of its stages (double; a == b; x87 long double, emulated bit for bit; exact
+    arithmetic; symbolic perturbation) returns the reference's vector, bit for bit, on pairs that reach each stage."""
+    a, b = robust_cross_prod_cases()
+    got, stage = hs_robust_cross_prod(hostsim, a, b)
+    want = ref.robust_cross_prod(a, b)
+    counts = np.bincount(stage, minlength=4)
+    assert (counts > [1000, 1000, 1000, 1000]).all(), counts          # every stage is exercised
+    bad = (got.view(np.uint64) != want.view(np.uint64)).any(axis=1) & ~((got == 0) & (want == 0)).all(axis=1)
+    assert not bad.any(), (int(bad.sum()), np.bincount(stage[bad], minlength=4), a[bad][:3], b[bad][:3], got[bad][:3], want[bad][:3])
+    assert (got.view(np.uint64) == want.view(np.uint64)).all()          # signed zeros included (clip_exit_axis reads sign bits)
+
+
+def test_long_double_threshold_constant():
+    """kMinNorm^2 of GetStableCrossProd<long double> (s2edge_crossings.cc:128-135) as embedded in s2b_region.cuh:
+    recomputed here in the x87's format (numpy.longdouble on x86-64)."""
+    ld = np.longdouble
+    if np.finfo(ld).nmant != 63:
+        pytest.skip("numpy.longdouble is not the x87 80-bit format here")
+    dbl_err, t_err, sqrt3 = 2.0 ** -53, ld(2.0) ** -64, 1.7320508075688772935274463415058
+    k_min = ld(32 * sqrt3 * dbl_err) / (ld(6 * dbl_err) / t_err - ld(1 + 2 * sqrt3))
+    sq = k_min * k_min
+    mant, exp = np.frexp(sq)
+    assert int(mant * ld(2.0) ** 64) == 0xAACA6DBF0CAB2C09 and int(exp) - 64 == -185
+
+
+def test_clipping_edges_that_need_the_extended_stages(hostsim, ref):
+    """ClipToPaddedFace on edges whose RobustCrossProd leaves the double-precision stage (endpoints a few ulps apart,
+    antipodal): clipped (u, v) bit-identical to the reference."""
+    a, b = robust_cross_prod_cases(seed=9, n=4000)
+    for face in range(6):
+        f = np.full(len(a), face, np.int32)
+        uv = np.zeros((len(a), 4)); ok = np.zeros(len(a), np.uint8); plain = np.ones(len(a), np.uint8)
+        hostsim.hs_clip_to_padded_face(vp(a), vp(b), vp(f), ctypes.c_size_t(len(a)), ctypes.c_double(1e-9), vp(uv), vp(ok), vp(plain))
+        want_uv, want_ok = ref.clip_to_padded_face(a, b, f, 1e-9)
+        assert (ok == want_ok).all()
+        hit = ok.astype(bool)
+        assert (uv[hit] == want_uv[hit]).all()
+        assert (plain == 0).sum() > 1000
 
 
 def test_region_cell_tests_over_the_librarys_own_builder(hostsim, ref):

@@ -48,20 +48,40 @@ def test_region_over_the_device_granularity_index(ref):
     assert (region.contains_cells(targets) == ri.region_cells(targets, 1)).all()
 
 
-def test_unsupported_edge_is_refused_loudly():
-    """An edge whose endpoints are ~1 ulp apart needs RobustCrossProd's extended-precision stages: the region queries
-    refuse the index (S2B_EUNSUPPORTED) instead of answering approximately; point queries are unaffected."""
-    from s2geometry_b200 import _lib
-    from s2geometry_b200.index import ContainsPointQuery, ShapeIndex, ShapeIndexRegion, build_flat_index
+def test_edges_that_need_robust_cross_prods_extended_stages(ref):
+    """Edges whose endpoints are 1-3 ulps apart (RobustCrossProd leaves its double-precision stage for the x87 long double
+    and exact stages, which now run on the device) in a polygon and in polylines: the region cell tests over the
+    reference-built index equal the reference's on every target; no index is refused any more."""
+    from s2geometry_b200.index import ContainsPointQuery, FlatIndex, ShapeIndex, ShapeIndexRegion
     from s2geometry_b200.shapes import ShapeSoup
-    a = scenes._norm(np.array([[1.0, 1e-3, 0.0], [1.0, 1e-3, 0.0], [1.0, 0.2, 0.1], [1.0, 0.0, 0.3]]))
-    a[1, 1] += 2e-16
-    soup = ShapeSoup(); soup.add_polygon([a]); soup = soup.freeze()
-    index = ShapeIndex(build_flat_index(soup, 0))
-    with pytest.raises(_lib.S2BError) as e:
-        ShapeIndexRegion(index).may_intersect(np.array([0x1000000000000000], np.uint64))
-    assert e.value.code == _lib.S2B_EUNSUPPORTED
-    assert ContainsPointQuery(index, 1).contains(a).shape == (4,)
+    from tests.test_region_cpu import _nudge
+    rng = np.random.default_rng(4)
+    loop = scenes._norm(np.array([[1.0, 1e-3, 0.0], [1.0, 1e-3, 0.0], [1.0, 0.2, 0.1], [1.0, 0.2, 0.1], [1.0, 0.0, 0.3]]))
+    loop[1] = _nudge(loop[0:1], np.array([[0, 1, 0]]))[0]          # 1 ulp from vertex 0
+    loop[3] = _nudge(loop[2:3], np.array([[-1, 2, 1]]))[0]
+    soup = ShapeSoup(); soup.add_polygon([loop])
+    for k in range(40):                                              # short polylines with a degenerate first edge across the sphere
+        p = scenes._norm(rng.standard_normal((1, 3)))
+        q = _nudge(p, rng.integers(-3, 4, (1, 3)))
+        r = scenes._norm(p + 0.05 * rng.standard_normal((1, 3)))
+        if (q == p).all():
+            q = _nudge(p, np.array([[1, 0, -1]]))
+        soup.add_polyline(np.concatenate([p, q, r]))
+    soup = soup.freeze()
+    ri = ref.index_create(soup)
+    flat = FlatIndex(**ri.flatten())
+    index = ShapeIndex(flat)
+    region = ShapeIndexRegion(index)
+    targets = region_scenes.region_targets(ref, flat.cell_ids, soup.vertices, 6)
+    # plus the cells around every degenerate vertex at all levels
+    leaf = ref.encode_points(soup.vertices, 30)
+    extra = np.concatenate([ref.parent(leaf, lvl) for lvl in range(0, 31, 3)])
+    targets = np.concatenate([targets, extra])
+    for mode, fn in ((0, region.may_intersect), (1, region.contains_cells)):
+        want = ri.region_cells(targets, mode)
+        assert (fn(targets) == want).all()
+        assert 0 < want.sum() < len(want)
+    assert (ContainsPointQuery(index, 1).contains(soup.vertices) == ri.contains(soup.vertices, 1)).all()
 
 
 def test_fixed_level_covering_equals_the_reference_coverer(ref):
