@@ -572,13 +572,14 @@ def join_section(args, torch, dev, rank, world):
     res = None
     hits_dev = torch.zeros(1, dtype=torch.int64, device=dev)
 
-    from s2geometry_b200.index import CellUnionIndex
+    from s2geometry_b200.index import CellUnionIndex, count_flags
     uq = ContainsPointQuery(CellUnionIndex(union_ids), 1)   # the union replicated on this GPU as an index of interior cells
 
     def ustep():
         nonlocal res
         res = uq.contains(pts)
-        hits_dev[0] = res.sum(dtype=torch.int64)                # device-side count, no host synchronisation in the step
+        hits_dev.zero_()
+        count_flags(res, out=hits_dev)                          # device-side count (s2b_count_flags_dev), no host synchronisation in the step
         sdist.all_reduce_sum_(hits_dev)
 
     for _ in range(3):

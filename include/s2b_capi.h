@@ -254,11 +254,13 @@ int s2b_index_encode(const S2bFlatIndex* flat, const int32_t* edge_id, int max_e
                      size_t* size_out);
 
 /* The geometry half of a serialized index: the bytes of s2shapeutil::FastEncodeTaggedShapes / CompactEncodeTaggedShapes
- * (s2shapeutil_coding.cc:134-156; read back there by TaggedShapeFactory, :158-172) for S2PointVectorShape (tag 3),
- * S2LaxPolylineShape (tag 4) and S2LaxPolygonShape (tag 5), whose points are EncodedS2PointVectors in either format
- * (UNCOMPRESSED or CELL_IDS, encoded_s2point_vector.cc). Decoding yields the shape soup s2b_index_build /
- * s2b_index_decode take (arrays valid until s2b_shape_soup_destroy); vertices are bit-identical to the reference's
- * decoder. Other shape types (S2Polygon::Shape, S2Polyline::Shape) and malformed input fail with S2B_EINVAL.
+ * (s2shapeutil_coding.cc:134-156; read back there by TaggedShapeFactory / FullDecodeShape, :73-110, :158-172) for every
+ * shape type the reference can decode: S2Polygon::Shape (tag 1; S2Polygon::Decode, lossless and compressed — loops become
+ * oriented chains, holes reversed as S2Polygon::Shape orients its edges), S2Polyline::Shape (tag 2; lossless and
+ * compressed), S2PointVectorShape (tag 3), S2LaxPolylineShape (tag 4) and S2LaxPolygonShape (tag 5), whose points are
+ * EncodedS2PointVectors in either format (UNCOMPRESSED or CELL_IDS, encoded_s2point_vector.cc). Decoding yields the shape
+ * soup s2b_index_build / s2b_index_decode take (arrays valid until s2b_shape_soup_destroy); vertices and edge order are
+ * bit-identical to the reference's decoders. Unknown tags and malformed input fail with S2B_EINVAL.
  * s2b_shapes_encode writes the FAST (uncompressed) form, byte-identical to the reference; two-call capacity protocol
  * as s2b_index_encode. */
 typedef struct S2bShapeSoup S2bShapeSoup;
@@ -339,6 +341,11 @@ int s2b_index_info(const S2bIndex* index, uint64_t* num_cells, uint64_t* num_cli
  * out[i] = 1 if any shape contains point i. Locate = s2cell_iterator.h:137-155. */
 int s2b_contains(const S2bIndex* index, const double* xyz, size_t n, int vertex_model, uint8_t* out);
 int s2b_contains_dev(const S2bIndex* index, const double* xyz_dev, size_t n, int vertex_model, uint8_t* out_dev, void* stream);
+
+/* Hit count of a batch: *count_dev += number of non-zero bytes of flags_dev[0..n) (the output of s2b_contains_dev /
+ * s2b_cellunion_contains_dev). ADDS into the device counter (zero it first; all-reduce it across GPUs): the "how many of
+ * these points does the region contain" half of BASELINE configs[4], at HBM speed (1 byte per point). */
+int s2b_count_flags_dev(const uint8_t* flags_dev, size_t n, uint64_t* count_dev, void* stream);
 
 /* ...ShapeContains(shape_id, p)  (s2contains_point_query.h:267-280). */
 int s2b_shape_contains(const S2bIndex* index, int shape_id, const double* xyz, size_t n, int vertex_model, uint8_t* out);

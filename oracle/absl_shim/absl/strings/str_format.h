@@ -27,6 +27,7 @@ template <class... A> std::string StrFormat(const char* f, const A&... a) {
   std::string out(n > 0 ? n : 0, '\0'); if (n > 0) std::snprintf(out.data(), n + 1, fmt.c_str(), widen(a)...);
   return out;
 }
+template <class... S, class... A> std::string StrFormat(const FormatSpec<S...>& f, const A&... a) { return StrFormat(f.f, a...); }
 template <class... A> void StrAppendFormat(std::string* d, const char* f, const A&... a) { d->append(StrFormat(f, a...)); }
 struct StreamFormatted { std::string s; };
 inline std::ostream& operator<<(std::ostream& os, const StreamFormatted& f) { return os << f.s; }

@@ -14,8 +14,13 @@ s2cell_union s2shape_index mutable_s2shape_index s2memory_tracker s2shapeutil_co
 s2shapeutil_get_reference_point s2contains_vertex_query encoded_s2cell_id_vector encoded_string_vector
 util/coding/coder util/coding/varint util/math/mathutil util/math/exactfloat/exactfloat util/math/exactfloat/bignum
 base/malloc_extension s2region_coverer s2closest_point_query s2min_distance_targets s2closest_edge_query
-s2closest_cell_query s2cell_index s2region_sharder s2lax_polygon_shape s2lax_polyline_shape encoded_s2point_vector"
-CXXFLAGS="-std=c++20 -O2 -DNDEBUG -w -fPIC -ffunction-sections -fdata-sections -I$HERE/absl_shim -I$REF"
+s2closest_cell_query s2cell_index s2region_sharder s2lax_polygon_shape s2lax_polyline_shape encoded_s2point_vector
+s2loop s2polygon s2polyline s2loop_measures s2polyline_measures s2latlng_rect_bounder s2crossing_edge_query
+s2wedge_relations s2point_compression s2centroids s2shapeutil_edge_wrap s2shapeutil_visit_crossing_edge_pairs
+internal/s2index_cell_data internal/s2incident_edge_tracker util/bits/bit-interleave"
+# -fvisibility=hidden + --gc-sections: only what ref_capi.cc's exported functions reach is linked, so S2Polygon / S2Loop /
+# S2Polyline (serialization, containment) come in without S2Builder and the boolean operations they can also call.
+CXXFLAGS="-std=c++20 -O2 -DNDEBUG -w -fPIC -ffunction-sections -fdata-sections -fvisibility=hidden -I$HERE/absl_shim -I$REF"
 pids=()
 for t in $TUS; do
   o="$OUT/obj/$(echo $t | tr / _).o"

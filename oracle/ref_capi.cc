@@ -32,6 +32,9 @@
 #include "s2/s2edge_crosser.h"
 #include "s2/s2edge_crossings.h"
 #include "s2/s2latlng.h"
+#include "s2/s2loop.h"
+#include "s2/s2polygon.h"
+#include "s2/s2polyline.h"
 #include "s2/s2lax_polygon_shape.h"
 #include "s2/s2lax_polyline_shape.h"
 #include "s2/s2point_vector_shape.h"
@@ -121,6 +124,7 @@ S2VertexModel Model(int m) { return m == 0 ? S2VertexModel::OPEN : (m == 1 ? S2V
 
 }  // namespace
 
+#pragma GCC visibility push(default)
 extern "C" {
 
 int ref_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
@@ -600,15 +604,44 @@ static std::unique_ptr<S2Shape> SoupToLaxShape(int s, const int8_t* dim, const u
   if (dim[s] == 1) return std::make_unique<S2LaxPolylineShape>(chains.empty() ? std::vector<S2Point>() : chains[0]);
   return std::make_unique<S2LaxPolygonShape>(chains);
 }
+// hint bit 0: CodingHint::COMPACT instead of FAST; bit 1: polygons and polylines as S2Polygon::Shape (tag 1, loops
+// through S2Polygon::InitOriented) and S2Polyline::Shape (tag 2) instead of the lax shapes.
+static std::unique_ptr<S2Shape> SoupToClassicShape(int s, const int8_t* dim, const uint32_t* scb, const uint32_t* cvb, const double* v) {
+  if (dim[s] == 1) {
+    std::vector<S2Point> pts;
+    for (uint32_t c = scb[s]; c < scb[s + 1]; ++c)
+      for (uint32_t k = cvb[c]; k < cvb[c + 1]; ++k) pts.push_back(P(v + 3 * k));
+    auto shape = std::make_unique<S2Polyline::OwningShape>();
+    shape->Init(std::make_unique<S2Polyline>(pts, S2Debug::DISABLE));
+    return shape;
+  }
+  if (dim[s] == 2) {
+    std::vector<std::unique_ptr<S2Loop>> loops;
+    for (uint32_t c = scb[s]; c < scb[s + 1]; ++c) {
+      std::vector<S2Point> pts;
+      for (uint32_t k = cvb[c]; k < cvb[c + 1]; ++k) pts.push_back(P(v + 3 * k));
+      if (pts.empty()) pts.push_back(S2Loop::kFull()[0]);   // a zero-vertex chain is the full loop (S2LaxPolygonShape convention)
+      loops.push_back(std::make_unique<S2Loop>(pts, S2Debug::DISABLE));
+    }
+    auto poly = std::make_unique<S2Polygon>();
+    poly->set_s2debug_override(S2Debug::DISABLE);
+    poly->InitOriented(std::move(loops));
+    auto shape = std::make_unique<S2Polygon::OwningShape>();
+    shape->Init(std::move(poly));
+    return shape;
+  }
+  return SoupToLaxShape(s, dim, scb, cvb, v);
+}
 size_t ref_tagged_shapes_encode(int num_shapes, const int8_t* dim, const uint32_t* scb, const uint32_t* cvb, const double* v, int hint,
                                 uint8_t* out, size_t capacity) {
   s2coding::StringVectorEncoder shape_vector;
   for (int s = 0; s < num_shapes; ++s) {
-    auto shape = SoupToLaxShape(s, dim, scb, cvb, v);
+    auto shape = (hint & 2) ? SoupToClassicShape(s, dim, scb, cvb, v) : SoupToLaxShape(s, dim, scb, cvb, v);
+    hint &= ~0;
     Encoder* sub = shape_vector.AddViaEncoder();
     sub->Ensure(Encoder::kVarintMax32);
     sub->put_varint32(shape->type_tag());
-    shape->Encode(sub, hint ? s2coding::CodingHint::COMPACT : s2coding::CodingHint::FAST);
+    shape->Encode(sub, (hint & 1) ? s2coding::CodingHint::COMPACT : s2coding::CodingHint::FAST);
   }
   Encoder enc;
   shape_vector.Encode(&enc);
@@ -634,6 +667,8 @@ size_t ref_tagged_shapes_decode_edges(const uint8_t* bytes, size_t len, int max_
     if (tag == S2PointVectorShape::kTypeTag) { auto p = std::make_unique<S2PointVectorShape>(); if (!p->Init(&d)) return (size_t)-1; shape = std::move(p); }
     else if (tag == S2LaxPolylineShape::kTypeTag) { auto p = std::make_unique<S2LaxPolylineShape>(); if (!p->Init(&d)) return (size_t)-1; shape = std::move(p); }
     else if (tag == S2LaxPolygonShape::kTypeTag) { auto p = std::make_unique<S2LaxPolygonShape>(); if (!p->Init(&d)) return (size_t)-1; shape = std::move(p); }
+    else if (tag == S2Polygon::Shape::kTypeTag) { auto p = std::make_unique<S2Polygon::OwningShape>(); if (!p->Init(&d)) return (size_t)-1; shape = std::move(p); }
+    else if (tag == S2Polyline::Shape::kTypeTag) { auto p = std::make_unique<S2Polyline::OwningShape>(); if (!p->Init(&d)) return (size_t)-1; shape = std::move(p); }
     else return (size_t)-1;
     dims_out[s] = shape->dimension();
     num_edges_out[s] = (uint32_t)shape->num_edges();
@@ -869,3 +904,4 @@ size_t ref_cellunion_cell_union_bound(const uint64_t* ids, size_t m, uint64_t* o
 }
 
 }  // extern "C"
+#pragma GCC visibility pop

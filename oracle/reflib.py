@@ -185,11 +185,13 @@ class Ref:
         self.lib.ref_chord_length2.restype = ctypes.c_double
         return float(self.lib.ref_chord_length2(ctypes.c_double(angle_rad)))
 
-    def tagged_shapes_encode(self, soup, compact=False):
-        """The soup as S2PointVectorShape / S2LaxPolylineShape / S2LaxPolygonShape, encoded as EncodeTaggedShapes does."""
+    def tagged_shapes_encode(self, soup, compact=False, classic=False):
+        """The soup as S2PointVectorShape / S2LaxPolylineShape / S2LaxPolygonShape — or, with classic=True, polygons as
+        S2Polygon::Shape (loops through S2Polygon::InitOriented) and polylines as S2Polyline::Shape — encoded as
+        EncodeTaggedShapes does (hint FAST, or COMPACT)."""
         self.lib.ref_tagged_shapes_encode.restype = _sz
         args = (int(soup.num_shapes), _p(soup.shape_dim), _p(soup.shape_chain_begin), _p(soup.chain_vertex_begin),
-                _p(np.ascontiguousarray(soup.vertices, np.float64)), int(bool(compact)))
+                _p(np.ascontiguousarray(soup.vertices, np.float64)), int(bool(compact)) | (2 if classic else 0))
         n = int(self.lib.ref_tagged_shapes_encode(*args, None, _sz(0)))
         out = np.zeros(max(n, 1), np.uint8)
         self.lib.ref_tagged_shapes_encode(*args, _p(out), _sz(out.size))

@@ -110,6 +110,7 @@ SIGNATURES = {
     "s2b_index_info": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "s2b_contains": (_i, [_vp, _vp, _sz, _i, _vp]),
     "s2b_contains_dev": (_i, [_vp, _vp, _sz, _i, _vp, _vp]),
+    "s2b_count_flags_dev": (_i, [_vp, _sz, _vp, _vp]),
     "s2b_shape_contains": (_i, [_vp, _i, _vp, _sz, _i, _vp]),
     "s2b_shape_contains_dev": (_i, [_vp, _i, _vp, _sz, _i, _vp, _vp]),
     "s2b_shape_histogram": (_i, [_vp, _vp, _sz, _i, _vp]),

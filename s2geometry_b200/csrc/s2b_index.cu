@@ -509,6 +509,30 @@ incident_edges_kernel(const FlatIndexView ix, const int32_t* __restrict__ edge_i
   }
 }
 
+// Number of non-zero flags (the hit count of a Contains batch): 16 flags per load, one atomic per CTA.
+__global__ void __launch_bounds__(kThreads)
+count_flags_kernel(const uint8_t* __restrict__ flags, size_t n, unsigned long long* __restrict__ count) {
+  unsigned int local = 0;
+  const size_t n16 = n / 16;
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  for (size_t k = (size_t)blockIdx.x * kThreads + threadIdx.x; k < n16; k += stride) {
+    const uint4 v = __ldcs((const uint4*)flags + k);
+    // flags are 0 or 1 per byte for this library's outputs, but any non-zero byte counts: fold each byte to its low bit
+    auto nz = [](uint32_t w) { w |= w >> 4; w |= w >> 2; w |= w >> 1; return __popc(w & 0x01010101u); };
+    local += nz(v.x) + nz(v.y) + nz(v.z) + nz(v.w);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 15)) local += flags[n16 * 16 + threadIdx.x] != 0;
+  for (int o = 16; o; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+  __shared__ unsigned int s_part[kThreads / 32];
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < kThreads / 32; ++w) t += s_part[w];
+    if (t) atomicAdd(count, t);
+  }
+}
+
 static int grid_for_ix(size_t n, const void* kernel) {
   int per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
@@ -922,6 +946,16 @@ int s2b_containing_shapes_fill_dev(const S2bIndex* ix, const double* xyz, size_t
   QueryOut o{}; o.offsets = offsets; o.shape_ids = shape_ids;
   cudaError_t e = launch_query_t<kModeFill>(ix->view, xyz, n, model, o, (cudaStream_t)stream);
   return e == cudaSuccess ? S2B_OK : cuda_fail(e, "fill launch");
+}
+
+int s2b_count_flags_dev(const uint8_t* flags_dev, size_t n, uint64_t* count_dev, void* stream) {
+  if (n == 0) return S2B_OK;
+  if (!flags_dev || !count_dev) return set_error(S2B_EINVAL, "null pointer");
+  if ((uintptr_t)flags_dev % 16) return set_error(S2B_EINVAL, "flags_dev must be 16-byte aligned");
+  count_flags_kernel<<<grid_for_ix(n / 16 + 1, (const void*)count_flags_kernel), kThreads, 0, (cudaStream_t)stream>>>(flags_dev, n, (unsigned long long*)count_dev);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? S2B_OK : cuda_fail(e, "count_flags launch");
 }
 
 int s2b_diag_force_exact_locate(int on) {

@@ -5,10 +5,14 @@
 //   S2LaxPolylineShape   (tag 4)  s2lax_polyline_shape.cc:74-86    EncodedS2PointVector
 //   S2LaxPolygonShape    (tag 5)  s2lax_polygon_shape.cc:177-252   version, num_loops, EncodedS2PointVector, loop starts
 //   EncodedS2PointVector           encoded_s2point_vector.cc:121-134 (format), :205-250 (UNCOMPRESSED), :836-942 (CELL_IDS)
+//   S2Polygon::Shape     (tag 1)  s2polygon.cc:787-860 (lossless, version 1), :1485-1531 (compressed, version 4);
+//                                 loops: s2loop.cc:640-690, :1377-1436; edges are ORIENTED (holes reversed): s2polygon.cc Shape::chain_edge
+//   S2Polyline::Shape    (tag 2)  s2polyline.cc:425-475 (lossless, version 1), :527-560 (compressed, version 2)
+//   S2DecodePointsCompressed       s2point_compression.cc:330-391 (face runs, 2nd-order delta coded (pi, qi), off-centre points)
 // Decoding handles both point-vector formats (the CELL_IDS decoder is restated from the format description and the
-// reference decoder's arithmetic); encoding writes the UNCOMPRESSED ("FAST" hint) form, byte-identical to the reference.
-// S2Polygon::Shape (tag 1) and S2Polyline::Shape (tag 2) are not handled (S2B_EINVAL): they carry S2Loop/S2Polygon
-// state this path never uses.
+// reference decoder's arithmetic) and both encodings of S2Polygon / S2Polyline; encoding writes the lax shapes in their
+// UNCOMPRESSED ("FAST" hint) form, byte-identical to the reference. Of an S2Polygon only what the shape exposes is kept:
+// its loops as oriented vertex chains (the depth decides the orientation); bounds and origin_inside are skipped.
 #pragma once
 #include <cstdint>
 #include <cstring>
@@ -133,6 +137,167 @@ inline bool decode_point_vector(Reader* r, std::vector<double>* out, std::string
 
 }  // namespace wire
 
+namespace wire {
+
+// S2DecodePointsCompressed (s2point_compression.cc:330-391): n points snapped to `level`, appended to *out.
+inline bool decode_points_compressed(Reader* r, int level, uint64_t n, std::vector<double>* out, std::string* why) {
+  auto fail = [&](const char* m) { *why = m; return false; };
+  if (level > 30) return fail("bad snap level");
+  if (n > (uint64_t)r->avail() + 1) return fail("more points than bytes");   // every point but the first takes >= 1 byte
+  std::vector<uint8_t> faces;   // one face per point, from the run-length list (Faces::Decode :131-142)
+  faces.reserve((size_t)(n < (1u << 20) ? n : (1u << 20)));
+  while (faces.size() < n) {
+    uint64_t face_and_count;
+    if (!r->varint64(&face_and_count)) return fail("truncated face runs");
+    const uint64_t count = face_and_count / 6;
+    if (count == 0 || count > 0x7FFFFFFFull) return fail("bad face run");
+    if (count > n - faces.size() && r->avail() == 0) return fail("face run beyond the points");
+    // the reference accepts a last run that overshoots; only the faces of the n points are used
+    const uint64_t take = count < n - faces.size() ? count : n - faces.size();
+    faces.insert(faces.end(), (size_t)take, (uint8_t)(face_and_count % 6));
+  }
+  // NthDerivativeCoder(2)::Decode (util/coding/nth-derivative.h:122-128): the order in use grows 1, 2, 2, ... with the
+  // calls; for (i = used - 1 .. 0) k = memory[i] = memory[i] + k, in wrap-around 32-bit arithmetic.
+  struct Nth { int32_t m[2] = {0, 0}; int used = 0; } pm, qm;
+  auto nth_decode = [](Nth& c, int32_t k) {
+    if (c.used < 2) ++c.used;
+    for (int i = c.used - 1; i >= 0; --i) { k = (int32_t)((uint32_t)k + (uint32_t)c.m[i]); c.m[i] = k; }
+    return k;
+  };
+  auto deinterleave = [](uint64_t code, uint32_t* even, uint32_t* odd) {   // util_bits::DeinterleaveUint32: val0 = even bits, val1 = odd bits
+    auto compact = [](uint64_t x) {
+      x &= 0x5555555555555555ull; x = (x | (x >> 1)) & 0x3333333333333333ull; x = (x | (x >> 2)) & 0x0f0f0f0f0f0f0f0full;
+      x = (x | (x >> 4)) & 0x00ff00ff00ff00ffull; x = (x | (x >> 8)) & 0x0000ffff0000ffffull; x = (x | (x >> 16)) & 0xffffffffull;
+      return (uint32_t)x;
+    };
+    *even = compact(code); *odd = compact(code >> 1);
+  };
+  const size_t at = out->size();
+  out->resize(at + 3 * (size_t)n);
+  for (uint64_t i = 0; i < n; ++i) {
+    uint32_t a, b;
+    int32_t pi, qi;
+    if (i == 0) {   // DecodeFirstPointFixedLength: (level + 7) / 8 * 2 bytes, interleaved, little endian
+      const int bytes = (level + 7) / 8 * 2;
+      uint64_t code;
+      if (!r->uint_with_length(bytes, &code)) return fail("truncated first point");
+      deinterleave(code, &a, &b);
+      pi = nth_decode(pm, (int32_t)a); qi = nth_decode(qm, (int32_t)b);
+    } else {        // DecodePointCompressed: varint64 of interleaved zig-zag coded second differences
+      uint64_t code;
+      if (!r->varint64(&code)) return fail("truncated point");
+      deinterleave(code, &a, &b);
+      auto zz = [](uint32_t n) { return (int32_t)((n >> 1) ^ (uint32_t)(-(int32_t)(n & 1))); };
+      pi = nth_decode(pm, zz(a)); qi = nth_decode(qm, zz(b));
+    }
+    // FacePiQitoXYZ: FaceUVtoXYZ(face, STtoUV((pi + 0.5) / 2^level), STtoUV((qi + 0.5) / 2^level)).Normalize()
+    const double scale = (double)(1 << level);
+    const P3 p = normalize(face_uv_to_xyz(faces[i], st_to_uv((pi + 0.5) / scale), st_to_uv((qi + 0.5) / scale)));
+    double* q = out->data() + at + 3 * i;
+    q[0] = p.x; q[1] = p.y; q[2] = p.z;
+  }
+  uint32_t num_off_center;
+  if (!r->varint32(&num_off_center) || num_off_center > n) return fail("bad off-centre count");
+  for (uint32_t k = 0; k < num_off_center; ++k) {
+    uint32_t index;
+    if (!r->varint32(&index) || index >= n) return fail("bad off-centre index");
+    if (r->avail() < 24) return fail("truncated off-centre point");
+    std::memcpy(out->data() + at + 3 * (size_t)index, r->p, 24);
+    r->p += 24;
+  }
+  return true;
+}
+
+inline bool skip_latlng_rect(Reader* r) {   // S2LatLngRect::Encode: version byte + 4 doubles (s2latlng_rect.cc)
+  if (r->avail() < 33) return false;
+  r->p += 33;
+  return true;
+}
+
+// One decoded S2Loop -> an oriented chain appended to the soup (S2Polygon::Shape: holes run backwards, the full loop is a
+// chain without vertices, empty loops are dropped as S2Polygon::Decode drops them).
+inline void append_oriented_loop(ShapeSoupData* out, std::vector<double>* loop, uint32_t depth) {
+  const size_t nv = loop->size() / 3;
+  if (nv == 0) return;
+  if (nv == 1) {                                  // S2Loop::is_empty_or_full(): empty if z >= 0, full if z < 0
+    if (!((*loop)[2] < 0)) return;
+    out->chain_vertex_begin.push_back((uint32_t)(out->vertices.size() / 3));
+    return;
+  }
+  if (depth & 1)                                  // is_hole(): oriented_vertex(i) = vertex(n - 1 - i)
+    for (size_t i = 0; i < nv / 2; ++i)
+      for (int c = 0; c < 3; ++c) std::swap((*loop)[3 * i + c], (*loop)[3 * (nv - 1 - i) + c]);
+  out->vertices.insert(out->vertices.end(), loop->begin(), loop->end());
+  out->chain_vertex_begin.push_back((uint32_t)(out->vertices.size() / 3));
+}
+
+// S2Polygon::Decode (tag 1 payload).
+inline bool decode_s2polygon(Reader* r, ShapeSoupData* out, std::string* why) {
+  auto fail = [&](const char* m) { *why = m; return false; };
+  uint32_t version;
+  if (!r->get8(&version)) return fail("truncated polygon");
+  std::vector<double> loop;
+  if (version == 1) {                             // DecodeUncompressed
+    uint32_t owns, holes;
+    uint64_t num_loops;
+    if (!r->get8(&owns) || !r->get8(&holes) || !r->uint_with_length(4, &num_loops)) return fail("truncated polygon header");
+    if (num_loops > 10000000) return fail("too many loops");
+    for (uint64_t l = 0; l < num_loops; ++l) {    // S2Loop::Decode
+      uint32_t lv, origin_inside;
+      uint64_t nv, depth;
+      if (!r->get8(&lv) || lv != 1) return fail("bad loop version");
+      if (!r->uint_with_length(4, &nv) || nv > 50000000 || r->avail() < nv * 24 + 5) return fail("truncated loop");
+      loop.resize(3 * (size_t)nv);
+      if (nv) std::memcpy(loop.data(), r->p, (size_t)nv * 24);
+      r->p += nv * 24;
+      r->get8(&origin_inside);
+      if (!r->uint_with_length(4, &depth)) return fail("truncated loop");
+      if (!skip_latlng_rect(r)) return fail("truncated loop bound");
+      append_oriented_loop(out, &loop, (uint32_t)depth);
+    }
+    if (!skip_latlng_rect(r)) return fail("truncated polygon bound");
+    return true;
+  }
+  if (version != 4) return fail("unknown polygon encoding version");
+  uint32_t snap_level, num_loops;                 // DecodeCompressed
+  if (!r->get8(&snap_level) || snap_level > 30) return fail("bad snap level");
+  if (!r->varint32(&num_loops) || num_loops > 10000000) return fail("bad loop count");
+  for (uint32_t l = 0; l < num_loops; ++l) {      // S2Loop::DecodeCompressed
+    uint32_t nv, properties, depth;
+    if (!r->varint32(&nv) || nv == 0 || nv > 50000000) return fail("bad vertex count");
+    loop.clear();
+    if (!decode_points_compressed(r, (int)snap_level, nv, &loop, why)) return false;
+    if (!r->varint32(&properties) || !r->varint32(&depth)) return fail("truncated loop properties");
+    if ((properties & 2) && !skip_latlng_rect(r)) return fail("truncated loop bound");   // kBoundEncoded = bit 1
+    append_oriented_loop(out, &loop, depth);
+  }
+  return true;
+}
+
+// S2Polyline::Decode (tag 2 payload): the vertices as one chain.
+inline bool decode_s2polyline(Reader* r, ShapeSoupData* out, std::string* why) {
+  auto fail = [&](const char* m) { *why = m; return false; };
+  uint32_t version;
+  if (!r->get8(&version)) return fail("truncated polyline");
+  if (version == 1) {
+    uint64_t nv;
+    if (!r->uint_with_length(4, &nv) || nv > 50000000 || r->avail() < nv * 24) return fail("truncated polyline");
+    const size_t at = out->vertices.size();
+    out->vertices.resize(at + 3 * (size_t)nv);
+    if (nv) std::memcpy(out->vertices.data() + at, r->p, (size_t)nv * 24);
+    r->p += nv * 24;
+    return true;
+  }
+  if (version != 2) return fail("unknown polyline encoding version");
+  uint32_t snap_level, nv;
+  if (!r->get8(&snap_level) || snap_level > 30) return fail("bad snap level");
+  if (!r->varint32(&nv) || nv > 50000000) return fail("bad vertex count");
+  return nv == 0 || decode_points_compressed(r, (int)snap_level, nv, &out->vertices, why);
+}
+
+}  // namespace wire
+
+
 // Decodes s2shapeutil::{Fast,Compact}EncodeTaggedShapes output into a shape soup (dimension-2 shapes: one chain per loop).
 inline int decode_tagged_shapes(const uint8_t* bytes, size_t len, ShapeSoupData* out, size_t* consumed, std::string* err) {
   using namespace wire;
@@ -196,6 +361,13 @@ inline int decode_tagged_shapes(const uint8_t* bytes, size_t len, ShapeSoupData*
           }
           if (prev != nv) return fail("loop starts do not cover the vertices" + where);
         }
+      } else if (tag == 1) {             // S2Polygon::Shape
+        out->shape_dim.push_back(2);
+        if (!decode_s2polygon(&sr, out, &why)) return fail(why + where);
+      } else if (tag == 2) {             // S2Polyline::Shape
+        out->shape_dim.push_back(1);
+        if (!decode_s2polyline(&sr, out, &why)) return fail(why + where);
+        end_chain();
       } else {
         return fail("unsupported shape type tag " + std::to_string(tag) + where);
       }

@@ -472,6 +472,17 @@ def cell_union_contains(sorted_ids, xyz):
     return out
 
 
+def count_flags(flags, out=None):
+    """Number of non-zero entries of a uint8 CUDA tensor of flags (the hit count of a contains() batch), accumulated into
+    `out` (int64 CUDA tensor of one element; allocated and zeroed when None). No host synchronisation."""
+    lib = _lib.load()
+    if out is None:
+        out = torch.zeros(1, dtype=torch.int64, device=flags.device)
+    with torch.cuda.device(flags.device):
+        _lib.check(lib.s2b_count_flags_dev(_ptr(flags), flags.numel(), _ptr(out), _stream()))
+    return out
+
+
 def exact_stage_count(reset=False):
     """How many predicate evaluations ran the exact (superaccumulator) stage on the device so far."""
     v = ctypes.c_uint64(0)

@@ -98,12 +98,13 @@ def test_serialized_index_plus_shapes_round_trip(ref):
 
 def test_malformed_shapes_are_rejected_not_crashed(ref):
     soup = [s for n, s in wire_soups(ref) if n == "snapped18"][0]
-    for compact in (False, True):
-        data = ref.tagged_shapes_encode(soup, compact)
+    csoup = [s for n, s in classic_soups(ref) if n == "snapped20"][0]
+    for compact, classic in ((False, False), (True, False), (False, True), (True, True)):
+        data = ref.tagged_shapes_encode(csoup if classic else soup, compact, classic=classic)
         for cut in list(range(0, 64)) + list(range(64, len(data), 131)):
             with pytest.raises(_lib.S2BError):
                 decode_shapes(data[:cut])
-        rng = np.random.default_rng(3 + compact)
+        rng = np.random.default_rng(3 + compact + 2 * classic)
         bad = 0
         for _ in range(1500):
             b = bytearray(data)
@@ -115,8 +116,60 @@ def test_malformed_shapes_are_rejected_not_crashed(ref):
             except _lib.S2BError:
                 bad += 1
         assert bad > 0
-    with pytest.raises(_lib.S2BError):          # S2Polygon::Shape (tag 1) is not a supported geometry carrier
-        decode_shapes(bytes([8, 2, 1, 0]))
+    with pytest.raises(_lib.S2BError):          # an unknown type tag
+        decode_shapes(bytes([8, 2, 9, 0]))
+
+
+def classic_soups(ref):
+    """Scenes for S2Polygon::Shape / S2Polyline::Shape: valid nested polygons (holes, several shells), polylines, snapped
+    (compressed encodings: S2EncodePointsCompressed) and unsnapped (lossless), with a few off-centre vertices."""
+    yield "polygons", scenes.polygons_scene(60, 23)
+    for level in (30, 20, 9):
+        s = ShapeSoup()
+        for loops in synth.many_polygons(25, 70 + level, min_vertices=4, max_vertices=90, min_radius_km=300.0, max_radius_km=1200.0):
+            s.add_polygon([snap(ref, l, level) for l in loops])
+        line = snap(ref, synth.cap_points(np.array([0.3, 0.2, 0.9]), 0.3, 120, 4), level)
+        s.add_polyline(line)
+        mixed = line.copy(); mixed[5] = synth.sphere_points(1, 6)[0]; mixed[77] = synth.sphere_points(1, 8)[0]     # off-centre points
+        s.add_polyline(mixed)
+        big = snap(ref, synth.wobbly_loop(np.array([-0.2, 0.7, 0.1]), 0.4, 200), level)                              # >= 64 vertices: bound encoded
+        s.add_polygon([big])
+        yield "snapped%d" % level, s.freeze()
+    e = ShapeSoup(); e.add_polygon([]); e.add_polyline(np.zeros((0, 3))); e.add_polygon([np.zeros((0, 3))]); e.add_polyline(synth.sphere_points(2, 2))
+    yield "empty_and_full", e.freeze()
+
+
+def test_s2polygon_and_s2polyline_shapes_decode_like_the_reference(ref):
+    """Tags 1 and 2 (S2Polygon::Shape, S2Polyline::Shape), both coding hints: the decoded vertex chains give exactly the
+    edges the reference's own OwningShape::Init gives (oriented: holes reversed), and the lossless form reproduces the
+    input rings up to the reference's own loop reordering (compared as edge sets per shape)."""
+    saw_compressed = 0
+    for name, soup in classic_soups(ref):
+        for compact in (False, True):
+            data = ref.tagged_shapes_encode(soup, compact, classic=True)
+            lax = ref.tagged_shapes_encode(soup, False)
+            got, used = decode_shapes(data)
+            assert used == len(data), name
+            dims, ne, redges = ref.tagged_shapes_decode_edges(data)
+            ge, gc = edges_of(got)
+            assert got.num_shapes == soup.num_shapes and (got.shape_dim == dims).all(), (name, compact)
+            assert (gc == ne).all(), (name, compact, gc, ne)
+            assert (ge.view(np.uint64) == redges.view(np.uint64)).all(), (name, compact)     # bit-identical, same edge order
+            if compact and len(data) < 0.5 * len(lax):
+                saw_compressed += 1
+            if not compact:      # lossless: the same set of directed edges as the input soup, shape by shape
+                we, wc = edges_of(soup)
+                assert (gc == wc).all(), name
+                o = 0
+                for n in gc:
+                    a = sorted(map(bytes, ge[o:o + n].view(np.uint8).reshape(n, 48))) if n else []
+                    b = sorted(map(bytes, we[o:o + n].view(np.uint8).reshape(n, 48))) if n else []
+                    assert a == b, name
+                    o += n
+            # and the decoded geometry indexes to the same answers as the reference's index over the original shapes
+        flat = build_flat_index(decode_shapes(ref.tagged_shapes_encode(soup, False, classic=True))[0])
+        assert flat.num_shape_ids == soup.num_shapes
+    assert saw_compressed >= 2      # the snapped scenes really used S2EncodePointsCompressed
 
 
 def test_golden_shapes_fixture():
@@ -124,7 +177,7 @@ def test_golden_shapes_fixture():
     from tests.util import fixture
     z = fixture("shapes_wire.npz")
     keys = sorted({k.split("__")[0] for k in z.files})
-    assert len(keys) == 4
+    assert len(keys) == 6 and sum(k.startswith("classic") for k in keys) == 2
     for key in keys:
         data = z[key + "__bytes"].tobytes()
         got, used = decode_shapes(data)
@@ -132,5 +185,5 @@ def test_golden_shapes_fixture():
         ge, gc = edges_of(got)
         assert (got.shape_dim == z[key + "__dims"]).all() and (gc == z[key + "__num_edges"]).all()
         assert (ge.view(np.uint64) == z[key + "__edges"].reshape(-1, 6).view(np.uint64)).all()
-        if key.endswith("_fast"):
+        if key.endswith("_fast") and not key.startswith("classic"):
             assert encode_shapes(got) == data

@@ -106,6 +106,18 @@ def shapes_wire_fixture(ref):
             out[key + "__bytes"] = np.frombuffer(data, np.uint8)
             out[key + "__dims"] = dims; out[key + "__num_edges"] = ne; out[key + "__edges"] = edges
             print("shapes_wire", key, "bytes=%d edges=%d" % (len(data), len(edges)))
+    # S2Polygon::Shape / S2Polyline::Shape (tags 1, 2) in their lossless and compressed encodings
+    from tests.test_shapes_wire import classic_soups
+    for name, soup in classic_soups(ref):
+        if name != "snapped20":
+            continue
+        for compact in (False, True):
+            data = ref.tagged_shapes_encode(soup, compact, classic=True)
+            dims, ne, edges = ref.tagged_shapes_decode_edges(data)
+            key = "classic%s_%s" % (name, "compact" if compact else "fast")
+            out[key + "__bytes"] = np.frombuffer(data, np.uint8)
+            out[key + "__dims"] = dims; out[key + "__num_edges"] = ne; out[key + "__edges"] = edges
+            print("shapes_wire", key, "bytes=%d edges=%d" % (len(data), len(edges)))
     np.savez_compressed(os.path.join(G, "shapes_wire.npz"), **out)
 
 
@@ -127,6 +139,9 @@ if __name__ == "__main__":
     ref = reflib.load()
     if len(sys.argv) > 1 and sys.argv[1] == "covering":
         covering_fixture(ref)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "shapes":
+        shapes_wire_fixture(ref)
         sys.exit(0)
     encode_fixture(ref)
     index_fixture(ref)
