@@ -25,7 +25,6 @@ struct FlatClip { int32_t shape_id; uint32_t edge_begin; uint32_t num_edges; uin
 struct FlatEdge { double v0x, v0y, v0z, v1x, v1y, v1z; };
 
 struct LutRange { uint32_t lo, hi; };
-
 struct FlatIndexView {
   const uint64_t* cell_ids;
   const FlatCell* cells;

@@ -112,13 +112,15 @@ struct PhaseAOut {
   unsigned long long* hist; int target_shape; unsigned int* cell_counts;
 };
 
+// have_info: the caller already loaded ix.interior_info[c] (the staged exact Locate issues that load together with its last probe).
 template <int kInteriorMode>
 __device__ __forceinline__ void route_located(const FlatIndexView& ix, const PhaseAOut& o, bool write_outputs, uint32_t i, int c,
-                                              WarpSlots& edge_slots, WarpSlots& interior_slots, unsigned lane, bool single_interior = false) {
+                                              WarpSlots& edge_slots, WarpSlots& interior_slots, unsigned lane, bool single_interior = false,
+                                              bool have_info = false, int loaded_info = 0) {
   // single_interior: the lookup table already said that cell c is a pure interior cell with one clipped shape. "Any" and
   // "count" then need nothing else; the other modes still read the cell's info for the shape id.
   int info = 0;
-  if (c >= 0) info = ((kInteriorMode == 1 || kInteriorMode == 2) && single_interior) ? -1 : ix.interior_info[c];
+  if (c >= 0) info = ((kInteriorMode == 1 || kInteriorMode == 2) && single_interior) ? -1 : (have_info ? loaded_info : ix.interior_info[c]);
   uint8_t flag = 0;
   uint32_t cnt = 0;
   const bool to_edges = c >= 0 && info == 0;
@@ -141,7 +143,10 @@ __device__ __forceinline__ void route_located(const FlatIndexView& ix, const Pha
   if (kInteriorMode != 1 && kInteriorMode != 2) interior_slots.append(to_interior, HitWork{i, c}, o.work, o.capacity, o.counters + 1, -1, lane);
 }
 
-// Phase A, exact: FP64 K1 + Locate, then route_located.
+// Phase A, exact: FP64 K1 + Locate, then route_located. The kernel is a chain of dependent gathers per point
+// (list -> point -> table -> candidate range -> ~6 probes of cell_ids -> cell info), so every stage is issued for all
+// kPointsPerThread points of a thread before any of them is consumed: the loads of a stage are in flight together
+// (the binary searches of a thread advance in lock step, one probe each per round).
 template <int kInteriorMode, int kCtasPerSm, int kPointsPerThread>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 locate_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint32_t n_points, const uint32_t* __restrict__ list,
@@ -153,20 +158,25 @@ locate_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint32_t n
   __shared__ uint16_t s_pos[16384];   // 6-bit Hilbert table
   for (int k = threadIdx.x; k < 16384 / 8; k += kThreads) ((uint4*)s_pos)[k] = ((const uint4*)g_hilbert_wide_ix)[k];
   __syncthreads();
-  constexpr uint32_t kSpan = kThreads * kPointsPerThread;
+  constexpr int kP = kPointsPerThread;
+  constexpr uint32_t kSpan = kThreads * kP;
   const uint32_t stride = gridDim.x * kSpan;
   const unsigned lane = threadIdx.x & 31u;
+  const bool have_cells = ix.num_cells != 0;
   WarpSlots edge_slots, interior_slots;
-  // whole warps iterate together (the ballots need all lanes); kPointsPerThread independent chains per thread
+  // whole warps iterate together (the ballots need all lanes)
   for (uint32_t base = blockIdx.x * kSpan + (threadIdx.x & ~31u); base < n; base += stride) {
-    uint32_t idx[kPointsPerThread];
-    int cell[kPointsPerThread];
-    P3 p[kPointsPerThread];
+    uint32_t idx[kP];
+    P3 p[kP];
+    // stage 0: the indices, then the points (independent gathers)
 #pragma unroll
-    for (int t = 0; t < kPointsPerThread; ++t) {
+    for (int t = 0; t < kP; ++t) {
       const uint32_t k = base + t * kThreads + lane;
       idx[t] = 0xFFFFFFFFu;
       if (k < n) idx[t] = list ? list[k] : k;
+    }
+#pragma unroll
+    for (int t = 0; t < kP; ++t) {
       if (idx[t] != 0xFFFFFFFFu) {
         const double* q = xyz + 3 * (size_t)idx[t];
         p[t] = P3{__ldcs(q), __ldcs(q + 1), __ldcs(q + 2)};
@@ -174,18 +184,67 @@ locate_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint32_t n
         p[t] = P3{1.0, 0.0, 0.0};
       }
     }
+    // stage 1: projection; stage 2: the lookup-table entries
+    int face[kP];
+    uint32_t ci[kP], cj[kP], e0[kP];
 #pragma unroll
-    for (int t = 0; t < kPointsPerThread; ++t) {
+    for (int t = 0; t < kP; ++t) {
       double fi, fj;
-      const int face = point_to_face_fij(p[t], &fi, &fj);
-      const uint32_t ci = fij_to_ij(fi), cj = fij_to_ij(fj);
-      cell[t] = locate_cell(ix, face, ci, cj, [&] { return from_face_ij_wide(face, ci, cj, s_pos); });
+      face[t] = point_to_face_fij(p[t], &fi, &fj);
+      ci[t] = fij_to_ij(fi); cj[t] = fij_to_ij(fj);
     }
 #pragma unroll
-    for (int t = 0; t < kPointsPerThread; ++t) {
+    for (int t = 0; t < kP; ++t)
+      e0[t] = (have_cells && idx[t] != 0xFFFFFFFFu) ? ix.lut[lut_bucket(ix.lut_level, face[t], ci[t], cj[t])] : kLutEmpty;
+    // stage 3: candidate ranges of the mixed buckets; stage 4: their leaf ids
+    uint32_t lo[kP], hi[kP];
+    uint64_t leaf[kP];
+#pragma unroll
+    for (int t = 0; t < kP; ++t) {
+      lo[t] = hi[t] = 0;
+      if ((e0[t] & ~kLutIndexMask) == kLutMixed) { const LutRange r = ix.mixed[e0[t] & kLutIndexMask]; lo[t] = r.lo; hi[t] = r.hi; }
+    }
+#pragma unroll
+    for (int t = 0; t < kP; ++t)
+      leaf[t] = (e0[t] & ~kLutIndexMask) == kLutMixed ? from_face_ij_wide(face[t], ci[t], cj[t], s_pos) : 0;
+    // stage 5: the searches (locate_cell's loop: last cell whose range_min <= leaf), one probe per point per round
+    bool any = true;
+    while (any) {
+      uint32_t mid[kP];
+      uint64_t probe[kP];
+#pragma unroll
+      for (int t = 0; t < kP; ++t) {
+        mid[t] = (lo[t] + hi[t] + 1) >> 1;
+        probe[t] = lo[t] < hi[t] ? ix.cell_ids[mid[t]] : 0;
+      }
+      any = false;
+#pragma unroll
+      for (int t = 0; t < kP; ++t) {
+        if (lo[t] < hi[t]) {
+          if (cellid_range_min(probe[t]) <= leaf[t]) lo[t] = mid[t]; else hi[t] = mid[t] - 1;
+          any |= lo[t] < hi[t];
+        }
+      }
+    }
+    // stage 6: the candidate's id and, speculatively, its interior info (both depend only on the search result)
+    int cell[kP], info[kP];
+    uint64_t cand[kP];
+#pragma unroll
+    for (int t = 0; t < kP; ++t) {
+      const uint32_t kind = e0[t] & ~kLutIndexMask;
+      cell[t] = kind == kLutMixed ? (int)lo[t] : ((kind == kLutInside || kind == kLutInterior) ? (int)(e0[t] & kLutIndexMask) : -1);
+      cand[t] = kind == kLutMixed ? ix.cell_ids[cell[t]] : 0;
+      info[t] = cell[t] >= 0 ? ix.interior_info[cell[t]] : 0;
+    }
+#pragma unroll
+    for (int t = 0; t < kP; ++t)
+      if ((e0[t] & ~kLutIndexMask) == kLutMixed && !(cellid_range_min(cand[t]) <= leaf[t] && leaf[t] <= cellid_range_max(cand[t]))) cell[t] = -1;
+    // stage 7: outputs, work lists
+#pragma unroll
+    for (int t = 0; t < kP; ++t) {
       const uint32_t i = idx[t];
       const bool valid = i != 0xFFFFFFFFu;
-      route_located<kInteriorMode>(ix, o, valid, i, valid ? cell[t] : -1, edge_slots, interior_slots, lane);
+      route_located<kInteriorMode>(ix, o, valid, i, valid ? cell[t] : -1, edge_slots, interior_slots, lane, false, true, info[t]);
     }
   }
   edge_slots.finish(o.work, o.capacity, +1, lane);
@@ -261,12 +320,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // 12 KB tile (kThreads * kPointsPerThread points) and the tile after the current one is in flight while the current one
 // is processed, so the bytes in flight occupy neither registers nor issue slots. (History: with register staging this
 // kernel was DRAM-latency-bound at 2.0 TB/s; with per-thread cp.async the copy loop itself cost ~35 instructions per
-// point.) Requires xyz to be 16-byte aligned; an odd point count leaves 8 bytes that the issuing thread copies itself.
+// point; per-WARP tiles of 1.5 KB — no block barrier — were slower still, 112 vs 149 Gpts/s: eight times as many bulk
+// copies.) Requires xyz to be 16-byte aligned; an odd point count leaves 8 bytes that the issuing thread copies itself.
+// (Measured and rejected here: folding the located cell's info into 8-byte table entries — one load instead of two —
+// 113 vs 149 Gpts/s on uniform points: the 50 MB table no longer stays in the L2 next to the point stream; issuing the
+// table and info loads of a thread's two points together before routing either: join +2 %, uniform points -5 %.)
 template <int kInteriorMode, int kPointsPerThread>
 __global__ void __launch_bounds__(kThreads, 6)
 locate_fast_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint32_t n, uint32_t* __restrict__ uncertain, const PhaseAOut o) {
   unsigned int* const counters = o.counters;
-  constexpr uint32_t kTilePoints = kThreads * kPointsPerThread;
+  constexpr int kP = kPointsPerThread;
+  constexpr uint32_t kTilePoints = kThreads * kP;
   constexpr uint32_t kTileBytes = kTilePoints * 24;
   __shared__ __align__(128) double s_tile[2][kTilePoints * 3];
   __shared__ __align__(8) uint64_t s_bar[2];
@@ -279,7 +343,8 @@ locate_fast_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint3
   const unsigned lane = threadIdx.x & 31u;
   const int lut_level = ix.lut_level;                           // 2..10
   const int bucket_bits = 30 - lut_level;                       // log2 of the bucket size in leaf cells (>= 20)
-  const int bucket_mask = (1 << bucket_bits) - 1;
+  const uint32_t bucket_mask = (1u << bucket_bits) - 1u;
+  const uint32_t margin_span = bucket_mask - 2u * (uint32_t)kFastRadius;
   const uint64_t total_bytes = (uint64_t)n * 24;
   const uint32_t num_tiles = (n + kTilePoints - 1) / kTilePoints;
   WarpSlots edge_slots, interior_slots;
@@ -307,7 +372,7 @@ locate_fast_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint3
     const double* pts = s_tile[stage];
     const uint32_t tile_point0 = tile * kTilePoints;
 #pragma unroll
-    for (int t = 0; t < kPointsPerThread; ++t) {
+    for (int t = 0; t < kP; ++t) {
       const uint32_t li = t * kThreads + threadIdx.x;
       const uint32_t i = tile_point0 + li;
       const bool valid = i < n;
@@ -326,13 +391,11 @@ locate_fast_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint3
       // certain only if both coordinates are valid and well inside their lookup-table bucket (NaN/garbage gives fi = 0 or
       // saturated / negative values, which fail these tests). Unsigned arithmetic folds each pair of bounds into one compare.
       const uint32_t ufi = (uint32_t)fi, ufj = (uint32_t)fj;
-      const uint32_t ri = ufi & (uint32_t)bucket_mask, rj = ufj & (uint32_t)bucket_mask;
-      const uint32_t margin_span = (uint32_t)bucket_mask - 2u * (uint32_t)kFastRadius;
+      const uint32_t ri = ufi & bucket_mask, rj = ufj & bucket_mask;
       bool certain = valid & ((ufi | ufj) < (1u << 30)) & (max(ri - (uint32_t)kFastRadius, rj - (uint32_t)kFastRadius) <= margin_span);
       // the table is addressed by (face, i, j) of the bucket: no Hilbert encoding on this path. The masked coordinates
       // always give a valid bucket, so the read is unconditional (no branch around it).
-      const uint32_t bucket = lut_bucket(lut_level, face, ufi & 0x3FFFFFFFu, ufj & 0x3FFFFFFFu);
-      const uint32_t e0 = ix.lut[bucket];
+      const uint32_t e0 = ix.lut[lut_bucket(lut_level, face, ufi & 0x3FFFFFFFu, ufj & 0x3FFFFFFFu)];
       const uint32_t kind = e0 & ~kLutIndexMask;
       const bool inside = (kind == kLutInside) | (kind == kLutInterior);
       const int c = (certain & inside) ? (int)(e0 & kLutIndexMask) : -1;
@@ -363,44 +426,54 @@ cell_scatter_kernel(const HitWork* __restrict__ work, const unsigned int* __rest
   }
 }
 
+// One work item: crossing parity of point `hw.point` against every clipped shape of cell `hw.cell`.
+template <int kMode>
+__device__ __forceinline__ void process_hit(const FlatIndexView& ix, const double* __restrict__ xyz, const HitWork hw, int model, const QueryOut& out) {
+  const double* q = xyz + 3 * (size_t)hw.point;
+  const P3 p{q[0], q[1], q[2]};
+  const FlatCell fc = ix.cells[hw.cell];
+  const P3 a{fc.cx, fc.cy, fc.cz};
+  const P3 a_cross_b = cross(a, p);
+  uint32_t result = 0;
+  uint32_t fill_at = kMode == kModeFill ? out.offsets[hw.point] : 0u;
+  for (uint32_t k = 0; k < fc.clip_count; ++k) {
+    const FlatClip clip = ix.clips[fc.clip_begin + k];
+    if (kMode == kModeShape && clip.shape_id != out.shape_id) continue;
+    if (clip_contains(ix, clip, a, p, a_cross_b, model)) {
+      if (kMode == kModeAny || kMode == kModeShape) { result = 1; break; }
+      if (kMode == kModeHistogram) atomicAdd(out.counts + clip.shape_id, 1ull);
+      if (kMode == kModeCount) ++result;
+      if (kMode == kModeFill) out.shape_ids[fill_at++] = clip.shape_id;
+    } else if (kMode == kModeShape) {
+      break;
+    }
+  }
+  if (kMode == kModeAny || kMode == kModeShape) { if (result) out.flags[hw.point] = 1; }
+  if (kMode == kModeCount) { if (result) out.per_point[hw.point] = result; }
+}
+
+// Phase B, both work lists in one launch: first the edge-bearing hits — `edge_list`[0 .. *edge_count), either the forward
+// list of phase A or its cell-sorted copy — then, when `with_interior`, the interior hits that still need per-shape
+// output, stored backward from work_base[capacity - 1] (their number is counters[1]). (As two launches the second one,
+// a few thousand items, cost as much as half of the first: launch latency and an almost empty GPU.)
 template <int kMode, int kCtasPerSm>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
-process_kernel(const FlatIndexView ix, const double* __restrict__ xyz, const HitWork* __restrict__ work_base, uint32_t capacity,
-               const unsigned int* __restrict__ counters, int which_list, int model, const QueryOut out) {
-  // list 0: hits with edge work, stored forward from work_base[0]; list 1: interior hits, stored backward from the end
-  // which_list == 3: the cell-sorted copy of list 0; its length is the last element of the scanned per-cell counts,
-  // which the host passes as `counters` (so counters[0] is the length)
-  const unsigned int count = which_list == 3 ? counters[0] : counters[which_list];
-  const HitWork* work = which_list == 1 ? work_base + (capacity - count) : work_base;
+process_kernel(const FlatIndexView ix, const double* __restrict__ xyz, const HitWork* __restrict__ edge_list, const unsigned int* __restrict__ edge_count,
+               const HitWork* __restrict__ work_base, uint32_t capacity, const unsigned int* __restrict__ counters, bool with_interior, int model,
+               const QueryOut out) {
   const unsigned int stride = gridDim.x * kThreads;
   const unsigned lane = threadIdx.x & 31u;
-  // warp-uniform trip count + __syncwarp(): lanes with long edge lists or exact-stage work rejoin every iteration
-  for (unsigned int wbase = blockIdx.x * kThreads + (threadIdx.x & ~31u); wbase < count; wbase += stride, __syncwarp()) {
-    const unsigned int w = wbase + lane;
-    if (w >= count) continue;
-    const HitWork hw = work[w];
-    if (hw.cell < 0) continue;   // unused slot of a reservation chunk
-    const double* q = xyz + 3 * (size_t)hw.point;
-    const P3 p{q[0], q[1], q[2]};
-    const FlatCell fc = ix.cells[hw.cell];
-    const P3 a{fc.cx, fc.cy, fc.cz};
-    const P3 a_cross_b = cross(a, p);
-    uint32_t result = 0;
-    uint32_t fill_at = kMode == kModeFill ? out.offsets[hw.point] : 0u;
-    for (uint32_t k = 0; k < fc.clip_count; ++k) {
-      const FlatClip clip = ix.clips[fc.clip_begin + k];
-      if (kMode == kModeShape && clip.shape_id != out.shape_id) continue;
-      if (clip_contains(ix, clip, a, p, a_cross_b, model)) {
-        if (kMode == kModeAny || kMode == kModeShape) { result = 1; break; }
-        if (kMode == kModeHistogram) atomicAdd(out.counts + clip.shape_id, 1ull);
-        if (kMode == kModeCount) ++result;
-        if (kMode == kModeFill) out.shape_ids[fill_at++] = clip.shape_id;
-      } else if (kMode == kModeShape) {
-        break;
-      }
+  for (int pass = 0; pass < (with_interior ? 2 : 1); ++pass) {
+    const unsigned int count = pass == 0 ? *edge_count : counters[1];
+    const HitWork* work = pass == 0 ? edge_list : work_base + (capacity - count);
+    // warp-uniform trip count + __syncwarp(): lanes with long edge lists or exact-stage work rejoin every iteration
+    for (unsigned int wbase = blockIdx.x * kThreads + (threadIdx.x & ~31u); wbase < count; wbase += stride, __syncwarp()) {
+      const unsigned int w = wbase + lane;
+      if (w >= count) continue;
+      const HitWork hw = work[w];
+      if (hw.cell < 0) continue;   // unused slot of a reservation chunk
+      process_hit<kMode>(ix, xyz, hw, model, out);
     }
-    if (kMode == kModeAny || kMode == kModeShape) { if (result) out.flags[hw.point] = 1; }
-    if (kMode == kModeCount) { if (result) out.per_point[hw.point] = result; }
   }
 }
 
@@ -564,7 +637,16 @@ static bool g_force_exact_locate = false;
 
 // Launch shapes, fixed after measurement on B200 (DESIGN.md "Measured and rejected" lists the alternatives): exact Locate
 // 4 CTAs/SM x 2 points per thread, FP32 pre-filter 2 points per thread, phase B 2 CTAs/SM.
-constexpr int kLocateCtas = 4, kLocatePoints = 2, kFastPoints = 2, kProcessCtas = 2;
+#ifndef S2B_LOCATE_POINTS
+#define S2B_LOCATE_POINTS 4
+#endif
+#ifndef S2B_LOCATE_CTAS
+#define S2B_LOCATE_CTAS 3
+#endif
+#ifndef S2B_FAST_POINTS
+#define S2B_FAST_POINTS 2
+#endif
+constexpr int kLocateCtas = S2B_LOCATE_CTAS, kLocatePoints = S2B_LOCATE_POINTS, kFastPoints = S2B_FAST_POINTS, kProcessCtas = 2;
 
 template <int kMode>
 static cudaError_t launch_query_t(const FlatIndexView& ix, const double* xyz, size_t n, int model, const QueryOut& out, cudaStream_t st) {
@@ -639,15 +721,12 @@ static cudaError_t launch_query_t(const FlatIndexView& ix, const double* xyz, si
       // the scatter advances cell_counts[c] from the start to the end of cell c's segment; cell_counts[C] stays the total
       cell_scatter_kernel<<<sort_grid, kThreads, 0, st>>>(work, counter, cell_counts, sorted);
       count_launch();
-      proc<<<proc_grid, kThreads, 0, st>>>(ix, xyz + 3 * off, sorted, 0u, cell_counts + C, 3, model, o);
-    } else {
-      proc<<<proc_grid, kThreads, 0, st>>>(ix, xyz + 3 * off, work, (uint32_t)capacity, counter, 0, model, o);
     }
+    constexpr bool kWithInterior = kInteriorMode != 1 && kInteriorMode != 2;
+    // cell_counts[C] (after the scan) = number of valid edge hits = length of the sorted list
+    proc<<<proc_grid, kThreads, 0, st>>>(ix, xyz + 3 * off, sort_by_cell ? sorted : work, sort_by_cell ? cell_counts + C : counter, work,
+                                         (uint32_t)capacity, counter, kWithInterior, model, o);
     count_launch();
-    if (kInteriorMode != 1 && kInteriorMode != 2) {
-      proc<<<proc_grid, kThreads, 0, st>>>(ix, xyz + 3 * off, work, (uint32_t)capacity, counter, 1, model, o);
-      count_launch();
-    }
     e = cudaGetLastError();
   }
   cudaError_t e2 = cudaFreeAsync(work, st);
