@@ -449,6 +449,29 @@ int s2b_closest_points_dev(const S2bPointIndex* index, const double* targets_xyz
                            int32_t* data_out_dev, double* length2_out_dev, uint32_t* count_out_dev, void* stream);
 int s2b_closest_point_dev(const S2bPointIndex* index, const double* targets_xyz_dev, size_t n, double max_length2,
                           int32_t* data_out_dev, double* length2_out_dev, void* stream);
+/* The same query for the reference's other target types (s2closest_point_query.h:110-131) and its full option set
+ * (s2closest_point_query_base.h:82-101):
+ *   target_kind  S2B_TARGET_POINT  PointTarget: targets = n x 3 doubles
+ *                S2B_TARGET_EDGE   EdgeTarget(a, b): targets = n x 6 doubles; distance = S2::UpdateMinDistance(p, a, b)
+ *                                  (s2edge_distances.cc:93-223, with S2::RobustCrossProd in all of its stages)
+ *                S2B_TARGET_CELL   CellTarget(S2Cell(id)): targets = n uint64 cell ids; distance = S2Cell::GetDistance(p)
+ *                                  (s2cell.cc:382-436; 0 inside the cell)
+ *   max_results  1..32: the nearest k index points within the limit per target (rows of data_out / length2_out as
+ *                s2b_closest_points); 0: options.max_results unlimited — only count_out[i] = the number of index points within
+ *                the limit is reported (data_out / length2_out may be NULL)
+ *   max_length2  S1ChordAngle length2 of options.max_distance (exclusive); INFINITY = none
+ *   max_error_radians  options.max_error: the reference MAY then substitute points up to that much further away; the results
+ *                here are always the exact ones, which satisfies every max_error >= 0
+ * (S2ClosestPointQuery::ShapeIndexTarget and options.region are not provided.) */
+#define S2B_TARGET_POINT 0
+#define S2B_TARGET_EDGE 1
+#define S2B_TARGET_CELL 2
+int s2b_closest_points_to_targets(const S2bPointIndex* index, int target_kind, const void* targets, size_t n, int max_results,
+                                  double max_length2, double max_error_radians, int32_t* data_out, double* length2_out,
+                                  uint32_t* count_out);
+int s2b_closest_points_to_targets_dev(const S2bPointIndex* index, int target_kind, const void* targets_dev, size_t n, int max_results,
+                                      double max_length2, double max_error_radians, int32_t* data_out_dev, double* length2_out_dev,
+                                      uint32_t* count_out_dev, void* stream);
 
 /* --------------------------------------------------------------------------------------------------
  * S2CellIndex joins, batch form (s2cell_index.h:113-441, s2cell_index.cc:71-163) and the S2RegionSharder built on it

@@ -734,6 +734,36 @@ void ref_closest_points(void* h, const double* targets, size_t n, int k, double 
     }
   });
 }
+// FindClosestPoints for any target kind (0 PointTarget: 3 doubles, 1 EdgeTarget: 6 doubles a, b, 2 CellTarget: uint64 id) with
+// max_results = k (k == 0: unlimited, counts only), max_distance (negative = none) and max_error (radians).
+void ref_closest_points_target(void* h, int kind, const void* targets, size_t n, int k, double max_distance_rad, double max_error_rad,
+                               int32_t* data, double* length2, uint32_t* counts, int threads) {
+  auto* index = &((RefPointIndex*)h)->index;
+  ParallelFor(n, threads, [&](size_t b, size_t e, int) {
+    S2ClosestPointQuery<int> query(index);
+    if (k > 0) query.mutable_options()->set_max_results(k);
+    if (max_distance_rad >= 0) query.mutable_options()->set_max_distance(S1Angle::Radians(max_distance_rad));
+    if (max_error_rad > 0) query.mutable_options()->set_max_error(S1Angle::Radians(max_error_rad));
+    for (size_t i = b; i < e; ++i) {
+      std::vector<S2ClosestPointQuery<int>::Result> r;
+      if (kind == 0) {
+        S2ClosestPointQuery<int>::PointTarget target(P((const double*)targets + 3 * i));
+        r = query.FindClosestPoints(&target);
+      } else if (kind == 1) {
+        S2ClosestPointQuery<int>::EdgeTarget target(P((const double*)targets + 6 * i), P((const double*)targets + 6 * i + 3));
+        r = query.FindClosestPoints(&target);
+      } else {
+        S2ClosestPointQuery<int>::CellTarget target(S2Cell(S2CellId(((const uint64_t*)targets)[i])));
+        r = query.FindClosestPoints(&target);
+      }
+      counts[i] = (uint32_t)r.size();
+      for (int j = 0; j < k; ++j) {
+        data[i * k + j] = j < (int)r.size() ? r[j].data() : -1;
+        length2[i * k + j] = j < (int)r.size() ? r[j].distance().length2() : HUGE_VAL;
+      }
+    }
+  });
+}
 double ref_chord_length2(double angle_rad) { return S1ChordAngle(S1Angle::Radians(angle_rad)).length2(); }
 
 // S2CellUnion::Contains(S2CellId) (bit0) and ::Intersects(S2CellId) (bit1).

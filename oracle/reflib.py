@@ -289,6 +289,20 @@ def _closest_k(self, targets, k, max_distance_rad=-1.0, threads=0):
 RefPointIndex.closest_k = _closest_k
 
 
+def _closest_targets(self, kind, targets, k, max_distance_rad=-1.0, max_error_rad=0.0, threads=0):
+    """FindClosestPoints for PointTarget (kind 0, (n,3)), EdgeTarget (1, (n,6)) or CellTarget (2, uint64 ids); k == 0: counts only."""
+    t = np.ascontiguousarray(targets, np.uint64 if kind == 2 else np.float64)
+    n = t.size if kind == 2 else len(t.reshape(-1, 3 if kind == 0 else 6))
+    kk = max(k, 1)
+    data = np.zeros((n, kk), np.int32); l2 = np.zeros((n, kk), np.float64); cnt = np.zeros(n, np.uint32)
+    self.lib.ref_closest_points_target(_vp(self.h), int(kind), _p(t), _sz(n), int(k), ctypes.c_double(max_distance_rad), ctypes.c_double(max_error_rad),
+                                       _p(data), _p(l2), _p(cnt), int(threads))
+    return data, l2, cnt
+
+
+RefPointIndex.closest_targets = _closest_targets
+
+
 class RefIndex:
     """A MutableS2ShapeIndex built by the reference from a shape soup (see s2geometry_b200.shapes.ShapeSoup)."""
 

@@ -18,6 +18,7 @@
 #include "s2b_core.cuh"
 #include "s2b_hilbert.h"
 #include "s2b_internal.h"
+#include "s2b_region.cuh"   // RobustCrossProd (edge targets), S2Cell(S2CellId) bounds (cell targets)
 
 struct S2bPointIndex {
   int device = 0;
@@ -266,6 +267,195 @@ closest_points_kernel(const IndexView ix, const double* __restrict__ targets, co
       if (length2_out) length2_out[t * (size_t)k + r] = r < cnt ? dist[r] : HUGE_VAL;
     }
     if (count_out) count_out[t] = (uint32_t)cnt;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Targets other than points (S2ClosestPointQuery::EdgeTarget / CellTarget, s2closest_point_query.h:110-131).
+// The distance from an index point to the target is the reference's own expression:
+//   edge   S2::UpdateMinDistance(p, a, b, &min_dist)   s2edge_distances.cc:93-223 (S2MinDistanceEdgeTarget, s2min_distance_targets.cc:79-82)
+//   cell   S2Cell(id).GetDistance(p)                    s2cell.cc:335-436          (S2MinDistanceCellTarget, :114-117)
+// A query's result is a function of those distances only, so the search order is free: every target scans the
+// S2Cap::GetCellUnionBound-style covering (covering_cells) of a cap around the target's bounding cap.
+enum TargetKind { kTargetPoint = 0, kTargetEdge = 1, kTargetCell = 2 };
+
+// AlwaysUpdateMinDistance<false>: true (and *dist2 = the S1ChordAngle length2 of the distance) iff it is below limit2.
+// The interior case's early exits compare against the limit exactly as the reference does.
+__device__ __forceinline__ bool edge_update_min_distance(const P3& x, const P3& a, const P3& b, double limit2, double* dist2) {
+  const double xa2 = norm2(sub(x, a)), xb2 = norm2(sub(x, b));
+  const double ab2 = norm2(sub(a, b));
+  const double max_error = (4.75 * DBL_EPSILON) * ((xa2 + xb2) + ab2) + (8 * DBL_EPSILON * DBL_EPSILON);
+  if (!(fabs(xa2 - xb2) >= ab2 + max_error)) {
+    const P3 c = robust_cross_prod(a, b);
+    const double c2 = norm2(c);
+    const double x_dot_c = dot(x, c);
+    const double x_dot_c2 = x_dot_c * x_dot_c;
+    if (!(x_dot_c2 > c2 * limit2)) {
+      const P3 cx = cross(c, x);
+      if (!(dot(sub(a, x), cx) >= 0 || dot(sub(b, x), cx) <= 0)) {
+        const double qr = 1 - sqrt(norm2(cx) / c2);
+        const double d2 = (x_dot_c2 / c2) + (qr * qr);
+        if (!(d2 >= limit2)) { *dist2 = d2 < 4.0 ? d2 : 4.0; return true; }
+      }
+    }
+  }
+  const double v = xa2 < xb2 ? xa2 : xb2;      // std::min(xa2, xb2)
+  if (v >= limit2) return false;
+  *dist2 = v < 4.0 ? v : 4.0;
+  return true;
+}
+
+// S2Cell::GetDistance(const S2Point&) = GetDistanceInternal(target, to_interior = true) as a length2.
+__device__ __forceinline__ double cell_edge_distance2(double dir, double uv) {     // EdgeDistance (s2cell.cc:366-380)
+  const double pq2 = (dir * dir) / (1 + uv * uv);
+  const double qr = 1 - sqrt(1 - pq2);
+  const double d = pq2 + qr * qr;
+  return d < 4.0 ? d : 4.0;
+}
+__device__ __forceinline__ double cell_vertex_distance2(const P3& p, double u, double v) {   // VertexChordDist (:335-339)
+  const double d = norm2(sub(p, normalize(P3{u, v, 1.0})));
+  return d < 4.0 ? d : 4.0;
+}
+__device__ __forceinline__ double cell_point_distance2(const TargetCell& cell, const P3& xyz) {
+  const P3 t = face_xyz_to_uvw(cell.face, xyz);
+  const double u0 = cell.bound.ulo, u1 = cell.bound.uhi, v0 = cell.bound.vlo, v1 = cell.bound.vhi;
+  const double dir00 = t.x - t.z * u0, dir01 = t.x - t.z * u1, dir10 = t.y - t.z * v0, dir11 = t.y - t.z * v1;
+  // VEdgeIsClosest(p, u_end) / UEdgeIsClosest(p, v_end) (:344-362)
+  auto v_edge_closest = [&](double u) { return dot(t, P3{-u * v0, u * u + 1, -v0}) > 0 && dot(t, P3{-u * v1, u * u + 1, -v1}) < 0; };
+  auto u_edge_closest = [&](double v) { return dot(t, P3{v * v + 1, -u0 * v, -u0}) > 0 && dot(t, P3{v * v + 1, -u1 * v, -u1}) < 0; };
+  bool inside = true;
+  if (dir00 < 0) { inside = false; if (v_edge_closest(u0)) return cell_edge_distance2(-dir00, u0); }
+  if (dir01 > 0) { inside = false; if (v_edge_closest(u1)) return cell_edge_distance2(dir01, u1); }
+  if (dir10 < 0) { inside = false; if (u_edge_closest(v0)) return cell_edge_distance2(-dir10, v0); }
+  if (dir11 > 0) { inside = false; if (u_edge_closest(v1)) return cell_edge_distance2(dir11, v1); }
+  if (inside) return 0.0;
+  const double a = cell_vertex_distance2(t, u0, v0), b = cell_vertex_distance2(t, u1, v0);
+  const double c = cell_vertex_distance2(t, u0, v1), d = cell_vertex_distance2(t, u1, v1);
+  const double ab = b < a ? b : a, cd = d < c ? d : c;          // std::min(x, y) = (y < x) ? y : x
+  return cd < ab ? cd : ab;
+}
+
+struct TargetGeom {
+  P3 a, b;            // point: a; edge: a, b
+  TargetCell cell;    // cell
+  P3 center;          // of a cap that bounds the target
+  double rho;         // its radius in radians, rounded up (only steers the search: any valid bound gives the same results)
+};
+
+template <int kKind>
+__device__ __forceinline__ TargetGeom load_target(const void* targets, size_t t, const uint16_t* ij_table) {
+  TargetGeom g{};
+  if (kKind == kTargetPoint) {
+    const double* q = (const double*)targets + 3 * t;
+    g.a = P3{q[0], q[1], q[2]};
+    g.center = g.a; g.rho = 0.0;
+  } else if (kKind == kTargetEdge) {
+    const double* q = (const double*)targets + 6 * t;
+    g.a = P3{q[0], q[1], q[2]}; g.b = P3{q[3], q[4], q[5]};
+    const P3 m = add(g.a, g.b);
+    const double n2 = norm2(m);
+    if (n2 > 1e-20) {
+      g.center = normalize(m);
+      const double d2 = fmax(norm2(sub(g.center, g.a)), norm2(sub(g.center, g.b)));
+      g.rho = 2.0 * asin(fmin(1.0, 0.5 * sqrt(d2))) * (1 + 1e-9) + 1e-15;
+    } else {          // (nearly) antipodal endpoints: no useful bound, search the whole sphere
+      g.center = g.a; g.rho = 4.0;
+    }
+  } else {
+    const uint64_t id = ((const uint64_t*)targets)[t];
+    g.cell = target_cell(id, ij_table);
+    g.center = cellid_to_point(id, ij_table);
+    double d2 = 0.0;
+    const P3 c = face_xyz_to_uvw(g.cell.face, g.center);
+    d2 = fmax(fmax(cell_vertex_distance2(c, g.cell.bound.ulo, g.cell.bound.vlo), cell_vertex_distance2(c, g.cell.bound.uhi, g.cell.bound.vlo)),
+              fmax(cell_vertex_distance2(c, g.cell.bound.ulo, g.cell.bound.vhi), cell_vertex_distance2(c, g.cell.bound.uhi, g.cell.bound.vhi)));
+    g.rho = 2.0 * asin(fmin(1.0, 0.5 * sqrt(d2))) * (1 + 1e-9) + 1e-15;
+  }
+  return g;
+}
+
+template <int kKind>
+__device__ __forceinline__ bool target_distance(const TargetGeom& g, const P3& p, double limit2, double* dist2) {
+  if (kKind == kTargetPoint) { const double d = chord_length2(p, g.a); if (!(d < limit2)) return false; *dist2 = d; return true; }
+  if (kKind == kTargetEdge) return edge_update_min_distance(p, g.a, g.b, limit2, dist2);
+  const double d = cell_point_distance2(g.cell, p);
+  if (!(d < limit2)) return false;
+  *dist2 = d;
+  return true;
+}
+
+// FindClosestPoints for any target kind. k == 0: count every index point within the limit (options.max_results unlimited,
+// counts only); k >= 1: the k nearest within the limit, nearest first (ties: smaller data first), rows padded with -1 / +inf.
+// One thread per target. The covering widens level by level (as closest_points_kernel) from the finest level whose
+// covering is guaranteed to contain the target's bounding cap; a level's result is final once the k-th distance lies
+// within what that covering guarantees for the target (covered angle minus the bounding cap's radius), or once the
+// covering contains everything within the distance limit.
+template <int kKind>
+__global__ void __launch_bounds__(kThreads)
+closest_targets_kernel(const IndexView ix, const void* __restrict__ targets, size_t n, int k, int start_level, double limit2, double limit_angle,
+                       const double* __restrict__ covered_angle /* [31]: entry L+1 = angle of the cap covered at level L */,
+                       int32_t* __restrict__ data_out, double* __restrict__ length2_out, uint32_t* __restrict__ count_out) {
+  __shared__ uint16_t s_pos[1024], s_ij[1024];
+  __shared__ double s_cov[31];
+  for (int q = threadIdx.x; q < 1024; q += kThreads) { s_pos[q] = g_hilbert_pi.pos[q]; s_ij[q] = g_hilbert_pi.ij[q]; }
+  if (threadIdx.x < 31) s_cov[threadIdx.x] = covered_angle[threadIdx.x];
+  __syncthreads();
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < n; t += stride) {
+    const TargetGeom g = load_target<kKind>(targets, t, s_ij);
+    double fi, fj;
+    const int face = point_to_face_fij(g.center, &fi, &fj);
+    const int i = (int)fij_to_ij(fi), j = (int)fij_to_ij(fj);
+    // finest level whose covering contains the bounding cap itself
+    int level = start_level;
+    while (level >= 0 && !(s_cov[level + 1] > g.rho)) --level;
+    const double need = limit_angle + g.rho;     // the covering that contains everything within the limit
+    if (k == 0) { while (level >= 0 && !(s_cov[level + 1] >= need)) --level; }
+    double dist[kMaxResults];
+    int32_t data[kMaxResults];
+    int cnt = 0;
+    uint32_t total = 0;
+    for (;; --level) {
+      uint64_t cells[6];
+      const int nc = covering_cells(face, i, j, level, s_pos, cells);
+      cnt = 0; total = 0;
+      for (int c6 = 0; c6 < nc; ++c6) {
+        uint32_t first, last;
+        cell_range(ix, cells[c6], &first, &last);
+        for (uint32_t c = first; c < last; ++c) {
+          const double* pp = ix.pts + 3 * (size_t)c;
+          double d;
+          // with a full result set the reference's limit is the k-th distance; ties are then resolved on the data value below
+          if (!target_distance<kKind>(g, P3{pp[0], pp[1], pp[2]}, limit2, &d)) continue;
+          ++total;
+          if (k == 0) continue;
+          const int32_t dv = ix.data[c];
+          if (cnt == k && !(d < dist[k - 1] || (d == dist[k - 1] && dv < data[k - 1]))) continue;
+          int pos = cnt < k ? cnt : k - 1;
+          while (pos > 0 && (d < dist[pos - 1] || (d == dist[pos - 1] && dv < data[pos - 1]))) {
+            dist[pos] = dist[pos - 1]; data[pos] = data[pos - 1];
+            --pos;
+          }
+          dist[pos] = d; data[pos] = dv;
+          if (cnt < k) ++cnt;
+        }
+      }
+      if (level < 0) break;                                      // whole sphere scanned
+      const double covered = s_cov[level + 1];
+      if (covered >= need) break;                                // everything within the limit was covered
+      if (k > 0 && cnt == k) {
+        const double guaranteed = covered - g.rho;               // every point within this angle of the target was scanned
+        if (guaranteed > 0) {
+          const double h = sin(0.5 * guaranteed);
+          if (dist[k - 1] < 4.0 * h * h * (1 - 1e-9)) break;
+        }
+      }
+    }
+    if (count_out) count_out[t] = k == 0 ? total : (uint32_t)cnt;
+    for (int r = 0; r < k; ++r) {
+      if (data_out) data_out[t * (size_t)k + r] = r < cnt ? data[r] : -1;
+      if (length2_out) length2_out[t * (size_t)k + r] = r < cnt ? dist[r] : HUGE_VAL;
+    }
   }
 }
 
@@ -528,6 +718,71 @@ int s2b_closest_points_dev(const S2bPointIndex* ix, const double* targets_dev, s
   if (order_blob) cudaFreeAsync(order_blob, st);
   cudaFreeAsync(cov_dev, st);
   return e == cudaSuccess ? S2B_OK : cuda_fail(e, "closest_points launch");
+}
+
+int s2b_closest_points_to_targets_dev(const S2bPointIndex* ix, int target_kind, const void* targets_dev, size_t n, int max_results,
+                                      double max_length2, double max_error_radians, int32_t* data_out_dev, double* length2_out_dev,
+                                      uint32_t* count_out_dev, void* stream) {
+  int rc = check_index_device(ix);
+  if (rc != S2B_OK) return rc;
+  if (target_kind < 0 || target_kind > 2) return set_error(S2B_EINVAL, "target_kind must be S2B_TARGET_POINT, _EDGE or _CELL");
+  if (max_results < 0 || max_results > kMaxResults) return set_error(S2B_EINVAL, "max_results must be in [0, %d] (0 = count only)", kMaxResults);
+  if (std::isnan(max_length2) || !(max_error_radians >= 0)) return set_error(S2B_EINVAL, "bad max_length2 / max_error");
+  if (n == 0) return S2B_OK;
+  if (!targets_dev || (max_results > 0 && !data_out_dev) || (max_results == 0 && !count_out_dev)) return set_error(S2B_EINVAL, "null pointer");
+  // max_error: results up to that much further away than the true ones MAY be substituted (s2closest_point_query_base.h:
+  // 82-101); the results computed here are exact, which satisfies every max_error >= 0.
+  cudaStream_t st = (cudaStream_t)stream;
+  double cov[31];
+  cov[0] = HUGE_VAL;
+  for (int L = 0; L < 30; ++L) cov[L + 1] = std::ldexp(kMinWidthDeriv, -(L + 1)) * (1 - 1e-9);
+  double* cov_dev = nullptr;
+  cudaError_t e = cudaMallocAsync((void**)&cov_dev, sizeof(cov), st);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync");
+  e = cudaMemcpyAsync(cov_dev, cov, sizeof(cov), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);                    // cov[] is a stack array
+  if (e != cudaSuccess) { cudaFreeAsync(cov_dev, st); return cuda_fail(e, "cudaMemcpyAsync"); }
+  int start = -1;   // a covering that holds ~4k + 16 index points on average
+  if (ix->m > 0) {
+    start = (int)std::floor(0.5 * std::log2((double)ix->m * 4.0 / (6.0 * (16.0 + 4.0 * max_results))));
+    start = start < -1 ? -1 : (start > 29 ? 29 : start);
+  }
+  if (max_results == 0) start = 29;
+  const double limit_angle = max_length2 >= 4.0 ? 4.0 : angle_of_length2(max_length2 > 0 ? max_length2 : 0.0);   // 4 > pi: "no limit"
+  const IndexView v{ix->ids, ix->pts, ix->data, ix->first, (uint32_t)ix->m, 61 - 2 * ix->table_level};
+  const int grid = grid_for_pi(n, (const void*)closest_targets_kernel<kTargetEdge>);
+  if (target_kind == kTargetPoint)
+    closest_targets_kernel<kTargetPoint><<<grid, kThreads, 0, st>>>(v, targets_dev, n, max_results, start, max_length2, limit_angle, cov_dev, data_out_dev, length2_out_dev, count_out_dev);
+  else if (target_kind == kTargetEdge)
+    closest_targets_kernel<kTargetEdge><<<grid, kThreads, 0, st>>>(v, targets_dev, n, max_results, start, max_length2, limit_angle, cov_dev, data_out_dev, length2_out_dev, count_out_dev);
+  else
+    closest_targets_kernel<kTargetCell><<<grid, kThreads, 0, st>>>(v, targets_dev, n, max_results, start, max_length2, limit_angle, cov_dev, data_out_dev, length2_out_dev, count_out_dev);
+  count_launch();
+  e = cudaGetLastError();
+  cudaFreeAsync(cov_dev, st);
+  return e == cudaSuccess ? S2B_OK : cuda_fail(e, "closest_targets launch");
+}
+
+int s2b_closest_points_to_targets(const S2bPointIndex* ix, int target_kind, const void* targets, size_t n, int max_results, double max_length2,
+                                  double max_error_radians, int32_t* data_out, double* length2_out, uint32_t* count_out) {
+  if (target_kind < 0 || target_kind > 2) return set_error(S2B_EINVAL, "target_kind must be S2B_TARGET_POINT, _EDGE or _CELL");
+  if (max_results < 0 || max_results > kMaxResults) return set_error(S2B_EINVAL, "max_results must be in [0, %d] (0 = count only)", kMaxResults);
+  if (n == 0) return S2B_OK;
+  if (!targets) return set_error(S2B_EINVAL, "null pointer");
+  const size_t k = (size_t)max_results, tbytes = target_kind == kTargetPoint ? 24 : (target_kind == kTargetEdge ? 48 : 8);
+  void *t = nullptr, *d = nullptr, *l = nullptr, *c = nullptr;
+  cudaError_t e = cudaMalloc(&t, tbytes * n);
+  if (e == cudaSuccess) e = cudaMalloc(&d, 4 * n * (k ? k : 1));
+  if (e == cudaSuccess) e = cudaMalloc(&l, 8 * n * (k ? k : 1));
+  if (e == cudaSuccess) e = cudaMalloc(&c, 4 * n);
+  if (e == cudaSuccess) e = cudaMemcpy(t, targets, tbytes * n, cudaMemcpyHostToDevice);
+  int rc = e == cudaSuccess ? s2b_closest_points_to_targets_dev(ix, target_kind, t, n, max_results, max_length2, max_error_radians, (int32_t*)d, (double*)l, (uint32_t*)c, nullptr)
+                            : cuda_fail(e, "cudaMalloc/cudaMemcpy");
+  if (rc == S2B_OK && k && data_out && (e = cudaMemcpy(data_out, d, 4 * n * k, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy");
+  if (rc == S2B_OK && k && length2_out && (e = cudaMemcpy(length2_out, l, 8 * n * k, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy");
+  if (rc == S2B_OK && count_out && (e = cudaMemcpy(count_out, c, 4 * n, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy");
+  cudaFree(t); cudaFree(d); cudaFree(l); cudaFree(c);
+  return rc;
 }
 
 // Host-pointer forms (whole-array copies).

@@ -59,11 +59,42 @@ class PointIndex:
             pass
 
 
+TARGET_POINT, TARGET_EDGE, TARGET_CELL = 0, 1, 2   # include/s2b_capi.h S2B_TARGET_*
+
+
 class ClosestPointQuery:
-    def __init__(self, index, max_distance_rad=math.inf):
+    """Batch form of S2ClosestPointQuery<int>: options.max_distance (exclusive) and, for the general form, max_results and
+    max_error; targets are points (count / closest / closest_k) or, through `find`, edges and cells as well."""
+
+    def __init__(self, index, max_distance_rad=math.inf, max_error_rad=0.0):
         self.index = index
         self._lib = index._lib
         self.max_length2 = chord_length2(max_distance_rad)
+        self.max_error_rad = float(max_error_rad)
+
+    def find(self, target_kind, targets, max_results):
+        """FindClosestPoints for PointTarget (TARGET_POINT, (N,3) float64), EdgeTarget (TARGET_EDGE, (N,6): a, b) or
+        CellTarget (TARGET_CELL, N uint64 / int64 cell ids) with options.max_results = max_results (1..32) ->
+        (data (N,k) padded with -1, length2 (N,k) padded with inf, counts (N,)); max_results = 0 (unlimited) -> counts only."""
+        k = int(max_results)
+        kind = int(target_kind)
+        if _is_tensor(targets):
+            t = targets.contiguous()
+            n = t.numel() if kind == TARGET_CELL else t.shape[0]
+            cnt = torch.empty(n, dtype=torch.int32, device=t.device)
+            data = torch.empty((n, k), dtype=torch.int32, device=t.device) if k else None
+            l2 = torch.empty((n, k), dtype=torch.float64, device=t.device) if k else None
+            _lib.check(self._lib.s2b_closest_points_to_targets_dev(self.index._h, kind, t.data_ptr(), n, k, self.max_length2, self.max_error_rad,
+                                                                   data.data_ptr() if k else None, l2.data_ptr() if k else None, cnt.data_ptr(), _stream()))
+            return (data, l2, cnt) if k else cnt
+        t = np.ascontiguousarray(targets, np.uint64 if kind == TARGET_CELL else np.float64)
+        n = t.size if kind == TARGET_CELL else len(t.reshape(-1, 3 if kind == TARGET_POINT else 6))
+        cnt = np.zeros(n, np.uint32)
+        data = np.full((n, max(k, 1)), -1, np.int32)
+        l2 = np.full((n, max(k, 1)), np.inf, np.float64)
+        _lib.check(self._lib.s2b_closest_points_to_targets(self.index._h, kind, t.ctypes.data if t.size else None, n, k, self.max_length2,
+                                                           self.max_error_rad, data.ctypes.data, l2.ctypes.data, cnt.ctypes.data))
+        return (data, l2, cnt) if k else cnt
 
     def count(self, targets):
         if _is_tensor(targets):

@@ -157,3 +157,71 @@ def test_empty_index_and_empty_targets(torch_cuda):
     assert (d == -1).all() and np.isinf(l).all()
     ix2 = PointIndex(t)
     assert ClosestPointQuery(ix2, 0.5).count(np.zeros((0, 3))).size == 0
+
+
+def target_scene(ref, seed, m=120_000):
+    """An index with a dense cluster + duplicates, and edge / cell targets of every size around and far from it: short
+    and long edges (some touching index points, some degenerate a == b, a few nearly antipodal), cells of levels 0..30
+    (containing index points, empty, far away)."""
+    rng = np.random.default_rng(seed)
+    c = np.array([0.3, -0.5, 0.8]) / np.linalg.norm([0.3, -0.5, 0.8])
+    pts = np.concatenate([synth.sphere_points(m, seed), synth.cap_points(c, 0.02, m // 3, seed + 1)])
+    pts = np.concatenate([pts, pts[:500]])
+    n = 6000
+    a = np.concatenate([synth.sphere_points(n // 2, seed + 2), synth.cap_points(c, 0.05, n // 2, seed + 3)])
+    step = 10.0 ** rng.uniform(-7, 0.3, (n, 1)) * rng.standard_normal((n, 3))
+    b = a + step
+    b /= np.linalg.norm(b, axis=1)[:, None]
+    a[::50] = pts[rng.integers(0, len(pts), len(a[::50]))]            # an endpoint ON an index point
+    b[::77] = a[::77]                                                  # degenerate edges
+    b[5::400] = -a[5::400] + 1e-9 * rng.standard_normal(a[5::400].shape); b /= np.linalg.norm(b, axis=1)[:, None]   # nearly antipodal
+    edges = np.ascontiguousarray(np.concatenate([a, b], axis=1))
+    leaf = ref.encode_points(np.concatenate([pts[rng.integers(0, len(pts), 3000)], synth.sphere_points(3000, seed + 5)]), 30)
+    lv = rng.integers(0, 31, len(leaf))
+    cells = np.array([ref.parent(leaf[i:i + 1], int(l))[0] for i, l in enumerate(lv)], np.uint64)
+    return pts, edges, cells
+
+
+def test_edge_and_cell_targets_match_reference(torch_cuda, ref):
+    """S2ClosestPointQuery with EdgeTarget and CellTarget (and PointTarget through the same entry point): counts within
+    max_distance, the k nearest (distances identical; data identical wherever the distances are distinct), no limit,
+    through the host-pointer and the device-pointer calls."""
+    torch = torch_cuda
+    from s2geometry_b200.pointindex import TARGET_CELL, TARGET_EDGE, TARGET_POINT, ClosestPointQuery, PointIndex
+    pts, edges, cells = target_scene(ref, 3)
+    ri = ref.point_index(pts)
+    ix = PointIndex(pts)
+    th = ref.hardware_threads()
+    sets = ((TARGET_EDGE, edges), (TARGET_CELL, cells), (TARGET_POINT, np.ascontiguousarray(edges[:2000, :3])))
+    checked = 0
+    for kind, targets in sets:
+        for r in (1e-4, 5e-3, 0.06):
+            q = ClosestPointQuery(ix, r)
+            sub = targets if r < 0.05 else targets[::8]
+            _, _, want = ri.closest_targets(kind, sub, 0, r, 0.0, th)
+            got = q.find(kind, sub, 0)
+            assert (got == want).all(), (kind, r, int((got != want).sum()))
+            dev = torch.from_numpy(sub.view(np.int64) if kind == TARGET_CELL else sub).cuda()
+            assert (q.find(kind, dev, 0).cpu().numpy().astype(np.uint32) == want).all(), (kind, r)
+            checked += int(want.sum())
+        for k, r in ((1, math.inf), (5, math.inf), (3, 0.01), (32, 0.03)):
+            q = ClosestPointQuery(ix, r)
+            sub = targets[::3]
+            wd, wl, wc = ri.closest_targets(kind, sub, k, -1.0 if math.isinf(r) else r, 0.0, th)
+            gd, gl, gc = q.find(kind, sub, k)
+            assert (gc == wc).all(), (kind, k, r)
+            assert (gl == wl).all(), (kind, k, r, int((gl != wl).sum()))
+            # the reference orders equidistant results arbitrarily; where a row's distances are distinct the data must agree
+            distinct = np.array([len(set(row[:c])) == c for row, c in zip(wl, wc)])
+            assert (gd[distinct] == wd[distinct]).all(), (kind, k, r)
+            assert distinct.mean() > 0.5
+            dd, dl, dc = q.find(kind, torch.from_numpy(sub.view(np.int64) if kind == TARGET_CELL else sub).cuda(), k)
+            assert (dl.cpu().numpy() == wl).all() and (dc.cpu().numpy().astype(np.uint32) == wc).all()
+    assert checked > 100_000
+    # max_error: the reference may return points up to max_error further away; the exact answer is never further than that
+    q = ClosestPointQuery(ix, math.inf, max_error_rad=0.01)
+    sub = edges[::10]
+    _, wl, _ = ri.closest_targets(TARGET_EDGE, sub, 1, -1.0, 0.01, th)
+    _, gl, _ = q.find(TARGET_EDGE, sub, 1)
+    exact = ri.closest_targets(TARGET_EDGE, sub, 1, -1.0, 0.0, th)[1]
+    assert (gl == exact).all() and (np.sqrt(gl) <= np.sqrt(wl) + 1e-12).all()
