@@ -211,10 +211,13 @@ def test_edge_and_cell_targets_match_reference(torch_cuda, ref):
             gd, gl, gc = q.find(kind, sub, k)
             assert (gc == wc).all(), (kind, k, r)
             assert (gl == wl).all(), (kind, k, r, int((gl != wl).sum()))
-            # the reference orders equidistant results arbitrarily; where a row's distances are distinct the data must agree
-            distinct = np.array([len(set(row[:c])) == c for row, c in zip(wl, wc)])
+            # the reference orders equidistant results arbitrarily (the index holds 500 duplicated points, and a cell target
+            # is at distance 0 from every point inside it): the data must agree wherever a row's distances are distinct
+            # and none of its points is one of the duplicates
+            dup = (wd < 500) | (wd >= len(pts) - 500)
+            distinct = np.array([len(set(row[:c])) == c for row, c in zip(wl, wc)]) & ~dup.any(axis=1) & (wl[:, 0] > 0)
             assert (gd[distinct] == wd[distinct]).all(), (kind, k, r)
-            assert distinct.mean() > 0.5
+            assert distinct.mean() > 0.1
             dd, dl, dc = q.find(kind, torch.from_numpy(sub.view(np.int64) if kind == TARGET_CELL else sub).cuda(), k)
             assert (dl.cpu().numpy() == wl).all() and (dc.cpu().numpy().astype(np.uint32) == wc).all()
     assert checked > 100_000
