@@ -19,6 +19,7 @@
 #include "s2b_index_handle.h"
 #include "s2b_region.cuh"
 #include "s2b_internal.h"
+#include "s2b_stream.cuh"
 
 namespace s2b {
 
@@ -60,8 +61,6 @@ struct HitWork { uint32_t point; int32_t cell; };
 // Work-list slots are reserved per warp in chunks of kSlotChunk with ONE global atomicAdd per chunk (a same-address
 // atomic per warp iteration serialises at the L2: ~600k of them per 20M points when most warps see a hit). Unused slots
 // of a chunk are filled with a sentinel (cell = -1) that phase B skips.
-constexpr uint32_t kSlotChunk = 128;
-
 struct WarpSlots {
   uint32_t next = 0, end = 0;   // warp-uniform
   // Appends one entry for every lane with `want` set. dir = +1: list grows forward from work[0]; dir = -1: backward from
@@ -261,61 +260,6 @@ locate_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint32_t n
 // Error budget: double->float inputs 2^-24 each, hardware approximate reciprocal and square root <= 2 ulp each, a few
 // roundings: |u| error < 5e-7, s error < 7.5e-7, i.e. < 800 leaf cells at 2^30; kFastRadius = 2048 leaves 2.5x margin. A wrong face choice needs
 // two |components| within 6e-8 of each other, which puts (i,j) within ~60 leaf cells of a face edge: inside the radius.
-constexpr int kFastRadius = 2048;
-
-struct U32Slots {   // like WarpSlots, for a list of point indices (sentinel 0xFFFFFFFF)
-  uint32_t next = 0, end = 0;
-  __device__ __forceinline__ void append(bool want, uint32_t value, uint32_t* list, unsigned int* counter, unsigned lane) {
-    const unsigned m = __ballot_sync(0xffffffffu, want);
-    if (!m) return;
-    const uint32_t k = (uint32_t)__popc(m);
-    if (next + k > end) {
-      for (uint32_t s = next + lane; s < end; s += 32) list[s] = 0xFFFFFFFFu;
-      uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(counter, kSlotChunk);
-      next = __shfl_sync(0xffffffffu, base, 0);
-      end = next + kSlotChunk;
-    }
-    if (want) list[next + (uint32_t)__popc(m & ((1u << lane) - 1u))] = value;
-    next += k;
-  }
-  __device__ __forceinline__ void finish(uint32_t* list, unsigned lane) {
-    for (uint32_t s = next + lane; s < end; s += 32) list[s] = 0xFFFFFFFFu;
-  }
-};
-
-__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-
-__device__ __forceinline__ int approx_leaf_coord(float w) {   // w = u or v  ->  approximate leaf index (may be off by < 800)
-  const float r = 0.5f * sqrt_approx(fmaf(3.0f, fabsf(w), 1.0f));
-  const float s = w >= 0.0f ? r : 1.0f - r;
-  return __float2int_rz(1073741824.0f * s);                     // saturating; NaN -> 0
-}
-
-// mbarrier + 1-D bulk copy (TMA) helpers: one thread moves a whole tile with a single instruction.
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)), "l"(src),
-               "r"(bytes), "r"(smem_addr(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done = 0;
-  while (!done) {
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(done)
-                 : "r"(smem_addr(bar)), "r"(parity)
-                 : "memory");
-  }
-}
-
 // The point stream is staged through shared memory by the TMA unit, double buffered: one thread issues one bulk copy per
 // 12 KB tile (kThreads * kPointsPerThread points) and the tile after the current one is in flight while the current one
 // is processed, so the bytes in flight occupy neither registers nor issue slots. (History: with register staging this
