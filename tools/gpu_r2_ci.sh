@@ -1,5 +1,5 @@
 #!/bin/bash
-# S2CellIndex point join: parity tests, then the bench section's scene timed with the pre-filter and with the exact kernel only.
+# S2CellIndex point join: parity tests, then the bench section's two scenes timed.
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_cellindex_gpu.py -q -m gpu --maxfail=5 2>&1 | tail -8 | tee gpurun_out/pytest_ci.log
 timeout 600 python - <<'PY' 2>&1 | tee gpurun_out/ci_join.log
@@ -27,15 +27,12 @@ def scene(lo, hi):
 for lo, hi in ((5, 11), (9, 13)):
     ids, labels = scene(lo, hi)
     ix = CellIndex(ids, labels)
-    for force in (0, 1):
-        lib.s2b_diag_cell_index_force_exact(force)
-        for _ in range(3): c = ix.point_histogram(pts)
-        torch.cuda.synchronize()
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(10): c = ix.point_histogram(pts)
-        e1.record(); torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 10
-        print("levels %d..%d %s: %.1f Gpts/s  frac %.3f  pairs %d" % (lo, hi, "exact only" if force else "pre-filter", n / ms / 1e6, 24 * n / ms / 1e6 / 6541.1, int(c.sum().item())))
-    lib.s2b_diag_cell_index_force_exact(0)
+    for _ in range(3): c = ix.point_histogram(pts)
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10): c = ix.point_histogram(pts)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print("levels %d..%d: %.1f Gpts/s  frac %.3f  pairs %d" % (lo, hi, n / ms / 1e6, 24 * n / ms / 1e6 / 6541.1, int(c.sum().item())))
 PY
