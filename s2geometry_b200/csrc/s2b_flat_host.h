@@ -87,7 +87,7 @@ inline int pack_flat_index(const S2bFlatIndex& f, HostFlat* out, std::string* er
   // Walk the buckets in Hilbert order (b = leaf id >> lut_shift) with c = number of cells whose range_max < first leaf
   // of the bucket (the first cell a leaf of bucket b can be in), classify each (s2b_contains.cuh: empty / entirely
   // inside cell c / mixed) and store the entry at the bucket's (face, i, j) address.
-  if (C > kLutIndexMask) return fail(S2B_EINVAL, "index too large for the 30-bit lookup-table entries");
+  if (C > kLutCellMask) return fail(S2B_EINVAL, "index too large for the 29-bit cell field of the lookup-table entries");
   out->mixed.clear();
   uint64_t c = 0;
   for (uint64_t b = 0; b < nb; ++b) {
@@ -96,7 +96,8 @@ inline int pack_flat_index(const S2bFlatIndex& f, HostFlat* out, std::string* er
     uint32_t entry;
     if (c == C || cellid_range_min(f.cell_ids[c]) > last) entry = kLutEmpty;
     else if (cellid_range_min(f.cell_ids[c]) <= (first | 1) && cellid_range_max(f.cell_ids[c]) >= last)   // first | 1: the bucket's first LEAF id (leaf ids are odd)
-      entry = (out->interior_info[c] < 0 ? kLutInterior : kLutInside) | (uint32_t)c;
+      entry = out->interior_info[c] < 0 ? (kLutInterior | (uint32_t)(-out->interior_info[c] - 1))
+                                        : (kLutInside | (uint32_t)c | (out->interior_info[c] == 0 ? kLutHasEdges : 0u));
     else {
       uint64_t h = c;   // last cell starting inside the bucket
       while (h + 1 < C && cellid_range_min(f.cell_ids[h + 1]) <= last) ++h;

@@ -111,26 +111,39 @@ struct PhaseAOut {
   unsigned long long* hist; int target_shape; unsigned int* cell_counts;
 };
 
-// have_info: the caller already loaded ix.interior_info[c] (the staged exact Locate issues that load together with its last probe).
+// What is known about a located point when it is routed:
+//   kHitNone     not in any index cell
+//   kHitEdges    in cell c, which has clipped edges (the lookup table said so)           -> edge list
+//   kHitSingle   in a pure interior cell whose only clipped shape is `shape` (from the table; c unknown)
+//   kHitCell     in cell c, nothing else known: its info is read here (or was read by the caller: have_info)
+enum HitKind { kHitNone = 0, kHitEdges = 1, kHitSingle = 2, kHitCell = 3 };
+
+// Interior-list entries of a single-shape interior cell carry the shape instead of the cell: cell = -(shape + 2).
+__device__ __forceinline__ int32_t encode_single_shape(int shape) { return -(shape + 2); }
+
 template <int kInteriorMode>
-__device__ __forceinline__ void route_located(const FlatIndexView& ix, const PhaseAOut& o, bool write_outputs, uint32_t i, int c,
-                                              WarpSlots& edge_slots, WarpSlots& interior_slots, unsigned lane, bool single_interior = false,
-                                              bool have_info = false, int loaded_info = 0) {
-  // single_interior: the lookup table already said that cell c is a pure interior cell with one clipped shape. "Any" and
-  // "count" then need nothing else; the other modes still read the cell's info for the shape id.
-  int info = 0;
-  if (c >= 0) info = ((kInteriorMode == 1 || kInteriorMode == 2) && single_interior) ? -1 : (have_info ? loaded_info : ix.interior_info[c]);
+__device__ __forceinline__ void route_located(const FlatIndexView& ix, const PhaseAOut& o, bool write_outputs, uint32_t i, int hit_kind, int c, int shape,
+                                              WarpSlots& edge_slots, WarpSlots& interior_slots, unsigned lane, bool have_info = false, int loaded_info = 0) {
   uint8_t flag = 0;
   uint32_t cnt = 0;
-  const bool to_edges = c >= 0 && info == 0;
-  bool to_interior = false;
-  if (c >= 0 && info != 0) {
-    const int single_shape = info < 0 ? -info - 1 : -1;
+  bool to_edges = hit_kind == kHitEdges, to_interior = false;
+  int32_t interior_entry = c;
+  if (hit_kind == kHitCell) {
+    const int info = have_info ? loaded_info : ix.interior_info[c];
+    if (info == 0) to_edges = true;
+    else if (info < 0) { hit_kind = kHitSingle; shape = -info - 1; }
+    else {                                               // pure interior cell with `info` clipped shapes
+      if (kInteriorMode == 1) flag = 1;
+      else if (kInteriorMode == 2) cnt = (uint32_t)info;
+      else to_interior = true;
+    }
+  }
+  if (hit_kind == kHitSingle) {
     if (kInteriorMode == 1) flag = 1;
-    else if (kInteriorMode == 2) cnt = info < 0 ? 1u : (uint32_t)info;
-    else if (kInteriorMode == 3 && single_shape >= 0) atomicAdd(o.hist + single_shape, 1ull);
-    else if (kInteriorMode == 4 && single_shape >= 0) flag = single_shape == o.target_shape;
-    else to_interior = true;
+    else if (kInteriorMode == 2) cnt = 1u;
+    else if (kInteriorMode == 3) atomicAdd(o.hist + shape, 1ull);
+    else if (kInteriorMode == 4) flag = shape == o.target_shape;
+    else { to_interior = true; interior_entry = encode_single_shape(shape); }
   }
   // which per-point output exists is a property of the mode (flags: any / one shape; counts: count), known at compile time
   if (write_outputs) {
@@ -139,7 +152,7 @@ __device__ __forceinline__ void route_located(const FlatIndexView& ix, const Pha
   }
   if (to_edges && o.cell_counts) atomicAdd(o.cell_counts + c, 1u);
   edge_slots.append(to_edges, HitWork{i, c}, o.work, o.capacity, o.counters, +1, lane);
-  if (kInteriorMode != 1 && kInteriorMode != 2) interior_slots.append(to_interior, HitWork{i, c}, o.work, o.capacity, o.counters + 1, -1, lane);
+  if (kInteriorMode != 1 && kInteriorMode != 2) interior_slots.append(to_interior, HitWork{i, interior_entry}, o.work, o.capacity, o.counters + 1, -1, lane);
 }
 
 // Phase A, exact: FP64 K1 + Locate, then route_located. The kernel is a chain of dependent gathers per point
@@ -231,19 +244,22 @@ locate_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint32_t n
 #pragma unroll
     for (int t = 0; t < kP; ++t) {
       const uint32_t kind = e0[t] & ~kLutIndexMask;
-      cell[t] = kind == kLutMixed ? (int)lo[t] : ((kind == kLutInside || kind == kLutInterior) ? (int)(e0[t] & kLutIndexMask) : -1);
+      cell[t] = kind == kLutMixed ? (int)lo[t] : (kind == kLutInside ? (int)(e0[t] & kLutCellMask) : -1);
       cand[t] = kind == kLutMixed ? ix.cell_ids[cell[t]] : 0;
-      info[t] = cell[t] >= 0 ? ix.interior_info[cell[t]] : 0;
+      info[t] = kind == kLutMixed ? ix.interior_info[cell[t]] : 0;
     }
-#pragma unroll
-    for (int t = 0; t < kP; ++t)
-      if ((e0[t] & ~kLutIndexMask) == kLutMixed && !(cellid_range_min(cand[t]) <= leaf[t] && leaf[t] <= cellid_range_max(cand[t]))) cell[t] = -1;
     // stage 7: outputs, work lists
 #pragma unroll
     for (int t = 0; t < kP; ++t) {
       const uint32_t i = idx[t];
       const bool valid = i != 0xFFFFFFFFu;
-      route_located<kInteriorMode>(ix, o, valid, i, valid ? cell[t] : -1, edge_slots, interior_slots, lane, false, true, info[t]);
+      const uint32_t kind = e0[t] & ~kLutIndexMask;
+      int hit = kHitNone;
+      if (kind == kLutMixed) hit = (cellid_range_min(cand[t]) <= leaf[t] && leaf[t] <= cellid_range_max(cand[t])) ? kHitCell : kHitNone;
+      else if (kind == kLutInside) hit = (e0[t] & kLutHasEdges) ? kHitEdges : kHitCell;
+      else if (kind == kLutInterior) hit = kHitSingle;
+      if (!valid) hit = kHitNone;
+      route_located<kInteriorMode>(ix, o, valid, i, hit, cell[t], (int)(e0[t] & kLutIndexMask), edge_slots, interior_slots, lane, kind == kLutMixed, info[t]);
     }
   }
   edge_slots.finish(o.work, o.capacity, +1, lane);
@@ -341,11 +357,11 @@ locate_fast_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint3
       // always give a valid bucket, so the read is unconditional (no branch around it).
       const uint32_t e0 = ix.lut[lut_bucket(lut_level, face, ufi & 0x3FFFFFFFu, ufj & 0x3FFFFFFFu)];
       const uint32_t kind = e0 & ~kLutIndexMask;
-      const bool inside = (kind == kLutInside) | (kind == kLutInterior);
-      const int c = (certain & inside) ? (int)(e0 & kLutIndexMask) : -1;
-      certain &= inside | (kind == kLutEmpty);
-      // undecided points are routed (and their outputs written) by the exact kernel
-      route_located<kInteriorMode>(ix, o, certain, i, c, edge_slots, interior_slots, lane, kind == kLutInterior);
+      certain &= kind != kLutMixed;
+      // everything a decided point needs is in the table entry: no second load unless its cell is a pure interior cell with
+      // several clipped shapes. Undecided points are routed (and their outputs written) by the exact kernel.
+      const int hit = !certain ? kHitNone : (kind == kLutInterior ? kHitSingle : (kind == kLutInside ? ((e0 & kLutHasEdges) ? kHitEdges : kHitCell) : kHitNone));
+      route_located<kInteriorMode>(ix, o, certain, i, hit, (int)(e0 & kLutCellMask), (int)(e0 & kLutIndexMask), edge_slots, interior_slots, lane);
       unc_slots.append(valid & !certain, i, uncertain, counters + 2, lane);
     }
     __syncthreads();                                            // everyone is done with this stage before it is refilled
@@ -415,7 +431,11 @@ process_kernel(const FlatIndexView ix, const double* __restrict__ xyz, const Hit
       const unsigned int w = wbase + lane;
       if (w >= count) continue;
       const HitWork hw = work[w];
-      if (hw.cell < 0) continue;   // unused slot of a reservation chunk
+      if (hw.cell == -1) continue;   // unused slot of a reservation chunk
+      if (hw.cell < -1) {            // a pure interior cell with the single shape -(cell + 2) (only the fill mode lists these)
+        if (kMode == kModeFill) out.shape_ids[out.offsets[hw.point]] = -(hw.cell + 2);
+        continue;
+      }
       process_hit<kMode>(ix, xyz, hw, model, out);
     }
   }

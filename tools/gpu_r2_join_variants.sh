@@ -1,6 +1,7 @@
 #!/bin/bash
 # Index-query timings for each experimental build in variants/ and the in-tree library; then the index GPU tests in-tree.
 mkdir -p gpurun_out
+shopt -s nullglob
 for lib in "" variants/*.so; do
   S2B_LIB_PATH=${lib:+$PWD/$lib} timeout 600 python tools/join_time.py 2>&1 | tail -1
 done | tee gpurun_out/join_variants.log

@@ -1,6 +1,7 @@
 #!/bin/bash
 # Kernel-only timing of the headline encode step for each experimental build in variants/ (and the in-tree library).
 mkdir -p gpurun_out
+shopt -s nullglob
 for lib in "" variants/*.so; do
   S2B_LIB_PATH=${lib:+$PWD/$lib} timeout 300 python - <<'PY'
 import os, ctypes, torch
