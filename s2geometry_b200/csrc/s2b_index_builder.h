@@ -79,8 +79,29 @@ struct FrameEdge {      // an edge expressed in one face's frame: value(t) = a +
   double t0, t1;        // parameter interval still alive
 };
 
-constexpr double kPad = 1e-14;       // uv padding (the reference pads by kCellPadding ~ 3.9e-15; larger is merely more conservative)
-constexpr double kSlack = 1e-13;     // slack on the linear inequalities (coordinates are O(1))
+// Why the three constants below make every cell's edge list a SUPERSET of the edges that meet the cell (what point
+// queries need: the segment from a cell's centre to a query point of that cell stays inside the cell's uv rectangle).
+// With eps = 2^-53 and all frame coordinates, bounds and their products bounded by 1 in magnitude:
+//  (1) Each constraint value f = pu - ulo*w (etc.) is computed with one product and one difference:
+//      |f_computed - f| <= eps*|ulo*w| + eps*|f_computed| <= 3 eps < 4e-16 =: delta. The constraint is linear along the
+//      chord, so the line through the computed end values lies within delta of the true one on all of [0,1].
+//  (2) kSlack = 1e-13 > 250 delta is added to both end values (rounding of that sum: <= 2 eps, absorbed). Wherever the
+//      TRUE f(t) >= 0, the slackened computed line is >= kSlack - delta - 2 eps > 9.9e-14 > 0. Its slope is at most
+//      |f1 - f0| <= 4, so every truly feasible t lies at least 9.9e-14 / 4 > 2.4e-14 inside the computed half-line.
+//  (3) The root tz = F0 / (F0 - F1) is one difference (F0 and F1 have opposite signs: no cancellation) and one
+//      division: relative error <= 3 eps, absolute <= 3.4e-16 since tz is in [0,1] — 70 times below the 2.4e-14 margin of (2). The extra
+//      1e-12 by which the live interval is widened is therefore not needed for correctness; it keeps the interval
+//      conservative when children re-clip an interval inherited from their parent.
+//  (4) kPad = 1e-14 widens the rectangle in uv before (1). It plays the part of the reference's kCellPadding
+//      (3.9e-15, mutable_s2shape_index.cc:183-185) and covers what (1)-(3) do not: a query point is assigned to its cell
+//      by the FLOATING-POINT chain XYZtoFaceUV -> UVtoST -> STtoIJ, whose uv error is a few eps (< 1e-15), so a point of
+//      the cell can lie that far outside the exact rectangle [st_to_uv(i/2^30), ...] the clipping uses.
+// tests/test_index_cpu.py::test_own_builder_edge_lists_are_supersets_of_the_exact_intersections checks the conclusion
+// in exact rational arithmetic on sampled cells (no truly intersecting edge is ever missing, lists <= 1.5x the exact ones).
+constexpr double kPad = 1e-14;       // uv padding, (4)
+constexpr double kSlack = 1e-13;     // slack on the linear inequalities, (2)
+constexpr double kRootSlack = 1e-12; // widening of the live parameter interval at a root, (3)
+static_assert(kSlack > 100 * 4e-16 && kRootSlack > 1e3 * 3.4e-16 && kPad > 2 * 3.9e-15, "see the derivation above");
 
 // Intersects [t0,t1] with { t : f0 + t*(f1 - f0) >= -slack }. Returns false if empty.
 inline bool clip_halfline(double f0, double f1, double* t0, double* t1) {
@@ -91,8 +112,8 @@ inline bool clip_halfline(double f0, double f1, double* t0, double* t1) {
     return false;
   }
   double tz = f0 / (f0 - f1);          // root in [0,1]
-  if (f0 < 0) { double lo = tz - 1e-12; if (lo > *t0) *t0 = lo; }
-  else        { double hi = tz + 1e-12; if (hi < *t1) *t1 = hi; }
+  if (f0 < 0) { double lo = tz - kRootSlack; if (lo > *t0) *t0 = lo; }
+  else        { double hi = tz + kRootSlack; if (hi < *t1) *t1 = hi; }
   return *t0 <= *t1;
 }
 

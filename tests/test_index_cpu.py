@@ -250,3 +250,111 @@ def test_degenerate_shapes(hostsim, ref):
     rflat = flat_of(ri)
     for m in (0, 1, 2):
         assert (hs_query(hostsim, rflat, pts, m, 2)[0] == ri.shape_histogram(pts, m, 1)).all(), m
+
+
+def _cell_face_ij(cell_id):
+    """(face, i_lo, j_lo, size in leaf cells) of one S2CellId (ToFaceIJOrientation, s2cell_id.cc:319-355)."""
+    from oracle import restatement as rs
+    cid = int(cell_id)
+    face = cid >> 61
+    bits = face & 1
+    i = j = 0
+    for k in range(7, -1, -1):
+        nbits = 2 if k == 7 else 4
+        bits += ((cid >> (k * 8 + 1)) & ((1 << (2 * nbits)) - 1)) << 2
+        bits = int(rs.LOOKUP_IJ[bits])
+        i += (bits >> 6) << (k * 4)
+        j += ((bits >> 2) & 15) << (k * 4)
+        bits &= 3
+    lsb = cid & -cid
+    size = 1 << ((lsb.bit_length() - 1) // 2)      # leaf cells per side
+    return face, i & -size, j & -size, size
+
+
+def _face_frame(face, p):
+    x, y, z = p[..., 0], p[..., 1], p[..., 2]
+    return [(y, z, x), (-x, z, y), (-x, -y, z), (-z, -y, -x), (-z, x, -y), (y, x, -z)][face]
+
+
+def _chord_meets_rect_exactly(a, b, face, rect):
+    """Exact rational decision: does the chord a + t (b - a), t in [0, 1], centrally projected on `face`, meet the closed
+    rectangle [ulo, uhi] x [vlo, vhi] (the cell's bound as the doubles every query sees)? The five conditions
+    w >= 0, pu - ulo w >= 0, uhi w - pu >= 0, pv - vlo w >= 0, vhi w - pv >= 0 are linear in t."""
+    from fractions import Fraction as F
+    au, av, aw = (F(float(c)) for c in _face_frame(face, a))
+    bu, bv, bw = (F(float(c)) for c in _face_frame(face, b))
+    ulo, uhi, vlo, vhi = (F(float(c)) for c in rect)
+    t0, t1 = F(0), F(1)
+    for f0, f1 in ((aw, bw), (au - ulo * aw, bu - ulo * bw), (uhi * aw - au, uhi * bw - bu), (av - vlo * aw, bv - vlo * bw),
+                   (vhi * aw - av, vhi * bw - bv)):
+        if f0 >= 0 and f1 >= 0:
+            continue
+        if f0 < 0 and f1 < 0:
+            return False
+        tz = f0 / (f0 - f1)
+        if f0 < 0:
+            t0 = max(t0, tz)
+        else:
+            t1 = min(t1, tz)
+        if t0 > t1:
+            return False
+    return True
+
+
+@pytest.mark.parametrize("scene", ["loop", "polygons_fine"])
+def test_own_builder_edge_lists_are_supersets_of_the_exact_intersections(scene):
+    """The builder's clipping (s2b_index_builder.h: linear inequalities with the slacks derived in its header comment) must
+    never drop an edge that meets a cell: for sampled cells, every edge whose chord meets the cell's rectangle in EXACT
+    rational arithmetic has to be in that cell's clipped list. (Point queries need exactly this: the segment from the cell
+    centre to a query point of the cell stays inside the rectangle, so every edge it can cross is in the list.)"""
+    from oracle import restatement as rs
+    from s2geometry_b200 import synth
+    if scene == "loop":
+        soup, _ = scenes.loop_scene(3000)
+        flat = own_flat(soup)
+    else:
+        soup = scenes.polygons_scene(120, 77, min_radius_km=50, max_radius_km=1500)
+        flat = own_flat(soup, 1)
+    # every edge of the scene, from the soup's chains (polygon chains are closed)
+    e0, e1 = [], []
+    cvb, scb = soup.chain_vertex_begin, soup.shape_chain_begin
+    for s in range(soup.num_shapes):
+        for c in range(scb[s], scb[s + 1]):
+            v = soup.vertices[cvb[c]:cvb[c + 1]]
+            if soup.shape_dim[s] == 2 and len(v):
+                e0.append(v); e1.append(np.roll(v, -1, 0))
+            elif soup.shape_dim[s] == 1 and len(v) > 1:
+                e0.append(v[:-1]); e1.append(v[1:])
+    e0 = np.concatenate(e0); e1 = np.concatenate(e1)
+    rng = np.random.default_rng(5)
+    clip_begin = flat.cell_clip_begin.astype(np.int64)
+    edge_begin = flat.clip_edge_begin.astype(np.int64)
+    checked = exact_hits = extra = 0
+    cell_edges = edge_begin[clip_begin[1:]] - edge_begin[clip_begin[:-1]]
+    sample = np.concatenate([rng.choice(np.flatnonzero(cell_edges > 0), 200, replace=False), rng.choice(flat.num_cells, 50, replace=False)])
+    for c in sample:
+        face, i, j, size = _cell_face_ij(flat.cell_ids[c])
+        rect = [float(rs.st_to_uv(np.float64((1.0 / 1073741824.0) * x))) for x in (i, i + size, j, j + size)]
+        rect = [rect[0], rect[1], rect[2], rect[3]]
+        lo, hi = edge_begin[clip_begin[c]], edge_begin[clip_begin[c + 1]]
+        have = {flat.edge_v0[k].tobytes() + flat.edge_v1[k].tobytes() for k in range(lo, hi)}
+        # float screening with a generous margin picks the candidates for the exact test
+        au, av, aw = _face_frame(face, e0); bu, bv, bw = _face_frame(face, e1)
+        t0 = np.zeros(len(e0)); t1 = np.ones(len(e0)); alive = np.ones(len(e0), bool)
+        with np.errstate(all="ignore"):
+            for f0, f1 in ((aw, bw), (au - rect[0] * aw, bu - rect[0] * bw), (rect[1] * aw - au, rect[1] * bw - bu),
+                           (av - rect[2] * aw, bv - rect[2] * bw), (rect[3] * aw - av, rect[3] * bw - bv)):
+                f0 = f0 + 1e-9; f1 = f1 + 1e-9
+                alive &= ~((f0 < 0) & (f1 < 0))
+                tz = f0 / (f0 - f1)
+                t0 = np.where((f0 < 0) & (f1 >= 0), np.maximum(t0, tz - 1e-9), t0)
+                t1 = np.where((f0 >= 0) & (f1 < 0), np.minimum(t1, tz + 1e-9), t1)
+            alive &= t0 <= t1
+        for k in np.flatnonzero(alive):
+            checked += 1
+            if _chord_meets_rect_exactly(e0[k], e1[k], face, rect):
+                exact_hits += 1
+                assert e0[k].tobytes() + e1[k].tobytes() in have, (int(c), int(k))
+        extra += len(have)
+    assert exact_hits > 200 and checked >= exact_hits
+    assert extra <= 1.5 * exact_hits + 50      # and the lists are not much larger than the exact ones
