@@ -34,10 +34,10 @@ N_POINTS = 100_000_000
 DEVICE_MAX_EDGES_PER_CELL = 1   # S2B_MAX_EDGES_PER_CELL_DEVICE (include/s2b_capi.h): granularity of device-resident indexes
 BYTES_PER_POINT = 16 + 8 * len(LEVELS) + 16 + 1   # algorithmic HBM bytes per point of the fused kernel
 # FP64-pipe instructions (DADD/DMUL/DFMA/DSETP) executed per point by encode_kernel<latlng>, measured with ncu's
-# per-instruction counts (profiles/r1_encode_latlng_final_ncu.json); used only for the informational fp64 roofline.
-FP64_INSTR_PER_POINT = 109
-DRAM_BYTES_PER_POINT = 54.14      # ncu dram__bytes_read.sum + dram__bytes_write.sum of the encode kernel, per point
-PROFILE_SOURCE = "profiles/r1_encode_latlng_final_ncu.json"
+# per-instruction counts (profiles/r2_encode_latlng_ncu.json, opcode mix in its "sass_per_point"); used only for the informational fp64 roofline.
+FP64_INSTR_PER_POINT = 73.7       # DFMA 31.1 + DMUL 24.2 + DADD 8.4 + DSETP 10.0 executed per point (SASS counters of the same ncu capture)
+DRAM_BYTES_PER_POINT = 56.44      # ncu dram__bytes_read.sum + dram__bytes_write.sum of the encode kernel, per point
+PROFILE_SOURCE = "profiles/r2_encode_latlng_ncu.json"
 METRIC = "points/sec (S2CellId encode, lat/lng -> levels 12/20/30 + ToToken)"
 WORKLOAD = "configs[1]: 100M lat/lng (radians, uniform on sphere) per GPU -> S2CellId at levels 12/20/30 + ToToken(level 30)"
 

@@ -217,7 +217,7 @@ def test_edge_and_cell_targets_match_reference(torch_cuda, ref):
             dup = (wd < 500) | (wd >= len(pts) - 500)
             distinct = np.array([len(set(row[:c])) == c for row, c in zip(wl, wc)]) & ~dup.any(axis=1) & (wl[:, 0] > 0)
             assert (gd[distinct] == wd[distinct]).all(), (kind, k, r)
-            assert distinct.mean() > 0.1
+            assert distinct.sum() >= 50, (kind, k, r, int(distinct.sum()))   # the comparison is not vacuous
             dd, dl, dc = q.find(kind, torch.from_numpy(sub.view(np.int64) if kind == TARGET_CELL else sub).cuda(), k)
             assert (dl.cpu().numpy() == wl).all() and (dc.cpu().numpy().astype(np.uint32) == wc).all()
     assert checked > 100_000
