@@ -261,8 +261,13 @@ int s2b_index_encode(const S2bFlatIndex* flat, const int32_t* edge_id, int max_e
  * EncodedS2PointVectors in either format (UNCOMPRESSED or CELL_IDS, encoded_s2point_vector.cc). Decoding yields the shape
  * soup s2b_index_build / s2b_index_decode take (arrays valid until s2b_shape_soup_destroy); vertices and edge order are
  * bit-identical to the reference's decoders. Unknown tags and malformed input fail with S2B_EINVAL.
- * s2b_shapes_encode writes the FAST (uncompressed) form, byte-identical to the reference; two-call capacity protocol
- * as s2b_index_encode. */
+ * s2b_shapes_encode writes the lax shapes as s2shapeutil::FastEncodeTaggedShapes does (CodingHint::FAST, uncompressed
+ * point vectors); s2b_shapes_encode_hint with S2B_CODING_COMPACT writes what CompactEncodeTaggedShapes writes
+ * (EncodeS2PointVectorCompact, encoded_s2point_vector.cc:323-594: the CELL_IDS block coding for vectors in which at
+ * least 5 % of the points are cell centres, the uncompressed form otherwise). Both are byte-identical to the reference's
+ * encoders; two-call capacity protocol as s2b_index_encode. */
+#define S2B_CODING_FAST 0
+#define S2B_CODING_COMPACT 1
 typedef struct S2bShapeSoup S2bShapeSoup;
 int s2b_shapes_decode(const void* bytes, size_t len, S2bShapeSoup** soup_out, size_t* consumed_out);
 int s2b_shape_soup_arrays(const S2bShapeSoup* soup, int* num_shapes, const int8_t** shape_dim, const uint32_t** shape_chain_begin,
@@ -270,6 +275,8 @@ int s2b_shape_soup_arrays(const S2bShapeSoup* soup, int* num_shapes, const int8_
 void s2b_shape_soup_destroy(S2bShapeSoup* soup);
 int s2b_shapes_encode(int num_shapes, const int8_t* shape_dim, const uint32_t* shape_chain_begin, const uint32_t* chain_vertex_begin,
                       const double* vertices, void* out, size_t capacity, size_t* size_out);
+int s2b_shapes_encode_hint(int coding_hint, int num_shapes, const int8_t* shape_dim, const uint32_t* shape_chain_begin,
+                           const uint32_t* chain_vertex_begin, const double* vertices, void* out, size_t capacity, size_t* size_out);
 
 typedef struct S2bIndex S2bIndex;
 

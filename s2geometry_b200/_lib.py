@@ -89,6 +89,7 @@ SIGNATURES = {
     "s2b_shape_soup_arrays": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "s2b_shape_soup_destroy": (None, [_vp]),
     "s2b_shapes_encode": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "s2b_shapes_encode_hint": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "s2b_index_decode": (_i, [_vp, _sz, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "s2b_index_encode": (_i, [_vp, _vp, _i, _vp, _sz, _vp]),
     "s2b_index_create": (_i, [_vp, _vp]),

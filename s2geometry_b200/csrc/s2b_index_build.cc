@@ -114,14 +114,15 @@ int s2b_shape_soup_arrays(const S2bShapeSoup* soup, int* num_shapes, const int8_
 
 void s2b_shape_soup_destroy(S2bShapeSoup* soup) { delete soup; }
 
-int s2b_shapes_encode(int num_shapes, const int8_t* shape_dim, const uint32_t* shape_chain_begin, const uint32_t* chain_vertex_begin,
-                      const double* vertices, void* out, size_t capacity, size_t* size_out) {
+int s2b_shapes_encode_hint(int coding_hint, int num_shapes, const int8_t* shape_dim, const uint32_t* shape_chain_begin,
+                           const uint32_t* chain_vertex_begin, const double* vertices, void* out, size_t capacity, size_t* size_out) {
+  if (coding_hint != S2B_CODING_FAST && coding_hint != S2B_CODING_COMPACT) return s2b::set_error(S2B_EINVAL, "coding_hint must be S2B_CODING_FAST or S2B_CODING_COMPACT");
   if (!size_out || num_shapes < 0 || (num_shapes && (!shape_dim || !shape_chain_begin || !chain_vertex_begin))) return s2b::set_error(S2B_EINVAL, "null argument");
   std::vector<uint8_t> bytes;
   std::string err;
   int rc;
   try {
-    rc = s2b::encode_tagged_shapes(num_shapes, shape_dim, shape_chain_begin, chain_vertex_begin, vertices, &bytes, &err);
+    rc = s2b::encode_tagged_shapes(num_shapes, shape_dim, shape_chain_begin, chain_vertex_begin, vertices, &bytes, &err, coding_hint == S2B_CODING_COMPACT);
   } catch (const std::bad_alloc&) {
     return s2b::set_error(S2B_ENOMEM, "host allocation failed while encoding shapes");
   }
@@ -130,6 +131,11 @@ int s2b_shapes_encode(int num_shapes, const int8_t* shape_dim, const uint32_t* s
   if (!out || capacity < bytes.size()) return s2b::set_error(S2B_ECAPACITY, "shape encode: %zu bytes needed", bytes.size());
   if (!bytes.empty()) std::memcpy(out, bytes.data(), bytes.size());
   return S2B_OK;
+}
+
+int s2b_shapes_encode(int num_shapes, const int8_t* shape_dim, const uint32_t* shape_chain_begin, const uint32_t* chain_vertex_begin,
+                      const double* vertices, void* out, size_t capacity, size_t* size_out) {
+  return s2b_shapes_encode_hint(S2B_CODING_FAST, num_shapes, shape_dim, shape_chain_begin, chain_vertex_begin, vertices, out, capacity, size_out);
 }
 
 }  // extern "C"

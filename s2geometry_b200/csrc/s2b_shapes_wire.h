@@ -10,8 +10,8 @@
 //   S2Polyline::Shape    (tag 2)  s2polyline.cc:425-475 (lossless, version 1), :527-560 (compressed, version 2)
 //   S2DecodePointsCompressed       s2point_compression.cc:330-391 (face runs, 2nd-order delta coded (pi, qi), off-centre points)
 // Decoding handles both point-vector formats (the CELL_IDS decoder is restated from the format description and the
-// reference decoder's arithmetic) and both encodings of S2Polygon / S2Polyline; encoding writes the lax shapes in their
-// UNCOMPRESSED ("FAST" hint) form, byte-identical to the reference. Of an S2Polygon only what the shape exposes is kept:
+// reference decoder's arithmetic) and both encodings of S2Polygon / S2Polyline; encoding writes the lax shapes with
+// either coding hint (FAST = UNCOMPRESSED point vectors, COMPACT = CELL_IDS), byte-identical to the reference. Of an S2Polygon only what the shape exposes is kept:
 // its loops as oriented vertex chains (the depth decides the orientation); bounds and origin_inside are skipped.
 #pragma once
 #include <cstdint>
@@ -133,6 +133,182 @@ inline bool decode_point_vector(Reader* r, std::vector<double>* out, std::string
     dst[3 * i] = p.x; dst[3 * i + 1] = p.y; dst[3 * i + 2] = p.z;
   }
   return true;
+}
+
+
+// ---- EncodeS2PointVectorCompact (encoded_s2point_vector.cc:323-594): the CELL_IDS writer -------------------------------
+// The format is restated from its description there (two header bytes, base, a string vector of 16-value blocks, each
+// block = header byte, offset, nibble-packed deltas, exceptions); the parameter choices (level, base, per-block delta /
+// offset / overlap sizes) have to be the reference's own for the bytes to be identical, so ChooseBestLevel (:597-632),
+// ConvertCellsToValues (:639-664), ChooseBase (:666-712), CanEncode (:716-731) and GetBlockCode (:736-830) are followed.
+
+inline uint64_t bit_mask(int n) { return n == 0 ? 0 : (~0ull >> (64 - n)); }
+inline int bit_width64(uint64_t v) { return v ? 64 - __builtin_clzll(v) : 0; }
+
+inline uint64_t interleave_bit_pairs(uint32_t val0, uint32_t val1) {   // encoded_s2point_vector.cc:53-66
+  uint64_t v0 = val0, v1 = val1;
+  v0 = (v0 | (v0 << 16)) & 0x0000ffff0000ffffull; v1 = (v1 | (v1 << 16)) & 0x0000ffff0000ffffull;
+  v0 = (v0 | (v0 << 8)) & 0x00ff00ff00ff00ffull;  v1 = (v1 | (v1 << 8)) & 0x00ff00ff00ff00ffull;
+  v0 = (v0 | (v0 << 4)) & 0x0f0f0f0f0f0f0f0full;  v1 = (v1 | (v1 << 4)) & 0x0f0f0f0f0f0f0f0full;
+  v0 = (v0 | (v0 << 2)) & 0x3333333333333333ull;  v1 = (v1 | (v1 << 2)) & 0x3333333333333333ull;
+  return v0 | (v1 << 2);
+}
+
+// S2::XYZtoFaceSiTi (s2coords.cc:43-66): the level at which p is exactly a cell centre, or -1.
+inline int xyz_to_face_si_ti(const P3& p, int* face, uint32_t* si, uint32_t* ti) {
+  double u, v;
+  *face = xyz_to_face_uv(p, &u, &v);
+  auto st_to_si_ti = [](double s) {   // s2coords.h:363-366 with MathUtil::Round<int64_t> (mathutil.h:71-79)
+    const double x = s * 2147483648.0;
+    return (uint32_t)(int64_t)(x < 0 ? x - 0.5 : x + 0.5);
+  };
+  *si = st_to_si_ti(uv_to_st(u));
+  *ti = st_to_si_ti(uv_to_st(v));
+  const int level = 30 - __builtin_ctz(*si | 0x80000000u);
+  if (level < 0 || level != 30 - __builtin_ctz(*ti | 0x80000000u)) return -1;
+  const P3 c = normalize(face_uv_to_xyz(*face, st_to_uv((1.0 / 2147483648.0) * *si), st_to_uv((1.0 / 2147483648.0) * *ti)));
+  return eq(p, c) ? level : -1;
+}
+
+struct BlockCode { int delta_bits, offset_bits, overlap_bits; };
+
+inline bool can_encode(uint64_t d_min, uint64_t d_max, int delta_bits, int overlap_bits, bool have_exceptions) {
+  d_min &= ~bit_mask(delta_bits - overlap_bits);
+  uint64_t max_delta = bit_mask(delta_bits);
+  if (have_exceptions) {
+    if (max_delta < 16) return false;
+    max_delta -= 16;
+  }
+  return (d_min > ~max_delta) || (d_min + max_delta >= d_max);
+}
+
+inline BlockCode block_code(const uint64_t* values, int count, uint64_t base, bool have_exceptions) {
+  uint64_t b_min = ~0ull, b_max = 0;
+  for (int k = 0; k < count; ++k)
+    if (values[k] != ~0ull) { b_min = std::min(b_min, values[k]); b_max = std::max(b_max, values[k]); }
+  if (b_min == ~0ull) return BlockCode{4, 0, 0};
+  b_min -= base; b_max -= base;
+  int delta_bits = (std::max(1, bit_width64(b_max - b_min) - 1) + 3) & ~3;
+  int overlap_bits = 0;
+  if (!can_encode(b_min, b_max, delta_bits, 0, have_exceptions)) {
+    if (can_encode(b_min, b_max, delta_bits, 4, have_exceptions)) {
+      overlap_bits = 4;
+    } else {
+      delta_bits += 4;
+      if (!can_encode(b_min, b_max, delta_bits, 0, have_exceptions)) overlap_bits = 4;
+    }
+  }
+  if (count == 1 && !have_exceptions) delta_bits = 8;
+  const uint64_t max_delta = bit_mask(delta_bits) - (have_exceptions ? 16 : 0);
+  int offset_bits = 0;
+  if (b_max > max_delta) {
+    const int offset_shift = delta_bits - overlap_bits;
+    const uint64_t mask = bit_mask(offset_shift);
+    const uint64_t min_offset = (b_max - max_delta + mask) & ~mask;
+    offset_bits = (bit_width64(min_offset) - offset_shift + 7) & ~7;
+    if (offset_bits == 64) overlap_bits = 4;
+  }
+  return BlockCode{delta_bits, offset_bits, overlap_bits};
+}
+
+inline void encode_point_vector_fast(const double* pts, uint64_t n, std::vector<uint8_t>* out) {   // :205-213
+  Writer w{out};
+  w.varint64(n << 3 | 0);
+  const uint8_t* src = (const uint8_t*)pts;
+  out->insert(out->end(), src, src + n * 24);
+}
+
+inline void encode_point_vector_compact(const double* pts, uint64_t n, std::vector<uint8_t>* out) {
+  // 1. the level at which most points are cell centres (or give up: fewer than 5 % are)
+  struct CellPoint { int8_t level, face; uint32_t si, ti; };
+  std::vector<CellPoint> cps((size_t)n);
+  int level_counts[31] = {0};
+  for (uint64_t k = 0; k < n; ++k) {
+    int face; uint32_t si, ti;
+    const int level = xyz_to_face_si_ti(P3{pts[3 * k], pts[3 * k + 1], pts[3 * k + 2]}, &face, &si, &ti);
+    cps[k] = CellPoint{(int8_t)level, (int8_t)face, si, ti};
+    if (level >= 0) ++level_counts[level];
+  }
+  int level = 0;
+  for (int l = 1; l <= 30; ++l) if (level_counts[l] > level_counts[level]) level = l;
+  if (level_counts[level] <= 0.05 * (double)n) return encode_point_vector_fast(pts, n, out);
+  // 2. the 64-bit values: (face, si, ti) at that level with bit pairs interleaved; others are exceptions
+  std::vector<uint64_t> values((size_t)n);
+  bool have_exceptions = false;
+  const int shift = 30 - level;
+  for (uint64_t k = 0; k < n; ++k) {
+    const CellPoint& cp = cps[k];
+    if (cp.level != level) { values[k] = ~0ull; have_exceptions = true; continue; }
+    const uint32_t sj = ((((uint32_t)cp.face & 3u) << 30) | (cp.si >> 1)) >> shift;
+    const uint32_t tj = ((((uint32_t)cp.face & 4u) << 29) | cp.ti) >> (shift + 1);
+    values[k] = interleave_bit_pairs(sj, tj);
+  }
+  // 3. base: the prefix shared by all values, at most 7 bytes of it
+  const int max_bits = 2 * level + 3;
+  auto base_shift_for = [&](int base_bits) { return std::max(0, max_bits - base_bits); };
+  uint64_t v_min = ~0ull, v_max = 0;
+  for (uint64_t v : values) if (v != ~0ull) { v_min = std::min(v_min, v); v_max = std::max(v_max, v); }
+  uint64_t base = 0;
+  int base_bits = 0;
+  if (v_min != ~0ull) {
+    const int min_delta_bits = (have_exceptions || n == 1) ? 8 : 4;
+    const int excluded_bits = std::max(bit_width64(v_min ^ v_max), std::max(min_delta_bits, base_shift_for(56)));
+    const uint64_t prefix = v_min & ~bit_mask(excluded_bits);
+    if (prefix != 0) base_bits = (max_bits - __builtin_ctzll(prefix) + 7) & ~7;
+    base = v_min & ~bit_mask(base_shift_for(base_bits));
+  }
+  const uint64_t num_blocks = (n + 15) >> 4;
+  const int base_bytes = base_bits >> 3;
+  const int last_block_count = (int)((int64_t)n - 16 * ((int64_t)num_blocks - 1));
+  Writer w{out};
+  w.put8(1u | ((uint32_t)have_exceptions << 3) | ((uint32_t)(last_block_count - 1) << 4));
+  w.put8((uint32_t)base_bytes | ((uint32_t)level << 3));
+  w.uint_with_length(base >> base_shift_for(base_bits), base_bytes);
+  // 4. the blocks
+  std::vector<uint8_t> blocks;
+  std::vector<uint64_t> ends;
+  Writer b{&blocks};
+  for (uint64_t i = 0; i < n; i += 16) {
+    const int block_size = (int)std::min<uint64_t>(16, n - i);
+    const BlockCode code = block_code(&values[i], block_size, base, have_exceptions);
+    const int offset_bytes = code.offset_bits >> 3, delta_nibbles = code.delta_bits >> 2, overlap_nibbles = code.overlap_bits >> 2;
+    b.put8((uint32_t)(offset_bytes - overlap_nibbles) | ((uint32_t)overlap_nibbles << 3) | ((uint32_t)(delta_nibbles - 1) << 4));
+    uint64_t offset = ~0ull;
+    int num_exceptions = 0;
+    for (int j = 0; j < block_size; ++j) {
+      if (values[i + j] == ~0ull) ++num_exceptions;
+      else offset = std::min(offset, values[i + j] - base);
+    }
+    if (num_exceptions == block_size) offset = 0;
+    const int offset_shift = code.delta_bits - code.overlap_bits;
+    offset &= ~bit_mask(offset_shift);
+    if (offset > 0) b.uint_with_length(offset >> offset_shift, offset_bytes);
+    const int delta_bytes = (delta_nibbles + 1) >> 1;
+    int exceptions = 0;
+    for (int j = 0; j < block_size; ++j) {
+      uint64_t delta;
+      if (values[i + j] == ~0ull) {
+        delta = (uint64_t)exceptions++;
+      } else {
+        delta = values[i + j] - (offset + base);
+        if (have_exceptions) delta += 16;
+      }
+      if ((delta_nibbles & 1) && (j & 1)) {   // odd nibble count: share a byte with the previous delta's high nibble
+        const uint8_t last = blocks.back();
+        blocks.pop_back();
+        delta = (delta << 4) | (last & 0xf);
+      }
+      b.uint_with_length(delta, delta_bytes);
+    }
+    for (int j = 0; j < block_size; ++j)
+      if (values[i + j] == ~0ull) {
+        const uint8_t* src = (const uint8_t*)(pts + 3 * (i + j));
+        blocks.insert(blocks.end(), src, src + 24);
+      }
+    ends.push_back(blocks.size());
+  }
+  w.uint_vector(ends);          // StringVectorEncoder::Encode: offsets (EncodeUintVector<uint64_t>), then the data
+  out->insert(out->end(), blocks.begin(), blocks.end());
 }
 
 }  // namespace wire
@@ -377,20 +553,19 @@ inline int decode_tagged_shapes(const uint8_t* bytes, size_t len, ShapeSoupData*
   return S2B_OK;
 }
 
-// Encodes a shape soup as s2shapeutil::FastEncodeTaggedShapes would encode the corresponding S2PointVectorShape /
-// S2LaxPolylineShape / S2LaxPolygonShape objects (CodingHint::FAST: uncompressed point vectors).
+// Encodes a shape soup as s2shapeutil::FastEncodeTaggedShapes (compact = false: uncompressed point vectors) or
+// s2shapeutil::CompactEncodeTaggedShapes (compact = true: CELL_IDS point vectors where at least 5 % of a vector's points
+// are cell centres) would encode the corresponding S2PointVectorShape / S2LaxPolylineShape / S2LaxPolygonShape objects.
 inline int encode_tagged_shapes(int num_shapes, const int8_t* shape_dim, const uint32_t* shape_chain_begin, const uint32_t* chain_vertex_begin,
-                                const double* vertices, std::vector<uint8_t>* bytes, std::string* err) {
+                                const double* vertices, std::vector<uint8_t>* bytes, std::string* err, bool compact = false) {
   using namespace wire;
   auto fail = [&](const std::string& m) { *err = "shape encode: " + m; return S2B_EINVAL; };
   std::vector<uint8_t> records;
   std::vector<uint64_t> ends((size_t)num_shapes);
   Writer w{&records};
-  auto point_vector = [&](uint32_t vbegin, uint32_t vend) {   // EncodeS2PointVectorFast
-    const uint64_t n = vend - vbegin;
-    w.varint64(n << 3 | 0);
-    const uint8_t* src = (const uint8_t*)(vertices + 3 * (size_t)vbegin);
-    records.insert(records.end(), src, src + n * 24);
+  auto point_vector = [&](uint32_t vbegin, uint32_t vend) {   // EncodeS2PointVector(points, hint)
+    if (compact) encode_point_vector_compact(vertices + 3 * (size_t)vbegin, vend - vbegin, &records);
+    else encode_point_vector_fast(vertices + 3 * (size_t)vbegin, vend - vbegin, &records);
   };
   for (int s = 0; s < num_shapes; ++s) {
     const uint32_t cb = shape_chain_begin[s], ce = shape_chain_begin[s + 1];

@@ -102,19 +102,20 @@ def decode_shapes(data):
         lib.s2b_shape_soup_destroy(h)
 
 
-def encode_shapes(soup):
-    """Serializes a soup as s2shapeutil::FastEncodeTaggedShapes would serialize the corresponding lax shapes."""
+def encode_shapes(soup, compact=False):
+    """Serializes a soup as s2shapeutil::FastEncodeTaggedShapes (or, with compact=True, CompactEncodeTaggedShapes) would
+    serialize the corresponding lax shapes."""
     import ctypes
     from . import _lib
     lib = _lib.load()
     soup = soup.freeze()
     v = np.ascontiguousarray(soup.vertices, np.float64)
-    args = (int(soup.num_shapes), soup.shape_dim.ctypes.data, soup.shape_chain_begin.ctypes.data, soup.chain_vertex_begin.ctypes.data,
+    args = (1 if compact else 0, int(soup.num_shapes), soup.shape_dim.ctypes.data, soup.shape_chain_begin.ctypes.data, soup.chain_vertex_begin.ctypes.data,
             v.ctypes.data if v.size else None)
     size = ctypes.c_size_t(0)
-    rc = lib.s2b_shapes_encode(*args, None, 0, ctypes.byref(size))
+    rc = lib.s2b_shapes_encode_hint(*args, None, 0, ctypes.byref(size))
     if rc != _lib.S2B_ECAPACITY:
         _lib.check(rc)
     out = np.zeros(max(int(size.value), 1), np.uint8)
-    _lib.check(lib.s2b_shapes_encode(*args, out.ctypes.data, int(out.size), ctypes.byref(size)))
+    _lib.check(lib.s2b_shapes_encode_hint(*args, out.ctypes.data, int(out.size), ctypes.byref(size)))
     return out[: int(size.value)].tobytes()

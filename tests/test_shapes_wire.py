@@ -77,6 +77,7 @@ def test_decode_and_encode_match_reference(ref):
                 assert (got.shape_chain_begin == soup.shape_chain_begin).all() and (got.chain_vertex_begin == soup.chain_vertex_begin).all()
         if single_chain_polylines(soup):
             assert encode_shapes(soup) == ref.tagged_shapes_encode(soup, False), name           # byte-identical FAST encoding
+            assert encode_shapes(soup, compact=True) == ref.tagged_shapes_encode(soup, True), name   # ... and COMPACT encoding
     # the compact form really exercised the CELL_IDS format: much smaller than 24 bytes per vertex
     soup = [s for n, s in wire_soups(ref) if n == "snapped18"][0]
     assert len(ref.tagged_shapes_encode(soup, True)) < 0.4 * len(ref.tagged_shapes_encode(soup, False))
@@ -187,3 +188,66 @@ def test_golden_shapes_fixture():
         assert (ge.view(np.uint64) == z[key + "__edges"].reshape(-1, 6).view(np.uint64)).all()
         if key.endswith("_fast") and not key.startswith("classic"):
             assert encode_shapes(got) == data
+
+
+def test_compact_point_vector_encoder_is_byte_identical_on_adversarial_vectors(ref):
+    """EncodeS2PointVectorCompact's parameter choices (level, base, per-block delta / offset / overlap widths, exceptions)
+    on point vectors built to reach its corners: single points, one block / many blocks / a last block of one value,
+    blocks made only of exceptions, values spread over several faces (wide deltas, long offsets), tight clusters (short
+    deltas, long base), mixed levels (the majority level wins, the rest become exceptions), and too few cell centres
+    (falls back to the uncompressed form). Every vector must come out byte for byte as the reference writes it."""
+    rng = np.random.default_rng(2024)
+    vectors = []
+    for level in (0, 1, 2, 5, 11, 15, 23, 29, 30):
+        for n in (1, 2, 15, 16, 17, 31, 33, 100):
+            for spread in (3.0, 0.3, 1e-2, 1e-5, 1e-8):
+                c = synth.sphere_points(1, int(rng.integers(1 << 30)))[0]
+                raw = c + spread * rng.standard_normal((n, 3))
+                raw /= np.linalg.norm(raw, axis=1)[:, None]
+                pts = snap(ref, raw, level)
+                kind = int(rng.integers(5))
+                if kind == 1 and n > 2:                       # a few exceptions
+                    k = rng.choice(n, max(1, n // 7), replace=False)
+                    pts[k] = synth.sphere_points(len(k), int(rng.integers(1 << 30)))
+                elif kind == 2 and n >= 32:                   # one block of exceptions only
+                    pts[16:32] = synth.sphere_points(16, int(rng.integers(1 << 30)))
+                elif kind == 3 and n > 4:                     # a minority at another level
+                    k = rng.choice(n, n // 3, replace=False)
+                    pts[k] = snap(ref, raw[k], max(0, level - 3))
+                elif kind == 4 and n >= 40:                   # hardly any cell centres: < 5 % -> uncompressed
+                    pts[2:] = synth.sphere_points(n - 2, int(rng.integers(1 << 30)))
+                vectors.append(pts)
+    # block minima / maxima placed around the nibble and byte boundaries GetBlockCode's comment works through
+    from oracle import restatement as rs
+
+    def deinterleave(v):          # inverse of InterleaveUint32BitPairs: bit pairs alternate between sj and tj
+        sj = tj = 0
+        for k in range(16):
+            sj |= ((v >> (4 * k)) & 3) << (2 * k)
+            tj |= ((v >> (4 * k + 2)) & 3) << (2 * k)
+        return sj, tj
+
+    level = 24
+    for lo, hi in ((0x72, 0x7e), (0x78, 0x84), (0x08, 0x104), (0xf08, 0x1004), (0, 0xffff), (0xfff0, 0x1000f), (0x3, 0x3)):
+        for base in (0, 0x5a5a5a5a5a5 << 8):
+            vals = np.unique(np.linspace(lo, hi, 16).astype(np.int64)) + base
+            st = np.array([deinterleave(int(v)) for v in vals], np.int64)      # face 0: sj = i, tj = j at `level`
+            leaf = rs.from_face_ij(np.zeros(len(vals), np.int64), st[:, 0] << (30 - level), st[:, 1] << (30 - level))
+            vectors.append(ref.to_point(ref.parent(leaf, level)))
+    checked = compressed = 0
+    for pts in vectors:
+        s = ShapeSoup(); s.add_points(pts); s = s.freeze()
+        want = ref.tagged_shapes_encode(s, True)
+        got = encode_shapes(s, compact=True)
+        assert got == want, (len(pts), checked)
+        compressed += len(want) < 20 * len(pts)
+        checked += 1
+    assert checked >= 370 and compressed > 250
+    # polylines and polygons take the same path
+    for level in (30, 12):
+        s = ShapeSoup()
+        for loops in synth.many_polygons(20, 5 + level, min_vertices=3, max_vertices=90, min_radius_km=0.01, max_radius_km=3000.0):
+            s.add_polygon([snap(ref, l, level) for l in loops])
+        s.add_polyline(snap(ref, synth.cap_points(np.array([0.0, 0.6, 0.8]), 1e-4, 77, 3), level))
+        s = s.freeze()
+        assert encode_shapes(s, compact=True) == ref.tagged_shapes_encode(s, True)
