@@ -616,6 +616,82 @@ def join_section(args, torch, dev, rank, world):
     return out, cu
 
 
+def capi_multi_section(args, torch, rank, world, expected_checksum):
+    """north_star (4) behind the C ABI: ONE process (rank 0) drives all `world` GPUs of the box through
+    s2b_index_replicate + s2b_shape_histogram_multi_dev — shard k of the SAME global stream as join_section resident on
+    GPU k, the library's own streams, and its all-reduce of the uint64[10000] histogram inside the call (NCCL bound at
+    run time, then the library's peer-memory reduction kernel). The other ranks have released their GPU memory and wait
+    on the rendezvous store (a host-side wait: no kernel of theirs is resident meanwhile). Timed with the host clock
+    around `steps` synchronous calls (the streams are the library's own), so launch latency is included."""
+    import ctypes
+    import torch.distributed as dist
+    from s2geometry_b200 import _lib, dist as sdist, synth
+    from s2geometry_b200.index import ShapeIndex, build_flat_index
+    from s2geometry_b200.shapes import ShapeSoup
+    torch.cuda.synchronize(); torch.cuda.empty_cache()
+    dist.barrier(); torch.cuda.synchronize()
+    store = dist.distributed_c10d._get_default_store()
+    out = None
+    if rank != 0:
+        store.wait(["s2b_capi_multi_done"])
+        return None
+    try:
+        lib = _lib.load()
+        soup = ShapeSoup()
+        for loops in synth.many_polygons(10000, 4):
+            soup.add_polygon(loops)
+        ix = ShapeIndex(build_flat_index(soup.freeze(), DEVICE_MAX_EDGES_PER_CELL))
+        S = 10000
+        devs = (ctypes.c_int * world)(*range(world))
+        t0 = time.perf_counter()
+        _lib.check(lib.s2b_index_replicate(ix._h, devs, world))
+        replicate_s = time.perf_counter() - t0
+        order = (ctypes.c_int * world)()
+        _lib.check(lib.s2b_index_replica_devices(ix._h, order, world))
+        assert lib.s2b_index_num_replicas(ix._h) == world
+        n_total = args.join_points
+        pts, outs, ns = [], [], []
+        for k in range(world):
+            lo, hi = sdist.shard_range(n_total, k, world)
+            d = torch.device("cuda", order[k])
+            pts.append(synth.stream_sphere_points_cuda(1000, lo, hi - lo, d))
+            outs.append(torch.zeros(S, dtype=torch.int64, device=d))
+            ns.append(hi - lo)
+            torch.cuda.synchronize(d)
+        xyz_p = (ctypes.c_void_p * world)(*[p_.data_ptr() for p_ in pts])
+        out_p = (ctypes.c_void_p * world)(*[o_.data_ptr() for o_ in outs])
+        n_p = (ctypes.c_size_t * world)(*ns)
+        out = {"workload": "configs[3] through the C ABI from one process: %d points (stream 1000) over %d GPUs, s2b_index_replicate + s2b_shape_histogram_multi_dev" % (n_total, world),
+               "index_replicate_s": replicate_s, "timing": "host clock around %d synchronous calls" % args.steps}
+        for mode, name in ((0, "nccl"), (1, "peer_kernel")):
+            prev = lib.s2b_index_set_reduce_mode(ix._h, mode)
+            if prev < 0:
+                out[name] = {"unavailable": lib.s2b_last_error().decode("utf-8", "replace")}
+                continue
+
+            def step():
+                _lib.check(lib.s2b_shape_histogram_multi_dev(ix._h, xyz_p, n_p, 1, out_p, 1))
+            for _ in range(3):
+                step()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                step()
+            ms = (time.perf_counter() - t0) / args.steps * 1e3
+            hists = [o_.cpu().numpy().astype(np.uint64) for o_ in outs]
+            hist = hists[0]
+            checksum = "%016x" % int((hist * (np.arange(len(hist), dtype=np.uint64) * np.uint64(2654435761) + np.uint64(1))).sum() & np.uint64(0xFFFFFFFFFFFFFFFF))
+            out[name] = {"points_per_s": n_total / (ms * 1e-3), "ms_per_step": ms, "total_hits": int(hist.sum()), "histogram_checksum": checksum,
+                         "same_on_every_gpu": all(bool((h == hist).all()) for h in hists),
+                         "equals_torch_distributed_driver": checksum == expected_checksum}
+        del pts, outs
+        ix.close()
+    except Exception as e:
+        out = {"error": repr(e)}
+    finally:
+        store.set("s2b_capi_multi_done", "1")
+    return out
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -793,6 +869,9 @@ def run_gpu(args):
             torch.cuda.empty_cache()
         except Exception as e:
             region_cells = {"error": repr(e)}
+    capi_multi = None
+    if world > 1 and not args.no_join:
+        capi_multi = capi_multi_section(args, torch, rank, world, (join or {}).get("histogram_checksum"))
     if rank == 0:
         hbm_peak, peak_src = peaks()
         kern_ms = float(np.mean(per_launch_ms))
@@ -834,6 +913,10 @@ def run_gpu(args):
             "cellunion_hits": brief(cellunion, "hits"), "cellunion_parity": brief(cellunion, "parity_vs_reference"),
             "cell_index_join_Gpts": gpts(brief(cell_index_join, "points_per_s")), "cell_index_join_hbm_frac": frac(brief(cell_index_join, "roofline", "frac")),
         }
+        if capi_multi is not None:
+            summary["capi_multi_join_nccl_Gpts"] = gpts(brief(capi_multi, "nccl", "points_per_s"))
+            summary["capi_multi_join_peer_Gpts"] = gpts(brief(capi_multi, "peer_kernel", "points_per_s"))
+            summary["capi_multi_join_equals_join"] = brief(capi_multi, "nccl", "equals_torch_distributed_driver")
         line = {
             "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -858,7 +941,7 @@ def run_gpu(args):
         if headline_cpu is not None:
             line["cpu_baseline"] = headline_cpu
         for name, sec in (("encode_xyz", enc_xyz), ("pip", pip), ("join", join), ("cellunion", cellunion), ("radius_join", radius_join),
-                          ("cell_index_join", cell_index_join), ("region_cells", region_cells)):
+                          ("cell_index_join", cell_index_join), ("region_cells", region_cells), ("capi_multi_join", capi_multi)):
             if sec is not None:
                 line[name] = sec
         _emit(line)

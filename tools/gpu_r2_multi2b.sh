@@ -1,9 +1,6 @@
 #!/bin/bash
-# 2-GPU checks: the C ABI multi-GPU driver (C++ test: NCCL and peer-memory reductions) and bench.py under torchrun at N=2.
+# bench.py under torchrun at N=2 (incl. the single-process C-ABI multi-GPU join section).
 mkdir -p gpurun_out
-nvidia-smi topo -m > gpurun_out/topo.txt 2>&1
-timeout 600 python -m pytest tests/test_cpp_api.py -q -m gpu -s > gpurun_out/pytest_multi.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_multi.log
-tail -6 gpurun_out/pytest_multi.log
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_2gpu.json 2> gpurun_out/bench_2gpu.err; echo "bench2 exit $?"
 tail -3 gpurun_out/bench_2gpu.err
 python - <<'PY'
