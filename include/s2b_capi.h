@@ -479,6 +479,17 @@ int s2b_closest_points_to_targets(const S2bPointIndex* index, int target_kind, c
 int s2b_closest_points_to_targets_dev(const S2bPointIndex* index, int target_kind, const void* targets_dev, size_t n, int max_results,
                                       double max_length2, double max_error_radians, int32_t* data_out_dev, double* length2_out_dev,
                                       uint32_t* count_out_dev, void* stream);
+/* FindClosestPoints(ShapeIndexTarget(index)) (s2closest_point_query.h:132-165; S2MinDistanceShapeIndexTarget,
+ * s2min_distance_targets.cc): ONE target — a whole shape index resident on the same device as the point index. The distance
+ * of an index point p is what S2ClosestEdgeQuery(index).FindClosestEdge(PointTarget(p)) returns: 0 if include_interiors
+ * != 0 and a polygon of the index contains p (SEMI_OPEN), else the minimum of S2::UpdateMinDistance(p, v0, v1) over the
+ * index's edges, bit for bit. Results: the index points with distance < max_length2 (INFINITY = no limit), nearest first
+ * (ties: smaller data first), at most max_results of them (0 = no limit). *total_out = the number of results; the first
+ * min(total, capacity) are written to data_out / length2_out (nullable) and S2B_ECAPACITY is returned if total > capacity.
+ * max_error_radians is accepted as in the calls above (the results are exact). */
+int s2b_closest_points_to_shape_index(const S2bPointIndex* index, const S2bIndex* target, int include_interiors, int max_results,
+                                      double max_length2, double max_error_radians, int32_t* data_out, double* length2_out,
+                                      size_t capacity, size_t* total_out);
 
 /* --------------------------------------------------------------------------------------------------
  * S2CellIndex joins, batch form (s2cell_index.h:113-441, s2cell_index.cc:71-163) and the S2RegionSharder built on it

@@ -764,6 +764,24 @@ void ref_closest_points_target(void* h, int kind, const void* targets, size_t n,
     }
   });
 }
+// FindClosestPoints(ShapeIndexTarget(&shape index)) with include_interiors, max_results = k (0: unlimited), max_distance
+// (negative = none), max_error. Returns the number of results; the first `capacity` are written, nearest first.
+size_t ref_closest_points_shape_index(void* h, void* index_h, int include_interiors, int k, double max_distance_rad, double max_error_rad,
+                                      int32_t* data, double* length2, size_t capacity) {
+  auto* index = &((RefPointIndex*)h)->index;
+  S2ClosestPointQuery<int> query(index);
+  if (k > 0) query.mutable_options()->set_max_results(k);
+  if (max_distance_rad >= 0) query.mutable_options()->set_max_distance(S1Angle::Radians(max_distance_rad));
+  if (max_error_rad > 0) query.mutable_options()->set_max_error(S1Angle::Radians(max_error_rad));
+  S2ClosestPointQuery<int>::ShapeIndexTarget target(&((RefIndex*)index_h)->index);
+  target.set_include_interiors(include_interiors != 0);
+  const auto r = query.FindClosestPoints(&target);
+  for (size_t j = 0; j < r.size() && j < capacity; ++j) {
+    data[j] = r[j].data();
+    length2[j] = r[j].distance().length2();
+  }
+  return r.size();
+}
 double ref_chord_length2(double angle_rad) { return S1ChordAngle(S1Angle::Radians(angle_rad)).length2(); }
 
 // S2CellUnion::Contains(S2CellId) (bit0) and ::Intersects(S2CellId) (bit1).

@@ -303,6 +303,22 @@ def _closest_targets(self, kind, targets, k, max_distance_rad=-1.0, max_error_ra
 RefPointIndex.closest_targets = _closest_targets
 
 
+def _closest_shape_index(self, ref_index, k=0, max_distance_rad=-1.0, include_interiors=True, max_error_rad=0.0):
+    """FindClosestPoints(ShapeIndexTarget(ref_index.index)) -> (data, length2), nearest first; k == 0: unlimited."""
+    self.lib.ref_closest_points_shape_index.restype = _sz
+    cap = k if k else 1 << 16
+    while True:
+        data = np.zeros(cap, np.int32); l2 = np.zeros(cap, np.float64)
+        n = self.lib.ref_closest_points_shape_index(_vp(self.h), _vp(ref_index.h), 1 if include_interiors else 0, int(k), ctypes.c_double(max_distance_rad),
+                                                    ctypes.c_double(max_error_rad), _p(data), _p(l2), _sz(cap))
+        if n <= cap:
+            return data[:n].copy(), l2[:n].copy()
+        cap = int(n)
+
+
+RefPointIndex.closest_shape_index = _closest_shape_index
+
+
 class RefIndex:
     """A MutableS2ShapeIndex built by the reference from a shape soup (see s2geometry_b200.shapes.ShapeSoup)."""
 

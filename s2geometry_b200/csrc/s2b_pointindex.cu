@@ -19,6 +19,7 @@
 #include "s2b_hilbert.h"
 #include "s2b_internal.h"
 #include "s2b_region.cuh"   // RobustCrossProd (edge targets), S2Cell(S2CellId) bounds (cell targets)
+#include "s2b_index_handle.h"   // S2bIndex: the target of a ShapeIndexTarget query
 
 struct S2bPointIndex {
   int device = 0;
@@ -394,7 +395,8 @@ template <int kKind>
 __global__ void __launch_bounds__(kThreads)
 closest_targets_kernel(const IndexView ix, const void* __restrict__ targets, size_t n, int k, int start_level, double limit2, double limit_angle,
                        const double* __restrict__ covered_angle /* [31]: entry L+1 = angle of the cap covered at level L */,
-                       int32_t* __restrict__ data_out, double* __restrict__ length2_out, uint32_t* __restrict__ count_out) {
+                       int32_t* __restrict__ data_out, double* __restrict__ length2_out, uint32_t* __restrict__ count_out,
+                       unsigned long long* __restrict__ min_bits /* nullable, k == 0: min_bits[c] = min(min_bits[c], bits of the distance) */) {
   __shared__ uint16_t s_pos[1024], s_ij[1024];
   __shared__ double s_cov[31];
   for (int q = threadIdx.x; q < 1024; q += kThreads) { s_pos[q] = g_hilbert_pi.pos[q]; s_ij[q] = g_hilbert_pi.ij[q]; }
@@ -428,6 +430,7 @@ closest_targets_kernel(const IndexView ix, const void* __restrict__ targets, siz
           // with a full result set the reference's limit is the k-th distance; ties are then resolved on the data value below
           if (!target_distance<kKind>(g, P3{pp[0], pp[1], pp[2]}, limit2, &d)) continue;
           ++total;
+          if (min_bits) atomicMin(min_bits + c, (unsigned long long)__double_as_longlong(d));   // d >= 0: bit order = numeric order
           if (k == 0) continue;
           const int32_t dv = ix.data[c];
           if (cnt == k && !(d < dist[k - 1] || (d == dist[k - 1] && dv < data[k - 1]))) continue;
@@ -457,6 +460,22 @@ closest_targets_kernel(const IndexView ix, const void* __restrict__ targets, siz
       if (length2_out) length2_out[t * (size_t)k + r] = r < cnt ? dist[r] : HUGE_VAL;
     }
   }
+}
+
+// ShapeIndexTarget helpers: per-index-point distance slots.
+constexpr unsigned long long kInfBits = 0x7FF0000000000000ull;
+__global__ void fill_u64_kernel(unsigned long long* v, size_t n, unsigned long long value) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = value;
+}
+__global__ void zero_where_flag_kernel(unsigned long long* v, const uint8_t* __restrict__ flags, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && flags[i]) v[i] = 0ull;
+}
+// keys sorted ascending: *total = number of keys below `limit`
+__global__ void count_below_sorted_kernel(const unsigned long long* __restrict__ keys, size_t n, unsigned long long limit, unsigned long long* total) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && keys[i] < limit && (i + 1 == n || keys[i + 1] >= limit)) *total = i + 1;
 }
 
 // kMinWidth (quadratic projection, s2metrics.cc:54-58) and Metric::GetLevelForMinValue (s2metrics.h:185-200).
@@ -720,6 +739,12 @@ int s2b_closest_points_dev(const S2bPointIndex* ix, const double* targets_dev, s
   return e == cudaSuccess ? S2B_OK : cuda_fail(e, "closest_points launch");
 }
 
+// Launches closest_targets_kernel; min_bits != nullptr (with max_results == 0) makes it record, per index point, the
+// smallest distance to any of the targets instead of per-target results.
+static int launch_closest_targets(const S2bPointIndex* ix, int target_kind, const void* targets_dev, size_t n, int max_results, double max_length2,
+                                  int32_t* data_out_dev, double* length2_out_dev, uint32_t* count_out_dev, unsigned long long* min_bits,
+                                  cudaStream_t st);
+
 int s2b_closest_points_to_targets_dev(const S2bPointIndex* ix, int target_kind, const void* targets_dev, size_t n, int max_results,
                                       double max_length2, double max_error_radians, int32_t* data_out_dev, double* length2_out_dev,
                                       uint32_t* count_out_dev, void* stream) {
@@ -730,9 +755,15 @@ int s2b_closest_points_to_targets_dev(const S2bPointIndex* ix, int target_kind, 
   if (std::isnan(max_length2) || !(max_error_radians >= 0)) return set_error(S2B_EINVAL, "bad max_length2 / max_error");
   if (n == 0) return S2B_OK;
   if (!targets_dev || (max_results > 0 && !data_out_dev) || (max_results == 0 && !count_out_dev)) return set_error(S2B_EINVAL, "null pointer");
+  return launch_closest_targets(ix, target_kind, targets_dev, n, max_results, max_length2, data_out_dev, length2_out_dev, count_out_dev, nullptr,
+                                (cudaStream_t)stream);
+}
+
+static int launch_closest_targets(const S2bPointIndex* ix, int target_kind, const void* targets_dev, size_t n, int max_results, double max_length2,
+                                  int32_t* data_out_dev, double* length2_out_dev, uint32_t* count_out_dev, unsigned long long* min_bits,
+                                  cudaStream_t st) {
   // max_error: results up to that much further away than the true ones MAY be substituted (s2closest_point_query_base.h:
   // 82-101); the results computed here are exact, which satisfies every max_error >= 0.
-  cudaStream_t st = (cudaStream_t)stream;
   double cov[31];
   cov[0] = HUGE_VAL;
   for (int L = 0; L < 30; ++L) cov[L + 1] = std::ldexp(kMinWidthDeriv, -(L + 1)) * (1 - 1e-9);
@@ -752,11 +783,11 @@ int s2b_closest_points_to_targets_dev(const S2bPointIndex* ix, int target_kind, 
   const IndexView v{ix->ids, ix->pts, ix->data, ix->first, (uint32_t)ix->m, 61 - 2 * ix->table_level};
   const int grid = grid_for_pi(n, (const void*)closest_targets_kernel<kTargetEdge>);
   if (target_kind == kTargetPoint)
-    closest_targets_kernel<kTargetPoint><<<grid, kThreads, 0, st>>>(v, targets_dev, n, max_results, start, max_length2, limit_angle, cov_dev, data_out_dev, length2_out_dev, count_out_dev);
+    closest_targets_kernel<kTargetPoint><<<grid, kThreads, 0, st>>>(v, targets_dev, n, max_results, start, max_length2, limit_angle, cov_dev, data_out_dev, length2_out_dev, count_out_dev, min_bits);
   else if (target_kind == kTargetEdge)
-    closest_targets_kernel<kTargetEdge><<<grid, kThreads, 0, st>>>(v, targets_dev, n, max_results, start, max_length2, limit_angle, cov_dev, data_out_dev, length2_out_dev, count_out_dev);
+    closest_targets_kernel<kTargetEdge><<<grid, kThreads, 0, st>>>(v, targets_dev, n, max_results, start, max_length2, limit_angle, cov_dev, data_out_dev, length2_out_dev, count_out_dev, min_bits);
   else
-    closest_targets_kernel<kTargetCell><<<grid, kThreads, 0, st>>>(v, targets_dev, n, max_results, start, max_length2, limit_angle, cov_dev, data_out_dev, length2_out_dev, count_out_dev);
+    closest_targets_kernel<kTargetCell><<<grid, kThreads, 0, st>>>(v, targets_dev, n, max_results, start, max_length2, limit_angle, cov_dev, data_out_dev, length2_out_dev, count_out_dev, min_bits);
   count_launch();
   e = cudaGetLastError();
   cudaFreeAsync(cov_dev, st);
@@ -833,6 +864,97 @@ int s2b_closest_point(const S2bPointIndex* ix, const double* targets, size_t n, 
   if (rc == S2B_OK && length2_out && (e = cudaMemcpy(length2_out, l, 8 * n, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy");
   cudaFree(t); cudaFree(d); cudaFree(l);
   return rc;
+}
+
+
+// FindClosestPoints(ShapeIndexTarget(index)) (s2closest_point_query.h:132-165, S2MinDistanceShapeIndexTarget in
+// s2min_distance_targets.cc:196-255): the distance of an index point p to the target is what
+// S2ClosestEdgeQuery(index).FindClosestEdge(PointTarget(p)) returns — 0 if include_interiors and a polygon of the index
+// contains p (S2ContainsPointQuery, SEMI_OPEN), else the minimum over the index's edges of S2::UpdateMinDistance(p, v0, v1).
+// Here the loops are turned inside out: every (clipped) edge of the device-resident index is an edge target whose
+// candidates within the limit are scanned as for EdgeTarget, and each candidate's slot keeps the minimum (atomicMin on
+// the bits of a non-negative double); points inside polygons are found by the index's own Contains query. The slots are
+// then sorted by (distance, data). With max_results = k and no distance limit, the k index points nearest to one vertex
+// of the target bound the k-th result's distance from above, which gives the edge scan a finite radius.
+int s2b_closest_points_to_shape_index(const S2bPointIndex* pix, const S2bIndex* target, int include_interiors, int max_results, double max_length2,
+                                      double max_error_radians, int32_t* data_out, double* length2_out, size_t capacity, size_t* total_out) {
+  int rc = check_index_device(pix);
+  if (rc != S2B_OK) return rc;
+  if (!target || !total_out) return set_error(S2B_EINVAL, "null argument");
+  if (target->device != pix->device) return set_error(S2B_EINVAL, "the point index (device %d) and the target index (device %d) must be on the same device", pix->device, target->device);
+  if (max_results < 0 || std::isnan(max_length2) || !(max_error_radians >= 0)) return set_error(S2B_EINVAL, "bad max_results / max_length2 / max_error");
+  if (capacity && (!data_out)) return set_error(S2B_EINVAL, "null output with non-zero capacity");
+  *total_out = 0;
+  const size_t m = pix->m;
+  const size_t E = (size_t)target->num_edges;
+  if (m == 0 || (E == 0 && target->view.num_cells == 0) || !(max_length2 > 0)) return S2B_OK;
+  cudaStream_t st = nullptr;
+  auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+  size_t t_sort = 0, t_sort2 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, t_sort, (const int32_t*)nullptr, (int32_t*)nullptr, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (int)m, 0, 32, st);
+  cub::DeviceRadixSort::SortPairs(nullptr, t_sort2, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (const int32_t*)nullptr, (int32_t*)nullptr, (int)m, 0, 64, st);
+  if (t_sort2 > t_sort) t_sort = t_sort2;
+  const size_t o_bits = 0, o_bits2 = up(8 * m), o_data = o_bits2 + up(8 * m), o_data2 = o_data + up(4 * m), o_flags = o_data2 + up(4 * m),
+               o_total = o_flags + up(m), o_tmp = o_total + 256;
+  char* blob = nullptr;
+  cudaError_t e = cudaMalloc((void**)&blob, o_tmp + up(t_sort));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+  unsigned long long* bits = (unsigned long long*)(blob + o_bits);
+  unsigned long long* bits2 = (unsigned long long*)(blob + o_bits2);
+  int32_t* data = (int32_t*)(blob + o_data);
+  int32_t* data2 = (int32_t*)(blob + o_data2);
+  uint8_t* flags = (uint8_t*)(blob + o_flags);
+  unsigned long long* total_dev = (unsigned long long*)(blob + o_total);
+  const int blocks = (int)((m + 255) / 256);
+  auto done = [&](int code) { cudaFree(blob); return code; };
+  fill_u64_kernel<<<blocks, 256, 0, st>>>(bits, m, kInfBits);
+  count_launch();
+  // a finite radius for "the k nearest" without a distance limit (or a tighter one than the caller's)
+  double limit2 = max_length2;
+  if (max_results > 0 && max_results <= kMaxResults && m > (size_t)max_results && E > 0) {
+    double* kd = (double*)bits2;                       // scratch: k distances
+    int32_t* ki = data2;
+    rc = s2b_closest_points_dev(pix, (const double*)target->view.edges, 1, max_results, HUGE_VAL, ki, kd, nullptr, st);
+    if (rc != S2B_OK) return done(rc);
+    double far = 0;
+    e = cudaMemcpy(&far, kd + (max_results - 1), 8, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return done(cuda_fail(e, "cudaMemcpy"));
+    const double bound = far * (1 + 1e-12) + 1e-300;      // the limit is exclusive; at least k points lie within `far` of the target
+    if (bound < limit2) limit2 = bound;
+  }
+  if (include_interiors && target->view.num_cells > 0) {
+    rc = s2b_contains_dev(target, pix->pts, m, S2B_VERTEX_MODEL_SEMI_OPEN, flags, st);
+    if (rc != S2B_OK) return done(rc);
+    zero_where_flag_kernel<<<blocks, 256, 0, st>>>(bits, flags, m);
+    count_launch();
+  }
+  if (E > 0) {
+    rc = launch_closest_targets(pix, kTargetEdge, target->view.edges, E, 0, limit2, nullptr, nullptr, nullptr, bits, st);
+    if (rc != S2B_OK) return done(rc);
+  }
+  // order by (distance, data): stable sort by data, then by the distance bits
+  e = cub::DeviceRadixSort::SortPairs(blob + o_tmp, t_sort, pix->data, data2, (const unsigned long long*)bits, bits2, (int)m, 0, 32, st);
+  if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(blob + o_tmp, t_sort, (const unsigned long long*)bits2, bits, (const int32_t*)data2, data, (int)m, 0, 64, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(total_dev, 0, 8, st);
+  if (e != cudaSuccess) return done(cuda_fail(e, "result sort"));
+  count_launch(); count_launch();
+  unsigned long long limit_bits;
+  { const double l = limit2 < HUGE_VAL ? limit2 : HUGE_VAL; memcpy(&limit_bits, &l, 8); }
+  if (!(max_length2 < HUGE_VAL) && limit2 == max_length2) limit_bits = kInfBits;   // no limit: every point reached by a distance qualifies
+  count_below_sorted_kernel<<<blocks, 256, 0, st>>>(bits, m, limit_bits, total_dev);
+  count_launch();
+  unsigned long long total = 0;
+  e = cudaMemcpy(&total, total_dev, 8, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return done(cuda_fail(e, "cudaMemcpy"));
+  if (max_results > 0 && total > (unsigned long long)max_results) total = (unsigned long long)max_results;
+  *total_out = (size_t)total;
+  const size_t w = total < capacity ? (size_t)total : capacity;
+  if (w) {
+    e = cudaMemcpy(data_out, data, 4 * w, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && length2_out) e = cudaMemcpy(length2_out, bits, 8 * w, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return done(cuda_fail(e, "cudaMemcpy"));
+  }
+  return done(total > capacity ? set_error(S2B_ECAPACITY, "%llu results, capacity %zu", total, capacity) : S2B_OK);
 }
 
 }  // extern "C"

@@ -96,6 +96,24 @@ class ClosestPointQuery:
                                                            self.max_error_rad, data.ctypes.data, l2.ctypes.data, cnt.ctypes.data))
         return (data, l2, cnt) if k else cnt
 
+    def find_shape_index(self, shape_index, max_results=0, include_interiors=True):
+        """FindClosestPoints(ShapeIndexTarget(shape_index)): the index points within max_distance of the geometry of a
+        device-resident ShapeIndex (s2geometry_b200.index.ShapeIndex on the same GPU), nearest first -> (data, length2);
+        points inside a polygon of the index are at distance 0 when include_interiors. max_results = 0: no limit."""
+        import ctypes
+        k = int(max_results)
+        total = ctypes.c_size_t(0)
+        cap = k if k else 1 << 16
+        while True:
+            data = np.empty(cap, np.int32); l2 = np.empty(cap, np.float64)
+            rc = self._lib.s2b_closest_points_to_shape_index(self.index._h, shape_index._h, 1 if include_interiors else 0, k, self.max_length2,
+                                                             self.max_error_rad, data.ctypes.data, l2.ctypes.data, cap, ctypes.byref(total))
+            if rc == _lib.S2B_ECAPACITY:
+                cap = int(total.value)
+                continue
+            _lib.check(rc)
+            return data[: total.value].copy(), l2[: total.value].copy()
+
     def count(self, targets):
         if _is_tensor(targets):
             t = targets.contiguous()

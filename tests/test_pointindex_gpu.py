@@ -228,3 +228,58 @@ def test_edge_and_cell_targets_match_reference(torch_cuda, ref):
     _, gl, _ = q.find(TARGET_EDGE, sub, 1)
     exact = ri.closest_targets(TARGET_EDGE, sub, 1, -1.0, 0.0, th)[1]
     assert (gl == exact).all() and (np.sqrt(gl) <= np.sqrt(wl) + 1e-12).all()
+
+
+def _same_results(got, want, truncated):
+    """(data, length2) lists: the distance sequences must be identical; the data must agree group by group of equal
+    distance (the reference orders ties arbitrarily), except for a last group cut by max_results."""
+    gd, gl = got
+    wd, wl = want
+    assert len(gd) == len(wd), (len(gd), len(wd))
+    assert (gl.view(np.uint64) == wl.view(np.uint64)).all(), int((gl != wl).sum())
+    if len(gl) == 0:
+        return
+    starts = np.flatnonzero(np.concatenate([[True], gl[1:] != gl[:-1]]))
+    ends = np.concatenate([starts[1:], [len(gl)]])
+    for a, b in zip(starts, ends):
+        if truncated and b == len(gl):
+            continue
+        assert sorted(gd[a:b].tolist()) == sorted(wd[a:b].tolist()), (a, b)
+
+
+def test_shape_index_target_matches_reference(torch_cuda, ref):
+    """S2ClosestPointQuery with a ShapeIndexTarget: distances to a whole shape index (polygons with holes, a polyline, a
+    point shape), with and without polygon interiors, with a distance limit, a result limit (<= 32 and > 32), both, and
+    neither (small index) — identical distances to the reference's, index built at the default and the device granularity."""
+    from s2geometry_b200.index import ShapeIndex, build_flat_index
+    from s2geometry_b200.pointindex import ClosestPointQuery, PointIndex
+    from s2geometry_b200.shapes import ShapeSoup
+    soup = ShapeSoup()
+    for loops in synth.many_polygons(60, 21, min_vertices=8, max_vertices=90, min_radius_km=150.0, max_radius_km=1200.0):
+        soup.add_polygon(loops)
+    c = np.array([0.3, -0.5, 0.8]) / np.linalg.norm([0.3, -0.5, 0.8])
+    soup.add_polyline(synth.cap_points(c, 0.3, 40, 5))
+    soup.add_points(synth.sphere_points(25, 6))
+    soup = soup.freeze()
+    rsi = ref.index_create(soup)
+    pts = np.concatenate([synth.sphere_points(250_000, 31), synth.cap_points(c, 0.4, 150_000, 32), soup.vertices[::7]])
+    rpi = ref.point_index(pts)
+    pix = PointIndex(pts)
+    small_pts = pts[:3000]
+    rpi_small = ref.point_index(small_pts)
+    pix_small = PointIndex(small_pts)
+    for max_edges in (0, 1):
+        six = ShapeIndex(build_flat_index(soup, max_edges))
+        for k, r, interiors in ((0, 0.004, True), (0, 0.004, False), (10, math.inf, True), (32, 0.02, False), (100, 0.003, True),
+                                (5, math.inf, False), (1, math.inf, True), (200, math.inf, False), (0, 1e-9, True)):
+            want = rpi.closest_shape_index(rsi, k, -1.0 if math.isinf(r) else r, interiors)
+            got = ClosestPointQuery(pix, r).find_shape_index(six, k, interiors)
+            _same_results(got, want, truncated=k > 0 and len(want[0]) == k)
+            if k == 0 and r > 1e-6:
+                assert len(want[0]) > 1000
+        # no limit at all: every index point with its distance (small index)
+        want = rpi_small.closest_shape_index(rsi, 0, -1.0, True)
+        got = ClosestPointQuery(pix_small, math.inf).find_shape_index(six, 0, True)
+        assert len(got[0]) == len(small_pts)
+        _same_results(got, want, truncated=False)
+        six.close()
