@@ -368,31 +368,21 @@ int s2b_shape_histogram_multi_dev(const S2bIndex* ix, const double* const* xyz_d
   if (!xyz_dev || !n) return set_error(S2B_EINVAL, "null argument");
   const int R = (int)g->rep.size();
   const size_t S = (size_t)(ix->view.num_shape_ids > 0 ? ix->view.num_shape_ids : 1);
-  int cur = 0;
-  cudaGetDevice(&cur);
-  int rc = S2B_OK;
-  for (int k = 0; k < R && rc == S2B_OK; ++k) {
-    cudaSetDevice(g->devices[k]);
+  // every GPU's launches are enqueued by its own worker thread (a round of the join is ~7 launches; from one thread the
+  // enqueue of 8 GPUs would cost more than a small shard takes to run)
+  int rc = on_all_devices(g->devices.data(), R, [&](int k) -> int {
     wait_for_peer_reads(g, k);
-    cudaError_t e = cudaMemsetAsync(g->part[k], 0, 8 * S, g->streams[k]);
-    if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemsetAsync"); break; }
-    if (n[k]) rc = s2b_shape_histogram_dev(g->rep[k], xyz_dev[k], n[k], model, (uint64_t*)g->part[k], g->streams[k]);
-  }
-  if (rc == S2B_OK) rc = R > 1 ? enqueue_allreduce(g) : S2B_OK;
-  for (int k = 0; k < R && rc == S2B_OK; ++k) {
-    cudaSetDevice(g->devices[k]);
+    S2B_CUDA(cudaMemsetAsync(g->part[k], 0, 8 * S, g->streams[k]));
+    return n[k] ? s2b_shape_histogram_dev(g->rep[k], xyz_dev[k], n[k], model, (uint64_t*)g->part[k], g->streams[k]) : S2B_OK;
+  });
+  if (rc == S2B_OK && R > 1) rc = enqueue_allreduce(g);
+  if (rc != S2B_OK) return rc;
+  return on_all_devices(g->devices.data(), R, [&](int k) -> int {
     const unsigned long long* src = R > 1 ? g->total[k] : g->part[k];
-    if (counts_out_dev && counts_out_dev[k]) {
-      cudaError_t e = cudaMemcpyAsync(counts_out_dev[k], src, 8 * S, cudaMemcpyDeviceToDevice, g->streams[k]);
-      if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync");
-    }
-    if (synchronize && rc == S2B_OK) {
-      cudaError_t e = cudaStreamSynchronize(g->streams[k]);
-      if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize");
-    }
-  }
-  cudaSetDevice(cur);
-  return rc;
+    if (counts_out_dev && counts_out_dev[k]) S2B_CUDA(cudaMemcpyAsync(counts_out_dev[k], src, 8 * S, cudaMemcpyDeviceToDevice, g->streams[k]));
+    if (synchronize) S2B_CUDA(cudaStreamSynchronize(g->streams[k]));
+    return S2B_OK;
+  });
 }
 
 // Host-pointer form: the batch is split into one contiguous range per replica; each GPU streams its range through its
