@@ -336,18 +336,21 @@ locate_fast_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint3
       const uint32_t li = t * kThreads + threadIdx.x;
       const uint32_t i = tile_point0 + li;
       const bool valid = i < n;
-      float x = 1.0f, y = 0.0f, z = 0.0f;
-      if (valid) { x = (float)pts[3 * li]; y = (float)pts[3 * li + 1]; z = (float)pts[3 * li + 2]; }
+      // Slots past the end of the batch hold stale or uninitialised bytes: they are read like any point (garbage is just an
+      // "undecided" candidate) and `valid` gates everything that is written.
+      const float x = (float)pts[3 * li], y = (float)pts[3 * li + 1], z = (float)pts[3 * li + 2];
       const float ax = fabsf(x), ay = fabsf(y), az = fabsf(z);
-      const int axis = ax > ay ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
-      const float m = axis == 0 ? x : (axis == 1 ? y : z);
+      // major axis as XYZtoFaceUV picks it (largest |component|, first wins ties), spelled as selects: no branch
+      const bool xy = ax > ay, xz = ax > az, yz = ay > az;
+      const bool axis0 = xy & xz, axis1 = !xy & yz;
+      const float m = axis0 ? x : (axis1 ? y : z);
       const bool neg = m < 0.0f;
-      const float a = axis == 0 ? y : -x;
-      const float b = axis == 2 ? -y : z;
+      const float a = axis0 ? y : -x;
+      const float b = (axis0 | axis1) ? z : -y;
       const float inv = rcp_approx(m);
       const int fi = approx_leaf_coord((neg ? b : a) * inv);
       const int fj = approx_leaf_coord((neg ? a : b) * inv);
-      const int face = axis + (neg ? 3 : 0);
+      const int face = (axis0 ? 0 : (axis1 ? 1 : 2)) + (neg ? 3 : 0);
       // certain only if both coordinates are valid and well inside their lookup-table bucket (NaN/garbage gives fi = 0 or
       // saturated / negative values, which fail these tests). Unsigned arithmetic folds each pair of bounds into one compare.
       const uint32_t ufi = (uint32_t)fi, ufj = (uint32_t)fj;
@@ -356,11 +359,12 @@ locate_fast_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint3
       // the table is addressed by (face, i, j) of the bucket: no Hilbert encoding on this path. The masked coordinates
       // always give a valid bucket, so the read is unconditional (no branch around it).
       const uint32_t e0 = ix.lut[lut_bucket(lut_level, face, ufi & 0x3FFFFFFFu, ufj & 0x3FFFFFFFu)];
-      const uint32_t kind = e0 & ~kLutIndexMask;
-      certain &= kind != kLutMixed;
-      // everything a decided point needs is in the table entry: no second load unless its cell is a pure interior cell with
-      // several clipped shapes. Undecided points are routed (and their outputs written) by the exact kernel.
-      const int hit = !certain ? kHitNone : (kind == kLutInterior ? kHitSingle : (kind == kLutInside ? ((e0 & kLutHasEdges) ? kHitEdges : kHitCell) : kHitNone));
+      // Everything a decided point needs is in the table entry (no second load unless its cell is a pure interior cell
+      // with several clipped shapes). The top three bits of the entry (kind, has-edges) index a packed 2-bit table of
+      // hit kinds: mixed -> none (undecided), empty -> none, inside/no edges -> kHitCell, inside/edges -> kHitEdges,
+      // single-shape interior -> kHitSingle. Undecided points are routed (and their outputs written) by the exact kernel.
+      certain &= (e0 >> 30) != 0u;
+      const int hit = certain ? (int)((0xA700u >> (2u * (e0 >> 29))) & 3u) : kHitNone;
       route_located<kInteriorMode>(ix, o, certain, i, hit, (int)(e0 & kLutCellMask), (int)(e0 & kLutIndexMask), edge_slots, interior_slots, lane);
       unc_slots.append(valid & !certain, i, uncertain, counters + 2, lane);
     }
