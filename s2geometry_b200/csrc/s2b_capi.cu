@@ -133,7 +133,8 @@ struct LiveList {
   FixRecord* h = nullptr;        // cudaHostAlloc(mapped); device alias below
   FixRecord* d_alias = nullptr;
   uint32_t* d_count = nullptr;   // device counter
-  uint32_t* h_count = nullptr;   // pinned copy of the final count
+  uint32_t* h_count = nullptr;   // mapped host word: [0] = set to 1 by the kernel when the list overflowed
+  uint32_t* d_overflow = nullptr; // its device alias
   cudaEvent_t ev = nullptr;
   uint32_t cap = 0;
   uint32_t base = 0;             // the device counter is never reset: records of a launch start at slot (count - base)
@@ -146,7 +147,7 @@ struct LiveList {
     if (d_count) cudaFree(d_count);
     if (h_count) cudaFreeHost(h_count);
     if (ev) cudaEventDestroy(ev);
-    h = nullptr; d_alias = nullptr; d_count = nullptr; h_count = nullptr; ev = nullptr; cap = 0; device = -1; dirty = false;
+    h = nullptr; d_alias = nullptr; d_count = nullptr; h_count = nullptr; d_overflow = nullptr; ev = nullptr; cap = 0; device = -1; dirty = false;
   }
   int ensure(int dev, uint32_t want) {
     if (device == dev && cap >= want) return S2B_OK;
@@ -157,7 +158,9 @@ struct LiveList {
     S2B_CUDA(cudaHostGetDevicePointer((void**)&d_alias, h, 0));
     S2B_CUDA(cudaMalloc((void**)&d_count, sizeof(uint32_t)));
     S2B_CUDA(cudaMemset(d_count, 0, sizeof(uint32_t)));
-    S2B_CUDA(cudaMallocHost((void**)&h_count, sizeof(uint32_t)));
+    S2B_CUDA(cudaHostAlloc((void**)&h_count, sizeof(uint32_t), cudaHostAllocMapped));
+    *h_count = 0;
+    S2B_CUDA(cudaHostGetDevicePointer((void**)&d_overflow, h_count, 0));
     S2B_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     cap = want;
     base = 0;
@@ -362,15 +365,15 @@ static int encode_dev(InputKind kind, const void* in, size_t n, const int* level
   if (live.dirty) {   // a previous call failed half way: stale markers may be left
     S2B_CUDA(cudaStreamSynchronize(st));
     memset(live.h, 0, sizeof(FixRecord) * (size_t)live.cap);
+    *live.h_count = 0;
     S2B_CUDA(cudaMemcpy(&live.base, live.d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost));
     live.dirty = false;
   }
   o.ids_stride = n;
   o.index_base = 0;
-  o.fix_list = live.d_alias; o.fix_count = live.d_count; o.fix_cap = live.cap; o.fix_base = live.base;
+  o.fix_list = live.d_alias; o.fix_count = live.d_count; o.fix_cap = live.cap; o.fix_base = live.base; o.fix_overflow = live.d_overflow;
   cudaError_t e = launch_encode(kind, in, n, o, st);
   if (e != cudaSuccess) return cuda_fail(e, "encode launch");
-  S2B_CUDA(cudaMemcpyAsync(live.h_count, live.d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   S2B_CUDA(cudaEventRecord(live.ev, st));
   std::vector<FixPatch> changed;
   std::vector<FixRecord>& seen = live.seen;   // the records as consumed (id = the device's id) ...
@@ -399,11 +402,13 @@ static int encode_dev(InputKind kind, const void* in, size_t n, const int* level
     if (q != cudaErrorNotReady) return cuda_fail(q, "encode kernel");
   }
   const uint32_t early = k;
-  const uint32_t c = *(volatile uint32_t*)live.h_count - live.base;
-  live.base += c;
-  if (c <= live.cap) {
-    consume_ready(c);   // the kernel has completed: every record below c is in host memory
-    if (k != c) return set_error(S2B_ECUDA, "strict lat/lng list: %u of %u records arrived", k, c);
+  // The kernel has completed, so every record it wrote is in host memory: the list ends at the first empty slot. No copy
+  // of the device counter is needed unless an append found the list full (the kernel then set the overflow word).
+  const bool overflowed = *(volatile uint32_t*)live.h_count != 0;
+  if (!overflowed) {
+    consume_ready(live.cap);
+    const uint32_t c = k;
+    live.base += c;
     // Records consumed while the kernel was running were read behind a marker; now that the launch has completed their
     // payload is visible by definition — make sure it is what was used (it always is when stores land in order).
     for (uint32_t s = 0; s < early; ++s) {
@@ -419,9 +424,12 @@ static int encode_dev(InputKind kind, const void* in, size_t n, const int* level
     g_strict_changed.fetch_add(changed.size(), std::memory_order_relaxed);
     live.dirty = false;
   } else {
-    // More sensitive points than the live list holds (input concentrated on cell boundaries): wipe it and redo the
-    // batch piecewise through a device-side list (collect_patches' fallback), which counts and patches everything.
+    // More sensitive points than the live list holds (input concentrated on cell boundaries): wipe it, resynchronise the
+    // slot base with the device counter and redo the batch piecewise through a device-side list (collect_patches'
+    // fallback), which counts and patches everything.
     for (uint32_t s = 0; s < live.cap; ++s) live.h[s].id = 0;
+    *live.h_count = 0;
+    S2B_CUDA(cudaMemcpy(&live.base, live.d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost));
     live.dirty = false;
     changed.clear();
     FixBuf& fb = t_fix_dev;

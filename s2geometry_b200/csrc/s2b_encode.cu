@@ -68,6 +68,7 @@ struct EncodeArgs {
   FixRecord* fix_list;     // nullable: strict host-libm mode (s2b_internal.h)
   uint32_t* fix_count;
   uint32_t fix_cap, fix_base;
+  uint32_t* fix_overflow;
   uint64_t index_base;
 };
 
@@ -84,7 +85,7 @@ __device__ __forceinline__ RawPoint<kInLatLngRad> load_raw(const void* in, uint3
 __device__ __forceinline__ RawPoint<kInLatLngE7> load_raw(const void* in, uint32_t i, RawPoint<kInLatLngE7>*) { return {__ldcs((const int2*)in + i)}; }
 
 // Strict host-libm mode, rare path (out of line so that it costs the main loop no registers).
-__device__ __noinline__ void append_fix(FixRecord* list, uint32_t* count, uint32_t cap, uint32_t base, uint64_t index, double lat, double lng, uint64_t id) {
+__device__ __noinline__ void append_fix(FixRecord* list, uint32_t* count, uint32_t cap, uint32_t base, uint32_t* overflow, uint64_t index, double lat, double lng, uint64_t id) {
   const uint32_t slot = atomicAdd(count, 1u) - base;   // unsigned arithmetic: correct across a wrap of the counter
   if (slot < cap) {
     // The list may live in mapped host memory that the host reads WHILE this kernel runs (s2b_capi.cu, LiveList): the id
@@ -95,6 +96,8 @@ __device__ __noinline__ void append_fix(FixRecord* list, uint32_t* count, uint32
     r[2] = (unsigned long long)__double_as_longlong(lng);
     __threadfence_system();
     r[3] = id;
+  } else if (overflow) {
+    *(volatile uint32_t*)overflow = 1u;   // the host falls back to a piecewise re-scan (s2b_capi.cu)
   }
 }
 
@@ -188,7 +191,7 @@ encode_kernel(const void* __restrict__ in, uint32_t n, const EncodeArgs a) {
             lng = (M_PI / 180) * (1e-7 * (double)again.e7.y);
           }
           if (near_cell_boundary(fi, fj, kFlagTolIj) || !(fabs(lat) < 1048576.0 && fabs(lng) < 1048576.0))
-            append_fix(a.fix_list, a.fix_count, a.fix_cap, a.fix_base, a.index_base + i, lat, lng, id);
+            append_fix(a.fix_list, a.fix_count, a.fix_cap, a.fix_base, a.fix_overflow, a.index_base + i, lat, lng, id);
         }
       }
     }
@@ -198,10 +201,25 @@ encode_kernel(const void* __restrict__ in, uint32_t n, const EncodeArgs a) {
   }
 }
 
-static int grid_for(size_t n, const void* kernel) {
+// Resident CTAs per SM of a kernel on the current device, looked up once per (thread, kernel, device): the occupancy query
+// costs several microseconds, which a synchronous 1 ms call should not pay every time.
+static int resident_ctas(const void* kernel) {
+  struct Entry { const void* kernel; int device; int per_sm; };
+  static thread_local Entry cache[64];
+  static thread_local int used = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  for (int k = 0; k < used; ++k)
+    if (cache[k].kernel == kernel && cache[k].device == dev) return cache[k].per_sm;
   int per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
   if (per_sm < 1) per_sm = 1;
+  if (used < 64) cache[used++] = Entry{kernel, dev, per_sm};
+  return per_sm;
+}
+
+static int grid_for(size_t n, const void* kernel) {
+  const int per_sm = resident_ctas(kernel);
   size_t want = (n + kThreads - 1) / kThreads;
   size_t cap = (size_t)sm_count() * per_sm;
   return (int)(want < cap ? (want ? want : 1) : cap);
@@ -254,6 +272,7 @@ cudaError_t launch_encode(InputKind kind, const void* in, size_t n, const Encode
     a.fix_count = o.fix_count;
     a.fix_cap = o.fix_cap;
     a.fix_base = o.fix_base;
+    a.fix_overflow = o.fix_overflow;
     a.index_base = o.index_base + off;
     if (token) {
       const int L = o.levels.level[o.token_level_index];

@@ -29,6 +29,7 @@ struct EncodeOut {
   uint32_t* fix_count = nullptr;          // device counter, incremented past fix_cap on overflow
   uint32_t fix_cap = 0;
   uint32_t fix_base = 0;                  // value of *fix_count when the launch starts (the counter is never reset for the live list)
+  uint32_t* fix_overflow = nullptr;       // nullable: set to 1 (mapped host memory) by an append that found the list full
   uint64_t index_base = 0;                // index of point 0 of this launch in the caller's batch
   size_t ids_stride = 0;                  // distance between the per-level id arrays; 0 = n
 };
