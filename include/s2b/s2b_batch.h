@@ -17,6 +17,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <string>
+#include <cmath>
 #include <vector>
 
 #include "../s2b_capi.h"
@@ -255,6 +256,78 @@ class S2CellIndexBatch {
   std::vector<uint64_t> ids_;
   std::vector<int32_t> labels_;
   S2bCellIndex* h_ = nullptr;
+};
+
+// ---- S2PointIndex<int> + S2ClosestPointQuery<int>, batch form (s2point_index.h, s2closest_point_query.h) -----------------
+// Add() collects points on the host (data = the order of insertion, as S2PointIndex<int>::Add(point, i)); Build() sorts them
+// by leaf cell id on the current CUDA device.
+class S2PointIndexBatch {
+ public:
+  S2PointIndexBatch() = default;
+  S2PointIndexBatch(const S2PointIndexBatch&) = delete;
+  S2PointIndexBatch& operator=(const S2PointIndexBatch&) = delete;
+  ~S2PointIndexBatch() { s2b_point_index_destroy(h_); }
+  void Add(const Point& p) { points_.push_back(p); }
+  void Add(const Point* points, size_t n) { points_.insert(points_.end(), points, points + n); }
+  int num_points() const { return (int)points_.size(); }
+  bool Build() {
+    s2b_point_index_destroy(h_);
+    h_ = nullptr;
+    return s2b_point_index_create(points_.empty() ? nullptr : &points_[0].x, points_.size(), &h_) == S2B_OK;
+  }
+  const S2bPointIndex* handle() const { return h_; }
+
+ private:
+  std::vector<Point> points_;
+  S2bPointIndex* h_ = nullptr;
+};
+
+// Options mirror S2ClosestPointQuery::Options: max_results (0 = unlimited; per-target lists hold at most 32), max_distance
+// as S1ChordAngle::length2() (exclusive; INFINITY = none), max_error in radians. Results per target: rows of max_results
+// (data, length2) entries, nearest first, padded with -1 / INFINITY, and the number found.
+class S2ClosestPointQueryBatch {
+ public:
+  explicit S2ClosestPointQueryBatch(const S2PointIndexBatch* index) : index_(index) {}
+  void set_max_results(int k) { max_results_ = k; }
+  void set_max_distance_length2(double length2) { max_length2_ = length2; }
+  void set_max_error_radians(double e) { max_error_ = e; }
+  // FindClosestPoints(PointTarget(targets[i]))
+  bool FindClosestPoints(const Point* targets, size_t n, std::vector<int32_t>* data, std::vector<double>* length2, std::vector<uint32_t>* counts) const {
+    return Find(S2B_TARGET_POINT, &targets->x, n, data, length2, counts);
+  }
+  // FindClosestPoints(EdgeTarget(a, b)): targets = n x (a, b)
+  bool FindClosestPointsToEdges(const Point* endpoints_ab, size_t n, std::vector<int32_t>* data, std::vector<double>* length2, std::vector<uint32_t>* counts) const {
+    return Find(S2B_TARGET_EDGE, &endpoints_ab->x, n, data, length2, counts);
+  }
+  // FindClosestPoints(CellTarget(S2Cell(cell_ids[i])))
+  bool FindClosestPointsToCells(const uint64_t* cell_ids, size_t n, std::vector<int32_t>* data, std::vector<double>* length2, std::vector<uint32_t>* counts) const {
+    return Find(S2B_TARGET_CELL, cell_ids, n, data, length2, counts);
+  }
+  // FindClosestPoints(ShapeIndexTarget(&index)) with include_interiors: ONE target, a list of (data, length2), nearest first.
+  bool FindClosestPointsToShapeIndex(const DeviceShapeIndex& target, bool include_interiors, std::vector<int32_t>* data, std::vector<double>* length2) const {
+    size_t total = 0, cap = max_results_ > 0 ? (size_t)max_results_ : 4096;
+    for (;;) {
+      data->resize(cap); length2->resize(cap);
+      const int rc = s2b_closest_points_to_shape_index(index_->handle(), target.handle(), include_interiors ? 1 : 0, max_results_, max_length2_, max_error_,
+                                                       data->data(), length2->data(), cap, &total);
+      if (rc == S2B_ECAPACITY) { cap = total; continue; }
+      if (rc != S2B_OK) return false;
+      data->resize(total); length2->resize(total);
+      return true;
+    }
+  }
+
+ private:
+  bool Find(int kind, const void* targets, size_t n, std::vector<int32_t>* data, std::vector<double>* length2, std::vector<uint32_t>* counts) const {
+    const size_t k = (size_t)(max_results_ > 0 ? max_results_ : 0);
+    data->assign(n * (k ? k : 1), -1);
+    length2->assign(n * (k ? k : 1), HUGE_VAL);
+    counts->assign(n, 0);
+    return s2b_closest_points_to_targets(index_->handle(), kind, targets, n, (int)k, max_length2_, max_error_, data->data(), length2->data(), counts->data()) == S2B_OK;
+  }
+  const S2PointIndexBatch* index_;
+  int max_results_ = 1;
+  double max_length2_ = HUGE_VAL, max_error_ = 0.0;
 };
 
 }  // namespace s2b

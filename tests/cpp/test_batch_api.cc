@@ -137,6 +137,36 @@ int main() {
     CHECK(ci.CountPointsPerLabel(&on_face2, 1, &counts) && counts.size() == 5 && counts[1] + counts[2] + counts[3] + counts[4] == 0);
   }
 
+  // S2PointIndex + S2ClosestPointQuery through the C++ sugar: five points on the equator, point / edge / cell targets and a
+  // shape-index target (a small square around (0, 0)); answers follow from the geometry.
+  {
+    s2b::S2PointIndexBatch pi;
+    for (int k = 0; k < 5; ++k) pi.Add(FromDegrees(0.0, 10.0 * k));           // data 0..4 at longitudes 0, 10, 20, 30, 40
+    CHECK(pi.Build() && pi.num_points() == 5);
+    s2b::S2ClosestPointQueryBatch q(&pi);
+    q.set_max_results(2);
+    std::vector<int32_t> data; std::vector<double> l2; std::vector<uint32_t> cnt;
+    s2b::Point t = FromDegrees(1.0, 19.0);
+    CHECK(q.FindClosestPoints(&t, 1, &data, &l2, &cnt) && cnt[0] == 2 && data[0] == 2 && data[1] == 1 && l2[0] < l2[1]);
+    s2b::Point edge[2] = {FromDegrees(5.0, 28.0), FromDegrees(5.0, 41.0)};     // runs above points 3 and 4
+    CHECK(q.FindClosestPointsToEdges(edge, 1, &data, &l2, &cnt) && cnt[0] == 2 && ((data[0] == 3 && data[1] == 4) || (data[0] == 4 && data[1] == 3)));
+    std::vector<uint64_t> leaf;
+    std::vector<s2b::Point> at = {FromDegrees(0.0, 10.0)};
+    CHECK(s2b::S2CellIdBatch::FromPoints(at, &leaf));
+    const uint64_t lsb10 = 1ull << (2 * (30 - 10));
+    const uint64_t cell10 = (leaf[0] & (~lsb10 + 1)) | lsb10;                  // the level-10 cell containing point 1
+    CHECK(q.FindClosestPointsToCells(&cell10, 1, &data, &l2, &cnt) && cnt[0] == 2 && data[0] == 1 && l2[0] == 0.0);
+    std::vector<s2b::Point> sq = {FromDegrees(-1, -1), FromDegrees(-1, 1), FromDegrees(1, 1), FromDegrees(1, -1)};
+    const int8_t dim2[] = {2};
+    const uint32_t scb1[] = {0, 1}, cvb1[] = {0, 4};
+    s2b::DeviceShapeIndex square;
+    CHECK(square.InitFromShapes(1, dim2, scb1, cvb1, &sq[0].x));
+    q.set_max_results(0);
+    q.set_max_distance_length2(0.04);                                           // chord^2 of ~11.5 degrees: points 0 and 1
+    CHECK(q.FindClosestPointsToShapeIndex(square, true, &data, &l2) && data.size() == 2 && data[0] == 0 && l2[0] == 0.0 && data[1] == 1 && l2[1] > 0.0);
+    CHECK(q.FindClosestPointsToShapeIndex(square, false, &data, &l2) && data.size() == 2 && data[0] == 0 && l2[0] > 0.0);   // the boundary is 1 degree away
+  }
+
   // Multi-GPU driver behind the C ABI: shard over every visible GPU (2 on the test box; 1 still runs every code path but
   // the exchange), results must equal the single-GPU calls; both reductions (NCCL and the library's peer-memory kernel).
   {
