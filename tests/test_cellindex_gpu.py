@@ -66,10 +66,14 @@ def test_random_and_semi_random_unions(ref):
 def test_clustered_scene(ref):
     rng = np.random.default_rng(11)
     ids, labels = cs.clustered_scene(rng, 200000, 3000, n_seeds=400)
-    singles = np.concatenate([cs.random_cells(rng, 30000), ids[:30000], cs.parent(ids[:20000], rng.integers(0, 31, 20000)),
-                              cs.random_leaves(rng, 20000), (ids[:10000] - (ids[:10000] & (~ids[:10000] + np.uint64(1))) + np.uint64(1))])
+    # random cells, indexed cells, their ancestors at every level (a few of them very coarse: a level-0 target returns every
+    # pair of its face), random leaves and the first leaf of indexed cells. The scene nests deeply (~2000 pairs per target):
+    # 15k targets give ~30M pairs; eight times as many spent 100 s in the reference and the per-target sort.
+    singles = np.concatenate([cs.random_cells(rng, 4000, 5, 30), cs.random_cells(rng, 100, 0, 4), ids[:4000],
+                              cs.parent(ids[:3000], rng.integers(5, 31, 3000)), cs.parent(ids[:100], rng.integers(0, 5, 100)),
+                              cs.random_leaves(rng, 3000), (ids[:1500] - (ids[:1500] & (~ids[:1500] + np.uint64(1))) + np.uint64(1))])
     assert check_scene(ref, ids, labels, singles) > 200000
-    unions = [cs.normalize_sorted_disjoint(np.concatenate([cs.random_cells(rng, 5, 2, 30), ids[rng.integers(0, len(ids), 6)]])) for _ in range(2000)]
+    unions = [cs.normalize_sorted_disjoint(np.concatenate([cs.random_cells(rng, 5, 2, 30), ids[rng.integers(0, len(ids), 6)]])) for _ in range(600)]
     check_scene(ref, ids, labels, unions)
 
 
