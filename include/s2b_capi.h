@@ -166,6 +166,17 @@ int s2b_cellid_edge_neighbors_dev(const uint64_t* ids_dev, size_t n, uint64_t* n
 int s2b_cellid_info(const uint64_t* ids, size_t n, uint8_t* valid_out, int8_t* level_out, uint64_t* range_min_out, uint64_t* range_max_out);
 int s2b_cellid_info_dev(const uint64_t* ids_dev, size_t n, uint8_t* valid_out_dev, int8_t* level_out_dev, uint64_t* range_min_out_dev,
                         uint64_t* range_max_out_dev, void* stream);
+/* Traversal helpers of S2CellId, element-wise (s2cell_id.h:670-677, s2cell_id.cc:119-168, :193-207):
+ *   children:  children4_out[4 i + k] = ids[i].child(k), k = 0..3 (Hilbert order); 0 for leaf cells and invalid ids
+ *   advance:   out[i] = ids[i].advance(steps[i]) (clamped to [Begin(level), End(level)]) or, with wrap != 0,
+ *              ids[i].advance_wrap(steps[i]); next() / prev() are steps of +1 / -1. 0 for invalid ids
+ *   common_ancestor_level: level_out[i] = a[i].GetCommonAncestorLevel(b[i]) (-1: different faces, or an invalid id) */
+int s2b_cellid_children(const uint64_t* ids, size_t n, uint64_t* children4_out);
+int s2b_cellid_children_dev(const uint64_t* ids_dev, size_t n, uint64_t* children4_out_dev, void* stream);
+int s2b_cellid_advance(const uint64_t* ids, const int64_t* steps, size_t n, int wrap, uint64_t* out);
+int s2b_cellid_advance_dev(const uint64_t* ids_dev, const int64_t* steps_dev, size_t n, int wrap, uint64_t* out_dev, void* stream);
+int s2b_cellid_common_ancestor_level(const uint64_t* a, const uint64_t* b, size_t n, int8_t* level_out);
+int s2b_cellid_common_ancestor_level_dev(const uint64_t* a_dev, const uint64_t* b_dev, size_t n, int8_t* level_out_dev, void* stream);
 /* S2CellId::AppendVertexNeighbors(level) (s2cell_id.cc:514-556): the cells of `level` around the vertex of
  * parent(level) closest to the cell, in the reference's order: neighbors4_out[4*i + k], count_out[i] = 3 (cube vertex)
  * or 4; unused slots are 0. Requires level < level(ids[i]) (as the reference does); otherwise count 0. */

@@ -782,6 +782,23 @@ size_t ref_closest_points_shape_index(void* h, void* index_h, int include_interi
   }
   return r.size();
 }
+// S2CellId::child(k), advance / advance_wrap, GetCommonAncestorLevel element-wise (valid ids only).
+void ref_cellid_children(const uint64_t* ids, size_t n, uint64_t* out4) {
+  for (size_t i = 0; i < n; ++i)
+    for (int k = 0; k < 4; ++k) out4[4 * i + k] = S2CellId(ids[i]).child(k).id();
+}
+void ref_cellid_advance(const uint64_t* ids, const int64_t* steps, size_t n, int wrap, uint64_t* out) {
+  for (size_t i = 0; i < n; ++i) out[i] = (wrap ? S2CellId(ids[i]).advance_wrap(steps[i]) : S2CellId(ids[i]).advance(steps[i])).id();
+}
+void ref_cellid_next_prev(const uint64_t* ids, size_t n, uint64_t* next, uint64_t* prev, uint64_t* next_wrap, uint64_t* prev_wrap) {
+  for (size_t i = 0; i < n; ++i) {
+    const S2CellId c(ids[i]);
+    next[i] = c.next().id(); prev[i] = c.prev().id(); next_wrap[i] = c.next_wrap().id(); prev_wrap[i] = c.prev_wrap().id();
+  }
+}
+void ref_cellid_common_ancestor_level(const uint64_t* a, const uint64_t* b, size_t n, int8_t* out) {
+  for (size_t i = 0; i < n; ++i) out[i] = (int8_t)S2CellId(a[i]).GetCommonAncestorLevel(S2CellId(b[i]));
+}
 double ref_chord_length2(double angle_rad) { return S1ChordAngle(S1Angle::Radians(angle_rad)).length2(); }
 
 // S2CellUnion::Contains(S2CellId) (bit0) and ::Intersects(S2CellId) (bit1).

@@ -50,6 +50,12 @@ SIGNATURES = {
     "s2b_cellid_to_latlng_dev": (_i, [_vp, _sz, _vp, _vp]),
     "s2b_cellid_from_token": (_i, [_vp, _vp, _sz, _vp]),
     "s2b_cellid_from_token_dev": (_i, [_vp, _vp, _sz, _vp, _vp]),
+    "s2b_cellid_children": (_i, [_vp, _sz, _vp]),
+    "s2b_cellid_children_dev": (_i, [_vp, _sz, _vp, _vp]),
+    "s2b_cellid_advance": (_i, [_vp, _vp, _sz, _i, _vp]),
+    "s2b_cellid_advance_dev": (_i, [_vp, _vp, _sz, _i, _vp, _vp]),
+    "s2b_cellid_common_ancestor_level": (_i, [_vp, _vp, _sz, _vp]),
+    "s2b_cellid_common_ancestor_level_dev": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "s2b_cellid_info": (_i, [_vp, _sz, _vp, _vp, _vp, _vp]),
     "s2b_cellid_info_dev": (_i, [_vp, _sz, _vp, _vp, _vp, _vp, _vp]),
     "s2b_cellid_vertex_neighbors": (_i, [_vp, _sz, _i, _vp, _vp]),

@@ -265,6 +265,54 @@ def edge_neighbors(ids):
     return out
 
 
+def children(ids):
+    """S2CellId::child(0..3) element-wise -> (N,4) ids in Hilbert order (0 for leaf cells and invalid ids)."""
+    lib = _lib.load()
+    if _is_tensor(ids):
+        ids = _tensor_in(ids, torch.int64, 0)
+        out = torch.empty((ids.numel(), 4), dtype=torch.int64, device=ids.device)
+        with torch.cuda.device(ids.device):
+            _lib.check(lib.s2b_cellid_children_dev(_ptr(ids), ids.numel(), _ptr(out), _stream()))
+        return out
+    ids = _np_in(ids, np.uint64, 0)
+    out = np.empty((ids.size, 4), dtype=np.uint64)
+    _lib.check(lib.s2b_cellid_children(_ptr(ids), ids.size, _ptr(out)))
+    return out
+
+
+def advance(ids, steps, wrap=False):
+    """S2CellId::advance(steps) (clamped at the ends of the level) or, with wrap=True, advance_wrap(steps), element-wise;
+    next() / prev() are steps of +1 / -1."""
+    lib = _lib.load()
+    if _is_tensor(ids):
+        ids = _tensor_in(ids, torch.int64, 0)
+        st = _tensor_in(torch.as_tensor(steps, dtype=torch.int64, device=ids.device).expand(ids.numel()).contiguous(), torch.int64, 0)
+        out = torch.empty_like(ids)
+        with torch.cuda.device(ids.device):
+            _lib.check(lib.s2b_cellid_advance_dev(_ptr(ids), _ptr(st), ids.numel(), 1 if wrap else 0, _ptr(out), _stream()))
+        return out
+    ids = _np_in(ids, np.uint64, 0)
+    st = np.ascontiguousarray(np.broadcast_to(np.asarray(steps, np.int64), ids.shape))
+    out = np.empty_like(ids)
+    _lib.check(lib.s2b_cellid_advance(_ptr(ids), _ptr(st), ids.size, 1 if wrap else 0, _ptr(out)))
+    return out
+
+
+def common_ancestor_level(a, b):
+    """S2CellId::GetCommonAncestorLevel element-wise -> int8 (-1: different faces or an invalid id)."""
+    lib = _lib.load()
+    if _is_tensor(a):
+        a = _tensor_in(a, torch.int64, 0); b = _tensor_in(b, torch.int64, 0)
+        out = torch.empty(a.numel(), dtype=torch.int8, device=a.device)
+        with torch.cuda.device(a.device):
+            _lib.check(lib.s2b_cellid_common_ancestor_level_dev(_ptr(a), _ptr(b), a.numel(), _ptr(out), _stream()))
+        return out
+    a = _np_in(a, np.uint64, 0); b = _np_in(b, np.uint64, 0)
+    out = np.empty(a.size, dtype=np.int8)
+    _lib.check(lib.s2b_cellid_common_ancestor_level(_ptr(a), _ptr(b), a.size, _ptr(out)))
+    return out
+
+
 def info(ids):
     """S2CellId::is_valid / level / range_min / range_max element-wise -> (valid bool, level int8 (-1 if invalid), range_min, range_max)."""
     lib = _lib.load()

@@ -155,6 +155,27 @@ cellid_info_kernel(const uint64_t* __restrict__ ids, size_t n, uint8_t* __restri
   }
 }
 
+// S2CellId::child(0..3), advance / advance_wrap, GetCommonAncestorLevel element-wise (any output may be null).
+__global__ void __launch_bounds__(kThreads)
+cellid_traverse_kernel(const uint64_t* __restrict__ ids, const uint64_t* __restrict__ others, const long long* __restrict__ steps, size_t n, int wrap,
+                       uint64_t* __restrict__ children4, uint64_t* __restrict__ advanced, int8_t* __restrict__ ancestor_level) {
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < n; t += stride) {
+    const uint64_t id = __ldcs(ids + t);
+    const bool ok = cellid_is_valid(id);
+    if (children4) {
+      const bool parent = ok && !(id & 1);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) children4[4 * t + k] = parent ? cellid_child(id, k) : 0;
+    }
+    if (advanced) advanced[t] = ok ? cellid_advance(id, steps[t], wrap != 0) : 0;
+    if (ancestor_level) {
+      const uint64_t other = others[t];
+      ancestor_level[t] = (ok && cellid_is_valid(other)) ? (int8_t)cellid_common_ancestor_level(id, other) : (int8_t)-1;
+    }
+  }
+}
+
 // ---- Normalize -----------------------------------------------------------------------------------------------------
 struct MaxOp { __host__ __device__ __forceinline__ uint64_t operator()(uint64_t a, uint64_t b) const { return a > b ? a : b; } };
 struct MinOp { __host__ __device__ __forceinline__ uint64_t operator()(uint64_t a, uint64_t b) const { return a < b ? a : b; } };
@@ -425,6 +446,76 @@ int s2b_cellunion_normalize(const uint64_t* ids, size_t m, uint64_t* out, size_t
   int rc = normalize_dev((const uint64_t*)in.p, m, (uint64_t*)o.p, count_out, nullptr);
   if (rc != S2B_OK) return rc;
   if (*count_out && (e = cudaMemcpy(out, o.p, 8 * *count_out, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
+  return S2B_OK;
+}
+
+
+int s2b_cellid_children_dev(const uint64_t* ids_dev, size_t n, uint64_t* children4_out_dev, void* stream) {
+  if (n == 0) return S2B_OK;
+  if (!ids_dev || !children4_out_dev) return set_error(S2B_EINVAL, "null pointer");
+  cellid_traverse_kernel<<<grid_for_ops(n, (const void*)cellid_traverse_kernel), kThreads, 0, (cudaStream_t)stream>>>(ids_dev, nullptr, nullptr, n, 0, children4_out_dev, nullptr, nullptr);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? S2B_OK : cuda_fail(e, "cellid_children launch");
+}
+
+int s2b_cellid_advance_dev(const uint64_t* ids_dev, const int64_t* steps_dev, size_t n, int wrap, uint64_t* out_dev, void* stream) {
+  if (n == 0) return S2B_OK;
+  if (!ids_dev || !steps_dev || !out_dev) return set_error(S2B_EINVAL, "null pointer");
+  cellid_traverse_kernel<<<grid_for_ops(n, (const void*)cellid_traverse_kernel), kThreads, 0, (cudaStream_t)stream>>>(ids_dev, nullptr, (const long long*)steps_dev, n, wrap, nullptr, out_dev, nullptr);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? S2B_OK : cuda_fail(e, "cellid_advance launch");
+}
+
+int s2b_cellid_common_ancestor_level_dev(const uint64_t* a_dev, const uint64_t* b_dev, size_t n, int8_t* level_out_dev, void* stream) {
+  if (n == 0) return S2B_OK;
+  if (!a_dev || !b_dev || !level_out_dev) return set_error(S2B_EINVAL, "null pointer");
+  cellid_traverse_kernel<<<grid_for_ops(n, (const void*)cellid_traverse_kernel), kThreads, 0, (cudaStream_t)stream>>>(a_dev, b_dev, nullptr, n, 0, nullptr, nullptr, level_out_dev);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? S2B_OK : cuda_fail(e, "cellid_common_ancestor_level launch");
+}
+
+// Host-pointer forms of the three above (whole-array copies).
+int s2b_cellid_children(const uint64_t* ids, size_t n, uint64_t* children4_out) {
+  if (n == 0) return S2B_OK;
+  if (!ids || !children4_out) return set_error(S2B_EINVAL, "null pointer");
+  DevBuf in, out;
+  cudaError_t e;
+  if ((e = in.alloc(8 * n)) != cudaSuccess || (e = out.alloc(32 * n)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+  if ((e = cudaMemcpy(in.p, ids, 8 * n, cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
+  int rc = s2b_cellid_children_dev((const uint64_t*)in.p, n, (uint64_t*)out.p, nullptr);
+  if (rc != S2B_OK) return rc;
+  if ((e = cudaMemcpy(children4_out, out.p, 32 * n, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
+  return S2B_OK;
+}
+
+int s2b_cellid_advance(const uint64_t* ids, const int64_t* steps, size_t n, int wrap, uint64_t* out) {
+  if (n == 0) return S2B_OK;
+  if (!ids || !steps || !out) return set_error(S2B_EINVAL, "null pointer");
+  DevBuf in, st, o;
+  cudaError_t e;
+  if ((e = in.alloc(8 * n)) != cudaSuccess || (e = st.alloc(8 * n)) != cudaSuccess || (e = o.alloc(8 * n)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+  if ((e = cudaMemcpy(in.p, ids, 8 * n, cudaMemcpyHostToDevice)) != cudaSuccess || (e = cudaMemcpy(st.p, steps, 8 * n, cudaMemcpyHostToDevice)) != cudaSuccess)
+    return cuda_fail(e, "cudaMemcpy");
+  int rc = s2b_cellid_advance_dev((const uint64_t*)in.p, (const int64_t*)st.p, n, wrap, (uint64_t*)o.p, nullptr);
+  if (rc != S2B_OK) return rc;
+  if ((e = cudaMemcpy(out, o.p, 8 * n, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
+  return S2B_OK;
+}
+
+int s2b_cellid_common_ancestor_level(const uint64_t* a, const uint64_t* b, size_t n, int8_t* level_out) {
+  if (n == 0) return S2B_OK;
+  if (!a || !b || !level_out) return set_error(S2B_EINVAL, "null pointer");
+  DevBuf da, db, o;
+  cudaError_t e;
+  if ((e = da.alloc(8 * n)) != cudaSuccess || (e = db.alloc(8 * n)) != cudaSuccess || (e = o.alloc(n)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+  if ((e = cudaMemcpy(da.p, a, 8 * n, cudaMemcpyHostToDevice)) != cudaSuccess || (e = cudaMemcpy(db.p, b, 8 * n, cudaMemcpyHostToDevice)) != cudaSuccess)
+    return cuda_fail(e, "cudaMemcpy");
+  int rc = s2b_cellid_common_ancestor_level_dev((const uint64_t*)da.p, (const uint64_t*)db.p, n, (int8_t*)o.p, nullptr);
+  if (rc != S2B_OK) return rc;
+  if ((e = cudaMemcpy(level_out, o.p, n, cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
   return S2B_OK;
 }
 

@@ -305,6 +305,59 @@ S2B_HD int cellid_to_token(uint64_t id, uint32_t out[4]) {
 
 // S2CellId::level() for a valid id (s2cell_id.h:595-603).
 S2B_HD int cellid_level(uint64_t id) { return 30 - (ctz64(id) >> 1); }
+S2B_HD int bit_width64(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+  return 64 - __clzll((long long)v);
+#else
+  return v ? 64 - __builtin_clzll(v) : 0;
+#endif
+}
+
+// ---- traversal helpers of S2CellId (pure integer) -------------------------------------------------------------------
+S2B_HD uint64_t cellid_child(uint64_t id, int position) {            // s2cell_id.h:670-677
+  const uint64_t new_lsb = cellid_lsb(id) >> 2;
+  return id + (uint64_t)(2 * position + 1 - 4) * new_lsb;
+}
+constexpr uint64_t kCellIdWrapOffset = 6ull << 61;                     // S2CellId::kWrapOffset (s2cell_id.h:525)
+// S2CellId::advance (s2cell_id.cc:119-138; clamped to [Begin(level), End(level)]) and ::advance_wrap (:145-168).
+S2B_HD uint64_t cellid_advance(uint64_t id, long long steps, bool wrap) {
+  if (steps == 0) return id;
+  const int step_shift = 2 * (30 - cellid_level(id)) + 1;
+  if (steps < 0) {
+    const long long min_steps = -(long long)(id >> step_shift);
+    if (steps < min_steps) {
+      if (!wrap) {
+        steps = min_steps;
+      } else {
+        const long long step_wrap = (long long)(kCellIdWrapOffset >> step_shift);
+        steps %= step_wrap;
+        if (steps < min_steps) steps += step_wrap;
+      }
+    }
+  } else {
+    const long long max_steps = (long long)((wrap ? kCellIdWrapOffset - id : kCellIdWrapOffset + cellid_lsb(id) - id) >> step_shift);
+    if (steps > max_steps) {
+      if (!wrap) {
+        steps = max_steps;
+      } else {
+        const long long step_wrap = (long long)(kCellIdWrapOffset >> step_shift);
+        steps %= step_wrap;
+        if (steps > max_steps) steps -= step_wrap;
+      }
+    }
+  }
+  return id + ((uint64_t)steps << step_shift);
+}
+// S2CellId::GetCommonAncestorLevel (s2cell_id.cc:193-207): -1 when the cells are on different faces.
+S2B_HD int cellid_common_ancestor_level(uint64_t a, uint64_t b) {
+  uint64_t bits = a ^ b;
+  const uint64_t la = cellid_lsb(a), lb = cellid_lsb(b);
+  if (la > bits) bits = la;
+  if (lb > bits) bits = lb;
+  const int width = bit_width64(bits);                                 // absl::bit_width: position of the top bit + 1
+  const int v = 61 - width;
+  return (v > -1 ? v : -1) >> 1;
+}
 
 // S2CellId::FromFaceIJWrap (s2cell_id.cc:458-489): (i,j) just outside a face -> the leaf cell on the adjacent face.
 template <class TableT>

@@ -352,17 +352,7 @@ S2B_HD int region_clip_relation(const FlatIndexView& ix, const FlatClip& clip, b
   return clip_contains_centre(ix, clip, a, centre, a_cross_b) ? 2 : 0;
 }
 
-// S2CellId::GetCommonAncestorLevel (s2cell_id.cc:193-207): -1 when the cells are on different faces.
-S2B_HD int cellid_common_ancestor_level(uint64_t a, uint64_t b) {
-  uint64_t bits = a ^ b;
-  const uint64_t la = cellid_lsb(a), lb = cellid_lsb(b);
-  if (la > bits) bits = la;
-  if (lb > bits) bits = lb;
-  int width = 0;
-  while (bits) { ++width; bits >>= 1; }
-  const int v = 61 - width;
-  return (v < -1 ? -1 : v) >> 1;
-}
+// (S2CellId::GetCommonAncestorLevel is cellid_common_ancestor_level in s2b_core.cuh.)
 
 // S2ShapeIndexRegion::GetCellUnionBound (s2shape_index_region.h:232-305) over the sorted index cell ids: at most six
 // cells (one per face the index touches, or the up-to-four children of the smallest cell holding a single-face index,

@@ -194,3 +194,60 @@ def test_cellid_info_matches_reference(torch_cuda, ref):
     assert (~v2).all() and (l2 == -1).all()
     dv, dl, da, db = cellid.info(torch.from_numpy(ids.view(np.int64)).cuda())
     assert dv.all().item() and (dl.cpu().numpy() == level).all() and (da.cpu().numpy().view(np.uint64) == rmin).all() and (db.cpu().numpy().view(np.uint64) == rmax).all()
+
+
+def test_children_advance_and_common_ancestor_level(torch_cuda, ref):
+    """S2CellId::child, advance, advance_wrap, next / prev (+ _wrap) and GetCommonAncestorLevel element-wise against the
+    reference: cells of every level incl. the first and last cell of each level (where advance clamps and the wrapping
+    forms wrap), steps from 0 to far beyond the level's size, pairs on the same and on different faces."""
+    import ctypes
+    from oracle.reflib import _p, _sz
+    torch = torch_cuda
+    from s2geometry_b200 import cellid
+    rng = np.random.default_rng(5)
+    leaf = ref.encode_points(rng.standard_normal((60000, 3)), 30, 1)
+    lv = rng.integers(0, 31, len(leaf))
+    ids = np.array([ref.parent(leaf[i:i + 1], int(l))[0] for i, l in enumerate(lv)], np.uint64)
+    ends = []
+    for level in range(31):
+        lsb = np.uint64(1) << np.uint64(2 * (30 - level))
+        ends += [lsb, np.uint64(6 << 61) - lsb, lsb + (lsb << np.uint64(1)), np.uint64(3 << 61) + lsb]   # Begin, last, second, first of face 3
+    ids = np.concatenate([ids, np.array(ends, np.uint64)])
+    n = len(ids)
+    lib = ref.lib
+    # children (non-leaf cells)
+    par = ids[(ids & np.uint64(1)) == 0]
+    want = np.empty((len(par), 4), np.uint64)
+    lib.ref_cellid_children(_p(par), _sz(len(par)), _p(want))
+    assert (cellid.children(par) == want).all()
+    assert (cellid.children(torch.from_numpy(par.view(np.int64)).cuda()).cpu().numpy().view(np.uint64) == want).all()
+    assert (cellid.children(ids[(ids & np.uint64(1)) == 1][:100]) == 0).all()          # leaf cells have no children
+    # advance / advance_wrap
+    mag = 10.0 ** rng.uniform(0, 18.9, n)
+    steps = (rng.choice([-1, 1], n) * mag).astype(np.int64)
+    steps[::11] = rng.integers(-3, 4, len(steps[::11]))
+    steps[::97] = 0
+    for wrap in (0, 1):
+        want = np.empty(n, np.uint64)
+        lib.ref_cellid_advance(_p(ids), _p(steps), _sz(n), wrap, _p(want))
+        assert (cellid.advance(ids, steps, bool(wrap)) == want).all(), wrap
+        got = cellid.advance(torch.from_numpy(ids.view(np.int64)).cuda(), torch.from_numpy(steps).cuda(), bool(wrap))
+        assert (got.cpu().numpy().view(np.uint64) == want).all(), wrap
+    nx, pv, nxw, pvw = (np.empty(n, np.uint64) for _ in range(4))
+    lib.ref_cellid_next_prev(_p(ids), _sz(n), _p(nx), _p(pv), _p(nxw), _p(pvw))
+    # next() / prev() do not clamp (they may return End(level) / an id before Begin); advance(+-1) equals them except there
+    inner = (ids != np.array([np.uint64(6 << 61) - (i & (~i + np.uint64(1))) for i in ids], np.uint64))
+    assert (cellid.advance(ids, 1)[inner] == nx[inner]).all()
+    assert (cellid.advance(ids, 1, wrap=True) == nxw).all() and (cellid.advance(ids, -1, wrap=True) == pvw).all()
+    first = ids == (ids & (~ids + np.uint64(1)))
+    assert (cellid.advance(ids, -1)[~first] == pv[~first]).all()
+    # common ancestor level
+    other = np.concatenate([ids[rng.permutation(n)[: n // 2]], ids[n // 2:]])                              # unrelated cells, and each cell with itself
+    anc = rng.integers(0, 31, n)
+    near = np.array([ref.parent(leaf[i % len(leaf)][None], int(min(a, 30)))[0] for i, a in enumerate(anc)], np.uint64)   # relatives of the same leaves
+    for b in (other, near):
+        want = np.empty(n, np.int8)
+        lib.ref_cellid_common_ancestor_level(_p(ids), _p(b), _sz(n), _p(want))
+        assert (cellid.common_ancestor_level(ids, b) == want).all()
+        assert (cellid.common_ancestor_level(torch.from_numpy(ids.view(np.int64)).cuda(), torch.from_numpy(b.view(np.int64)).cuda()).cpu().numpy() == want).all()
+        assert (want >= 0).sum() > 1000
