@@ -100,6 +100,13 @@ class ClockSampler:
 STREAM_LATLNG = 2   # seed of the headline lat/lng stream (s2geometry_b200/synth.py: point i = f(seed, i), any host or GPU)
 
 
+def workload_config(n):
+    """The `config` object of BOTH arms (the reference arm must run the product arm's config)."""
+    return {"workload": WORKLOAD, "points_per_gpu": n, "levels": LEVELS,
+            "input": "counter-based stream %d, rank r encodes points [r*n, (r+1)*n) (s2geometry_b200/synth.py)" % STREAM_LATLNG,
+            "l2_policy": "inputs (1.6 GB) and outputs (4.1 GB) per step exceed the 126 MB L2"}
+
+
 def run_reference(args):
     """The reference's own CPU implementation of the step on this box's host cores: the same 100M-point stream the
     GPU arm encodes (counter-based generator: identical bits on the host), all host threads."""
@@ -125,10 +132,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "points_per_gpu": n, "levels": LEVELS, "points_per_step": n,
-                   "note": "unmodified reference sources + abseil stand-in, -O2, %d host threads; one GPU's share of the stream per step" % threads},
+        "config": workload_config(n),   # the product arm's config, key for key
         "cpu_baseline": {"value": value, "unit": "points/s", "cores": threads, "kind": "reference",
-                         "sample": "all %d lat/lng points of stream %d per step, %d threads" % (n, STREAM_LATLNG, threads)},
+                         "sample": "all %d lat/lng points of stream %d per step (one GPU's share of the stream), %d threads; unmodified reference sources + abseil stand-in, -O2"
+                                   % (n, STREAM_LATLNG, threads)},
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     _emit(line)
@@ -931,12 +938,12 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD,
-                       "points_per_gpu": n, "levels": LEVELS, "l2_policy": "inputs (1.6 GB) and outputs (4.1 GB) per step exceed the 126 MB L2",
-                       "input": "counter-based stream %d, rank r encodes points [r*n, (r+1)*n) (s2geometry_b200/synth.py)" % STREAM_LATLNG,
-                       "step": "s2b_encode_latlng_strict_dev: encode_kernel<latlng> (1 launch: fast sin/cos filter + correctly rounded path for boundary-sensitive points, fused parent/ToToken epilogues) + host-libm re-evaluation of the libm-sensitive points (S2B_LATLNG_HOST_LIBM)",
-                       "summary": summary},
+            "config": workload_config(n),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "step": "s2b_encode_latlng_strict_dev: encode_kernel<latlng> (1 launch: fast sin/cos filter + correctly rounded path for boundary-sensitive points, fused parent/ToToken epilogues) + host-libm re-evaluation of the libm-sensitive points (S2B_LATLNG_HOST_LIBM)",
+                         # compact results of the secondary sections (configs[0], [2], [3], [4] and the widened rows): Gpts/s, fraction
+                         # of the HBM roofline at their algorithmic bytes per point, parity against the reference
+                         "secondary": summary,
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from ncu --set full, scaled to this launch
                          "traffic": DRAM_BYTES_PER_POINT * n, "traffic_source": "profile: " + PROFILE_SOURCE,
                          "traffic_unit": "bytes per launch (ncu dram read+write, %.2f B/point)" % DRAM_BYTES_PER_POINT,

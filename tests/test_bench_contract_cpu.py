@@ -28,6 +28,10 @@ def _check_reference_line(stdout):
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
+    # the reference arm runs the product arm's config: the same object, key for key (bench.workload_config)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.workload_config(d["config"]["points_per_gpu"])
     return d
 
 

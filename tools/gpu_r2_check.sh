@@ -16,7 +16,7 @@ try:
     print('roofline', {k: v for k, v in d['roofline'].items() if k != 'fp64'})
     print('e2e', d['e2e'])
     print('cpu', d.get('cpu_baseline'))
-    print('summary', json.dumps(d['config']['summary'], indent=0))
+    print('summary', json.dumps(d['roofline']['secondary'], indent=0))
     r=json.load(open('gpurun_out/bench_ref.json')); print('ref', r['value'], r['ms_per_step'], r['cpu_baseline'])
 except Exception as e:
     print('summary failed', e)

@@ -10,6 +10,6 @@ python - <<'PY'
 import json
 d=json.load(open('gpurun_out/bench_2gpu.json'))
 print('value', d['value']/1e9, 'e2e', d['e2e']['value']/1e9, d['e2e']['host_link_ceiling'], d['e2e']['host_placement'])
-print(json.dumps(d['config']['summary']))
+print(json.dumps(d['roofline']['secondary']))
 print(json.dumps(d.get('capi_multi_join')))
 PY

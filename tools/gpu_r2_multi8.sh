@@ -9,7 +9,7 @@ for N in 8 4; do
 import json, sys
 d=json.load(open('gpurun_out/bench_%sgpu.json' % sys.argv[1]))
 print('n_gpus', d['n_gpus'], 'encode', d['value']/1e9, 'ms', d['ms_per_step'], 'e2e', d['e2e']['value']/1e9, d['e2e']['host_link_ceiling'], d['e2e']['host_placement'])
-print(json.dumps(d['config']['summary']))
+print(json.dumps(d['roofline']['secondary']))
 print(json.dumps(d.get('capi_multi_join')))
 PY
 done
