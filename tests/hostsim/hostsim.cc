@@ -104,6 +104,16 @@ extern "C" void hs_edge_neighbors(const uint64_t* ids, size_t n, uint64_t* out4)
   for (size_t i = 0; i < n; ++i) cellid_edge_neighbors(ids[i], kHilbert.pos, kHilbert.ij, out4 + 4 * i);
 }
 
+extern "C" void hs_cellid_traverse(const uint64_t* ids, const uint64_t* others, const int64_t* steps, size_t n, uint64_t* children4, uint64_t* adv,
+                                   uint64_t* adv_wrap, int8_t* ancestor) {
+  for (size_t i = 0; i < n; ++i) {
+    for (int k = 0; k < 4; ++k) children4[4 * i + k] = (ids[i] & 1) ? 0 : cellid_child(ids[i], k);
+    adv[i] = cellid_advance(ids[i], steps[i], false);
+    adv_wrap[i] = cellid_advance(ids[i], steps[i], true);
+    ancestor[i] = (int8_t)cellid_common_ancestor_level(ids[i], others[i]);
+  }
+}
+
 // ---- counter-based synthetic streams (s2b_synth.cuh) and the strict host-libm lat/lng mode, host compilation ----
 #include <math.h>
 #include "s2b_synth.cuh"

@@ -225,6 +225,34 @@ def test_edge_neighbors_hostsim(hostsim, ref):
     assert (out == ref.edge_neighbors(ids)).all()
 
 
+def test_traversal_helpers_hostsim(hostsim, ref):
+    """child / advance / advance_wrap / GetCommonAncestorLevel as the kernels compute them (host build of s2b_core.cuh)
+    against the reference, incl. the first and last cell of every level and steps far beyond a level's size."""
+    from oracle.reflib import _p, _sz
+    rng = np.random.default_rng(23)
+    ids = random_ids_all_levels(ref, 100000, 29)
+    ends = []
+    for level in range(31):
+        lsb = 1 << (2 * (30 - level))
+        ends += [lsb, (6 << 61) - lsb, 3 * lsb, (3 << 61) + lsb]
+    ids = np.concatenate([ids, np.array(ends, np.uint64)])
+    n = len(ids)
+    others = np.concatenate([ids[rng.permutation(n)[: n // 2]], ids[n // 2:]])
+    steps = (rng.choice([-1, 1], n) * 10.0 ** rng.uniform(0, 18.9, n)).astype(np.int64)
+    steps[::7] = rng.integers(-3, 4, len(steps[::7]))
+    ch = np.empty((n, 4), np.uint64); adv = np.empty(n, np.uint64); advw = np.empty(n, np.uint64); anc = np.empty(n, np.int8)
+    hostsim.hs_cellid_traverse(vp(ids), vp(others), vp(steps), ctypes.c_size_t(n), vp(ch), vp(adv), vp(advw), vp(anc))
+    want = np.empty(n, np.uint64)
+    ref.lib.ref_cellid_advance(_p(ids), _p(steps), _sz(n), 0, _p(want)); assert (adv == want).all()
+    ref.lib.ref_cellid_advance(_p(ids), _p(steps), _sz(n), 1, _p(want)); assert (advw == want).all()
+    wa = np.empty(n, np.int8)
+    ref.lib.ref_cellid_common_ancestor_level(_p(ids), _p(others), _sz(n), _p(wa)); assert (anc == wa).all()
+    par = (ids & np.uint64(1)) == 0
+    wc = np.empty((int(par.sum()), 4), np.uint64)
+    pids = np.ascontiguousarray(ids[par])
+    ref.lib.ref_cellid_children(_p(pids), _sz(len(pids)), _p(wc)); assert (ch[par] == wc).all() and (ch[~par] == 0).all()
+
+
 def test_strict_host_libm_mode_logic_equals_reference(hostsim, ref):
     """The strict lat/lng mode (kernel filter -> correctly rounded ids -> host libm for the points whose leaf cell a 1-ulp
     change of sin/cos could move), restated on the host from the same headers: ids == the reference's S2CellId(S2LatLng)
