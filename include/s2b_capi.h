@@ -501,6 +501,17 @@ int s2b_closest_points_to_targets_dev(const S2bPointIndex* index, int target_kin
 int s2b_closest_points_to_shape_index(const S2bPointIndex* index, const S2bIndex* target, int include_interiors, int max_results,
                                       double max_length2, double max_error_radians, int32_t* data_out, double* length2_out,
                                       size_t capacity, size_t* total_out);
+/* The same computation seen from the other side: S2ClosestEdgeQuery(index).GetDistance(PointTarget(points[i])) for a batch
+ * (s2closest_edge_query.h; options include_interiors and max_distance). length2_out[i] = S1ChordAngle::length2() of the
+ * distance from points[i] to the index's geometry — 0 inside a polygon when include_interiors != 0, the minimum of
+ * S2::UpdateMinDistance over the index's edges otherwise, bit for bit — or INFINITY if that is not below max_length2
+ * (exclusive). The work grows with the number of (edge, point) pairs within the limit: pass a finite limit for large
+ * batches (INFINITY compares every edge with every point). Must be called with the index's device current; the _dev form
+ * takes device pointers and returns after the default stream has finished. */
+int s2b_index_point_distances(const S2bIndex* index, const double* xyz, size_t n, int include_interiors, double max_length2,
+                              double* length2_out);
+int s2b_index_point_distances_dev(const S2bIndex* index, const double* xyz_dev, size_t n, int include_interiors, double max_length2,
+                                  double* length2_out_dev);
 
 /* --------------------------------------------------------------------------------------------------
  * S2CellIndex joins, batch form (s2cell_index.h:113-441, s2cell_index.cc:71-163) and the S2RegionSharder built on it

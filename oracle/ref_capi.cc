@@ -26,6 +26,7 @@
 #include "s2/s2cell_index.h"
 #include "s2/s2cell_union.h"
 #include "s2/s2region_sharder.h"
+#include "s2/s2closest_edge_query.h"
 #include "s2/s2closest_point_query.h"
 #include "s2/s2point_index.h"
 #include "s2/s2contains_point_query.h"
@@ -798,6 +799,20 @@ void ref_cellid_next_prev(const uint64_t* ids, size_t n, uint64_t* next, uint64_
 }
 void ref_cellid_common_ancestor_level(const uint64_t* a, const uint64_t* b, size_t n, int8_t* out) {
   for (size_t i = 0; i < n; ++i) out[i] = (int8_t)S2CellId(a[i]).GetCommonAncestorLevel(S2CellId(b[i]));
+}
+// S2ClosestEdgeQuery(&index).GetDistance(PointTarget(p)).length2() per point (HUGE_VAL for S1ChordAngle::Infinity()).
+void ref_index_point_distances(void* index_h, const double* xyz, size_t n, int include_interiors, double max_distance_rad, double* out, int threads) {
+  auto& index = ((RefIndex*)index_h)->index;
+  ParallelFor(n, threads, [&](size_t b, size_t e, int) {
+    S2ClosestEdgeQuery query(&index);
+    query.mutable_options()->set_include_interiors(include_interiors != 0);
+    if (max_distance_rad >= 0) query.mutable_options()->set_max_distance(S1Angle::Radians(max_distance_rad));
+    for (size_t i = b; i < e; ++i) {
+      S2ClosestEdgeQuery::PointTarget target(P(xyz + 3 * i));
+      const S1ChordAngle d = query.GetDistance(&target);
+      out[i] = d.is_infinity() ? HUGE_VAL : d.length2();
+    }
+  });
 }
 double ref_chord_length2(double angle_rad) { return S1ChordAngle(S1Angle::Radians(angle_rad)).length2(); }
 

@@ -428,6 +428,13 @@ class RefIndex:
         self.lib.ref_shape_contains(_vp(self.h), shape_id, _p(xyz), _sz(len(xyz)), model, _p(out), threads)
         return out
 
+    def point_distances(self, xyz, max_distance_rad=-1.0, include_interiors=True, threads=0):
+        """S2ClosestEdgeQuery::GetDistance(PointTarget(p)).length2() per point (inf if not below max_distance)."""
+        xyz = np.ascontiguousarray(xyz, np.float64)
+        out = np.empty(len(xyz), np.float64)
+        self.lib.ref_index_point_distances(_vp(self.h), _p(xyz), _sz(len(xyz)), 1 if include_interiors else 0, ctypes.c_double(max_distance_rad), _p(out), int(threads))
+        return out
+
     def shape_histogram(self, xyz, model=1, threads=0):
         xyz = np.ascontiguousarray(xyz, np.float64)
         out = np.zeros(self.num_shape_ids, np.uint64)

@@ -78,6 +78,8 @@ SIGNATURES = {
     "s2b_closest_points_to_targets": (_i, [_vp, _i, _vp, _sz, _i, ctypes.c_double, ctypes.c_double, _vp, _vp, _vp]),
     "s2b_closest_points_to_targets_dev": (_i, [_vp, _i, _vp, _sz, _i, ctypes.c_double, ctypes.c_double, _vp, _vp, _vp, _vp]),
     "s2b_closest_points_to_shape_index": (_i, [_vp, _vp, _i, _i, ctypes.c_double, ctypes.c_double, _vp, _vp, _sz, _vp]),
+    "s2b_index_point_distances": (_i, [_vp, _vp, _sz, _i, ctypes.c_double, _vp]),
+    "s2b_index_point_distances_dev": (_i, [_vp, _vp, _sz, _i, ctypes.c_double, _vp]),
     "s2b_cell_index_create": (_i, [_vp, _vp, _sz, _vp]),
     "s2b_cell_index_destroy": (None, [_vp]),
     "s2b_cell_index_info": (_i, [_vp, _vp, _vp, _vp]),

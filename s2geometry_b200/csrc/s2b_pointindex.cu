@@ -478,6 +478,13 @@ __global__ void count_below_sorted_kernel(const unsigned long long* __restrict__
   if (i < n && keys[i] < limit && (i + 1 == n || keys[i + 1] >= limit)) *total = i + 1;
 }
 
+// out[data[c]] = the distance recorded for sorted point c (+inf where nothing within the limit was found)
+__global__ void scatter_distances_kernel(const unsigned long long* __restrict__ bits, const int32_t* __restrict__ data, size_t n,
+                                         unsigned long long limit_bits, double* __restrict__ out) {
+  const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n) out[data[c]] = bits[c] < limit_bits ? __longlong_as_double((long long)bits[c]) : HUGE_VAL;
+}
+
 // kMinWidth (quadratic projection, s2metrics.cc:54-58) and Metric::GetLevelForMinValue (s2metrics.h:185-200).
 const double kMinWidthDeriv = 2 * std::sqrt(2.0) / 3;
 int level_for_min_width(double value) {
@@ -571,7 +578,7 @@ int s2b_point_index_create(const double* xyz, size_t m, S2bPointIndex** out) {
   e = cudaMalloc((void**)&tmp, o_sort + up(t_sort));
   int rc = S2B_OK;
   if (e != cudaSuccess) rc = cuda_fail(e, "cudaMalloc(point index build)");
-  if (rc == S2B_OK && (e = cudaMemcpy(tmp, xyz, 24 * m, cudaMemcpyHostToDevice)) != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy(points)");
+  if (rc == S2B_OK && (e = cudaMemcpy(tmp, xyz, 24 * m, cudaMemcpyDefault)) != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy(points)");
   if (rc == S2B_OK) {
     EncodeOut eo{};
     eo.levels.n = 1; eo.levels.level[0] = 30;
@@ -955,6 +962,58 @@ int s2b_closest_points_to_shape_index(const S2bPointIndex* pix, const S2bIndex* 
     if (e != cudaSuccess) return done(cuda_fail(e, "cudaMemcpy"));
   }
   return done(total > capacity ? set_error(S2B_ECAPACITY, "%llu results, capacity %zu", total, capacity) : S2B_OK);
+}
+
+
+// S2ClosestEdgeQuery(index).GetDistance(PointTarget(points[i])) for a batch (s2closest_edge_query.h:301-318; options
+// include_interiors and max_distance): the ShapeIndexTarget machinery above run over a temporary point index of the batch
+// (cell-sorted points; every clipped edge of the index scans its candidates within the limit and keeps the per-point
+// minimum), then scattered back to the caller's order. xyz / length2_out: both host or both device pointers.
+static int point_distances(const S2bIndex* target, const double* xyz, size_t n, int include_interiors, double max_length2, double* out, bool device_out) {
+  if (!target) return set_error(S2B_EINVAL, "null index");
+  if (std::isnan(max_length2)) return set_error(S2B_EINVAL, "max_length2 is NaN");
+  if (n == 0) return S2B_OK;
+  if (!xyz || !out) return set_error(S2B_EINVAL, "null pointer");
+  S2bPointIndex* pix = nullptr;
+  int rc = s2b_point_index_create(xyz, n, &pix);
+  if (rc != S2B_OK) return rc;
+  if (pix->device != target->device) { s2b_point_index_destroy(pix); return set_error(S2B_EINVAL, "the current device (%d) is not the index's device (%d)", pix->device, target->device); }
+  unsigned long long* bits = nullptr;
+  double* out_dev = device_out ? out : nullptr;
+  uint8_t* flags = nullptr;
+  cudaError_t e = cudaMalloc((void**)&bits, 8 * n);
+  if (e == cudaSuccess && !device_out) e = cudaMalloc((void**)&out_dev, 8 * n);
+  if (e == cudaSuccess && include_interiors) e = cudaMalloc((void**)&flags, n);
+  auto done = [&](int code) { cudaFree(bits); if (!device_out) cudaFree(out_dev); cudaFree(flags); s2b_point_index_destroy(pix); return code; };
+  if (e != cudaSuccess) return done(cuda_fail(e, "cudaMalloc"));
+  const int blocks = (int)((n + 255) / 256);
+  cudaStream_t st = nullptr;
+  fill_u64_kernel<<<blocks, 256, 0, st>>>(bits, n, kInfBits);
+  count_launch();
+  if (max_length2 > 0) {
+    if (include_interiors && target->view.num_cells > 0) {
+      rc = s2b_contains_dev(target, pix->pts, n, S2B_VERTEX_MODEL_SEMI_OPEN, flags, st);
+      if (rc != S2B_OK) return done(rc);
+      zero_where_flag_kernel<<<blocks, 256, 0, st>>>(bits, flags, n);
+      count_launch();
+    }
+    if (target->num_edges > 0) {
+      rc = launch_closest_targets(pix, kTargetEdge, target->view.edges, (size_t)target->num_edges, 0, max_length2, nullptr, nullptr, nullptr, bits, st);
+      if (rc != S2B_OK) return done(rc);
+    }
+  }
+  scatter_distances_kernel<<<blocks, 256, 0, st>>>(bits, pix->data, n, kInfBits, out_dev);
+  count_launch();
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = device_out ? cudaStreamSynchronize(st) : cudaMemcpy(out, out_dev, 8 * n, cudaMemcpyDeviceToHost);
+  return done(e == cudaSuccess ? S2B_OK : cuda_fail(e, "point distances"));
+}
+
+int s2b_index_point_distances(const S2bIndex* index, const double* xyz, size_t n, int include_interiors, double max_length2, double* length2_out) {
+  return point_distances(index, xyz, n, include_interiors, max_length2, length2_out, false);
+}
+int s2b_index_point_distances_dev(const S2bIndex* index, const double* xyz_dev, size_t n, int include_interiors, double max_length2, double* length2_out_dev) {
+  return point_distances(index, xyz_dev, n, include_interiors, max_length2, length2_out_dev, true);
 }
 
 }  // extern "C"

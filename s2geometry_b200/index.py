@@ -11,6 +11,7 @@ walking a reference-built index through its public iterator or 
 """
 import ctypes
 import enum
+import math
 
 import numpy as np
 
@@ -236,6 +237,22 @@ class ShapeIndex:
         rel = np.empty(ids.size, np.uint8); cell = np.empty(ids.size, np.int32)
         _lib.check(self._lib.s2b_index_locate_cells(self._h, _ptr(ids), ids.size, _ptr(rel), _ptr(cell)))
         return rel, cell
+
+    def point_distances(self, xyz, max_distance_rad=math.inf, include_interiors=True):
+        """S2ClosestEdgeQuery(index).GetDistance(PointTarget(p)) per point as S1ChordAngle::length2() (0 inside polygons when
+        include_interiors; inf where the distance is not below max_distance_rad)."""
+        p = _points(xyz)
+        n = p.shape[0]
+        limit2 = math.inf if math.isinf(max_distance_rad) else (2.0 * math.sin(0.5 * min(max_distance_rad, math.pi))) ** 2
+        if _is_tensor(p):
+            out = torch.empty(n, dtype=torch.float64, device=p.device)
+            with torch.cuda.device(p.device):
+                torch.cuda.current_stream().synchronize()
+                _lib.check(self._lib.s2b_index_point_distances_dev(self._h, _ptr(p), n, 1 if include_interiors else 0, limit2, _ptr(out)))
+            return out
+        out = np.empty(n, np.float64)
+        _lib.check(self._lib.s2b_index_point_distances(self._h, _ptr(p), n, 1 if include_interiors else 0, limit2, _ptr(out)))
+        return out
 
     def info(self):
         c = ctypes.c_uint64(); k = ctypes.c_uint64(); e = ctypes.c_uint64(); s = ctypes.c_int32(); b = ctypes.c_uint64()

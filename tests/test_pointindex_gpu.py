@@ -283,3 +283,36 @@ def test_shape_index_target_matches_reference(torch_cuda, ref):
         assert len(got[0]) == len(small_pts)
         _same_results(got, want, truncated=False)
         six.close()
+
+
+def test_point_distances_to_a_shape_index_match_the_reference_edge_query(torch_cuda, ref):
+    """S2ClosestEdgeQuery::GetDistance(PointTarget(p)) for batches of points (s2b_index_point_distances): polygons with
+    holes + a polyline + a point shape, with and without interiors, several distance limits and none, host and device
+    arrays — bit-identical distances (and the same points beyond the limit)."""
+    torch = torch_cuda
+    from s2geometry_b200.index import ShapeIndex, build_flat_index
+    from s2geometry_b200.shapes import ShapeSoup
+    soup = ShapeSoup()
+    for loops in synth.many_polygons(60, 21, min_vertices=8, max_vertices=90, min_radius_km=150.0, max_radius_km=1200.0):
+        soup.add_polygon(loops)
+    c = np.array([0.3, -0.5, 0.8]) / np.linalg.norm([0.3, -0.5, 0.8])
+    soup.add_polyline(synth.cap_points(c, 0.3, 40, 5))
+    soup.add_points(synth.sphere_points(25, 6))
+    soup = soup.freeze()
+    rsi = ref.index_create(soup)
+    pts = np.concatenate([synth.sphere_points(200_000, 41), synth.cap_points(c, 0.4, 100_000, 42), soup.vertices[::5]])
+    th = ref.hardware_threads()
+    for max_edges in (0, 1):
+        six = ShapeIndex(build_flat_index(soup, max_edges))
+        for r, interiors in ((0.003, True), (0.05, True), (0.05, False), (1e-9, True), (0.5, True)):
+            want = rsi.point_distances(pts, r, interiors, th)
+            got = six.point_distances(pts, r, interiors)
+            assert (got.view(np.uint64) == want.view(np.uint64)).all(), (max_edges, r, interiors, int((got != want).sum()))
+            assert np.isinf(want).any() and (want == 0).sum() > (5000 if interiors else 100)   # inside polygons / on vertices
+        dev = six.point_distances(torch.from_numpy(pts).cuda(), 0.05, True).cpu().numpy()
+        assert (dev.view(np.uint64) == rsi.point_distances(pts, 0.05, True, th).view(np.uint64)).all()
+        small = pts[::150]
+        want = rsi.point_distances(small, -1.0, True, th)                     # no limit: every point gets its distance
+        got = six.point_distances(small)
+        assert (got.view(np.uint64) == want.view(np.uint64)).all() and np.isfinite(got).all()
+        six.close()
