@@ -396,14 +396,18 @@ __global__ void __launch_bounds__(kThreads)
 closest_targets_kernel(const IndexView ix, const void* __restrict__ targets, size_t n, int k, int start_level, double limit2, double limit_angle,
                        const double* __restrict__ covered_angle /* [31]: entry L+1 = angle of the cap covered at level L */,
                        int32_t* __restrict__ data_out, double* __restrict__ length2_out, uint32_t* __restrict__ count_out,
-                       unsigned long long* __restrict__ min_bits /* nullable, k == 0: min_bits[c] = min(min_bits[c], bits of the distance) */) {
+                       unsigned long long* __restrict__ min_bits /* nullable, k == 0: min_bits[c] = min(min_bits[c], bits of the distance) */,
+                       int lane_shift /* with min_bits: 2^lane_shift neighbouring lanes share one target and split its candidates */) {
   __shared__ uint16_t s_pos[1024], s_ij[1024];
   __shared__ double s_cov[31];
   for (int q = threadIdx.x; q < 1024; q += kThreads) { s_pos[q] = g_hilbert_pi.pos[q]; s_ij[q] = g_hilbert_pi.ij[q]; }
   if (threadIdx.x < 31) s_cov[threadIdx.x] = covered_angle[threadIdx.x];
   __syncthreads();
   const size_t stride = (size_t)gridDim.x * kThreads;
-  for (size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x; t < n; t += stride) {
+  const uint32_t sub_step = 1u << lane_shift;
+  for (size_t gt = (size_t)blockIdx.x * kThreads + threadIdx.x; (gt >> lane_shift) < n; gt += stride) {
+    const size_t t = gt >> lane_shift;
+    const uint32_t lane_off = (uint32_t)gt & (sub_step - 1u);
     const TargetGeom g = load_target<kKind>(targets, t, s_ij);
     double fi, fj;
     const int face = point_to_face_fij(g.center, &fi, &fj);
@@ -412,6 +416,7 @@ closest_targets_kernel(const IndexView ix, const void* __restrict__ targets, siz
     int level = start_level;
     while (level >= 0 && !(s_cov[level + 1] > g.rho)) --level;
     const double need = limit_angle + g.rho;     // the covering that contains everything within the limit
+    const double rc = g.rho >= 3.14 ? 4.0 : 2.0 * sin(0.5 * g.rho) * (1 + 1e-9);   // chord length of the bounding cap's radius
     if (k == 0) { while (level >= 0 && !(s_cov[level + 1] >= need)) --level; }
     double dist[kMaxResults];
     int32_t data[kMaxResults];
@@ -424,13 +429,28 @@ closest_targets_kernel(const IndexView ix, const void* __restrict__ targets, siz
       for (int c6 = 0; c6 < nc; ++c6) {
         uint32_t first, last;
         cell_range(ix, cells[c6], &first, &last);
-        for (uint32_t c = first; c < last; ++c) {
+        for (uint32_t c = first + lane_off; c < last; c += sub_step) {
           const double* pp = ix.pts + 3 * (size_t)c;
+          const P3 p{pp[0], pp[1], pp[2]};
           double d;
+          if (min_bits) {
+            // Per-point minimum over many targets: the point's current best (possibly stale: that only weakens the pruning)
+            // bounds what this target still has to beat, as S2ClosestEdgeQuery's shrinking max_distance does. A target
+            // whose bounding ball — centre g.center, chord radius rc — is further away than that is skipped after ~12
+            // operations: |p - x| >= |p - centre| - rc for every point x of the target.
+            const double cur = __longlong_as_double((long long)min_bits[c]);
+            const double beat = cur < limit2 ? cur : limit2;
+            const double dc2 = norm2(sub(p, g.center));
+            const double reach = rc + (double)(__fsqrt_ru((float)beat) * 1.000001f) + 1e-12;
+            if (beat < 4.0 && dc2 * (1 - 1e-6) >= reach * reach) continue;
+            if (!target_distance<kKind>(g, p, beat, &d)) continue;
+            ++total;
+            atomicMin(min_bits + c, (unsigned long long)__double_as_longlong(d));   // d >= 0: bit order = numeric order
+            continue;
+          }
           // with a full result set the reference's limit is the k-th distance; ties are then resolved on the data value below
-          if (!target_distance<kKind>(g, P3{pp[0], pp[1], pp[2]}, limit2, &d)) continue;
+          if (!target_distance<kKind>(g, p, limit2, &d)) continue;
           ++total;
-          if (min_bits) atomicMin(min_bits + c, (unsigned long long)__double_as_longlong(d));   // d >= 0: bit order = numeric order
           if (k == 0) continue;
           const int32_t dv = ix.data[c];
           if (cnt == k && !(d < dist[k - 1] || (d == dist[k - 1] && dv < data[k - 1]))) continue;
@@ -788,13 +808,22 @@ static int launch_closest_targets(const S2bPointIndex* ix, int target_kind, cons
   if (max_results == 0) start = 29;
   const double limit_angle = max_length2 >= 4.0 ? 4.0 : angle_of_length2(max_length2 > 0 ? max_length2 : 0.0);   // 4 > pi: "no limit"
   const IndexView v{ix->ids, ix->pts, ix->data, ix->first, (uint32_t)ix->m, 61 - 2 * ix->table_level};
-  const int grid = grid_for_pi(n, (const void*)closest_targets_kernel<kTargetEdge>);
+  // Per-point minima over many targets (min_bits): a target's candidates are independent, so a group of neighbouring lanes
+  // shares one target and strides its candidate ranges (coalesced, and parallelism no longer ends at the number of
+  // targets). Group size from the expected number of candidates per target: m * (limit angle)^2 / 4 on a uniform sphere.
+  int lane_shift = 0;
+  if (min_bits) {
+    const double la = limit_angle > 3.2 ? 3.2 : limit_angle;
+    const double expected = (double)ix->m * la * la / 4.0;
+    lane_shift = expected >= 256 ? 5 : (expected >= 32 ? 3 : 0);
+  }
+  const int grid = grid_for_pi(n << lane_shift, (const void*)closest_targets_kernel<kTargetEdge>);
   if (target_kind == kTargetPoint)
-    closest_targets_kernel<kTargetPoint><<<grid, kThreads, 0, st>>>(v, targets_dev, n, max_results, start, max_length2, limit_angle, cov_dev, data_out_dev, length2_out_dev, count_out_dev, min_bits);
+    closest_targets_kernel<kTargetPoint><<<grid, kThreads, 0, st>>>(v, targets_dev, n, max_results, start, max_length2, limit_angle, cov_dev, data_out_dev, length2_out_dev, count_out_dev, min_bits, lane_shift);
   else if (target_kind == kTargetEdge)
-    closest_targets_kernel<kTargetEdge><<<grid, kThreads, 0, st>>>(v, targets_dev, n, max_results, start, max_length2, limit_angle, cov_dev, data_out_dev, length2_out_dev, count_out_dev, min_bits);
+    closest_targets_kernel<kTargetEdge><<<grid, kThreads, 0, st>>>(v, targets_dev, n, max_results, start, max_length2, limit_angle, cov_dev, data_out_dev, length2_out_dev, count_out_dev, min_bits, lane_shift);
   else
-    closest_targets_kernel<kTargetCell><<<grid, kThreads, 0, st>>>(v, targets_dev, n, max_results, start, max_length2, limit_angle, cov_dev, data_out_dev, length2_out_dev, count_out_dev, min_bits);
+    closest_targets_kernel<kTargetCell><<<grid, kThreads, 0, st>>>(v, targets_dev, n, max_results, start, max_length2, limit_angle, cov_dev, data_out_dev, length2_out_dev, count_out_dev, min_bits, lane_shift);
   count_launch();
   e = cudaGetLastError();
   cudaFreeAsync(cov_dev, st);
