@@ -583,8 +583,15 @@ static int grid_for_ix(size_t n, const void* kernel) {
   return (int)(want < cap ? (want ? want : 1) : cap);
 }
 
-// Points per phase-A/phase-B round: bounds the work list (8 B per point in the worst case) at 512 MB.
-constexpr size_t kRoundPoints = size_t(1) << 26;
+// Points per phase-A/phase-B round. A round is ~8 launches of persistent kernels, each with a tail in which SMs idle, so few
+// large rounds beat many small ones: measured on the 1B-point join, 2^25 / 2^26 / 2^27 / 2^28 / 2^29 points per round give
+// 68 / 81 / 90 / 96 / 98 Gpts/s. 2^28 needs 24 B of scratch per point of the round in the worst case (work list 10.7 B,
+// cell-sorted copy 8 B, undecided list 5.3 B: 6.4 GB), so the round shrinks when the allocation fails.
+#ifndef S2B_ROUND_BITS
+#define S2B_ROUND_BITS 28
+#endif
+constexpr size_t kRoundPoints = size_t(1) << S2B_ROUND_BITS;
+constexpr size_t kMinRoundPoints = size_t(1) << 22;
 
 // The work list comes from the stream-ordered allocator; keep freed blocks cached in the pool (the default release
 // threshold of 0 hands them back to the driver at every synchronisation, which costs milliseconds per call).
@@ -624,14 +631,11 @@ static cudaError_t launch_query_t(const FlatIndexView& ix, const double* xyz, si
     cudaError_t te = ensure_wide_table_ix();
     if (te != cudaSuccess) return te;
   }
-  const size_t round = n < kRoundPoints ? n : kRoundPoints;
   HitWork* work = nullptr;
   unsigned int* counter = nullptr;
   // worst-case slot consumption (work_list_capacity): two lists x the warps of the two phase-A kernels (<= 6 + 4 CTAs
   // per SM); the undecided list is written by the pre-filter's warps only
   const size_t max_warps = (size_t)sm_count() * 8 * (kThreads / 32);
-  const size_t capacity = work_list_capacity(round, 4 * max_warps);
-  const size_t unc_capacity = work_list_capacity(round, max_warps);
   const bool use_fast = !g_force_exact_locate && ((uintptr_t)xyz % 16 == 0);   // cp.async staging needs 16-byte alignment
   // cell-major ordering of the edge hits pays off when the index is too large to stay cache resident and has enough
   // cells for the per-cell atomics not to collide (S2B_SORT_BY_CELL=0/1 overrides)
@@ -641,10 +645,21 @@ static cudaError_t launch_query_t(const FlatIndexView& ix, const double* xyz, si
   size_t scan_tmp_bytes = 0;
   if (sort_by_cell) cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp_bytes, (unsigned int*)nullptr, (unsigned int*)nullptr, (int)(C + 1), st);
   auto up256 = [](size_t v) { return (v + 255) / 256 * 256; };
-  const size_t b_work = up256(sizeof(HitWork) * capacity), b_counter = 256, b_unc = use_fast ? up256(sizeof(uint32_t) * unc_capacity) : 0,
-               b_sorted = sort_by_cell ? up256(sizeof(HitWork) * round) : 0, b_cells = sort_by_cell ? up256(sizeof(unsigned int) * (C + 1)) : 0,
-               b_scan = sort_by_cell ? up256(scan_tmp_bytes) : 0;
-  cudaError_t e = cudaMallocAsync((void**)&work, b_work + b_counter + b_unc + b_sorted + b_cells + b_scan, st);
+  size_t round = n < kRoundPoints ? n : kRoundPoints;
+  size_t capacity = 0, b_work = 0, b_unc = 0, b_sorted = 0;
+  const size_t b_counter = 256, b_cells = sort_by_cell ? up256(sizeof(unsigned int) * (C + 1)) : 0, b_scan = sort_by_cell ? up256(scan_tmp_bytes) : 0;
+  cudaError_t e;
+  for (;;) {
+    capacity = work_list_capacity(round, 4 * max_warps);
+    const size_t unc_capacity = work_list_capacity(round, max_warps);
+    b_work = up256(sizeof(HitWork) * capacity);
+    b_unc = use_fast ? up256(sizeof(uint32_t) * unc_capacity) : 0;
+    b_sorted = sort_by_cell ? up256(sizeof(HitWork) * round) : 0;
+    e = cudaMallocAsync((void**)&work, b_work + b_counter + b_unc + b_sorted + b_cells + b_scan, st);
+    if (e != cudaErrorMemoryAllocation || round <= kMinRoundPoints) break;
+    cudaGetLastError();                                         // not enough memory for this round size: halve it
+    round = (round + 1) / 2;
+  }
   if (e != cudaSuccess) return e;
   counter = (unsigned int*)((char*)work + b_work);   // [0] edge slots, [1] interior slots, [2] undecided points
   HitWork* sorted = (HitWork*)((char*)counter + b_counter + b_unc);
