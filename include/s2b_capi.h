@@ -356,7 +356,10 @@ int s2b_index_info(const S2bIndex* index, uint64_t* num_cells, uint64_t* num_cli
                    int32_t* num_shape_ids, uint64_t* device_bytes);
 
 /* S2ContainsPointQuery<S2ShapeIndex>(index, vertex_model).Contains(p)  (s2contains_point_query.h:255-265):
- * out[i] = 1 if any shape contains point i. Locate = s2cell_iterator.h:137-155. */
+ * out[i] = 1 if any shape contains point i. Locate = s2cell_iterator.h:137-155.
+ * Scratch: the point queries of this section take their work lists from the device's stream-ordered memory pool
+ * (cudaMallocAsync on the call's stream, kept cached in the pool afterwards): at most 24 bytes per point of a round of up
+ * to 2^28 points (6.4 GB), less when that much cannot be allocated. */
 int s2b_contains(const S2bIndex* index, const double* xyz, size_t n, int vertex_model, uint8_t* out);
 int s2b_contains_dev(const S2bIndex* index, const double* xyz_dev, size_t n, int vertex_model, uint8_t* out_dev, void* stream);
 
