@@ -207,14 +207,14 @@ locate_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint32_t n
     }
 #pragma unroll
     for (int t = 0; t < kP; ++t)
-      e0[t] = (have_cells && idx[t] != 0xFFFFFFFFu) ? ix.lut[lut_bucket(ix.lut_level, face[t], ci[t], cj[t])] : kLutEmpty;
+      e0[t] = (have_cells && idx[t] != 0xFFFFFFFFu) ? __ldcg(ix.lut + lut_bucket(ix.lut_level, face[t], ci[t], cj[t])) : kLutEmpty;
     // stage 3: candidate ranges of the mixed buckets; stage 4: their leaf ids
     uint32_t lo[kP], hi[kP];
     uint64_t leaf[kP];
 #pragma unroll
     for (int t = 0; t < kP; ++t) {
       lo[t] = hi[t] = 0;
-      if ((e0[t] & ~kLutIndexMask) == kLutMixed) { const LutRange r = ix.mixed[e0[t] & kLutIndexMask]; lo[t] = r.lo; hi[t] = r.hi; }
+      if ((e0[t] & ~kLutIndexMask) == kLutMixed) { const uint2 r = __ldcg((const uint2*)ix.mixed + (e0[t] & kLutIndexMask)); lo[t] = r.x; hi[t] = r.y; }
     }
 #pragma unroll
     for (int t = 0; t < kP; ++t)
