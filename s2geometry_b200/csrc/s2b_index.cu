@@ -207,14 +207,14 @@ locate_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint32_t n
     }
 #pragma unroll
     for (int t = 0; t < kP; ++t)
-      e0[t] = (have_cells && idx[t] != 0xFFFFFFFFu) ? __ldcg(ix.lut + lut_bucket(ix.lut_level, face[t], ci[t], cj[t])) : kLutEmpty;
+      e0[t] = (have_cells && idx[t] != 0xFFFFFFFFu) ? ix.lut[lut_bucket(ix.lut_level, face[t], ci[t], cj[t])] : kLutEmpty;
     // stage 3: candidate ranges of the mixed buckets; stage 4: their leaf ids
     uint32_t lo[kP], hi[kP];
     uint64_t leaf[kP];
 #pragma unroll
     for (int t = 0; t < kP; ++t) {
       lo[t] = hi[t] = 0;
-      if ((e0[t] & ~kLutIndexMask) == kLutMixed) { const uint2 r = __ldcg((const uint2*)ix.mixed + (e0[t] & kLutIndexMask)); lo[t] = r.x; hi[t] = r.y; }
+      if ((e0[t] & ~kLutIndexMask) == kLutMixed) { const LutRange r = ix.mixed[e0[t] & kLutIndexMask]; lo[t] = r.lo; hi[t] = r.hi; }
     }
 #pragma unroll
     for (int t = 0; t < kP; ++t)
@@ -358,9 +358,7 @@ locate_fast_kernel(const FlatIndexView ix, const double* __restrict__ xyz, uint3
       bool certain = valid & ((ufi | ufj) < (1u << 30)) & (max(ri - (uint32_t)kFastRadius, rj - (uint32_t)kFastRadius) <= margin_span);
       // the table is addressed by (face, i, j) of the bucket: no Hilbert encoding on this path. The masked coordinates
       // always give a valid bucket, so the read is unconditional (no branch around it).
-      // (ld.global.cg: the gather has no reuse in the L1 — hit rate 2.5 % — so it is cached in the L2 only: +2 %. Evict-first
-      // (.cs) instead throws the table out of the L2: 62 vs 157 Gpts/s.)
-      const uint32_t e0 = __ldcg(ix.lut + lut_bucket(lut_level, face, ufi & 0x3FFFFFFFu, ufj & 0x3FFFFFFFu));
+      const uint32_t e0 = ix.lut[lut_bucket(lut_level, face, ufi & 0x3FFFFFFFu, ufj & 0x3FFFFFFFu)];
       // Everything a decided point needs is in the table entry (no second load unless its cell is a pure interior cell
       // with several clipped shapes). The top three bits of the entry (kind, has-edges) index a packed 2-bit table of
       // hit kinds: mixed -> none (undecided), empty -> none, inside/no edges -> kHitCell, inside/edges -> kHitEdges,
