@@ -37,6 +37,12 @@ struct FlatIndexView {
   uint32_t num_cells;
   int lut_level;                   // 2..10: buckets are the cells of this level
   int num_shape_ids;
+  // Optional (device indexes): a Hilbert-order bucket table over cell_ids for Locate(S2CellId) — id_first[b] = number of
+  // cells whose id >> id_shift is below b (id_buckets + 1 entries) — so that a target cell is located with one table read and
+  // a search inside one bucket instead of a binary search over all cells.
+  const uint32_t* id_first = nullptr;
+  uint32_t id_buckets = 0;
+  int id_shift = 0;
 };
 
 enum VertexModel { kOpen = 0, kSemiOpen = 1, kClosed = 2 };

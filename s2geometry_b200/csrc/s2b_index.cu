@@ -756,8 +756,21 @@ int s2b_index_create(const S2bFlatIndex* f, S2bIndex** out) {
   auto align = [](size_t v) { return (v + 255) / 256 * 256; };
   size_t o_ids = 0, o_cells = o_ids + align(8 * (C + 1)), o_clips = o_cells + align(sizeof(FlatCell) * (C + 1)),
          o_edges = o_clips + align(sizeof(FlatClip) * (K + 1)), o_lut = o_edges + align(sizeof(FlatEdge) * (E + 1)),
-         o_mixed = o_lut + align(4 * nb), o_kind = o_mixed + align(sizeof(LutRange) * M), o_view = o_kind + align(4 * (C + 1)),
-         total = o_view + align(sizeof(FlatIndexView));
+         o_mixed = o_lut + align(4 * nb), o_kind = o_mixed + align(sizeof(LutRange) * M), o_idtab = o_kind + align(4 * (C + 1));
+  // Hilbert-order bucket table over the cell ids (Locate(S2CellId), s2b_region.cuh): about two buckets per cell
+  int id_level = 0;
+  while (id_level < 11 && (size_t)(6u << (2 * id_level)) < 2 * C) ++id_level;
+  const uint32_t id_buckets = 6u << (2 * id_level);
+  const int id_shift = 61 - 2 * id_level;
+  std::vector<uint32_t> id_first((size_t)id_buckets + 1, 0);
+  {
+    size_t k = 0;
+    for (uint32_t b = 0; b <= id_buckets; ++b) {
+      while (k < C && (f->cell_ids[k] >> id_shift) < b) ++k;
+      id_first[b] = (uint32_t)k;
+    }
+  }
+  size_t o_view = o_idtab + align(4 * ((size_t)id_buckets + 1)), total = o_view + align(sizeof(FlatIndexView));
   e = cudaMalloc(&ix->blob, total);
   if (e != cudaSuccess) { delete ix; return cuda_fail(e, "cudaMalloc(index)"); }
   ix->blob_bytes = total;
@@ -770,6 +783,7 @@ int s2b_index_create(const S2bFlatIndex* f, S2bIndex** out) {
   ok &= cudaMemcpy(base + o_lut, lut.data(), 4 * nb, cudaMemcpyHostToDevice) == cudaSuccess;
   ok &= cudaMemcpy(base + o_mixed, hf.mixed.data(), sizeof(LutRange) * M, cudaMemcpyHostToDevice) == cudaSuccess;
   ok &= cudaMemcpy(base + o_kind, hf.interior_info.data(), 4 * (C + 1), cudaMemcpyHostToDevice) == cudaSuccess;
+  ok &= cudaMemcpy(base + o_idtab, id_first.data(), 4 * id_first.size(), cudaMemcpyHostToDevice) == cudaSuccess;
   if (!ok) { e = cudaGetLastError(); cudaFree(ix->blob); delete ix; return cuda_fail(e, "cudaMemcpy(index)"); }
   ix->view.cell_ids = (const uint64_t*)(base + o_ids);
   ix->view.cells = (const FlatCell*)(base + o_cells);
@@ -778,6 +792,9 @@ int s2b_index_create(const S2bFlatIndex* f, S2bIndex** out) {
   ix->view.lut = (const uint32_t*)(base + o_lut);
   ix->view.mixed = (const LutRange*)(base + o_mixed);
   ix->view.interior_info = (const int32_t*)(base + o_kind);
+  ix->view.id_first = (const uint32_t*)(base + o_idtab);
+  ix->view.id_buckets = id_buckets;
+  ix->view.id_shift = id_shift;
   ix->view.num_cells = (uint32_t)C;
   ix->view.lut_level = hf.lut_level;
   ix->view.num_shape_ids = f->num_shape_ids;

@@ -243,7 +243,7 @@ int s2b_index_replicate(S2bIndex* ix, const int* devices, int ndev) {
       const ptrdiff_t shift = (char*)r->blob - (char*)ix->blob;
       auto rebase = [shift](auto*& p) { p = (std::remove_reference_t<decltype(p)>)((char*)p + shift); };
       rebase(r->view.cell_ids); rebase(r->view.cells); rebase(r->view.clips); rebase(r->view.edges);
-      rebase(r->view.lut); rebase(r->view.mixed); rebase(r->view.interior_info); rebase(r->view_dev);
+      rebase(r->view.lut); rebase(r->view.mixed); rebase(r->view.interior_info); rebase(r->view.id_first); rebase(r->view_dev);
       e = cudaMemcpy((void*)r->view_dev, &r->view, sizeof r->view, cudaMemcpyHostToDevice);
       if (e == cudaSuccess && ix->edge_ids) {
         e = cudaMalloc((void**)&r->edge_ids, sizeof(int32_t) * (ix->num_edges ? ix->num_edges : 1));

@@ -19,6 +19,7 @@
 #include "s2b_index_handle.h"
 #include "s2b_internal.h"
 #include "s2b_region.cuh"
+#include "s2b_stream.cuh"
 
 using namespace s2b;
 
@@ -60,6 +61,7 @@ region_classify_kernel(const FlatIndexView ix, const uint64_t* __restrict__ targ
                        uint64_t* __restrict__ work, unsigned int* __restrict__ work_count) {
   const uint32_t stride = gridDim.x * 256u;
   const unsigned lane = threadIdx.x & 31u;
+  U64Slots slots;
   for (uint64_t base = (uint64_t)blockIdx.x * 256u + (threadIdx.x & ~31u); base < n; base += stride) {
     const uint64_t t = base + lane;
     bool hard = false;
@@ -86,14 +88,11 @@ region_classify_kernel(const FlatIndexView ix, const uint64_t* __restrict__ targ
       }
       if (!hard) out[t] = r;
     }
-    const unsigned m = __ballot_sync(0xffffffffu, hard);
-    if (m) {
-      unsigned first = 0;
-      if (lane == 0) first = atomicAdd(work_count, (unsigned)__popc(m));
-      first = __shfl_sync(0xffffffffu, first, 0);
-      if (hard) work[first + __popc(m & ((1u << lane) - 1))] = (t << 32) | (uint32_t)at;
-    }
+    // slots are reserved per warp in chunks (one same-address atomic per warp iteration serialises at the L2: 625k of them
+    // per 20M targets were most of this kernel's time); unused slots of a chunk hold the sentinel ~0
+    slots.append(hard, (unsigned long long)((t << 32) | (uint32_t)at), (unsigned long long*)work, work_count, lane);
   }
+  slots.finish((unsigned long long*)work, lane);
 }
 
 template <int kMode>
@@ -106,6 +105,7 @@ region_process_kernel(const FlatIndexView ix, const uint64_t* __restrict__ targe
   const unsigned stride = gridDim.x * kThreads;
   for (unsigned w = blockIdx.x * kThreads + threadIdx.x; w < count; w += stride) {
     const uint64_t item = work[w];
+    if (item == ~0ull) continue;                                 // unused slot of a reservation chunk
     const uint64_t t = item >> 32;
     const uint32_t at = (uint32_t)item;
     const uint64_t target = targets[t];
@@ -291,7 +291,12 @@ int region_cells_dev(const S2bIndex* ix, const uint64_t* ids_dev, size_t n, uint
   keep_pool_memory_once();
   const size_t round = n < kRegionRound ? n : kRegionRound;
   void* scratch = nullptr;
-  cudaError_t e = cudaMallocAsync(&scratch, 8 * round + 256, st);
+  // slots: a chunk of kSlotChunk holds at least kSlotChunk - 31 items, every warp leaves at most one partly used chunk
+  int per_sm_c = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_c, (const void*)region_classify_kernel<kMode>, 256, 0);
+  const size_t warps = (size_t)sm_count() * (per_sm_c < 1 ? 1 : per_sm_c) * 8;
+  const size_t slots_cap = kSlotChunk * (round / (kSlotChunk - 31) + 2 + warps);
+  cudaError_t e = cudaMallocAsync(&scratch, 8 * slots_cap + 256, st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync(region work list)");
   uint64_t* work = (uint64_t*)((char*)scratch + 256);
   unsigned int* work_count = (unsigned int*)scratch;
@@ -308,7 +313,7 @@ int region_cells_dev(const S2bIndex* ix, const uint64_t* ids_dev, size_t n, uint
   void* sort_tmp = nullptr;
   uint64_t* sorted = nullptr;
   size_t sort_bytes = 0;
-  cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, work, work, round, 0, cell_bits, st);
+  cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, work, work, slots_cap, 0, cell_bits, st);
   for (size_t off = 0; off < n && e == cudaSuccess; off += round) {
     const size_t cnt = n - off < round ? n - off : round;
     e = cudaMemsetAsync(work_count, 0, sizeof(unsigned int), st);
@@ -323,7 +328,7 @@ int region_cells_dev(const S2bIndex* ix, const uint64_t* ids_dev, size_t n, uint
     const uint64_t* items = work;
     if (hard >= kRegionSortMin) {
       if (!sorted) {
-        e = cudaMallocAsync(&sort_tmp, sort_bytes + 8 * round + 256, st);
+        e = cudaMallocAsync(&sort_tmp, sort_bytes + 8 * slots_cap + 256, st);
         if (e != cudaSuccess) break;
         sorted = (uint64_t*)((char*)sort_tmp + ((sort_bytes + 255) / 256) * 256);
       }

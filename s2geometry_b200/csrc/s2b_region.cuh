@@ -281,6 +281,11 @@ S2B_HD int locate_target(const FlatIndexView& ix, uint64_t target, int32_t* at) 
   const uint32_t C = ix.num_cells;
   const uint64_t tmin = cellid_range_min(target), tmax = cellid_range_max(target);
   uint32_t lo = 0, hi = C;
+  if (ix.id_first) {   // lower_bound(tmin) lies inside the bucket of tmin: cells before it are smaller, cells after it larger
+    uint64_t b = tmin >> ix.id_shift;
+    if (b >= ix.id_buckets) b = ix.id_buckets - 1;             // invalid ids beyond face 5
+    lo = ix.id_first[b]; hi = ix.id_first[b + 1];
+  }
   while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (ix.cell_ids[mid] < tmin) lo = mid + 1; else hi = mid; }
   if (lo < C) {
     const uint64_t id = ix.cell_ids[lo];

@@ -34,6 +34,28 @@ struct U32Slots {   // like WarpSlots, for a list of point indices (sentinel 0xF
   }
 };
 
+// The same for 64-bit work items (sentinel: all ones).
+struct U64Slots {
+  uint32_t next = 0, end = 0;
+  __device__ __forceinline__ void append(bool want, unsigned long long value, unsigned long long* list, unsigned int* counter, unsigned lane) {
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (!m) return;
+    const uint32_t k = (uint32_t)__popc(m);
+    if (next + k > end) {
+      for (uint32_t s = next + lane; s < end; s += 32) list[s] = ~0ull;
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(counter, kSlotChunk);
+      next = __shfl_sync(0xffffffffu, base, 0);
+      end = next + kSlotChunk;
+    }
+    if (want) list[next + (uint32_t)__popc(m & ((1u << lane) - 1u))] = value;
+    next += k;
+  }
+  __device__ __forceinline__ void finish(unsigned long long* list, unsigned lane) {
+    for (uint32_t s = next + lane; s < end; s += 32) list[s] = ~0ull;
+  }
+};
+
 __device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
