@@ -331,7 +331,9 @@ int s2b_index_locate_cells_dev(const S2bIndex* index, const uint64_t* cell_ids_d
  *   s2b_region_contains_cells       S2ShapeIndexRegion::Contains(const S2Cell&)      :313-342
  * S2::RobustCrossProd (s2edge_crossings.cc:147-359) runs with all of its stages on the device: the double-precision
  * product, the x87 long double product the reference uses on x86-64 (emulated bit for bit), exact arithmetic and symbolic
- * perturbation — edges shorter than 9 * DBL_EPSILON, antipodal and exactly proportional endpoints included. */
+ * perturbation — edges shorter than 9 * DBL_EPSILON, antipodal and exactly proportional endpoints included.
+ * The _dev forms enqueue on `stream` but wait for it once per round of 2^27 targets (the number of targets that need edge
+ * tests sizes the sort that precedes them), so they return with the results complete. */
 int s2b_region_may_intersect_cells(const S2bIndex* index, const uint64_t* cell_ids, size_t n, uint8_t* out);
 int s2b_region_may_intersect_cells_dev(const S2bIndex* index, const uint64_t* cell_ids_dev, size_t n, uint8_t* out_dev, void* stream);
 int s2b_region_contains_cells(const S2bIndex* index, const uint64_t* cell_ids, size_t n, uint8_t* out);
